@@ -1,0 +1,121 @@
+"""Pin the C oracle (oracle/prms_oracle.c) to outputs of the reference itself.
+
+The golden files were produced by oracle/gen_golden.py from the UNMODIFIED
+reference (numpy calc_method) in the build container; the reference ships no
+golden vectors for this path.  CPU only.
+"""
+import numpy as np
+import pytest
+
+import parity
+import prms_oracle as po
+import scenarios
+
+
+def _run_oracle(p, f, start, nd=731):
+    o = po.Oracle(p, start=start)
+    st = o.soltabs()
+    res, viol = o.run(f["prcp"][:nd], f["tmax"][:nd], f["tmin"][:nd], po.HRU_VARS, po.SEG_VARS)
+    o.close()
+    return st, res, viol
+
+
+@pytest.fixture(scope="module")
+def drb_run(drb):
+    return _run_oracle(*drb)
+
+
+@pytest.fixture(scope="module")
+def drbx_run(drbx):
+    return _run_oracle(*drbx)
+
+
+def test_calendar_matches_reference_time_utils():
+    # utils/time_utils.py:25-68 semantics on known dates
+    cal = po.calendar("1979-01-01", 731)
+    assert tuple(cal[0]) == (1, 93, 1, 1)        # 1 Jan 1979: dowy counts from 1 Oct 1978
+    assert tuple(cal[273]) == (274, 1, 10, 1)    # 1 Oct 1979 starts water year
+    assert tuple(cal[365 + 59]) == (60, 152, 2, 29)  # 29 Feb 1980 (leap)
+    assert tuple(cal[730]) == (366, 92, 12, 31)
+
+
+def test_soltab_matches_reference(drb_run):
+    st, _, _ = drb_run
+    g = np.load(scenarios.GOLDEN / "drb_golden.npz")
+    hs = g["hru_sample"]
+    for k in ("soltab_potsw", "soltab_horad_potsw", "soltab_sunhrs"):
+        # autotest/test_prms_solar_geom.py:14 uses 1e-10
+        np.testing.assert_allclose(st[k][:, hs], g[k], rtol=1e-9, atol=1e-10)
+
+
+def test_drb_known_answers(drb_run):
+    """Last-day sums recorded from the reference run."""
+    _, res, viol = drb_run
+    assert res["seg_outflow"][-1].sum() == pytest.approx(214752.70363439058, rel=1e-10)
+    assert res["pkwater_equiv"][-1].sum() == pytest.approx(186.00889550764475, rel=1e-10)
+    assert viol.sum() == 0  # all six budgets close every day, as in the reference
+
+
+@pytest.mark.parametrize("scen", ["drb", "drbx"])
+def test_full_chain_matches_reference(scen, drb_run, drbx_run):
+    _, res, _ = drb_run if scen == "drb" else drbx_run
+    g = np.load(scenarios.GOLDEN / f"{scen}_golden.npz")
+    hs, ss, snap = g["hru_sample"], g["seg_sample"], g["snap_days"]
+    # (1) every day for the HRU sample
+    got = {k: res[k][:, hs] for k in po.HRU_VARS}
+    ref = {k: g["ts_" + k] for k in po.HRU_VARS}
+    rep = parity.compare_columns(got, ref, po.HRU_VARS, got["pkwater_equiv"], ref["pkwater_equiv"])
+    assert rep["mismatches"] == []
+    # (2) every HRU on the snapshot days, skipping HRUs past a ghost-pack tie
+    got = {k: res[k][snap, :] for k in po.HRU_VARS}
+    ref = {k: g["snap_" + k] for k in po.HRU_VARS}
+    rep2 = parity.compare_columns(got, ref, po.HRU_VARS, rtol=1e-9, atol=1e-10)
+    nbad = len(rep2["mismatches"])
+    if scen == "drb":
+        assert rep["ties"] == [] and nbad == 0
+        parity.assert_segments_close({k: res[k][:, ss] for k in po.SEG_VARS},
+                                     {k: g["ts_" + k] for k in po.SEG_VARS}, po.SEG_VARS)
+        for k in po.INT_VARS + po.BOOL_VARS:
+            assert (res[k][:, hs] == g["ts_" + k]).all(), k
+    else:
+        # 4 of 765 HRUs leave tolerance in drbx; each was traced to a ghost
+        # pack (see parity.py); flow routed below those HRUs then agrees to ~1e-5 relative only
+        assert nbad <= 4, rep2["mismatches"]
+        for k in ("seg_outflow", "seg_upstream_inflow"):
+            np.testing.assert_allclose(res[k][:, ss], g["ts_" + k], rtol=1e-4)
+    # (3) checksum of checksums: per-day domain sums of every variable
+    for k in po.HRU_VARS:
+        s = res[k].sum(axis=1)
+        tol = 1e-9 if scen == "drb" else 1e-3
+        np.testing.assert_allclose(s, g["sum_" + k], rtol=tol, atol=1e-7, equal_nan=True, err_msg=k)
+
+
+def test_channel_alone_matches_full_chain(drb, drb_run):
+    """orc_run_channel fed the chain's own lateral inflow reproduces the
+    chain's routing (the reference can run PRMSChannel alone the same way,
+    examples/05_parameter_ensemble.ipynb cell 20)."""
+    p, f, start = drb
+    _, res, _ = drb_run
+    o = po.Oracle(p, start=start)
+    out = o.run_channel(res["seg_lateral_inflow"][:60])
+    for k in po.SEG_VARS:
+        np.testing.assert_array_equal(out[k], res[k][:60], err_msg=k)
+
+
+def test_hru_columns_are_independent(drb):
+    """Tiling recipe: every tile of a tiled domain with
+    identical forcing reproduces the single domain bit for bit."""
+    p, f, start = drb
+    pt, ft = scenarios.tile(p, f, 2, temp_shift=False)
+    nd = 40
+    a = po.Oracle(p, start=start)
+    ra, _ = a.run(f["prcp"][:nd], f["tmax"][:nd], f["tmin"][:nd], po.HRU_VARS, po.SEG_VARS)
+    b = po.Oracle(pt, start=start)
+    rb, _ = b.run(ft["prcp"][:nd], ft["tmax"][:nd], ft["tmin"][:nd], po.HRU_VARS, po.SEG_VARS)
+    nh, ns = a.nhru, a.nseg
+    for k in po.HRU_VARS:
+        np.testing.assert_array_equal(rb[k][:, :nh], ra[k], err_msg=k)
+        np.testing.assert_array_equal(rb[k][:, nh:], ra[k], err_msg=k)
+    for k in po.SEG_VARS:
+        np.testing.assert_array_equal(rb[k][:, :ns], ra[k], err_msg=k)
+        np.testing.assert_array_equal(rb[k][:, ns:], ra[k], err_msg=k)
