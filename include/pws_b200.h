@@ -1,0 +1,125 @@
+/*
+ * pws_b200.h -- C ABI of libpwsb200.so, the B200 (sm_100a) implementation of
+ * pywatershed's per-timestep PRMS/NHM process chain.
+ *
+ * The reference has no FFI for this path: it is pure Python, each process a
+ * class whose calculate() runs a scalar loop over HRUs
+ * (pywatershed/base/process.py:407-422 -> e.g.
+ * pywatershed/hydrology/prms_snow.py:623).  The entry points below are what a
+ * ctypes binding of that path needs; each cites the reference interface it
+ * stands in for.  Paths are relative to /root/reference/pywatershed/.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every function
+ * returns 0 on success and a non-zero code on failure, after which
+ * pws_last_error(h) describes it (the Python wrapper raises the exception
+ * class the reference would: ValueError / RuntimeError).  A handle belongs to
+ * one host thread and one GPU.  Arrays named d_* are DEVICE pointers (e.g.
+ * torch.Tensor.data_ptr()), h_* are HOST pointers (pinned for real overlap).
+ *
+ * There is no CPU fallback: pws_create fails when no CUDA device is present.
+ */
+#ifndef PWS_B200_H
+#define PWS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pws_handle pws_handle;
+
+/* ---- registry (names follow static/metadata/variables.yaml) ------------ */
+int pws_n_hru_vars(void);               /* 143 public [nhru] variables       */
+const char *pws_hru_var_name(int idx);
+int pws_hru_var_kind(int idx);          /* 0 float64, 1 int32, 2 bool        */
+int pws_n_seg_vars(void);               /* 5 public [nsegment] variables     */
+const char *pws_seg_var_name(int idx);
+int pws_n_hru_state(void);              /* prognostic state, restart-ready   */
+const char *pws_hru_state_name(int idx);
+int pws_abi_version(void);
+
+/* ---- lifetime ---------------------------------------------------------- */
+/* Process.__init__(control, discretization, parameters): base/process.py:91 */
+int pws_create(pws_handle **out, int device, int64_t nhru, int64_t nsegment,
+               int ndeplval);
+int pws_destroy(pws_handle *h);
+const char *pws_last_error(pws_handle *h); /* h may be NULL: last create error */
+
+/* ---- parameters: Process._set_params, base/process.py:219-241 -----------
+ * name = the reference's parameter name; n = nhru | 12*nhru | nsegment |
+ * ndeplval | 1 (1 broadcasts, as prms_snow.py:302-320 does for den_init...). */
+int pws_set_param_f64(pws_handle *h, const char *name, const double *h_v, int64_t n);
+int pws_set_param_i32(pws_handle *h, const char *name, const int32_t *h_v, int64_t n);
+/* options: "dprst_flag" (Process._set_options, base/process.py:339-360),
+ * "temp_units", "start_month", "start_doy" (control.start_month/start_doy,
+ * prms_atmosphere.py:695-696), "adjust_parameters" (prms_soilzone.py:100),
+ * "albset_rna|rnm|sna|snm" (scalar parameters, prms_snow.py:911-914),
+ * "block_days" (days per device time block of pws_run_host). */
+int pws_set_option(pws_handle *h, const char *name, double value);
+
+/* Everything the reference derives at construction: soltab tables
+ * (atmosphere/prms_solar_geometry.py:138-161), basin_init/dprst_init
+ * (hydrology/prms_runoff.py:253-389), _initialize_soilzone_data
+ * (prms_soilzone.py:261-536), snow/groundwater initial conditions
+ * (prms_snow.py:295-431, prms_groundwater.py:145-149), the transp_on start-up
+ * (prms_atmosphere.py:690-716) and _initialize_channel_data
+ * (prms_channel.py:189-342).  Resets state to the initial conditions. */
+int pws_init(pws_handle *h);
+
+/* soltab_potsw (0), soltab_horad_potsw (1), soltab_sunhrs (2): [366][nhru] */
+int pws_get_soltab(pws_handle *h, int which, double *h_out);
+
+/* ---- output selection: control.options["netcdf_output_var_names"],
+ * base/process.py:463-569.  Indices into the registries above; outputs of a
+ * run are laid out [day][selected var][unit] in selection order, float64
+ * variables in out_f64, int32/bool variables (as int32) in out_i32. */
+int pws_select_outputs(pws_handle *h, int n_hru_vars, const int32_t *hru_var_idx,
+                       int n_seg_vars, const int32_t *seg_var_idx);
+int pws_n_selected(pws_handle *h, int *n_f64, int *n_i32, int *n_seg);
+
+/* ---- the time loop: Model.run / advance / calculate,
+ * base/model.py:678-743.  cal = [ndays][4] int32 (doy, dowy, month,
+ * day-of-month) = control.current_doy/current_dowy/current_month
+ * (base/control.py:439-453, utils/time_utils.py:25-68).
+ * budget_viol [ndays][6] int32 (may be NULL): number of units whose
+ * Budget.calculate closure fails (base/budget.py:336-416) for canopy, snow,
+ * runoff, soilzone, groundwater (unit basis) and channel (global basis). */
+
+/* forcings and outputs already resident in HBM; asynchronous (pws_sync) */
+int pws_run_device(pws_handle *h, int ndays, const int32_t *h_cal,
+                   const double *d_prcp, const double *d_tmax, const double *d_tmin,
+                   double *d_out_f64, int32_t *d_out_i32, double *d_seg_out,
+                   int32_t *h_budget_viol);
+
+/* forcings and outputs in host memory: staged through pinned-memory rings in
+ * time blocks, H2D / compute / D2H overlapped on three streams; returns when
+ * the last block has been drained */
+int pws_run_host(pws_handle *h, int ndays, const int32_t *h_cal,
+                 const double *h_prcp, const double *h_tmax, const double *h_tmin,
+                 double *h_out_f64, int32_t *h_out_i32, double *h_seg_out,
+                 int32_t *h_budget_viol);
+
+/* PRMSChannel alone (examples/05_parameter_ensemble.ipynb cell 20):
+ * d_seg_lateral_inflow [ndays][nsegment] */
+int pws_run_channel_device(pws_handle *h, int ndays, const double *d_seg_lateral_inflow,
+                           double *d_seg_out);
+
+int pws_sync(pws_handle *h);
+
+/* ---- state: get_restart_variables (prms_snow.py:269-293 etc.) ---------- */
+int pws_get_state(pws_handle *h, const char *name, double *h_out); /* [nhru] */
+int pws_set_state(pws_handle *h, const char *name, const double *h_in);
+
+/* ---- instrumentation ---------------------------------------------------- */
+/* kernels launched since create, and device milliseconds (CUDA events on the
+ * compute stream) spent in the hru column kernel / channel kernels during
+ * the last pws_run_* call (valid after pws_sync) */
+int64_t pws_launch_count(pws_handle *h);
+int pws_last_timing(pws_handle *h, double *ms_column, double *ms_channel);
+int pws_column_kernel_info(pws_handle *h, int *regs, int *local_bytes, int *max_blocks_per_sm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,166 @@
+// column_host.cpp -- TEST-ONLY host build of the device physics in
+// pywatershed_b200/csrc/hru_column.cuh (the same source the CUDA kernels
+// inline), so its logic can be checked against the oracle on a machine
+// without a GPU.  Never part of libpwsb200.so; built into tests/_build/ by
+// tests/test_column_host.py.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../pywatershed_b200/csrc/hru_column.cuh"
+
+using namespace pws;
+
+namespace {
+struct Shim {
+  int64_t nhru;
+  int ndepl;
+  std::map<std::string, std::vector<double>> pf;
+  std::map<std::string, std::vector<int32_t>> pi;
+  std::map<std::string, double> opt;
+  std::vector<double> derived, state, soltab[3], snarea, allsnow_c;
+  HruParams P{};
+  HruDerivedMut D{};
+};
+
+struct HostSink {
+  double* out;  // [PWS_N_HRU_VARS][nhru] for the current day, at this HRU
+  int64_t nhru;
+  int* pv;
+  int err = 0;
+  void f(int var, double v) { out[(int64_t)var * nhru] = v; }
+  void i(int var, int v) { out[(int64_t)var * nhru] = (double)v; }
+  void viol(int proc, bool open) { if (open && pv) pv[proc]++; }
+  void lateral(double) {}
+  void error(int c) { err |= c; }
+};
+}  // namespace
+
+extern "C" {
+void* shim_create(int64_t nhru, int ndepl) {
+  Shim* s = new Shim();
+  s->nhru = nhru;
+  s->ndepl = ndepl;
+  return s;
+}
+void shim_destroy(void* p) { delete (Shim*)p; }
+void shim_set_f64(void* p, const char* name, const double* v, int64_t n) {
+  ((Shim*)p)->pf[name].assign(v, v + n);
+}
+void shim_set_i32(void* p, const char* name, const int32_t* v, int64_t n) {
+  ((Shim*)p)->pi[name].assign(v, v + n);
+}
+void shim_set_opt(void* p, const char* name, double v) { ((Shim*)p)->opt[name] = v; }
+
+int shim_init(void* p) {
+  Shim* s = (Shim*)p;
+  const int64_t n = s->nhru;
+  HruParams& P = s->P;
+  P.nhru = n;
+  P.stride = n;
+  auto bc = [&](std::vector<double>& v, int64_t len) {
+    if ((int64_t)v.size() == 1) v.assign(len, v[0]);
+  };
+#define X(nm) bc(s->pf[#nm], n); if ((int64_t)s->pf[#nm].size() != n) return -1; P.nm = s->pf[#nm].data();
+  PWS_HRU_F64_PARAMS(X)
+#undef X
+#define X(nm) if ((int64_t)s->pf[#nm].size() != 12 * n) return -2; P.nm = s->pf[#nm].data();
+  PWS_MON_F64_PARAMS(X)
+#undef X
+#define X(nm) if ((int64_t)s->pi[#nm].size() != n) return -3; P.nm = s->pi[#nm].data();
+  PWS_HRU_I32_PARAMS(X)
+#undef X
+#define X(nm) if ((int64_t)s->pi[#nm].size() != 12 * n) return -4; P.nm = s->pi[#nm].data();
+  PWS_MON_I32_PARAMS(X)
+#undef X
+  int nd = 0;
+#define X(nm) ++nd;
+  PWS_HRU_F64_DERIVED(X)
+#undef X
+  s->derived.assign((size_t)nd * n, 0.0);
+  s->allsnow_c.assign((size_t)12 * n, 0.0);
+  int k = 0;
+#define X(nm) s->D.nm = s->derived.data() + (size_t)(k++) * n; P.nm = s->D.nm;
+  PWS_HRU_F64_DERIVED(X)
+#undef X
+  s->D.tmax_allsnow_c = s->allsnow_c.data();
+  P.tmax_allsnow_c = s->allsnow_c.data();
+  s->snarea = s->pf["snarea_curve"];
+  P.snarea_curve = s->snarea.data();
+  P.albset_rna = s->opt["albset_rna"]; P.albset_rnm = s->opt["albset_rnm"];
+  P.albset_sna = s->opt["albset_sna"]; P.albset_snm = s->opt["albset_snm"];
+  P.dprst_flag = (int)s->opt["dprst_flag"];
+  P.temp_units = (int)s->opt["temp_units"];
+  for (auto& t : s->soltab) t.assign((size_t)366 * n, 0.0);
+  const double rad_day = (2 * kPi) / 365.242;
+  for (int j = 0; j < 366; ++j) {
+    const double jd = (double)(j + 1);
+    const double obliquity = 1 - (0.01671 * std::cos((jd - 3) * rad_day));
+    const double yy = (jd - 1) * rad_day, yy2 = yy * 2, yy3 = yy * 3;
+    const double decl = 0.006918 - 0.399912 * std::cos(yy) + 0.070257 * std::sin(yy) -
+                        0.006758 * std::cos(yy2) + 0.000907 * std::sin(yy2) -
+                        0.002697 * std::cos(yy3) + 0.00148 * std::sin(yy3);
+    const double r1 = (60.0 * 2.0) / (obliquity * obliquity);
+    for (int64_t i = 0; i < n; ++i) {
+      double solt, sunh;
+      sol_one(0.0, 0.0, P.hru_lat[i], decl, r1, solt, sunh);
+      s->soltab[1][(size_t)j * n + i] = solt;
+      sol_one(P.hru_slope[i], P.hru_aspect[i], P.hru_lat[i], decl, r1, solt, sunh);
+      s->soltab[0][(size_t)j * n + i] = solt;
+      s->soltab[2][(size_t)j * n + i] = sunh;
+    }
+  }
+  P.soltab_potsw = s->soltab[0].data();
+  P.soltab_horad_potsw = s->soltab[1].data();
+  s->state.assign((size_t)PWS_N_HRU_STATE * n, 0.0);
+  int err = 0;
+  for (int64_t i = 0; i < n; ++i)
+    err |= hru_init_one(P, s->D, s->state.data(), i, (int)s->opt["start_month"],
+                        (int)s->opt["start_doy"], 1);
+  return err;
+}
+
+const double* shim_soltab(void* p, int which) { return ((Shim*)p)->soltab[which].data(); }
+
+// out [ndays][PWS_N_HRU_VARS][nhru] float64, viol [ndays][6]
+int shim_run(void* p, int ndays, const int32_t* cal, const double* prcp, const double* tmax,
+             const double* tmin, double* out, int32_t* viol) {
+  Shim* sh = (Shim*)p;
+  const int64_t n = sh->nhru;
+  int err = 0;
+  for (int64_t i = 0; i < n; ++i) {  // thread = HRU, state "in registers" over the block
+    HruState s;
+#define LD_F(name) s.name = sh->state[(size_t)ST_##name * n + i];
+#define LD_I(name) s.name = (int)sh->state[(size_t)ST_##name * n + i];
+#define X(name, kind) LD_##kind(name)
+    PWS_HRU_STATE(X)
+#undef X
+    for (int d = 0; d < ndays; ++d) {
+      DayIn in;
+      in.doy = cal[4 * d]; in.dowy = cal[4 * d + 1]; in.month = cal[4 * d + 2]; in.dom = cal[4 * d + 3];
+      in.prcp = prcp[(size_t)d * n + i]; in.tmax = tmax[(size_t)d * n + i]; in.tmin = tmin[(size_t)d * n + i];
+      in.potsw = sh->soltab[0][(size_t)(in.doy - 1) * n + i];
+      in.horad = sh->soltab[1][(size_t)(in.doy - 1) * n + i];
+      HostSink sink{out + (size_t)d * PWS_N_HRU_VARS * n + i, n, viol ? viol + 6 * d : nullptr};
+      column_day(sh->P, i, s, in, sink);
+      err |= sink.err;
+    }
+#define X(name, kind) sh->state[(size_t)ST_##name * n + i] = (double)s.name;
+    PWS_HRU_STATE(X)
+#undef X
+  }
+  return err;
+}
+const char* shim_var_name(int i) {
+  static const char* nm[] = {
+#define X(n, kind, init) #n,
+      PWS_HRU_VARS(X)
+#undef X
+  };
+  return nm[i];
+}
+int shim_n_vars() { return PWS_N_HRU_VARS; }
+}
