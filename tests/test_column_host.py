@@ -1,0 +1,75 @@
+"""The device physics (pywatershed_b200/csrc/hru_column.cuh) compiled for the
+HOST by tests/host_shim and run against the oracle: same inputs, every public
+HRU variable of every day bit-identical.  This is a logic check that runs
+without a GPU; the shipped library contains no such host path, and the GPU
+parity proper is tests/test_gpu_parity.py."""
+import ctypes as C
+import pathlib as pl
+import subprocess
+
+import numpy as np
+import pytest
+
+import prms_oracle as po
+import scenarios
+
+ROOT = pl.Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def shim():
+    out = ROOT / "tests" / "_build" / "libcolumn_host.so"
+    out.parent.mkdir(exist_ok=True)
+    src = ROOT / "tests" / "host_shim" / "column_host.cpp"
+    subprocess.run(["g++", "-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-shared",
+                    "-o", str(out), str(src)], check=True)
+    L = C.CDLL(str(out))
+    L.shim_create.restype = C.c_void_p
+    L.shim_create.argtypes = [C.c_int64, C.c_int]
+    L.shim_set_f64.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]
+    L.shim_set_i32.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]
+    L.shim_set_opt.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+    L.shim_init.argtypes = [C.c_void_p]
+    L.shim_run.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6
+    L.shim_var_name.restype = C.c_char_p
+    L.shim_destroy.argtypes = [C.c_void_p]
+    return L
+
+
+def _run(L, P, F, start, nd):
+    n = P["hru_area"].shape[0]
+    h = L.shim_create(n, P["snarea_curve"].size)
+    for k in po.HRU_F8 + po.MON_F8 + ["snarea_curve"]:
+        a = np.ascontiguousarray(np.asarray(P[k], dtype=np.float64).ravel())
+        L.shim_set_f64(h, k.encode(), a.ctypes.data, a.size)
+    for k in po.HRU_I4 + po.MON_I4:
+        a = np.ascontiguousarray(np.asarray(P[k]).ravel().astype(np.int32))
+        L.shim_set_i32(h, k.encode(), a.ctypes.data, a.size)
+    for k in po.SCALAR_F8:
+        L.shim_set_opt(h, k.encode(), float(np.ravel(P[k])[0]))
+    cal = po.calendar(start, nd)
+    L.shim_set_opt(h, b"dprst_flag", 1.0)
+    L.shim_set_opt(h, b"temp_units", float(np.ravel(P["temp_units"])[0]))
+    L.shim_set_opt(h, b"start_month", float(cal[0, 2]))
+    L.shim_set_opt(h, b"start_doy", float(cal[0, 0]))
+    assert L.shim_init(h) == 0
+    names = [L.shim_var_name(i).decode() for i in range(L.shim_n_vars())]
+    out = np.empty((nd, len(names), n))
+    viol = np.zeros((nd, 6), np.int32)
+    pr, tx, tn = [np.ascontiguousarray(F[k][:nd]) for k in ("prcp", "tmax", "tmin")]
+    assert L.shim_run(h, nd, cal.ctypes.data, pr.ctypes.data, tx.ctypes.data, tn.ctypes.data,
+                      out.ctypes.data, viol.ctypes.data) == 0
+    L.shim_destroy(h)
+    return {k: out[:, i, :] for i, k in enumerate(names)}, viol
+
+
+@pytest.mark.parametrize("scen", ["drb", "drbx"])
+def test_device_physics_bit_identical_to_oracle(shim, scen, drb, drbx):
+    P, F, start = drb if scen == "drb" else drbx
+    nd = 731
+    got, viol = _run(shim, P, F, start, nd)
+    o = po.Oracle(P, start=start)
+    ref, oviol = o.run(F["prcp"][:nd], F["tmax"][:nd], F["tmin"][:nd], po.HRU_VARS, ())
+    for k in po.HRU_VARS:
+        np.testing.assert_array_equal(got[k], ref[k], err_msg=k)
+    np.testing.assert_array_equal(viol[:, :5], oviol[:, :5])
