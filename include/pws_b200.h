@@ -55,7 +55,9 @@ int pws_set_param_i32(pws_handle *h, const char *name, const int32_t *h_v, int64
  * "temp_units", "start_month", "start_doy" (control.start_month/start_doy,
  * prms_atmosphere.py:695-696), "adjust_parameters" (prms_soilzone.py:100),
  * "albset_rna|rnm|sna|snm" (scalar parameters, prms_snow.py:911-914),
- * "block_days" (days per device time block of pws_run_host). */
+ * "block_days" (days per device time block of pws_run_host),
+ * "soltab_device" (1: build the PRMSSolarGeometry tables with the CUDA kernel
+ * k_soltab; 0, default: with the host libm the reference's tables come from). */
 int pws_set_option(pws_handle *h, const char *name, double value);
 
 /* Everything the reference derives at construction: soltab tables
@@ -118,6 +120,15 @@ int pws_set_state(pws_handle *h, const char *name, const double *h_in);
 int64_t pws_launch_count(pws_handle *h);
 int pws_last_timing(pws_handle *h, double *ms_column, double *ms_channel);
 int pws_column_kernel_info(pws_handle *h, int *regs, int *local_bytes, int *max_blocks_per_sm);
+/* CUDA events on the library's compute stream (torch.cuda.Event only sees
+ * torch's stream): mark which = 0 (start) / 1 (stop); elapsed after pws_sync */
+int pws_timer_mark(pws_handle *h, int which);
+int pws_timer_elapsed_ms(pws_handle *h, double *ms);
+/* number of hru-column launches and channel launches in the last run */
+int pws_last_launches(pws_handle *h, int *n_column, int *n_channel);
+/* reset prognostic state to the initial conditions without rebuilding the
+ * static tables (what re-instantiating the reference's processes would do) */
+int pws_reset_state(pws_handle *h);
 
 #ifdef __cplusplus
 }

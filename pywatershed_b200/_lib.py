@@ -58,6 +58,10 @@ def lib():
         "pws_launch_count": (i64, [vp]),
         "pws_last_timing": (i32, [vp, C.POINTER(dbl), C.POINTER(dbl)]),
         "pws_column_kernel_info": (i32, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
+        "pws_timer_mark": (i32, [vp, i32]),
+        "pws_timer_elapsed_ms": (i32, [vp, C.POINTER(dbl)]),
+        "pws_last_launches": (i32, [vp, C.POINTER(i32), C.POINTER(i32)]),
+        "pws_reset_state": (i32, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError if the ABI lost a symbol
@@ -75,4 +79,5 @@ EXPORTED_SYMBOLS = (
     "pws_select_outputs", "pws_n_selected", "pws_run_device", "pws_run_host",
     "pws_run_channel_device", "pws_sync", "pws_get_state", "pws_set_state",
     "pws_launch_count", "pws_last_timing", "pws_column_kernel_info",
+    "pws_timer_mark", "pws_timer_elapsed_ms", "pws_last_launches", "pws_reset_state",
 )

@@ -29,10 +29,12 @@
 
 #if defined(__CUDACC__)
 #define PWS_DEV __device__ __forceinline__
+#define PWS_HD __host__ __device__ __forceinline__
 #define PWS_LD(p) __ldg(p)
 #define PWS_TABLE static __device__ const
 #else
 #define PWS_DEV static inline
+#define PWS_HD static inline
 #define PWS_LD(p) (*(p))
 #define PWS_TABLE static const
 #endif
@@ -181,6 +183,18 @@ PWS_DEV void calc_caloss(HruState& s, double cal) {
     s.pkwater_equiv = 0.0;
 }
 
+// x**4 rounded once: x*x and (x*x)*(x*x) are split exactly with fma, so the
+// result is the correctly rounded fourth power -- what a < 1 ulp host pow(x, 4.0)
+// returns (prms_snow.py:2768 evaluates `(temp + 273.16) ** 4.0` through libm),
+// where CUDA's pow() may be 2 ulp off.
+PWS_DEV double pow4(double x) {
+  const double t = x * x;
+  const double e = fma(x, x, -t);
+  const double p = t * t;
+  const double pe = fma(t, t, -p);
+  return p + (pe + 2.0 * t * e);
+}
+
 // prms_snow.py:2734-3093; one half-day energy balance, returns cal
 PWS_DEV double calc_snowbal(HruState& s, double& snowmelt, int niteda, double cec,
                             double cst, double esv, double sw, double temp,
@@ -188,7 +202,7 @@ PWS_DEV double calc_snowbal(HruState& s, double& snowmelt, int niteda, double ce
                             double denmaxinv, double emis_noppt,
                             double freeh2o_cap, double hru_ppt, int tstorm_mo) {
   const double tk = temp + 273.16;
-  const double air = 0.585e-7 * pow(tk, 4.0);
+  const double air = 0.585e-7 * pow4(tk);
   double emis = esv;
   double ts, sno;
   if (temp < 0.0) {
@@ -325,41 +339,63 @@ PWS_DEV bool compute_interflow(double coef_lin, double coef_sq, double ssres_in,
 constexpr double kPi = 3.141592653589793;
 
 // ---------------------------------------------------------------- soltab
-// prms_solar_geometry.py:319-358
-PWS_DEV double sol_compute_t(double lat, double decl) {
-  const double tx = (-1 * tan(lat)) * tan(decl);
+// PRMSSolarGeometry (atmosphere/prms_solar_geometry.py:176-408), split into the
+// per-HRU part (slope/aspect/latitude geometry) and the per-(doy, HRU) part.
+// Host+device: pws_init evaluates it with the host libm by default, because the
+// reference's own tables come from a host libm and PRMSSnow's melt-out is
+// sensitive to their last bit (see tests/parity.py); k_soltab is the device
+// version of the same code.
+struct SolHru {
+  double sl, x0, x1, x2, sin_x1, cos_x1, tan_x1, sin_x0, cos_x0, tan_x0;
+};
+
+PWS_HD SolHru sol_hru(double slope, double aspect, double lat) {
+  const double deg2rad = kPi / 180.0;
+  SolHru h;
+  h.sl = atan(slope);
+  const double sl_sin = sin(h.sl), sl_cos = cos(h.sl);
+  const double aspects_rad = aspect * deg2rad;
+  const double aspects_cos = cos(aspects_rad);
+  h.x0 = lat * deg2rad;
+  h.cos_x0 = cos(h.x0);
+  h.sin_x0 = sin(h.x0);
+  // x1: latitude of the equivalent slope (Lee 1963 eq. 13), :207
+  h.x1 = asin(sl_cos * h.sin_x0 + sl_sin * h.cos_x0 * aspects_cos);
+  double d1 = sl_cos * h.cos_x0 - sl_sin * h.sin_x0 * aspects_cos;  // :210-211
+  if (fabs(d1) < PWS_DNEARZERO) d1 = PWS_DNEARZERO;
+  h.x2 = atan(sl_sin * sin(aspects_rad) / d1);  // :216
+  if (d1 < 0.0) h.x2 = h.x2 + kPi;
+  h.sin_x1 = sin(h.x1);
+  h.cos_x1 = cos(h.x1);
+  h.tan_x1 = tan(h.x1);
+  h.tan_x0 = tan(h.x0);
+  return h;
+}
+
+// compute_t :319-358 with tan(lat), tan(decl) hoisted
+PWS_HD double sol_compute_t(double tan_lat, double tan_decl) {
+  const double tx = (-1 * tan_lat) * tan_decl;
   if (tx < -1.0) return kPi;
   if (tx > 1.0) return 0.0;
   return acos(tx);
 }
-// prms_solar_geometry.py:361-408
-PWS_DEV double sol_func3(double v, double w, double x, double y,
-                                            double r1, double decl) {
+
+// func3 :361-408 with sin/cos of the declination and of w hoisted
+PWS_HD double sol_func3(double v, double sin_w, double cos_w, double x, double y, double r1,
+                        double sin_d, double cos_d) {
   const double pi_12 = 12 / kPi;
-  return r1 * pi_12 *
-         (sin(decl) * sin(w) * (x - y) + cos(decl) * cos(w) * (sin(x + v) - sin(y + v)));
+  return r1 * pi_12 * (sin_d * sin_w * (x - y) + cos_d * cos_w * (sin(x + v) - sin(y + v)));
 }
 
-// prms_solar_geometry.py:176-316 for one (doy, hru); t3/t7 and t2/t6 alias in
-// the reference (:255-272), which is why the clamped values feed t6'/t7'.
-PWS_DEV void sol_one(double slope, double aspect, double lat, double decl, double r1,
-                     double& solt, double& sunh) {
-  const double two_pi = 2 * kPi, pi_12 = 12 / kPi, deg2rad = kPi / 180.0;
-  const double sl = atan(slope);
-  const double sl_sin = sin(sl), sl_cos = cos(sl);
-  const double aspects_rad = aspect * deg2rad;
-  const double aspects_cos = cos(aspects_rad);
-  const double x0 = lat * deg2rad;
-  const double x0_cos = cos(x0);
-  const double x1 = asin(sl_cos * sin(x0) + sl_sin * x0_cos * aspects_cos);
-  double d1 = sl_cos * x0_cos - sl_sin * sin(x0) * aspects_cos;
-  if (fabs(d1) < PWS_DNEARZERO) d1 = PWS_DNEARZERO;
-  double x2 = atan(sl_sin * sin(aspects_rad) / d1);
-  if (d1 < 0.0) x2 = x2 + kPi;
-  double tt = sol_compute_t(x1, decl);
-  double t6 = (-1 * tt) - x2;
-  double t7 = tt - x2;
-  tt = sol_compute_t(x0, decl);
+// One (doy, HRU) of compute_soltab :230-316.  t3/t7 and t2/t6 are ALIASES in
+// the reference (:255-272), so the clamped values feed t6' and t7'.
+PWS_HD void sol_day(const SolHru& h, double sin_d, double cos_d, double tan_d, double r1,
+                    double& solt, double& sunh) {
+  const double two_pi = 2 * kPi, pi_12 = 12 / kPi;
+  double tt = sol_compute_t(h.tan_x1, tan_d);
+  double t6 = (-1 * tt) - h.x2;
+  double t7 = tt - h.x2;
+  tt = sol_compute_t(h.tan_x0, tan_d);
   const double t0 = -1 * tt, t1 = tt;
   if (t7 > t1) t7 = t1;
   double t3 = t7;
@@ -371,24 +407,35 @@ PWS_DEV void sol_one(double slope, double aspect, double lat, double decl, doubl
     t2 = 0.0;
     t3 = 0.0;
   }
-  solt = sol_func3(x2, x1, t3, t2, r1, decl);
+  const double base = sol_func3(h.x2, h.sin_x1, h.cos_x1, t3, t2, r1, sin_d, cos_d);
+  solt = base;
   sunh = (t3 - t2) * pi_12;
   if (t7 > t0) {
-    solt = sol_func3(x2, x1, t3, t2, r1, decl) + sol_func3(x2, x1, t7, t0, r1, decl);
+    solt = base + sol_func3(h.x2, h.sin_x1, h.cos_x1, t7, t0, r1, sin_d, cos_d);
     sunh = (t3 - t2 + t7 - t0) * pi_12;
   }
   if (t6 < t1) {
-    solt = sol_func3(x2, x1, t3, t2, r1, decl) + sol_func3(x2, x1, t1, t6, r1, decl);
+    solt = base + sol_func3(h.x2, h.sin_x1, h.cos_x1, t1, t6, r1, sin_d, cos_d);
     sunh = (t3 - t2 + t1 - t6) * pi_12;
   }
-  if (fabs(sl) < PWS_DNEARZERO) {
-    solt = sol_func3(0.0, x0, t1, t0, r1, decl);
+  if (fabs(h.sl) < PWS_DNEARZERO) {
+    solt = sol_func3(0.0, h.sin_x0, h.cos_x0, t1, t0, r1, sin_d, cos_d);
     sunh = (t1 - t0) * pi_12;
   }
   if (sunh < PWS_DNEARZERO) sunh = 0.0;
   if (solt < 0.0) solt = 0.0;
 }
 
+// solar_constants.py:10-43 for julian day j+1: declination and r1
+PWS_HD void sol_constants(int j, double& decl, double& r1) {
+  const double rad_day = (2 * kPi) / 365.242;
+  const double jd = (double)(j + 1);
+  const double obliquity = 1 - (0.01671 * cos((jd - 3) * rad_day));
+  const double yy = (jd - 1) * rad_day, yy2 = yy * 2, yy3 = yy * 3;
+  decl = 0.006918 - 0.399912 * cos(yy) + 0.070257 * sin(yy) - 0.006758 * cos(yy2) +
+         0.000907 * sin(yy2) - 0.002697 * cos(yy3) + 0.00148 * sin(yy3);
+  r1 = (60.0 * 2.0) / (obliquity * obliquity);
+}
 
 struct HruDerivedMut {
 #define X(n) double* n;
@@ -415,7 +462,7 @@ PWS_DEV int hru_init_one(const HruParams& P, const HruDerivedMut& D, double* sta
   const int ht = P.hru_type[i];
   const double harea = P.hru_area[i];
   // --- atmosphere: prms_atmosphere.py:519, 690-716
-  D.hru_cossl[i] = cos(atan(P.hru_slope[i]));
+  // hru_cossl = cos(atan(hru_slope)) is filled by the caller (host libm, see pws_init)
   {
     const int beg = P.transp_beg[i], end = P.transp_end[i];
     const int motmp = start_month + 12;

@@ -19,6 +19,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pws_b200.h"
@@ -95,6 +96,7 @@ struct pws_handle {
   // options
   int dprst_flag = 1, temp_units = 0, start_month = 1, start_doy = 1, adjust_parameters = 1;
   int block_days = 0;
+  int soltab_device = 0;
   double albset[4] = {0, 0, 0, 0};
   // host copies of the parameters (set before pws_init)
   std::map<std::string, std::vector<double>> pf;
@@ -138,6 +140,8 @@ struct pws_handle {
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr},
               ev_d2h[2] = {nullptr, nullptr};
   double ms_column = 0.0, ms_channel = 0.0;
+  int n_col_launch = 0, n_ch_launch = 0;
+  std::vector<double> h_seg_inflow_init;
   bool timing_pending = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pairs_col, ev_pairs_ch;
 };
@@ -334,6 +338,7 @@ extern "C" int pws_set_option(pws_handle* h, const char* name, double value) {
   else if (!strcmp(name, "albset_sna")) h->albset[2] = value;
   else if (!strcmp(name, "albset_snm")) h->albset[3] = value;
   else if (!strcmp(name, "block_days")) { h->block_days = (int)value; return 0; }
+  else if (!strcmp(name, "soltab_device")) h->soltab_device = value != 0.0;
   else PWS_FAIL(h, "pws_set_option: unknown option '%s'", name);
   h->inited = false;
   return 0;
@@ -480,6 +485,7 @@ static int channel_build(pws_handle* h) {
   PWS_CUDA(h, up_f64(&h->d_c2, c2));
   PWS_CUDA(h, up_f64(&h->d_outflow_ts, outflow_ts));
   PWS_CUDA(h, up_f64(&h->d_seg_inflow, seg_inflow));
+  h->h_seg_inflow_init = seg_inflow;
   return 0;
 }
 
@@ -576,25 +582,63 @@ extern "C" int pws_init(pws_handle* h) {
   P.dprst_flag = h->dprst_flag;
   P.temp_units = h->temp_units;
   PWS_CUDA(h, cudaGetLastError());
-  // solar tables (solar_constants.py:10-43) on the host, soltab on the device
+  // PRMSSolarGeometry tables + hru_cossl.  Default: host libm, threaded over
+  // HRUs (init-time, ~12 libm calls per (doy, HRU)); option "soltab_device"
+  // runs k_soltab instead (same code, CUDA's libm, 1-2 ulp from the host's).
   {
-    double decl[kNdoy], r1[kNdoy];
-    const double rad_day = (2 * kPi) / 365.242;
+    double sin_d[kNdoy], cos_d[kNdoy], tan_d[kNdoy], r1[kNdoy];
     for (int j = 0; j < kNdoy; ++j) {
-      const double jd = (double)(j + 1);
-      const double obliquity = 1 - (0.01671 * std::cos((jd - 3) * rad_day));
-      const double yy = (jd - 1) * rad_day, yy2 = yy * 2, yy3 = yy * 3;
-      decl[j] = 0.006918 - 0.399912 * std::cos(yy) + 0.070257 * std::sin(yy) -
-                0.006758 * std::cos(yy2) + 0.000907 * std::sin(yy2) -
-                0.002697 * std::cos(yy3) + 0.00148 * std::sin(yy3);
-      r1[j] = (60.0 * 2.0) / (obliquity * obliquity);
+      double decl;
+      sol_constants(j, decl, r1[j]);
+      sin_d[j] = std::sin(decl);
+      cos_d[j] = std::cos(decl);
+      tan_d[j] = std::tan(decl);
     }
-    PWS_CUDA(h, cudaMemcpyToSymbol(c_solar_declination, decl, sizeof decl));
-    PWS_CUDA(h, cudaMemcpyToSymbol(c_r1, r1, sizeof r1));
-    dim3 grid((unsigned)((n + 127) / 128), kNdoy);
-    k_soltab<<<grid, 128, 0, h->s_compute>>>(n, S, P.hru_slope, P.hru_aspect, P.hru_lat,
-                                             h->d_soltab[0], h->d_soltab[1], h->d_soltab[2]);
-    h->launches++;
+    if (h->soltab_device) {
+      PWS_CUDA(h, cudaMemcpyToSymbol(c_sol_sin_d, sin_d, sizeof sin_d));
+      PWS_CUDA(h, cudaMemcpyToSymbol(c_sol_cos_d, cos_d, sizeof cos_d));
+      PWS_CUDA(h, cudaMemcpyToSymbol(c_sol_tan_d, tan_d, sizeof tan_d));
+      PWS_CUDA(h, cudaMemcpyToSymbol(c_sol_r1, r1, sizeof r1));
+      dim3 grid((unsigned)((n + 127) / 128), kNdoy);
+      k_soltab<<<grid, 128, 0, h->s_compute>>>(n, S, P.hru_slope, P.hru_aspect, P.hru_lat,
+                                               h->d_soltab[0], h->d_soltab[1], h->d_soltab[2],
+                                               h->D.hru_cossl);
+      h->launches++;
+    } else {
+      const std::vector<double>&slope = h->pf["hru_slope"], &aspect = h->pf["hru_aspect"],
+            &lat = h->pf["hru_lat"];
+      std::vector<double> tab[3], cossl((size_t)n);
+      for (auto& tb : tab) tb.assign((size_t)kNdoy * S, 0.0);
+      const int nthr = (int)std::max<int64_t>(
+          1, std::min<int64_t>(std::thread::hardware_concurrency(), (n + 255) / 256));
+      auto work = [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+          cossl[(size_t)i] = std::cos(std::atan(slope[(size_t)i]));
+          const SolHru flat = sol_hru(0.0, 0.0, lat[(size_t)i]);
+          const SolHru hs = sol_hru(slope[(size_t)i], aspect[(size_t)i], lat[(size_t)i]);
+          for (int j = 0; j < kNdoy; ++j) {
+            double solt, sunh;
+            sol_day(flat, sin_d[j], cos_d[j], tan_d[j], r1[j], solt, sunh);
+            tab[1][(size_t)j * S + i] = solt;
+            sol_day(hs, sin_d[j], cos_d[j], tan_d[j], r1[j], solt, sunh);
+            tab[0][(size_t)j * S + i] = solt;
+            tab[2][(size_t)j * S + i] = sunh;
+          }
+        }
+      };
+      std::vector<std::thread> pool;
+      const int64_t chunk = (n + nthr - 1) / nthr;
+      for (int t = 0; t < nthr; ++t) {
+        const int64_t lo = t * chunk, hi = std::min<int64_t>(n, lo + chunk);
+        if (lo < hi) pool.emplace_back(work, lo, hi);
+      }
+      for (auto& th : pool) th.join();
+      for (int k = 0; k < 3; ++k)
+        PWS_CUDA(h, cudaMemcpy(h->d_soltab[k], tab[k].data(), (size_t)kNdoy * S * sizeof(double),
+                               cudaMemcpyHostToDevice));
+      PWS_CUDA(h, cudaMemcpy(h->D.hru_cossl, cossl.data(), (size_t)n * sizeof(double),
+                             cudaMemcpyHostToDevice));
+    }
   }
   k_hru_init<<<(unsigned)((n + 127) / 128), 128, 0, h->s_compute>>>(
       P, h->D, h->d_state, h->start_month, h->start_doy, h->adjust_parameters, h->d_err);
@@ -781,6 +825,8 @@ extern "C" int pws_sync(pws_handle* h) {
   PWS_CUDA(h, cudaStreamSynchronize(h->s_d2h));
   if (!h->ev_pairs_col.empty()) {
     h->ms_column = h->ms_channel = 0.0;
+    h->n_col_launch = (int)h->ev_pairs_col.size();
+    h->n_ch_launch = (int)h->ev_pairs_ch.size() * (h->nlevels + 1);
     for (auto& pr : h->ev_pairs_col) {
       float ms = 0;
       cudaEventElapsedTime(&ms, pr.first, pr.second);
@@ -803,7 +849,6 @@ extern "C" int pws_run_device(pws_handle* h, int ndays, const int32_t* h_cal,
   if (!h->inited) PWS_FAIL(h, "pws_run_device before pws_init");
   if (ndays <= 0) return 0;
   PWS_CUDA(h, cudaSetDevice(h->device));
-  clear_timing(h);
   if (enqueue_block(h, ndays, h_cal, d_prcp, d_tmax, d_tmin, h->nhru, d_out_f64, d_out_i32,
                     d_seg_out, h_budget_viol != nullptr))
     return 1;
@@ -819,7 +864,6 @@ extern "C" int pws_run_channel_device(pws_handle* h, int ndays, const double* d_
   if (h->nseg == 0) PWS_FAIL(h, "pws_run_channel_device: no segments");
   if (ndays <= 0) return 0;
   PWS_CUDA(h, cudaSetDevice(h->device));
-  clear_timing(h);
   if (ensure_scratch(h, ndays)) return 1;
   cudaEvent_t e0 = new_event(h), e1 = new_event(h);
   cudaEventRecord(e0, h->s_compute);
@@ -953,5 +997,42 @@ extern "C" int pws_column_kernel_info(pws_handle* h, int* regs, int* local_bytes
   if (regs) *regs = at.numRegs;
   if (local_bytes) *local_bytes = (int)at.localSizeBytes;
   if (max_blocks_per_sm) *max_blocks_per_sm = nb;
+  return 0;
+}
+
+extern "C" int pws_timer_mark(pws_handle* h, int which) {
+  PWS_CUDA(h, cudaSetDevice(h->device));
+  PWS_CUDA(h, cudaEventRecord(which == 0 ? h->ev_col0 : h->ev_col1, h->s_compute));
+  return 0;
+}
+
+extern "C" int pws_timer_elapsed_ms(pws_handle* h, double* ms) {
+  float f = 0.f;
+  PWS_CUDA(h, cudaEventSynchronize(h->ev_col1));
+  PWS_CUDA(h, cudaEventElapsedTime(&f, h->ev_col0, h->ev_col1));
+  *ms = f;
+  return 0;
+}
+
+extern "C" int pws_last_launches(pws_handle* h, int* n_column, int* n_channel) {
+  if (n_column) *n_column = h->n_col_launch;
+  if (n_channel) *n_channel = h->n_ch_launch;
+  return 0;
+}
+
+extern "C" int pws_reset_state(pws_handle* h) {
+  if (!h->inited) PWS_FAIL(h, "pws_reset_state before pws_init");
+  PWS_CUDA(h, cudaSetDevice(h->device));
+  k_hru_init<<<(unsigned)((h->nhru + 127) / 128), 128, 0, h->s_compute>>>(
+      h->P, h->D, h->d_state, h->start_month, h->start_doy, h->adjust_parameters, h->d_err);
+  h->launches++;
+  if (h->nseg > 0) {
+    PWS_CUDA(h, cudaMemsetAsync(h->d_outflow_ts, 0, (size_t)h->nseg * sizeof(double), h->s_compute));
+    PWS_CUDA(h, cudaMemcpyAsync(h->d_seg_inflow, h->h_seg_inflow_init.data(),
+                                (size_t)h->nseg * sizeof(double), cudaMemcpyHostToDevice,
+                                h->s_compute));
+  }
+  PWS_CUDA(h, cudaGetLastError());
+  PWS_CUDA(h, cudaStreamSynchronize(h->s_compute));
   return 0;
 }

@@ -16,26 +16,33 @@ namespace pws {
 constexpr int kNdoy = 366;
 
 
-// solar_constants.py:10-43, filled from the host at pws_init
-__constant__ double c_solar_declination[kNdoy];
-__constant__ double c_r1[kNdoy];
+// sin / cos / tan of the solar declination and r1 per day of year
+// (solar_constants.py:10-43), filled from the host at pws_init
+__constant__ double c_sol_sin_d[kNdoy];
+__constant__ double c_sol_cos_d[kNdoy];
+__constant__ double c_sol_tan_d[kNdoy];
+__constant__ double c_sol_r1[kNdoy];
 
-// grid: (ceil(nhru/128), 366)
+// Device version of the soltab tables (option "soltab_device"): grid
+// (ceil(nhru/128), 366), one (doy, HRU) per thread.
 __global__ void __launch_bounds__(128)
 k_soltab(int64_t nhru, int64_t stride, const double* __restrict__ hru_slope,
          const double* __restrict__ hru_aspect, const double* __restrict__ hru_lat,
          double* __restrict__ potsw, double* __restrict__ horad,
-         double* __restrict__ sunhrs) {
+         double* __restrict__ sunhrs, double* __restrict__ hru_cossl) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y;
   if (i >= nhru) return;
   double solt, sunh;
   // horizontal surface (prms_solar_geometry.py:141-147), then slope/aspect
-  sol_one(0.0, 0.0, hru_lat[i], c_solar_declination[j], c_r1[j], solt, sunh);
+  const SolHru flat = sol_hru(0.0, 0.0, hru_lat[i]);
+  sol_day(flat, c_sol_sin_d[j], c_sol_cos_d[j], c_sol_tan_d[j], c_sol_r1[j], solt, sunh);
   horad[(int64_t)j * stride + i] = solt;
-  sol_one(hru_slope[i], hru_aspect[i], hru_lat[i], c_solar_declination[j], c_r1[j], solt, sunh);
+  const SolHru h = sol_hru(hru_slope[i], hru_aspect[i], hru_lat[i]);
+  sol_day(h, c_sol_sin_d[j], c_sol_cos_d[j], c_sol_tan_d[j], c_sol_r1[j], solt, sunh);
   potsw[(int64_t)j * stride + i] = solt;
   sunhrs[(int64_t)j * stride + i] = sunh;
+  if (j == 0) hru_cossl[i] = cos(atan(hru_slope[i]));  // prms_atmosphere.py:519
 }
 
 // ---------------------------------------------------------------- init

@@ -157,9 +157,22 @@ class Engine:
         self._opt("block_days", n)
 
     def reset(self):
-        """Back to the initial conditions (re-runs pws_init)."""
-        self._check(self.L.pws_init(self.h))
+        """Back to the initial conditions (static tables are kept)."""
+        self._check(self.L.pws_reset_state(self.h))
         self.day = 0
+
+    def timer_mark(self, which: int):
+        self._check(self.L.pws_timer_mark(self.h, which))
+
+    def timer_elapsed_ms(self) -> float:
+        ms = C.c_double()
+        self._check(self.L.pws_timer_elapsed_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def last_launches(self):
+        a, b = C.c_int(), C.c_int()
+        self.L.pws_last_launches(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
 
     def close(self):
         if getattr(self, "h", None):

@@ -95,20 +95,16 @@ int shim_init(void* p) {
   P.dprst_flag = (int)s->opt["dprst_flag"];
   P.temp_units = (int)s->opt["temp_units"];
   for (auto& t : s->soltab) t.assign((size_t)366 * n, 0.0);
-  const double rad_day = (2 * kPi) / 365.242;
+  for (int64_t i = 0; i < n; ++i) s->D.hru_cossl[i] = std::cos(std::atan(P.hru_slope[i]));
   for (int j = 0; j < 366; ++j) {
-    const double jd = (double)(j + 1);
-    const double obliquity = 1 - (0.01671 * std::cos((jd - 3) * rad_day));
-    const double yy = (jd - 1) * rad_day, yy2 = yy * 2, yy3 = yy * 3;
-    const double decl = 0.006918 - 0.399912 * std::cos(yy) + 0.070257 * std::sin(yy) -
-                        0.006758 * std::cos(yy2) + 0.000907 * std::sin(yy2) -
-                        0.002697 * std::cos(yy3) + 0.00148 * std::sin(yy3);
-    const double r1 = (60.0 * 2.0) / (obliquity * obliquity);
+    double decl, r1;
+    sol_constants(j, decl, r1);
+    const double sd = std::sin(decl), cd = std::cos(decl), td = std::tan(decl);
     for (int64_t i = 0; i < n; ++i) {
       double solt, sunh;
-      sol_one(0.0, 0.0, P.hru_lat[i], decl, r1, solt, sunh);
+      sol_day(sol_hru(0.0, 0.0, P.hru_lat[i]), sd, cd, td, r1, solt, sunh);
       s->soltab[1][(size_t)j * n + i] = solt;
-      sol_one(P.hru_slope[i], P.hru_aspect[i], P.hru_lat[i], decl, r1, solt, sunh);
+      sol_day(sol_hru(P.hru_slope[i], P.hru_aspect[i], P.hru_lat[i]), sd, cd, td, r1, solt, sunh);
       s->soltab[0][(size_t)j * n + i] = solt;
       s->soltab[2][(size_t)j * n + i] = sunh;
     }

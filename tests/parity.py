@@ -5,8 +5,8 @@ rtol 1e-9 / atol 1e-10; integer and flag outputs bit-exact, "with any
 disagreements counted and traced to threshold ties".
 
 The one tie source in this chain is PRMSSnow's *ghost pack*: when a pack melts
-out, `pkwater_equiv` can be left at rounding-noise level (1e-16 .. 1e-12,
-the residue of a cancellation) and the day on which it finally drops below
+out, `pkwater_equiv` can be left at rounding-noise level (1e-16 .. 1e-8 inches,
+the residue of a cancellation that has already lost most of its digits) and the day on which it finally drops below
 `dnearzero = 2.23e-16` (prms_snow.py:797) depends on the last bits of the
 transcendental functions.  Rain on such a ghost pack is routed as snowmelt
 through check_capacity instead of perv_comp (prms_runoff.py:905-935), so a
@@ -22,7 +22,7 @@ import numpy as np
 
 RTOL = 1e-9
 ATOL = 1e-10
-GHOST = 1e-9
+GHOST = 1e-6  # = PRMS's own `nearzero` (inches of water)
 
 # differences of two large numbers: compared with an absolute tolerance scaled
 # by the magnitude of the operands (a flow of ~1e4 cfs x 86400 s)
