@@ -57,7 +57,10 @@ int pws_set_param_i32(pws_handle *h, const char *name, const int32_t *h_v, int64
  * "albset_rna|rnm|sna|snm" (scalar parameters, prms_snow.py:911-914),
  * "block_days" (days per device time block of pws_run_host),
  * "soltab_device" (1: build the PRMSSolarGeometry tables with the CUDA kernel
- * k_soltab; 0, default: with the host libm the reference's tables come from). */
+ * k_soltab; 0, default: with the host libm the reference's tables come from),
+ * "wavefront" (1, default: route all DAG levels concurrently in one persistent
+ * cooperative kernel when every segment thread can be resident; 0: one launch
+ * per topological level). */
 int pws_set_option(pws_handle *h, const char *name, double value);
 
 /* Everything the reference derives at construction: soltab tables

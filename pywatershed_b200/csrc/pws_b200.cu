@@ -127,6 +127,9 @@ struct pws_handle {
          *d_day_lat = nullptr;
   int4* d_cal = nullptr;
   int* d_viol = nullptr;
+  int* d_progress = nullptr;
+  int wavefront = 1;      // option: 1 = persistent wavefront routing when it fits
+  int wavefront_ok = -1;  // -1 unknown, 0 does not fit, 1 fits
   // host ring for pws_run_host
   int ring_days = 0;
   double* d_forc[2] = {nullptr, nullptr};
@@ -140,7 +143,7 @@ struct pws_handle {
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr},
               ev_d2h[2] = {nullptr, nullptr};
   double ms_column = 0.0, ms_channel = 0.0;
-  int n_col_launch = 0, n_ch_launch = 0;
+  int n_col_launch = 0, n_ch_launch = 0, last_channel_launches = 0;
   std::vector<double> h_seg_inflow_init;
   bool timing_pending = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pairs_col, ev_pairs_ch;
@@ -251,6 +254,7 @@ static void free_scratch(pws_handle* h) {
   cudaFree(h->d_day_lat); h->d_day_lat = nullptr;
   cudaFree(h->d_cal); h->d_cal = nullptr;
   cudaFree(h->d_viol); h->d_viol = nullptr;
+  cudaFree(h->d_progress); h->d_progress = nullptr;
   h->scratch_days = 0;
 }
 
@@ -339,6 +343,7 @@ extern "C" int pws_set_option(pws_handle* h, const char* name, double value) {
   else if (!strcmp(name, "albset_snm")) h->albset[3] = value;
   else if (!strcmp(name, "block_days")) { h->block_days = (int)value; return 0; }
   else if (!strcmp(name, "soltab_device")) h->soltab_device = value != 0.0;
+  else if (!strcmp(name, "wavefront")) { h->wavefront = value != 0.0; return 0; }
   else PWS_FAIL(h, "pws_set_option: unknown option '%s'", name);
   h->inited = false;
   return 0;
@@ -714,6 +719,7 @@ static int ensure_scratch(pws_handle* h, int ndays) {
   if (h->nseg > 0) {
     PWS_CUDA(h, cudaMalloc(&h->d_hru_lat, T * h->stride * sizeof(double)));
     PWS_CUDA(h, cudaMalloc(&h->d_ots, T * 24 * h->sstride * sizeof(double)));
+    PWS_CUDA(h, cudaMalloc(&h->d_progress, (size_t)h->sstride * sizeof(int)));
     PWS_CUDA(h, cudaMalloc(&h->d_day_outvol, T * h->sstride * sizeof(double)));
     PWS_CUDA(h, cudaMalloc(&h->d_day_dstor, T * h->sstride * sizeof(double)));
     PWS_CUDA(h, cudaMalloc(&h->d_day_lat, T * h->sstride * sizeof(double)));
@@ -745,16 +751,41 @@ static int enqueue_channel(pws_handle* h, int ndays, const double* d_hru_lat,
   a.seg_out = h->n_seg_sel > 0 ? d_seg_out : nullptr;
   a.n_seg_sel = h->n_seg_sel;
   memcpy(a.slot, h->slot_seg, sizeof a.slot);
-  for (int l = 0; l < h->nlevels; ++l) {
-    const int b = h->level_begin[l], c = h->level_begin[l + 1] - b;
-    if (c <= 0) continue;
-    k_route_level<<<(c + 127) / 128, 128, 0, h->s_compute>>>(a, b, c);
+  a.progress = h->d_progress;
+  a.err = h->d_err;
+  bool use_wave = false;
+  if (h->wavefront) {
+    if (h->wavefront_ok < 0) {
+      int per_sm = 0, nsm = 0, coop = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_route_wavefront, 128, 0);
+      cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
+      h->wavefront_ok = (coop && (int64_t)per_sm * nsm * 128 >= h->nseg) ? 1 : 0;
+    }
+    use_wave = h->wavefront_ok == 1;
+  }
+  if (use_wave) {
+    PWS_CUDA(h, cudaMemsetAsync(h->d_progress, 0, (size_t)h->sstride * sizeof(int), h->s_compute));
+    void* kargs[] = {(void*)&a};
+    const unsigned grid = (unsigned)((h->nseg + 127) / 128);
+    PWS_CUDA(h, cudaLaunchCooperativeKernel((void*)k_route_wavefront, dim3(grid), dim3(128), kargs,
+                                            0, h->s_compute));
     h->launches++;
+    h->last_channel_launches += 1;
+  } else {
+    for (int l = 0; l < h->nlevels; ++l) {
+      const int b = h->level_begin[l], c = h->level_begin[l + 1] - b;
+      if (c <= 0) continue;
+      k_route_level<<<(c + 127) / 128, 128, 0, h->s_compute>>>(a, b, c);
+      h->launches++;
+      h->last_channel_launches += 1;
+    }
   }
   if (budget) {
     k_channel_budget<<<ndays, 256, 0, h->s_compute>>>(h->nseg, h->sstride, h->d_day_lat,
                                                       h->d_day_outvol, h->d_day_dstor, h->d_viol);
     h->launches++;
+    h->last_channel_launches += 1;
   }
   PWS_CUDA(h, cudaGetLastError());
   return 0;
@@ -813,6 +844,8 @@ static int check_device_errors(pws_handle* h) {
     if (errflag & 1)
       PWS_FAIL(h, "ERROR, in compute_interflow sos=0, please contact code developers "
                   "(prms_soilzone.py:1282-1287)");
+    if (errflag & 16)
+      PWS_FAIL(h, "k_route_wavefront: a segment waited too long for its upstream segments");
     PWS_FAIL(h, "device error flag %d", errflag);
   }
   return 0;
@@ -826,7 +859,8 @@ extern "C" int pws_sync(pws_handle* h) {
   if (!h->ev_pairs_col.empty()) {
     h->ms_column = h->ms_channel = 0.0;
     h->n_col_launch = (int)h->ev_pairs_col.size();
-    h->n_ch_launch = (int)h->ev_pairs_ch.size() * (h->nlevels + 1);
+    h->n_ch_launch = h->last_channel_launches;
+    h->last_channel_launches = 0;
     for (auto& pr : h->ev_pairs_col) {
       float ms = 0;
       cudaEventElapsedTime(&ms, pr.first, pr.second);

@@ -3,8 +3,9 @@
 //   k_hru_init      derived parameters + initial conditions, once per run
 //   k_hru_column    the fused atmosphere..groundwater column, 1 thread / HRU,
 //                   state in registers across a block of days
-//   k_route_level   Muskingum-Mann routing of one topological level of the
-//                   segment DAG over a whole block of days
+//   k_route_wavefront  Muskingum-Mann routing, all topological levels of the
+//                   segment DAG concurrently over a block of days (persistent,
+//                   cooperative); k_route_level = per-level fallback
 //   k_channel_budget per-day global channel mass balance
 #pragma once
 #include <cuda_runtime.h>
@@ -166,12 +167,20 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
 }
 
 // ---------------------------------------------------------------- channel
-// Muskingum-Mann routing (prms_channel.py:456-585) of the segments of ONE
-// topological level for every hour of a block of days.  Segments are stored
-// in level order ("pos"); thread = segment.  The hourly outflow of every
-// segment with a downstream neighbour goes to the HBM scratch
-// ots[hour][pos] (coalesced across the warp); the next level's launch gathers
-// its upstream hours from it in the reference's accumulation order.
+// Muskingum-Mann routing (prms_channel.py:456-585).  Segments are stored in
+// topological-level order ("pos"); thread = segment.  Every segment with a
+// downstream neighbour publishes its 24 hourly outflows of a day as one
+// contiguous 192-byte row of the HBM scratch ots[pos][day][hour]; a consumer
+// gathers whole rows of its upstream segments (fully used sectors) before it
+// enters the hourly recurrence, so no load sits on the recurrence's critical
+// path.  Two drivers share route_day():
+//   k_route_wavefront  ONE cooperative launch per block of days; all levels
+//                      run concurrently, a segment starts day d as soon as
+//                      its upstream segments have published day d (progress
+//                      counters in HBM, acquire/release through L2).  Critical
+//                      path = nlevels + ndays segment-days, not their product.
+//   k_route_level      one launch per level (fallback when the segment
+//                      threads cannot all be co-resident).
 struct ChannelArgs {
   int64_t nseg, sstride;
   int ndays;
@@ -194,81 +203,170 @@ struct ChannelArgs {
   const double* hru_lat;     // [ndays][hstride] or null
   int64_t hstride;
   const double* seg_lat_in;  // [ndays][nseg] in ORIGINAL order (channel-only runs) or null
-  double* ots;               // [ndays*24][sstride]
+  double* ots;               // [nseg][ndays][24] hourly outflow of segments with a downstream
+  int* progress;             // [nseg] days published (wavefront)
   double* day_outvol;        // [ndays][sstride] channel_outflow_vol (pos order)
   double* day_dstor;         // [ndays][sstride] seg_stor_change
   double* day_lat;           // [ndays][sstride] seg_lateral_inflow
   // outputs, original segment order: [ndays][n_seg_sel][nseg]
   double* seg_out;
   int n_seg_sel;
+  int* err;
   short slot[PWS_N_SEG_VARS];
 };
+
+struct SegStatic {
+  int tsi, ub, ue, hb, he, orig;
+  bool down;
+  double ts, c0, c1, c2;
+};
+
+__device__ __forceinline__ SegStatic seg_static(const ChannelArgs& a, int pos) {
+  SegStatic g;
+  g.tsi = a.tsi[pos];
+  g.ts = a.ts[pos]; g.c0 = a.c0[pos]; g.c1 = a.c1[pos]; g.c2 = a.c2[pos];
+  g.ub = a.up_ptr[pos]; g.ue = a.up_ptr[pos + 1];
+  g.hb = a.hru_ptr[pos]; g.he = a.hru_ptr[pos + 1];
+  g.down = a.has_down[pos] != 0;
+  g.orig = a.orig[pos];
+  return g;
+}
+
+// One segment, one day (24 hourly steps).  Upstream hours are summed in the
+// reference's accumulation order (topological rank, prms_channel.py:566-571).
+__device__ __forceinline__ void route_day(const ChannelArgs& a, const SegStatic& g, int pos,
+                                          int d, double& outflow_ts, double& seg_inflow_prev) {
+  // lateral inflow: HRU contributions in ascending HRU order (prms_channel.py:396-421)
+  double lateral = 0.0;
+  if (a.seg_lat_in != nullptr) {
+    lateral = a.seg_lat_in[(int64_t)d * a.nseg + g.orig];
+  } else {
+    for (int k = g.hb; k < g.he; ++k)
+      lateral += __ldcg(a.hru_lat + (int64_t)d * a.hstride + a.hru_idx[k]);
+  }
+  double up[24];
+#pragma unroll
+  for (int h = 0; h < 24; ++h) up[h] = 0.0;
+  const int64_t day_off = (int64_t)d * 24;
+  const int64_t row_len = (int64_t)a.ndays * 24;
+  for (int k = g.ub; k < g.ue; ++k) {
+    const double2* src =
+        reinterpret_cast<const double2*>(a.ots + (int64_t)a.up_idx[k] * row_len + day_off);
+#pragma unroll
+    for (int h = 0; h < 12; ++h) {
+      const double2 v = __ldcg(src + h);
+      up[2 * h] += v.x;
+      up[2 * h + 1] += v.y;
+    }
+  }
+  double seg_inflow0 = seg_inflow_prev;  // _advance_variables, prms_channel.py:384-386
+  double seg_inflow = seg_inflow0 * 0.0, seg_outflow = seg_inflow0 * 0.0;
+  double inflow_ts = seg_inflow0 * 0.0, cur_sum = seg_inflow0 * 0.0;
+  double2* dst = reinterpret_cast<double2*>(a.ots + (int64_t)pos * row_len + day_off);
+  double o_even = 0.0;
+#pragma unroll
+  for (int h = 0; h < 24; ++h) {
+    const double cur = lateral + up[h];
+    seg_inflow += cur;
+    inflow_ts += cur;
+    cur_sum += up[h];
+    const bool fire = g.tsi < 0 ? true : ((h + 1) % g.tsi) == 0;
+    if (fire) {
+      inflow_ts /= g.ts;
+      if (g.tsi > 0) outflow_ts = inflow_ts * g.c0 + seg_inflow0 * g.c1 + outflow_ts * g.c2;
+      else outflow_ts = inflow_ts;
+      seg_inflow0 = inflow_ts;
+      inflow_ts = 0.0;
+    }
+    seg_outflow += outflow_ts;
+    if ((h & 1) == 0) o_even = outflow_ts;
+    else if (g.down) __stcg(dst + (h >> 1), make_double2(o_even, outflow_ts));
+  }
+  seg_outflow /= 24.0;
+  seg_inflow /= 24.0;
+  const double upstream = cur_sum / 24.0;
+  const double dstor = (seg_inflow - seg_outflow) * 86400.0;
+  const double outvol = (g.down ? 0.0 : seg_outflow) * 86400.0;
+  seg_inflow_prev = seg_inflow;
+  const int64_t drow = (int64_t)d * a.sstride + pos;
+  a.day_outvol[drow] = outvol;
+  a.day_dstor[drow] = dstor;
+  a.day_lat[drow] = lateral;
+  if (a.seg_out != nullptr) {
+    double* q = a.seg_out + (int64_t)d * a.n_seg_sel * a.nseg + g.orig;
+    if (a.slot[S_channel_outflow_vol] >= 0) q[(int64_t)a.slot[S_channel_outflow_vol] * a.nseg] = outvol;
+    if (a.slot[S_seg_lateral_inflow] >= 0) q[(int64_t)a.slot[S_seg_lateral_inflow] * a.nseg] = lateral;
+    if (a.slot[S_seg_upstream_inflow] >= 0) q[(int64_t)a.slot[S_seg_upstream_inflow] * a.nseg] = upstream;
+    if (a.slot[S_seg_outflow] >= 0) q[(int64_t)a.slot[S_seg_outflow] * a.nseg] = seg_outflow;
+    if (a.slot[S_seg_stor_change] >= 0) q[(int64_t)a.slot[S_seg_stor_change] * a.nseg] = dstor;
+  }
+}
 
 __global__ void __launch_bounds__(128)
 k_route_level(const __grid_constant__ ChannelArgs a, int level_begin, int level_count) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= level_count) return;
   const int pos = level_begin + t;
-  const int tsi = a.tsi[pos];
-  const double ts = a.ts[pos], c0 = a.c0[pos], c1 = a.c1[pos], c2 = a.c2[pos];
-  const int ub = a.up_ptr[pos], ue = a.up_ptr[pos + 1];
-  const int hb = a.hru_ptr[pos], he = a.hru_ptr[pos + 1];
-  const bool down = a.has_down[pos] != 0;
-  const int orig = a.orig[pos];
+  const SegStatic g = seg_static(a, pos);
   double outflow_ts = a.outflow_ts[pos];
   double seg_inflow_prev = a.seg_inflow[pos];
-  for (int d = 0; d < a.ndays; ++d) {
-    // lateral inflow: HRU contributions in ascending HRU order (prms_channel.py:396-421)
-    double lateral = 0.0;
-    if (a.seg_lat_in != nullptr) {
-      lateral = a.seg_lat_in[(int64_t)d * a.nseg + orig];
-    } else {
-      for (int k = hb; k < he; ++k)
-        lateral += __ldcg(a.hru_lat + (int64_t)d * a.hstride + a.hru_idx[k]);
-    }
-    double seg_inflow0 = seg_inflow_prev;  // _advance_variables, prms_channel.py:384-386
-    double seg_inflow = seg_inflow0 * 0.0, seg_outflow = seg_inflow0 * 0.0;
-    double inflow_ts = seg_inflow0 * 0.0, cur_sum = seg_inflow0 * 0.0;
-    for (int h = 0; h < 24; ++h) {
-      const int64_t row = ((int64_t)d * 24 + h) * a.sstride;
-      double up = seg_inflow * 0.0;
-      for (int k = ub; k < ue; ++k) up += __ldcg(a.ots + row + a.up_idx[k]);
-      const double cur = lateral + up;
-      seg_inflow += cur;
-      inflow_ts += cur;
-      cur_sum += up;
-      const bool fire = tsi < 0 ? true : ((h + 1) % tsi) == 0;
-      if (fire) {
-        inflow_ts /= ts;
-        if (tsi > 0) outflow_ts = inflow_ts * c0 + seg_inflow0 * c1 + outflow_ts * c2;
-        else outflow_ts = inflow_ts;
-        seg_inflow0 = inflow_ts;
-        inflow_ts = 0.0;
-      }
-      seg_outflow += outflow_ts;
-      if (down) a.ots[row + pos] = outflow_ts;
-    }
-    seg_outflow /= 24.0;
-    seg_inflow /= 24.0;
-    const double upstream = cur_sum / 24.0;
-    const double dstor = (seg_inflow - seg_outflow) * 86400.0;
-    const double outvol = (down ? 0.0 : seg_outflow) * 86400.0;
-    seg_inflow_prev = seg_inflow;
-    const int64_t drow = (int64_t)d * a.sstride + pos;
-    a.day_outvol[drow] = outvol;
-    a.day_dstor[drow] = dstor;
-    a.day_lat[drow] = lateral;
-    if (a.seg_out != nullptr) {
-      double* o = a.seg_out + (int64_t)d * a.n_seg_sel * a.nseg + orig;
-      if (a.slot[S_channel_outflow_vol] >= 0) o[(int64_t)a.slot[S_channel_outflow_vol] * a.nseg] = outvol;
-      if (a.slot[S_seg_lateral_inflow] >= 0) o[(int64_t)a.slot[S_seg_lateral_inflow] * a.nseg] = lateral;
-      if (a.slot[S_seg_upstream_inflow] >= 0) o[(int64_t)a.slot[S_seg_upstream_inflow] * a.nseg] = upstream;
-      if (a.slot[S_seg_outflow] >= 0) o[(int64_t)a.slot[S_seg_outflow] * a.nseg] = seg_outflow;
-      if (a.slot[S_seg_stor_change] >= 0) o[(int64_t)a.slot[S_seg_stor_change] * a.nseg] = dstor;
-    }
-  }
+  for (int d = 0; d < a.ndays; ++d) route_day(a, g, pos, d, outflow_ts, seg_inflow_prev);
   a.outflow_ts[pos] = outflow_ts;
   a.seg_inflow[pos] = seg_inflow_prev;
+}
+
+// Persistent wavefront over (segment, day).  Cooperative launch: every CTA is
+// resident, so a spinning consumer can never keep its producer off the GPU.
+// Rounds are warp-synchronous: in each round a lane whose upstream segments
+// have published day d routes that day and publishes; the other lanes poll
+// again next round, so producer and consumer lanes of one warp cannot block
+// each other.  A bounded number of idle rounds turns a would-be hang into an
+// error flag.
+#ifndef PWS_WAVEFRONT_MAX_IDLE
+#define PWS_WAVEFRONT_MAX_IDLE (1 << 22)
+#endif
+__global__ void __launch_bounds__(128, 4)
+k_route_wavefront(const __grid_constant__ ChannelArgs a) {
+  const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = pos < a.nseg;
+  SegStatic g{};
+  double outflow_ts = 0.0, seg_inflow_prev = 0.0;
+  if (live) {
+    g = seg_static(a, pos);
+    outflow_ts = a.outflow_ts[pos];
+    seg_inflow_prev = a.seg_inflow[pos];
+  }
+  int d = live ? 0 : a.ndays;
+  int idle = 0;
+  while (__any_sync(0xffffffffu, d < a.ndays)) {
+    bool ready = d < a.ndays;
+    if (ready) {
+      for (int k = g.ub; k < g.ue; ++k) {
+        const int pu = *reinterpret_cast<volatile const int*>(a.progress + a.up_idx[k]);
+        ready = ready && (pu > d);
+      }
+    }
+    if (ready) {
+      __threadfence();  // acquire: the published rows are visible after the counter
+      route_day(a, g, pos, d, outflow_ts, seg_inflow_prev);
+      ++d;
+      if (g.down) {
+        __threadfence();  // release: rows before the counter
+        *reinterpret_cast<volatile int*>(a.progress + pos) = d;
+      }
+      idle = 0;
+    } else if (d < a.ndays) {
+      if (++idle > PWS_WAVEFRONT_MAX_IDLE) {
+        atomicOr(a.err, 16);
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  if (live) {
+    a.outflow_ts[pos] = outflow_ts;
+    a.seg_inflow[pos] = seg_inflow_prev;
+  }
 }
 
 // Global-basis channel budget (prms_channel.py:115,165-174; budget.py:388-416):
