@@ -1,6 +1,28 @@
 """pywatershed_b200: B200-native (sm_100a CUDA, fp64) implementation of
 pywatershed's per-timestep PRMS/NHM process chain, behind the reference's
-Process / Model API.  See DESIGN.md."""
+Process / Model API.  See DESIGN.md and INTEGRATION.md."""
+from .budget import Budget  # noqa: F401
+from .control import Control  # noqa: F401
 from .engine import Engine, Registry, calendar  # noqa: F401
+from .model import Model  # noqa: F401
+from .parameters import Parameters, PrmsParameters  # noqa: F401
+from .processes import (  # noqa: F401
+    ConservativeProcess,
+    PRMSAtmosphere,
+    PRMSCanopy,
+    PRMSChannel,
+    PRMSGroundwater,
+    PRMSRunoff,
+    PRMSSnow,
+    PRMSSoilzone,
+    PRMSSolarGeometry,
+    Process,
+    TimeseriesArray,
+)
 
-__all__ = ["Engine", "Registry", "calendar"]
+__all__ = [
+    "Budget", "Control", "Engine", "Registry", "calendar", "Model", "Parameters",
+    "PrmsParameters", "Process", "ConservativeProcess", "TimeseriesArray",
+    "PRMSSolarGeometry", "PRMSAtmosphere", "PRMSCanopy", "PRMSSnow", "PRMSRunoff",
+    "PRMSSoilzone", "PRMSGroundwater", "PRMSChannel",
+]

@@ -10,8 +10,12 @@ from __future__ import annotations
 import ctypes as C
 import pathlib as pl
 
+import os
+
 PKG = pl.Path(__file__).resolve().parent
-LIB_PATH = PKG / "libpwsb200.so"
+# PWS_B200_LIB: development knob to load an alternative build of the same
+# library (kernel tuning variants); the default is the in-tree build.
+LIB_PATH = pl.Path(os.environ.get("PWS_B200_LIB", PKG / "libpwsb200.so"))
 _lib = None
 
 

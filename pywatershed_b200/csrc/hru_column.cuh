@@ -30,13 +30,15 @@
 #if defined(__CUDACC__)
 #define PWS_DEV __device__ __forceinline__
 #define PWS_HD __host__ __device__ __forceinline__
-#define PWS_LD(p) __ldg(p)
+#define PWS_LD(p) (*(p))
 #define PWS_TABLE static __device__ const
+#define PWS_EXP10(x) exp10(x)
 #else
 #define PWS_DEV static inline
 #define PWS_HD static inline
 #define PWS_LD(p) (*(p))
 #define PWS_TABLE static const
+#define PWS_EXP10(x) pow(10.0, (x))
 #endif
 
 namespace pws {
@@ -226,42 +228,42 @@ PWS_DEV double calc_snowbal(HruState& s, double& snowmelt, int niteda, double ce
   double cecsub = 0.0;
   if (temp > 0.0 && hru_ppt > 0.0) cecsub = cec * temp;
   const double cal = sky + can + cecsub + sw;
-  if (ts >= 0.0 && cal > 0.0) {
-    calc_calin(s, snowmelt, cal, den_max, denmaxinv, freeh2o_cap);
-    return cal;
-  }
-  const double qcond = cst * (ts - s.pk_temp);
-  if (qcond < 0.0) {
-    if (s.pk_temp < 0.0) {
-      s.pk_def = s.pk_def - qcond;
-      s.pk_temp = -1 * s.pk_def / (s.pkwater_equiv * 1.27);
+  bool do_calin = ts >= 0.0 && cal > 0.0;
+  if (!do_calin) {
+    const double qcond = cst * (ts - s.pk_temp);
+    if (qcond < 0.0) {
+      if (s.pk_temp < 0.0) {
+        s.pk_def = s.pk_def - qcond;
+        s.pk_temp = -1 * s.pk_def / (s.pkwater_equiv * 1.27);
+      } else {
+        calc_caloss(s, qcond);
+      }
+    } else if (qcond < PWS_CLOSEZERO) {
+      do_calin = s.pk_temp >= 0.0 && cal > 0.0;
+    } else if (ts >= 0.0) {
+      const double pk_defsub = s.pk_def - qcond;
+      if (pk_defsub < 0.0) {
+        s.pk_def = 0.0;
+        s.pk_temp = 0.0;
+      } else {
+        s.pk_def = pk_defsub;
+        s.pk_temp = -pk_defsub / (s.pkwater_equiv * 1.27);
+      }
     } else {
-      calc_caloss(s, qcond);
-    }
-  } else if (qcond < PWS_CLOSEZERO) {
-    if (s.pk_temp >= 0.0 && cal > 0.0)
-      calc_calin(s, snowmelt, cal, den_max, denmaxinv, freeh2o_cap);
-  } else if (ts >= 0.0) {
-    const double pk_defsub = s.pk_def - qcond;
-    if (pk_defsub < 0.0) {
-      s.pk_def = 0.0;
-      s.pk_temp = 0.0;
-    } else {
-      s.pk_def = pk_defsub;
-      s.pk_temp = -pk_defsub / (s.pkwater_equiv * 1.27);
-    }
-  } else {
-    const double pkt = -ts * (s.pkwater_equiv * 1.27);
-    const double pks = s.pk_def - pkt;
-    const double pk_defsub = pks - qcond;
-    if (pk_defsub < 0.0) {
-      s.pk_def = pkt;
-      s.pk_temp = ts;
-    } else {
-      s.pk_def = pk_defsub + pkt;
-      s.pk_temp = -1 * s.pk_def / (s.pkwater_equiv * 1.27);
+      const double pkt = -ts * (s.pkwater_equiv * 1.27);
+      const double pks = s.pk_def - pkt;
+      const double pk_defsub = pks - qcond;
+      if (pk_defsub < 0.0) {
+        s.pk_def = pkt;
+        s.pk_temp = ts;
+      } else {
+        s.pk_def = pk_defsub + pkt;
+        s.pk_temp = -1 * s.pk_def / (s.pkwater_equiv * 1.27);
+      }
     }
   }
+  // one call site for both the direct and the qcond ~ 0 melt paths (:2812, :2957)
+  if (do_calin) calc_calin(s, snowmelt, cal, den_max, denmaxinv, freeh2o_cap);
   return cal;
 }
 
@@ -272,7 +274,7 @@ PWS_DEV void perv_comp(double soil_moist_prev, double carea_max, double smidx_co
   const double smidx = soil_moist_prev + 0.5 * ptc;
   double ca_fraction;
   if (smidx > 25.0) ca_fraction = carea_max;
-  else ca_fraction = smidx_coef * pow(10.0, smidx_exp * smidx);
+  else ca_fraction = smidx_coef * PWS_EXP10(smidx_exp * smidx);
   if (ca_fraction > carea_max) ca_fraction = carea_max;
   const double srpp = ca_fraction * pptp;
   infil = infil - srpp;
@@ -848,6 +850,8 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
           if (net_rain > 0.0) {
             s.pkwater_equiv = s.pkwater_equiv + net_rain;
             pk_precip = pk_precip + net_rain;
+            double calpr = 0.0;
+            bool do_calin = false;
             if (s.pk_def > 0.0) {
               const double caln = (80.000 + train) * PWS_INCH2CM;
               const double pndz = s.pk_def / caln;
@@ -864,14 +868,15 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
                 s.pk_temp = 0.0;
                 s.pk_ice = s.pk_ice + pndz;
                 s.freeh2o = net_rain - pndz;
-                const double calpr = train * (net_rain - pndz) * PWS_INCH2CM;
-                calc_calin(s, snowmelt, calpr, den_max, denmaxinv, freeh2o_cap);
+                calpr = train * (net_rain - pndz) * PWS_INCH2CM;
+                do_calin = true;
               }
             } else {
               s.freeh2o = s.freeh2o + net_rain;
-              const double calpr = train * net_rain * PWS_INCH2CM;
-              calc_calin(s, snowmelt, calpr, den_max, denmaxinv, freeh2o_cap);
+              calpr = train * net_rain * PWS_INCH2CM;
+              do_calin = true;
             }
+            if (do_calin) calc_calin(s, snowmelt, calpr, den_max, denmaxinv, freeh2o_cap);
           }
         } else if (net_rain > 0.0) {
           pptmix_nopack = 1;
@@ -1049,15 +1054,17 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
         else s.pk_den = 0.0;
         const double effk = 0.0154 * s.pk_den;
         const double cst = s.pk_den * (sqrt(effk * 13751.0));
-        tcal = calc_snowbal(s, snowmelt, 1, cec, cst, esv, 0.0, (tminc + tavgc) * 0.5,
-                            trd, canopy_covden, den_max, denmaxinv, emis_noppt,
-                            freeh2o_cap, hru_ppt, tstorm_mo);
-        if (s.pkwater_equiv > 0.0) {
-          const double cals =
-              calc_snowbal(s, snowmelt, 2, cec, cst, esv, swn, (tmaxc + tavgc) * 0.5,
-                           trd, canopy_covden, den_max, denmaxinv, emis_noppt,
-                           freeh2o_cap, hru_ppt, tstorm_mo);
-          tcal = tcal + cals;
+        // night (niteda 1) then day (niteda 2) through ONE inlined copy of the
+        // energy balance (instruction-cache footprint)
+#pragma unroll 1
+        for (int niteda = 1; niteda <= 2; ++niteda) {
+          if (!(s.pkwater_equiv > 0.0)) break;
+          const double temp = (niteda == 1 ? tminc : tmaxc);
+          const double cal =
+              calc_snowbal(s, snowmelt, niteda, cec, cst, esv, niteda == 1 ? 0.0 : swn,
+                           (temp + tavgc) * 0.5, trd, canopy_covden, den_max, denmaxinv,
+                           emis_noppt, freeh2o_cap, hru_ppt, tstorm_mo);
+          tcal = niteda == 1 ? cal : tcal + cal;
         }
         // ---- step 5: sublimation, prms_snow.py:3096-3222
         if (s.pkwater_equiv > 0.0) {
@@ -1191,43 +1198,56 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
     const double carea_max = PWS_LD(P.carea_max + i);
     const double smidx_coef = PWS_LD(P.smidx_coef + i);
     const double smidx_exp = PWS_LD(P.smidx_exp + i);
-    if (intcp_changeover > 0.0) {
-      avail_water = avail_water + intcp_changeover;
-      infil = infil + intcp_changeover;
-      if (land)
-        perv_comp(soil_moist_prev, carea_max, smidx_coef, smidx_exp, intcp_changeover,
-                  intcp_changeover, infil, srp, contrib_fraction);
-    }
-    if (pptmix_nopack != 0) {
-      avail_water = avail_water + through_rain;
-      infil = infil + through_rain;
-      if (land)
-        perv_comp(soil_moist_prev, carea_max, smidx_coef, smidx_exp, through_rain,
-                  through_rain, infil, srp, contrib_fraction);
-    }
-    if (snowmelt > 0.0) {
-      avail_water = avail_water + snowmelt;
-      infil = infil + snowmelt;
-      if (land) {
-        if (s.pkwater_equiv > 0.0 || net_rain < PWS_NEARZERO)
-          check_capacity(soil_moist_prev, PWS_LD(P.soil_moist_max + i),
-                         PWS_LD(P.snowinfil_max + i), infil, srp);
-        else
-          perv_comp(soil_moist_prev, carea_max, smidx_coef, smidx_exp, snowmelt, net_ppt,
-                    infil, srp, contrib_fraction);
+    // The reference calls perv_comp / check_capacity from up to three places in
+    // sequence (:868-963); the three stages run through one loop body so the
+    // pow() and the capacity check are inlined once.
+    const double soil_moist_max_ro = PWS_LD(P.soil_moist_max + i);
+    const double snowinfil_max = PWS_LD(P.snowinfil_max + i);
+#pragma unroll 1
+    for (int stage = 0; stage < 3; ++stage) {
+      int kind = 0;  // 1 perv_comp(pptp, ptc), 2 check_capacity
+      double pptp = 0.0, ptc = 0.0;
+      if (stage == 0) {
+        if (intcp_changeover > 0.0) {
+          avail_water = avail_water + intcp_changeover;
+          infil = infil + intcp_changeover;
+          kind = land ? 1 : 0;
+          pptp = ptc = intcp_changeover;
+        }
+      } else if (stage == 1) {
+        if (pptmix_nopack != 0) {
+          avail_water = avail_water + through_rain;
+          infil = infil + through_rain;
+          kind = land ? 1 : 0;
+          pptp = ptc = through_rain;
+        }
+      } else if (snowmelt > 0.0) {
+        avail_water = avail_water + snowmelt;
+        infil = infil + snowmelt;
+        if (land) {
+          if (s.pkwater_equiv > 0.0 || net_rain < PWS_NEARZERO) {
+            kind = 2;
+          } else {
+            kind = 1;
+            pptp = snowmelt;
+            ptc = net_ppt;
+          }
+        }
+      } else if (s.pkwater_equiv < PWS_DNEARZERO) {
+        if (net_snow < PWS_NEARZERO && through_rain > 0.0) {
+          avail_water = avail_water + through_rain;
+          infil = infil + through_rain;
+          kind = land ? 1 : 0;
+          pptp = ptc = through_rain;
+        }
+      } else if (infil > 0.0) {
+        kind = land ? 2 : 0;
       }
-    } else if (s.pkwater_equiv < PWS_DNEARZERO) {
-      if (net_snow < PWS_NEARZERO && through_rain > 0.0) {
-        avail_water = avail_water + through_rain;
-        infil = infil + through_rain;
-        if (land)
-          perv_comp(soil_moist_prev, carea_max, smidx_coef, smidx_exp, through_rain,
-                    through_rain, infil, srp, contrib_fraction);
-      }
-    } else if (infil > 0.0) {
-      if (land)
-        check_capacity(soil_moist_prev, PWS_LD(P.soil_moist_max + i),
-                       PWS_LD(P.snowinfil_max + i), infil, srp);
+      if (kind == 1)
+        perv_comp(soil_moist_prev, carea_max, smidx_coef, smidx_exp, pptp, ptc, infil, srp,
+                  contrib_fraction);
+      else if (kind == 2)
+        check_capacity(soil_moist_prev, soil_moist_max_ro, snowinfil_max, infil, srp);
     }
     if (hruarea_imperv > 0.0) {
       s.imperv_stor = s.imperv_stor + avail_water;
@@ -1478,7 +1498,10 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
       const double ssr2gw_rate = PWS_LD(P.ssr2gw_rate + i);
       if (s.slow_stor > 0.0 && ssr2gw_rate > 0.0) {
         // _compute_gwflow :1315-1320
-        ssr_to_gw = fmax(0.0, ssr2gw_rate * pow(s.slow_stor, PWS_LD(P.ssr2gw_exp + i)));
+        const double ssr2gw_exp = PWS_LD(P.ssr2gw_exp + i);
+        // pow(x, 1.0) == x exactly; the NHM default exponent is 1
+        const double sp = ssr2gw_exp == 1.0 ? s.slow_stor : pow(s.slow_stor, ssr2gw_exp);
+        ssr_to_gw = fmax(0.0, ssr2gw_rate * sp);
         ssr_to_gw = fmin(ssr_to_gw, s.slow_stor);
         s.slow_stor = s.slow_stor - ssr_to_gw;
       }

@@ -97,6 +97,7 @@ struct pws_handle {
   int dprst_flag = 1, temp_units = 0, start_month = 1, start_doy = 1, adjust_parameters = 1;
   int block_days = 0;
   int soltab_device = 0;
+  bool smem_attr_set = false;
   double albset[4] = {0, 0, 0, 0};
   // host copies of the parameters (set before pws_init)
   std::map<std::string, std::vector<double>> pf;
@@ -813,11 +814,20 @@ static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const d
   a.hru_lat = h->nseg > 0 ? h->d_hru_lat : nullptr;
   a.viol = want_viol ? h->d_viol : nullptr;
   a.err = h->d_err;
-  memcpy(a.slot, h->slot_hru, sizeof a.slot);
+  for (int v = 0; v < PWS_N_HRU_VARS; ++v) {
+    const int sl = h->slot_hru[v];
+    const int64_t esz = names().hru_var_kind[v] == 0 ? 8 : 4;
+    a.off[v] = sl < 0 ? -1 : (int64_t)sl * a.ostride * esz;
+  }
+  if (kColumnSmemBytes > 48 * 1024 && !h->smem_attr_set) {
+    PWS_CUDA(h, cudaFuncSetAttribute(k_hru_column, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)kColumnSmemBytes));
+    h->smem_attr_set = true;
+  }
   cudaEvent_t e0 = new_event(h), e1 = new_event(h), e2 = new_event(h);
   cudaEventRecord(e0, h->s_compute);
   const unsigned grid = (unsigned)((h->nhru + PWS_COLUMN_THREADS - 1) / PWS_COLUMN_THREADS);
-  k_hru_column<<<grid, PWS_COLUMN_THREADS, 0, h->s_compute>>>(a);
+  k_hru_column<<<grid, PWS_COLUMN_THREADS, kColumnSmemBytes, h->s_compute>>>(a);
   h->launches++;
   PWS_CUDA(h, cudaGetLastError());
   cudaEventRecord(e1, h->s_compute);
@@ -1026,8 +1036,11 @@ extern "C" int pws_column_kernel_info(pws_handle* h, int* regs, int* local_bytes
   cudaFuncAttributes at{};
   PWS_CUDA(h, cudaFuncGetAttributes(&at, k_hru_column));
   int nb = 0;
+  if (kColumnSmemBytes > 48 * 1024)
+    PWS_CUDA(h, cudaFuncSetAttribute(k_hru_column, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)kColumnSmemBytes));
   PWS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_hru_column,
-                                                            PWS_COLUMN_THREADS, 0));
+                                                            PWS_COLUMN_THREADS, kColumnSmemBytes));
   if (regs) *regs = at.numRegs;
   if (local_bytes) *local_bytes = (int)at.localSizeBytes;
   if (max_blocks_per_sm) *max_blocks_per_sm = nb;

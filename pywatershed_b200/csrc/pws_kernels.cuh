@@ -73,23 +73,25 @@ struct ColumnArgs {
   double* hru_lat;          // [ndays][stride] lateral inflow per HRU (cfs) or null
   int* viol;                // [ndays][BUD_N] or null
   int* err;
-  short slot[PWS_N_HRU_VARS];  // output slot of each variable, -1 = not requested
+  // byte offset of each public variable's row inside one day of out_f64 /
+  // out_i32 (slot * ostride * sizeof), -1 = not requested
+  int64_t off[PWS_N_HRU_VARS];
 };
 
 struct GpuSink {
   const ColumnArgs& a;
-  double* pf;
-  int32_t* pi;
+  char* pf;
+  char* pi;
   double* plat;
   unsigned violmask;
   int errmask;
   __device__ __forceinline__ void f(int var, double v) {
-    const int sl = a.slot[var];
-    if (sl >= 0) __stcs(pf + (int64_t)sl * a.ostride, v);
+    const int64_t o = a.off[var];
+    if (o >= 0) __stcs(reinterpret_cast<double*>(pf + o), v);
   }
   __device__ __forceinline__ void i(int var, int v) {
-    const int sl = a.slot[var];
-    if (sl >= 0) __stcs(pi + (int64_t)sl * a.ostride, v);
+    const int64_t o = a.off[var];
+    if (o >= 0) __stcs(reinterpret_cast<int*>(pi + o), v);
   }
   __device__ __forceinline__ void viol(int proc, bool open) {
     if (open) violmask |= 1u << proc;
@@ -106,10 +108,37 @@ struct GpuSink {
 #ifndef PWS_COLUMN_MIN_BLOCKS
 #define PWS_COLUMN_MIN_BLOCKS 2
 #endif
+// 1: every per-HRU parameter column_day reads is staged once per launch (the
+// monthly ones once per month) in shared memory, one private column per
+// thread -- no inter-thread sharing, so no barrier.  0: read through L1/L2.
+#ifndef PWS_COLUMN_SMEM
+#define PWS_COLUMN_SMEM 1
+#endif
+
+constexpr int kDailyF64 = 0
+#define X(n) +1
+    PWS_DAILY_F64(X)
+#undef X
+    ;
+constexpr int kDailyMonF64 = 0
+#define X(n) +1
+    PWS_DAILY_MON_F64(X)
+#undef X
+    ;
+constexpr int kDailyI32 = 0
+#define X(n) +1
+    PWS_DAILY_I32(X) PWS_DAILY_MON_I32(X)
+#undef X
+    ;
+constexpr size_t kColumnSmemBytes =
+    PWS_COLUMN_SMEM ? (size_t)PWS_COLUMN_THREADS * ((kDailyF64 + kDailyMonF64) * 8 + kDailyI32 * 4)
+                    : 0;
 
 __global__ void __launch_bounds__(PWS_COLUMN_THREADS, PWS_COLUMN_MIN_BLOCKS)
 k_hru_column(const __grid_constant__ ColumnArgs a) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int T = PWS_COLUMN_THREADS;
+  const int tid = threadIdx.x;
+  const int64_t i = (int64_t)blockIdx.x * T + tid;
   const bool live = i < a.P.nhru;
   const int64_t ii = live ? i : a.P.nhru - 1;  // dead lanes shadow the last HRU, never store
   const int64_t S = a.P.stride;
@@ -119,6 +148,54 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
 #define X(name, kind) PWS_LOADST_##kind(name)
   PWS_HRU_STATE(X)
 #undef X
+
+#if PWS_COLUMN_SMEM
+  // Q: the parameter view column_day sees, indexed by tid.  Staged columns
+  // live in shared memory; anything else is the global array re-based so that
+  // [tid] is this thread's HRU.
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* const sp = reinterpret_cast<double*>(smem_raw);
+  int32_t* const spi = reinterpret_cast<int32_t*>(sp + (size_t)(kDailyF64 + kDailyMonF64) * T);
+  HruParams Q = a.P;
+  Q.stride = 0;  // monthly rows: only the current month is staged
+  {
+    int k = 0;
+#define X(n) sp[k * T + tid] = __ldg(a.P.n + ii); Q.n = sp + k * T; ++k;
+    PWS_DAILY_F64(X)
+#undef X
+    k = 0;
+#define X(n) spi[k * T + tid] = __ldg(a.P.n + ii); Q.n = spi + k * T; ++k;
+    PWS_DAILY_I32(X)
+#undef X
+  }
+  auto stage_month = [&](int month) {
+    const int64_t mo = (int64_t)(month - 1) * S + ii;
+    int k = kDailyF64;
+#define X(n) sp[k * T + tid] = __ldg(a.P.n + mo); ++k;
+    PWS_DAILY_MON_F64(X)
+#undef X
+    k = kDailyI32 - 1;
+#define X(n) spi[k * T + tid] = __ldg(a.P.n + mo);
+    PWS_DAILY_MON_I32(X)
+#undef X
+  };
+  {
+    int k = kDailyF64;
+#define X(n) Q.n = sp + k * T; ++k;
+    PWS_DAILY_MON_F64(X)
+#undef X
+    k = kDailyI32 - 1;
+#define X(n) Q.n = spi + k * T;
+    PWS_DAILY_MON_I32(X)
+#undef X
+  }
+  int staged_month = 0;
+  const int64_t pidx = tid;
+#else
+  const HruParams& Q = a.P;
+  const int64_t pidx = ii;
+#endif
+
   GpuSink out{a, nullptr, nullptr, nullptr, 0u, 0};
   // forcing prefetch: day d+1 is in flight while day d computes
   DayIn nxt;
@@ -131,6 +208,10 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
     nxt.potsw = __ldg(a.P.soltab_potsw + (int64_t)(c.x - 1) * S + ii);
     nxt.horad = __ldg(a.P.soltab_horad_potsw + (int64_t)(c.x - 1) * S + ii);
   }
+  const int64_t day_f64 = (int64_t)a.n_f64 * a.ostride * 8;
+  const int64_t day_i32 = (int64_t)a.n_i32 * a.ostride * 4;
+  out.pf = reinterpret_cast<char*>(a.out_f64 + ii);
+  out.pi = reinterpret_cast<char*>(a.out_i32 + ii);
   for (int d = 0; d < a.ndays; ++d) {
     const DayIn in = nxt;
     if (d + 1 < a.ndays) {
@@ -143,13 +224,19 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
       nxt.potsw = __ldg(a.P.soltab_potsw + (int64_t)(c.x - 1) * S + ii);
       nxt.horad = __ldg(a.P.soltab_horad_potsw + (int64_t)(c.x - 1) * S + ii);
     }
+#if PWS_COLUMN_SMEM
+    if (in.month != staged_month) {  // warp-uniform
+      stage_month(in.month);
+      staged_month = in.month;
+    }
+#endif
     out.violmask = 0u;
     if (live) {
-      out.pf = a.out_f64 + (int64_t)d * a.n_f64 * a.ostride + i;
-      out.pi = a.out_i32 + (int64_t)d * a.n_i32 * a.ostride + i;
       out.plat = a.hru_lat ? a.hru_lat + (int64_t)d * S + i : nullptr;
-      column_day(a.P, i, s, in, out);
+      column_day(Q, pidx, s, in, out);
     }
+    out.pf += day_f64;
+    out.pi += day_i32;
     if (a.viol != nullptr && __any_sync(0xffffffffu, out.violmask != 0u)) {
       for (int p = 0; p < BUD_CHANNEL; ++p) {
         const unsigned m = __ballot_sync(0xffffffffu, (out.violmask >> p) & 1u);
@@ -217,6 +304,7 @@ struct ChannelArgs {
 
 struct SegStatic {
   int tsi, ub, ue, hb, he, orig;
+  unsigned fire;  // bit h set: hour h+1 is a routing update, (h + 1) % tsi == 0 (:529)
   bool down;
   double ts, c0, c1, c2;
 };
@@ -229,6 +317,9 @@ __device__ __forceinline__ SegStatic seg_static(const ChannelArgs& a, int pos) {
   g.hb = a.hru_ptr[pos]; g.he = a.hru_ptr[pos + 1];
   g.down = a.has_down[pos] != 0;
   g.orig = a.orig[pos];
+  g.fire = 0u;
+  for (int h = 0; h < 24; ++h)
+    if (g.tsi < 0 || ((h + 1) % g.tsi) == 0) g.fire |= 1u << h;
   return g;
 }
 
@@ -270,9 +361,8 @@ __device__ __forceinline__ void route_day(const ChannelArgs& a, const SegStatic&
     seg_inflow += cur;
     inflow_ts += cur;
     cur_sum += up[h];
-    const bool fire = g.tsi < 0 ? true : ((h + 1) % g.tsi) == 0;
-    if (fire) {
-      inflow_ts /= g.ts;
+    if ((g.fire >> h) & 1u) {
+      if (g.ts != 1.0) inflow_ts /= g.ts;  // x / 1.0 == x exactly
       if (g.tsi > 0) outflow_ts = inflow_ts * g.c0 + seg_inflow0 * g.c1 + outflow_ts * g.c2;
       else outflow_ts = inflow_ts;
       seg_inflow0 = inflow_ts;
@@ -360,7 +450,7 @@ k_route_wavefront(const __grid_constant__ ChannelArgs a) {
         atomicOr(a.err, 16);
         break;
       }
-      __nanosleep(64);
+      __nanosleep(256);
     }
   }
   if (live) {

@@ -1,0 +1,440 @@
+"""Model: the time loop over the NHM process chain, behind the reference's
+Model API (pywatershed/base/model.py:31-755): same constructor styles, same
+`run / advance / calculate / output / finalize / initialize_netcdf`, processes
+reachable as `model.processes[ClassName][var]`.
+
+Differences that stay invisible to a caller:
+  * The chain is computed in *time blocks*: on the first `calculate()` of a
+    block the whole block runs on the GPU (pws_run_host: forcings staged
+    H2D in sub-blocks, outputs drained D2H asynchronously); the following days
+    are served from the drained block.  Public variables keep stable array
+    identities (the reference's tests check `id(proc.var)`), refreshed in
+    place for the current day.
+  * `Model.run()` uses the fast path: whole blocks go to netCDF with
+    `var[t0:t1, :] = block` instead of one write per variable per day.
+"""
+from __future__ import annotations
+
+import pathlib as pl
+from warnings import warn
+
+import numpy as np
+
+from . import processes as P
+from ._process_meta import PROCESS_META, VARIABLE_META
+from .control import Control
+from .engine import Engine, Registry
+from .parameters import Parameters, PrmsParameters, as_param_dict
+from .prms_files import read_cbh
+
+COLUMN_CHAIN = ("PRMSSolarGeometry", "PRMSAtmosphere", "PRMSCanopy", "PRMSSnow", "PRMSRunoff",
+                "PRMSSoilzone", "PRMSGroundwater")
+FORCINGS = ("prcp", "tmax", "tmin")
+BUDGET_INDEX = {"PRMSCanopy": 0, "PRMSSnow": 1, "PRMSRunoff": 2, "PRMSSoilzone": 3,
+                "PRMSGroundwater": 4, "PRMSChannel": 5}
+
+
+class Model:
+    def __init__(self, process_list_or_model_dict, control: Control = None,
+                 parameters=None, find_input_files: bool = True, write_control=False):
+        self.control = control
+        self.parameters = parameters
+        self._find_input_files = find_input_files
+        self._netcdf_initialized = False
+        self._netcdf = None
+        proc_classes, proc_kwargs = self._parse_spec(process_list_or_model_dict)
+        names = [c.__name__ for c in proc_classes]
+        order = [n for n in P.PROCESS_ORDER_NHM if n in names]  # base/model.py:294-317
+        unknown = [n for n in names if n not in P.PROCESS_ORDER_NHM]
+        if unknown:
+            raise NotImplementedError(f"processes outside the NHM chain: {unknown}")
+        if "input_dir" not in self.control.options and find_input_files:
+            # base/model.py:509-518
+            raise ValueError("Control object must have an input_dir specified in its options")
+        self._mode = self._classify(order)
+        self.processes = {}
+        for n in order:
+            cls = P.PROCESS_CLASSES[n]
+            kw = dict(proc_kwargs.get(n, {}))
+            dis = kw.pop("dis", None)
+            par = kw.pop("parameters", self.parameters)
+            proc = cls(self.control, dis, par, **kw)
+            proc._model = self
+            self.processes[n] = proc
+        self.process_order = order
+        self._param_dict = {}
+        for n in order:
+            self._param_dict.update(self.processes[n]._param_dict)
+        self._engine = None
+        self._forcings = None
+        self._block = None
+        self._block_t0 = 0
+        self._block_n = 0
+        self._block_viol = None
+        self._calculated_step = -1
+        self.block_days = int(self.control.options.get("block_days", 64) or 64)
+        if write_control:
+            self._write_control(write_control)
+
+    # ---------------------------------------------------------------- spec
+    def _parse_spec(self, spec):
+        if isinstance(spec, dict):
+            # model_dict style (base/model.py:56-120): {'control':..., 'dis_x':...,
+            # 'proc': {'class': C, 'parameters': p, 'dis': 'dis_x'}, 'model_order': [...]}
+            md = spec
+            ctl = [v for v in md.values() if isinstance(v, Control) or type(v).__name__ == "Control"]
+            if ctl:
+                self.control = ctl[0]
+            classes, kwargs = [], {}
+            keys = md.get("model_order", [k for k, v in md.items() if isinstance(v, dict) and "class" in v])
+            for k in keys:
+                d = md[k]
+                cls = d["class"]
+                cls = P.PROCESS_CLASSES[cls.__name__ if not isinstance(cls, str) else cls]
+                classes.append(cls)
+                kw = {kk: vv for kk, vv in d.items() if kk not in ("class",)}
+                if isinstance(kw.get("dis"), str):
+                    kw["dis"] = md[kw["dis"]]
+                kwargs[cls.__name__] = kw
+            if self.control is None:
+                raise ValueError("model_dict has no Control")
+            return classes, kwargs
+        classes = []
+        for c in spec:
+            name = c if isinstance(c, str) else c.__name__
+            if name not in P.PROCESS_CLASSES:
+                raise NotImplementedError(f"process {name} is outside the NHM chain")
+            classes.append(P.PROCESS_CLASSES[name])  # a reference class maps to ours by name
+        if self.control is None or self.parameters is None:
+            raise ValueError("a process list needs control= and parameters=")
+        return classes, {}
+
+    @staticmethod
+    def _classify(order):
+        has_col = [n in order for n in COLUMN_CHAIN]
+        if all(has_col):
+            return "chain+channel" if "PRMSChannel" in order else "chain"
+        if order == ["PRMSChannel"]:
+            return "channel"
+        raise NotImplementedError(
+            "pywatershed_b200 runs the fused NHM column (PRMSSolarGeometry, PRMSAtmosphere, "
+            "PRMSCanopy, PRMSSnow, PRMSRunoff, PRMSSoilzone, PRMSGroundwater), optionally followed "
+            f"by PRMSChannel, or PRMSChannel alone; got {order}")
+
+    @classmethod
+    def from_yaml(cls, yaml_file):
+        raise NotImplementedError("Model.from_yaml is not implemented in pywatershed_b200")
+
+    # ---------------------------------------------------------------- inputs
+    def _load_input(self, name, nunits):
+        """An 'adaptable' (base/adapter.py:143-190): ndarray [ntime, n], path to a CBH
+        ASCII / netCDF file, or None -> input_dir/<name>.{nc,cbh}."""
+        nt = self.control.n_times
+        src = None
+        for proc in self.processes.values():
+            v = proc._input_variables_dict.get(name)
+            if v is not None:
+                src = v
+        if src is None:
+            if not self._find_input_files:
+                raise ValueError(f"input '{name}' was not provided and find_input_files=False")
+            d = pl.Path(self.control.options["input_dir"])
+            for cand in (d / f"{name}.nc", d / f"{name}.cbh"):
+                if cand.exists():
+                    src = cand
+                    break
+            if src is None:
+                raise FileNotFoundError(f"no {name}.nc / {name}.cbh in {d}")
+        if hasattr(src, "data") and not isinstance(src, np.ndarray):  # adapter-like
+            arr, times = np.asarray(src.data), getattr(getattr(src, "_nc_read", None), "times", None)
+        elif isinstance(src, (str, pl.Path)):
+            src = pl.Path(src)
+            if src.suffix == ".cbh":
+                times, arr = read_cbh(src, nunits)
+            else:
+                times, arr = _read_netcdf_var(src, name)
+        else:
+            arr, times = np.asarray(src, dtype=np.float64), None
+        if times is not None:
+            times = np.asarray(times).astype("datetime64[s]")
+            i0 = np.where(times == self.control.start_time.astype("datetime64[s]"))[0]
+            if not len(i0):
+                raise ValueError("Control start_time is not in the input data time")
+            arr = arr[i0[0]:]
+        if arr.ndim != 2 or arr.shape[1] != nunits or arr.shape[0] < nt:
+            raise ValueError(f"input '{name}' must be [>= {nt}, {nunits}], got {arr.shape}")
+        return np.ascontiguousarray(arr[:nt], dtype=np.float64)
+
+    def _ensure_engine(self):
+        if self._engine is not None:
+            return
+        pd = self._param_dict
+        dprst = self.processes[self.process_order[-1]]._dprst_flag
+        for n in self.process_order:
+            f = getattr(self.processes[n], "_dprst_flag", None)
+            if f is not None:
+                dprst = f
+        if dprst is None:
+            dprst = True
+        if not dprst:
+            raise NotImplementedError("dprst_flag=False (the *NoDprst processes) is not implemented")
+        adj = True
+        for n in ("PRMSSoilzone", "PRMSChannel"):
+            if n in self.processes and self.processes[n]._adjust_parameters == "no":
+                adj = False
+        start = self.control.start_time
+        dev = int(self.control.options.get("device", 0) or 0)
+        if self._mode == "channel":
+            # the HRU column is not run; Engine still needs the HRU tables it validates
+            self._engine = Engine(pd, start, device=dev, channel=True)
+            nh = self._engine.nhru
+            self._forcings = {k: self._load_input(k, nh) for k in
+                              ("sroff_vol", "ssres_flow_vol", "gwres_flow_vol")}
+        else:
+            self._engine = Engine(pd, start, device=dev, channel=self._mode == "chain+channel",
+                                  adjust_parameters=adj)
+            nh = self._engine.nhru
+            self._forcings = {k: self._load_input(k, nh) for k in FORCINGS}
+        reg = self._engine.reg
+        hv = list(reg.hru_vars) if self._mode != "channel" else [
+            "channel_sroff_vol", "channel_ssres_flow_vol", "channel_gwres_flow_vol"]
+        sv = list(reg.seg_vars) if self._engine.nseg else []
+        if self._mode != "channel":
+            self._engine.select_outputs(hv, sv)
+            st = self._engine.soltab()
+            sg = self.processes["PRMSSolarGeometry"]
+            for k, v in st.items():
+                sg[k].data[:] = v
+        else:
+            self._engine.select_outputs([], sv)
+
+    # ---------------------------------------------------------------- blocks
+    def _compute_block(self, t0, n):
+        self._ensure_engine()
+        eng = self._engine
+        if eng.day != t0:
+            raise RuntimeError(f"engine is at day {eng.day}, block starts at {t0}")
+        if self._mode == "channel":
+            blk, viol = self._channel_block(t0, n)
+        else:
+            eng.set_block_days(min(n, 64))
+            f = self._forcings
+            blk, viol = eng.run_host(f["prcp"][t0:t0 + n], f["tmax"][t0:t0 + n], f["tmin"][t0:t0 + n])
+        self._block, self._block_t0, self._block_n, self._block_viol = blk, t0, n, viol
+        # all-time variables of Atmosphere: fill the rows of this block
+        if "PRMSAtmosphere" in self.processes:
+            atm = self.processes["PRMSAtmosphere"]
+            for var in atm.get_variables():
+                atm[var].data[t0:t0 + n] = blk[var]
+        dt = float(self.control.time_step / np.timedelta64(1, "D"))
+        for name, proc in self.processes.items():
+            if getattr(proc, "budget", None) is not None:
+                proc.budget.accumulate_block(blk, dt)
+
+    def _channel_block(self, t0, n):
+        import torch
+
+        eng = self._engine
+        f = self._forcings
+        hs = np.asarray(self._param_dict["hru_segment"]) - 1
+        vols = [f[k][t0:t0 + n] for k in ("sroff_vol", "ssres_flow_vol", "gwres_flow_vol")]
+        lat = np.zeros((n, eng.nseg))
+        ch = [np.where(hs[None, :] >= 0, v, 0.0) for v in vols]
+        contrib = (ch[0] + ch[1] + ch[2]) / 86400.0
+        for h in np.where(hs >= 0)[0]:  # HRU order, as prms_channel.py:396-421
+            lat[:, hs[h]] += contrib[:, h]
+        dev = torch.device("cuda", eng.device)
+        dl = torch.from_numpy(lat).to(dev)
+        out = torch.empty((n, len(eng.sel_seg), eng.nseg), dtype=torch.float64, device=dev)
+        torch.cuda.synchronize(dev)
+        eng.run_channel_device(n, dl.data_ptr(), out.data_ptr())
+        eng.day += n
+        o = out.cpu().numpy()
+        blk = {v: o[:, k, :] for k, v in enumerate(eng.sel_seg)}
+        blk.update({"channel_sroff_vol": ch[0], "channel_ssres_flow_vol": ch[1],
+                    "channel_gwres_flow_vol": ch[2]})
+        return blk, None
+
+    # ---------------------------------------------------------------- stepping
+    def advance(self):
+        """base/model.py:723-737"""
+        if self._engine is None:
+            self._ensure_engine()
+        self.control.advance()
+        for name in ("PRMSSolarGeometry", "PRMSAtmosphere"):
+            if name in self.processes:
+                proc = self.processes[name]
+                if name == "PRMSAtmosphere":
+                    self._ensure_block(self.control.itime_step)
+                for var in proc.get_variables():
+                    proc[var].advance()
+
+    def _ensure_block(self, it, limit=None):
+        if self._block is not None and self._block_t0 <= it < self._block_t0 + self._block_n:
+            return
+        remaining = self.control.n_times - it
+        n = min(self.block_days, remaining)
+        if limit is not None:
+            n = min(n, limit)
+        self._compute_block(it, n)
+
+    def calculate(self):
+        """base/model.py:739-743: after this call every process shows day itime_step."""
+        it = self.control.itime_step
+        if it < 0:
+            raise RuntimeError("advance() before calculate()")
+        self._ensure_block(it)
+        j = it - self._block_t0
+        blk = self._block
+        for name, proc in self.processes.items():
+            if proc._all_time:
+                continue
+            for var in proc.get_variables():
+                if var in blk:
+                    proc._vars[var][:] = blk[var][j]
+        if "PRMSRunoff" in self.processes and "PRMSSoilzone" not in self.processes:
+            pass
+        self._calculated_step = it
+        for name, proc in self.processes.items():
+            b = getattr(proc, "budget", None)
+            if b is None:
+                continue
+            nv = None
+            if self._block_viol is not None:
+                nv = int(self._block_viol[j, BUDGET_INDEX[name]])
+            b.calculate(nv)
+
+    def output(self):
+        """base/model.py:745-749"""
+        if self._netcdf is not None:
+            it = self.control.itime_step
+            self._netcdf.write_days(self, it, it + 1)
+
+    def finalize(self):
+        if self._netcdf is not None:
+            self._netcdf.close()
+            self._netcdf = None
+        self._netcdf_initialized = False
+
+    # ---------------------------------------------------------------- netcdf
+    def initialize_netcdf(self, output_dir=None, separate_files: bool = None,
+                          budget_args: dict = None, output_vars: list = None):
+        """base/model.py:644-676"""
+        from .netcdf_out import ModelNetcdfOutput
+
+        if self._netcdf_initialized:
+            warn("Model class previously initialized netcdf output", RuntimeWarning)
+            return
+        opts = self.control.options
+        output_dir = output_dir if output_dir is not None else opts.get("netcdf_output_dir")
+        if output_dir is None:
+            raise ValueError("no netcdf output_dir")
+        if separate_files is None:
+            separate_files = opts.get("netcdf_output_separate_files", True)
+        if output_vars is None:
+            output_vars = opts.get("netcdf_output_var_names")
+        self._ensure_engine()
+        self._netcdf = ModelNetcdfOutput(self, pl.Path(output_dir), separate_files, output_vars,
+                                         budget_args)
+        self._netcdf_initialized = True
+        for proc in self.processes.values():
+            proc._netcdf_initialized = True
+
+    def _initialize_netcdf_for(self, proc, output_dir=None, separate_files=None,
+                               budget_args=None, output_vars=None, **kw):
+        if not self._netcdf_initialized:
+            self.initialize_netcdf(output_dir, separate_files, budget_args, output_vars)
+
+    # ---------------------------------------------------------------- run
+    def run(self, netcdf_dir=None, finalize: bool = True, n_time_steps: int = None,
+            output_vars: list = None):
+        """base/model.py:678-721, time-blocked."""
+        if netcdf_dir:
+            self.initialize_netcdf(netcdf_dir, output_vars=output_vars)
+        if n_time_steps is None:
+            n_time_steps = self.control.n_times - (self.control.itime_step + 1)
+        self._ensure_engine()
+        done = 0
+        while done < n_time_steps:
+            it = self.control.itime_step + 1
+            self._ensure_block(it, limit=n_time_steps - done)
+            t1 = min(self._block_t0 + self._block_n, it + (n_time_steps - done))
+            nd = t1 - it
+            # budgets for the whole block: any violating day raises / warns as the
+            # reference would on that day
+            if self._block_viol is not None:
+                v = self._block_viol[it - self._block_t0:t1 - self._block_t0]
+                if v.any():
+                    bad_day = int(np.argwhere(v.any(axis=1))[0, 0])
+                    for _ in range(bad_day + 1):
+                        self.advance()
+                    self.calculate()  # raises ValueError / warns through Budget
+                    if self._netcdf is not None:
+                        self._netcdf.write_days(self, it, it + bad_day + 1)
+                    done += bad_day + 1
+                    continue
+            if self._netcdf is not None:
+                self._netcdf.write_days(self, it, t1)
+            for _ in range(nd):
+                self.control.advance()
+            for name in ("PRMSSolarGeometry", "PRMSAtmosphere"):
+                if name in self.processes:
+                    for var in self.processes[name].get_variables():
+                        self.processes[name][var].advance()
+            self.calculate_last_only()
+            done += nd
+        if finalize:
+            self.finalize()
+
+    def calculate_last_only(self):
+        """Expose the last computed day in the process arrays (what a caller
+        inspecting the model after run() sees)."""
+        it = self.control.itime_step
+        j = it - self._block_t0
+        for name, proc in self.processes.items():
+            if proc._all_time:
+                continue
+            for var in proc.get_variables():
+                if var in self._block:
+                    proc._vars[var][:] = self._block[var][j]
+            b = getattr(proc, "budget", None)
+            if b is not None and self._block_viol is not None:
+                b._n_violations = int(self._block_viol[j, BUDGET_INDEX[name]])
+                b._zero_sum = b._n_violations == 0
+                b._itime_accumulated = it
+        self._calculated_step = it
+
+    def _write_control(self, where):
+        path = pl.Path(where) if not isinstance(where, bool) else pl.Path("control.yaml")
+        import yaml
+
+        opts = {k: (str(v) if isinstance(v, pl.Path) else v) for k, v in self.control.options.items()}
+        path.write_text(yaml.safe_dump({
+            "start_time": str(self.control.start_time), "end_time": str(self.control.end_time),
+            "time_step": str(self.control.time_step), "options": opts}))
+
+
+def _read_netcdf_var(path, name):
+    """[time, unit] variable + decoded times from a netCDF file (netCDF4 when
+    importable, scipy for classic files)."""
+    try:
+        import netCDF4 as nc4
+
+        with nc4.Dataset(path) as ds:
+            t = ds.variables["time"]
+            times = nc4.num2date(t[:], t.units, only_use_cftime_datetimes=False,
+                                 only_use_python_datetimes=True)
+            times = np.array(times, dtype="datetime64[s]")
+            return times, np.asarray(ds.variables[name][:], dtype=np.float64)
+    except ImportError:
+        from scipy.io import netcdf_file
+
+        with netcdf_file(str(path), "r", mmap=False) as ds:
+            t = ds.variables["time"]
+            units = t.units.decode() if isinstance(t.units, bytes) else t.units
+            unit, _, ref = units.partition(" since ")
+            ref = np.datetime64(ref.strip().replace(" ", "T"))
+            step = {"days": "D", "hours": "h", "seconds": "s"}[unit.strip()]
+            times = ref + (np.asarray(t[:]).astype(np.float64) * (
+                np.timedelta64(1, step) / np.timedelta64(1, "s"))).astype("timedelta64[s]")
+            return times.astype("datetime64[s]"), np.asarray(ds.variables[name][:], dtype=np.float64)

@@ -1,0 +1,196 @@
+"""netCDF output with the reference's layout (pywatershed/utils/netcdf_utils.py:356-697,
+base/process.py:463-592, base/budget.py:661-748):
+
+  <output_dir>/<var>.nc          separate_files=True (default)
+  <output_dir>/<Process>.nc      separate_files=False
+  <output_dir>/<Process>_budget.nc   inputs_sum / outputs_sum / storage_changes_sum
+
+dims `time` (unlimited) x `nhm_id` | `nhm_seg`; coordinate variables
+nhm_id / nhm_seg (i4) and time (f4, "days since 1970-01-01 00:00:00");
+variable attributes from the metadata; global attributes
+Description="pywatershed output data" and "process class".
+SolarGeometry / Atmosphere variables are all-time arrays written once per block
+with the same dims (their time axis is `doy` for the soltab tables).
+
+Backend: netCDF4 (zlib level 4, chunks (1, n), exactly the reference's files)
+when it is importable; otherwise scipy.io.netcdf_file, i.e. NetCDF-3 64-bit
+offset with the same names, dims, dtypes and attributes but no compression.
+Whole blocks are written with `var[t0:t1, :] = block`.
+"""
+from __future__ import annotations
+
+import pathlib as pl
+
+import numpy as np
+
+from ._process_meta import VARIABLE_META
+
+try:  # pragma: no cover - depends on the environment
+    import netCDF4 as _nc4
+except Exception:  # noqa: BLE001
+    _nc4 = None
+
+_NC_TYPES = {"float64": "f8", "int32": "i4", "bool": "i4", "int64": "i8"}
+
+
+class _File:
+    """One netCDF file holding one or more [time, unit] variables."""
+
+    def __init__(self, path: pl.Path, var_names, coord_name, coord_vals, process_name,
+                 time_name="time", n_doy=None):
+        self.path = path
+        self.vars = list(var_names)
+        self.coord_name = coord_name
+        self.time_name = time_name
+        path.parent.mkdir(parents=True, exist_ok=True)
+        if _nc4 is not None:
+            ds = _nc4.Dataset(path, "w", format="NETCDF4")
+            ds.setncattr("Description", "pywatershed output data")
+            ds.setncattr("process class", process_name)
+            ds.createDimension(time_name, n_doy)
+            ds.createDimension(coord_name, len(coord_vals))
+            tv = ds.createVariable(time_name, "f4", (time_name,))
+            if time_name == "time":
+                tv.units = "days since 1970-01-01 00:00:00"
+            cv = ds.createVariable(coord_name, "i4", (coord_name,))
+            cv[:] = np.asarray(coord_vals, dtype=np.int32)
+            self.v = {}
+            for name in self.vars:
+                m = VARIABLE_META.get(name, {})
+                v = ds.createVariable(name, _NC_TYPES[m.get("type", "float64")],
+                                      (time_name, coord_name), zlib=True, complevel=4,
+                                      chunksizes=(1, len(coord_vals)))
+                for k in ("desc", "units"):
+                    if k in m:
+                        v.setncattr(k, m[k])
+                self.v[name] = v
+        else:
+            from scipy.io import netcdf_file
+
+            ds = netcdf_file(str(path), "w", version=2)
+            ds.Description = "pywatershed output data"
+            setattr(ds, "process_class", process_name)
+            ds.createDimension(time_name, n_doy)
+            ds.createDimension(coord_name, len(coord_vals))
+            tv = ds.createVariable(time_name, "f4", (time_name,))
+            if time_name == "time":
+                tv.units = "days since 1970-01-01 00:00:00"
+            cv = ds.createVariable(coord_name, "i4", (coord_name,))
+            cv[:] = np.asarray(coord_vals, dtype=np.int32)
+            self.v = {}
+            for name in self.vars:
+                m = VARIABLE_META.get(name, {})
+                v = ds.createVariable(name, _NC_TYPES[m.get("type", "float64")],
+                                      (time_name, coord_name))
+                for k in ("desc", "units"):
+                    if k in m:
+                        setattr(v, k, m[k])
+                self.v[name] = v
+        self.ds = ds
+        self.tv = tv
+
+    def write(self, t0, t1, times_days, blocks: dict):
+        self.tv[t0:t1] = np.asarray(times_days, dtype=np.float32)
+        for name, arr in blocks.items():
+            if name in self.v:
+                a = np.asarray(arr)
+                if a.dtype == np.bool_:
+                    a = a.astype(np.int32)
+                self.v[name][t0:t1, :] = a
+
+    def close(self):
+        self.ds.close()
+
+
+class ModelNetcdfOutput:
+    def __init__(self, model, output_dir: pl.Path, separate_files: bool, output_vars, budget_args):
+        self.model = model
+        self.dir = pl.Path(output_dir)
+        self.files = []
+        self.budget_files = {}
+        pd = model._param_dict
+        nhm_id = np.asarray(pd.get("nhm_id", np.arange(1, model._engine.nhru + 1)))
+        nhm_seg = np.asarray(pd.get("nhm_seg", np.arange(1, max(model._engine.nseg, 1) + 1)))
+        self._written_static = False
+        for pname, proc in model.processes.items():
+            names = [v for v in proc.get_variables() if output_vars is None or v in output_vars]
+            if not names:
+                continue
+            doy = pname == "PRMSSolarGeometry"
+            groups = [[v] for v in names] if separate_files else [names]
+            for g in groups:
+                seg = "nsegment" in VARIABLE_META[g[0]]["dims"]
+                same = [v for v in g if ("nsegment" in VARIABLE_META[v]["dims"]) == seg]
+                rest = [v for v in g if v not in same]
+                for part in (same, rest):
+                    if not part:
+                        continue
+                    pseg = "nsegment" in VARIABLE_META[part[0]]["dims"]
+                    fname = f"{part[0]}.nc" if separate_files else (
+                        f"{pname}.nc" if part is same else f"{pname}_seg.nc")
+                    self.files.append((pname, doy, _File(
+                        self.dir / fname, part, "nhm_seg" if pseg else "nhm_id",
+                        nhm_seg if pseg else nhm_id, pname,
+                        time_name="doy" if doy else "time", n_doy=366 if doy else None)))
+            b = getattr(proc, "budget", None)
+            if b is not None:
+                self.budget_files[pname] = _BudgetFile(self.dir / f"{pname}_budget.nc", pname, b,
+                                                       nhm_seg if False else nhm_id)
+
+    def write_days(self, model, t0, t1):
+        """Write days [t0, t1) of the model's current block."""
+        blk, b0 = model._block, model._block_t0
+        start = model.control.start_time.astype("datetime64[D]")
+        epoch = np.datetime64("1970-01-01", "D")
+        tdays = (start - epoch).astype(int) + np.arange(t0, t1)
+        for pname, doy, f in self.files:
+            if doy:
+                if not self._written_static:
+                    sg = model.processes[pname]
+                    f.write(0, 366, np.arange(1, 367), {v: sg[v].data for v in f.vars})
+                continue
+            f.write(t0, t1, tdays, {v: blk[v][t0 - b0:t1 - b0] for v in f.vars if v in blk})
+        self._written_static = True
+        for pname, bf in self.budget_files.items():
+            bf.write(t0, t1, tdays, blk, t0 - b0, t1 - b0)
+
+    def close(self):
+        for _, _, f in self.files:
+            f.close()
+        for bf in self.budget_files.values():
+            bf.close()
+
+
+class _BudgetFile:
+    """<Process>_budget.nc: the three component sums per unit (or per domain
+    for a global-basis budget), base/budget.py:661-748."""
+
+    def __init__(self, path, pname, budget, nhm_id):
+        self.budget = budget
+        self.glob = budget.basis == "global"
+        coord = np.array([0]) if self.glob else nhm_id
+        self.f = _File(path, [], "one" if self.glob else "nhm_id", coord, pname)
+        ds = self.f.ds
+        self.v = {}
+        for name in ("inputs_sum", "outputs_sum", "storage_changes_sum"):
+            if _nc4 is not None:
+                self.v[name] = ds.createVariable(name, "f8", ("time", self.f.coord_name))
+            else:
+                self.v[name] = ds.createVariable(name, "f8", ("time", self.f.coord_name))
+
+    def write(self, t0, t1, tdays, blk, j0, j1):
+        self.f.tv[t0:t1] = np.asarray(tdays, dtype=np.float32)
+        for comp, name in (("inputs", "inputs_sum"), ("outputs", "outputs_sum"),
+                           ("storage_changes", "storage_changes_sum")):
+            terms = [np.asarray(blk[v][j0:j1], dtype=np.float64) for v in self.budget.terms[comp]
+                     if v in blk]
+            if not terms:
+                continue
+            if self.glob:
+                tot = sum(t.sum(axis=1) for t in terms)[:, None]
+            else:
+                tot = sum(terms)
+            self.v[name][t0:t1, :] = tot
+
+    def close(self):
+        self.f.close()

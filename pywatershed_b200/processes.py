@@ -1,0 +1,353 @@
+"""The eight PRMS/NHM process classes with the reference's constructor
+signatures, static descriptors and public variable names
+(pywatershed/base/process.py:19-592, conservative_process.py:13-210 and the
+per-process files cited on each class).
+
+On the reference a process computes itself in `calculate()`; here the whole
+vertical column runs fused on the GPU, so a process object is a *view*: its
+public variables are stable numpy arrays (same names, dtypes and shapes as the
+reference) that the owning Model refreshes for the current day, plus a Budget.
+`calc_method` accepts "cuda" (default); "numpy"/"numba" name CPU paths this
+package does not have and raise.
+"""
+from __future__ import annotations
+
+import pathlib as pl
+from warnings import warn
+
+import numpy as np
+
+from ._process_meta import PROCESS_META, VARIABLE_META
+from .budget import Budget
+
+_DTYPES = {"float64": np.float64, "int32": np.int32, "bool": np.bool_, "int64": np.int64}
+
+
+class TimeseriesArray:
+    """All-time variable with a `.current` row (base/timeseries.py:8-70).
+
+    `.data` is [ntime or 366, nhru]; rows are filled as blocks are computed
+    (SolarGeometry tables are complete from the start)."""
+
+    def __init__(self, control, var_name, array, doy_indexed=False):
+        self.name = "TimeseriresArray"
+        self.control = control
+        self.variable_name = var_name
+        self.data = array
+        self._doy = doy_indexed
+        self._current = self.data[0, :].copy()
+
+    def advance(self):
+        if self._doy:
+            ind = self.control.current_doy - 1
+        else:
+            ind = max(self.control.itime_step, 0)
+        self._current[:] = self.data[ind, :]
+
+    @property
+    def current(self):
+        return self._current
+
+
+class Process:
+    """Base class: self-describing, variables allocated from metadata."""
+
+    _all_time = False  # SolarGeometry / Atmosphere keep [ntime, nhru] arrays
+
+    def __init__(self, control, discretization, parameters, **kwargs):
+        self.name = type(self).__name__
+        self.control = control
+        self.discretization = discretization
+        self._params_in = parameters
+        self._model = None
+        meta = PROCESS_META[self.name]
+        from .parameters import Parameters, as_param_dict
+
+        merged = {}
+        for p in (discretization, parameters):
+            if p is not None:
+                merged.update(as_param_dict(p))
+        # declared by the reference but never read on this path (gwstor_min,
+        # tosegment_nhm, obsin_segment, ... ) are not required
+        from . import engine as _e
+
+        used = set(_e.HRU_PARAMS_F64 + _e.MON_PARAMS_F64 + _e.HRU_PARAMS_I32 + _e.MON_PARAMS_I32
+                   + _e.SEG_PARAMS_F64 + _e.SEG_PARAMS_I32 + _e.SCALAR_OPTIONS
+                   + ("snarea_curve", "temp_units"))
+        missing = [k for k in meta["parameters"] if k not in merged and k in used]
+        if missing:
+            # base/process.py:233-237
+            raise ValueError(f"{self.name}: parameters missing: {sorted(missing)}")
+        self._param_dict = merged
+        self.params = parameters
+        self.nhru = int(np.asarray(merged["hru_area"]).shape[0]) if "hru_area" in merged else 0
+        self.nsegment = int(np.asarray(merged["tosegment"]).shape[0]) if "tosegment" in merged else 0
+        self._input_variables_dict = {k: kwargs.get(k) for k in meta["inputs"]}
+        self._vars = {}
+        self._netcdf_initialized = False
+        self._verbose = kwargs.get("verbose")
+        self._set_options(kwargs)
+        self._allocate()
+
+    # ---- descriptors (static in the reference, base/process.py:144-187)
+    @classmethod
+    def get_dimensions(cls) -> tuple:
+        return PROCESS_META[cls.__name__]["dimensions"]
+
+    @classmethod
+    def get_parameters(cls) -> tuple:
+        return PROCESS_META[cls.__name__]["parameters"]
+
+    @classmethod
+    def get_inputs(cls) -> tuple:
+        return PROCESS_META[cls.__name__]["inputs"]
+
+    @classmethod
+    def get_variables(cls) -> tuple:
+        return PROCESS_META[cls.__name__]["variables"]
+
+    @classmethod
+    def get_init_values(cls) -> dict:
+        return {k: (np.nan if v is None else v)
+                for k, v in PROCESS_META[cls.__name__]["init_values"].items()}
+
+    @classmethod
+    def get_restart_variables(cls) -> tuple:
+        return PROCESS_META[cls.__name__].get("restart_variables", ())
+
+    @classmethod
+    def description(cls) -> dict:
+        return {"class_name": cls.__name__, "mass_budget_terms": getattr(
+                    cls, "get_mass_budget_terms", lambda: None)(),
+                "inputs": cls.get_inputs(), "variables": cls.get_variables(),
+                "parameters": cls.get_parameters()}
+
+    @property
+    def dimensions(self):
+        return self.get_dimensions()
+
+    @property
+    def parameters(self):
+        return self.get_parameters()
+
+    @property
+    def inputs(self):
+        return self.get_inputs()
+
+    @property
+    def variables(self):
+        return self.get_variables()
+
+    @property
+    def init_values(self):
+        return self.get_init_values()
+
+    # ---- options: per-process kwargs override control (base/process.py:339-360)
+    def _set_options(self, kw):
+        opts = getattr(self.control, "options", {}) or {}
+        for name in ("budget_type", "calc_method", "dprst_flag", "adjust_parameters"):
+            val = kw.get(name)
+            if val is None and name in opts:
+                val = opts[name]
+            setattr(self, "_" + name, val)
+        cm = self._calc_method
+        if cm not in (None, "cuda"):
+            if cm in ("numpy", "numba", "fortran"):
+                raise ValueError(
+                    f"{self.name}: calc_method='{cm}' names a CPU path of the reference; "
+                    "pywatershed_b200 only has calc_method='cuda' (no CPU fallback)")
+            raise ValueError(f"{self.name}: invalid calc_method '{cm}'")
+        self._calc_method = "cuda"
+
+    def _n_units(self, var):
+        dims = VARIABLE_META[var]["dims"]
+        return self.nsegment if "nsegment" in dims else self.nhru
+
+    def _allocate(self):
+        init = self.get_init_values()
+        for var in self.get_variables():
+            dt = _DTYPES[VARIABLE_META[var]["type"]]
+            n = self._n_units(var)
+            fill = init[var]
+            if dt is not np.float64 and (fill is None or (isinstance(fill, float) and np.isnan(fill))):
+                fill = 0
+            self._vars[var] = np.full(n, fill, dtype=dt)
+
+    # ---- access (base/accessor.py:1-15)
+    def __getitem__(self, key):
+        if key in self._vars:
+            return self._vars[key]
+        if key in self._param_dict:
+            return self._param_dict[key]
+        return getattr(self, key)
+
+    def __getattr__(self, key):
+        d = self.__dict__
+        if "_vars" in d and key in d["_vars"]:
+            return d["_vars"][key]
+        if "_param_dict" in d and key in d["_param_dict"]:
+            return d["_param_dict"][key]
+        raise AttributeError(key)
+
+    def set_input_to_adapter(self, input_variable_name: str, adapter):
+        self._input_variables_dict[input_variable_name] = adapter
+
+    # ---- stepping: only meaningful under a Model that owns the engine
+    def _need_model(self):
+        if self._model is None:
+            raise NotImplementedError(
+                f"{self.name} computes inside the fused GPU column: build a pywatershed_b200.Model "
+                "with the NHM chain (or PRMSChannel alone) and step the model; stand-alone "
+                "stepping of a single HRU process is not implemented yet")
+
+    def advance(self):
+        self._need_model()
+
+    def calculate(self, time_length: float = 1.0, **kwargs):
+        self._need_model()
+
+    def output(self):
+        self._need_model()
+
+    def finalize(self):
+        pass
+
+    def initialize_netcdf(self, *args, **kwargs):
+        self._need_model()
+        if self._netcdf_initialized:
+            warn(f"{self.name} class previously initialized netcdf output", RuntimeWarning)
+            return
+        self._model._initialize_netcdf_for(self, *args, **kwargs)
+        self._netcdf_initialized = True
+
+
+class ConservativeProcess(Process):
+    _budget_basis = "unit"
+
+    def __init__(self, control, discretization, parameters, **kwargs):
+        super().__init__(control, discretization, parameters, **kwargs)
+        terms = self.get_mass_budget_terms()
+        self.budget = None
+        if self._budget_type is not None:
+            self.budget = Budget(control, self, terms, self._budget_type, basis=self._budget_basis,
+                                 description=self.name)
+
+    @classmethod
+    def get_mass_budget_terms(cls) -> dict:
+        return PROCESS_META[cls.__name__]["mass_budget_terms"]
+
+
+# --------------------------------------------------------------------------
+class PRMSSolarGeometry(Process):
+    """atmosphere/prms_solar_geometry.py:60-68"""
+    _all_time = True
+
+    def __init__(self, control, discretization, parameters, verbose: bool = None,
+                 from_prms_file=None, from_nc_files_dir=None):
+        if from_prms_file is not None or from_nc_files_dir is not None:
+            raise NotImplementedError("PRMSSolarGeometry from files is not implemented: the "
+                                      "tables are computed (pws_init)")
+        super().__init__(control, discretization, parameters, verbose=verbose)
+
+    def _allocate(self):
+        for var in self.get_variables():
+            self._vars[var] = TimeseriesArray(
+                self.control, var, np.full((366, self.nhru), np.nan), doy_indexed=True)
+
+
+class PRMSAtmosphere(Process):
+    """atmosphere/prms_atmosphere.py:88-99"""
+    _all_time = True
+
+    def __init__(self, control, discretization, parameters, prcp=None, tmax=None, tmin=None,
+                 soltab_potsw=None, soltab_horad_potsw=None, verbose: bool = None):
+        super().__init__(control, discretization, parameters, prcp=prcp, tmax=tmax, tmin=tmin,
+                         soltab_potsw=soltab_potsw, soltab_horad_potsw=soltab_horad_potsw,
+                         verbose=verbose)
+
+    def _allocate(self):
+        nt = self.control.n_times
+        init = self.get_init_values()
+        for var in self.get_variables():
+            dt = _DTYPES[VARIABLE_META[var]["type"]]
+            fill = init[var]
+            if dt is not np.float64 and isinstance(fill, float) and np.isnan(fill):
+                fill = 0
+            self._vars[var] = TimeseriesArray(self.control, var, np.full((nt, self.nhru), fill, dtype=dt))
+
+
+class PRMSCanopy(ConservativeProcess):
+    """hydrology/prms_canopy.py:67-83"""
+
+    def __init__(self, control, discretization, parameters, pk_ice_prev=None, freeh2o_prev=None,
+                 transp_on=None, hru_ppt=None, hru_rain=None, hru_snow=None, potet=None,
+                 pptmix=None, budget_type=None, calc_method=None, verbose: bool = None):
+        super().__init__(control, discretization, parameters, **_kw(locals()))
+
+
+class PRMSSnow(ConservativeProcess):
+    """hydrology/prms_snow.py:122-145"""
+
+    def __init__(self, control, discretization, parameters, orad_hru=None, soltab_horad_potsw=None,
+                 swrad=None, hru_intcpevap=None, hru_ppt=None, potet=None, pptmix=None, prmx=None,
+                 tavgc=None, tmaxc=None, tminc=None, net_ppt=None, net_rain=None, net_snow=None,
+                 transp_on=None, budget_type=None, calc_method=None, verbose: bool = None):
+        super().__init__(control, discretization, parameters, **_kw(locals()))
+
+
+class PRMSRunoff(ConservativeProcess):
+    """hydrology/prms_runoff.py:77-100"""
+
+    def __init__(self, control, discretization, parameters, soil_lower_prev=None,
+                 soil_rechr_prev=None, net_ppt=None, net_rain=None, net_snow=None, potet=None,
+                 snowmelt=None, snow_evap=None, pkwater_equiv=None, pptmix_nopack=None,
+                 snowcov_area=None, through_rain=None, hru_intcpevap=None, intcp_changeover=None,
+                 dprst_flag: bool = None, budget_type=None, calc_method=None,
+                 verbose: bool = None):
+        super().__init__(control, discretization, parameters, **_kw(locals()))
+
+
+class PRMSSoilzone(ConservativeProcess):
+    """hydrology/prms_soilzone.py:81-102"""
+
+    def __init__(self, control, discretization, parameters, dprst_evap_hru=None,
+                 dprst_seep_hru=None, hru_impervevap=None, hru_intcpevap=None, infil_hru=None,
+                 sroff=None, sroff_vol=None, potet=None, snow_evap=None, snowcov_area=None,
+                 transp_on=None, dprst_flag: bool = None, budget_type=None, calc_method=None,
+                 adjust_parameters="warn", verbose: bool = None):
+        if adjust_parameters not in ("warn", "error", "no"):
+            raise ValueError("adjust_parameters must be one of 'warn', 'error', 'no'")
+        super().__init__(control, discretization, parameters, **_kw(locals()))
+
+
+class PRMSGroundwater(ConservativeProcess):
+    """hydrology/prms_groundwater.py:52-64"""
+
+    def __init__(self, control, discretization, parameters, soil_to_gw=None, ssr_to_gw=None,
+                 dprst_seep_hru=None, dprst_flag: bool = None, budget_type=None,
+                 calc_method=None, verbose: bool = None):
+        super().__init__(control, discretization, parameters, **_kw(locals()))
+
+
+class PRMSChannel(ConservativeProcess):
+    """hydrology/prms_channel.py:92-104; global-basis budget (:115)"""
+    _budget_basis = "global"
+
+    def __init__(self, control, discretization, parameters, sroff_vol=None, ssres_flow_vol=None,
+                 gwres_flow_vol=None, budget_type=None, calc_method=None,
+                 adjust_parameters="warn", verbose: bool = None):
+        super().__init__(control, discretization, parameters, **_kw(locals()))
+
+
+def _kw(loc):
+    return {k: v for k, v in loc.items()
+            if k not in ("self", "control", "discretization", "parameters", "__class__")}
+
+
+PROCESS_CLASSES = {c.__name__: c for c in (
+    PRMSSolarGeometry, PRMSAtmosphere, PRMSCanopy, PRMSSnow, PRMSRunoff, PRMSSoilzone,
+    PRMSGroundwater, PRMSChannel)}
+
+# base/model.py:15-28
+PROCESS_ORDER_NHM = ("PRMSSolarGeometry", "PRMSAtmosphere", "PRMSCanopy", "PRMSSnow",
+                     "PRMSRunoff", "PRMSSoilzone", "PRMSEt", "PRMSGroundwater", "PRMSChannel")
