@@ -338,6 +338,17 @@ PWS_DEV bool compute_interflow(double coef_lin, double coef_sq, double ssres_in,
   return true;
 }
 
+// x / ts for ts in {2, 3, 4, 6, 8, 12, 24} with the correctly rounded
+// reciprocal r: q = RN(x r), q' = RN(q + RN(x - ts q) r) is the correctly
+// rounded quotient (Markstein), i.e. bit-identical to the reference's
+// division, in three dependent instructions instead of the division
+// subroutine (checked exhaustively-at-random in tests/test_column_host.py::test_div_by_ts_is_the_division).
+PWS_HD double div_by_ts(double x, double ts, double r) {
+  const double q = x * r;
+  const double rem = fma(-q, ts, x);
+  return fma(rem, r, q);
+}
+
 constexpr double kPi = 3.141592653589793;
 
 // ---------------------------------------------------------------- soltab
@@ -588,9 +599,13 @@ PWS_DEV int hru_init_one(const HruParams& P, const HruDerivedMut& D, double* sta
 
 // ------------------------------------------------------------------------
 // One HRU, one day.  `i` indexes the SoA arrays.  `out` receives every public
-// variable (out.f / out.i), budget closure flags (out.viol), the lateral
-// inflow contribution (out.lateral) and device-side error flags (out.error).
+// variable (PWS_F / PWS_I: the variable is a template argument of the sink's
+// f<V_x>() / i<V_x>(), so a sink can turn it into a compile-time address),
+// budget closure flags (out.viol), the lateral inflow contribution
+// (out.lateral) and device-side error flags (out.error).
 // ------------------------------------------------------------------------
+#define PWS_F(var, val) out.template f<V_##var>(val)
+#define PWS_I(var, val) out.template i<V_##var>(val)
 template <class Sink>
 PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
                         const DayIn& in, Sink& out) {
@@ -690,12 +705,12 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
     }
   }
   const int transp_on = s.transp_on;
-  out.f(V_tmaxf, tmaxf); out.f(V_tminf, tminf); out.f(V_prmx, prmx);
-  out.f(V_hru_ppt, hru_ppt); out.f(V_hru_rain, hru_rain); out.f(V_hru_snow, hru_snow);
-  out.f(V_swrad, swrad); out.f(V_potet, potet); out.i(V_transp_on, transp_on);
-  out.f(V_tmaxc, tmaxc); out.f(V_tavgc, tavgc); out.f(V_tminc, tminc);
-  out.i(V_pptmix, pptmix);  // the all-time value Atmosphere writes to file
-  out.f(V_orad_hru, orad_hru);
+  PWS_F(tmaxf, tmaxf); PWS_F(tminf, tminf); PWS_F(prmx, prmx);
+  PWS_F(hru_ppt, hru_ppt); PWS_F(hru_rain, hru_rain); PWS_F(hru_snow, hru_snow);
+  PWS_F(swrad, swrad); PWS_F(potet, potet); PWS_I(transp_on, transp_on);
+  PWS_F(tmaxc, tmaxc); PWS_F(tavgc, tavgc); PWS_F(tminc, tminc);
+  PWS_I(pptmix, pptmix);  // the all-time value Atmosphere writes to file
+  PWS_F(orad_hru, orad_hru);
 
   // ===================== PRMSCanopy ======================================
   const double covden_sum = PWS_LD(P.covden_sum + i);
@@ -790,17 +805,17 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
     s.hru_intcpstor = intcpstor * cov;
     hru_intcpevap = intcpevap * cov;
     intcp_changeover = changeover + extra_water;
-    out.f(V_intcp_evap, intcpevap);
-    out.i(V_intcp_form, intcp_form);
+    PWS_F(intcp_evap, intcpevap);
+    PWS_I(intcp_form, intcp_form);
   }
   const double net_ppt = net_rain + net_snow;
   const double hru_intcpstor_change = s.hru_intcpstor - hru_intcpstor_old;
-  out.f(V_net_ppt, net_ppt); out.f(V_net_rain, net_rain); out.f(V_net_snow, net_snow);
-  out.f(V_intcp_changeover, intcp_changeover); out.f(V_intcp_stor, s.intcp_stor);
-  out.i(V_intcp_transp_on, s.intcp_transp_on); out.f(V_hru_intcpevap, hru_intcpevap);
-  out.f(V_hru_intcpstor, s.hru_intcpstor);
-  out.f(V_hru_intcpstor_change, hru_intcpstor_change);
-  out.f(V_hru_intcpstor_old, hru_intcpstor_old);
+  PWS_F(net_ppt, net_ppt); PWS_F(net_rain, net_rain); PWS_F(net_snow, net_snow);
+  PWS_F(intcp_changeover, intcp_changeover); PWS_F(intcp_stor, s.intcp_stor);
+  PWS_I(intcp_transp_on, s.intcp_transp_on); PWS_F(hru_intcpevap, hru_intcpevap);
+  PWS_F(hru_intcpstor, s.hru_intcpstor);
+  PWS_F(hru_intcpstor_change, hru_intcpstor_change);
+  PWS_F(hru_intcpstor_old, hru_intcpstor_old);
   out.viol(BUD_CANOPY,
            budget_open(0 + hru_rain + hru_snow,
                        (0 + net_rain + net_snow + hru_intcpevap + intcp_changeover) +
@@ -1152,21 +1167,21 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
     if (cond1 && cond2) through_rain = net_rain;
     if (cond1 && cond6 && cond7) through_rain = 0.0;
   }
-  out.f(V_ai, ai); out.f(V_albedo, s.albedo); out.f(V_frac_swe, frac_swe);
-  out.f(V_freeh2o, s.freeh2o); out.f(V_freeh2o_change, freeh2o_change);
-  out.f(V_freeh2o_prev, freeh2o_prev); out.i(V_iasw, s.iasw);
-  out.i(V_int_alb, s.int_alb); out.i(V_iso, s.iso); out.i(V_lso, s.lso);
-  out.i(V_lst, s.lst); out.i(V_mso, s.mso); out.i(V_newsnow, newsnow);
-  out.f(V_pk_def, s.pk_def); out.f(V_pk_den, s.pk_den); out.f(V_pk_depth, s.pk_depth);
-  out.f(V_pk_ice, s.pk_ice); out.f(V_pk_ice_change, pk_ice_change);
-  out.f(V_pk_ice_prev, pk_ice_prev); out.f(V_pk_precip, pk_precip);
-  out.f(V_pk_temp, s.pk_temp); out.f(V_pksv, s.pksv);
-  out.f(V_pkwater_equiv, s.pkwater_equiv); out.i(V_pptmix_nopack, pptmix_nopack);
-  out.f(V_pss, s.pss); out.f(V_pst, s.pst); out.f(V_salb, s.salb);
-  out.f(V_scrv, s.scrv); out.f(V_slst, s.slst); out.f(V_snow_evap, snow_evap);
-  out.f(V_snowcov_area, s.snowcov_area); out.f(V_snowcov_areasv, s.snowcov_areasv);
-  out.f(V_snowmelt, snowmelt); out.f(V_snsv, s.snsv); out.f(V_tcal, tcal);
-  out.f(V_through_rain, through_rain);
+  PWS_F(ai, ai); PWS_F(albedo, s.albedo); PWS_F(frac_swe, frac_swe);
+  PWS_F(freeh2o, s.freeh2o); PWS_F(freeh2o_change, freeh2o_change);
+  PWS_F(freeh2o_prev, freeh2o_prev); PWS_I(iasw, s.iasw);
+  PWS_I(int_alb, s.int_alb); PWS_I(iso, s.iso); PWS_I(lso, s.lso);
+  PWS_I(lst, s.lst); PWS_I(mso, s.mso); PWS_I(newsnow, newsnow);
+  PWS_F(pk_def, s.pk_def); PWS_F(pk_den, s.pk_den); PWS_F(pk_depth, s.pk_depth);
+  PWS_F(pk_ice, s.pk_ice); PWS_F(pk_ice_change, pk_ice_change);
+  PWS_F(pk_ice_prev, pk_ice_prev); PWS_F(pk_precip, pk_precip);
+  PWS_F(pk_temp, s.pk_temp); PWS_F(pksv, s.pksv);
+  PWS_F(pkwater_equiv, s.pkwater_equiv); PWS_I(pptmix_nopack, pptmix_nopack);
+  PWS_F(pss, s.pss); PWS_F(pst, s.pst); PWS_F(salb, s.salb);
+  PWS_F(scrv, s.scrv); PWS_F(slst, s.slst); PWS_F(snow_evap, snow_evap);
+  PWS_F(snowcov_area, s.snowcov_area); PWS_F(snowcov_areasv, s.snowcov_areasv);
+  PWS_F(snowmelt, snowmelt); PWS_F(snsv, s.snsv); PWS_F(tcal, tcal);
+  PWS_F(through_rain, through_rain);
   out.viol(BUD_SNOW, budget_open(0 + net_rain + net_snow,
                                  (0 + snow_evap + snowmelt + through_rain) +
                                      (0 + freeh2o_change + pk_ice_change)));
@@ -1404,24 +1419,24 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
   const double infil_hru = infil * perv_frac;
   const double hru_impervstor_change = s.hru_impervstor - hru_impervstor_old;
   const double dprst_stor_hru_change = dprst_stor_hru - dprst_stor_hru_old;
-  out.f(V_contrib_fraction, contrib_fraction); out.f(V_infil, infil);
-  out.f(V_infil_hru, infil_hru); out.f(V_hru_sroffp, hru_sroffp);
-  out.f(V_hru_sroffi, hru_sroffi); out.f(V_imperv_stor, s.imperv_stor);
-  out.f(V_imperv_evap, imperv_evap); out.f(V_hru_impervevap, hru_impervevap);
-  out.f(V_hru_impervstor, s.hru_impervstor);
-  out.f(V_hru_impervstor_old, hru_impervstor_old);
-  out.f(V_hru_impervstor_change, hru_impervstor_change);
-  out.f(V_dprst_vol_frac, dprst_on ? dprst_vol_frac : 0.0);
-  out.f(V_dprst_vol_clos, s.dprst_vol_clos); out.f(V_dprst_vol_open, s.dprst_vol_open);
-  out.f(V_dprst_vol_clos_frac, dprst_vol_clos_frac);
-  out.f(V_dprst_vol_open_frac, dprst_vol_open_frac);
-  out.f(V_dprst_area_clos, dprst_area_clos); out.f(V_dprst_area_open, s.dprst_area_open);
-  out.f(V_dprst_area_clos_max, PWS_LD(P.dprst_area_clos_max + i));
-  out.f(V_dprst_area_open_max, PWS_LD(P.dprst_area_open_max + i));
-  out.f(V_dprst_sroff_hru, dprst_sroff_hru); out.f(V_dprst_seep_hru, dprst_seep_hru);
-  out.f(V_dprst_evap_hru, dprst_evap_hru); out.f(V_dprst_insroff_hru, dprst_insroff_hru);
-  out.f(V_dprst_stor_hru, dprst_stor_hru); out.f(V_dprst_stor_hru_old, dprst_stor_hru_old);
-  out.f(V_dprst_stor_hru_change, dprst_stor_hru_change);
+  PWS_F(contrib_fraction, contrib_fraction); PWS_F(infil, infil);
+  PWS_F(infil_hru, infil_hru); PWS_F(hru_sroffp, hru_sroffp);
+  PWS_F(hru_sroffi, hru_sroffi); PWS_F(imperv_stor, s.imperv_stor);
+  PWS_F(imperv_evap, imperv_evap); PWS_F(hru_impervevap, hru_impervevap);
+  PWS_F(hru_impervstor, s.hru_impervstor);
+  PWS_F(hru_impervstor_old, hru_impervstor_old);
+  PWS_F(hru_impervstor_change, hru_impervstor_change);
+  PWS_F(dprst_vol_frac, dprst_on ? dprst_vol_frac : 0.0);
+  PWS_F(dprst_vol_clos, s.dprst_vol_clos); PWS_F(dprst_vol_open, s.dprst_vol_open);
+  PWS_F(dprst_vol_clos_frac, dprst_vol_clos_frac);
+  PWS_F(dprst_vol_open_frac, dprst_vol_open_frac);
+  PWS_F(dprst_area_clos, dprst_area_clos); PWS_F(dprst_area_open, s.dprst_area_open);
+  PWS_F(dprst_area_clos_max, PWS_LD(P.dprst_area_clos_max + i));
+  PWS_F(dprst_area_open_max, PWS_LD(P.dprst_area_open_max + i));
+  PWS_F(dprst_sroff_hru, dprst_sroff_hru); PWS_F(dprst_seep_hru, dprst_seep_hru);
+  PWS_F(dprst_evap_hru, dprst_evap_hru); PWS_F(dprst_insroff_hru, dprst_insroff_hru);
+  PWS_F(dprst_stor_hru, dprst_stor_hru); PWS_F(dprst_stor_hru_old, dprst_stor_hru_old);
+  PWS_F(dprst_stor_hru_change, dprst_stor_hru_change);
   out.viol(BUD_RUNOFF,
            budget_open(0 + through_rain + snowmelt + intcp_changeover,
                        (0 + hru_sroffi + hru_sroffp + dprst_sroff_hru + infil_hru +
@@ -1614,35 +1629,35 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
   const double sroff_vol = sroff * hru_in_to_cf;  // prms_soilzone.py:707
   double recharge = soil_to_gw + ssr_to_gw;
   if (P.dprst_flag) recharge = recharge + dprst_seep_hru;
-  out.f(V_sroff, sroff); out.f(V_sroff_vol, sroff_vol);
-  out.f(V_cap_infil_tot, cap_infil_tot); out.f(V_cap_waterin, cap_waterin);
-  out.f(V_dunnian_flow, dunnian_flow); out.f(V_hru_actet, hru_actet);
-  out.f(V_perv_actet, perv_actet); out.f(V_perv_actet_hru, perv_actet_hru);
-  out.f(V_potet_lower, potet_lower); out.f(V_potet_rechr, potet_rechr);
-  out.f(V_pref_flow, pref_flow); out.f(V_pref_flow_in, pref_flow_in);
-  out.f(V_pref_flow_infil, pref_flow_infil); out.f(V_pref_flow_max, pref_flow_max);
-  out.f(V_pref_flow_stor, s.pref_flow_stor);
-  out.f(V_pref_flow_stor_change, pref_flow_stor_change);
-  out.f(V_pref_flow_stor_prev, pref_flow_stor_prev);
-  out.f(V_pref_flow_thrsh, PWS_LD(P.pref_flow_thrsh + i));
-  out.f(V_recharge, recharge); out.f(V_slow_flow, slow_flow);
-  out.f(V_slow_stor, s.slow_stor); out.f(V_slow_stor_change, slow_stor_change);
-  out.f(V_slow_stor_prev, slow_stor_prev); out.f(V_soil_lower, soil_lower);
-  out.f(V_soil_lower_change, soil_lower_change);
-  out.f(V_soil_lower_change_hru, soil_lower_change_hru);
-  out.f(V_soil_lower_prev, soil_lower_prev);
-  out.f(V_soil_lower_ratio, soil_lower_max > 0.0 ? soil_lower / soil_lower_max
+  PWS_F(sroff, sroff); PWS_F(sroff_vol, sroff_vol);
+  PWS_F(cap_infil_tot, cap_infil_tot); PWS_F(cap_waterin, cap_waterin);
+  PWS_F(dunnian_flow, dunnian_flow); PWS_F(hru_actet, hru_actet);
+  PWS_F(perv_actet, perv_actet); PWS_F(perv_actet_hru, perv_actet_hru);
+  PWS_F(potet_lower, potet_lower); PWS_F(potet_rechr, potet_rechr);
+  PWS_F(pref_flow, pref_flow); PWS_F(pref_flow_in, pref_flow_in);
+  PWS_F(pref_flow_infil, pref_flow_infil); PWS_F(pref_flow_max, pref_flow_max);
+  PWS_F(pref_flow_stor, s.pref_flow_stor);
+  PWS_F(pref_flow_stor_change, pref_flow_stor_change);
+  PWS_F(pref_flow_stor_prev, pref_flow_stor_prev);
+  PWS_F(pref_flow_thrsh, PWS_LD(P.pref_flow_thrsh + i));
+  PWS_F(recharge, recharge); PWS_F(slow_flow, slow_flow);
+  PWS_F(slow_stor, s.slow_stor); PWS_F(slow_stor_change, slow_stor_change);
+  PWS_F(slow_stor_prev, slow_stor_prev); PWS_F(soil_lower, soil_lower);
+  PWS_F(soil_lower_change, soil_lower_change);
+  PWS_F(soil_lower_change_hru, soil_lower_change_hru);
+  PWS_F(soil_lower_prev, soil_lower_prev);
+  PWS_F(soil_lower_ratio, soil_lower_max > 0.0 ? soil_lower / soil_lower_max
                                                  : PWS_LD(P.soil_lower_ratio_init + i));
-  out.f(V_soil_lower_max, soil_lower_max); out.f(V_soil_moist, s.soil_moist);
-  out.f(V_soil_moist_tot, ssres_stor + s.soil_moist * hru_frac_perv);
-  out.f(V_soil_rechr, s.soil_rechr); out.f(V_soil_rechr_change, soil_rechr_change);
-  out.f(V_soil_rechr_change_hru, soil_rechr_change_hru);
-  out.f(V_soil_rechr_prev, soil_rechr_prev); out.f(V_soil_to_gw, soil_to_gw);
-  out.f(V_soil_to_ssr, soil_to_ssr); out.f(V_soil_zone_max, PWS_LD(P.soil_zone_max + i));
-  out.f(V_ssr_to_gw, ssr_to_gw); out.f(V_ssres_flow, ssres_flow);
-  out.f(V_ssres_flow_vol, ssres_flow_vol);
-  out.f(V_ssres_in, soil_to_ssr + pref_flow_infil + 0.0); out.f(V_ssres_stor, ssres_stor);
-  out.f(V_swale_actet, swale_actet); out.f(V_unused_potet, potet - hru_actet);
+  PWS_F(soil_lower_max, soil_lower_max); PWS_F(soil_moist, s.soil_moist);
+  PWS_F(soil_moist_tot, ssres_stor + s.soil_moist * hru_frac_perv);
+  PWS_F(soil_rechr, s.soil_rechr); PWS_F(soil_rechr_change, soil_rechr_change);
+  PWS_F(soil_rechr_change_hru, soil_rechr_change_hru);
+  PWS_F(soil_rechr_prev, soil_rechr_prev); PWS_F(soil_to_gw, soil_to_gw);
+  PWS_F(soil_to_ssr, soil_to_ssr); PWS_F(soil_zone_max, PWS_LD(P.soil_zone_max + i));
+  PWS_F(ssr_to_gw, ssr_to_gw); PWS_F(ssres_flow, ssres_flow);
+  PWS_F(ssres_flow_vol, ssres_flow_vol);
+  PWS_F(ssres_in, soil_to_ssr + pref_flow_infil + 0.0); PWS_F(ssres_stor, ssres_stor);
+  PWS_F(swale_actet, swale_actet); PWS_F(unused_potet, potet - hru_actet);
   out.viol(BUD_SOILZONE,
            budget_open(0 + infil_hru,
                        (0 + perv_actet_hru + soil_to_gw + ssr_to_gw + slow_flow +
@@ -1670,9 +1685,9 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
     gwres_stor_change = s.gwres_stor - gwres_stor_old;
     gwres_flow_vol = gwres_flow * hru_in_to_cf;
   }
-  out.f(V_gwres_flow, gwres_flow); out.f(V_gwres_flow_vol, gwres_flow_vol);
-  out.f(V_gwres_sink, gwres_sink); out.f(V_gwres_stor, s.gwres_stor);
-  out.f(V_gwres_stor_old, gwres_stor_old); out.f(V_gwres_stor_change, gwres_stor_change);
+  PWS_F(gwres_flow, gwres_flow); PWS_F(gwres_flow_vol, gwres_flow_vol);
+  PWS_F(gwres_sink, gwres_sink); PWS_F(gwres_stor, s.gwres_stor);
+  PWS_F(gwres_stor_old, gwres_stor_old); PWS_F(gwres_stor_change, gwres_stor_change);
   out.viol(BUD_GW, budget_open(0 + soil_to_gw + ssr_to_gw + dprst_seep_hru,
                                (0 + gwres_flow) + (0 + gwres_stor_change)));
 
@@ -1682,8 +1697,8 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
   const double ch_sroff = has_seg ? sroff_vol : 0.0;
   const double ch_ssres = has_seg ? ssres_flow_vol : 0.0;
   const double ch_gwres = has_seg ? gwres_flow_vol : 0.0;
-  out.f(V_channel_sroff_vol, ch_sroff); out.f(V_channel_ssres_flow_vol, ch_ssres);
-  out.f(V_channel_gwres_flow_vol, ch_gwres);
+  PWS_F(channel_sroff_vol, ch_sroff); PWS_F(channel_ssres_flow_vol, ch_ssres);
+  PWS_F(channel_gwres_flow_vol, ch_gwres);
   out.lateral((ch_sroff + ch_ssres + ch_gwres) / 86400.0);
 }
 

@@ -116,10 +116,13 @@ struct pws_handle {
   short slot_seg[PWS_N_SEG_VARS];
   int n_f64 = 0, n_i32 = 0, n_seg_sel = 0;
   // channel (level order)
-  int nlevels = 0;
-  std::vector<int> level_begin;  // [nlevels+1]
+  int nlevels = 0, nchunks = 0, n_cross_edges = 0, n_ext_rows = 0, max_dmax = 0;
+  int channel_chunk = PWS_CHUNK_THREADS;  // option: segments per routing chunk (<= CTA size)
   int32_t *d_tsi = nullptr, *d_up_ptr = nullptr, *d_up_idx = nullptr, *d_hru_ptr = nullptr,
-          *d_hru_idx = nullptr, *d_has_down = nullptr, *d_orig = nullptr;
+          *d_hru_idx = nullptr, *d_seg_flags = nullptr, *d_orig = nullptr,
+          *d_chunk_begin = nullptr, *d_chunk_dmax = nullptr, *d_delay = nullptr,
+          *d_ext_row = nullptr;
+  double* d_rts = nullptr;
   double *d_ts = nullptr, *d_c0 = nullptr, *d_c1 = nullptr, *d_c2 = nullptr;
   double *d_outflow_ts = nullptr, *d_seg_inflow = nullptr;
   // per-block scratch (sized for scratch_days)
@@ -128,9 +131,7 @@ struct pws_handle {
          *d_day_lat = nullptr;
   int4* d_cal = nullptr;
   int* d_viol = nullptr;
-  int* d_progress = nullptr;
-  int wavefront = 1;      // option: 1 = persistent wavefront routing when it fits
-  int wavefront_ok = -1;  // -1 unknown, 0 does not fit, 1 fits
+  int* d_progress = nullptr;  // [sstride] days published + 1 ticket counter at the end
   // host ring for pws_run_host
   int ring_days = 0;
   double* d_forc[2] = {nullptr, nullptr};
@@ -266,10 +267,13 @@ static void free_device(pws_handle* h) {
   for (auto& p : h->d_soltab) { cudaFree(p); p = nullptr; }
   cudaFree(h->d_snarea); h->d_snarea = nullptr;
   cudaFree(h->d_err); h->d_err = nullptr;
-  void* ch[] = {h->d_tsi, h->d_up_ptr, h->d_up_idx, h->d_hru_ptr, h->d_hru_idx, h->d_has_down,
-                h->d_orig, h->d_ts, h->d_c0, h->d_c1, h->d_c2, h->d_outflow_ts, h->d_seg_inflow};
+  void* ch[] = {h->d_tsi, h->d_up_ptr, h->d_up_idx, h->d_hru_ptr, h->d_hru_idx, h->d_seg_flags,
+                h->d_orig, h->d_chunk_begin, h->d_chunk_dmax, h->d_delay, h->d_ext_row, h->d_rts,
+                h->d_ts, h->d_c0, h->d_c1, h->d_c2, h->d_outflow_ts, h->d_seg_inflow};
   for (void* p : ch) cudaFree(p);
-  h->d_tsi = h->d_up_ptr = h->d_up_idx = h->d_hru_ptr = h->d_hru_idx = h->d_has_down = h->d_orig = nullptr;
+  h->d_tsi = h->d_up_ptr = h->d_up_idx = h->d_hru_ptr = h->d_hru_idx = h->d_seg_flags = h->d_orig =
+      h->d_chunk_begin = h->d_chunk_dmax = h->d_delay = h->d_ext_row = nullptr;
+  h->d_rts = nullptr;
   h->d_ts = h->d_c0 = h->d_c1 = h->d_c2 = h->d_outflow_ts = h->d_seg_inflow = nullptr;
   free_scratch(h);
   free_ring(h);
@@ -344,7 +348,11 @@ extern "C" int pws_set_option(pws_handle* h, const char* name, double value) {
   else if (!strcmp(name, "albset_snm")) h->albset[3] = value;
   else if (!strcmp(name, "block_days")) { h->block_days = (int)value; return 0; }
   else if (!strcmp(name, "soltab_device")) h->soltab_device = value != 0.0;
-  else if (!strcmp(name, "wavefront")) { h->wavefront = value != 0.0; return 0; }
+  else if (!strcmp(name, "channel_chunk")) {
+    if (value < 1 || value > PWS_CHUNK_THREADS)
+      PWS_FAIL(h, "pws_set_option: channel_chunk must be in 1..%d", PWS_CHUNK_THREADS);
+    h->channel_chunk = (int)value;
+  }
   else PWS_FAIL(h, "pws_set_option: unknown option '%s'", name);
   h->inited = false;
   return 0;
@@ -389,21 +397,129 @@ static int channel_build(pws_handle* h) {
   if ((int64_t)order.size() != nseg) PWS_FAIL(h, "pws_init: the segment graph has a cycle");
   int nlev = 0;
   for (int64_t i = 0; i < nseg; ++i) nlev = std::max(nlev, level[i] + 1);
-  // pos order: by (level, original index); rank in `order` kept for the
-  // accumulation order of upstream inflows
   std::vector<int> rank(nseg);
   for (int64_t k = 0; k < nseg; ++k) rank[order[k]] = (int)k;
+  h->nlevels = nlev;
+  // ---- chunks.  (1) Cut the forest into connected pieces of <= cap segments:
+  // walking upstream-first, a segment keeps its upstream subtrees until they
+  // no longer fit, then sheds the largest ones (each becomes a piece of its
+  // own).  Outlet trees that fit stay whole.
+  const int cap = h->channel_chunk;
+  std::vector<std::vector<int>> kids(nseg);
+  for (int k = 0; k < nseg; ++k) {
+    const int i = order[k];
+    if (toseg[i] > 0) kids[toseg[i] - 1].push_back(i);
+  }
+  std::vector<int> resid(nseg, 1);
+  std::vector<char> is_root(nseg, 0);
+  for (int k = 0; k < nseg; ++k) {
+    const int i = order[k];
+    int tot = 1;
+    for (int c : kids[i]) tot += resid[c];
+    if (tot > cap) {
+      std::vector<int> by = kids[i];
+      std::stable_sort(by.begin(), by.end(), [&](int x, int y) { return resid[x] > resid[y]; });
+      for (int c : by) {
+        if (tot <= cap) break;
+        is_root[c] = 1;
+        tot -= resid[c];
+      }
+    }
+    resid[i] = tot;
+    if (toseg[i] <= 0) is_root[i] = 1;
+  }
+  // (2) Number the pieces upstream-first (depth-first over the piece forest,
+  // outlets in original order) and pack them next-fit, so that a chunk only
+  // ever waits for chunks with a lower number.
+  std::vector<int> piece_of(nseg, -1), piece_size, piece_root;
+  {
+    // piece forest post-order: iterative DFS from each outlet
+    std::vector<int> root_order;  // piece roots, upstream pieces first
+    std::vector<std::pair<int, int>> stack;  // (root segment, state)
+    std::vector<std::vector<int>> piece_kids(nseg);  // piece root -> roots of upstream pieces
+    // a cut child c hangs below the piece that contains its downstream segment;
+    // find that piece's root by walking down until a root is met
+    std::vector<int> root_of(nseg, -1);
+    for (int k = (int)nseg - 1; k >= 0; --k) {  // downstream-first
+      const int i = order[k];
+      root_of[i] = is_root[i] ? i : root_of[toseg[i] - 1];
+    }
+    for (int k = 0; k < nseg; ++k) {
+      const int i = order[k];
+      if (is_root[i] && toseg[i] > 0) piece_kids[root_of[toseg[i] - 1]].push_back(i);
+    }
+    for (int64_t o = 0; o < nseg; ++o) {
+      if (toseg[o] > 0) continue;
+      stack.push_back({(int)o, 0});
+      while (!stack.empty()) {
+        auto& top = stack.back();
+        const int r = top.first;
+        if (top.second < (int)piece_kids[r].size()) {
+          const int nxt = piece_kids[r][top.second++];
+          stack.push_back({nxt, 0});
+        } else {
+          root_order.push_back(r);
+          stack.pop_back();
+        }
+      }
+    }
+    std::vector<int> pid_of_root(nseg, -1);
+    for (size_t k = 0; k < root_order.size(); ++k) {
+      pid_of_root[root_order[k]] = (int)k;
+      piece_root.push_back(root_order[k]);
+      piece_size.push_back(resid[root_order[k]]);
+    }
+    for (int64_t i = 0; i < nseg; ++i) piece_of[i] = pid_of_root[root_of[i]];
+  }
+  std::vector<int> chunk_of_piece(piece_size.size(), 0);
+  int nchunks = 0;
+  {
+    int fill = 0;
+    for (size_t p = 0; p < piece_size.size(); ++p) {
+      if (p == 0 || fill + piece_size[p] > cap) {
+        nchunks++;
+        fill = 0;
+      }
+      chunk_of_piece[p] = nchunks - 1;
+      fill += piece_size[p];
+    }
+  }
+  h->nchunks = nchunks;
+  std::vector<int> chunk_of(nseg);
+  for (int64_t i = 0; i < nseg; ++i) chunk_of[i] = chunk_of_piece[piece_of[i]];
+  // systolic delay: hops to the root of the chunk-local tree, counted from the
+  // deepest segment of the chunk, so a local upstream segment is one step ahead
+  std::vector<int> hops(nseg, 0), chunk_dmax_v(nchunks, 0), delay_v(nseg, 0);
+  for (int k = (int)nseg - 1; k >= 0; --k) {  // downstream-first
+    const int i = order[k];
+    const int to = toseg[i] - 1;
+    hops[i] = (to >= 0 && chunk_of[to] == chunk_of[i]) ? hops[to] + 1 : 0;
+    chunk_dmax_v[chunk_of[i]] = std::max(chunk_dmax_v[chunk_of[i]], hops[i]);
+  }
+  h->max_dmax = 0;
+  for (int64_t i = 0; i < nseg; ++i) {
+    delay_v[i] = chunk_dmax_v[chunk_of[i]] - hops[i];
+    h->max_dmax = std::max(h->max_dmax, chunk_dmax_v[chunk_of[i]]);
+  }
+  // pos order: by (chunk, delay mod 24, delay, original index), so the lanes
+  // of a warp cross their day boundaries in the same step; rank in `order`
+  // kept for the accumulation order of upstream inflows
   std::vector<int> bypos(nseg);
   for (int64_t i = 0; i < nseg; ++i) bypos[i] = (int)i;
-  std::stable_sort(bypos.begin(), bypos.end(), [&](int a, int b) { return level[a] < level[b]; });
+  std::stable_sort(bypos.begin(), bypos.end(), [&](int x, int y) {
+    if (chunk_of[x] != chunk_of[y]) return chunk_of[x] < chunk_of[y];
+    if (delay_v[x] % 24 != delay_v[y] % 24) return delay_v[x] % 24 < delay_v[y] % 24;
+    return delay_v[x] < delay_v[y];
+  });
   std::vector<int> pos_of(nseg);
   for (int64_t p = 0; p < nseg; ++p) pos_of[bypos[p]] = (int)p;
-  h->nlevels = nlev;
-  h->level_begin.assign(nlev + 1, 0);
-  for (int64_t i = 0; i < nseg; ++i) h->level_begin[level[i] + 1]++;
-  for (int l = 0; l < nlev; ++l) h->level_begin[l + 1] += h->level_begin[l];
+  std::vector<int32_t> chunk_begin(nchunks + 1, 0);
+  for (int64_t i = 0; i < nseg; ++i) chunk_begin[chunk_of[i] + 1]++;
+  for (int cidx = 0; cidx < nchunks; ++cidx) chunk_begin[cidx + 1] += chunk_begin[cidx];
   // coefficients
-  std::vector<int32_t> tsi(nseg), has_down(nseg), orig(nseg);
+  std::vector<int32_t> tsi(nseg), seg_flags(nseg, 0), orig(nseg), delay(nseg), ext_row(nseg, -1);
+  std::vector<double> rts(nseg);
+  h->n_ext_rows = 0;
   std::vector<double> ts(nseg), c0(nseg), c1(nseg), c2(nseg), seg_inflow(nseg, 0.0),
       outflow_ts(nseg, 0.0);
   for (int64_t p = 0; p < nseg; ++p) {
@@ -436,7 +552,13 @@ static int channel_build(pws_handle* h) {
     if (a2 < 0.0) { a1 += a2; a2 = 0.0; }
     if (a0 < 0.0) { a1 += a0; a0 = 0.0; }
     tsi[p] = tsiv; ts[p] = tsv; c0[p] = a0; c1[p] = a1; c2[p] = a2;
-    has_down[p] = toseg[i] > 0;
+    rts[p] = 1.0 / tsv;
+    delay[p] = delay_v[i];
+    if (toseg[i] > 0) {
+      seg_flags[p] |= SEG_HAS_DOWN;
+      if (chunk_of[toseg[i] - 1] == chunk_of[i]) seg_flags[p] |= SEG_DOWN_LOCAL;
+      else ext_row[p] = h->n_ext_rows++;
+    }
     orig[p] = i;
   }
   // initial _seg_inflow: assignment, not sum, in index order (prms_channel.py:336-340)
@@ -452,9 +574,18 @@ static int channel_build(pws_handle* h) {
     if (to >= 0) ups[pos_of[to]].push_back(pos_of[i]);
   }
   std::vector<int32_t> up_ptr(nseg + 1, 0), up_idx;
+  h->n_cross_edges = 0;
   for (int64_t p = 0; p < nseg; ++p) {
     up_ptr[p + 1] = up_ptr[p] + (int32_t)ups[p].size();
-    for (int u : ups[p]) up_idx.push_back(u);
+    bool all_local = true;
+    for (int u : ups[p]) {
+      up_idx.push_back(u);
+      if (chunk_of[bypos[u]] != chunk_of[bypos[p]]) {
+        all_local = false;
+        h->n_cross_edges++;
+      }
+    }
+    if (all_local) seg_flags[p] |= SEG_UPS_LOCAL;
   }
   // HRU CSR, ascending HRU index
   std::vector<std::vector<int>> hrus(nseg);
@@ -483,7 +614,15 @@ static int channel_build(pws_handle* h) {
   PWS_CUDA(h, up_i32(&h->d_up_idx, up_idx));
   PWS_CUDA(h, up_i32(&h->d_hru_ptr, hru_ptr));
   PWS_CUDA(h, up_i32(&h->d_hru_idx, hru_idx));
-  PWS_CUDA(h, up_i32(&h->d_has_down, has_down));
+  PWS_CUDA(h, up_i32(&h->d_seg_flags, seg_flags));
+  PWS_CUDA(h, up_i32(&h->d_chunk_begin, chunk_begin));
+  {
+    std::vector<int32_t> dm(chunk_dmax_v.begin(), chunk_dmax_v.end());
+    PWS_CUDA(h, up_i32(&h->d_chunk_dmax, dm));
+  }
+  PWS_CUDA(h, up_i32(&h->d_delay, delay));
+  PWS_CUDA(h, up_i32(&h->d_ext_row, ext_row));
+  PWS_CUDA(h, up_f64(&h->d_rts, rts));
   PWS_CUDA(h, up_i32(&h->d_orig, orig));
   PWS_CUDA(h, up_f64(&h->d_ts, ts));
   PWS_CUDA(h, up_f64(&h->d_c0, c0));
@@ -719,8 +858,8 @@ static int ensure_scratch(pws_handle* h, int ndays) {
   PWS_CUDA(h, cudaMalloc(&h->d_viol, T * BUD_N * sizeof(int)));
   if (h->nseg > 0) {
     PWS_CUDA(h, cudaMalloc(&h->d_hru_lat, T * h->stride * sizeof(double)));
-    PWS_CUDA(h, cudaMalloc(&h->d_ots, T * 24 * h->sstride * sizeof(double)));
-    PWS_CUDA(h, cudaMalloc(&h->d_progress, (size_t)h->sstride * sizeof(int)));
+    PWS_CUDA(h, cudaMalloc(&h->d_ots, T * 24 * std::max(h->n_ext_rows, 1) * sizeof(double)));
+    PWS_CUDA(h, cudaMalloc(&h->d_progress, (size_t)(h->sstride + 32) * sizeof(int)));
     PWS_CUDA(h, cudaMalloc(&h->d_day_outvol, T * h->sstride * sizeof(double)));
     PWS_CUDA(h, cudaMalloc(&h->d_day_dstor, T * h->sstride * sizeof(double)));
     PWS_CUDA(h, cudaMalloc(&h->d_day_lat, T * h->sstride * sizeof(double)));
@@ -744,7 +883,9 @@ static int enqueue_channel(pws_handle* h, int ndays, const double* d_hru_lat,
   a.ndays = ndays;
   a.tsi = h->d_tsi; a.ts = h->d_ts; a.c0 = h->d_c0; a.c1 = h->d_c1; a.c2 = h->d_c2;
   a.up_ptr = h->d_up_ptr; a.up_idx = h->d_up_idx; a.hru_ptr = h->d_hru_ptr;
-  a.hru_idx = h->d_hru_idx; a.has_down = h->d_has_down; a.orig = h->d_orig;
+  a.hru_idx = h->d_hru_idx; a.flags = h->d_seg_flags; a.orig = h->d_orig;
+  a.chunk_begin = h->d_chunk_begin; a.nchunks = h->nchunks;
+  a.chunk_dmax = h->d_chunk_dmax; a.delay = h->d_delay; a.ext_row = h->d_ext_row; a.rts = h->d_rts;
   a.outflow_ts = h->d_outflow_ts; a.seg_inflow = h->d_seg_inflow;
   a.hru_lat = d_hru_lat; a.hstride = h->stride; a.seg_lat_in = d_seg_lat_in;
   a.ots = h->d_ots; a.day_outvol = h->d_day_outvol; a.day_dstor = h->d_day_dstor;
@@ -753,35 +894,14 @@ static int enqueue_channel(pws_handle* h, int ndays, const double* d_hru_lat,
   a.n_seg_sel = h->n_seg_sel;
   memcpy(a.slot, h->slot_seg, sizeof a.slot);
   a.progress = h->d_progress;
+  a.ticket = h->d_progress + h->sstride;
   a.err = h->d_err;
-  bool use_wave = false;
-  if (h->wavefront) {
-    if (h->wavefront_ok < 0) {
-      int per_sm = 0, nsm = 0, coop = 0;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_route_wavefront, 128, 0);
-      cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
-      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
-      h->wavefront_ok = (coop && (int64_t)per_sm * nsm * 128 >= h->nseg) ? 1 : 0;
-    }
-    use_wave = h->wavefront_ok == 1;
-  }
-  if (use_wave) {
-    PWS_CUDA(h, cudaMemsetAsync(h->d_progress, 0, (size_t)h->sstride * sizeof(int), h->s_compute));
-    void* kargs[] = {(void*)&a};
-    const unsigned grid = (unsigned)((h->nseg + 127) / 128);
-    PWS_CUDA(h, cudaLaunchCooperativeKernel((void*)k_route_wavefront, dim3(grid), dim3(128), kargs,
-                                            0, h->s_compute));
-    h->launches++;
-    h->last_channel_launches += 1;
-  } else {
-    for (int l = 0; l < h->nlevels; ++l) {
-      const int b = h->level_begin[l], c = h->level_begin[l + 1] - b;
-      if (c <= 0) continue;
-      k_route_level<<<(c + 127) / 128, 128, 0, h->s_compute>>>(a, b, c);
-      h->launches++;
-      h->last_channel_launches += 1;
-    }
-  }
+  // progress counters (cross-chunk edges) and the chunk ticket start at 0
+  PWS_CUDA(h, cudaMemsetAsync(h->d_progress, 0, (size_t)(h->sstride + 32) * sizeof(int),
+                              h->s_compute));
+  k_route_chunks<<<(unsigned)h->nchunks, PWS_CHUNK_THREADS, 0, h->s_compute>>>(a);
+  h->launches++;
+  h->last_channel_launches += 1;
   if (budget) {
     k_channel_budget<<<ndays, 256, 0, h->s_compute>>>(h->nseg, h->sstride, h->d_day_lat,
                                                       h->d_day_outvol, h->d_day_dstor, h->d_viol);
@@ -820,14 +940,29 @@ static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const d
     a.off[v] = sl < 0 ? -1 : (int64_t)sl * a.ostride * esz;
   }
   if (kColumnSmemBytes > 48 * 1024 && !h->smem_attr_set) {
-    PWS_CUDA(h, cudaFuncSetAttribute(k_hru_column, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)kColumnSmemBytes));
+    for (auto fn : {k_hru_column<SINK_SELECT>, k_hru_column<SINK_FULL>, k_hru_column<SINK_NONE>})
+      PWS_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)kColumnSmemBytes));
     h->smem_attr_set = true;
   }
   cudaEvent_t e0 = new_event(h), e1 = new_event(h), e2 = new_event(h);
   cudaEventRecord(e0, h->s_compute);
   const unsigned grid = (unsigned)((h->nhru + PWS_COLUMN_THREADS - 1) / PWS_COLUMN_THREADS);
-  k_hru_column<<<grid, PWS_COLUMN_THREADS, kColumnSmemBytes, h->s_compute>>>(a);
+  // sink: nothing selected / everything in registry order / a subset
+  int mode = SINK_SELECT;
+  if (h->n_f64 + h->n_i32 == 0) {
+    mode = SINK_NONE;
+  } else if (h->n_f64 + h->n_i32 == PWS_N_HRU_VARS) {
+    mode = SINK_FULL;
+    for (int v = 0; v < PWS_N_HRU_VARS; ++v)
+      if (h->slot_hru[v] != full_slot(v)) mode = SINK_SELECT;
+  }
+  if (mode == SINK_FULL)
+    k_hru_column<SINK_FULL><<<grid, PWS_COLUMN_THREADS, kColumnSmemBytes, h->s_compute>>>(a);
+  else if (mode == SINK_NONE)
+    k_hru_column<SINK_NONE><<<grid, PWS_COLUMN_THREADS, kColumnSmemBytes, h->s_compute>>>(a);
+  else
+    k_hru_column<SINK_SELECT><<<grid, PWS_COLUMN_THREADS, kColumnSmemBytes, h->s_compute>>>(a);
   h->launches++;
   PWS_CUDA(h, cudaGetLastError());
   cudaEventRecord(e1, h->s_compute);
@@ -855,7 +990,7 @@ static int check_device_errors(pws_handle* h) {
       PWS_FAIL(h, "ERROR, in compute_interflow sos=0, please contact code developers "
                   "(prms_soilzone.py:1282-1287)");
     if (errflag & 16)
-      PWS_FAIL(h, "k_route_wavefront: a segment waited too long for its upstream segments");
+      PWS_FAIL(h, "k_route_chunks: a segment waited too long for its upstream segments");
     PWS_FAIL(h, "device error flag %d", errflag);
   }
   return 0;
@@ -1034,12 +1169,13 @@ extern "C" int pws_last_timing(pws_handle* h, double* ms_column, double* ms_chan
 extern "C" int pws_column_kernel_info(pws_handle* h, int* regs, int* local_bytes,
                                       int* max_blocks_per_sm) {
   cudaFuncAttributes at{};
-  PWS_CUDA(h, cudaFuncGetAttributes(&at, k_hru_column));
+  PWS_CUDA(h, cudaFuncGetAttributes(&at, k_hru_column<SINK_FULL>));
   int nb = 0;
   if (kColumnSmemBytes > 48 * 1024)
-    PWS_CUDA(h, cudaFuncSetAttribute(k_hru_column, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PWS_CUDA(h, cudaFuncSetAttribute(k_hru_column<SINK_FULL>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)kColumnSmemBytes));
-  PWS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_hru_column,
+  PWS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_hru_column<SINK_FULL>,
                                                             PWS_COLUMN_THREADS, kColumnSmemBytes));
   if (regs) *regs = at.numRegs;
   if (local_bytes) *local_bytes = (int)at.localSizeBytes;

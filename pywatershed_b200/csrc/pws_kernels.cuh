@@ -3,9 +3,9 @@
 //   k_hru_init      derived parameters + initial conditions, once per run
 //   k_hru_column    the fused atmosphere..groundwater column, 1 thread / HRU,
 //                   state in registers across a block of days
-//   k_route_wavefront  Muskingum-Mann routing, all topological levels of the
-//                   segment DAG concurrently over a block of days (persistent,
-//                   cooperative); k_route_level = per-level fallback
+//   k_route_chunks  Muskingum-Mann routing: one CTA per chunk of connected
+//                   segments, systolic hour-by-hour schedule over a block of
+//                   days, hand-over through double-buffered shared memory
 //   k_channel_budget per-day global channel mass balance
 #pragma once
 #include <cuda_runtime.h>
@@ -78,20 +78,66 @@ struct ColumnArgs {
   int64_t off[PWS_N_HRU_VARS];
 };
 
+// How k_hru_column writes the public variables:
+//   SINK_SELECT  any subset, row offsets looked up in ColumnArgs::off
+//   SINK_FULL    every variable, in registry order: the row of a variable is a
+//                compile-time constant, one IMAD.WIDE + one STG per value
+//   SINK_NONE    nothing (routing-only runs: the lateral inflow is the output)
+enum { SINK_SELECT = 0, SINK_FULL = 1, SINK_NONE = 2 };
+
+constexpr int kHruVarKind[PWS_N_HRU_VARS] = {
+#define KIND_F 0
+#define KIND_I 1
+#define KIND_B 1
+#define X(name, kind, init) KIND_##kind,
+    PWS_HRU_VARS(X)
+#undef X
+#undef KIND_F
+#undef KIND_I
+#undef KIND_B
+};
+// slot of a variable among the variables of its storage class (float64 /
+// int32) when all are selected in registry order
+constexpr int full_slot(int var) {
+  int n = 0;
+  for (int k = 0; k < var; ++k)
+    if (kHruVarKind[k] == kHruVarKind[var]) ++n;
+  return n;
+}
+
+template <int var>
+struct FullSlot {
+  static constexpr unsigned value = (unsigned)full_slot(var);
+};
+
+template <int kMode>
 struct GpuSink {
   const ColumnArgs& a;
   char* pf;
   char* pi;
   double* plat;
+  unsigned stride8, stride4;  // bytes between the rows of two variables
   unsigned violmask;
   int errmask;
-  __device__ __forceinline__ void f(int var, double v) {
-    const int64_t o = a.off[var];
-    if (o >= 0) __stcs(reinterpret_cast<double*>(pf + o), v);
+  template <int var>
+  __device__ __forceinline__ void f(double v) {
+    if constexpr (kMode == SINK_FULL) {
+      constexpr unsigned slot = FullSlot<var>::value;
+      __stcs(reinterpret_cast<double*>(pf + (size_t)slot * stride8), v);
+    } else if constexpr (kMode == SINK_SELECT) {
+      const int64_t o = a.off[var];
+      if (o >= 0) __stcs(reinterpret_cast<double*>(pf + o), v);
+    }
   }
-  __device__ __forceinline__ void i(int var, int v) {
-    const int64_t o = a.off[var];
-    if (o >= 0) __stcs(reinterpret_cast<int*>(pi + o), v);
+  template <int var>
+  __device__ __forceinline__ void i(int v) {
+    if constexpr (kMode == SINK_FULL) {
+      constexpr unsigned slot = FullSlot<var>::value;
+      __stcs(reinterpret_cast<int*>(pi + (size_t)slot * stride4), v);
+    } else if constexpr (kMode == SINK_SELECT) {
+      const int64_t o = a.off[var];
+      if (o >= 0) __stcs(reinterpret_cast<int*>(pi + o), v);
+    }
   }
   __device__ __forceinline__ void viol(int proc, bool open) {
     if (open) violmask |= 1u << proc;
@@ -134,6 +180,7 @@ constexpr size_t kColumnSmemBytes =
     PWS_COLUMN_SMEM ? (size_t)PWS_COLUMN_THREADS * ((kDailyF64 + kDailyMonF64) * 8 + kDailyI32 * 4)
                     : 0;
 
+template <int kMode>
 __global__ void __launch_bounds__(PWS_COLUMN_THREADS, PWS_COLUMN_MIN_BLOCKS)
 k_hru_column(const __grid_constant__ ColumnArgs a) {
   constexpr int T = PWS_COLUMN_THREADS;
@@ -196,7 +243,8 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
   const int64_t pidx = ii;
 #endif
 
-  GpuSink out{a, nullptr, nullptr, nullptr, 0u, 0};
+  GpuSink<kMode> out{a, nullptr, nullptr, nullptr, (unsigned)(a.ostride * 8),
+                     (unsigned)(a.ostride * 4), 0u, 0};
   // forcing prefetch: day d+1 is in flight while day d computes
   DayIn nxt;
   {
@@ -254,26 +302,36 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
 }
 
 // ---------------------------------------------------------------- channel
-// Muskingum-Mann routing (prms_channel.py:456-585).  Segments are stored in
-// topological-level order ("pos"); thread = segment.  Every segment with a
-// downstream neighbour publishes its 24 hourly outflows of a day as one
-// contiguous 192-byte row of the HBM scratch ots[pos][day][hour]; a consumer
-// gathers whole rows of its upstream segments (fully used sectors) before it
-// enters the hourly recurrence, so no load sits on the recurrence's critical
-// path.  Two drivers share route_day():
-//   k_route_wavefront  ONE cooperative launch per block of days; all levels
-//                      run concurrently, a segment starts day d as soon as
-//                      its upstream segments have published day d (progress
-//                      counters in HBM, acquire/release through L2).  Critical
-//                      path = nlevels + ndays segment-days, not their product.
-//   k_route_level      one launch per level (fallback when the segment
-//                      threads cannot all be co-resident).
+// Muskingum-Mann routing (prms_channel.py:456-585), thread = segment.
+//
+// The hourly recurrence of a segment needs, at hour h, the hour-h outflow of
+// its upstream segments: a dependency chain as deep as the network, 24 times a
+// day.  The kernel runs it as a SYSTOLIC schedule inside one CTA per chunk of
+// connected segments:
+//   * The host cuts the segment forest into connected pieces of at most
+//     `channel_chunk` segments (whole outlet trees when they fit) and packs
+//     them into chunks.  In a tree every segment has ONE downstream segment,
+//     so with delay(i) = dmax - (hops from i to the root of its chunk-local
+//     tree) every local upstream segment of i is exactly one step ahead of i.
+//   * At step t, segment i advances hour t - delay(i).  The outflow it
+//     publishes goes to a double-buffered shared-memory slot; its downstream
+//     segment reads it in the next step.  One __syncthreads() per step is the
+//     only synchronisation; a block of T days takes 24 T + dmax steps.
+//   * Edges that cross chunks (only when a tree does not fit one chunk) go
+//     through a global scratch row per day and a per-segment progress counter
+//     with device-scope fences.  Chunks are numbered so that a chunk only
+//     waits for lower-numbered ones, and a CTA takes its chunk from an atomic
+//     ticket, so whatever it waits for is already running: a plain launch
+//     cannot deadlock and may share the GPU with other kernels.
+// Upstream flows are summed in the reference's accumulation order
+// (topological rank, prms_channel.py:566-571).
 struct ChannelArgs {
   int64_t nseg, sstride;
   int ndays;
-  // static, in pos order
+  // static, in pos order (chunk, then delay, then original index)
   const int32_t* tsi;
   const double* ts;
+  const double* rts;         // 1 / ts
   const double* c0;
   const double* c1;
   const double* c2;
@@ -281,8 +339,14 @@ struct ChannelArgs {
   const int32_t* up_idx;
   const int32_t* hru_ptr;    // [nseg+1] CSR of contributing HRUs (ascending HRU index)
   const int32_t* hru_idx;
-  const int32_t* has_down;   // 1 if tosegment > 0
+  const int32_t* flags;      // SEG_* bits
   const int32_t* orig;       // pos -> original segment index
+  const int32_t* delay;      // systolic delay inside the chunk, hours
+  const int32_t* ext_row;    // row of `ots` for a segment whose downstream is in another chunk, else -1
+  const int32_t* chunk_begin;  // [nchunks+1]
+  const int32_t* chunk_dmax;   // [nchunks] largest delay in the chunk
+  int nchunks;
+  int* ticket;               // chunk ticket counter, zeroed before each launch
   // state, in pos order
   double* outflow_ts;
   double* seg_inflow;        // yesterday's daily mean inflow (prms_channel.py:384-386)
@@ -290,8 +354,8 @@ struct ChannelArgs {
   const double* hru_lat;     // [ndays][hstride] or null
   int64_t hstride;
   const double* seg_lat_in;  // [ndays][nseg] in ORIGINAL order (channel-only runs) or null
-  double* ots;               // [nseg][ndays][24] hourly outflow of segments with a downstream
-  int* progress;             // [nseg] days published (wavefront)
+  double* ots;               // [n_ext][ndays][24] hourly outflow across chunk boundaries
+  int* progress;             // [nseg] days published, for edges that cross chunks
   double* day_outvol;        // [ndays][sstride] channel_outflow_vol (pos order)
   double* day_dstor;         // [ndays][sstride] seg_stor_change
   double* day_lat;           // [ndays][sstride] seg_lateral_inflow
@@ -302,157 +366,218 @@ struct ChannelArgs {
   short slot[PWS_N_SEG_VARS];
 };
 
-struct SegStatic {
-  int tsi, ub, ue, hb, he, orig;
-  unsigned fire;  // bit h set: hour h+1 is a routing update, (h + 1) % tsi == 0 (:529)
-  bool down;
-  double ts, c0, c1, c2;
+enum {
+  SEG_HAS_DOWN = 1,     // tosegment > 0
+  SEG_DOWN_LOCAL = 2,   // the downstream segment is in the same chunk
+  SEG_UPS_LOCAL = 4,    // every upstream segment is in the same chunk
 };
 
-__device__ __forceinline__ SegStatic seg_static(const ChannelArgs& a, int pos) {
-  SegStatic g;
-  g.tsi = a.tsi[pos];
-  g.ts = a.ts[pos]; g.c0 = a.c0[pos]; g.c1 = a.c1[pos]; g.c2 = a.c2[pos];
-  g.ub = a.up_ptr[pos]; g.ue = a.up_ptr[pos + 1];
-  g.hb = a.hru_ptr[pos]; g.he = a.hru_ptr[pos + 1];
-  g.down = a.has_down[pos] != 0;
-  g.orig = a.orig[pos];
-  g.fire = 0u;
-  for (int h = 0; h < 24; ++h)
-    if (g.tsi < 0 || ((h + 1) % g.tsi) == 0) g.fire |= 1u << h;
-  return g;
-}
-
-// One segment, one day (24 hourly steps).  Upstream hours are summed in the
-// reference's accumulation order (topological rank, prms_channel.py:566-571).
-__device__ __forceinline__ void route_day(const ChannelArgs& a, const SegStatic& g, int pos,
-                                          int d, double& outflow_ts, double& seg_inflow_prev) {
-  // lateral inflow: HRU contributions in ascending HRU order (prms_channel.py:396-421)
-  double lateral = 0.0;
-  if (a.seg_lat_in != nullptr) {
-    lateral = a.seg_lat_in[(int64_t)d * a.nseg + g.orig];
-  } else {
-    for (int k = g.hb; k < g.he; ++k)
-      lateral += __ldcg(a.hru_lat + (int64_t)d * a.hstride + a.hru_idx[k]);
-  }
-  double up[24];
-#pragma unroll
-  for (int h = 0; h < 24; ++h) up[h] = 0.0;
-  const int64_t day_off = (int64_t)d * 24;
-  const int64_t row_len = (int64_t)a.ndays * 24;
-  for (int k = g.ub; k < g.ue; ++k) {
-    const double2* src =
-        reinterpret_cast<const double2*>(a.ots + (int64_t)a.up_idx[k] * row_len + day_off);
-#pragma unroll
-    for (int h = 0; h < 12; ++h) {
-      const double2 v = __ldcg(src + h);
-      up[2 * h] += v.x;
-      up[2 * h + 1] += v.y;
-    }
-  }
-  double seg_inflow0 = seg_inflow_prev;  // _advance_variables, prms_channel.py:384-386
-  double seg_inflow = seg_inflow0 * 0.0, seg_outflow = seg_inflow0 * 0.0;
-  double inflow_ts = seg_inflow0 * 0.0, cur_sum = seg_inflow0 * 0.0;
-  double2* dst = reinterpret_cast<double2*>(a.ots + (int64_t)pos * row_len + day_off);
-  double o_even = 0.0;
-#pragma unroll
-  for (int h = 0; h < 24; ++h) {
-    const double cur = lateral + up[h];
-    seg_inflow += cur;
-    inflow_ts += cur;
-    cur_sum += up[h];
-    if ((g.fire >> h) & 1u) {
-      if (g.ts != 1.0) inflow_ts /= g.ts;  // x / 1.0 == x exactly
-      if (g.tsi > 0) outflow_ts = inflow_ts * g.c0 + seg_inflow0 * g.c1 + outflow_ts * g.c2;
-      else outflow_ts = inflow_ts;
-      seg_inflow0 = inflow_ts;
-      inflow_ts = 0.0;
-    }
-    seg_outflow += outflow_ts;
-    if ((h & 1) == 0) o_even = outflow_ts;
-    else if (g.down) __stcg(dst + (h >> 1), make_double2(o_even, outflow_ts));
-  }
-  seg_outflow /= 24.0;
-  seg_inflow /= 24.0;
-  const double upstream = cur_sum / 24.0;
-  const double dstor = (seg_inflow - seg_outflow) * 86400.0;
-  const double outvol = (g.down ? 0.0 : seg_outflow) * 86400.0;
-  seg_inflow_prev = seg_inflow;
-  const int64_t drow = (int64_t)d * a.sstride + pos;
-  a.day_outvol[drow] = outvol;
-  a.day_dstor[drow] = dstor;
-  a.day_lat[drow] = lateral;
-  if (a.seg_out != nullptr) {
-    double* q = a.seg_out + (int64_t)d * a.n_seg_sel * a.nseg + g.orig;
-    if (a.slot[S_channel_outflow_vol] >= 0) q[(int64_t)a.slot[S_channel_outflow_vol] * a.nseg] = outvol;
-    if (a.slot[S_seg_lateral_inflow] >= 0) q[(int64_t)a.slot[S_seg_lateral_inflow] * a.nseg] = lateral;
-    if (a.slot[S_seg_upstream_inflow] >= 0) q[(int64_t)a.slot[S_seg_upstream_inflow] * a.nseg] = upstream;
-    if (a.slot[S_seg_outflow] >= 0) q[(int64_t)a.slot[S_seg_outflow] * a.nseg] = seg_outflow;
-    if (a.slot[S_seg_stor_change] >= 0) q[(int64_t)a.slot[S_seg_stor_change] * a.nseg] = dstor;
-  }
-}
-
-__global__ void __launch_bounds__(128)
-k_route_level(const __grid_constant__ ChannelArgs a, int level_begin, int level_count) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= level_count) return;
-  const int pos = level_begin + t;
-  const SegStatic g = seg_static(a, pos);
-  double outflow_ts = a.outflow_ts[pos];
-  double seg_inflow_prev = a.seg_inflow[pos];
-  for (int d = 0; d < a.ndays; ++d) route_day(a, g, pos, d, outflow_ts, seg_inflow_prev);
-  a.outflow_ts[pos] = outflow_ts;
-  a.seg_inflow[pos] = seg_inflow_prev;
-}
-
-// Persistent wavefront over (segment, day).  Cooperative launch: every CTA is
-// resident, so a spinning consumer can never keep its producer off the GPU.
-// Rounds are warp-synchronous: in each round a lane whose upstream segments
-// have published day d routes that day and publishes; the other lanes poll
-// again next round, so producer and consumer lanes of one warp cannot block
-// each other.  A bounded number of idle rounds turns a would-be hang into an
-// error flag.
-#ifndef PWS_WAVEFRONT_MAX_IDLE
-#define PWS_WAVEFRONT_MAX_IDLE (1 << 22)
+#ifndef PWS_CHUNK_THREADS
+#define PWS_CHUNK_THREADS 512
 #endif
-__global__ void __launch_bounds__(128, 4)
-k_route_wavefront(const __grid_constant__ ChannelArgs a) {
-  const int pos = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = pos < a.nseg;
-  SegStatic g{};
+#ifndef PWS_ROUTE_MAX_IDLE
+#define PWS_ROUTE_MAX_IDLE (1 << 24)
+#endif
+
+__global__ void __launch_bounds__(PWS_CHUNK_THREADS, 1)
+k_route_chunks(const __grid_constant__ ChannelArgs a) {
+  constexpr int kZero = PWS_CHUNK_THREADS;  // a slot that always holds 0.0
+  __shared__ double s_out[2][PWS_CHUNK_THREADS + 1];
+  __shared__ int s_chunk;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    s_chunk = atomicAdd(a.ticket, 1);
+    s_out[0][kZero] = 0.0;
+    s_out[1][kZero] = 0.0;
+  }
+  __syncthreads();
+  const int chunk = s_chunk;
+  if (chunk >= a.nchunks) return;
+  const int cb = a.chunk_begin[chunk], ce = a.chunk_begin[chunk + 1];
+  const int dmax = a.chunk_dmax[chunk];
+  const int pos = cb + tid;
+  const bool live = pos < ce;
+  const int T = a.ndays;
+  const int64_t row_len = (int64_t)T * 24;
+
+  // ---- static description of this thread's segment
+  int tsi = 1, flags = 0, ub = 0, ue = 0, hb = 0, he = 0, orig = 0, delay = 0, ext_row = -1;
+  double ts = 1.0, rts = 1.0, c0 = 0.0, c1 = 0.0, c2 = 0.0;
+  unsigned fire = 0u;  // bit h set: hour h+1 is a routing update, (h + 1) % tsi == 0 (:529)
+  int u0 = kZero, u1 = kZero, u2 = kZero;  // local upstream segments (slot in the chunk)
+  int h0 = -1, h1 = -1, h2 = -1;           // contributing HRUs
+  if (live) {
+    tsi = a.tsi[pos];
+    ts = a.ts[pos]; rts = a.rts[pos]; c0 = a.c0[pos]; c1 = a.c1[pos]; c2 = a.c2[pos];
+    ub = a.up_ptr[pos]; ue = a.up_ptr[pos + 1];
+    hb = a.hru_ptr[pos]; he = a.hru_ptr[pos + 1];
+    flags = a.flags[pos];
+    orig = a.orig[pos];
+    delay = a.delay[pos];
+    ext_row = a.ext_row[pos];
+    for (int h = 0; h < 24; ++h)
+      if (tsi < 0 || ((h + 1) % tsi) == 0) fire |= 1u << h;
+  }
+  const int nup = ue - ub, nh = he - hb;
+  const bool fast_up = (flags & SEG_UPS_LOCAL) && nup <= 3;
+  if (live && fast_up) {
+    if (nup > 0) u0 = a.up_idx[ub] - cb;
+    if (nup > 1) u1 = a.up_idx[ub + 1] - cb;
+    if (nup > 2) u2 = a.up_idx[ub + 2] - cb;
+  }
+  const bool fast_lat = a.seg_lat_in != nullptr || nh <= 3;
+  if (live && a.seg_lat_in == nullptr && nh <= 3) {
+    if (nh > 0) h0 = a.hru_idx[hb];
+    if (nh > 1) h1 = a.hru_idx[hb + 1];
+    if (nh > 2) h2 = a.hru_idx[hb + 2];
+  }
+  const bool divide = ts != 1.0;  // x / 1.0 == x exactly
+  const bool muskingum = tsi > 0;
+  const bool down = (flags & SEG_HAS_DOWN) != 0;
+
+  // Lateral inflow of day k as up to three raw addends (summed a window later,
+  // so the loads stay in flight): HRU contributions in ascending HRU order
+  // (prms_channel.py:396-421).
+  double qa = 0.0, qb = 0.0, qr = 0.0;
+  auto fetch_lateral = [&](int k) {
+    qa = qb = qr = 0.0;
+    if (!live || k < 0 || k >= T) return;
+    if (a.seg_lat_in != nullptr) {
+      qa = __ldcg(a.seg_lat_in + (int64_t)k * a.nseg + orig);
+    } else if (fast_lat) {
+      const double* row = a.hru_lat + (int64_t)k * a.hstride;
+      if (h0 >= 0) qa = __ldcg(row + h0);
+      if (h1 >= 0) qb = __ldcg(row + h1);
+      if (h2 >= 0) qr = __ldcg(row + h2);
+    } else {
+      double lat = 0.0;
+      for (int j = hb; j < he; ++j)
+        lat += __ldcg(a.hru_lat + (int64_t)k * a.hstride + a.hru_idx[j]);
+      qa = lat;
+    }
+  };
+  // Results of the day a segment finished during the current 24-step window;
+  // written to HBM by all threads together at the next window start, so the
+  // stores are off the per-step critical path.
+  double st_outvol = 0.0, st_dstor = 0.0, st_lat = 0.0, st_up = 0.0, st_out = 0.0;
+  int st_day = -1;
+  auto flush_day = [&]() {
+    if (st_day < 0) return;
+    const int64_t drow = (int64_t)st_day * a.sstride + pos;
+    a.day_outvol[drow] = st_outvol;
+    a.day_dstor[drow] = st_dstor;
+    a.day_lat[drow] = st_lat;
+    if (a.seg_out != nullptr) {
+      double* q = a.seg_out + (int64_t)st_day * a.n_seg_sel * a.nseg + orig;
+      if (a.slot[S_channel_outflow_vol] >= 0) q[(int64_t)a.slot[S_channel_outflow_vol] * a.nseg] = st_outvol;
+      if (a.slot[S_seg_lateral_inflow] >= 0) q[(int64_t)a.slot[S_seg_lateral_inflow] * a.nseg] = st_lat;
+      if (a.slot[S_seg_upstream_inflow] >= 0) q[(int64_t)a.slot[S_seg_upstream_inflow] * a.nseg] = st_up;
+      if (a.slot[S_seg_outflow] >= 0) q[(int64_t)a.slot[S_seg_outflow] * a.nseg] = st_out;
+      if (a.slot[S_seg_stor_change] >= 0) q[(int64_t)a.slot[S_seg_stor_change] * a.nseg] = st_dstor;
+    }
+    st_day = -1;
+  };
+
+  // ---- prognostic state
   double outflow_ts = 0.0, seg_inflow_prev = 0.0;
   if (live) {
-    g = seg_static(a, pos);
     outflow_ts = a.outflow_ts[pos];
     seg_inflow_prev = a.seg_inflow[pos];
   }
-  int d = live ? 0 : a.ndays;
-  int idle = 0;
-  while (__any_sync(0xffffffffu, d < a.ndays)) {
-    bool ready = d < a.ndays;
-    if (ready) {
-      for (int k = g.ub; k < g.ue; ++k) {
-        const int pu = *reinterpret_cast<volatile const int*>(a.progress + a.up_idx[k]);
-        ready = ready && (pu > d);
+  // The start of day k falls into window k + delay / 24; at every window start
+  // the lateral inflow for the day starting in the NEXT window is requested.
+  const int dd = delay / 24;
+  fetch_lateral(-dd);
+  double lat_window = 0.0;  // lateral inflow of the day that starts in the current window
+  double lateral = 0.0, seg_inflow0 = 0.0, seg_inflow = 0.0, seg_outflow = 0.0;
+  double inflow_ts = 0.0, cur_sum = 0.0;
+  int d = 0, h = 0;
+  const int nsteps = 24 * T + dmax;
+  int x = -delay;  // hour of the block this segment advances in step t
+  for (int t = 0, tw = 0, w = 0; t < nsteps; ++t, ++x) {
+    if (tw == 0) {  // window start (uniform across the CTA)
+      flush_day();
+      lat_window = ((0.0 + qa) + qb) + qr;
+      fetch_lateral(w + 1 - dd);
+    }
+    if (++tw == 24) {
+      tw = 0;
+      ++w;
+    }
+    const double* rd = s_out[(t & 1) ^ 1];  // published in step t - 1
+    if (live && x >= 0 && x < 24 * T) {
+      if (h == 0) {
+        lateral = lat_window;
+        seg_inflow0 = seg_inflow_prev;  // _advance_variables, prms_channel.py:384-386
+        seg_inflow = seg_inflow0 * 0.0;
+        seg_outflow = seg_inflow0 * 0.0;
+        inflow_ts = seg_inflow0 * 0.0;
+        cur_sum = seg_inflow0 * 0.0;
+        if (!(flags & SEG_UPS_LOCAL)) {
+          // upstream chunks must have published this day
+          for (int k = ub; k < ue; ++k) {
+            const int u = a.up_idx[k];
+            if (u >= cb && u < ce) continue;
+            int idle = 0;
+            while (*reinterpret_cast<volatile const int*>(a.progress + u) <= d) {
+              if (++idle > PWS_ROUTE_MAX_IDLE) {
+                atomicOr(a.err, 16);
+                break;
+              }
+              __nanosleep(64);
+            }
+          }
+          __threadfence();  // acquire: the rows are visible after the counter
+        }
+      }
+      double up;
+      if (fast_up) {
+        up = (rd[u0] + rd[u1]) + rd[u2];  // absent ones read the 0.0 slot
+      } else {
+        up = 0.0;
+        for (int k = ub; k < ue; ++k) {
+          const int u = a.up_idx[k];
+          if (u >= cb && u < ce) up += rd[u - cb];
+          else up += __ldcg(a.ots + (int64_t)a.ext_row[u] * row_len + d * 24 + h);
+        }
+      }
+      const double cur = lateral + up;
+      seg_inflow += cur;
+      cur_sum += up;
+      const double acc = inflow_ts + cur;
+      // routing update (branch-free; most segments update every hour)
+      const bool upd = (fire >> h) & 1u;
+      const double xq = divide ? div_by_ts(acc, ts, rts) : acc;
+      const double routed = muskingum ? (xq * c0 + seg_inflow0 * c1) + outflow_ts * c2 : xq;
+      outflow_ts = upd ? routed : outflow_ts;
+      seg_inflow0 = upd ? xq : seg_inflow0;
+      inflow_ts = upd ? 0.0 : acc;
+      seg_outflow += outflow_ts;
+      s_out[t & 1][tid] = outflow_ts;
+      if (ext_row >= 0) __stcg(a.ots + (int64_t)ext_row * row_len + d * 24 + h, outflow_ts);
+      if (h == 23) {
+        seg_outflow = div_by_ts(seg_outflow, 24.0, 1.0 / 24.0);
+        seg_inflow = div_by_ts(seg_inflow, 24.0, 1.0 / 24.0);
+        st_up = div_by_ts(cur_sum, 24.0, 1.0 / 24.0);
+        st_dstor = (seg_inflow - seg_outflow) * 86400.0;
+        st_outvol = (down ? 0.0 : seg_outflow) * 86400.0;
+        st_out = seg_outflow;
+        st_lat = lateral;
+        st_day = d;
+        seg_inflow_prev = seg_inflow;
+        if (ext_row >= 0) {
+          __threadfence();  // release: the day's row before the counter
+          *reinterpret_cast<volatile int*>(a.progress + pos) = d + 1;
+        }
+        ++d;
+        h = 0;
+      } else {
+        ++h;
       }
     }
-    if (ready) {
-      __threadfence();  // acquire: the published rows are visible after the counter
-      route_day(a, g, pos, d, outflow_ts, seg_inflow_prev);
-      ++d;
-      if (g.down) {
-        __threadfence();  // release: rows before the counter
-        *reinterpret_cast<volatile int*>(a.progress + pos) = d;
-      }
-      idle = 0;
-    } else if (d < a.ndays) {
-      if (++idle > PWS_WAVEFRONT_MAX_IDLE) {
-        atomicOr(a.err, 16);
-        break;
-      }
-      __nanosleep(256);
-    }
+    __syncthreads();
   }
+  flush_day();
   if (live) {
     a.outflow_ts[pos] = outflow_ts;
     a.seg_inflow[pos] = seg_inflow_prev;

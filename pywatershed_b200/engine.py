@@ -89,7 +89,8 @@ class Engine:
     """
 
     def __init__(self, params: dict, start, device: int = 0, dprst_flag: bool = True,
-                 adjust_parameters: bool = True, channel: bool = True):
+                 adjust_parameters: bool = True, channel: bool = True,
+                 channel_chunk: int | None = None):
         self.L = _lib.lib()
         self.reg = Registry.get()
         self.nhru = int(np.asarray(params["hru_area"]).shape[0])
@@ -127,6 +128,8 @@ class Engine:
         self._opt("start_doy", float(cal0[0]))
         self._opt("dprst_flag", 1.0 if dprst_flag else 0.0)
         self._opt("adjust_parameters", 1.0 if adjust_parameters else 0.0)
+        if channel_chunk is not None:
+            self._opt("channel_chunk", channel_chunk)
         self._check(self.L.pws_init(self.h))
         self.day = 0
         self.sel_hru: list[str] = []

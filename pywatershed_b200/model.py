@@ -417,16 +417,17 @@ class Model:
 def _read_netcdf_var(path, name):
     """[time, unit] variable + decoded times from a netCDF file (netCDF4 when
     importable, scipy for classic files)."""
-    try:
-        import netCDF4 as nc4
+    from .netcdf_out import nc4_module
 
+    nc4 = nc4_module()
+    if nc4 is not None:
         with nc4.Dataset(path) as ds:
             t = ds.variables["time"]
             times = nc4.num2date(t[:], t.units, only_use_cftime_datetimes=False,
                                  only_use_python_datetimes=True)
             times = np.array(times, dtype="datetime64[s]")
             return times, np.asarray(ds.variables[name][:], dtype=np.float64)
-    except ImportError:
+    else:
         from scipy.io import netcdf_file
 
         with netcdf_file(str(path), "r", mmap=False) as ds:

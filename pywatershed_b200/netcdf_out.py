@@ -25,10 +25,19 @@ import numpy as np
 
 from ._process_meta import VARIABLE_META
 
-try:  # pragma: no cover - depends on the environment
-    import netCDF4 as _nc4
-except Exception:  # noqa: BLE001
-    _nc4 = None
+
+
+def nc4_module():
+    """The real netCDF4 module, or None (absent, or a test stub standing in
+    for it in sys.modules)."""
+    try:
+        import netCDF4 as m
+    except Exception:  # noqa: BLE001
+        return None
+    return m if isinstance(getattr(m, "Dataset", None), type) else None
+
+
+_nc4 = nc4_module()
 
 _NC_TYPES = {"float64": "f8", "int32": "i4", "bool": "i4", "int64": "i8"}
 

@@ -187,7 +187,20 @@ class Process:
             return d["_vars"][key]
         if "_param_dict" in d and key in d["_param_dict"]:
             return d["_param_dict"][key]
+        if "_input_variables_dict" in d and key in d["_input_variables_dict"]:
+            return self._input_current(key)
         raise AttributeError(key)
+
+    def _input_current(self, key):
+        """An input is the producing process's array, shared by reference
+        (base/process.py:362-377): the current-day [n] values."""
+        model = self.__dict__.get("_model")
+        if model is not None:
+            for proc in model.processes.values():
+                if proc is not self and key in proc._vars:
+                    v = proc._vars[key]
+                    return v.current if isinstance(v, TimeseriesArray) else v
+        raise AttributeError(f"{self.name}: input '{key}' is only available under a Model")
 
     def set_input_to_adapter(self, input_variable_name: str, adapter):
         self._input_variables_dict[input_variable_name] = adapter
@@ -312,8 +325,8 @@ class PRMSSoilzone(ConservativeProcess):
 
     def __init__(self, control, discretization, parameters, dprst_evap_hru=None,
                  dprst_seep_hru=None, hru_impervevap=None, hru_intcpevap=None, infil_hru=None,
-                 sroff=None, sroff_vol=None, potet=None, snow_evap=None, snowcov_area=None,
-                 transp_on=None, dprst_flag: bool = None, budget_type=None, calc_method=None,
+                 sroff=None, sroff_vol=None, potet=None, transp_on=None, snow_evap=None,
+                 snowcov_area=None, dprst_flag: bool = None, budget_type=None, calc_method=None,
                  adjust_parameters="warn", verbose: bool = None):
         if adjust_parameters not in ("warn", "error", "no"):
             raise ValueError("adjust_parameters must be one of 'warn', 'error', 'no'")

@@ -31,8 +31,8 @@ struct HostSink {
   int64_t nhru;
   int* pv;
   int err = 0;
-  void f(int var, double v) { out[(int64_t)var * nhru] = v; }
-  void i(int var, int v) { out[(int64_t)var * nhru] = (double)v; }
+  template <int var> void f(double v) { out[(int64_t)var * nhru] = v; }
+  template <int var> void i(int v) { out[(int64_t)var * nhru] = (double)v; }
   void viol(int proc, bool open) { if (open && pv) pv[proc]++; }
   void lateral(double) {}
   void error(int c) { err |= c; }
@@ -40,6 +40,11 @@ struct HostSink {
 }  // namespace
 
 extern "C" {
+// Muskingum sub-daily division, exposed for tests/test_column_host.py
+void shim_div_by_ts(const double* x, int64_t n, double ts, double* out) {
+  const double r = 1.0 / ts;
+  for (int64_t k = 0; k < n; ++k) out[k] = pws::div_by_ts(x[k], ts, r);
+}
 void* shim_create(int64_t nhru, int ndepl) {
   Shim* s = new Shim();
   s->nhru = nhru;

@@ -73,3 +73,22 @@ def test_device_physics_bit_identical_to_oracle(shim, scen, drb, drbx):
     for k in po.HRU_VARS:
         np.testing.assert_array_equal(got[k], ref[k], err_msg=k)
     np.testing.assert_array_equal(viol[:, :5], oviol[:, :5])
+
+
+def test_div_by_ts_is_the_division(shim):
+    """k_route_chunks divides by the Muskingum sub-daily step with
+    q = x r, q + fma(-q, ts, x) r (r = correctly rounded 1/ts): must be the
+    IEEE quotient for every ts PRMSChannel can produce (prms_channel.py:286-317)
+    and for the daily mean's 24."""
+    rng = np.random.default_rng(3)
+    n = 4_000_000
+    x = np.concatenate([
+        rng.lognormal(0.0, 12.0, n), rng.random(n) * 1e-3, rng.random(n) * 1e6,
+        np.array([0.0, 1.0, 3.0, 1e-300, 1e300, 5e-324, 2.2250738585072014e-308])])
+    out = np.empty_like(x)
+    shim.shim_div_by_ts.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p]
+    for ts in (2.0, 3.0, 4.0, 6.0, 8.0, 12.0, 24.0):
+        shim.shim_div_by_ts(x.ctypes.data, x.size, ts, out.ctypes.data)
+        ok = out == x / ts
+        # the reformulation needs x / ts and the remainder to stay normal
+        assert ok[x > 1e-290].all(), (ts, x[~ok][:5])

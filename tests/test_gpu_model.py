@@ -1,0 +1,184 @@
+"""The reference-facing layer on the GPU: pywatershed_b200.Model driven the way
+the reference's own tests drive pws.Model (autotest/test_model.py,
+autotest/test_netcdf_output.py:155-198), compared with the oracle and with
+the reference's golden numbers.  GPU only; everything goes through the C ABI.
+"""
+import numpy as np
+import pytest
+
+import parity
+import prms_oracle as po
+import scenarios
+
+pytestmark = pytest.mark.gpu
+
+NHM = ["PRMSSolarGeometry", "PRMSAtmosphere", "PRMSCanopy", "PRMSSnow", "PRMSRunoff",
+       "PRMSSoilzone", "PRMSGroundwater", "PRMSChannel"]
+
+
+def _control(start, nd, **opts):
+    from pywatershed_b200 import Control
+
+    t0 = np.datetime64(start, "s")
+    o = {"budget_type": "error", "calc_method": "cuda"}
+    o.update(opts)
+    return Control(t0, t0 + np.timedelta64(nd - 1, "D"), np.timedelta64(24, "h"), options=o)
+
+
+def _parameters(p):
+    from pywatershed_b200 import Parameters
+
+    nhru, nseg = p["hru_area"].shape[0], p["tosegment"].shape[0]
+    coords = {"nhm_id": p.get("nhm_id", np.arange(1, nhru + 1)),
+              "nhm_seg": p.get("nhm_seg", np.arange(1, nseg + 1))}
+    data = {k: v for k, v in p.items() if k not in coords}
+    return Parameters(dims={"nhru": nhru, "nsegment": nseg, "nmonth": 12, "ndoy": 366},
+                      coords=coords, data_vars=data)
+
+
+def _model(p, f, start, nd, procs=NHM, **opts):
+    import pywatershed_b200 as pwsb
+
+    control = _control(start, nd, **opts)
+    m = pwsb.Model([getattr(pwsb, n) for n in procs], control=control,
+                   parameters=_parameters(p), find_input_files=False)
+    atm = m.processes["PRMSAtmosphere"]
+    for k in ("prcp", "tmax", "tmin"):
+        atm.set_input_to_adapter(k, f[k][:nd])
+    return m
+
+
+def test_model_run_matches_oracle_and_reference_known_answers(drb):
+    p, f, start = drb
+    nd = 731
+    m = _model(p, f, start, nd)
+    m.run(finalize=False)
+    assert m.control.itime_step == nd - 1
+    # the reference's last-day known answers
+    assert m.processes["PRMSChannel"]["seg_outflow"].sum() == pytest.approx(214752.70363439058, rel=1e-9)
+    assert m.processes["PRMSSnow"]["pkwater_equiv"].sum() == pytest.approx(186.00889550764475, rel=1e-6)
+    for name in NHM[2:]:
+        b = m.processes[name].budget
+        assert b._zero_sum, name
+        np.testing.assert_allclose(b._inputs_sum, b._outputs_sum + b._storage_changes_sum,
+                                   rtol=1e-5, atol=1e-5)
+    # all-time Atmosphere arrays hold the whole run, like the reference's
+    atm = m.processes["PRMSAtmosphere"]
+    assert atm["tmaxf"].data.shape == (nd, 765)
+    o = po.Oracle(p, start=start)
+    ref, _ = o.run(f["prcp"][:nd], f["tmax"][:nd], f["tmin"][:nd], ["tmaxf", "swrad", "potet"], ())
+    for k in ("tmaxf", "swrad", "potet"):
+        np.testing.assert_allclose(atm[k].data, ref[k], rtol=1e-9, atol=1e-10)
+    m.finalize()
+
+
+def test_stepwise_advance_calculate_equals_run(drb):
+    """autotest/test_netcdf_output.py:155-198 drives advance/calculate/output
+    one day at a time and reads state in between; time blocking must not show."""
+    p, f, start = drb
+    nd = 40
+    m = _model(p, f, start, nd, block_days=16)
+    ids = {}
+    o = po.Oracle(p, start=start)
+    names = ["pkwater_equiv", "soil_moist", "sroff", "pptmix", "gwres_stor", "hru_actet"]
+    ref, _ = o.run(f["prcp"][:nd], f["tmax"][:nd], f["tmin"][:nd], names, ["seg_outflow"])
+    owner = {"pkwater_equiv": "PRMSSnow", "soil_moist": "PRMSSoilzone", "sroff": "PRMSRunoff",
+             "pptmix": "PRMSAtmosphere", "gwres_stor": "PRMSGroundwater", "hru_actet": "PRMSSoilzone"}
+    for it in range(nd):
+        m.advance()
+        m.calculate()
+        assert m.control.itime_step == it
+        for k in names:
+            v = m.processes[owner[k]][k]
+            cur = v.current if hasattr(v, "current") else v
+            np.testing.assert_allclose(np.asarray(cur, dtype=np.float64), ref[k][it],
+                                       rtol=1e-9, atol=1e-10, err_msg=f"{k} day {it}")
+            # stable identities (autotest/test_prms_atmosphere.py:82,145)
+            ids.setdefault(k, id(cur))
+            assert ids[k] == id(cur)
+        np.testing.assert_allclose(m.processes["PRMSChannel"]["seg_outflow"], ref["seg_outflow"][it],
+                                   rtol=1e-9, atol=1e-10)
+        assert m.processes["PRMSSnow"].budget._zero_sum
+    with pytest.raises(ValueError, match="End of time"):
+        m.advance()
+
+
+def test_netcdf_output_files(drb, tmp_path):
+    """Same file names / dims / coordinate variables as the reference's
+    NetCdfWrite (utils/netcdf_utils.py:405-630); values equal the in-memory run."""
+    p, f, start = drb
+    nd = 20
+    out_vars = ["pkwater_equiv", "seg_outflow", "tmaxf", "newsnow", "soltab_potsw"]
+    m = _model(p, f, start, nd, netcdf_output_var_names=out_vars)
+    m.initialize_netcdf(tmp_path)
+    m.run(finalize=True)
+    for v in out_vars:
+        assert (tmp_path / f"{v}.nc").exists(), v
+    assert (tmp_path / "PRMSSnow_budget.nc").exists()
+    o = po.Oracle(p, start=start)
+    ref, _ = o.run(f["prcp"][:nd], f["tmax"][:nd], f["tmin"][:nd],
+                   ["pkwater_equiv", "tmaxf", "newsnow"], ["seg_outflow"])
+    from pywatershed_b200.netcdf_out import nc4_module
+
+    nc4 = nc4_module()
+    if nc4 is not None:
+        def read(path, var):
+            with nc4.Dataset(path) as ds:
+                return (np.asarray(ds.variables[var][:]), list(ds.variables[var].dimensions),
+                        np.asarray(ds.variables["time"][:]) if "time" in ds.variables else None)
+    else:
+        from scipy.io import netcdf_file
+
+        def read(path, var):
+            with netcdf_file(str(path), "r", mmap=False) as ds:
+                return (np.array(ds.variables[var][:]), list(ds.variables[var].dimensions),
+                        np.array(ds.variables["time"][:]) if "time" in ds.variables else None)
+    a, dims, t = read(tmp_path / "pkwater_equiv.nc", "pkwater_equiv")
+    assert dims == ["time", "nhm_id"] and a.shape == (nd, 765)
+    np.testing.assert_allclose(a, ref["pkwater_equiv"], rtol=1e-9, atol=1e-10)
+    day0 = (np.datetime64(start, "D") - np.datetime64("1970-01-01", "D")).astype(int)
+    np.testing.assert_array_equal(t, (day0 + np.arange(nd)).astype(np.float32))
+    a, dims, _ = read(tmp_path / "seg_outflow.nc", "seg_outflow")
+    assert dims == ["time", "nhm_seg"] and a.shape == (nd, 456)
+    np.testing.assert_allclose(a, ref["seg_outflow"], rtol=1e-9, atol=1e-10)
+    a, _, _ = read(tmp_path / "newsnow.nc", "newsnow")
+    np.testing.assert_array_equal(a, ref["newsnow"])
+    a, dims, _ = read(tmp_path / "soltab_potsw.nc", "soltab_potsw")
+    assert a.shape == (366, 765)
+
+
+def test_channel_only_model(drb):
+    """examples/05_parameter_ensemble.ipynb cell 20: Model([PRMSChannel]) fed
+    with the three volume fluxes."""
+    import pywatershed_b200 as pwsb
+
+    p, f, start = drb
+    nd = 60
+    o = po.Oracle(p, start=start)
+    ref, _ = o.run(f["prcp"][:nd], f["tmax"][:nd], f["tmin"][:nd],
+                   ["sroff_vol", "ssres_flow_vol", "gwres_flow_vol"], po.SEG_VARS)
+    control = _control(start, nd)
+    m = pwsb.Model([pwsb.PRMSChannel], control=control, parameters=_parameters(p),
+                   find_input_files=False)
+    ch = m.processes["PRMSChannel"]
+    for k in ("sroff_vol", "ssres_flow_vol", "gwres_flow_vol"):
+        ch.set_input_to_adapter(k, ref[k])
+    m.run(finalize=False)
+    np.testing.assert_allclose(ch["seg_outflow"], ref["seg_outflow"][-1], rtol=1e-9, atol=1e-10)
+
+
+def test_reference_error_conventions(drb):
+    import pywatershed_b200 as pwsb
+
+    p, f, start = drb
+    control = _control(start, 5)
+    with pytest.raises(NameError):
+        control.options["not_an_option"] = 1
+    q = {k: v for k, v in p.items() if k != "carea_max"}
+    with pytest.raises(ValueError, match="carea_max"):
+        pwsb.PRMSRunoff(control, None, _parameters(q))
+    with pytest.raises(ValueError, match="calc_method"):
+        pwsb.PRMSCanopy(control, None, _parameters(p), calc_method="numpy")
+    with pytest.raises(NotImplementedError):
+        pwsb.Model([pwsb.PRMSSnow], control=control, parameters=_parameters(p),
+                   find_input_files=False)

@@ -188,6 +188,90 @@ def test_channel_alone_bit_exact(drb):
         np.testing.assert_array_equal(out[:, k], ref[v], err_msg=v)
 
 
+@pytest.mark.parametrize("chunk", [512, 100, 7, 1])
+def test_channel_chunking_is_transparent(drb, chunk):
+    """The routing kernel cuts the segment forest into chunks of <= `chunk`
+    segments (one CTA each); edges inside a chunk hand over through shared
+    memory, edges across chunks through global memory.  Any chunk size must
+    give the oracle's bits (DRB's 434-segment tree is cut for chunk < 434)."""
+    import torch
+
+    p, f, start = drb
+    nd = 45
+    rng = np.random.default_rng(5)
+    nseg = p["tosegment"].shape[0]
+    lat = rng.lognormal(0.0, 1.0, size=(nd, nseg))
+    ref = po.Oracle(p, start=start).run_channel(lat)
+    e = _engine(p, start, channel_chunk=chunk)
+    dev = torch.device("cuda:0")
+    dl = torch.from_numpy(lat).to(dev)
+    out = torch.empty((nd, 5, nseg), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    # two launches: state carried across blocks
+    e.run_channel_device(20, dl.data_ptr(), out.data_ptr())
+    e.run_channel_device(nd - 20, dl[20:].data_ptr(), out[20:].data_ptr())
+    out = out.cpu().numpy()
+    for k, v in enumerate(po.SEG_VARS):
+        np.testing.assert_array_equal(out[:, k], ref[v], err_msg=v)
+
+
+def test_deep_chained_network(drb):
+    """BASELINE.json configs[4] in small: DRB tiles chained outlet -> headwater
+    so the network is several hundred levels deep and crosses chunks."""
+    import torch
+
+    p, f, start = drb
+    ntile = 4
+    pt, _ = scenarios.tile(p, {k: v[:2] for k, v in f.items()}, ntile)
+    nseg0 = p["tosegment"].shape[0]
+    tos = pt["tosegment"].copy()
+    main_outlet = int(np.argmax(np.bincount(_basin_of(p["tosegment"]))))  # outlet of the big tree
+    head = int(np.argmax(np.where(_basin_of(p["tosegment"]) == main_outlet,
+                                  _dist_to_outlet(p["tosegment"]), -1)))  # the farthest headwater
+    for t in range(ntile - 1):
+        tos[t * nseg0 + main_outlet] = (t + 1) * nseg0 + head + 1
+    pt["tosegment"] = tos
+    nd, nseg = 30, tos.shape[0]
+    rng = np.random.default_rng(11)
+    lat = rng.lognormal(0.0, 1.0, size=(nd, nseg))
+    ref = po.Oracle(pt, start=start).run_channel(lat)
+    e = _engine(pt, start)
+    dev = torch.device("cuda:0")
+    dl = torch.from_numpy(lat).to(dev)
+    out = torch.empty((nd, 5, nseg), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    e.run_channel_device(nd, dl.data_ptr(), out.data_ptr())
+    out = out.cpu().numpy()
+    for k, v in enumerate(po.SEG_VARS):
+        np.testing.assert_array_equal(out[:, k], ref[v], err_msg=v)
+
+
+def _dist_to_outlet(tosegment):
+    tos = np.asarray(tosegment) - 1
+    dist = np.zeros(len(tos), dtype=int)
+    cur = np.arange(len(tos))
+    for _ in range(len(tos)):
+        nxt = tos[cur]
+        step = nxt >= 0
+        if not step.any():
+            break
+        dist += step
+        cur = np.where(step, nxt, cur)
+    return dist
+
+
+def _basin_of(tosegment):
+    """index of the outlet each segment drains to"""
+    tos = np.asarray(tosegment) - 1
+    out = np.arange(len(tos))
+    for _ in range(len(tos)):
+        nxt = np.where(tos[out] >= 0, tos[out], out)
+        if (nxt == out).all():
+            break
+        out = nxt
+    return out
+
+
 def test_tiled_domain_and_ragged_sizes(drb):
     """3 DRB tiles in different climates, truncated to a ragged 1,531 HRUs
     (not a multiple of the warp or block size); every HRU within tolerance

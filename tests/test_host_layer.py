@@ -1,0 +1,240 @@
+"""CPU tests of the reference-facing host layer (no compute calls): Control,
+Parameters, the PRMS ASCII readers, Budget arithmetic, the process
+descriptors and the netCDF writer.  Where the reference's own input files are
+needed they are read from /root/reference and the test is skipped when that
+tree is absent (the GPU box)."""
+import pathlib as pl
+import warnings
+
+import numpy as np
+import pytest
+
+import scenarios
+
+REF_DRB = pl.Path("/root/reference/pywatershed/data/drb_2yr")
+needs_ref_files = pytest.mark.skipif(not REF_DRB.exists(), reason="reference input files absent")
+
+
+def _control(nd=4, **opts):
+    from pywatershed_b200 import Control
+
+    t0 = np.datetime64("1979-01-03T00:00:00")
+    return Control(t0, t0 + np.timedelta64(nd - 1, "D"), np.timedelta64(1, "D"), options=opts)
+
+
+# ---------------------------------------------------------------- Control
+def test_control_clock_follows_the_reference():
+    """autotest/test_control.py: init_time = start - step, itime_step -1 -> 0.."""
+    c = _control(4)
+    assert c.n_times == 4 and c.itime_step == -1
+    assert c.current_time == np.datetime64("1979-01-02T00:00:00")
+    c.advance()
+    assert c.itime_step == 0 and c.current_time == c.start_time
+    assert (c.current_doy, c.current_dowy, c.current_month) == (3, 95, 1)
+    assert c.previous_time == np.datetime64("1979-01-02T00:00:00")
+    for _ in range(3):
+        c.advance()
+    assert c.current_time == c.end_time
+    with pytest.raises(ValueError, match="End of time"):
+        c.advance()
+    with pytest.raises(NameError):
+        c.options["nope"] = 1
+    with pytest.raises(NameError):
+        _control(2, nope=1)
+    c.edit_n_time_steps(10)
+    assert c.end_time == c.start_time + np.timedelta64(9, "D")
+
+
+@needs_ref_files
+def test_control_load_prms_drb():
+    from pywatershed_b200 import Control
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        c = Control.load_prms(REF_DRB / "nhm.control", warn_unused_options=False)
+    assert c.start_time == np.datetime64("1979-01-01T00:00:00")
+    assert c.end_time == np.datetime64("1980-12-31T00:00:00")
+    assert c.n_times == 731
+    assert c.time_step == np.timedelta64(24, "h")
+    names = c.options["netcdf_output_var_names"]
+    import json
+
+    default = json.loads((scenarios.GOLDEN / "nhm_default_vars.json").read_text())
+    assert set(default) <= set(names)
+
+
+# ---------------------------------------------------------------- readers
+@needs_ref_files
+def test_prms_parameter_and_cbh_readers_equal_the_reference_loaders(drb):
+    """tests/golden/drb_inputs.npz was written from the reference's own
+    PrmsParameters.load / cbh_files_to_np_dict (oracle/gen_golden.py)."""
+    from pywatershed_b200 import PrmsParameters
+    from pywatershed_b200.prms_files import read_cbh
+
+    p, f, start = drb
+    mine = PrmsParameters.load(REF_DRB / "myparam.param")
+    d = mine.to_dict()
+    checked = 0
+    for k, v in p.items():
+        if k not in d:
+            continue
+        np.testing.assert_array_equal(np.asarray(d[k]).squeeze(), np.asarray(v).squeeze(), err_msg=k)
+        checked += 1
+    assert checked > 100
+    assert mine.dims["nhru"] == 765 and mine.dims["nsegment"] == 456
+    with pytest.raises(ValueError):
+        mine.parameters["hru_area"][0] = 1.0  # read-only, parameters.py:246-254
+    for k in ("prcp", "tmax", "tmin"):
+        times, vals = read_cbh(REF_DRB / f"{k}.cbh", 765)
+        assert times[0] == np.datetime64(start) and len(times) == 731
+        np.testing.assert_array_equal(vals, f[k])
+
+
+# ---------------------------------------------------------------- Budget
+class _FakeProc(dict):
+    pass
+
+
+def _budget(budget_type, stor):
+    from pywatershed_b200 import Budget
+
+    n = 5
+    proc = _FakeProc(in1=np.ones(n), in2=np.ones(n), out1=np.zeros(n), out2=np.ones(n),
+                     stor1=np.full(n, stor), stor2=np.zeros(n))
+    terms = {"inputs": ["in1", "in2"], "outputs": ["out1", "out2"], "storage_changes": ["stor1", "stor2"]}
+    c = _control(4)
+    return c, Budget(c, proc, terms, budget_type, description="simple_test"), proc
+
+
+def test_budget_arithmetic_as_reference_test_budget():
+    """autotest/test_budget.py:25-118."""
+    c, b, proc = _budget("error", 1.0)
+    for comp in b.components:
+        assert set(b[comp]) == set(b.terms[comp])
+    c.advance()
+    b.advance()
+    b.calculate()
+    assert (b._inputs_sum == 2).all() and (b._outputs_sum == 1).all()
+    assert (b._storage_changes_sum == 1).all()
+    assert (b.balance == 1).all() and b._zero_sum
+    with pytest.raises(ValueError, match="twice"):
+        b.calculate()
+    b.accumulate_block({k: np.stack([v, v]) for k, v in proc.items()}, 1.0)
+    assert (b.accumulations["inputs"]["in1"] == 2).all()
+
+
+def test_budget_imbalance_error_and_warn():
+    c, b, _ = _budget("error", 0.5)
+    c.advance()
+    with pytest.raises(ValueError, match="simple_test"):
+        b.calculate()
+    c, b, _ = _budget("warn", 0.5)
+    c.advance()
+    with pytest.warns(UserWarning, match="simple_test"):
+        b.calculate()
+    assert not b._zero_sum
+    c, b, _ = _budget("error", 1.0)
+    c.advance()
+    with pytest.raises(ValueError):
+        b.calculate(n_violations=3)  # the device's verdict
+
+
+# ---------------------------------------------------------------- processes
+def test_process_descriptors_and_variable_registry():
+    import pywatershed_b200 as pwsb
+    from pywatershed_b200._process_meta import PROCESS_META, VARIABLE_META
+
+    import prms_oracle as po
+
+    allv = []
+    for name in ("PRMSSolarGeometry", "PRMSAtmosphere", "PRMSCanopy", "PRMSSnow", "PRMSRunoff",
+                 "PRMSSoilzone", "PRMSGroundwater", "PRMSChannel"):
+        cls = getattr(pwsb, name)
+        assert cls.get_variables() == PROCESS_META[name]["variables"]
+        assert set(cls.get_init_values()) == set(cls.get_variables())
+        assert cls.description()["class_name"] == name
+        allv += list(cls.get_variables())
+    assert len(allv) == 151 == len(set(allv))
+    hru = [v for v in allv if not v.startswith("soltab") and "nsegment" not in VARIABLE_META[v]["dims"]]
+    assert sorted(hru) == sorted(po.HRU_VARS)
+    assert pwsb.PRMSSnow.get_mass_budget_terms()["outputs"] == ["snow_evap", "snowmelt", "through_rain"]
+    assert pwsb.PRMSChannel._budget_basis == "global"
+
+
+@pytest.mark.skipif(not pl.Path("/root/reference/pywatershed").exists(), reason="reference absent")
+def test_descriptors_equal_the_reference_classes():
+    import sys
+
+    sys.path.insert(0, str(pl.Path(__file__).resolve().parent.parent / "oracle"))
+    import ref_harness as rh
+
+    import pywatershed_b200 as pwsb
+
+    pws = rh.import_reference()
+    for name in rh.NHM_PROCESS_NAMES:
+        ref, mine = getattr(pws, name), getattr(pwsb, name)
+        assert tuple(ref.get_inputs()) == tuple(mine.get_inputs()), name
+        assert tuple(ref.get_variables()) == tuple(mine.get_variables()), name
+        assert tuple(ref.get_parameters()) == tuple(mine.get_parameters()), name
+        if hasattr(ref, "get_mass_budget_terms"):
+            assert {k: list(v) for k, v in ref.get_mass_budget_terms().items()} == \
+                mine.get_mass_budget_terms(), name
+        import inspect
+
+        a = list(inspect.signature(ref.__init__).parameters)
+        b = list(inspect.signature(mine.__init__).parameters)
+        assert a == b, (name, a, b)
+
+
+def test_model_builds_on_cpu_and_refuses_to_compute_without_a_gpu(drb):
+    import torch
+
+    import pywatershed_b200 as pwsb
+    from pywatershed_b200 import _lib
+
+    p, f, start = drb
+    nhru, nseg = 765, 456
+    params = pwsb.Parameters(dims={"nhru": nhru, "nsegment": nseg},
+                             coords={"nhm_id": np.arange(1, nhru + 1), "nhm_seg": np.arange(1, nseg + 1)},
+                             data_vars=p)
+    c = _control(5, budget_type="warn")
+    m = pwsb.Model([pwsb.PRMSSolarGeometry, pwsb.PRMSAtmosphere, pwsb.PRMSCanopy, pwsb.PRMSSnow,
+                    pwsb.PRMSRunoff, pwsb.PRMSSoilzone, pwsb.PRMSGroundwater, pwsb.PRMSChannel],
+                   control=c, parameters=params, find_input_files=False)
+    assert list(m.processes) == ["PRMSSolarGeometry", "PRMSAtmosphere", "PRMSCanopy", "PRMSSnow",
+                                 "PRMSRunoff", "PRMSSoilzone", "PRMSGroundwater", "PRMSChannel"]
+    snow = m.processes["PRMSSnow"]
+    assert snow["pkwater_equiv"].shape == (nhru,) and snow["newsnow"].dtype == np.int32
+    assert snow["iasw"].dtype == np.bool_
+    assert m.processes["PRMSChannel"]["seg_outflow"].shape == (nseg,)
+    assert m.processes["PRMSAtmosphere"]["tmaxf"].data.shape == (5, nhru)
+    assert m.processes["PRMSSolarGeometry"]["soltab_potsw"].data.shape == (366, nhru)
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.PwsLibraryError):  # no CPU fallback
+            m.advance()
+
+
+def test_netcdf_writer_layout(tmp_path):
+    from pywatershed_b200.netcdf_out import _File
+
+    f = _File(tmp_path / "pkwater_equiv.nc", ["pkwater_equiv"], "nhm_id", np.arange(1, 8), "PRMSSnow")
+    a = np.arange(21, dtype=np.float64).reshape(3, 7)
+    f.write(0, 2, [3287.0, 3288.0], {"pkwater_equiv": a[:2]})
+    f.write(2, 3, [3289.0], {"pkwater_equiv": a[2:]})
+    f.close()
+    from pywatershed_b200.netcdf_out import nc4_module
+
+    if nc4_module() is not None:
+        ds = nc4_module().Dataset(tmp_path / "pkwater_equiv.nc")
+    else:
+        from scipy.io import netcdf_file
+
+        ds = netcdf_file(str(tmp_path / "pkwater_equiv.nc"), "r", mmap=False)
+    v = ds.variables["pkwater_equiv"]
+    assert tuple(v.dimensions) == ("time", "nhm_id")
+    np.testing.assert_array_equal(np.array(v[:]), a)
+    np.testing.assert_array_equal(np.array(ds.variables["nhm_id"][:]), np.arange(1, 8))
+    np.testing.assert_array_equal(np.array(ds.variables["time"][:]), [3287.0, 3288.0, 3289.0])
+    units = ds.variables["time"].units
+    assert (units.decode() if isinstance(units, bytes) else units) == "days since 1970-01-01 00:00:00"
+    ds.close()
