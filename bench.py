@@ -254,7 +254,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="conus")
     ap.add_argument("--outputs", default="full")
-    ap.add_argument("--block-days", type=int, default=32)
+    ap.add_argument("--block-days", type=int, default=128)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -352,13 +352,14 @@ def main():
     # ---- e2e: host-facing call, pinned host buffers, H2D + D2H inside the region
     e2e = None
     if not args.no_e2e:
-        eng.select_outputs([], seg_vars)
+        e2e_seg = ["seg_outflow"]  # streamflow at every segment: the product of an NHM run
+        eng.select_outputs([], e2e_seg)
         hf = {k: v.cpu().pin_memory() for k, v in forc.items()}
         e2e_T = 64
         eng.set_block_days(e2e_T)
         # pin the result buffers too (the library drains with cudaMemcpyAsync)
         cal_nd = nd
-        res_seg = torch.empty((cal_nd, len(seg_vars), nseg), dtype=torch.float64).pin_memory()
+        res_seg = torch.empty((cal_nd, len(e2e_seg), nseg), dtype=torch.float64).pin_memory()
         res_viol = np.zeros((cal_nd, 6), dtype=np.int32)
         from pywatershed_b200.engine import calendar
 
@@ -385,9 +386,9 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": units_per_step * len(ts) / float(te.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(3 * nd * nhru * 8) * world,
-               "d2h_bytes_per_step": int(nd * (len(seg_vars) * nseg * 8 + 24)) * world,
-               "outputs": "5 segment variables per day + 6 budget verdicts per day",
-               "block_days": e2e_T, "checksum_seg_outflow_last_day": float(res_seg[-1, 3].sum())}
+               "d2h_bytes_per_step": int(nd * (len(e2e_seg) * nseg * 8 + 24)) * world,
+               "outputs": "seg_outflow [ndays, nsegment] + 6 budget verdicts per day",
+               "block_days": e2e_T, "checksum_seg_outflow_last_day": float(res_seg[-1, 0].sum())}
         eng.select_outputs(hru_vars, seg_vars)
 
     if rank != 0:

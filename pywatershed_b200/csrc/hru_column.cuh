@@ -602,18 +602,29 @@ PWS_DEV int hru_init_one(const HruParams& P, const HruDerivedMut& D, double* sta
 // variable (PWS_F / PWS_I: the variable is a template argument of the sink's
 // f<V_x>() / i<V_x>(), so a sink can turn it into a compile-time address),
 // budget closure flags (out.viol), the lateral inflow contribution
-// (out.lateral) and device-side error flags (out.error).
+// (out.lateral) and device-side error flags (out.error).  out.sync() marks the
+// process boundaries and out.sync2() finer points inside the large processes:
+// CTA-wide barriers on the GPU when PWS_COLUMN_SYNC is 1 / 2, so that the
+// warps of a CTA walk the code together and share instruction fetches (every
+// such point is in convergent code: all lanes of the CTA reach it).
 // ------------------------------------------------------------------------
 #define PWS_F(var, val) out.template f<V_##var>(val)
 #define PWS_I(var, val) out.template i<V_##var>(val)
+// What the upper half of the column (atmosphere, canopy, snow) hands to the
+// lower half (runoff, soilzone, groundwater) for one HRU-day.
+struct ColumnMid {
+  double potet, net_rain, net_snow, hru_intcpevap, intcp_changeover;
+  double snowmelt, snow_evap, pkwater_equiv, snowcov_area, through_rain;
+  int transp_on, pptmix_nopack;
+};
+
+// ---- upper half: PRMSAtmosphere, PRMSCanopy, PRMSSnow
 template <class Sink>
-PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
-                        const DayIn& in, Sink& out) {
+PWS_DEV void column_upper(const HruParams& P, const int64_t i, HruState& s,
+                          const DayIn& in, Sink& out, ColumnMid& mid) {
   const int64_t mi = (int64_t)(in.month - 1) * P.stride + i;
   const int hru_type = PWS_LD(P.hru_type + i);
   const int cov_type = PWS_LD(P.cov_type + i);
-  const double hru_area = PWS_LD(P.hru_area + i);
-  const double hru_in_to_cf = PWS_LD(P.hru_in_to_cf + i);
 
   // ===================== PRMSAtmosphere ==================================
   // adjust_temperature prms_atmosphere.py:287-317
@@ -712,6 +723,7 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
   PWS_I(pptmix, pptmix);  // the all-time value Atmosphere writes to file
   PWS_F(orad_hru, orad_hru);
 
+  out.sync();
   // ===================== PRMSCanopy ======================================
   const double covden_sum = PWS_LD(P.covden_sum + i);
   const double covden_win = PWS_LD(P.covden_win + i);
@@ -821,6 +833,7 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
                        (0 + net_rain + net_snow + hru_intcpevap + intcp_changeover) +
                            (0 + hru_intcpstor_change)));
 
+  out.sync();
   // ===================== PRMSSnow ========================================
   double snowmelt = 0.0, snow_evap = 0.0, tcal = 0.0, pk_precip = 0.0;
   double ai = 0.0, frac_swe = 0.0;
@@ -842,10 +855,10 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
         active = false;
       }
     }
+    const double den_max = PWS_LD(P.den_max + i);
+    const double denmaxinv = PWS_LD(P.denmaxinv + i);
+    const double freeh2o_cap = PWS_LD(P.freeh2o_cap + i);
     if (active) {
-      const double den_max = PWS_LD(P.den_max + i);
-      const double denmaxinv = PWS_LD(P.denmaxinv + i);
-      const double freeh2o_cap = PWS_LD(P.freeh2o_cap + i);
       if (newsnow && s.pkwater_equiv < PWS_DNEARZERO) s.snowcov_area = 1.0;
       // ---- step 1: precipitation into the pack, prms_snow.py:1204-1577
       if ((s.pkwater_equiv > 0.0 && net_ppt > 0.0) || net_snow > 0.0) {
@@ -913,6 +926,9 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
           }
         }
       }
+    }
+    out.sync2();
+    if (active) {
       if (s.pkwater_equiv > 0.0) {
         // ---- step 2: snow-covered area, prms_snow.py:1851-2128 + :1177-1201
         {
@@ -1038,6 +1054,9 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
           }
         }
       }
+    }
+    out.sync2();
+    if (active) {
       if (s.pkwater_equiv > 0.0) {
         // ---- step 4: night + day energy balance, prms_snow.py:2436-2731
         const double emis_noppt = PWS_LD(P.emis_noppt + i);
@@ -1186,6 +1205,35 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
                                  (0 + snow_evap + snowmelt + through_rain) +
                                      (0 + freeh2o_change + pk_ice_change)));
 
+  mid.potet = potet;
+  mid.net_rain = net_rain;
+  mid.net_snow = net_snow;
+  mid.hru_intcpevap = hru_intcpevap;
+  mid.intcp_changeover = intcp_changeover;
+  mid.snowmelt = snowmelt;
+  mid.snow_evap = snow_evap;
+  mid.pkwater_equiv = s.pkwater_equiv;
+  mid.snowcov_area = s.snowcov_area;
+  mid.through_rain = through_rain;
+  mid.transp_on = transp_on;
+  mid.pptmix_nopack = pptmix_nopack;
+}
+
+// ---- lower half: PRMSRunoff, PRMSSoilzone, PRMSGroundwater, lateral inflow
+template <class Sink>
+PWS_DEV void column_lower(const HruParams& P, const int64_t i, HruState& s,
+                          const ColumnMid& mid, Sink& out) {
+  const int hru_type = PWS_LD(P.hru_type + i);
+  const int cov_type = PWS_LD(P.cov_type + i);
+  const double hru_area = PWS_LD(P.hru_area + i);
+  const double hru_in_to_cf = PWS_LD(P.hru_in_to_cf + i);
+  const double potet = mid.potet, net_rain = mid.net_rain, net_snow = mid.net_snow;
+  const double net_ppt = net_rain + net_snow;
+  const double hru_intcpevap = mid.hru_intcpevap, intcp_changeover = mid.intcp_changeover;
+  const double snowmelt = mid.snowmelt, snow_evap = mid.snow_evap;
+  const double pkwater_equiv = mid.pkwater_equiv, snowcov_area = mid.snowcov_area;
+  const double through_rain = mid.through_rain;
+  const int transp_on = mid.transp_on, pptmix_nopack = mid.pptmix_nopack;
   // ===================== PRMSRunoff ======================================
   const double soil_rechr_prev = s.soil_rechr;
   const double soil_lower_prev = s.soil_moist - s.soil_rechr;  // = yesterday's soil_lower
@@ -1240,7 +1288,7 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
         avail_water = avail_water + snowmelt;
         infil = infil + snowmelt;
         if (land) {
-          if (s.pkwater_equiv > 0.0 || net_rain < PWS_NEARZERO) {
+          if (pkwater_equiv > 0.0 || net_rain < PWS_NEARZERO) {
             kind = 2;
           } else {
             kind = 1;
@@ -1248,7 +1296,7 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
             ptc = net_ppt;
           }
         }
-      } else if (s.pkwater_equiv < PWS_DNEARZERO) {
+      } else if (pkwater_equiv < PWS_DNEARZERO) {
         if (net_snow < PWS_NEARZERO && through_rain > 0.0) {
           avail_water = avail_water + through_rain;
           infil = infil + through_rain;
@@ -1264,6 +1312,7 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
       else if (kind == 2)
         check_capacity(soil_moist_prev, soil_moist_max_ro, snowinfil_max, infil, srp);
     }
+    out.sync2();
     if (hruarea_imperv > 0.0) {
       s.imperv_stor = s.imperv_stor + avail_water;
       if (land) {
@@ -1285,7 +1334,7 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
       if (pptmix_nopack) inflow = inflow + availh2o;
       if (snowmelt > 0.0) {
         inflow = inflow + snowmelt;
-      } else if (s.pkwater_equiv < PWS_DNEARZERO) {
+      } else if (pkwater_equiv < PWS_DNEARZERO) {
         if (net_snow < PWS_NEARZERO && availh2o > 0.0) inflow = inflow + availh2o;
       }
       if (open_max > 0.0) s.dprst_vol_open = s.dprst_vol_open + inflow * open_max;
@@ -1330,7 +1379,7 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
             dprst_area(s.dprst_vol_clos, vol_clos_max, clos_max, PWS_LD(P.va_clos_exp + i));
       double unsatisfied_et = avail_et;
       const double dprst_avail_et =
-          potet * (1.0 - s.snowcov_area) * PWS_LD(P.dprst_et_coef + i);
+          potet * (1.0 - snowcov_area) * PWS_LD(P.dprst_et_coef + i);
       if (dprst_avail_et > 0.0) {
         double evap_open = 0.0, evap_clos = 0.0;
         if (s.dprst_area_open > 0.0) {
@@ -1386,6 +1435,7 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
       // the public dprst_area_clos never changes after init
       dprst_area_clos = PWS_LD(P.dprst_area_clos_init + i);
     }
+    out.sync2();
     double srunoff = 0.0;
     if (land) {
       runoff = runoff + srp * PWS_LD(P.ro_hru_perv + i) + sri * hruarea_imperv;
@@ -1395,9 +1445,9 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
     if (hruarea_imperv > 0.0) {
       if (s.imperv_stor > 0.0) {
         // imperv_et prms_runoff.py:1278-1287
-        if (s.snowcov_area < 1.0) {
-          if (potet < s.imperv_stor) imperv_evap = potet * (1.0 - s.snowcov_area);
-          else imperv_evap = s.imperv_stor * (1.0 - s.snowcov_area);
+        if (snowcov_area < 1.0) {
+          if (potet < s.imperv_stor) imperv_evap = potet * (1.0 - snowcov_area);
+          else imperv_evap = s.imperv_stor * (1.0 - snowcov_area);
           if (imperv_evap * imperv_frac > avail_et) imperv_evap = avail_et / imperv_frac;
           s.imperv_stor = s.imperv_stor - imperv_evap;
         }
@@ -1443,6 +1493,7 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
                         hru_impervevap + dprst_seep_hru + dprst_evap_hru) +
                            (0 + hru_impervstor_change + dprst_stor_hru_change)));
 
+  out.sync();
   // ===================== PRMSSoilzone ====================================
   const double hru_frac_perv = PWS_LD(P.sz_hru_frac_perv + i);
   const double soil_moist_max = PWS_LD(P.sz_soil_moist_max + i);
@@ -1458,7 +1509,7 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
   double hru_actet = hru_impervevap + hru_intcpevap + snow_evap;
   if (P.dprst_flag) hru_actet = hru_actet + dprst_evap_hru;
   {
-    const double snow_free = 1.0 - s.snowcov_area;
+    const double snow_free = 1.0 - snowcov_area;
     double dunnianflw_pfr = 0.0, dunnianflw_gvr = 0.0, prefflow = 0.0;
     double avail_potet = fmax(0.0, potet - hru_actet);
     double capwater_maxin = infil_hru / hru_frac_perv;
@@ -1495,6 +1546,7 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
       }
       cap_waterin = wat * hru_frac_perv;
     }
+    out.sync2();
     double topfr = 0.0;
     double availh2o = s.slow_stor + soil_to_ssr;
     if (hru_type == HRU_LAND) {
@@ -1535,6 +1587,7 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
     } else if (hru_type == HRU_LAND) {
       dunnianflw_gvr = topfr;
     }
+    out.sync2();
     if (s.soil_moist > 0.0) {
       // _compute_szactet :1323-1456; et_type 1 default, 2 evap only, 3 evap+transp
       int et_type;
@@ -1593,6 +1646,7 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
         perv_actet = et;
       }
     }
+    out.sync2();
     hru_actet = hru_actet + perv_actet * hru_frac_perv;
     if (hru_type == HRU_LAND) {
       dunnian_flow = dunnianflw_gvr + dunnianflw_pfr;
@@ -1665,6 +1719,7 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
                            (0 + soil_rechr_change_hru + soil_lower_change_hru +
                             slow_stor_change + pref_flow_stor_change)));
 
+  out.sync();
   // ===================== PRMSGroundwater =================================
   const double gwres_stor_old = s.gwres_stor;
   double gwres_flow, gwres_sink, gwres_stor_change, gwres_flow_vol;
@@ -1700,6 +1755,17 @@ PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
   PWS_F(channel_sroff_vol, ch_sroff); PWS_F(channel_ssres_flow_vol, ch_ssres);
   PWS_F(channel_gwres_flow_vol, ch_gwres);
   out.lateral((ch_sroff + ch_ssres + ch_gwres) / 86400.0);
+}
+
+// One HRU, one day: the whole column (what the reference's Model.calculate
+// does for one unit, base/model.py:739-743).
+template <class Sink>
+PWS_DEV void column_day(const HruParams& P, const int64_t i, HruState& s,
+                        const DayIn& in, Sink& out) {
+  ColumnMid mid;
+  column_upper(P, i, s, in, out, mid);
+  out.sync();
+  column_lower(P, i, s, mid, out);
 }
 
 }  // namespace pws

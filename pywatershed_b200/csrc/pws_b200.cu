@@ -501,14 +501,15 @@ static int channel_build(pws_handle* h) {
     delay_v[i] = chunk_dmax_v[chunk_of[i]] - hops[i];
     h->max_dmax = std::max(h->max_dmax, chunk_dmax_v[chunk_of[i]]);
   }
-  // pos order: by (chunk, delay mod 24, delay, original index), so the lanes
+  // pos order: by (chunk, delay mod steps-per-day, delay, original index), so the lanes
   // of a warp cross their day boundaries in the same step; rank in `order`
   // kept for the accumulation order of upstream inflows
   std::vector<int> bypos(nseg);
   for (int64_t i = 0; i < nseg; ++i) bypos[i] = (int)i;
   std::stable_sort(bypos.begin(), bypos.end(), [&](int x, int y) {
     if (chunk_of[x] != chunk_of[y]) return chunk_of[x] < chunk_of[y];
-    if (delay_v[x] % 24 != delay_v[y] % 24) return delay_v[x] % 24 < delay_v[y] % 24;
+    constexpr int spd = 24 / PWS_ROUTE_HOURS;  // steps per day
+    if (delay_v[x] % spd != delay_v[y] % spd) return delay_v[x] % spd < delay_v[y] % spd;
     return delay_v[x] < delay_v[y];
   });
   std::vector<int> pos_of(nseg);
@@ -947,7 +948,7 @@ static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const d
   }
   cudaEvent_t e0 = new_event(h), e1 = new_event(h), e2 = new_event(h);
   cudaEventRecord(e0, h->s_compute);
-  const unsigned grid = (unsigned)((h->nhru + PWS_COLUMN_THREADS - 1) / PWS_COLUMN_THREADS);
+  const unsigned grid = (unsigned)((h->nhru + PWS_COLUMN_HRUS - 1) / PWS_COLUMN_HRUS);
   // sink: nothing selected / everything in registry order / a subset
   int mode = SINK_SELECT;
   if (h->n_f64 + h->n_i32 == 0) {
@@ -958,11 +959,11 @@ static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const d
       if (h->slot_hru[v] != full_slot(v)) mode = SINK_SELECT;
   }
   if (mode == SINK_FULL)
-    k_hru_column<SINK_FULL><<<grid, PWS_COLUMN_THREADS, kColumnSmemBytes, h->s_compute>>>(a);
+    k_hru_column<SINK_FULL><<<grid, 2 * PWS_COLUMN_HRUS, kColumnSmemBytes, h->s_compute>>>(a);
   else if (mode == SINK_NONE)
-    k_hru_column<SINK_NONE><<<grid, PWS_COLUMN_THREADS, kColumnSmemBytes, h->s_compute>>>(a);
+    k_hru_column<SINK_NONE><<<grid, 2 * PWS_COLUMN_HRUS, kColumnSmemBytes, h->s_compute>>>(a);
   else
-    k_hru_column<SINK_SELECT><<<grid, PWS_COLUMN_THREADS, kColumnSmemBytes, h->s_compute>>>(a);
+    k_hru_column<SINK_SELECT><<<grid, 2 * PWS_COLUMN_HRUS, kColumnSmemBytes, h->s_compute>>>(a);
   h->launches++;
   PWS_CUDA(h, cudaGetLastError());
   cudaEventRecord(e1, h->s_compute);
@@ -1176,7 +1177,7 @@ extern "C" int pws_column_kernel_info(pws_handle* h, int* regs, int* local_bytes
                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)kColumnSmemBytes));
   PWS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_hru_column<SINK_FULL>,
-                                                            PWS_COLUMN_THREADS, kColumnSmemBytes));
+                                                            2 * PWS_COLUMN_HRUS, kColumnSmemBytes));
   if (regs) *regs = at.numRegs;
   if (local_bytes) *local_bytes = (int)at.localSizeBytes;
   if (max_blocks_per_sm) *max_blocks_per_sm = nb;

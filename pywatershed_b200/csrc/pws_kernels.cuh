@@ -12,6 +12,20 @@
 
 #include "hru_column.cuh"
 
+// ---- build-time knobs of k_hru_column
+// HRUs per CTA; the CTA has twice as many threads (an upper-half and a
+// lower-half thread per HRU, see k_hru_column)
+#ifndef PWS_COLUMN_HRUS
+#define PWS_COLUMN_HRUS 256
+#endif
+// 1: CTA-wide (per warp group) barriers at the process boundaries inside a day
+// (see column_upper / column_lower): the warps of a group execute the same
+// stretch of code at the same time and share its instruction fetches; 2 = also
+// inside the large processes (loses more to imbalance than it gains).
+#ifndef PWS_COLUMN_SYNC
+#define PWS_COLUMN_SYNC 1
+#endif
+
 namespace pws {
 
 constexpr int kNdoy = 366;
@@ -119,186 +133,257 @@ struct GpuSink {
   unsigned stride8, stride4;  // bytes between the rows of two variables
   unsigned violmask;
   int errmask;
+  bool live;  // lanes past the last HRU compute a shadow column and store nothing
+  int group_barrier;  // named barrier of this thread's warp group
   template <int var>
   __device__ __forceinline__ void f(double v) {
     if constexpr (kMode == SINK_FULL) {
       constexpr unsigned slot = FullSlot<var>::value;
-      __stcs(reinterpret_cast<double*>(pf + (size_t)slot * stride8), v);
+      if (live) __stcs(reinterpret_cast<double*>(pf + (size_t)slot * stride8), v);
     } else if constexpr (kMode == SINK_SELECT) {
       const int64_t o = a.off[var];
-      if (o >= 0) __stcs(reinterpret_cast<double*>(pf + o), v);
+      if (o >= 0 && live) __stcs(reinterpret_cast<double*>(pf + o), v);
     }
   }
   template <int var>
   __device__ __forceinline__ void i(int v) {
     if constexpr (kMode == SINK_FULL) {
       constexpr unsigned slot = FullSlot<var>::value;
-      __stcs(reinterpret_cast<int*>(pi + (size_t)slot * stride4), v);
+      if (live) __stcs(reinterpret_cast<int*>(pi + (size_t)slot * stride4), v);
     } else if constexpr (kMode == SINK_SELECT) {
       const int64_t o = a.off[var];
-      if (o >= 0) __stcs(reinterpret_cast<int*>(pi + o), v);
+      if (o >= 0 && live) __stcs(reinterpret_cast<int*>(pi + o), v);
     }
   }
   __device__ __forceinline__ void viol(int proc, bool open) {
-    if (open) violmask |= 1u << proc;
+    if (open && live) violmask |= 1u << proc;
   }
   __device__ __forceinline__ void lateral(double v) {
-    if (plat) *plat = v;
+    if (plat && live) *plat = v;
   }
-  __device__ __forceinline__ void error(int code) { errmask |= code; }
+  __device__ __forceinline__ void error(int code) {
+    if (live) errmask |= code;
+  }
+  __device__ __forceinline__ void sync() {
+#if PWS_COLUMN_SYNC >= 1
+    asm volatile("bar.sync %0, %1;" ::"r"(group_barrier), "n"(PWS_COLUMN_HRUS) : "memory");
+#endif
+  }
+  __device__ __forceinline__ void sync2() {
+#if PWS_COLUMN_SYNC >= 2
+    asm volatile("bar.sync %0, %1;" ::"r"(group_barrier), "n"(PWS_COLUMN_HRUS) : "memory");
+#endif
+  }
 };
 
-#ifndef PWS_COLUMN_THREADS
-#define PWS_COLUMN_THREADS 128
-#endif
-#ifndef PWS_COLUMN_MIN_BLOCKS
-#define PWS_COLUMN_MIN_BLOCKS 2
-#endif
-// 1: every per-HRU parameter column_day reads is staged once per launch (the
-// monthly ones once per month) in shared memory, one private column per
-// thread -- no inter-thread sharing, so no barrier.  0: read through L1/L2.
-#ifndef PWS_COLUMN_SMEM
-#define PWS_COLUMN_SMEM 1
-#endif
+#define PWS_COUNT(n) +1
+constexpr int kUpperF64 = 0 PWS_UPPER_F64(PWS_COUNT);
+constexpr int kUpperMonF64 = 0 PWS_UPPER_MON_F64(PWS_COUNT);
+constexpr int kUpperI32 = 0 PWS_UPPER_I32(PWS_COUNT) PWS_UPPER_MON_I32(PWS_COUNT);
+constexpr int kLowerF64 = 0 PWS_LOWER_F64(PWS_COUNT);
+constexpr int kLowerI32 = 0 PWS_LOWER_I32(PWS_COUNT);
+#undef PWS_COUNT
+constexpr int kMidF64 = 10, kMidI32 = 2;  // ColumnMid
+constexpr int kColF64 = kUpperF64 + kUpperMonF64 + kLowerF64 + kMidF64;
+constexpr int kColI32 = kUpperI32 + kLowerI32 + kMidI32;
+constexpr size_t kColumnSmemBytes = (size_t)PWS_COLUMN_HRUS * (kColF64 * 8 + kColI32 * 4);
 
-constexpr int kDailyF64 = 0
-#define X(n) +1
-    PWS_DAILY_F64(X)
-#undef X
-    ;
-constexpr int kDailyMonF64 = 0
-#define X(n) +1
-    PWS_DAILY_MON_F64(X)
-#undef X
-    ;
-constexpr int kDailyI32 = 0
-#define X(n) +1
-    PWS_DAILY_I32(X) PWS_DAILY_MON_I32(X)
-#undef X
-    ;
-constexpr size_t kColumnSmemBytes =
-    PWS_COLUMN_SMEM ? (size_t)PWS_COLUMN_THREADS * ((kDailyF64 + kDailyMonF64) * 8 + kDailyI32 * 4)
-                    : 0;
+// named barriers of k_hru_column (0 is __syncthreads)
+enum { BAR_MID_FULL = 1, BAR_MID_EMPTY = 2, BAR_UPPER = 3, BAR_LOWER = 4 };
 
+__device__ __forceinline__ void bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// The fused column.  A CTA owns H = PWS_COLUMN_HRUS HRUs and has 2 H threads:
+// warps [0, H/32) run the UPPER half of the column (atmosphere, canopy, snow)
+// and warps [H/32, 2H/32) the LOWER half (runoff, soilzone, groundwater) of
+// the same HRUs, one day behind, as a producer/consumer pipeline: the upper
+// thread of an HRU leaves the ten values the lower half needs (ColumnMid) in
+// shared memory and the two groups hand the slot over with named barriers
+// (BAR_MID_FULL / BAR_MID_EMPTY).  Nothing in the upper half depends on the
+// lower half, so the groups overlap completely; each thread carries only its
+// half of the prognostic state in registers and stages only its half of the
+// parameters, which doubles the number of resident warps for the same
+// register file and shared memory, and each warp walks only its half of the
+// code.
 template <int kMode>
-__global__ void __launch_bounds__(PWS_COLUMN_THREADS, PWS_COLUMN_MIN_BLOCKS)
+__global__ void __launch_bounds__(2 * PWS_COLUMN_HRUS, 1)
 k_hru_column(const __grid_constant__ ColumnArgs a) {
-  constexpr int T = PWS_COLUMN_THREADS;
+  constexpr int H = PWS_COLUMN_HRUS;
   const int tid = threadIdx.x;
-  const int64_t i = (int64_t)blockIdx.x * T + tid;
+  const bool upper = tid < H;  // warp-uniform
+  const int r = upper ? tid : tid - H;
+  const int64_t i = (int64_t)blockIdx.x * H + r;
   const bool live = i < a.P.nhru;
   const int64_t ii = live ? i : a.P.nhru - 1;  // dead lanes shadow the last HRU, never store
   const int64_t S = a.P.stride;
-  HruState s;
-#define PWS_LOADST_F(name) s.name = a.state[(int64_t)ST_##name * S + ii];
-#define PWS_LOADST_I(name) s.name = (int)a.state[(int64_t)ST_##name * S + ii];
-#define X(name, kind) PWS_LOADST_##kind(name)
-  PWS_HRU_STATE(X)
-#undef X
 
-#if PWS_COLUMN_SMEM
-  // Q: the parameter view column_day sees, indexed by tid.  Staged columns
-  // live in shared memory; anything else is the global array re-based so that
-  // [tid] is this thread's HRU.
+  // shared memory: one private column per thread and staged quantity
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* const sp = reinterpret_cast<double*>(smem_raw);
-  int32_t* const spi = reinterpret_cast<int32_t*>(sp + (size_t)(kDailyF64 + kDailyMonF64) * T);
-  HruParams Q = a.P;
-  Q.stride = 0;  // monthly rows: only the current month is staged
-  {
-    int k = 0;
-#define X(n) sp[k * T + tid] = __ldg(a.P.n + ii); Q.n = sp + k * T; ++k;
-    PWS_DAILY_F64(X)
-#undef X
-    k = 0;
-#define X(n) spi[k * T + tid] = __ldg(a.P.n + ii); Q.n = spi + k * T; ++k;
-    PWS_DAILY_I32(X)
-#undef X
-  }
-  auto stage_month = [&](int month) {
-    const int64_t mo = (int64_t)(month - 1) * S + ii;
-    int k = kDailyF64;
-#define X(n) sp[k * T + tid] = __ldg(a.P.n + mo); ++k;
-    PWS_DAILY_MON_F64(X)
-#undef X
-    k = kDailyI32 - 1;
-#define X(n) spi[k * T + tid] = __ldg(a.P.n + mo);
-    PWS_DAILY_MON_I32(X)
-#undef X
-  };
-  {
-    int k = kDailyF64;
-#define X(n) Q.n = sp + k * T; ++k;
-    PWS_DAILY_MON_F64(X)
-#undef X
-    k = kDailyI32 - 1;
-#define X(n) Q.n = spi + k * T;
-    PWS_DAILY_MON_I32(X)
-#undef X
-  }
-  int staged_month = 0;
-  const int64_t pidx = tid;
-#else
-  const HruParams& Q = a.P;
-  const int64_t pidx = ii;
-#endif
+  double* const spU = reinterpret_cast<double*>(smem_raw);           // upper f64 (+ monthly)
+  double* const spL = spU + (size_t)(kUpperF64 + kUpperMonF64) * H;  // lower f64
+  double* const spM = spL + (size_t)kLowerF64 * H;                   // ColumnMid f64
+  int32_t* const siU = reinterpret_cast<int32_t*>(spM + (size_t)kMidF64 * H);
+  int32_t* const siL = siU + (size_t)kUpperI32 * H;
+  int32_t* const siM = siL + (size_t)kLowerI32 * H;
 
   GpuSink<kMode> out{a, nullptr, nullptr, nullptr, (unsigned)(a.ostride * 8),
-                     (unsigned)(a.ostride * 4), 0u, 0};
-  // forcing prefetch: day d+1 is in flight while day d computes
-  DayIn nxt;
-  {
-    const int4 c = a.cal[0];
-    nxt.doy = c.x; nxt.dowy = c.y; nxt.month = c.z; nxt.dom = c.w;
-    nxt.prcp = __ldcs(a.prcp + ii);
-    nxt.tmax = __ldcs(a.tmax + ii);
-    nxt.tmin = __ldcs(a.tmin + ii);
-    nxt.potsw = __ldg(a.P.soltab_potsw + (int64_t)(c.x - 1) * S + ii);
-    nxt.horad = __ldg(a.P.soltab_horad_potsw + (int64_t)(c.x - 1) * S + ii);
-  }
+                     (unsigned)(a.ostride * 4), 0u, 0, live, upper ? BAR_UPPER : BAR_LOWER};
   const int64_t day_f64 = (int64_t)a.n_f64 * a.ostride * 8;
   const int64_t day_i32 = (int64_t)a.n_i32 * a.ostride * 4;
   out.pf = reinterpret_cast<char*>(a.out_f64 + ii);
   out.pi = reinterpret_cast<char*>(a.out_i32 + ii);
-  for (int d = 0; d < a.ndays; ++d) {
-    const DayIn in = nxt;
-    if (d + 1 < a.ndays) {
-      const int4 c = a.cal[d + 1];
-      const int64_t fo = (int64_t)(d + 1) * a.fstride + ii;
-      nxt.doy = c.x; nxt.dowy = c.y; nxt.month = c.z; nxt.dom = c.w;
-      nxt.prcp = __ldcs(a.prcp + fo);
-      nxt.tmax = __ldcs(a.tmax + fo);
-      nxt.tmin = __ldcs(a.tmin + fo);
-      nxt.potsw = __ldg(a.P.soltab_potsw + (int64_t)(c.x - 1) * S + ii);
-      nxt.horad = __ldg(a.P.soltab_horad_potsw + (int64_t)(c.x - 1) * S + ii);
-    }
-#if PWS_COLUMN_SMEM
-    if (in.month != staged_month) {  // warp-uniform
-      stage_month(in.month);
-      staged_month = in.month;
-    }
-#endif
-    out.violmask = 0u;
-    if (live) {
-      out.plat = a.hru_lat ? a.hru_lat + (int64_t)d * S + i : nullptr;
-      column_day(Q, pidx, s, in, out);
-    }
-    out.pf += day_f64;
-    out.pi += day_i32;
+  auto reduce_violations = [&](int d) {
     if (a.viol != nullptr && __any_sync(0xffffffffu, out.violmask != 0u)) {
       for (int p = 0; p < BUD_CHANNEL; ++p) {
         const unsigned m = __ballot_sync(0xffffffffu, (out.violmask >> p) & 1u);
         if (m != 0u && (threadIdx.x & 31) == 0) atomicAdd(a.viol + d * BUD_N + p, __popc(m));
       }
     }
-  }
-  if (live) {
+  };
+  HruState s;
+  // Q: the parameter view column_upper / column_lower see, indexed by r
+  HruParams Q = a.P;
+  Q.stride = 0;  // monthly rows: only the current month is staged
+
+  if (upper) {
+#define PWS_LOADST_F(name) s.name = a.state[(int64_t)ST_##name * S + ii];
+#define PWS_LOADST_I(name) s.name = (int)a.state[(int64_t)ST_##name * S + ii];
+#define X(name, kind) PWS_LOADST_##kind(name)
+    PWS_HRU_STATE_UPPER(X)
+#undef X
+    {
+      int k = 0;
+#define X(n) spU[k * H + r] = __ldg(a.P.n + ii); Q.n = spU + k * H; ++k;
+      PWS_UPPER_F64(X)
+#undef X
+#define X(n) Q.n = spU + k * H; ++k;
+      PWS_UPPER_MON_F64(X)
+#undef X
+      k = 0;
+#define X(n) siU[k * H + r] = __ldg(a.P.n + ii); Q.n = siU + k * H; ++k;
+      PWS_UPPER_I32(X)
+#undef X
+#define X(n) Q.n = siU + k * H; ++k;
+      PWS_UPPER_MON_I32(X)
+#undef X
+    }
+    auto stage_month = [&](int month) {
+      const int64_t mo = (int64_t)(month - 1) * S + ii;
+      int k = kUpperF64;
+#define X(n) spU[k * H + r] = __ldg(a.P.n + mo); ++k;
+      PWS_UPPER_MON_F64(X)
+#undef X
+      k = kUpperI32 - 1;
+#define X(n) siU[k * H + r] = __ldg(a.P.n + mo);
+      PWS_UPPER_MON_I32(X)
+#undef X
+    };
+    int staged_month = 0;
+    // forcing prefetch: day d+1 is in flight while day d computes
+    DayIn nxt;
+    {
+      const int4 c = a.cal[0];
+      nxt.doy = c.x; nxt.dowy = c.y; nxt.month = c.z; nxt.dom = c.w;
+      nxt.prcp = __ldcs(a.prcp + ii);
+      nxt.tmax = __ldcs(a.tmax + ii);
+      nxt.tmin = __ldcs(a.tmin + ii);
+      nxt.potsw = __ldg(a.P.soltab_potsw + (int64_t)(c.x - 1) * S + ii);
+      nxt.horad = __ldg(a.P.soltab_horad_potsw + (int64_t)(c.x - 1) * S + ii);
+    }
+    for (int d = 0; d < a.ndays; ++d) {
+      const DayIn in = nxt;
+      if (d + 1 < a.ndays) {
+        const int4 c = a.cal[d + 1];
+        const int64_t fo = (int64_t)(d + 1) * a.fstride + ii;
+        nxt.doy = c.x; nxt.dowy = c.y; nxt.month = c.z; nxt.dom = c.w;
+        nxt.prcp = __ldcs(a.prcp + fo);
+        nxt.tmax = __ldcs(a.tmax + fo);
+        nxt.tmin = __ldcs(a.tmin + fo);
+        nxt.potsw = __ldg(a.P.soltab_potsw + (int64_t)(c.x - 1) * S + ii);
+        nxt.horad = __ldg(a.P.soltab_horad_potsw + (int64_t)(c.x - 1) * S + ii);
+      }
+      if (in.month != staged_month) {  // warp-uniform
+        stage_month(in.month);
+        staged_month = in.month;
+      }
+      out.violmask = 0u;
+      ColumnMid mid;
+      column_upper(Q, (int64_t)r, s, in, out, mid);
+      // hand the day over to the lower half of this HRU
+      if (d > 0) bar_sync(BAR_MID_EMPTY, 2 * H);  // the lower group has read day d - 1
+      spM[0 * H + r] = mid.potet;
+      spM[1 * H + r] = mid.net_rain;
+      spM[2 * H + r] = mid.net_snow;
+      spM[3 * H + r] = mid.hru_intcpevap;
+      spM[4 * H + r] = mid.intcp_changeover;
+      spM[5 * H + r] = mid.snowmelt;
+      spM[6 * H + r] = mid.snow_evap;
+      spM[7 * H + r] = mid.pkwater_equiv;
+      spM[8 * H + r] = mid.snowcov_area;
+      spM[9 * H + r] = mid.through_rain;
+      siM[0 * H + r] = mid.transp_on;
+      siM[1 * H + r] = mid.pptmix_nopack;
+      __threadfence_block();
+      bar_arrive(BAR_MID_FULL, 2 * H);
+      out.pf += day_f64;
+      out.pi += day_i32;
+      reduce_violations(d);
+    }
+    if (live) {
 #define PWS_STOREST(name) a.state[(int64_t)ST_##name * S + i] = (double)s.name;
 #define X(name, kind) PWS_STOREST(name)
-    PWS_HRU_STATE(X)
+      PWS_HRU_STATE_UPPER(X)
 #undef X
-    if (out.errmask) atomicOr(a.err, out.errmask);
+    }
+  } else {
+#define X(name, kind) PWS_LOADST_##kind(name)
+    PWS_HRU_STATE_LOWER(X)
+#undef X
+    {
+      int k = 0;
+#define X(n) spL[k * H + r] = __ldg(a.P.n + ii); Q.n = spL + k * H; ++k;
+      PWS_LOWER_F64(X)
+#undef X
+      k = 0;
+#define X(n) siL[k * H + r] = __ldg(a.P.n + ii); Q.n = siL + k * H; ++k;
+      PWS_LOWER_I32(X)
+#undef X
+    }
+    for (int d = 0; d < a.ndays; ++d) {
+      ColumnMid mid;
+      bar_sync(BAR_MID_FULL, 2 * H);  // the upper group has written day d
+      mid.potet = spM[0 * H + r];
+      mid.net_rain = spM[1 * H + r];
+      mid.net_snow = spM[2 * H + r];
+      mid.hru_intcpevap = spM[3 * H + r];
+      mid.intcp_changeover = spM[4 * H + r];
+      mid.snowmelt = spM[5 * H + r];
+      mid.snow_evap = spM[6 * H + r];
+      mid.pkwater_equiv = spM[7 * H + r];
+      mid.snowcov_area = spM[8 * H + r];
+      mid.through_rain = spM[9 * H + r];
+      mid.transp_on = siM[0 * H + r];
+      mid.pptmix_nopack = siM[1 * H + r];
+      if (d + 1 < a.ndays) bar_arrive(BAR_MID_EMPTY, 2 * H);
+      out.violmask = 0u;
+      out.plat = a.hru_lat ? a.hru_lat + (int64_t)d * S + ii : nullptr;
+      column_lower(Q, (int64_t)r, s, mid, out);
+      out.pf += day_f64;
+      out.pi += day_i32;
+      reduce_violations(d);
+    }
+    if (live) {
+#define X(name, kind) PWS_STOREST(name)
+      PWS_HRU_STATE_LOWER(X)
+#undef X
+    }
   }
+  if (live && out.errmask) atomicOr(a.err, out.errmask);
 }
 
 // ---------------------------------------------------------------- channel
@@ -313,10 +398,11 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
 //     them into chunks.  In a tree every segment has ONE downstream segment,
 //     so with delay(i) = dmax - (hops from i to the root of its chunk-local
 //     tree) every local upstream segment of i is exactly one step ahead of i.
-//   * At step t, segment i advances hour t - delay(i).  The outflow it
-//     publishes goes to a double-buffered shared-memory slot; its downstream
-//     segment reads it in the next step.  One __syncthreads() per step is the
-//     only synchronisation; a block of T days takes 24 T + dmax steps.
+//   * At step t, segment i advances the G = PWS_ROUTE_HOURS hours
+//     G (t - delay(i)) ...  The outflows it publishes go to a double-buffered
+//     shared-memory slot; its downstream segment reads them in the next step.
+//     One __syncthreads() per step is the only synchronisation; a block of T
+//     days takes 24 T / G + dmax steps.
 //   * Edges that cross chunks (only when a tree does not fit one chunk) go
 //     through a global scratch row per day and a per-segment progress counter
 //     with device-scope fences.  Chunks are numbered so that a chunk only
@@ -378,17 +464,25 @@ enum {
 #ifndef PWS_ROUTE_MAX_IDLE
 #define PWS_ROUTE_MAX_IDLE (1 << 24)
 #endif
+// hours a segment advances per systolic step (divides 24): one barrier, one
+// shared-memory round trip and one set of loop overheads per PWS_ROUTE_HOURS
+// hourly updates; the pipeline fill grows to PWS_ROUTE_HOURS * dmax hours
+#ifndef PWS_ROUTE_HOURS
+#define PWS_ROUTE_HOURS 4
+#endif
 
 __global__ void __launch_bounds__(PWS_CHUNK_THREADS, 1)
 k_route_chunks(const __grid_constant__ ChannelArgs a) {
   constexpr int kZero = PWS_CHUNK_THREADS;  // a slot that always holds 0.0
-  __shared__ double s_out[2][PWS_CHUNK_THREADS + 1];
+  constexpr int G = PWS_ROUTE_HOURS;
+  constexpr int kStepsPerDay = 24 / G;
+  static_assert(24 % G == 0, "PWS_ROUTE_HOURS must divide 24");
+  __shared__ double s_out[2][G][PWS_CHUNK_THREADS + 1];
   __shared__ int s_chunk;
   const int tid = threadIdx.x;
   if (tid == 0) {
     s_chunk = atomicAdd(a.ticket, 1);
-    s_out[0][kZero] = 0.0;
-    s_out[1][kZero] = 0.0;
+    for (int g = 0; g < G; ++g) s_out[0][g][kZero] = s_out[1][g][kZero] = 0.0;
   }
   __syncthreads();
   const int chunk = s_chunk;
@@ -484,28 +578,30 @@ k_route_chunks(const __grid_constant__ ChannelArgs a) {
     outflow_ts = a.outflow_ts[pos];
     seg_inflow_prev = a.seg_inflow[pos];
   }
-  // The start of day k falls into window k + delay / 24; at every window start
-  // the lateral inflow for the day starting in the NEXT window is requested.
-  const int dd = delay / 24;
+  // A window = the kStepsPerDay steps of one day.  The start of day k falls
+  // into window k + delay / kStepsPerDay; at every window start the lateral
+  // inflow for the day starting in the NEXT window is requested.
+  const int dd = delay / kStepsPerDay;
   fetch_lateral(-dd);
   double lat_window = 0.0;  // lateral inflow of the day that starts in the current window
   double lateral = 0.0, seg_inflow0 = 0.0, seg_inflow = 0.0, seg_outflow = 0.0;
   double inflow_ts = 0.0, cur_sum = 0.0;
   int d = 0, h = 0;
-  const int nsteps = 24 * T + dmax;
-  int x = -delay;  // hour of the block this segment advances in step t
-  for (int t = 0, tw = 0, w = 0; t < nsteps; ++t, ++x) {
+  const int nsteps = kStepsPerDay * T + dmax;
+  for (int t = 0, tw = 0, w = 0; t < nsteps; ++t) {
     if (tw == 0) {  // window start (uniform across the CTA)
       flush_day();
       lat_window = ((0.0 + qa) + qb) + qr;
       fetch_lateral(w + 1 - dd);
     }
-    if (++tw == 24) {
+    if (++tw == kStepsPerDay) {
       tw = 0;
       ++w;
     }
-    const double* rd = s_out[(t & 1) ^ 1];  // published in step t - 1
-    if (live && x >= 0 && x < 24 * T) {
+    const double(*rd)[PWS_CHUNK_THREADS + 1] = s_out[(t & 1) ^ 1];  // published in step t - 1
+    double(*wr)[PWS_CHUNK_THREADS + 1] = s_out[t & 1];
+    const int ts_local = t - delay;  // this segment's own step number
+    if (live && ts_local >= 0 && ts_local < kStepsPerDay * T) {
       if (h == 0) {
         lateral = lat_window;
         seg_inflow0 = seg_inflow_prev;  // _advance_variables, prms_channel.py:384-386
@@ -530,32 +626,37 @@ k_route_chunks(const __grid_constant__ ChannelArgs a) {
           __threadfence();  // acquire: the rows are visible after the counter
         }
       }
-      double up;
-      if (fast_up) {
-        up = (rd[u0] + rd[u1]) + rd[u2];  // absent ones read the 0.0 slot
-      } else {
-        up = 0.0;
-        for (int k = ub; k < ue; ++k) {
-          const int u = a.up_idx[k];
-          if (u >= cb && u < ce) up += rd[u - cb];
-          else up += __ldcg(a.ots + (int64_t)a.ext_row[u] * row_len + d * 24 + h);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        double up;
+        if (fast_up) {
+          up = (rd[g][u0] + rd[g][u1]) + rd[g][u2];  // absent ones read the 0.0 slot
+        } else {
+          up = 0.0;
+          for (int k = ub; k < ue; ++k) {
+            const int u = a.up_idx[k];
+            if (u >= cb && u < ce) up += rd[g][u - cb];
+            else up += __ldcg(a.ots + (int64_t)a.ext_row[u] * row_len + d * 24 + h + g);
+          }
         }
+        const double cur = lateral + up;
+        seg_inflow += cur;
+        cur_sum += up;
+        const double acc = inflow_ts + cur;
+        // routing update (branch-free; most segments update every hour)
+        const bool upd = (fire >> (h + g)) & 1u;
+        const double xq = divide ? div_by_ts(acc, ts, rts) : acc;
+        const double routed = muskingum ? (xq * c0 + seg_inflow0 * c1) + outflow_ts * c2 : xq;
+        outflow_ts = upd ? routed : outflow_ts;
+        seg_inflow0 = upd ? xq : seg_inflow0;
+        inflow_ts = upd ? 0.0 : acc;
+        seg_outflow += outflow_ts;
+        wr[g][tid] = outflow_ts;
+        if (ext_row >= 0)
+          __stcg(a.ots + (int64_t)ext_row * row_len + d * 24 + h + g, outflow_ts);
       }
-      const double cur = lateral + up;
-      seg_inflow += cur;
-      cur_sum += up;
-      const double acc = inflow_ts + cur;
-      // routing update (branch-free; most segments update every hour)
-      const bool upd = (fire >> h) & 1u;
-      const double xq = divide ? div_by_ts(acc, ts, rts) : acc;
-      const double routed = muskingum ? (xq * c0 + seg_inflow0 * c1) + outflow_ts * c2 : xq;
-      outflow_ts = upd ? routed : outflow_ts;
-      seg_inflow0 = upd ? xq : seg_inflow0;
-      inflow_ts = upd ? 0.0 : acc;
-      seg_outflow += outflow_ts;
-      s_out[t & 1][tid] = outflow_ts;
-      if (ext_row >= 0) __stcg(a.ots + (int64_t)ext_row * row_len + d * 24 + h, outflow_ts);
-      if (h == 23) {
+      h += G;
+      if (h == 24) {
         seg_outflow = div_by_ts(seg_outflow, 24.0, 1.0 / 24.0);
         seg_inflow = div_by_ts(seg_inflow, 24.0, 1.0 / 24.0);
         st_up = div_by_ts(cur_sum, 24.0, 1.0 / 24.0);
@@ -571,8 +672,6 @@ k_route_chunks(const __grid_constant__ ChannelArgs a) {
         }
         ++d;
         h = 0;
-      } else {
-        ++h;
       }
     }
     __syncthreads();

@@ -136,51 +136,59 @@
 // Lives in registers inside the column kernel, in a device SoA between
 // launches; pws_get_state/pws_set_state expose it (restart-ready; the
 // reference declares but does not implement restart, prms_snow.py:269-293).
-#define PWS_HRU_STATE(X)                                                      \
+#define PWS_HRU_STATE_UPPER(X)                                                \
   X(transp_on, I) X(transp_check, I) X(tmax_sum, F)                           \
   X(intcp_stor, F) X(intcp_transp_on, I) X(hru_intcpstor, F)                  \
   X(albedo, F) X(freeh2o, F) X(iasw, I) X(int_alb, I) X(iso, I) X(lso, I)     \
   X(lst, I) X(mso, I) X(pk_def, F) X(pk_depth, F) X(pk_den, F) X(pk_ice, F)   \
   X(pk_temp, F) X(pksv, F) X(pss, F) X(pst, F) X(salb, F) X(scrv, F)          \
   X(slst, F) X(snowcov_area, F) X(snowcov_areasv, F) X(snsv, F)               \
-  X(pkwater_equiv, F)                                                         \
+  X(pkwater_equiv, F)
+#define PWS_HRU_STATE_LOWER(X)                                                \
   X(imperv_stor, F) X(hru_impervstor, F) X(dprst_vol_open, F)                 \
   X(dprst_vol_clos, F) X(dprst_area_open, F)                                  \
   X(soil_moist, F) X(soil_rechr, F) X(slow_stor, F) X(pref_flow_stor, F)      \
   X(gwres_stor, F)
+// upper half of the column (atmosphere, canopy, snow) first, then the lower
+// half (runoff, soilzone, groundwater): k_hru_column gives each half its own warps
+#define PWS_HRU_STATE(X) PWS_HRU_STATE_UPPER(X) PWS_HRU_STATE_LOWER(X)
 
 
-// ---- what column_day reads every day, per HRU (generated from the PWS_LD
-// uses in hru_column.cuh; k_hru_column stages exactly these in shared memory,
-// one private column per thread) -------------------------------------------
-#define PWS_DAILY_F64(X) \
-  X(carea_max) X(covden_sum) X(covden_win) X(den_max) X(deninv) X(denmaxinv) \
-  X(dprst_area_clos_init) X(dprst_area_clos_max) X(dprst_area_max) \
-  X(dprst_area_open_max) X(dprst_et_coef) X(dprst_flow_coef) \
-  X(dprst_frac_clos) X(dprst_frac_open) X(dprst_seep_rate_clos) \
-  X(dprst_seep_rate_open) X(dprst_vol_clos_max) X(dprst_vol_open_max) \
-  X(dprst_vol_thres_open) X(emis_noppt) X(fastcoef_lin) X(fastcoef_sq) \
-  X(freeh2o_cap) X(gwflow_coef) X(gwsink_coef) X(hru_area) X(hru_cossl) \
-  X(hru_in_to_cf) X(hru_percent_imperv) X(imperv_stor_max) X(jh_coef_hru) \
-  X(potet_sublim) X(pref_flow_infil_frac) X(pref_flow_max) \
-  X(pref_flow_thrsh) X(rad_trncf) X(radj_sppt) X(radj_wppt) \
-  X(ro_hru_frac_perv) X(ro_hru_imperv) X(ro_hru_perv) X(settle_const) \
-  X(slowcoef_lin) X(slowcoef_sq) X(smidx_coef) X(smidx_exp) X(snarea_thresh) \
-  X(snow_intcp) X(snowinfil_max) X(soil2gw_max) X(soil_lower_max) \
-  X(soil_lower_ratio_init) X(soil_moist_max) X(soil_zone_max) X(srain_intcp) \
+// ---- what the two halves of the column read every day, per HRU (generated
+// from the P.<name> uses in column_upper / column_lower, hru_column.cuh);
+// k_hru_column stages exactly these in shared memory, one private column per
+// thread.  Monthly parameters are only read by the upper half.
+#define PWS_UPPER_F64(X) \
+  X(covden_sum) X(covden_win) X(den_max) X(deninv) X(denmaxinv) \
+  X(emis_noppt) X(freeh2o_cap) X(hru_cossl) X(jh_coef_hru) X(potet_sublim) \
+  X(rad_trncf) X(radj_sppt) X(radj_wppt) X(settle_const) X(snarea_thresh) \
+  X(snow_intcp) X(srain_intcp) X(transp_tmax) X(wrain_intcp)
+#define PWS_UPPER_I32(X) \
+  X(cov_type) X(hru_deplcrv) X(hru_type) X(melt_force) X(melt_look) \
+  X(transp_beg) X(transp_end)
+#define PWS_LOWER_F64(X) \
+  X(carea_max) X(dprst_area_clos_init) X(dprst_area_clos_max) \
+  X(dprst_area_max) X(dprst_area_open_max) X(dprst_et_coef) \
+  X(dprst_flow_coef) X(dprst_frac_clos) X(dprst_frac_open) \
+  X(dprst_seep_rate_clos) X(dprst_seep_rate_open) X(dprst_vol_clos_max) \
+  X(dprst_vol_open_max) X(dprst_vol_thres_open) X(fastcoef_lin) \
+  X(fastcoef_sq) X(gwflow_coef) X(gwsink_coef) X(hru_area) X(hru_in_to_cf) \
+  X(hru_percent_imperv) X(imperv_stor_max) X(pref_flow_infil_frac) \
+  X(pref_flow_max) X(pref_flow_thrsh) X(ro_hru_frac_perv) X(ro_hru_imperv) \
+  X(ro_hru_perv) X(slowcoef_lin) X(slowcoef_sq) X(smidx_coef) X(smidx_exp) \
+  X(snowinfil_max) X(soil2gw_max) X(soil_lower_max) \
+  X(soil_lower_ratio_init) X(soil_moist_max) X(soil_zone_max) \
   X(sro_to_dprst_imperv) X(sro_to_dprst_perv) X(ssr2gw_exp) X(ssr2gw_rate) \
   X(sz_hru_frac_perv) X(sz_pref_flow_den) X(sz_sat_threshold) \
-  X(sz_soil_moist_max) X(sz_soil_rechr_max) X(transp_tmax) X(va_clos_exp) \
-  X(va_open_exp) X(wrain_intcp)
-#define PWS_DAILY_I32(X) \
-  X(cov_type) X(hru_deplcrv) X(hru_segment) X(hru_type) X(melt_force) \
-  X(melt_look) X(soil_type) X(transp_beg) X(transp_end)
-#define PWS_DAILY_MON_F64(X) \
+  X(sz_soil_moist_max) X(sz_soil_rechr_max) X(va_clos_exp) X(va_open_exp)
+#define PWS_LOWER_I32(X) \
+  X(cov_type) X(hru_segment) X(hru_type) X(soil_type)
+#define PWS_UPPER_MON_F64(X) \
   X(adjmix_rain) X(cecn_coef) X(dday_intcp) X(dday_slope) X(jh_coef) \
   X(ppt_rad_adj) X(radadj_intcp) X(radadj_slope) X(radmax) X(rain_cbh_adj) \
   X(snow_cbh_adj) X(tmax_allrain_offset) X(tmax_allsnow) X(tmax_allsnow_c) \
   X(tmax_cbh_adj) X(tmax_index) X(tmin_cbh_adj)
-#define PWS_DAILY_MON_I32(X) \
+#define PWS_UPPER_MON_I32(X) \
   X(tstorm_mo)
 
 enum PwsHruVar {

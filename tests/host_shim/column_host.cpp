@@ -35,6 +35,8 @@ struct HostSink {
   template <int var> void i(int v) { out[(int64_t)var * nhru] = (double)v; }
   void viol(int proc, bool open) { if (open && pv) pv[proc]++; }
   void lateral(double) {}
+  void sync() {}
+  void sync2() {}
   void error(int c) { err |= c; }
 };
 }  // namespace
