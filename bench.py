@@ -254,7 +254,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="conus")
     ap.add_argument("--outputs", default="full")
-    ap.add_argument("--block-days", type=int, default=128)
+    ap.add_argument("--block-days", type=int, default=256)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -275,6 +275,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     import __graft_entry__ as g

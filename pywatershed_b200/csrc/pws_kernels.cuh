@@ -149,8 +149,13 @@ struct GpuSink {
   template <int var>
   __device__ __forceinline__ void f(double v) {
     if constexpr (kMode == SINK_FULL) {
+      // one IMAD.WIDE (row * stride + pointer) and one STG.CS per value
       constexpr unsigned slot = FullSlot<var>::value;
-      if (live) __stcs(reinterpret_cast<double*>(pf + (size_t)slot * stride8), v);
+      unsigned long long addr;
+      asm("mad.wide.u32 %0, %1, %2, %3;"
+          : "=l"(addr)
+          : "r"(stride8), "n"(slot), "l"((unsigned long long)pf));
+      if (live) asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(addr), "d"(v));
     } else if constexpr (kMode == SINK_SELECT) {
       const int64_t o = a.off[var];
       if (o >= 0 && live) __stcs(reinterpret_cast<double*>(pf + o), v);
@@ -160,7 +165,11 @@ struct GpuSink {
   __device__ __forceinline__ void i(int v) {
     if constexpr (kMode == SINK_FULL) {
       constexpr unsigned slot = FullSlot<var>::value;
-      if (live) __stcs(reinterpret_cast<int*>(pi + (size_t)slot * stride4), v);
+      unsigned long long addr;
+      asm("mad.wide.u32 %0, %1, %2, %3;"
+          : "=l"(addr)
+          : "r"(stride4), "n"(slot), "l"((unsigned long long)pi));
+      if (live) asm volatile("st.global.cs.s32 [%0], %1;" ::"l"(addr), "r"(v));
     } else if constexpr (kMode == SINK_SELECT) {
       const int64_t o = a.off[var];
       if (o >= 0 && live) __stcs(reinterpret_cast<int*>(pi + o), v);

@@ -288,6 +288,80 @@ def test_tiled_domain_and_ragged_sizes(drb):
         parity.assert_segments_close(got, ref, po.SEG_VARS)
 
 
+def _subset(p, f, hru_idx):
+    """The HRU columns `hru_idx` of a domain, without segments."""
+    nhru = p["hru_area"].shape[0]
+    nseg = p["tosegment"].shape[0]
+    q = {}
+    for k, v in p.items():
+        v = np.asarray(v)
+        if k in ("tosegment", "tosegment_nhm", "nhm_seg") or (v.ndim >= 1 and v.shape[-1] == nseg and k in (
+                "mann_n", "seg_depth", "seg_length", "seg_slope", "x_coef", "segment_flow_init", "segment_type")):
+            q[k] = v
+        elif v.ndim >= 1 and v.shape[-1] == nhru and k != "snarea_curve":
+            q[k] = np.ascontiguousarray(v[..., hru_idx])
+        else:
+            q[k] = v
+    return q, {k: np.ascontiguousarray(v[:, hru_idx]) for k, v in f.items()}
+
+
+@pytest.mark.parametrize("n", [1, 31, 257])
+def test_tiny_and_odd_domains(drbx, n):
+    """hru_1-sized and warp / CTA-straddling domains (the reference's smallest
+    test domain has one HRU): columns only, every variable against the oracle."""
+    p, f, start = drbx
+    idx = np.arange(n) * 2 + 2
+    q, g = _subset(p, f, idx)
+    q["hru_segment"] = np.zeros_like(q["hru_segment"])  # columns only: no HRU drains to a segment
+    nd = 200
+    e = _engine(q, start, channel=False)
+    e.select_outputs(e.reg.hru_vars, ())
+    got, viol = e.run_host(g["prcp"][:nd], g["tmax"][:nd], g["tmin"][:nd])
+    o = po.Oracle(q, start=start)
+    ref, oviol = o.run(g["prcp"][:nd], g["tmax"][:nd], g["tmin"][:nd], po.HRU_VARS, ())
+    rep = parity.compare_columns(got, ref, po.HRU_VARS, got["pkwater_equiv"], ref["pkwater_equiv"])
+    assert rep["mismatches"] == [], rep["mismatches"][:3]
+    assert len(rep["ties"]) <= max(1, n // 30)
+    # zero days is a no-op
+    got0, _ = e.run_host(g["prcp"][:0], g["tmax"][:0], g["tmin"][:0])
+    assert got0["pkwater_equiv"].shape == (0, n)
+
+
+def test_ensemble_members_are_independent(drb):
+    """BASELINE.json configs[3] in small: a parameter ensemble laid out
+    member-major in one engine (perturbed soil / snow parameters per member);
+    every member must equal the same member run alone, bit for bit."""
+    p, f, start = drb
+    nm, nd = 3, 150
+    nhru = p["hru_area"].shape[0]
+    pe, fe = scenarios.tile(p, {k: v[:nd] for k, v in f.items()}, nm, temp_shift=False)
+    rng = np.random.default_rng(2026)
+    scale = {k: rng.uniform(0.8, 1.2, nm) for k in
+             ("soil_moist_max", "soil2gw_max", "ssr2gw_rate", "slowcoef_lin", "smidx_coef", "carea_max",
+              "gwflow_coef", "freeh2o_cap", "emis_noppt", "rad_trncf", "potet_sublim")}
+    for k, sc in scale.items():
+        v = np.array(pe[k], dtype=np.float64, copy=True)
+        for m in range(nm):
+            v[..., m * nhru:(m + 1) * nhru] *= sc[m]
+        if k in ("carea_max", "emis_noppt", "rad_trncf"):
+            v = np.minimum(v, 1.0)
+        pe[k] = v
+    e = _engine(pe, start)
+    allm, _ = e.run_host(fe["prcp"], fe["tmax"], fe["tmin"])
+    nseg = p["tosegment"].shape[0]
+    for m in range(nm):
+        pm = dict(p)
+        for k in scale:
+            pm[k] = pe[k][..., m * nhru:(m + 1) * nhru]
+        em = _engine(pm, start)
+        one, _ = em.run_host(f["prcp"][:nd], f["tmax"][:nd], f["tmin"][:nd])
+        for k in po.HRU_VARS:
+            np.testing.assert_array_equal(np.asarray(allm[k])[:, m * nhru:(m + 1) * nhru],
+                                          np.asarray(one[k]), err_msg=f"{k} member {m}")
+        for k in po.SEG_VARS:
+            np.testing.assert_array_equal(allm[k][:, m * nseg:(m + 1) * nseg], one[k], err_msg=k)
+
+
 def test_missing_parameter_and_bad_option_raise(drb):
     from pywatershed_b200 import Engine
 
