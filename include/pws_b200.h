@@ -105,6 +105,22 @@ int pws_run_host(pws_handle *h, int ndays, const int32_t *h_cal,
                  double *h_out_f64, int32_t *h_out_i32, double *h_seg_out,
                  int32_t *h_budget_viol);
 
+/* A SUBSET of the chain's processes, the others replaced by the caller's
+ * arrays: what the reference does when a process (or a partial chain) is
+ * driven from files, e.g. autotest/test_self_drive.py:83-115,
+ * autotest/test_prms_snow.py:96-132, the two-process example of
+ * base/model.py:121-163.  Input registry: index 0..2 = prcp, tmax, tmin, then
+ * the inter-process inputs of Process.get_inputs() (base/process.py:160-163).
+ * h_in[k] = [ndays][nhru] float64 (integer inputs as float64).  process_mask:
+ * bit 0 canopy, 1 snow, 2 runoff, 3 soilzone, 4 groundwater, 5 channel --
+ * budgets / errors / routing of the processes that are part of the model. */
+int pws_n_inputs(void);
+const char *pws_input_name(int idx);
+int pws_run_host_inputs(pws_handle *h, int ndays, const int32_t *h_cal, int n_in,
+                        const int32_t *in_idx, const double *const *h_in,
+                        uint32_t process_mask, double *h_out_f64, int32_t *h_out_i32,
+                        double *h_seg_out, int32_t *h_budget_viol);
+
 /* PRMSChannel alone (examples/05_parameter_ensemble.ipynb cell 20):
  * d_seg_lateral_inflow [ndays][nsegment] */
 int pws_run_channel_device(pws_handle *h, int ndays, const double *d_seg_lateral_inflow,

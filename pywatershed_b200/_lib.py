@@ -56,6 +56,9 @@ def lib():
         "pws_run_device": (i32, [vp, i32] + [vp] * 8),
         "pws_run_host": (i32, [vp, i32] + [vp] * 8),
         "pws_run_channel_device": (i32, [vp, i32, vp, vp]),
+        "pws_n_inputs": (i32, []),
+        "pws_input_name": (cp, [i32]),
+        "pws_run_host_inputs": (i32, [vp, i32, vp, i32, vp, vp, C.c_uint32, vp, vp, vp, vp]),
         "pws_sync": (i32, [vp]),
         "pws_get_state": (i32, [vp, cp, vp]),
         "pws_set_state": (i32, [vp, cp, vp]),
@@ -81,7 +84,7 @@ EXPORTED_SYMBOLS = (
     "pws_create", "pws_destroy", "pws_last_error", "pws_set_param_f64",
     "pws_set_param_i32", "pws_set_option", "pws_init", "pws_get_soltab",
     "pws_select_outputs", "pws_n_selected", "pws_run_device", "pws_run_host",
-    "pws_run_channel_device", "pws_sync", "pws_get_state", "pws_set_state",
+    "pws_run_channel_device", "pws_n_inputs", "pws_input_name", "pws_run_host_inputs", "pws_sync", "pws_get_state", "pws_set_state",
     "pws_launch_count", "pws_last_timing", "pws_column_kernel_info",
     "pws_timer_mark", "pws_timer_elapsed_ms", "pws_last_launches", "pws_reset_state",
 )

@@ -619,6 +619,13 @@ PWS_DEV int hru_init_one(const HruParams& P, const HruDerivedMut& D, double* sta
 // ------------------------------------------------------------------------
 #define PWS_F(var, val) out.template f<V_##var>(val)
 #define PWS_I(var, val) out.template i<V_##var>(val)
+// Input override points: when a process of the chain is NOT part of the model
+// (a sub-chain, or a single process driven from files as the reference's own
+// tests do, autotest/test_self_drive.py), the variables it would have produced
+// are taken from the caller's input arrays instead.  For the fused full-chain
+// kernels out.ov<>() is the identity and compiles to nothing.
+#define PWS_OV(name, var) var = out.template ov<OV_##name>(var)
+#define PWS_OVI(name, var) var = out.template ovi<OV_##name>(var)
 // What the upper half of the column (atmosphere, canopy, snow) hands to the
 // lower half (runoff, soilzone, groundwater) for one HRU-day.
 struct ColumnMid {
@@ -639,9 +646,9 @@ PWS_DEV void column_upper(const HruParams& P, const int64_t i, HruState& s,
   // adjust_temperature prms_atmosphere.py:287-317
   const double tmaxf = in.tmax + PWS_LD(P.tmax_cbh_adj + mi);
   const double tminf = in.tmin + PWS_LD(P.tmin_cbh_adj + mi);
-  const double tminc = (tminf - 32.0) * (5.0 / 9.0);
-  const double tmaxc = (tmaxf - 32.0) * (5.0 / 9.0);
-  const double tavgc = (tmaxc + tminc) / 2.0;
+  double tminc = (tminf - 32.0) * (5.0 / 9.0);
+  double tmaxc = (tmaxf - 32.0) * (5.0 / 9.0);
+  double tavgc = (tmaxc + tminc) / 2.0;
   // adjust_precip :319-430 (mixed everywhere, then all-rain, then all-snow)
   const double allsnow = PWS_LD(P.tmax_allsnow + mi);
   const double allrain_off = PWS_LD(P.tmax_allrain_offset + mi);
@@ -693,8 +700,8 @@ PWS_DEV void column_upper(const HruParams& P, const int64_t i, HruState& s,
   }
   radadj = radadj * pptadj;
   if (radadj < 0.2) radadj = 0.2;
-  const double swrad = in.potsw * radadj / PWS_LD(P.hru_cossl + i);
-  const double orad_hru = radadj * in.horad;
+  double swrad = in.potsw * radadj / PWS_LD(P.hru_cossl + i);
+  double orad_hru = radadj * in.horad;
   // _potet_jh_run :643-668
   const double tavgf = (tavgc * 9 / 5) + 32;
   const double elh = (597.3 - (0.5653 * tavgc)) * PWS_INCH2CM;
@@ -724,21 +731,26 @@ PWS_DEV void column_upper(const HruParams& P, const int64_t i, HruState& s,
       }
     }
   }
-  const int transp_on = s.transp_on;
+  int transp_on = s.transp_on;
   PWS_F(tmaxf, tmaxf); PWS_F(tminf, tminf); PWS_F(prmx, prmx);
   PWS_F(hru_ppt, hru_ppt); PWS_F(hru_rain, hru_rain); PWS_F(hru_snow, hru_snow);
   PWS_F(swrad, swrad); PWS_F(potet, potet); PWS_I(transp_on, transp_on);
   PWS_F(tmaxc, tmaxc); PWS_F(tavgc, tavgc); PWS_F(tminc, tminc);
   PWS_I(pptmix, pptmix);  // the all-time value Atmosphere writes to file
   PWS_F(orad_hru, orad_hru);
+  PWS_OV(tmaxc, tmaxc); PWS_OV(tminc, tminc); PWS_OV(tavgc, tavgc); PWS_OV(prmx, prmx);
+  PWS_OV(hru_ppt, hru_ppt); PWS_OV(hru_rain, hru_rain); PWS_OV(hru_snow, hru_snow);
+  PWS_OV(swrad, swrad); PWS_OV(orad_hru, orad_hru); PWS_OV(potet, potet);
+  PWS_OVI(transp_on, transp_on); PWS_OVI(pptmix, pptmix);
 
   out.sync();
   // ===================== PRMSCanopy ======================================
   const double covden_sum = PWS_LD(P.covden_sum + i);
   const double covden_win = PWS_LD(P.covden_win + i);
   const double hru_intcpstor_old = s.hru_intcpstor;  // _advance_variables :277
-  const double pk_ice_prev = s.pk_ice;               // prms_snow.py:483-486
-  const double freeh2o_prev = s.freeh2o;
+  double pk_ice_prev = s.pk_ice;               // prms_snow.py:483-486
+  double freeh2o_prev = s.freeh2o;
+  PWS_OV(pk_ice_prev, pk_ice_prev); PWS_OV(freeh2o_prev, freeh2o_prev);
   double net_rain = hru_rain, net_snow = hru_snow;
   double hru_intcpevap, intcp_changeover;
   {
@@ -829,7 +841,7 @@ PWS_DEV void column_upper(const HruParams& P, const int64_t i, HruState& s,
     PWS_F(intcp_evap, intcpevap);
     PWS_I(intcp_form, intcp_form);
   }
-  const double net_ppt = net_rain + net_snow;
+  double net_ppt = net_rain + net_snow;
   const double hru_intcpstor_change = s.hru_intcpstor - hru_intcpstor_old;
   PWS_F(net_ppt, net_ppt); PWS_F(net_rain, net_rain); PWS_F(net_snow, net_snow);
   PWS_F(intcp_changeover, intcp_changeover); PWS_F(intcp_stor, s.intcp_stor);
@@ -841,6 +853,8 @@ PWS_DEV void column_upper(const HruParams& P, const int64_t i, HruState& s,
            budget_open(0 + hru_rain + hru_snow,
                        (0 + net_rain + net_snow + hru_intcpevap + intcp_changeover) +
                            (0 + hru_intcpstor_change)));
+  PWS_OV(net_ppt, net_ppt); PWS_OV(net_rain, net_rain); PWS_OV(net_snow, net_snow);
+  PWS_OV(hru_intcpevap, hru_intcpevap); PWS_OV(intcp_changeover, intcp_changeover);
 
   out.sync();
   // ===================== PRMSSnow ========================================
@@ -1226,6 +1240,9 @@ PWS_DEV void column_upper(const HruParams& P, const int64_t i, HruState& s,
   mid.through_rain = through_rain;
   mid.transp_on = transp_on;
   mid.pptmix_nopack = pptmix_nopack;
+  PWS_OV(snowmelt, mid.snowmelt); PWS_OV(snow_evap, mid.snow_evap);
+  PWS_OV(pkwater_equiv, mid.pkwater_equiv); PWS_OV(snowcov_area, mid.snowcov_area);
+  PWS_OV(through_rain, mid.through_rain); PWS_OVI(pptmix_nopack, mid.pptmix_nopack);
 }
 
 // ---- lower half: PRMSRunoff, PRMSSoilzone, PRMSGroundwater, lateral inflow
@@ -1241,15 +1258,17 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, HruState& s,
   const double r_hru_area = 1.0 / hru_area;
 #define PER_AREA(x) div_r((x), hru_area, r_hru_area)
   const double potet = mid.potet, net_rain = mid.net_rain, net_snow = mid.net_snow;
-  const double net_ppt = net_rain + net_snow;
+  double net_ppt = net_rain + net_snow;
+  PWS_OV(net_ppt, net_ppt);
   const double hru_intcpevap = mid.hru_intcpevap, intcp_changeover = mid.intcp_changeover;
   const double snowmelt = mid.snowmelt, snow_evap = mid.snow_evap;
   const double pkwater_equiv = mid.pkwater_equiv, snowcov_area = mid.snowcov_area;
   const double through_rain = mid.through_rain;
   const int transp_on = mid.transp_on, pptmix_nopack = mid.pptmix_nopack;
   // ===================== PRMSRunoff ======================================
-  const double soil_rechr_prev = s.soil_rechr;
-  const double soil_lower_prev = s.soil_moist - s.soil_rechr;  // = yesterday's soil_lower
+  double soil_rechr_prev = s.soil_rechr;
+  double soil_lower_prev = s.soil_moist - s.soil_rechr;  // = yesterday's soil_lower
+  PWS_OV(soil_rechr_prev, soil_rechr_prev); PWS_OV(soil_lower_prev, soil_lower_prev);
   const double perv_frac = PWS_LD(P.ro_hru_frac_perv + i);
   const double hruarea_imperv = PWS_LD(P.ro_hru_imperv + i);
   const double hru_impervstor_old = s.hru_impervstor;
@@ -1479,7 +1498,7 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, HruState& s,
     }
     sroff = srunoff;
   }
-  const double infil_hru = infil * perv_frac;
+  double infil_hru = infil * perv_frac;
   const double hru_impervstor_change = s.hru_impervstor - hru_impervstor_old;
   const double dprst_stor_hru_change = dprst_stor_hru - dprst_stor_hru_old;
   PWS_F(contrib_fraction, contrib_fraction); PWS_F(infil, infil);
@@ -1505,6 +1524,8 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, HruState& s,
                        (0 + hru_sroffi + hru_sroffp + dprst_sroff_hru + infil_hru +
                         hru_impervevap + dprst_seep_hru + dprst_evap_hru) +
                            (0 + hru_impervstor_change + dprst_stor_hru_change)));
+  PWS_OV(infil_hru, infil_hru); PWS_OV(sroff, sroff); PWS_OV(dprst_evap_hru, dprst_evap_hru);
+  PWS_OV(dprst_seep_hru, dprst_seep_hru); PWS_OV(hru_impervevap, hru_impervevap);
 
   out.sync();
   // ===================== PRMSSoilzone ====================================
@@ -1692,8 +1713,8 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, HruState& s,
   const double soil_lower_change_hru = soil_lower_change * hru_frac_perv;
   const double soil_rechr_change_hru = soil_rechr_change * hru_frac_perv;
   const double perv_actet_hru = perv_actet * hru_frac_perv;
-  const double ssres_flow_vol = ssres_flow * hru_in_to_cf;
-  const double sroff_vol = sroff * hru_in_to_cf;  // prms_soilzone.py:707
+  double ssres_flow_vol = ssres_flow * hru_in_to_cf;
+  double sroff_vol = sroff * hru_in_to_cf;  // prms_soilzone.py:707
   double recharge = soil_to_gw + ssr_to_gw;
   if (P.dprst_flag) recharge = recharge + dprst_seep_hru;
   PWS_F(sroff, sroff); PWS_F(sroff_vol, sroff_vol);
@@ -1731,6 +1752,7 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, HruState& s,
                         dunnian_flow + pref_flow) +
                            (0 + soil_rechr_change_hru + soil_lower_change_hru +
                             slow_stor_change + pref_flow_stor_change)));
+  PWS_OV(soil_to_gw, soil_to_gw); PWS_OV(ssr_to_gw, ssr_to_gw);
 
   out.sync();
   // ===================== PRMSGroundwater =================================
@@ -1761,6 +1783,8 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, HruState& s,
 
   // ===================== PRMSChannel, HRU side ===========================
   // prms_channel.py:396-421: HRUs without a segment contribute nothing
+  PWS_OV(sroff_vol, sroff_vol); PWS_OV(ssres_flow_vol, ssres_flow_vol);
+  PWS_OV(gwres_flow_vol, gwres_flow_vol);
   const bool has_seg = PWS_LD(P.hru_segment + i) > 0;
   const double ch_sroff = has_seg ? sroff_vol : 0.0;
   const double ch_ssres = has_seg ? ssres_flow_vol : 0.0;

@@ -913,16 +913,9 @@ static int enqueue_channel(pws_handle* h, int ndays, const double* d_hru_lat,
   return 0;
 }
 
-// enqueue one block of days on s_compute (forcings/outputs are device pointers)
-static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const double* d_prcp,
-                         const double* d_tmax, const double* d_tmin, int64_t fstride,
-                         double* d_out_f64, int32_t* d_out_i32, double* d_seg_out, bool want_viol) {
-  if (ensure_scratch(h, ndays)) return 1;
-  PWS_CUDA(h, cudaMemcpyAsync(h->d_cal, h_cal, (size_t)ndays * sizeof(int4),
-                              cudaMemcpyHostToDevice, h->s_compute));
-  if (want_viol)
-    PWS_CUDA(h, cudaMemsetAsync(h->d_viol, 0, (size_t)ndays * BUD_N * sizeof(int), h->s_compute));
-  ColumnArgs a{};
+static void fill_column_args(pws_handle* h, ColumnArgs& a, int ndays, const double* d_prcp,
+                             const double* d_tmax, const double* d_tmin, int64_t fstride,
+                             double* d_out_f64, int32_t* d_out_i32, bool want_viol) {
   a.P = h->P;
   a.state = h->d_state;
   a.prcp = d_prcp; a.tmax = d_tmax; a.tmin = d_tmin;
@@ -940,6 +933,19 @@ static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const d
     const int64_t esz = names().hru_var_kind[v] == 0 ? 8 : 4;
     a.off[v] = sl < 0 ? -1 : (int64_t)sl * a.ostride * esz;
   }
+}
+
+// enqueue one block of days on s_compute (forcings/outputs are device pointers)
+static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const double* d_prcp,
+                         const double* d_tmax, const double* d_tmin, int64_t fstride,
+                         double* d_out_f64, int32_t* d_out_i32, double* d_seg_out, bool want_viol) {
+  if (ensure_scratch(h, ndays)) return 1;
+  PWS_CUDA(h, cudaMemcpyAsync(h->d_cal, h_cal, (size_t)ndays * sizeof(int4),
+                              cudaMemcpyHostToDevice, h->s_compute));
+  if (want_viol)
+    PWS_CUDA(h, cudaMemsetAsync(h->d_viol, 0, (size_t)ndays * BUD_N * sizeof(int), h->s_compute));
+  ColumnArgs a{};
+  fill_column_args(h, a, ndays, d_prcp, d_tmax, d_tmin, fstride, d_out_f64, d_out_i32, want_viol);
   if (kColumnSmemBytes > 48 * 1024 && !h->smem_attr_set) {
     for (auto fn : {k_hru_column<SINK_SELECT>, k_hru_column<SINK_FULL>, k_hru_column<SINK_NONE>})
       PWS_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1133,6 +1139,105 @@ extern "C" int pws_run_host(pws_handle* h, int ndays, const int32_t* h_cal, cons
     // the caller's full-run array).
   }
   return pws_sync(h);
+}
+
+// --------------------------------------------------------------- sub-chains
+static const char* const kInputNames[] = {"prcp", "tmax", "tmin",
+#define X(n) #n,
+                                          PWS_OV_INPUTS(X)
+#undef X
+};
+extern "C" int pws_n_inputs(void) { return 3 + PWS_N_OV; }
+extern "C" const char* pws_input_name(int i) {
+  return (i >= 0 && i < 3 + PWS_N_OV) ? kInputNames[i] : nullptr;
+}
+
+// A subset of the chain's processes (process_mask, bits = BUD_* numbering; the
+// atmosphere is implied by supplying prcp/tmax/tmin), everything else fed from
+// the caller's arrays.  Compatibility path: synchronous per block of days.
+extern "C" int pws_run_host_inputs(pws_handle* h, int ndays, const int32_t* h_cal, int n_in,
+                                   const int32_t* in_idx, const double* const* h_in,
+                                   uint32_t process_mask, double* h_out_f64, int32_t* h_out_i32,
+                                   double* h_seg_out, int32_t* h_budget_viol) {
+  if (!h->inited) PWS_FAIL(h, "pws_run_host_inputs before pws_init");
+  if (ndays <= 0) return 0;
+  PWS_CUDA(h, cudaSetDevice(h->device));
+  for (int k = 0; k < n_in; ++k)
+    if (in_idx[k] < 0 || in_idx[k] >= 3 + PWS_N_OV || h_in[k] == nullptr)
+      PWS_FAIL(h, "pws_run_host_inputs: bad input index %d", in_idx[k]);
+  clear_timing(h);
+  const int64_t n = h->nhru;
+  int T = h->block_days > 0 ? h->block_days : 64;
+  T = std::min(T, ndays);
+  if (ensure_scratch(h, T)) return 1;
+  const bool channel = h->nseg > 0 && ((process_mask >> BUD_CHANNEL) & 1u);
+  double *d_in = nullptr, *d_zero = nullptr, *d_of = nullptr, *d_os = nullptr;
+  int32_t* d_oi = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_in); cudaFree(d_zero); cudaFree(d_of); cudaFree(d_oi); cudaFree(d_os);
+  };
+  const size_t blk = (size_t)T * n;
+  cudaError_t e = cudaMalloc(&d_in, std::max<size_t>(n_in, 1) * blk * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&d_zero, blk * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemset(d_zero, 0, blk * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&d_of, std::max<size_t>(h->n_f64, 1) * blk * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&d_oi, std::max<size_t>(h->n_i32, 1) * blk * sizeof(int32_t));
+  if (e == cudaSuccess)
+    e = cudaMalloc(&d_os, (size_t)T * std::max(h->n_seg_sel, 1) * std::max<int64_t>(h->nseg, 1) *
+                              sizeof(double));
+  if (e != cudaSuccess) {
+    cleanup();
+    PWS_FAIL(h, "pws_run_host_inputs: %s", cudaGetErrorString(e));
+  }
+  int rc = 0;
+  for (int d0 = 0; d0 < ndays && rc == 0; d0 += T) {
+    const int nd = std::min(T, ndays - d0);
+    OvArgs a{};
+    const double* forc[3] = {d_zero, d_zero, d_zero};
+    for (int k = 0; k < n_in; ++k) {
+      double* dst = d_in + (size_t)k * blk;
+      cudaMemcpyAsync(dst, h_in[k] + (size_t)d0 * n, (size_t)nd * n * sizeof(double),
+                      cudaMemcpyHostToDevice, h->s_compute);
+      if (in_idx[k] < 3) forc[in_idx[k]] = dst;
+      else a.ov[in_idx[k] - 3] = dst;
+    }
+    cudaMemcpyAsync(h->d_cal, h_cal + (size_t)d0 * 4, (size_t)nd * sizeof(int4),
+                    cudaMemcpyHostToDevice, h->s_compute);
+    if (h_budget_viol)
+      cudaMemsetAsync(h->d_viol, 0, (size_t)nd * BUD_N * sizeof(int), h->s_compute);
+    fill_column_args(h, a.c, nd, forc[0], forc[1], forc[2], n, d_of, d_oi, h_budget_viol != nullptr);
+    a.ovstride = n;
+    a.proc_mask = process_mask;
+    k_hru_column_ov<<<(unsigned)((n + 127) / 128), 128, 0, h->s_compute>>>(a);
+    h->launches++;
+    if (channel && rc == 0)
+      rc = enqueue_channel(h, nd, h->d_hru_lat, nullptr, d_os, h_budget_viol != nullptr);
+    if (h_budget_viol)
+      cudaMemcpyAsync(h_budget_viol + (size_t)d0 * BUD_N, h->d_viol, (size_t)nd * BUD_N * sizeof(int),
+                      cudaMemcpyDeviceToHost, h->s_compute);
+    if (h->n_f64 > 0 && h_out_f64)
+      cudaMemcpyAsync(h_out_f64 + (size_t)d0 * h->n_f64 * n, d_of,
+                      (size_t)nd * h->n_f64 * n * sizeof(double), cudaMemcpyDeviceToHost, h->s_compute);
+    if (h->n_i32 > 0 && h_out_i32)
+      cudaMemcpyAsync(h_out_i32 + (size_t)d0 * h->n_i32 * n, d_oi,
+                      (size_t)nd * h->n_i32 * n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->s_compute);
+    if (channel && h->n_seg_sel > 0 && h_seg_out)
+      cudaMemcpyAsync(h_seg_out + (size_t)d0 * h->n_seg_sel * h->nseg, d_os,
+                      (size_t)nd * h->n_seg_sel * h->nseg * sizeof(double), cudaMemcpyDeviceToHost,
+                      h->s_compute);
+    if (cudaStreamSynchronize(h->s_compute) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+      h->err = "pws_run_host_inputs: CUDA error in the block loop";
+      rc = 1;
+    }
+  }
+  cleanup();
+  if (rc) return rc;
+  // budget verdicts of processes that are not part of the model are not reported
+  if (h_budget_viol)
+    for (int d = 0; d < ndays; ++d)
+      for (int p = 0; p < BUD_N; ++p)
+        if (!((process_mask >> p) & 1u)) h_budget_viol[(size_t)d * BUD_N + p] = 0;
+  return check_device_errors(h);
 }
 
 // --------------------------------------------------------------- state

@@ -184,6 +184,10 @@ struct GpuSink {
   __device__ __forceinline__ void error(int code) {
     if (live) errmask |= code;
   }
+  template <int id>
+  __device__ __forceinline__ double ov(double v) const { return v; }
+  template <int id>
+  __device__ __forceinline__ int ovi(int v) const { return v; }
   __device__ __forceinline__ void sync() {
 #if PWS_COLUMN_SYNC >= 1
     asm volatile("bar.sync %0, %1;" ::"r"(group_barrier), "n"(PWS_COLUMN_HRUS) : "memory");
@@ -204,12 +208,17 @@ constexpr int kLowerF64 = 0 PWS_LOWER_F64(PWS_COUNT);
 constexpr int kLowerI32 = 0 PWS_LOWER_I32(PWS_COUNT);
 #undef PWS_COUNT
 constexpr int kMidF64 = 10, kMidI32 = 2;  // ColumnMid
-constexpr int kColF64 = kUpperF64 + kUpperMonF64 + kLowerF64 + kMidF64;
-constexpr int kColI32 = kUpperI32 + kLowerI32 + kMidI32;
+#ifndef PWS_COLUMN_MID_SLOTS
+#define PWS_COLUMN_MID_SLOTS 1  // days the upper half may run ahead of the lower half (2: no gain)
+#endif
+constexpr int kMidSlots = PWS_COLUMN_MID_SLOTS;
+constexpr int kColF64 = kUpperF64 + kUpperMonF64 + kLowerF64 + kMidSlots * kMidF64;
+constexpr int kColI32 = kUpperI32 + kLowerI32 + kMidSlots * kMidI32;
 constexpr size_t kColumnSmemBytes = (size_t)PWS_COLUMN_HRUS * (kColF64 * 8 + kColI32 * 4);
 
 // named barriers of k_hru_column (0 is __syncthreads)
-enum { BAR_MID_FULL = 1, BAR_MID_EMPTY = 2, BAR_UPPER = 3, BAR_LOWER = 4 };
+enum { BAR_UPPER = 1, BAR_LOWER = 2, BAR_MID_FULL = 3, BAR_MID_EMPTY = 3 + PWS_COLUMN_MID_SLOTS };
+static_assert(3 + 2 * PWS_COLUMN_MID_SLOTS <= 16, "named barriers");
 
 __device__ __forceinline__ void bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -247,7 +256,7 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
   double* const spU = reinterpret_cast<double*>(smem_raw);           // upper f64 (+ monthly)
   double* const spL = spU + (size_t)(kUpperF64 + kUpperMonF64) * H;  // lower f64
   double* const spM = spL + (size_t)kLowerF64 * H;                   // ColumnMid f64
-  int32_t* const siU = reinterpret_cast<int32_t*>(spM + (size_t)kMidF64 * H);
+  int32_t* const siU = reinterpret_cast<int32_t*>(spM + (size_t)kMidSlots * kMidF64 * H);
   int32_t* const siL = siU + (size_t)kUpperI32 * H;
   int32_t* const siM = siL + (size_t)kLowerI32 * H;
 
@@ -339,22 +348,25 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
       out.violmask = 0u;
       ColumnMid mid;
       column_upper(Q, (int64_t)r, s, in, out, mid);
-      // hand the day over to the lower half of this HRU
-      if (d > 0) bar_sync(BAR_MID_EMPTY, 2 * H);  // the lower group has read day d - 1
-      spM[0 * H + r] = mid.potet;
-      spM[1 * H + r] = mid.net_rain;
-      spM[2 * H + r] = mid.net_snow;
-      spM[3 * H + r] = mid.hru_intcpevap;
-      spM[4 * H + r] = mid.intcp_changeover;
-      spM[5 * H + r] = mid.snowmelt;
-      spM[6 * H + r] = mid.snow_evap;
-      spM[7 * H + r] = mid.pkwater_equiv;
-      spM[8 * H + r] = mid.snowcov_area;
-      spM[9 * H + r] = mid.through_rain;
-      siM[0 * H + r] = mid.transp_on;
-      siM[1 * H + r] = mid.pptmix_nopack;
+      // hand the day over to the lower half of this HRU (slot d mod kMidSlots)
+      const int slot = d % kMidSlots;
+      double* const mf = spM + (size_t)slot * kMidF64 * H + r;
+      int32_t* const mi32 = siM + (size_t)slot * kMidI32 * H + r;
+      if (d >= kMidSlots) bar_sync(BAR_MID_EMPTY + slot, 2 * H);  // day d - kMidSlots has been read
+      mf[0 * H] = mid.potet;
+      mf[1 * H] = mid.net_rain;
+      mf[2 * H] = mid.net_snow;
+      mf[3 * H] = mid.hru_intcpevap;
+      mf[4 * H] = mid.intcp_changeover;
+      mf[5 * H] = mid.snowmelt;
+      mf[6 * H] = mid.snow_evap;
+      mf[7 * H] = mid.pkwater_equiv;
+      mf[8 * H] = mid.snowcov_area;
+      mf[9 * H] = mid.through_rain;
+      mi32[0 * H] = mid.transp_on;
+      mi32[1 * H] = mid.pptmix_nopack;
       __threadfence_block();
-      bar_arrive(BAR_MID_FULL, 2 * H);
+      bar_arrive(BAR_MID_FULL + slot, 2 * H);
       out.pf += day_f64;
       out.pi += day_i32;
       reduce_violations(d);
@@ -386,20 +398,23 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
     }
     for (int d = 0; d < a.ndays; ++d) {
       ColumnMid mid;
-      bar_sync(BAR_MID_FULL, 2 * H);  // the upper group has written day d
-      mid.potet = spM[0 * H + r];
-      mid.net_rain = spM[1 * H + r];
-      mid.net_snow = spM[2 * H + r];
-      mid.hru_intcpevap = spM[3 * H + r];
-      mid.intcp_changeover = spM[4 * H + r];
-      mid.snowmelt = spM[5 * H + r];
-      mid.snow_evap = spM[6 * H + r];
-      mid.pkwater_equiv = spM[7 * H + r];
-      mid.snowcov_area = spM[8 * H + r];
-      mid.through_rain = spM[9 * H + r];
-      mid.transp_on = siM[0 * H + r];
-      mid.pptmix_nopack = siM[1 * H + r];
-      if (d + 1 < a.ndays) bar_arrive(BAR_MID_EMPTY, 2 * H);
+      const int slot = d % kMidSlots;
+      const double* const mf = spM + (size_t)slot * kMidF64 * H + r;
+      const int32_t* const mi32 = siM + (size_t)slot * kMidI32 * H + r;
+      bar_sync(BAR_MID_FULL + slot, 2 * H);  // the upper group has written day d
+      mid.potet = mf[0 * H];
+      mid.net_rain = mf[1 * H];
+      mid.net_snow = mf[2 * H];
+      mid.hru_intcpevap = mf[3 * H];
+      mid.intcp_changeover = mf[4 * H];
+      mid.snowmelt = mf[5 * H];
+      mid.snow_evap = mf[6 * H];
+      mid.pkwater_equiv = mf[7 * H];
+      mid.snowcov_area = mf[8 * H];
+      mid.through_rain = mf[9 * H];
+      mid.transp_on = mi32[0 * H];
+      mid.pptmix_nopack = mi32[1 * H];
+      if (d + kMidSlots < a.ndays) bar_arrive(BAR_MID_EMPTY + slot, 2 * H);
       out.violmask = 0u;
       out.plat = a.hru_lat ? a.hru_lat + (int64_t)d * S + ii : nullptr;
       column_lower(Q, (int64_t)r, s, mid, out);
@@ -414,6 +429,108 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
     }
   }
   if (live && out.errmask) atomicOr(a.err, out.errmask);
+}
+
+// ---------------------------------------------------------------- sub-chains
+// Any subset of the column's processes, the others replaced by caller-supplied
+// inputs (PWS_OV in hru_column.cuh): one thread per HRU runs both halves of
+// the column in sequence with an overriding sink.  This is the compatibility
+// path for single processes and partial chains (the reference's
+// autotest/test_self_drive.py pattern); the full chain runs k_hru_column.
+struct OvArgs {
+  ColumnArgs c;
+  const double* ov[PWS_N_OV];  // [ndays][ovstride] per overridden input, else null
+  int64_t ovstride;
+  unsigned proc_mask;          // bit BUD_*: the process is part of the model
+};
+
+struct OvSink {
+  const OvArgs& a;
+  char* pf;
+  char* pi;
+  double* plat;
+  int64_t idx;  // day * ovstride + hru
+  unsigned violmask;
+  int errmask;
+  bool live;
+  template <int var>
+  __device__ __forceinline__ void f(double v) {
+    const int64_t o = a.c.off[var];
+    if (o >= 0 && live) __stcs(reinterpret_cast<double*>(pf + o), v);
+  }
+  template <int var>
+  __device__ __forceinline__ void i(int v) {
+    const int64_t o = a.c.off[var];
+    if (o >= 0 && live) __stcs(reinterpret_cast<int*>(pi + o), v);
+  }
+  __device__ __forceinline__ void viol(int proc, bool open) {
+    if (open && live && ((a.proc_mask >> proc) & 1u)) violmask |= 1u << proc;
+  }
+  __device__ __forceinline__ void lateral(double v) {
+    if (plat && live) *plat = v;
+  }
+  __device__ __forceinline__ void error(int code) {
+    if (live && ((a.proc_mask >> BUD_SOILZONE) & 1u)) errmask |= code;
+  }
+  template <int id>
+  __device__ __forceinline__ double ov(double v) const {
+    const double* p = a.ov[id];
+    return p != nullptr ? __ldg(p + idx) : v;
+  }
+  template <int id>
+  __device__ __forceinline__ int ovi(int v) const {
+    const double* p = a.ov[id];
+    return p != nullptr ? (int)__ldg(p + idx) : v;
+  }
+  __device__ __forceinline__ void sync() {}
+  __device__ __forceinline__ void sync2() {}
+};
+
+__global__ void __launch_bounds__(128)
+k_hru_column_ov(const __grid_constant__ OvArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < a.c.P.nhru;
+  const int64_t ii = live ? i : a.c.P.nhru - 1;
+  const int64_t S = a.c.P.stride;
+  HruState s;
+#define X(name, kind) s.name = (decltype(s.name))a.c.state[(int64_t)ST_##name * S + ii];
+  PWS_HRU_STATE(X)
+#undef X
+  OvSink out{a, reinterpret_cast<char*>(a.c.out_f64 + ii), reinterpret_cast<char*>(a.c.out_i32 + ii),
+             nullptr, 0, 0u, 0, live};
+  const int64_t day_f64 = (int64_t)a.c.n_f64 * a.c.ostride * 8;
+  const int64_t day_i32 = (int64_t)a.c.n_i32 * a.c.ostride * 4;
+  for (int d = 0; d < a.c.ndays; ++d) {
+    const int4 c = a.c.cal[d];
+    DayIn in;
+    in.doy = c.x; in.dowy = c.y; in.month = c.z; in.dom = c.w;
+    const int64_t fo = (int64_t)d * a.c.fstride + ii;
+    in.prcp = a.c.prcp[fo];
+    in.tmax = a.c.tmax[fo];
+    in.tmin = a.c.tmin[fo];
+    in.potsw = a.c.P.soltab_potsw[(int64_t)(c.x - 1) * S + ii];
+    in.horad = a.c.P.soltab_horad_potsw[(int64_t)(c.x - 1) * S + ii];
+    out.idx = (int64_t)d * a.ovstride + ii;
+    out.violmask = 0u;
+    out.plat = a.c.hru_lat ? a.c.hru_lat + (int64_t)d * S + ii : nullptr;
+    ColumnMid mid;
+    column_upper(a.c.P, ii, s, in, out, mid);
+    column_lower(a.c.P, ii, s, mid, out);
+    out.pf += day_f64;
+    out.pi += day_i32;
+    if (a.c.viol != nullptr && __any_sync(0xffffffffu, out.violmask != 0u)) {
+      for (int p = 0; p < BUD_CHANNEL; ++p) {
+        const unsigned m = __ballot_sync(0xffffffffu, (out.violmask >> p) & 1u);
+        if (m != 0u && (threadIdx.x & 31) == 0) atomicAdd(a.c.viol + d * BUD_N + p, __popc(m));
+      }
+    }
+  }
+  if (live) {
+#define X(name, kind) a.c.state[(int64_t)ST_##name * S + i] = (double)s.name;
+    PWS_HRU_STATE(X)
+#undef X
+    if (out.errmask) atomicOr(a.c.err, out.errmask);
+  }
 }
 
 // ---------------------------------------------------------------- channel
@@ -555,8 +672,15 @@ k_route_chunks(const __grid_constant__ ChannelArgs a) {
     if (nh > 1) h1 = a.hru_idx[hb + 1];
     if (nh > 2) h2 = a.hru_idx[hb + 2];
   }
-  const bool divide = ts != 1.0;  // x / 1.0 == x exactly
-  const bool muskingum = tsi > 0;
+  // No special cases in the hour step: with ts == 1 the reciprocal quotient
+  // returns x exactly (q = x, remainder 0), and a pass-through segment
+  // (tsi < 0, K < 1 h: outflow = inflow, prms_channel.py:529-547) is the
+  // recurrence with c0 = 1, c1 = c2 = 0, exact for finite flows.
+  if (tsi < 0) {
+    c0 = 1.0;
+    c1 = 0.0;
+    c2 = 0.0;
+  }
   const bool down = (flags & SEG_HAS_DOWN) != 0;
 
   // Lateral inflow of day k as up to three raw addends (summed a window later,
@@ -675,8 +799,8 @@ k_route_chunks(const __grid_constant__ ChannelArgs a) {
         const double acc = inflow_ts + cur;
         // routing update (branch-free; most segments update every hour)
         const bool upd = (fire >> (h + g)) & 1u;
-        const double xq = divide ? div_by_ts(acc, ts, rts) : acc;
-        const double routed = muskingum ? (xq * c0 + seg_inflow0 * c1) + outflow_ts * c2 : xq;
+        const double xq = div_by_ts(acc, ts, rts);
+        const double routed = (xq * c0 + seg_inflow0 * c1) + outflow_ts * c2;
         outflow_ts = upd ? routed : outflow_ts;
         seg_inflow0 = upd ? xq : seg_inflow0;
         inflow_ts = upd ? 0.0 : acc;

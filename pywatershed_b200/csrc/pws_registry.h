@@ -191,6 +191,25 @@
 #define PWS_UPPER_MON_I32(X) \
   X(tstorm_mo)
 
+// ---- inputs a process can take from the caller instead of from the process
+// upstream of it (names = the reference's get_inputs(); see PWS_OV in
+// hru_column.cuh).  transp_on, pptmix, pptmix_nopack are integer-valued.
+#define PWS_OV_INPUTS(X) \
+  X(tmaxc) X(tminc) X(tavgc) X(prmx) X(hru_ppt) X(hru_rain) X(hru_snow) \
+  X(swrad) X(orad_hru) X(potet) X(transp_on) X(pptmix) X(pk_ice_prev) \
+  X(freeh2o_prev) X(net_ppt) X(net_rain) X(net_snow) X(hru_intcpevap) \
+  X(intcp_changeover) X(snowmelt) X(snow_evap) X(pkwater_equiv) \
+  X(pptmix_nopack) X(snowcov_area) X(through_rain) X(soil_lower_prev) \
+  X(soil_rechr_prev) X(dprst_evap_hru) X(dprst_seep_hru) X(hru_impervevap) \
+  X(infil_hru) X(sroff) X(soil_to_gw) X(ssr_to_gw) X(sroff_vol) \
+  X(ssres_flow_vol) X(gwres_flow_vol)
+enum PwsOvInput {
+#define X(name) OV_##name,
+  PWS_OV_INPUTS(X)
+#undef X
+  PWS_N_OV
+};
+
 enum PwsHruVar {
 #define X(name, kind, init) V_##name,
   PWS_HRU_VARS(X)

@@ -39,6 +39,8 @@ class Registry:
         self.hru_kind = [L.pws_hru_var_kind(i) for i in range(L.pws_n_hru_vars())]
         self.seg_vars = [L.pws_seg_var_name(i).decode() for i in range(L.pws_n_seg_vars())]
         self.states = [L.pws_hru_state_name(i).decode() for i in range(L.pws_n_hru_state())]
+        self.inputs = [L.pws_input_name(i).decode() for i in range(L.pws_n_inputs())]
+        self.input_index = {n: i for i, n in enumerate(self.inputs)}
         self.hru_index = {n: i for i, n in enumerate(self.hru_vars)}
         self.seg_index = {n: i for i, n in enumerate(self.seg_vars)}
 
@@ -81,6 +83,31 @@ MON_PARAMS_F64 = (
     "tmin_cbh_adj", "snow_cbh_adj", "rain_cbh_adj", "adjmix_rain", "cecn_coef")
 
 
+# Stand-in values for parameters of processes that are NOT part of a model (a
+# sub-chain or a single process): the library always carries the whole column,
+# the results of the missing processes are replaced by the caller's inputs and
+# never reported, so these only have to be finite and pass the init checks.
+# (Defaults follow static/metadata/parameters.yaml where it has one.)
+_FILL_F64 = {
+    "hru_area": 1.0, "hru_in_to_cf": 3630.0, "hru_lat": 40.0, "soil_moist_max": 1.0,
+    "soil_rechr_max_frac": 1.0, "den_init": 0.1, "den_max": 0.6, "settle_const": 0.1,
+    "carea_max": 0.6, "smidx_coef": 0.005, "smidx_exp": 0.3, "freeh2o_cap": 0.05,
+    "emis_noppt": 0.757, "rad_trncf": 0.5, "snarea_thresh": 50.0, "potet_sublim": 0.5,
+    "covden_sum": 0.5, "covden_win": 0.5, "jh_coef_hru": 13.0, "radj_sppt": 0.44,
+    "radj_wppt": 0.5, "transp_tmax": 1.0, "dprst_depth_avg": 132.0, "va_open_exp": 0.001,
+    "va_clos_exp": 0.001, "slowcoef_lin": 0.015, "slowcoef_sq": 0.1, "fastcoef_lin": 0.1,
+    "fastcoef_sq": 0.8, "ssr2gw_exp": 1.0, "ssr2gw_rate": 0.1, "sat_threshold": 999.0,
+    "gwflow_coef": 0.015, "radmax": 0.8, "jh_coef": 0.014, "dday_slope": 0.4, "dday_intcp": -40.0,
+    "tmax_index": 50.0, "tmax_allsnow": 32.0, "tmax_allrain_offset": 1.0, "adjmix_rain": 1.0,
+    "snow_cbh_adj": 1.0, "rain_cbh_adj": 1.0, "cecn_coef": 5.0, "radadj_intcp": 1.0,
+    "ppt_rad_adj": 0.02, "mann_n": 0.04, "seg_depth": 1.0, "seg_length": 1000.0,
+    "seg_slope": 0.001, "x_coef": 0.2, "albset_rna": 0.8, "albset_rnm": 0.6, "albset_sna": 0.05,
+    "albset_snm": 0.2,
+}
+_FILL_I32 = {"cov_type": 1, "hru_type": 1, "hru_deplcrv": 1, "soil_type": 1, "transp_beg": 1,
+             "transp_end": 13, "melt_force": 140, "melt_look": 90}
+
+
 class Engine:
     """A PRMS/NHM domain on one GPU.
 
@@ -90,9 +117,11 @@ class Engine:
 
     def __init__(self, params: dict, start, device: int = 0, dprst_flag: bool = True,
                  adjust_parameters: bool = True, channel: bool = True,
-                 channel_chunk: int | None = None):
+                 channel_chunk: int | None = None, fill_missing: bool = False):
         self.L = _lib.lib()
         self.reg = Registry.get()
+        if fill_missing:
+            params = self._filled(params)
         self.nhru = int(np.asarray(params["hru_area"]).shape[0])
         self.nseg = int(np.asarray(params["tosegment"]).shape[0]) if (
             channel and "tosegment" in params) else 0
@@ -134,6 +163,35 @@ class Engine:
         self.day = 0
         self.sel_hru: list[str] = []
         self.sel_seg: list[str] = []
+
+    @staticmethod
+    def _filled(params: dict) -> dict:
+        """`params` completed with stand-in values (see _FILL_F64)."""
+        p = dict(params)
+        nhru = None
+        for k in ("hru_area", "hru_segment", "nhm_id", "hru_type", "cov_type"):
+            if k in p:
+                nhru = int(np.asarray(p[k]).shape[-1])
+                break
+        if nhru is None:
+            raise ValueError("cannot tell nhru: no [nhru] parameter was given")
+        for k in HRU_PARAMS_F64:
+            p.setdefault(k, np.full(nhru, _FILL_F64.get(k, 0.0)))
+        for k in MON_PARAMS_F64:
+            p.setdefault(k, np.full((12, nhru), _FILL_F64.get(k, 0.0)))
+        for k in HRU_PARAMS_I32:
+            p.setdefault(k, np.full(nhru, _FILL_I32.get(k, 0), dtype=np.int64))
+        for k in MON_PARAMS_I32:
+            p.setdefault(k, np.zeros((12, nhru), dtype=np.int64))
+        for k in SCALAR_OPTIONS:
+            p.setdefault(k, np.array([_FILL_F64[k]]))
+        p.setdefault("snarea_curve", np.linspace(0.05, 1.0, 11))
+        if "tosegment" in p:
+            nseg = int(np.asarray(p["tosegment"]).shape[0])
+            for k in SEG_PARAMS_F64:
+                p.setdefault(k, np.full(nseg, _FILL_F64.get(k, 0.0)))
+            p.setdefault("segment_type", np.zeros(nseg, dtype=np.int64))
+        return p
 
     # ---- plumbing
     def _check(self, rc):
@@ -235,6 +293,49 @@ class Engine:
             a = oi[:, k, :]
             res[v] = a.astype(np.bool_) if self.reg.dtype(v) is np.bool_ else a
         res.update({v: os_[:, k, :] for k, v in enumerate(self.sel_seg)})
+        return res, viol
+
+    # bits of `process_mask` (= the library's budget numbering)
+    PROCESS_BITS = {"PRMSCanopy": 0, "PRMSSnow": 1, "PRMSRunoff": 2, "PRMSSoilzone": 3,
+                    "PRMSGroundwater": 4, "PRMSChannel": 5}
+
+    def run_host_inputs(self, inputs: dict, process_names, budgets: bool = True,
+                        ndays: int | None = None):
+        """Advance a SUBSET of the chain (`process_names`), every variable the
+        missing processes would have produced supplied in `inputs`
+        (name -> [ndays, nhru]; names = the reference's get_inputs()).  Returns
+        like run_host."""
+        names = [k for k in inputs if k in self.reg.input_index]
+        unknown = [k for k in inputs if k not in self.reg.input_index]
+        if unknown:
+            raise ValueError(f"unknown inputs {unknown}")
+        arrs = [np.ascontiguousarray(inputs[k], dtype=np.float64) for k in names]
+        nd = arrs[0].shape[0] if arrs else int(ndays or 0)
+        for k, a in zip(names, arrs):
+            if a.shape != (nd, self.nhru):
+                raise ValueError(f"input '{k}' must be [ndays, nhru] = {(nd, self.nhru)}, got {a.shape}")
+        mask = 0
+        for p in process_names:
+            if p in self.PROCESS_BITS:
+                mask |= 1 << self.PROCESS_BITS[p]
+        cal = calendar(self.start + self.day, nd)
+        idx = np.array([self.reg.input_index[k] for k in names], dtype=np.int32)
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        of = np.empty((nd, len(self.sel_f64), self.nhru))
+        oi = np.empty((nd, len(self.sel_i32), self.nhru), dtype=np.int32)
+        os_ = np.empty((nd, len(self.sel_seg), self.nseg))
+        viol = np.zeros((nd, 6), dtype=np.int32) if budgets else None
+        self._check(self.L.pws_run_host_inputs(
+            self.h, nd, cal.ctypes.data, len(arrs), idx.ctypes.data, C.cast(ptrs, C.c_void_p), mask,
+            of.ctypes.data, oi.ctypes.data, os_.ctypes.data,
+            viol.ctypes.data if budgets else None))
+        self.day += nd
+        res = {v: of[:, k, :] for k, v in enumerate(self.sel_f64)}
+        for k, v in enumerate(self.sel_i32):
+            a = oi[:, k, :]
+            res[v] = a.astype(np.bool_) if self.reg.dtype(v) is np.bool_ else a
+        if mask & (1 << self.PROCESS_BITS["PRMSChannel"]):
+            res.update({v: os_[:, k, :] for k, v in enumerate(self.sel_seg)})
         return res, viol
 
     def run_device(self, nd, d_prcp, d_tmax, d_tmin, d_out_f64=0, d_out_i32=0, d_seg_out=0,

@@ -72,6 +72,9 @@ class Model:
         self._block_n = 0
         self._block_viol = None
         self._calculated_step = -1
+        # True when a single process is stepped by its caller, who advances
+        # the Control (autotest/test_prms_snow.py:122-132)
+        self._control_is_external = False
         self.block_days = int(self.control.options.get("block_days", 64) or 64)
         if write_control:
             self._write_control(write_control)
@@ -111,15 +114,55 @@ class Model:
 
     @staticmethod
     def _classify(order):
+        """"chain" / "chain+channel": the whole NHM column on the fused kernel;
+        "channel": routing alone; "sub": any other subset (a single process or
+        a partial chain), the missing processes replaced by input arrays."""
+        if not order:
+            raise ValueError("no processes")
         has_col = [n in order for n in COLUMN_CHAIN]
         if all(has_col):
             return "chain+channel" if "PRMSChannel" in order else "chain"
         if order == ["PRMSChannel"]:
             return "channel"
-        raise NotImplementedError(
-            "pywatershed_b200 runs the fused NHM column (PRMSSolarGeometry, PRMSAtmosphere, "
-            "PRMSCanopy, PRMSSnow, PRMSRunoff, PRMSSoilzone, PRMSGroundwater), optionally followed "
-            f"by PRMSChannel, or PRMSChannel alone; got {order}")
+        return "sub"
+
+    def _external_inputs(self):
+        """Inputs of the model's processes that no process of the model
+        produces (base/model.py:_solve_inputs).  The soltab tables are always
+        computed from the parameters."""
+        produced = set()
+        for proc in self.processes.values():
+            produced.update(proc.get_variables())
+        ext = []
+        for proc in self.processes.values():
+            for k in proc.get_inputs():
+                if k not in produced and not k.startswith("soltab") and k not in ext:
+                    ext.append(k)
+        return ext
+
+    @classmethod
+    def _around(cls, proc):
+        """The private one-process model behind a process that is stepped on
+        its own (control.advance(); proc.advance(); proc.calculate(dt))."""
+        self = cls.__new__(cls)
+        self.control = proc.control
+        self.parameters = proc.params
+        self._find_input_files = False
+        self._netcdf_initialized = False
+        self._netcdf = None
+        self._mode = cls._classify([proc.name])
+        self.processes = {proc.name: proc}
+        self.process_order = [proc.name]
+        self._param_dict = dict(proc._param_dict)
+        self._engine = None
+        self._forcings = None
+        self._block = None
+        self._block_t0 = self._block_n = 0
+        self._block_viol = None
+        self._calculated_step = -1
+        self._control_is_external = True
+        self.block_days = int(self.control.options.get("block_days", 64) or 64)
+        return self
 
     @classmethod
     def from_yaml(cls, yaml_file):
@@ -185,11 +228,16 @@ class Model:
         start = self.control.start_time
         dev = int(self.control.options.get("device", 0) or 0)
         if self._mode == "channel":
-            # the HRU column is not run; Engine still needs the HRU tables it validates
-            self._engine = Engine(pd, start, device=dev, channel=True)
+            # the HRU column is not run; its tables get stand-in values
+            self._engine = Engine(pd, start, device=dev, channel=True, fill_missing=True)
             nh = self._engine.nhru
             self._forcings = {k: self._load_input(k, nh) for k in
                               ("sroff_vol", "ssres_flow_vol", "gwres_flow_vol")}
+        elif self._mode == "sub":
+            self._engine = Engine(pd, start, device=dev, channel="PRMSChannel" in self.processes,
+                                  adjust_parameters=adj, fill_missing=True)
+            nh = self._engine.nhru
+            self._forcings = {k: self._load_input(k, nh) for k in self._external_inputs()}
         else:
             self._engine = Engine(pd, start, device=dev, channel=self._mode == "chain+channel",
                                   adjust_parameters=adj)
@@ -199,12 +247,19 @@ class Model:
         hv = list(reg.hru_vars) if self._mode != "channel" else [
             "channel_sroff_vol", "channel_ssres_flow_vol", "channel_gwres_flow_vol"]
         sv = list(reg.seg_vars) if self._engine.nseg else []
+        if self._mode == "sub":
+            mine = set()
+            for proc in self.processes.values():
+                mine.update(proc.get_variables())
+            hv = [v for v in reg.hru_vars if v in mine]
+            sv = sv if "PRMSChannel" in self.processes else []
         if self._mode != "channel":
             self._engine.select_outputs(hv, sv)
-            st = self._engine.soltab()
-            sg = self.processes["PRMSSolarGeometry"]
-            for k, v in st.items():
-                sg[k].data[:] = v
+            if "PRMSSolarGeometry" in self.processes:
+                st = self._engine.soltab()
+                sg = self.processes["PRMSSolarGeometry"]
+                for k, v in st.items():
+                    sg[k].data[:] = v
         else:
             self._engine.select_outputs([], sv)
 
@@ -216,6 +271,10 @@ class Model:
             raise RuntimeError(f"engine is at day {eng.day}, block starts at {t0}")
         if self._mode == "channel":
             blk, viol = self._channel_block(t0, n)
+        elif self._mode == "sub":
+            eng.set_block_days(min(n, 64))
+            blk, viol = eng.run_host_inputs({k: v[t0:t0 + n] for k, v in self._forcings.items()},
+                                            self.process_order, ndays=n)
         else:
             eng.set_block_days(min(n, 64))
             f = self._forcings
@@ -260,7 +319,8 @@ class Model:
         """base/model.py:723-737"""
         if self._engine is None:
             self._ensure_engine()
-        self.control.advance()
+        if not self._control_is_external:
+            self.control.advance()
         for name in ("PRMSSolarGeometry", "PRMSAtmosphere"):
             if name in self.processes:
                 proc = self.processes[name]

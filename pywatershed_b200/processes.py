@@ -205,22 +205,32 @@ class Process:
     def set_input_to_adapter(self, input_variable_name: str, adapter):
         self._input_variables_dict[input_variable_name] = adapter
 
-    # ---- stepping: only meaningful under a Model that owns the engine
+    # ---- stepping a process on its own (base/process.py:379-422): the caller
+    # advances the Control, then proc.advance(); proc.calculate(dt); proc.output().
+    # Behind it sits a private one-process Model whose missing upstream
+    # processes are the process's input arrays / files.
     def _need_model(self):
         if self._model is None:
-            raise NotImplementedError(
-                f"{self.name} computes inside the fused GPU column: build a pywatershed_b200.Model "
-                "with the NHM chain (or PRMSChannel alone) and step the model; stand-alone "
-                "stepping of a single HRU process is not implemented yet")
+            from .model import Model
+
+            self._model = Model._around(self)
+            self._owns_model = True
+        return self._model
 
     def advance(self):
-        self._need_model()
+        m = self._need_model()
+        if getattr(self, "_owns_model", False):
+            m.advance()
 
     def calculate(self, time_length: float = 1.0, **kwargs):
-        self._need_model()
+        m = self._need_model()
+        if getattr(self, "_owns_model", False):
+            m.calculate()
 
     def output(self):
-        self._need_model()
+        m = self._need_model()
+        if getattr(self, "_owns_model", False):
+            m.output()
 
     def finalize(self):
         pass

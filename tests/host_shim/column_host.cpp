@@ -37,6 +37,8 @@ struct HostSink {
   void lateral(double) {}
   void sync() {}
   void sync2() {}
+  template <int id> double ov(double v) const { return v; }
+  template <int id> int ovi(int v) const { return v; }
   void error(int c) { err |= c; }
 };
 }  // namespace

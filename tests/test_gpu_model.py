@@ -179,6 +179,7 @@ def test_reference_error_conventions(drb):
         pwsb.PRMSRunoff(control, None, _parameters(q))
     with pytest.raises(ValueError, match="calc_method"):
         pwsb.PRMSCanopy(control, None, _parameters(p), calc_method="numpy")
-    with pytest.raises(NotImplementedError):
-        pwsb.Model([pwsb.PRMSSnow], control=control, parameters=_parameters(p),
+    m = pwsb.Model([pwsb.PRMSSnow], control=control, parameters=_parameters(p),
                    find_input_files=False)
+    with pytest.raises(ValueError, match="was not provided"):  # a single process needs its inputs
+        m.advance()
