@@ -15,7 +15,8 @@ import ref_harness as rh  # noqa: E402
 pws = rh.import_reference()
 out = {}
 varmeta = {}
-for name in rh.NHM_PROCESS_NAMES:
+NODPRST = ("PRMSRunoffNoDprst", "PRMSSoilzoneNoDprst", "PRMSGroundwaterNoDprst")
+for name in rh.NHM_PROCESS_NAMES + NODPRST:
     cls = getattr(pws, name)
     init = {}
     for k, v in cls.get_init_values().items():

@@ -12,9 +12,12 @@ from .processes import (  # noqa: F401
     PRMSCanopy,
     PRMSChannel,
     PRMSGroundwater,
+    PRMSGroundwaterNoDprst,
     PRMSRunoff,
+    PRMSRunoffNoDprst,
     PRMSSnow,
     PRMSSoilzone,
+    PRMSSoilzoneNoDprst,
     PRMSSolarGeometry,
     Process,
     TimeseriesArray,
@@ -24,5 +27,6 @@ __all__ = [
     "Budget", "Control", "Engine", "Registry", "calendar", "Model", "Parameters",
     "PrmsParameters", "Process", "ConservativeProcess", "TimeseriesArray",
     "PRMSSolarGeometry", "PRMSAtmosphere", "PRMSCanopy", "PRMSSnow", "PRMSRunoff",
-    "PRMSSoilzone", "PRMSGroundwater", "PRMSChannel",
+    "PRMSSoilzone", "PRMSGroundwater", "PRMSChannel", "PRMSRunoffNoDprst", "PRMSSoilzoneNoDprst",
+    "PRMSGroundwaterNoDprst",
 ]

@@ -119,7 +119,10 @@ class Model:
         a partial chain), the missing processes replaced by input arrays."""
         if not order:
             raise ValueError("no processes")
-        has_col = [n in order for n in COLUMN_CHAIN]
+        slots = [P.base_name(n) for n in order]
+        if len(set(slots)) != len(slots):
+            raise ValueError(f"two variants of the same process in one model: {order}")
+        has_col = [n in slots for n in COLUMN_CHAIN]
         if all(has_col):
             return "chain+channel" if "PRMSChannel" in order else "chain"
         if order == ["PRMSChannel"]:
@@ -219,11 +222,15 @@ class Model:
                 dprst = f
         if dprst is None:
             dprst = True
-        if not dprst:
-            raise NotImplementedError("dprst_flag=False (the *NoDprst processes) is not implemented")
+        flags = {bool(getattr(self.processes[n], "_dprst_flag")) for n in self.process_order
+                 if getattr(self.processes[n], "_dprst_flag", None) is not None}
+        if len(flags) > 1:
+            raise ValueError("dprst_flag must be the same for every process of the model "
+                             "(mixing PRMSRunoff with PRMSSoilzoneNoDprst, ...)")
         adj = True
-        for n in ("PRMSSoilzone", "PRMSChannel"):
-            if n in self.processes and self.processes[n]._adjust_parameters == "no":
+        for n in self.process_order:
+            if P.base_name(n) in ("PRMSSoilzone", "PRMSChannel") and \
+                    self.processes[n]._adjust_parameters == "no":
                 adj = False
         start = self.control.start_time
         dev = int(self.control.options.get("device", 0) or 0)
@@ -235,12 +242,13 @@ class Model:
                               ("sroff_vol", "ssres_flow_vol", "gwres_flow_vol")}
         elif self._mode == "sub":
             self._engine = Engine(pd, start, device=dev, channel="PRMSChannel" in self.processes,
-                                  adjust_parameters=adj, fill_missing=True)
+                                  adjust_parameters=adj, fill_missing=True, dprst_flag=bool(dprst))
             nh = self._engine.nhru
             self._forcings = {k: self._load_input(k, nh) for k in self._external_inputs()}
         else:
             self._engine = Engine(pd, start, device=dev, channel=self._mode == "chain+channel",
-                                  adjust_parameters=adj)
+                                  adjust_parameters=adj, dprst_flag=bool(dprst),
+                                  fill_missing=not dprst)
             nh = self._engine.nhru
             self._forcings = {k: self._load_input(k, nh) for k in FORCINGS}
         reg = self._engine.reg
@@ -274,7 +282,7 @@ class Model:
         elif self._mode == "sub":
             eng.set_block_days(min(n, 64))
             blk, viol = eng.run_host_inputs({k: v[t0:t0 + n] for k, v in self._forcings.items()},
-                                            self.process_order, ndays=n)
+                                            [P.base_name(x) for x in self.process_order], ndays=n)
         else:
             eng.set_block_days(min(n, 64))
             f = self._forcings
@@ -361,7 +369,7 @@ class Model:
                 continue
             nv = None
             if self._block_viol is not None:
-                nv = int(self._block_viol[j, BUDGET_INDEX[name]])
+                nv = int(self._block_viol[j, BUDGET_INDEX[P.base_name(name)]])
             b.calculate(nv)
 
     def output(self):
@@ -459,7 +467,7 @@ class Model:
                     proc._vars[var][:] = self._block[var][j]
             b = getattr(proc, "budget", None)
             if b is not None and self._block_viol is not None:
-                b._n_violations = int(self._block_viol[j, BUDGET_INDEX[name]])
+                b._n_violations = int(self._block_viol[j, BUDGET_INDEX[P.base_name(name)]])
                 b._zero_sum = b._n_violations == 0
                 b._itime_accumulated = it
         self._calculated_step = it

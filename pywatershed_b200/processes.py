@@ -362,15 +362,55 @@ class PRMSChannel(ConservativeProcess):
         super().__init__(control, discretization, parameters, **_kw(locals()))
 
 
+class PRMSRunoffNoDprst(PRMSRunoff):
+    """hydrology/prms_runoff_no_dprst.py:68-91: PRMSRunoff without depression storage"""
+
+    def __init__(self, control, discretization, parameters, soil_lower_prev=None,
+                 soil_rechr_prev=None, net_ppt=None, net_rain=None, net_snow=None, potet=None,
+                 snowmelt=None, snow_evap=None, pkwater_equiv=None, pptmix_nopack=None,
+                 snowcov_area=None, through_rain=None, hru_intcpevap=None, intcp_changeover=None,
+                 budget_type=None, calc_method=None, verbose: bool = None):
+        kw = _kw(locals())
+        ConservativeProcess.__init__(self, control, discretization, parameters, dprst_flag=False, **kw)
+
+
+class PRMSSoilzoneNoDprst(PRMSSoilzone):
+    """hydrology/prms_soilzone_no_dprst.py:62-79"""
+
+    def __init__(self, control, discretization, parameters, hru_impervevap=None,
+                 hru_intcpevap=None, infil_hru=None, sroff=None, sroff_vol=None, potet=None,
+                 transp_on=None, snow_evap=None, snowcov_area=None, budget_type=None,
+                 calc_method=None, adjust_parameters="warn", verbose: bool = None):
+        if adjust_parameters not in ("warn", "error", "no"):
+            raise ValueError("adjust_parameters must be one of 'warn', 'error', 'no'")
+        kw = _kw(locals())
+        ConservativeProcess.__init__(self, control, discretization, parameters, dprst_flag=False, **kw)
+
+
+class PRMSGroundwaterNoDprst(PRMSGroundwater):
+    """hydrology/prms_groundwater_no_dprst.py:42-51"""
+
+    def __init__(self, control, discretization, parameters, soil_to_gw=None, ssr_to_gw=None,
+                 budget_type=None, calc_method=None, verbose: bool = None):
+        kw = _kw(locals())
+        ConservativeProcess.__init__(self, control, discretization, parameters, dprst_flag=False, **kw)
+
+
+def base_name(name: str) -> str:
+    """PRMSRunoffNoDprst -> PRMSRunoff: the process slot in the chain."""
+    return name.replace("NoDprst", "")
+
+
 def _kw(loc):
     return {k: v for k, v in loc.items()
-            if k not in ("self", "control", "discretization", "parameters", "__class__")}
+            if k not in ("self", "control", "discretization", "parameters", "__class__", "kw")}
 
 
 PROCESS_CLASSES = {c.__name__: c for c in (
     PRMSSolarGeometry, PRMSAtmosphere, PRMSCanopy, PRMSSnow, PRMSRunoff, PRMSSoilzone,
-    PRMSGroundwater, PRMSChannel)}
+    PRMSGroundwater, PRMSChannel, PRMSRunoffNoDprst, PRMSSoilzoneNoDprst, PRMSGroundwaterNoDprst)}
 
 # base/model.py:15-28
 PROCESS_ORDER_NHM = ("PRMSSolarGeometry", "PRMSAtmosphere", "PRMSCanopy", "PRMSSnow",
-                     "PRMSRunoff", "PRMSSoilzone", "PRMSEt", "PRMSGroundwater", "PRMSChannel")
+                     "PRMSRunoff", "PRMSRunoffNoDprst", "PRMSSoilzone", "PRMSSoilzoneNoDprst",
+                     "PRMSEt", "PRMSGroundwater", "PRMSGroundwaterNoDprst", "PRMSChannel")

@@ -183,3 +183,44 @@ def test_reference_error_conventions(drb):
                    find_input_files=False)
     with pytest.raises(ValueError, match="was not provided"):  # a single process needs its inputs
         m.advance()
+
+
+def test_nodprst_model_matches_the_reference(drb):
+    """nhm_no_dprst: the chain with PRMSRunoffNoDprst / PRMSSoilzoneNoDprst /
+    PRMSGroundwaterNoDprst (autotest/test_prms_below_snow.py:31-45) against
+    the reference's own outputs (tests/golden/drb_nodprst_golden.npz)."""
+    import pywatershed_b200 as pwsb
+
+    p, f, start = drb
+    nd = 400
+    names = ["PRMSSolarGeometry", "PRMSAtmosphere", "PRMSCanopy", "PRMSSnow", "PRMSRunoffNoDprst",
+             "PRMSSoilzoneNoDprst", "PRMSGroundwaterNoDprst", "PRMSChannel"]
+    q = {k: v for k, v in p.items() if not k.startswith("dprst") and k not in (
+        "sro_to_dprst_perv", "sro_to_dprst_imperv", "va_open_exp", "va_clos_exp", "op_flow_thres")}
+    control = _control(start, nd, dprst_flag=False)
+    m = pwsb.Model([getattr(pwsb, n) for n in names], control=control, parameters=_parameters(q),
+                   find_input_files=False)
+    for k in ("prcp", "tmax", "tmin"):
+        m.processes["PRMSAtmosphere"].set_input_to_adapter(k, f[k][:nd])
+    g = np.load(scenarios.GOLDEN / "drb_nodprst_golden.npz")
+    hs, ss = g["hru_sample"], g["seg_sample"]
+    assert "dprst_stor_hru" not in m.processes["PRMSRunoffNoDprst"].get_variables()
+    series = {}
+    for it in range(nd):
+        m.advance()
+        m.calculate()
+        for pname in names[4:]:
+            proc = m.processes[pname]
+            for v in proc.get_variables():
+                a = np.asarray(proc[v], dtype=np.float64)
+                series.setdefault(v, []).append(a[ss] if v in po.SEG_VARS else a[hs])
+    got = {v: np.stack(rows) for v, rows in series.items()}
+    ref = {v: np.asarray(g["ts_" + v], dtype=np.float64) for v in got}
+    hru_names = [v for v in got if v not in po.SEG_VARS]
+    rep = parity.compare_columns(got, ref, hru_names)
+    # ghost-pack ties (tests/parity.py) can touch a sampled HRU; anything else is a mismatch
+    assert len(rep["mismatches"]) <= 1, rep["mismatches"][:3]
+    if not rep["mismatches"]:
+        np.testing.assert_allclose(got["seg_outflow"], ref["seg_outflow"], rtol=1e-9, atol=1e-10)
+    for pname in names[4:7]:
+        assert m.processes[pname].budget._zero_sum

@@ -122,3 +122,27 @@ def test_hru_columns_are_independent(drb):
     for k in po.SEG_VARS:
         np.testing.assert_array_equal(rb[k][:, :ns], ra[k], err_msg=k)
         np.testing.assert_array_equal(rb[k][:, ns:], ra[k], err_msg=k)
+
+
+def test_nodprst_variants_match_reference(drb):
+    """The reference's PRMSRunoffNoDprst / PRMSSoilzoneNoDprst /
+    PRMSGroundwaterNoDprst (hydrology/prms_*_no_dprst.py) are the parent
+    classes with dprst_flag=False; tests/golden/drb_nodprst_golden.npz holds
+    their outputs (oracle/gen_golden_nodprst.py), 400 days."""
+    p, f, start = drb
+    g = np.load(scenarios.GOLDEN / "drb_nodprst_golden.npz")
+    nd = 400
+    o = po.Oracle(p, start=start, dprst_flag=False)
+    res, viol = o.run(f["prcp"][:nd], f["tmax"][:nd], f["tmin"][:nd], po.HRU_VARS, po.SEG_VARS)
+    o.close()
+    hs, ss = g["hru_sample"], g["seg_sample"]
+    names = [k[3:] for k in g.files if k.startswith("ts_")]
+    assert len(names) >= 130
+    for k in names:
+        samp = ss if k in po.SEG_VARS else hs
+        np.testing.assert_allclose(np.asarray(res[k], dtype=np.float64)[:, samp],
+                                   np.asarray(g["ts_" + k], dtype=np.float64),
+                                   rtol=1e-9, atol=1e-10, err_msg=k)
+        np.testing.assert_allclose(np.asarray(res[k], dtype=np.float64).sum(axis=1), g["sum_" + k],
+                                   rtol=1e-9, atol=1e-8, err_msg="sum " + k)
+    assert viol.sum() == 0
