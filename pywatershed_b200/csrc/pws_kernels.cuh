@@ -25,6 +25,11 @@
 #ifndef PWS_COLUMN_SYNC
 #define PWS_COLUMN_SYNC 1
 #endif
+// 1: the upper half requests day d+1's forcings while it computes day d
+// (14 registers held across the day); 0: loads them at the top of the day
+#ifndef PWS_COLUMN_PREFETCH
+#define PWS_COLUMN_PREFETCH 1
+#endif
 // Registers per thread of the two warp groups (setmaxnreg, multiples of 8;
 // with 256 HRUs per CTA, upper + lower must be <= 256).  Unconstrained, the
 // upper half wants 204 registers (29 prognostic values, the snow energy
@@ -330,6 +335,7 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
       nxt.horad = __ldg(a.P.soltab_horad_potsw + (int64_t)(c.x - 1) * S + ii);
     }
     for (int d = 0; d < a.ndays; ++d) {
+#if PWS_COLUMN_PREFETCH
       const DayIn in = nxt;
       if (d + 1 < a.ndays) {
         const int4 c = a.cal[d + 1];
@@ -341,6 +347,19 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
         nxt.potsw = __ldg(a.P.soltab_potsw + (int64_t)(c.x - 1) * S + ii);
         nxt.horad = __ldg(a.P.soltab_horad_potsw + (int64_t)(c.x - 1) * S + ii);
       }
+#else
+      DayIn in;
+      {
+        const int4 c = a.cal[d];
+        const int64_t fo = (int64_t)d * a.fstride + ii;
+        in.doy = c.x; in.dowy = c.y; in.month = c.z; in.dom = c.w;
+        in.prcp = __ldcs(a.prcp + fo);
+        in.tmax = __ldcs(a.tmax + fo);
+        in.tmin = __ldcs(a.tmin + fo);
+        in.potsw = __ldg(a.P.soltab_potsw + (int64_t)(c.x - 1) * S + ii);
+        in.horad = __ldg(a.P.soltab_horad_potsw + (int64_t)(c.x - 1) * S + ii);
+      }
+#endif
       if (in.month != staged_month) {  // warp-uniform
         stage_month(in.month);
         staged_month = in.month;
