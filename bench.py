@@ -54,6 +54,10 @@ def workload_spec(name):
     if name == "ucb":
         return dict(ntile=6, nhru_keep=3851, ndays=731, label="ucb_2yr-shaped synthetic "
                     "(3,851 HRUs, 2,736 segments, 731 days; real ucb_2yr inputs are HDF5 blobs)")
+    if name in ("ensemble", "ensemble128"):
+        nm = 1024 if name == "ensemble" else 128
+        return dict(ntile=nm, nhru_keep=None, ndays=731, label=f"{nm}-member DRB parameter ensemble "
+                    f"({nm * 765:,} HRUs, {nm * 456:,} segments member-major, 731 days)")
     if name == "drb":
         return dict(ntile=1, nhru_keep=None, ndays=731, label="drb_2yr (765 HRUs, 456 segments, 731 days)")
     raise SystemExit(f"unknown workload {name}")
