@@ -409,14 +409,17 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     bpu = algorithmic_bytes_per_hru_day(eng.reg, hru_vars)
+    achieved = units_per_launch * bpu / avg_launch_s / 1e9
     avg_launch_s = (col_ms / max(ncol, 1)) * 1e-3
     units_per_launch = nhru * nd * args.steps / max(ncol, 1)
-    achieved = units_per_launch * bpu / avg_launch_s / 1e9
+    # DRAM bytes per launch from the committed ncu capture (profiles/), scaled to
+    # this run's launch size; only meaningful for the output mode it was taken in
     traffic = None
     prof = ROOT / "profiles" / "r01_column_traffic.json"
-    if prof.exists():
+    if prof.exists() and args.outputs == "full":
         try:
-            traffic = json.loads(prof.read_text()).get("dram_bytes_per_launch")
+            pj = json.loads(prof.read_text())
+            traffic = pj["dram_bytes_per_launch"] * units_per_launch / pj["hru_days_per_launch"]
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -428,7 +431,7 @@ def main():
                 "channel_share_of_step": ch_ms / max(sum(step_ms), 1e-9)}
 
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         ncores = os.cpu_count() or 1
         nthreads = max(1, min(ncores, 64))
         r, units, dt = cpu_oracle_rate(p0, f0, start, 1, min(nd, 3653), nthreads)
