@@ -409,9 +409,9 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     bpu = algorithmic_bytes_per_hru_day(eng.reg, hru_vars)
-    achieved = units_per_launch * bpu / avg_launch_s / 1e9
     avg_launch_s = (col_ms / max(ncol, 1)) * 1e-3
     units_per_launch = nhru * nd * args.steps / max(ncol, 1)
+    achieved = units_per_launch * bpu / avg_launch_s / 1e9
     # DRAM bytes per launch from the committed ncu capture (profiles/), scaled to
     # this run's launch size; only meaningful for the output mode it was taken in
     traffic = None
