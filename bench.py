@@ -261,6 +261,7 @@ def main():
     ap.add_argument("--block-days", type=int, default=256)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-block-days", type=int, default=128)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     spec = workload_spec(args.workload)
@@ -361,7 +362,7 @@ def main():
         e2e_seg = ["seg_outflow"]  # streamflow at every segment: the product of an NHM run
         eng.select_outputs([], e2e_seg)
         hf = {k: v.cpu().pin_memory() for k, v in forc.items()}
-        e2e_T = 64
+        e2e_T = args.e2e_block_days
         eng.set_block_days(e2e_T)
         # pin the result buffers too (the library drains with cudaMemcpyAsync)
         cal_nd = nd
