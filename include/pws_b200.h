@@ -56,11 +56,13 @@ int pws_set_param_i32(pws_handle *h, const char *name, const int32_t *h_v, int64
  * prms_atmosphere.py:695-696), "adjust_parameters" (prms_soilzone.py:100),
  * "albset_rna|rnm|sna|snm" (scalar parameters, prms_snow.py:911-914),
  * "block_days" (days per device time block of pws_run_host),
+ * "tma" (1, default: the column kernel stages each day's forcing rows in shared
+ * memory with TMA bulk copies when they are 16-byte aligned; 0: per-thread loads),
  * "soltab_device" (1: build the PRMSSolarGeometry tables with the CUDA kernel
  * k_soltab; 0, default: with the host libm the reference's tables come from),
- * "wavefront" (1, default: route all DAG levels concurrently in one persistent
- * cooperative kernel when every segment thread can be resident; 0: one launch
- * per topological level). */
+ * "channel_chunk" (segments per routing chunk = per CTA of k_route_chunks,
+ * default and maximum 512; outlet trees larger than a chunk are cut and linked
+ * through HBM). */
 int pws_set_option(pws_handle *h, const char *name, double value);
 
 /* Everything the reference derives at construction: soltab tables

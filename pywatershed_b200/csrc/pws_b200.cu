@@ -97,6 +97,7 @@ struct pws_handle {
   int dprst_flag = 1, temp_units = 0, start_month = 1, start_doy = 1, adjust_parameters = 1;
   int block_days = 0;
   int soltab_device = 0;
+  int tma = 1;  // option: stage forcings with TMA bulk copies when the rows are aligned
   bool smem_attr_set = false;
   double albset[4] = {0, 0, 0, 0};
   // host copies of the parameters (set before pws_init)
@@ -348,6 +349,7 @@ extern "C" int pws_set_option(pws_handle* h, const char* name, double value) {
   else if (!strcmp(name, "albset_snm")) h->albset[3] = value;
   else if (!strcmp(name, "block_days")) { h->block_days = (int)value; return 0; }
   else if (!strcmp(name, "soltab_device")) h->soltab_device = value != 0.0;
+  else if (!strcmp(name, "tma")) { h->tma = value != 0.0; return 0; }
   else if (!strcmp(name, "channel_chunk")) {
     if (value < 1 || value > PWS_CHUNK_THREADS)
       PWS_FAIL(h, "pws_set_option: channel_chunk must be in 1..%d", PWS_CHUNK_THREADS);
@@ -920,6 +922,10 @@ static void fill_column_args(pws_handle* h, ColumnArgs& a, int ndays, const doub
   a.state = h->d_state;
   a.prcp = d_prcp; a.tmax = d_tmax; a.tmin = d_tmin;
   a.fstride = fstride;
+  // TMA bulk copies need 16-byte aligned rows of a multiple of 16 bytes
+  // (an odd row is copied with one padding element, which must exist: fstride > nhru)
+  a.use_tma = (h->tma && fstride % 2 == 0 && (h->nhru % 2 == 0 || fstride > h->nhru) &&
+               ((uintptr_t)d_prcp | (uintptr_t)d_tmax | (uintptr_t)d_tmin) % 16 == 0) ? 1 : 0;
   a.cal = h->d_cal;
   a.ndays = ndays;
   a.out_f64 = d_out_f64; a.out_i32 = d_out_i32;
@@ -1087,7 +1093,7 @@ extern "C" int pws_run_host(pws_handle* h, int ndays, const int32_t* h_cal, cons
     h->ring_i32_elems = (size_t)T * std::max(h->n_i32, 1) * n;
     h->ring_seg_elems = (size_t)T * std::max(h->n_seg_sel, 1) * std::max<int64_t>(h->nseg, 1);
     for (int b = 0; b < 2; ++b) {
-      PWS_CUDA(h, cudaMalloc(&h->d_forc[b], (size_t)T * 3 * n * sizeof(double)));
+      PWS_CUDA(h, cudaMalloc(&h->d_forc[b], (size_t)T * 3 * h->stride * sizeof(double)));
       PWS_CUDA(h, cudaMalloc(&h->d_of64[b], h->ring_f64_elems * sizeof(double)));
       PWS_CUDA(h, cudaMalloc(&h->d_oi32[b], h->ring_i32_elems * sizeof(int32_t)));
       PWS_CUDA(h, cudaMalloc(&h->d_oseg[b], h->ring_seg_elems * sizeof(double)));
@@ -1102,16 +1108,20 @@ extern "C" int pws_run_host(pws_handle* h, int ndays, const int32_t* h_cal, cons
     const int nd = std::min(T, ndays - d0);
     // the ring slot is free once its previous outputs have drained
     if (blk >= 2) PWS_CUDA(h, cudaStreamWaitEvent(h->s_h2d, h->ev_comp[b], 0));
-    const size_t fb = (size_t)nd * n * sizeof(double);
-    PWS_CUDA(h, cudaMemcpyAsync(h->d_forc[b], h_prcp + (size_t)d0 * n, fb, cudaMemcpyHostToDevice, h->s_h2d));
-    PWS_CUDA(h, cudaMemcpyAsync(h->d_forc[b] + (size_t)T * n, h_tmax + (size_t)d0 * n, fb, cudaMemcpyHostToDevice, h->s_h2d));
-    PWS_CUDA(h, cudaMemcpyAsync(h->d_forc[b] + (size_t)2 * T * n, h_tmin + (size_t)d0 * n, fb, cudaMemcpyHostToDevice, h->s_h2d));
+    // forcing rows go into the ring with the padded row stride (16-byte aligned
+    // rows for the TMA staging of k_hru_column)
+    const size_t S8 = (size_t)h->stride * sizeof(double), n8 = (size_t)n * sizeof(double);
+    const double* srcs[3] = {h_prcp, h_tmax, h_tmin};
+    for (int k = 0; k < 3; ++k)
+      PWS_CUDA(h, cudaMemcpy2DAsync(h->d_forc[b] + (size_t)k * T * h->stride, S8,
+                                    srcs[k] + (size_t)d0 * n, n8, n8, (size_t)nd,
+                                    cudaMemcpyHostToDevice, h->s_h2d));
     PWS_CUDA(h, cudaEventRecord(h->ev_h2d[b], h->s_h2d));
     PWS_CUDA(h, cudaStreamWaitEvent(h->s_compute, h->ev_h2d[b], 0));
     if (blk >= 2) PWS_CUDA(h, cudaStreamWaitEvent(h->s_compute, h->ev_d2h[b], 0));
-    if (enqueue_block(h, nd, h_cal + (size_t)d0 * 4, h->d_forc[b], h->d_forc[b] + (size_t)T * n,
-                      h->d_forc[b] + (size_t)2 * T * n, n, h->d_of64[b], h->d_oi32[b], h->d_oseg[b],
-                      h_budget_viol != nullptr))
+    if (enqueue_block(h, nd, h_cal + (size_t)d0 * 4, h->d_forc[b],
+                      h->d_forc[b] + (size_t)T * h->stride, h->d_forc[b] + (size_t)2 * T * h->stride,
+                      h->stride, h->d_of64[b], h->d_oi32[b], h->d_oseg[b], h_budget_viol != nullptr))
       return 1;
     if (h_budget_viol)
       PWS_CUDA(h, cudaMemcpyAsync(h_budget_viol + (size_t)d0 * BUD_N, h->d_viol,

@@ -25,11 +25,7 @@
 #ifndef PWS_COLUMN_SYNC
 #define PWS_COLUMN_SYNC 1
 #endif
-// 1: the upper half requests day d+1's forcings while it computes day d
-// (14 registers held across the day); 0: loads them at the top of the day
-#ifndef PWS_COLUMN_PREFETCH
-#define PWS_COLUMN_PREFETCH 1
-#endif
+
 // Registers per thread of the two warp groups (setmaxnreg, multiples of 8;
 // with 256 HRUs per CTA, upper + lower must be <= 256).  Unconstrained, the
 // upper half wants 204 registers (29 prognostic values, the snow energy
@@ -94,6 +90,7 @@ struct ColumnArgs {
   const double* tmax;
   const double* tmin;
   int64_t fstride;
+  int use_tma;              // forcing rows are 16-byte aligned: stage them with cp.async.bulk
   const int4* cal;          // [ndays] (doy, dowy, month, dom), device
   int ndays;
   double* out_f64;          // [ndays][n_f64][ostride]
@@ -219,11 +216,47 @@ constexpr int kMidF64 = 10, kMidI32 = 2;  // ColumnMid
 constexpr int kMidSlots = PWS_COLUMN_MID_SLOTS;
 constexpr int kColF64 = kUpperF64 + kUpperMonF64 + kLowerF64 + kMidSlots * kMidF64;
 constexpr int kColI32 = kUpperI32 + kLowerI32 + kMidSlots * kMidI32;
-constexpr size_t kColumnSmemBytes = (size_t)PWS_COLUMN_HRUS * (kColF64 * 8 + kColI32 * 4);
+// forcing stage of the upper half: 2 days x {prcp, tmax, tmin, soltab_potsw row,
+// soltab_horad_potsw row} x H, filled by TMA bulk copies, + 2 mbarriers
+constexpr int kForcRows = 5;
+constexpr size_t kColumnParamBytes = (size_t)PWS_COLUMN_HRUS * (kColF64 * 8 + kColI32 * 4);
+constexpr size_t kColumnForcBytes = (size_t)2 * kForcRows * PWS_COLUMN_HRUS * 8;
+constexpr size_t kColumnSmemBytes = kColumnParamBytes + kColumnForcBytes + 16;
+static_assert(kColumnParamBytes % 16 == 0, "forcing stage must be 16-byte aligned");
 
 // named barriers of k_hru_column (0 is __syncthreads)
 enum { BAR_UPPER = 1, BAR_LOWER = 2, BAR_MID_FULL = 3, BAR_MID_EMPTY = 3 + PWS_COLUMN_MID_SLOTS };
 static_assert(3 + 2 * PWS_COLUMN_MID_SLOTS <= 16, "named barriers");
+
+// ---- TMA bulk copy + mbarrier (sm_90+ PTX; SASS: UBLKCP / SYNCS)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes,
+                                             uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; "
+        "selp.u32 %0, 1, 0, p; }"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
 
 __device__ __forceinline__ void bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -264,6 +297,8 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
   int32_t* const siU = reinterpret_cast<int32_t*>(spM + (size_t)kMidSlots * kMidF64 * H);
   int32_t* const siL = siU + (size_t)kUpperI32 * H;
   int32_t* const siM = siL + (size_t)kLowerI32 * H;
+  double* const sF = reinterpret_cast<double*>(smem_raw + kColumnParamBytes);  // [2][kForcRows][H]
+  const uint32_t mbar0 = smem_u32(smem_raw + kColumnParamBytes + kColumnForcBytes);
 
   GpuSink<kMode> out{a, nullptr, nullptr, nullptr, (unsigned)(a.ostride * 8),
                      (unsigned)(a.ostride * 4), 0u, 0, live, upper ? BAR_UPPER : BAR_LOWER};
@@ -323,9 +358,42 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
 #undef X
     };
     int staged_month = 0;
-    // forcing prefetch: day d+1 is in flight while day d computes
+    // Forcings of day d+1 are in flight while day d computes.  When the rows
+    // are 16-byte aligned (a.use_tma) one thread streams the five rows of the
+    // CTA's HRUs into shared memory with TMA bulk copies that complete on an
+    // mbarrier (2 slots); otherwise every thread prefetches its own values
+    // into registers.
+    const bool tma = a.use_tma != 0;
+    const int64_t hru0 = (int64_t)blockIdx.x * H;
+    // an odd tail is copied with the padding element behind it (see fill_column_args)
+    const int64_t row_n = (a.P.nhru - hru0) < H ? (a.P.nhru - hru0) : H;
+    const uint32_t row_bytes = (uint32_t)(((row_n + 1) & ~(int64_t)1) * 8);
+    auto tma_issue = [&](int d) {  // one thread
+      const int slot = d & 1;
+      const uint32_t bar = mbar0 + 8u * slot;
+      const uint32_t dst = smem_u32(sF + (size_t)slot * kForcRows * H);
+      const int doy = a.cal[d].x;
+      const int64_t fo = (int64_t)d * a.fstride + hru0;
+      const int64_t so = (int64_t)(doy - 1) * S + hru0;
+      mbar_expect_tx(bar, kForcRows * row_bytes);
+      tma_bulk_g2s(dst + 0 * H * 8, a.prcp + fo, row_bytes, bar);
+      tma_bulk_g2s(dst + 1 * H * 8, a.tmax + fo, row_bytes, bar);
+      tma_bulk_g2s(dst + 2 * H * 8, a.tmin + fo, row_bytes, bar);
+      tma_bulk_g2s(dst + 3 * H * 8, a.P.soltab_potsw + so, row_bytes, bar);
+      tma_bulk_g2s(dst + 4 * H * 8, a.P.soltab_horad_potsw + so, row_bytes, bar);
+    };
     DayIn nxt;
-    {
+    if (tma) {
+      if (r == 0) {
+        mbar_init(mbar0, 1);
+        mbar_init(mbar0 + 8u, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+      for (int k = 0; k < 2 * kForcRows; ++k) sF[k * H + r] = 0.0;  // lanes past the last HRU
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      bar_sync(BAR_UPPER, H);
+      if (r == 0) tma_issue(0);
+    } else {
       const int4 c = a.cal[0];
       nxt.doy = c.x; nxt.dowy = c.y; nxt.month = c.z; nxt.dom = c.w;
       nxt.prcp = __ldcs(a.prcp + ii);
@@ -335,31 +403,33 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
       nxt.horad = __ldg(a.P.soltab_horad_potsw + (int64_t)(c.x - 1) * S + ii);
     }
     for (int d = 0; d < a.ndays; ++d) {
-#if PWS_COLUMN_PREFETCH
-      const DayIn in = nxt;
-      if (d + 1 < a.ndays) {
-        const int4 c = a.cal[d + 1];
-        const int64_t fo = (int64_t)(d + 1) * a.fstride + ii;
-        nxt.doy = c.x; nxt.dowy = c.y; nxt.month = c.z; nxt.dom = c.w;
-        nxt.prcp = __ldcs(a.prcp + fo);
-        nxt.tmax = __ldcs(a.tmax + fo);
-        nxt.tmin = __ldcs(a.tmin + fo);
-        nxt.potsw = __ldg(a.P.soltab_potsw + (int64_t)(c.x - 1) * S + ii);
-        nxt.horad = __ldg(a.P.soltab_horad_potsw + (int64_t)(c.x - 1) * S + ii);
-      }
-#else
       DayIn in;
-      {
+      if (tma) {
+        // slot (d+1)&1 was last read at the top of day d-1; every thread of the
+        // group has since passed a group barrier inside column_upper
+        if (r == 0 && d + 1 < a.ndays) tma_issue(d + 1);
         const int4 c = a.cal[d];
-        const int64_t fo = (int64_t)d * a.fstride + ii;
         in.doy = c.x; in.dowy = c.y; in.month = c.z; in.dom = c.w;
-        in.prcp = __ldcs(a.prcp + fo);
-        in.tmax = __ldcs(a.tmax + fo);
-        in.tmin = __ldcs(a.tmin + fo);
-        in.potsw = __ldg(a.P.soltab_potsw + (int64_t)(c.x - 1) * S + ii);
-        in.horad = __ldg(a.P.soltab_horad_potsw + (int64_t)(c.x - 1) * S + ii);
+        mbar_wait(mbar0 + 8u * (d & 1), (uint32_t)((d >> 1) & 1));
+        const double* f = sF + (size_t)(d & 1) * kForcRows * H + r;
+        in.prcp = f[0 * H];
+        in.tmax = f[1 * H];
+        in.tmin = f[2 * H];
+        in.potsw = f[3 * H];
+        in.horad = f[4 * H];
+      } else {
+        in = nxt;
+        if (d + 1 < a.ndays) {
+          const int4 c = a.cal[d + 1];
+          const int64_t fo = (int64_t)(d + 1) * a.fstride + ii;
+          nxt.doy = c.x; nxt.dowy = c.y; nxt.month = c.z; nxt.dom = c.w;
+          nxt.prcp = __ldcs(a.prcp + fo);
+          nxt.tmax = __ldcs(a.tmax + fo);
+          nxt.tmin = __ldcs(a.tmin + fo);
+          nxt.potsw = __ldg(a.P.soltab_potsw + (int64_t)(c.x - 1) * S + ii);
+          nxt.horad = __ldg(a.P.soltab_horad_potsw + (int64_t)(c.x - 1) * S + ii);
+        }
       }
-#endif
       if (in.month != staged_month) {  // warp-uniform
         stage_month(in.month);
         staged_month = in.month;

@@ -97,6 +97,40 @@ def test_full_chain_parity(scen, drb, drbx):
         assert rep2["mismatches"] == []
 
 
+@pytest.mark.parametrize("tma", [1, 0])
+def test_forcing_staging_paths_agree(drb, tma):
+    """k_hru_column stages the forcing rows with TMA bulk copies when they are
+    16-byte aligned (pws_run_host's padded ring: always; device-resident
+    forcings: even nhru) and falls back to per-thread loads otherwise; both
+    must give the oracle's numbers.  2 tiles = 1,530 HRUs: an even domain whose
+    last CTA is partial."""
+    import torch
+
+    p, f, start = drb
+    pt, ft = scenarios.tile(p, f, 2)
+    nd = 120
+    ref = _oracle(pt, ft, start, nd)[1]
+    e = _engine(pt, start)
+    e._opt("tma", tma)
+    got, _ = e.run_host(ft["prcp"][:nd], ft["tmax"][:nd], ft["tmin"][:nd])
+    _assert_chain_parity(got, ref)
+    # device-resident forcings (row stride = nhru, even): same bits as the host path
+    e2 = _engine(pt, start)
+    e2._opt("tma", tma)
+    dev = torch.device("cuda:0")
+    t = {k: torch.from_numpy(np.ascontiguousarray(ft[k][:nd])).to(dev) for k in ("prcp", "tmax", "tmin")}
+    nf, ni = len(e2.sel_f64), len(e2.sel_i32)
+    of = torch.empty((nd, nf, e2.nhru), dtype=torch.float64, device=dev)
+    oi = torch.empty((nd, ni, e2.nhru), dtype=torch.int32, device=dev)
+    osg = torch.empty((nd, 5, e2.nseg), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    e2.run_device(nd, t["prcp"].data_ptr(), t["tmax"].data_ptr(), t["tmin"].data_ptr(),
+                  of.data_ptr(), oi.data_ptr(), osg.data_ptr())
+    of = of.cpu().numpy()
+    for k, v in enumerate(e2.sel_f64):
+        np.testing.assert_array_equal(of[:, k], got[v], err_msg=v)
+
+
 def test_time_blocking_is_transparent(drb):
     """Block length must not change a single bit (state round-trips through
     HBM between blocks)."""
