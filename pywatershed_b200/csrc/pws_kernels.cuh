@@ -278,11 +278,13 @@ __device__ __forceinline__ void bar_arrive(int id, int count) {
 // register file and shared memory, and each warp walks only its half of the
 // code.
 template <int kMode>
-__global__ void __launch_bounds__(2 * PWS_COLUMN_HRUS, 1)
+__global__ void __launch_bounds__(2 * PWS_COLUMN_HRUS, (2 * PWS_COLUMN_HRUS <= 256) ? 512 / (2 * PWS_COLUMN_HRUS) : 1)
 k_hru_column(const __grid_constant__ ColumnArgs a) {
   constexpr int H = PWS_COLUMN_HRUS;
+  // setmaxnreg acts on whole warpgroups (4 warps): each half must be a multiple of one
+  static_assert(H % 128 == 0, "PWS_COLUMN_HRUS must be a multiple of 128");
   const int tid = threadIdx.x;
-  const bool upper = tid < H;  // warp-uniform
+  const bool upper = tid < H;  // warpgroup-uniform
   const int r = upper ? tid : tid - H;
   const int64_t i = (int64_t)blockIdx.x * H + r;
   const bool live = i < a.P.nhru;
