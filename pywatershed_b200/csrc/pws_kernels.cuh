@@ -18,12 +18,14 @@
 #ifndef PWS_COLUMN_HRUS
 #define PWS_COLUMN_HRUS 256
 #endif
-// 1: CTA-wide (per warp group) barriers at the process boundaries inside a day
-// (see column_upper / column_lower): the warps of a group execute the same
-// stretch of code at the same time and share its instruction fetches; 2 = also
-// inside the large processes (loses more to imbalance than it gains).
+// 1: per warp group barriers at the process boundaries inside a day (see
+// column_upper / column_lower): the warps of a group execute the same stretch
+// of code at the same time and share its instruction fetches; 2 = also inside
+// the large processes.  Worth 16 % when one warp ran the whole column; with
+// the column split over two warp groups each warp walks half of the code and
+// the barriers only cost (CONUS domain, ms per pass: 0 -> 118, 1 -> 119, 2 -> 123).
 #ifndef PWS_COLUMN_SYNC
-#define PWS_COLUMN_SYNC 1
+#define PWS_COLUMN_SYNC 0
 #endif
 
 // Registers per thread of the two warp groups (setmaxnreg, multiples of 8;
@@ -407,8 +409,9 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
     for (int d = 0; d < a.ndays; ++d) {
       DayIn in;
       if (tma) {
-        // slot (d+1)&1 was last read at the top of day d-1; every thread of the
-        // group has since passed a group barrier inside column_upper
+        // slot (d+1)&1 was last read at the top of day d-1: wait until every
+        // thread of the group has finished that day before overwriting it
+        if (d > 0) bar_sync(BAR_UPPER, H);
         if (r == 0 && d + 1 < a.ndays) tma_issue(d + 1);
         const int4 c = a.cal[d];
         in.doy = c.x; in.dowy = c.y; in.month = c.z; in.dom = c.w;
