@@ -140,6 +140,13 @@ struct pws_handle {
   int32_t* d_oi32[2] = {nullptr, nullptr};
   double* d_oseg[2] = {nullptr, nullptr};
   size_t ring_f64_elems = 0, ring_i32_elems = 0, ring_seg_elems = 0;
+  // pinned staging for pageable caller buffers (pws_run_host)
+  int stage_days = 0;
+  double* hs_in[2] = {nullptr, nullptr};
+  double* hs_of[2] = {nullptr, nullptr};
+  int32_t* hs_oi[2] = {nullptr, nullptr};
+  double* hs_os[2] = {nullptr, nullptr};
+  int32_t* hs_viol[2] = {nullptr, nullptr};
   // streams / events
   cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_col0 = nullptr, ev_col1 = nullptr, ev_ch1 = nullptr;
@@ -239,7 +246,19 @@ extern "C" int pws_create(pws_handle** out, int device, int64_t nhru, int64_t ns
 
 static void clear_timing(pws_handle* h);
 
+static void free_stage(pws_handle* h) {
+  for (int b = 0; b < 2; ++b) {
+    cudaFreeHost(h->hs_in[b]); h->hs_in[b] = nullptr;
+    cudaFreeHost(h->hs_of[b]); h->hs_of[b] = nullptr;
+    cudaFreeHost(h->hs_oi[b]); h->hs_oi[b] = nullptr;
+    cudaFreeHost(h->hs_os[b]); h->hs_os[b] = nullptr;
+    cudaFreeHost(h->hs_viol[b]); h->hs_viol[b] = nullptr;
+  }
+  h->stage_days = 0;
+}
+
 static void free_ring(pws_handle* h) {
+  free_stage(h);
   for (int b = 0; b < 2; ++b) {
     cudaFree(h->d_forc[b]); h->d_forc[b] = nullptr;
     cudaFree(h->d_of64[b]); h->d_of64[b] = nullptr;
@@ -871,7 +890,7 @@ static int ensure_scratch(pws_handle* h, int ndays) {
   return 0;
 }
 
-static cudaEvent_t new_event(pws_handle* h) {
+static cudaEvent_t new_event(pws_handle* /*h*/) {
   cudaEvent_t e = nullptr;
   cudaEventCreate(&e);
   return e;
@@ -1068,8 +1087,39 @@ extern "C" int pws_run_channel_device(pws_handle* h, int ndays, const double* d_
   return 0;
 }
 
+// memcpy spread over a few threads (a single core moves ~10 GB/s, the PCIe link 30+)
+static void par_memcpy(void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return;
+  const size_t kChunk = (size_t)8 << 20;
+  const int nthr = (int)std::min<size_t>(8, std::max<size_t>(1, bytes / kChunk));
+  if (nthr <= 1) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  std::vector<std::thread> pool;
+  const size_t per = (bytes / nthr + 63) & ~(size_t)63;
+  for (int t = 0; t < nthr; ++t) {
+    const size_t lo = (size_t)t * per, hi = std::min(bytes, lo + per);
+    if (lo < hi) pool.emplace_back([=]() { memcpy((char*)dst + lo, (const char*)src + lo, hi - lo); });
+  }
+  for (auto& th : pool) th.join();
+}
+
+static bool is_pinned(const void* p) {
+  if (p == nullptr) return true;
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
 // Time-blocked host loop: block b's forcings go up on s_h2d while block b-1
-// computes on s_compute and block b-2's outputs drain on s_d2h.
+// computes on s_compute and block b-2's outputs drain on s_d2h.  Pinned caller
+// buffers are used directly; pageable ones (numpy arrays) would turn every
+// cudaMemcpyAsync into a blocking copy, so they are staged through two pinned
+// slots per direction, filled / emptied by the host while the GPU works.
 extern "C" int pws_run_host(pws_handle* h, int ndays, const int32_t* h_cal, const double* h_prcp,
                             const double* h_tmax, const double* h_tmin, double* h_out_f64,
                             int32_t* h_out_i32, double* h_seg_out, int32_t* h_budget_viol) {
@@ -1101,53 +1151,96 @@ extern "C" int pws_run_host(pws_handle* h, int ndays, const int32_t* h_cal, cons
     h->ring_days = T;
   }
   if (ensure_scratch(h, T)) return 1;
+  const bool want_f64 = h->n_f64 > 0 && h_out_f64, want_i32 = h->n_i32 > 0 && h_out_i32;
+  const bool want_seg = h->n_seg_sel > 0 && h->nseg > 0 && h_seg_out;
+  const bool staged = !(is_pinned(h_prcp) && is_pinned(h_tmax) && is_pinned(h_tmin) &&
+                        is_pinned(want_f64 ? h_out_f64 : nullptr) &&
+                        is_pinned(want_i32 ? h_out_i32 : nullptr) &&
+                        is_pinned(want_seg ? h_seg_out : nullptr));
+  if (staged && h->stage_days < h->ring_days) {
+    free_stage(h);
+    for (int b = 0; b < 2; ++b) {
+      PWS_CUDA(h, cudaHostAlloc(&h->hs_in[b], (size_t)h->ring_days * 3 * n * sizeof(double), 0));
+      PWS_CUDA(h, cudaHostAlloc(&h->hs_of[b], h->ring_f64_elems * sizeof(double), 0));
+      PWS_CUDA(h, cudaHostAlloc(&h->hs_oi[b], h->ring_i32_elems * sizeof(int32_t), 0));
+      PWS_CUDA(h, cudaHostAlloc(&h->hs_os[b], h->ring_seg_elems * sizeof(double), 0));
+      PWS_CUDA(h, cudaHostAlloc(&h->hs_viol[b], (size_t)h->ring_days * BUD_N * sizeof(int32_t), 0));
+    }
+    h->stage_days = h->ring_days;
+  }
+  const int RT = h->ring_days;  // row capacity of the ring / stage slots
   const int nblocks = (ndays + T - 1) / T;
+  // copy block `blk`'s drained outputs from its stage slot to the caller's arrays
+  auto drain_stage = [&](int blk) -> int {
+    const int b = blk & 1, d0 = blk * T, nd = std::min(T, ndays - d0);
+    PWS_CUDA(h, cudaEventSynchronize(h->ev_d2h[b]));
+    if (want_f64)
+      par_memcpy(h_out_f64 + (size_t)d0 * h->n_f64 * n, h->hs_of[b],
+                 (size_t)nd * h->n_f64 * n * sizeof(double));
+    if (want_i32)
+      par_memcpy(h_out_i32 + (size_t)d0 * h->n_i32 * n, h->hs_oi[b],
+                 (size_t)nd * h->n_i32 * n * sizeof(int32_t));
+    if (want_seg)
+      par_memcpy(h_seg_out + (size_t)d0 * h->n_seg_sel * h->nseg, h->hs_os[b],
+                 (size_t)nd * h->n_seg_sel * h->nseg * sizeof(double));
+    if (h_budget_viol)
+      memcpy(h_budget_viol + (size_t)d0 * BUD_N, h->hs_viol[b], (size_t)nd * BUD_N * sizeof(int32_t));
+    return 0;
+  };
   for (int blk = 0; blk < nblocks; ++blk) {
     const int b = blk & 1;
     const int d0 = blk * T;
     const int nd = std::min(T, ndays - d0);
+    const double* srcs[3] = {h_prcp + (size_t)d0 * n, h_tmax + (size_t)d0 * n, h_tmin + (size_t)d0 * n};
+    if (staged) {
+      // slot b: block blk-2 must have drained before its stage buffers are reused
+      if (blk >= 2 && drain_stage(blk - 2)) return 1;
+      for (int k = 0; k < 3; ++k) {
+        par_memcpy(h->hs_in[b] + (size_t)k * RT * n, srcs[k], (size_t)nd * n * sizeof(double));
+        srcs[k] = h->hs_in[b] + (size_t)k * RT * n;
+      }
+    }
     // the ring slot is free once its previous outputs have drained
     if (blk >= 2) PWS_CUDA(h, cudaStreamWaitEvent(h->s_h2d, h->ev_comp[b], 0));
     // forcing rows go into the ring with the padded row stride (16-byte aligned
     // rows for the TMA staging of k_hru_column)
     const size_t S8 = (size_t)h->stride * sizeof(double), n8 = (size_t)n * sizeof(double);
-    const double* srcs[3] = {h_prcp, h_tmax, h_tmin};
     for (int k = 0; k < 3; ++k)
-      PWS_CUDA(h, cudaMemcpy2DAsync(h->d_forc[b] + (size_t)k * T * h->stride, S8,
-                                    srcs[k] + (size_t)d0 * n, n8, n8, (size_t)nd,
-                                    cudaMemcpyHostToDevice, h->s_h2d));
+      PWS_CUDA(h, cudaMemcpy2DAsync(h->d_forc[b] + (size_t)k * RT * h->stride, S8, srcs[k], n8, n8,
+                                    (size_t)nd, cudaMemcpyHostToDevice, h->s_h2d));
     PWS_CUDA(h, cudaEventRecord(h->ev_h2d[b], h->s_h2d));
     PWS_CUDA(h, cudaStreamWaitEvent(h->s_compute, h->ev_h2d[b], 0));
     if (blk >= 2) PWS_CUDA(h, cudaStreamWaitEvent(h->s_compute, h->ev_d2h[b], 0));
     if (enqueue_block(h, nd, h_cal + (size_t)d0 * 4, h->d_forc[b],
-                      h->d_forc[b] + (size_t)T * h->stride, h->d_forc[b] + (size_t)2 * T * h->stride,
+                      h->d_forc[b] + (size_t)RT * h->stride, h->d_forc[b] + (size_t)2 * RT * h->stride,
                       h->stride, h->d_of64[b], h->d_oi32[b], h->d_oseg[b], h_budget_viol != nullptr))
       return 1;
     if (h_budget_viol)
-      PWS_CUDA(h, cudaMemcpyAsync(h_budget_viol + (size_t)d0 * BUD_N, h->d_viol,
-                                  (size_t)nd * BUD_N * sizeof(int), cudaMemcpyDeviceToHost,
-                                  h->s_compute));
+      PWS_CUDA(h, cudaMemcpyAsync(staged ? h->hs_viol[b] : h_budget_viol + (size_t)d0 * BUD_N,
+                                  h->d_viol, (size_t)nd * BUD_N * sizeof(int),
+                                  cudaMemcpyDeviceToHost, h->s_compute));
     PWS_CUDA(h, cudaEventRecord(h->ev_comp[b], h->s_compute));
     PWS_CUDA(h, cudaStreamWaitEvent(h->s_d2h, h->ev_comp[b], 0));
-    if (h->n_f64 > 0 && h_out_f64)
-      PWS_CUDA(h, cudaMemcpyAsync(h_out_f64 + (size_t)d0 * h->n_f64 * n, h->d_of64[b],
-                                  (size_t)nd * h->n_f64 * n * sizeof(double),
+    if (want_f64)
+      PWS_CUDA(h, cudaMemcpyAsync(staged ? h->hs_of[b] : h_out_f64 + (size_t)d0 * h->n_f64 * n,
+                                  h->d_of64[b], (size_t)nd * h->n_f64 * n * sizeof(double),
                                   cudaMemcpyDeviceToHost, h->s_d2h));
-    if (h->n_i32 > 0 && h_out_i32)
-      PWS_CUDA(h, cudaMemcpyAsync(h_out_i32 + (size_t)d0 * h->n_i32 * n, h->d_oi32[b],
-                                  (size_t)nd * h->n_i32 * n * sizeof(int32_t),
+    if (want_i32)
+      PWS_CUDA(h, cudaMemcpyAsync(staged ? h->hs_oi[b] : h_out_i32 + (size_t)d0 * h->n_i32 * n,
+                                  h->d_oi32[b], (size_t)nd * h->n_i32 * n * sizeof(int32_t),
                                   cudaMemcpyDeviceToHost, h->s_d2h));
-    if (h->n_seg_sel > 0 && h->nseg > 0 && h_seg_out)
-      PWS_CUDA(h, cudaMemcpyAsync(h_seg_out + (size_t)d0 * h->n_seg_sel * h->nseg, h->d_oseg[b],
-                                  (size_t)nd * h->n_seg_sel * h->nseg * sizeof(double),
+    if (want_seg)
+      PWS_CUDA(h, cudaMemcpyAsync(staged ? h->hs_os[b] : h_seg_out + (size_t)d0 * h->n_seg_sel * h->nseg,
+                                  h->d_oseg[b], (size_t)nd * h->n_seg_sel * h->nseg * sizeof(double),
                                   cudaMemcpyDeviceToHost, h->s_d2h));
     PWS_CUDA(h, cudaEventRecord(h->ev_d2h[b], h->s_d2h));
     // d_cal / d_viol / channel scratch are single-buffered: the next block's
-    // enqueue reuses them in stream order on s_compute, which is safe; the
-    // host-side cal pointer must stay valid until the copy ran, so sync here
-    // only when the caller's cal block could be reused (it is not: h_cal is
-    // the caller's full-run array).
+    // enqueue reuses them in stream order on s_compute, which is safe; h_cal is
+    // the caller's full-run array and stays valid.
   }
+  if (staged)
+    for (int blk = std::max(0, nblocks - 2); blk < nblocks; ++blk)
+      if (drain_stage(blk)) return 1;
   return pws_sync(h);
 }
 

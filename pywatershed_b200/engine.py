@@ -267,11 +267,14 @@ class Engine:
         return out
 
     # ---- runs
-    def run_host(self, prcp, tmax, tmin, budgets: bool = True):
+    def run_host(self, prcp, tmax, tmin, budgets: bool = True, pinned_outputs: bool = False):
         """Advance len(prcp) days with forcings / outputs in host memory
         (time-blocked, H2D / compute / D2H overlapped).  Returns
         (dict var -> [ndays, n] ndarray with the reference's dtype,
-        budget violation counts [ndays, 6] or None)."""
+        budget violation counts [ndays, 6] or None).  Pageable arrays are
+        staged through pinned buffers inside the library; with
+        `pinned_outputs` the result arrays are allocated page-locked (through
+        torch) so the drain needs no staging copy."""
         prcp = np.ascontiguousarray(prcp, dtype=np.float64)
         tmax = np.ascontiguousarray(tmax, dtype=np.float64)
         tmin = np.ascontiguousarray(tmin, dtype=np.float64)
@@ -279,9 +282,18 @@ class Engine:
         if not (prcp.shape == tmax.shape == tmin.shape == (nd, self.nhru)):
             raise ValueError("forcings must be [ndays, nhru]")
         cal = calendar(self.start + self.day, nd)
-        of = np.empty((nd, len(self.sel_f64), self.nhru))
-        oi = np.empty((nd, len(self.sel_i32), self.nhru), dtype=np.int32)
-        os_ = np.empty((nd, len(self.sel_seg), self.nseg))
+        if pinned_outputs:
+            import torch
+
+            def alloc(shape, dt):
+                return torch.empty(shape, dtype=dt).pin_memory().numpy()
+            of = alloc((nd, len(self.sel_f64), self.nhru), torch.float64)
+            oi = alloc((nd, len(self.sel_i32), self.nhru), torch.int32)
+            os_ = alloc((nd, len(self.sel_seg), self.nseg), torch.float64)
+        else:
+            of = np.empty((nd, len(self.sel_f64), self.nhru))
+            oi = np.empty((nd, len(self.sel_i32), self.nhru), dtype=np.int32)
+            os_ = np.empty((nd, len(self.sel_seg), self.nseg))
         viol = np.zeros((nd, 6), dtype=np.int32) if budgets else None
         self._check(self.L.pws_run_host(
             self.h, nd, cal.ctypes.data, prcp.ctypes.data, tmax.ctypes.data, tmin.ctypes.data,

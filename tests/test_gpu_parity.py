@@ -131,6 +131,27 @@ def test_forcing_staging_paths_agree(drb, tma):
         np.testing.assert_array_equal(of[:, k], got[v], err_msg=v)
 
 
+def test_pinned_and_pageable_host_buffers_agree(drb):
+    """pws_run_host uses pinned caller buffers directly and stages pageable
+    ones (numpy arrays) through its own pinned slots: same bits, any block
+    length (3+ blocks so that both stage slots are reused)."""
+    import torch
+
+    p, f, start = drb
+    nd = 75
+    e = _engine(p, start)
+    e.set_block_days(20)
+    a, va = e.run_host(f["prcp"][:nd], f["tmax"][:nd], f["tmin"][:nd])
+    e2 = _engine(p, start)
+    e2.set_block_days(20)
+    pin = {k: torch.from_numpy(np.ascontiguousarray(f[k][:nd])).pin_memory().numpy()
+           for k in ("prcp", "tmax", "tmin")}
+    b, vb = e2.run_host(pin["prcp"], pin["tmax"], pin["tmin"], pinned_outputs=True)
+    for k in po.HRU_VARS + po.SEG_VARS:
+        np.testing.assert_array_equal(np.asarray(a[k]), np.asarray(b[k]), err_msg=k)
+    np.testing.assert_array_equal(va, vb)
+
+
 def test_time_blocking_is_transparent(drb):
     """Block length must not change a single bit (state round-trips through
     HBM between blocks)."""
