@@ -238,3 +238,36 @@ def test_netcdf_writer_layout(tmp_path):
     units = ds.variables["time"].units
     assert (units.decode() if isinstance(units, bytes) else units) == "days since 1970-01-01 00:00:00"
     ds.close()
+
+
+@pytest.mark.skipif(not pl.Path("/root/reference/pywatershed").exists(), reason="reference absent")
+def test_model_accepts_the_reference_control_and_parameters():
+    """Duck typing: a pywatershed.Control / PrmsParameters
+    pair drives our Model; its clock and option dict are the ones used."""
+    import sys
+
+    sys.path.insert(0, str(pl.Path(__file__).resolve().parent.parent / "oracle"))
+    import ref_harness as rh
+
+    import pywatershed_b200 as pwsb
+
+    pws = rh.import_reference()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        control, params, forcings, times = rh.load_drb(pws)
+    for key in ("netcdf_output_dir", "netcdf_output_var_names"):
+        if key in control.options:
+            del control.options[key]
+    control.options["budget_type"] = "error"
+    if "calc_method" in control.options:
+        del control.options["calc_method"]  # "numpy" / "numba" name the reference's CPU paths
+    m = pwsb.Model([pws.PRMSSolarGeometry, pws.PRMSAtmosphere, pws.PRMSCanopy, pws.PRMSSnow,
+                    pws.PRMSRunoff, pws.PRMSSoilzone, pws.PRMSGroundwater, pws.PRMSChannel],
+                   control=control, parameters=params, find_input_files=False)
+    assert m._mode == "chain+channel" and m.control is control
+    assert m.processes["PRMSSnow"]["pkwater_equiv"].shape == (765,)
+    assert m.processes["PRMSAtmosphere"]["tmaxf"].data.shape == (control.n_times, 765)
+    # reference classes were mapped onto ours by name
+    assert type(m.processes["PRMSRunoff"]).__module__.startswith("pywatershed_b200")
+    np.testing.assert_array_equal(m._param_dict["hru_area"], params.parameters["hru_area"])
+    assert m._param_dict["tmax_cbh_adj"].shape == (12, 765)
