@@ -142,6 +142,7 @@ struct pws_handle {
   size_t ring_f64_elems = 0, ring_i32_elems = 0, ring_seg_elems = 0;
   // pinned staging for pageable caller buffers (pws_run_host)
   int stage_days = 0;
+  size_t stage_f64_elems = 0, stage_i32_elems = 0, stage_seg_elems = 0;
   double* hs_in[2] = {nullptr, nullptr};
   double* hs_of[2] = {nullptr, nullptr};
   int32_t* hs_oi[2] = {nullptr, nullptr};
@@ -255,6 +256,7 @@ static void free_stage(pws_handle* h) {
     cudaFreeHost(h->hs_viol[b]); h->hs_viol[b] = nullptr;
   }
   h->stage_days = 0;
+  h->stage_f64_elems = h->stage_i32_elems = h->stage_seg_elems = 0;
 }
 
 static void free_ring(pws_handle* h) {
@@ -266,6 +268,7 @@ static void free_ring(pws_handle* h) {
     cudaFree(h->d_oseg[b]); h->d_oseg[b] = nullptr;
   }
   h->ring_days = 0;
+  h->ring_f64_elems = h->ring_i32_elems = h->ring_seg_elems = 0;
 }
 
 static void free_scratch(pws_handle* h) {
@@ -857,9 +860,8 @@ extern "C" int pws_select_outputs(pws_handle* h, int n_hru, const int32_t* hru_i
   h->n_f64 = nf;
   h->n_i32 = ni;
   h->n_seg_sel = ns;
-  cudaSetDevice(h->device);
-  cudaDeviceSynchronize();
-  free_ring(h);
+  // the rings of pws_run_host are kept: they are re-allocated only when a run
+  // needs more room than they have
   return 0;
 }
 
@@ -1136,19 +1138,26 @@ extern "C" int pws_run_host(pws_handle* h, int ndays, const int32_t* h_cal, cons
     T = (int)std::max(1.0, std::min(366.0, 2.0e9 / bytes_per_day));
   }
   T = std::min(T, ndays);
-  if (T > h->ring_days) {
+  const size_t need_f64 = (size_t)T * std::max(h->n_f64, 1) * n;
+  const size_t need_i32 = (size_t)T * std::max(h->n_i32, 1) * n;
+  const size_t need_seg = (size_t)T * std::max(h->n_seg_sel, 1) * std::max<int64_t>(h->nseg, 1);
+  if (T > h->ring_days || need_f64 > h->ring_f64_elems || need_i32 > h->ring_i32_elems ||
+      need_seg > h->ring_seg_elems) {
     cudaDeviceSynchronize();
+    const int days = std::max(T, h->ring_days);
+    const size_t cf = std::max(need_f64, h->ring_f64_elems), ci = std::max(need_i32, h->ring_i32_elems),
+                 cs = std::max(need_seg, h->ring_seg_elems);
     free_ring(h);
-    h->ring_f64_elems = (size_t)T * std::max(h->n_f64, 1) * n;
-    h->ring_i32_elems = (size_t)T * std::max(h->n_i32, 1) * n;
-    h->ring_seg_elems = (size_t)T * std::max(h->n_seg_sel, 1) * std::max<int64_t>(h->nseg, 1);
+    h->ring_f64_elems = cf;
+    h->ring_i32_elems = ci;
+    h->ring_seg_elems = cs;
     for (int b = 0; b < 2; ++b) {
-      PWS_CUDA(h, cudaMalloc(&h->d_forc[b], (size_t)T * 3 * h->stride * sizeof(double)));
+      PWS_CUDA(h, cudaMalloc(&h->d_forc[b], (size_t)days * 3 * h->stride * sizeof(double)));
       PWS_CUDA(h, cudaMalloc(&h->d_of64[b], h->ring_f64_elems * sizeof(double)));
       PWS_CUDA(h, cudaMalloc(&h->d_oi32[b], h->ring_i32_elems * sizeof(int32_t)));
       PWS_CUDA(h, cudaMalloc(&h->d_oseg[b], h->ring_seg_elems * sizeof(double)));
     }
-    h->ring_days = T;
+    h->ring_days = days;
   }
   if (ensure_scratch(h, T)) return 1;
   const bool want_f64 = h->n_f64 > 0 && h_out_f64, want_i32 = h->n_i32 > 0 && h_out_i32;
@@ -1157,7 +1166,8 @@ extern "C" int pws_run_host(pws_handle* h, int ndays, const int32_t* h_cal, cons
                         is_pinned(want_f64 ? h_out_f64 : nullptr) &&
                         is_pinned(want_i32 ? h_out_i32 : nullptr) &&
                         is_pinned(want_seg ? h_seg_out : nullptr));
-  if (staged && h->stage_days < h->ring_days) {
+  if (staged && (h->stage_days < h->ring_days || h->stage_f64_elems < h->ring_f64_elems ||
+                 h->stage_i32_elems < h->ring_i32_elems || h->stage_seg_elems < h->ring_seg_elems)) {
     free_stage(h);
     for (int b = 0; b < 2; ++b) {
       PWS_CUDA(h, cudaHostAlloc(&h->hs_in[b], (size_t)h->ring_days * 3 * n * sizeof(double), 0));
@@ -1167,6 +1177,9 @@ extern "C" int pws_run_host(pws_handle* h, int ndays, const int32_t* h_cal, cons
       PWS_CUDA(h, cudaHostAlloc(&h->hs_viol[b], (size_t)h->ring_days * BUD_N * sizeof(int32_t), 0));
     }
     h->stage_days = h->ring_days;
+    h->stage_f64_elems = h->ring_f64_elems;
+    h->stage_i32_elems = h->ring_i32_elems;
+    h->stage_seg_elems = h->ring_seg_elems;
   }
   const int RT = h->ring_days;  // row capacity of the ring / stage slots
   const int nblocks = (ndays + T - 1) / T;

@@ -267,14 +267,18 @@ class Engine:
         return out
 
     # ---- runs
-    def run_host(self, prcp, tmax, tmin, budgets: bool = True, pinned_outputs: bool = False):
+    def run_host(self, prcp, tmax, tmin, budgets: bool = True, pinned_outputs: bool = False,
+                 reuse_buffers: bool = False):
         """Advance len(prcp) days with forcings / outputs in host memory
         (time-blocked, H2D / compute / D2H overlapped).  Returns
         (dict var -> [ndays, n] ndarray with the reference's dtype,
         budget violation counts [ndays, 6] or None).  Pageable arrays are
         staged through pinned buffers inside the library; with
         `pinned_outputs` the result arrays are allocated page-locked (through
-        torch) so the drain needs no staging copy."""
+        torch) so the drain needs no staging copy; with `reuse_buffers` the
+        result arrays of the previous call with the same shapes are written
+        again (the caller must be done with them), which avoids first-touch
+        page faults on every block of a long run."""
         prcp = np.ascontiguousarray(prcp, dtype=np.float64)
         tmax = np.ascontiguousarray(tmax, dtype=np.float64)
         tmin = np.ascontiguousarray(tmin, dtype=np.float64)
@@ -291,9 +295,16 @@ class Engine:
             oi = alloc((nd, len(self.sel_i32), self.nhru), torch.int32)
             os_ = alloc((nd, len(self.sel_seg), self.nseg), torch.float64)
         else:
-            of = np.empty((nd, len(self.sel_f64), self.nhru))
-            oi = np.empty((nd, len(self.sel_i32), self.nhru), dtype=np.int32)
-            os_ = np.empty((nd, len(self.sel_seg), self.nseg))
+            shapes = ((nd, len(self.sel_f64), self.nhru), (nd, len(self.sel_i32), self.nhru),
+                      (nd, len(self.sel_seg), self.nseg))
+            cache = getattr(self, "_out_cache", None)
+            if reuse_buffers and cache is not None and cache[0] == shapes:
+                of, oi, os_ = cache[1]
+            else:
+                of = np.empty(shapes[0])
+                oi = np.empty(shapes[1], dtype=np.int32)
+                os_ = np.empty(shapes[2])
+                self._out_cache = (shapes, (of, oi, os_)) if reuse_buffers else None
         viol = np.zeros((nd, 6), dtype=np.int32) if budgets else None
         self._check(self.L.pws_run_host(
             self.h, nd, cal.ctypes.data, prcp.ctypes.data, tmax.ctypes.data, tmin.ctypes.data,

@@ -75,7 +75,9 @@ class Model:
         # True when a single process is stepped by its caller, who advances
         # the Control (autotest/test_prms_snow.py:122-132)
         self._control_is_external = False
-        self.block_days = int(self.control.options.get("block_days", 64) or 64)
+        # days per host-side block (what one engine call brings back); None = sized
+        # from the domain when the engine exists (about 2 GB of results, <= 366 days)
+        self.block_days = self.control.options.get("block_days") or None
         if write_control:
             self._write_control(write_control)
 
@@ -164,7 +166,9 @@ class Model:
         self._block_viol = None
         self._calculated_step = -1
         self._control_is_external = True
-        self.block_days = int(self.control.options.get("block_days", 64) or 64)
+        # days per host-side block (what one engine call brings back); None = sized
+        # from the domain when the engine exists (about 2 GB of results, <= 366 days)
+        self.block_days = self.control.options.get("block_days") or None
         return self
 
     @classmethod
@@ -261,6 +265,12 @@ class Model:
                 mine.update(proc.get_variables())
             hv = [v for v in reg.hru_vars if v in mine]
             sv = sv if "PRMSChannel" in self.processes else []
+        self._full_selection = (list(hv), list(sv))
+        self._selection_is_full = True
+        if self.block_days is None:
+            per_day = 8.0 * (len(hv) * self._engine.nhru + len(sv) * self._engine.nseg) + 1.0
+            self.block_days = int(max(8, min(366, 2.0e9 / per_day)))
+        self.block_days = int(self.block_days)
         if self._mode != "channel":
             self._engine.select_outputs(hv, sv)
             if "PRMSSolarGeometry" in self.processes:
@@ -272,27 +282,57 @@ class Model:
             self._engine.select_outputs([], sv)
 
     # ---------------------------------------------------------------- blocks
-    def _compute_block(self, t0, n):
+    def _reduced_selection(self):
+        """What run() has to bring back for a block nobody looks into: the
+        all-time Atmosphere variables, the budget terms (accumulations) and
+        whatever goes to netCDF.  Everything else is only observable for the
+        last day of a run, i.e. in its last block."""
+        hv_full, sv = self._full_selection
+        want = set()
+        if "PRMSAtmosphere" in self.processes:
+            want.update(self.processes["PRMSAtmosphere"].get_variables())
+        for proc in self.processes.values():
+            b = getattr(proc, "budget", None)
+            if b is not None:
+                for comp in b.components:
+                    want.update(b.terms[comp])
+        if self._netcdf is not None:
+            for _, _, f in self._netcdf.files:
+                want.update(f.vars)
+        return [v for v in hv_full if v in want], sv
+
+    def _select(self, full: bool):
+        if self._mode == "channel" or full == self._selection_is_full:
+            return
+        hv, sv = self._full_selection if full else self._reduced_selection()
+        self._engine.select_outputs(hv, sv)
+        self._selection_is_full = full
+
+    def _compute_block(self, t0, n, reduced: bool = False):
         self._ensure_engine()
         eng = self._engine
         if eng.day != t0:
             raise RuntimeError(f"engine is at day {eng.day}, block starts at {t0}")
+        self._select(full=not reduced)
         if self._mode == "channel":
             blk, viol = self._channel_block(t0, n)
         elif self._mode == "sub":
-            eng.set_block_days(min(n, 64))
+            eng.set_block_days(min(n, 16))
             blk, viol = eng.run_host_inputs({k: v[t0:t0 + n] for k, v in self._forcings.items()},
                                             [P.base_name(x) for x in self.process_order], ndays=n)
         else:
-            eng.set_block_days(min(n, 64))
+            eng.set_block_days(min(n, 16))
             f = self._forcings
-            blk, viol = eng.run_host(f["prcp"][t0:t0 + n], f["tmax"][t0:t0 + n], f["tmin"][t0:t0 + n])
+            # the block's arrays are consumed before the next block is computed
+            blk, viol = eng.run_host(f["prcp"][t0:t0 + n], f["tmax"][t0:t0 + n], f["tmin"][t0:t0 + n],
+                                     reuse_buffers=True)
         self._block, self._block_t0, self._block_n, self._block_viol = blk, t0, n, viol
         # all-time variables of Atmosphere: fill the rows of this block
         if "PRMSAtmosphere" in self.processes:
             atm = self.processes["PRMSAtmosphere"]
             for var in atm.get_variables():
-                atm[var].data[t0:t0 + n] = blk[var]
+                if var in blk:
+                    atm[var].data[t0:t0 + n] = blk[var]
         dt = float(self.control.time_step / np.timedelta64(1, "D"))
         for name, proc in self.processes.items():
             if getattr(proc, "budget", None) is not None:
@@ -337,14 +377,16 @@ class Model:
                 for var in proc.get_variables():
                     proc[var].advance()
 
-    def _ensure_block(self, it, limit=None):
+    def _ensure_block(self, it, limit=None, reduced_unless_last=False):
         if self._block is not None and self._block_t0 <= it < self._block_t0 + self._block_n:
             return
+        self._ensure_engine()
         remaining = self.control.n_times - it
         n = min(self.block_days, remaining)
         if limit is not None:
             n = min(n, limit)
-        self._compute_block(it, n)
+        last = n == (remaining if limit is None else min(remaining, limit))
+        self._compute_block(it, n, reduced=reduced_unless_last and not last)
 
     def calculate(self):
         """base/model.py:739-743: after this call every process shows day itime_step."""
@@ -425,7 +467,8 @@ class Model:
         done = 0
         while done < n_time_steps:
             it = self.control.itime_step + 1
-            self._ensure_block(it, limit=n_time_steps - done)
+            # only the last block of a run is observable variable by variable
+            self._ensure_block(it, limit=n_time_steps - done, reduced_unless_last=True)
             t1 = min(self._block_t0 + self._block_n, it + (n_time_steps - done))
             nd = t1 - it
             # budgets for the whole block: any violating day raises / warns as the
