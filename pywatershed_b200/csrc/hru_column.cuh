@@ -1246,8 +1246,8 @@ PWS_DEV void column_upper(const HruParams& P, const int64_t i, HruState& s,
 }
 
 // ---- lower half: PRMSRunoff, PRMSSoilzone, PRMSGroundwater, lateral inflow
-template <class Sink>
-PWS_DEV void column_lower(const HruParams& P, const int64_t i, HruState& s,
+template <class State, class Sink>
+PWS_DEV void column_lower(const HruParams& P, const int64_t i, State& s,
                           const ColumnMid& mid, Sink& out) {
   const int hru_type = PWS_LD(P.hru_type + i);
   const int cov_type = PWS_LD(P.cov_type + i);

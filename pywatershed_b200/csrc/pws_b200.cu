@@ -689,10 +689,12 @@ extern "C" int pws_init(pws_handle* h) {
   const int64_t S = h->stride, n = h->nhru;
   const size_t rows_f64 = t.hru_f64.size() + 12 * t.mon_f64.size() + t.derived.size() + 12;
   const size_t rows_i32 = t.hru_i32.size() + 12 * t.mon_i32.size();
-  PWS_CUDA(h, cudaMalloc(&h->d_f64, rows_f64 * S * sizeof(double)));
-  PWS_CUDA(h, cudaMemset(h->d_f64, 0, rows_f64 * S * sizeof(double)));
-  PWS_CUDA(h, cudaMalloc(&h->d_i32, rows_i32 * S * sizeof(int32_t)));
-  PWS_CUDA(h, cudaMemset(h->d_i32, 0, rows_i32 * S * sizeof(int32_t)));
+  // + one CTA's worth of slack: lanes past the last HRU of the last CTA may read behind a row
+  const size_t slack = 2 * PWS_COLUMN_HRUS;
+  PWS_CUDA(h, cudaMalloc(&h->d_f64, (rows_f64 * S + slack) * sizeof(double)));
+  PWS_CUDA(h, cudaMemset(h->d_f64, 0, (rows_f64 * S + slack) * sizeof(double)));
+  PWS_CUDA(h, cudaMalloc(&h->d_i32, (rows_i32 * S + slack) * sizeof(int32_t)));
+  PWS_CUDA(h, cudaMemset(h->d_i32, 0, (rows_i32 * S + slack) * sizeof(int32_t)));
   PWS_CUDA(h, cudaMalloc(&h->d_state, (size_t)PWS_N_HRU_STATE * S * sizeof(double)));
   PWS_CUDA(h, cudaMemset(h->d_state, 0, (size_t)PWS_N_HRU_STATE * S * sizeof(double)));
   for (auto& p : h->d_soltab) PWS_CUDA(h, cudaMalloc(&p, (size_t)kNdoy * S * sizeof(double)));

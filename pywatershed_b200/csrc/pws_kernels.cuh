@@ -28,6 +28,19 @@
 #define PWS_COLUMN_SYNC 0
 #endif
 
+// 1: the upper half's monthly parameters are staged in shared memory once per
+// month; 0: read from global memory (L2) each day, which frees 35 KB that can
+// hold the lower half's prognostic state (next knob).  Measured on the CONUS
+// domain (ms per 10-year pass, default 118): monthly from L2 124; + lower state
+// in shared memory 125 (136/120 registers), 122 (144/112), 132 (128/128).
+#ifndef PWS_COLUMN_MONTHLY_SMEM
+#define PWS_COLUMN_MONTHLY_SMEM 1
+#endif
+// 1: the lower half keeps its 10 prognostic values in shared memory instead of
+// registers (it is the critical path of the pipeline and spills otherwise)
+#ifndef PWS_COLUMN_LOWER_STATE_SMEM
+#define PWS_COLUMN_LOWER_STATE_SMEM 0
+#endif
 // Registers per thread of the two warp groups (setmaxnreg, multiples of 8;
 // with 256 HRUs per CTA, upper + lower must be <= 256).  Unconstrained, the
 // upper half wants 204 registers (29 prognostic values, the snow energy
@@ -216,7 +229,15 @@ constexpr int kMidF64 = 10, kMidI32 = 2;  // ColumnMid
 #define PWS_COLUMN_MID_SLOTS 1  // days the upper half may run ahead of the lower half (2: no gain)
 #endif
 constexpr int kMidSlots = PWS_COLUMN_MID_SLOTS;
-constexpr int kColF64 = kUpperF64 + kUpperMonF64 + kLowerF64 + kMidSlots * kMidF64;
+constexpr int kLowerState = 0
+#define X(name, kind) +1
+    PWS_HRU_STATE_LOWER(X)
+#undef X
+    ;
+constexpr int kUpperMonStaged = PWS_COLUMN_MONTHLY_SMEM ? kUpperMonF64 : 0;
+constexpr int kLowerStateStaged = PWS_COLUMN_LOWER_STATE_SMEM ? kLowerState : 0;
+constexpr int kColF64 =
+    kUpperF64 + kUpperMonStaged + kLowerF64 + kMidSlots * kMidF64 + kLowerStateStaged;
 constexpr int kColI32 = kUpperI32 + kLowerI32 + kMidSlots * kMidI32;
 // forcing stage of the upper half: 2 days x {prcp, tmax, tmin, soltab_potsw row,
 // soltab_horad_potsw row} x H, filled by TMA bulk copies, + 2 mbarriers
@@ -267,6 +288,13 @@ __device__ __forceinline__ void bar_arrive(int id, int count) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
+// The lower half's prognostic state as references (into shared memory)
+struct LowerStateRef {
+#define X(name, kind) double& name;
+  PWS_HRU_STATE_LOWER(X)
+#undef X
+};
+
 // The fused column.  A CTA owns H = PWS_COLUMN_HRUS HRUs and has 2 H threads:
 // warps [0, H/32) run the UPPER half of the column (atmosphere, canopy, snow)
 // and warps [H/32, 2H/32) the LOWER half (runoff, soilzone, groundwater) of
@@ -296,9 +324,10 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
   // shared memory: one private column per thread and staged quantity
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* const spU = reinterpret_cast<double*>(smem_raw);           // upper f64 (+ monthly)
-  double* const spL = spU + (size_t)(kUpperF64 + kUpperMonF64) * H;  // lower f64
-  double* const spM = spL + (size_t)kLowerF64 * H;                   // ColumnMid f64
-  int32_t* const siU = reinterpret_cast<int32_t*>(spM + (size_t)kMidSlots * kMidF64 * H);
+  double* const spL = spU + (size_t)(kUpperF64 + kUpperMonStaged) * H;  // lower f64
+  double* const spM = spL + (size_t)kLowerF64 * H;                      // ColumnMid f64
+  double* const spS = spM + (size_t)kMidSlots * kMidF64 * H;            // lower state
+  int32_t* const siU = reinterpret_cast<int32_t*>(spS + (size_t)kLowerStateStaged * H);
   int32_t* const siL = siU + (size_t)kUpperI32 * H;
   int32_t* const siM = siL + (size_t)kLowerI32 * H;
   double* const sF = reinterpret_cast<double*>(smem_raw + kColumnParamBytes);  // [2][kForcRows][H]
@@ -339,17 +368,30 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
 #define X(n) spU[k * H + r] = __ldg(a.P.n + ii); Q.n = spU + k * H; ++k;
       PWS_UPPER_F64(X)
 #undef X
+#if PWS_COLUMN_MONTHLY_SMEM
 #define X(n) Q.n = spU + k * H; ++k;
       PWS_UPPER_MON_F64(X)
 #undef X
+#else
+      // monthly rows straight from global memory: row (month - 1) * S, element
+      // hru0 + r (the slabs are padded so lanes past the last HRU stay inside)
+      Q.stride = S;
+#define X(n) Q.n = a.P.n + (int64_t)blockIdx.x * H;
+      PWS_UPPER_MON_F64(X)
+      PWS_UPPER_MON_I32(X)
+#undef X
+#endif
       k = 0;
 #define X(n) siU[k * H + r] = __ldg(a.P.n + ii); Q.n = siU + k * H; ++k;
       PWS_UPPER_I32(X)
 #undef X
+#if PWS_COLUMN_MONTHLY_SMEM
 #define X(n) Q.n = siU + k * H; ++k;
       PWS_UPPER_MON_I32(X)
 #undef X
+#endif
     }
+#if PWS_COLUMN_MONTHLY_SMEM
     auto stage_month = [&](int month) {
       const int64_t mo = (int64_t)(month - 1) * S + ii;
       int k = kUpperF64;
@@ -362,6 +404,7 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
 #undef X
     };
     int staged_month = 0;
+#endif
     // Forcings of day d+1 are in flight while day d computes.  When the rows
     // are 16-byte aligned (a.use_tma) one thread streams the five rows of the
     // CTA's HRUs into shared memory with TMA bulk copies that complete on an
@@ -435,10 +478,12 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
           nxt.horad = __ldg(a.P.soltab_horad_potsw + (int64_t)(c.x - 1) * S + ii);
         }
       }
+#if PWS_COLUMN_MONTHLY_SMEM
       if (in.month != staged_month) {  // warp-uniform
         stage_month(in.month);
         staged_month = in.month;
       }
+#endif
       out.violmask = 0u;
       ColumnMid mid;
       column_upper(Q, (int64_t)r, s, in, out, mid);
@@ -477,9 +522,23 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
 #elif PWS_COLUMN_REGS_UPPER > PWS_COLUMN_REGS_LOWER
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PWS_COLUMN_REGS_LOWER));
 #endif
+#if PWS_COLUMN_LOWER_STATE_SMEM
+    // the lower half's state lives in this thread's shared-memory column
+    int ks = 0;
+#define X(name, kind) double& sm_##name = spS[(ks++) * H + r]; sm_##name = a.state[(int64_t)ST_##name * S + ii];
+    PWS_HRU_STATE_LOWER(X)
+#undef X
+    LowerStateRef sl{
+#define X(name, kind) sm_##name,
+        PWS_HRU_STATE_LOWER(X)
+#undef X
+    };
+#else
 #define X(name, kind) PWS_LOADST_##kind(name)
     PWS_HRU_STATE_LOWER(X)
 #undef X
+    HruState& sl = s;
+#endif
     {
       int k = 0;
 #define X(n) spL[k * H + r] = __ldg(a.P.n + ii); Q.n = spL + k * H; ++k;
@@ -511,13 +570,13 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
       if (d + kMidSlots < a.ndays) bar_arrive(BAR_MID_EMPTY + slot, 2 * H);
       out.violmask = 0u;
       out.plat = a.hru_lat ? a.hru_lat + (int64_t)d * S + ii : nullptr;
-      column_lower(Q, (int64_t)r, s, mid, out);
+      column_lower(Q, (int64_t)r, sl, mid, out);
       out.pf += day_f64;
       out.pi += day_i32;
       reduce_violations(d);
     }
     if (live) {
-#define X(name, kind) PWS_STOREST(name)
+#define X(name, kind) a.state[(int64_t)ST_##name * S + i] = (double)sl.name;
       PWS_HRU_STATE_LOWER(X)
 #undef X
     }
