@@ -86,6 +86,58 @@ class Parameters:
             meta.update(dict(getattr(p, "metadata", {})))
         return Parameters(dims=dims, coords=coords, data_vars=data, metadata=meta)
 
+    # ---- netCDF round trip (base/data_model.py:354-420).  netCDF4 when it is
+    # importable (HDF5 files, what pywatershed writes), else scipy's classic reader.
+    @classmethod
+    def from_netcdf(cls, nc_file, *args, **kwargs):
+        from .netcdf_out import nc4_module
+
+        nc4 = nc4_module()
+        dims, coords, data, meta = {}, {}, {}, {}
+        if nc4 is not None:
+            with nc4.Dataset(nc_file) as ds:
+                dims = {k: len(v) for k, v in ds.dimensions.items()}
+                for name, var in ds.variables.items():
+                    arr = np.asarray(var[:])
+                    meta[name] = {"dims": tuple(var.dimensions)}
+                    (coords if name in ("nhm_id", "nhm_seg", "doy") or name in dims else data)[name] = arr
+        else:
+            from scipy.io import netcdf_file
+
+            with netcdf_file(str(nc_file), "r", mmap=False) as ds:
+                dims = {k: (v if v is not None else 0) for k, v in ds.dimensions.items()}
+                for name, var in ds.variables.items():
+                    arr = np.array(var[:])
+                    meta[name] = {"dims": tuple(var.dimensions)}
+                    (coords if name in ("nhm_id", "nhm_seg", "doy") or name in dims else data)[name] = arr
+        return cls(dims=dims, coords=coords, data_vars=data, metadata=meta)
+
+    def to_netcdf(self, filename, use_xr=False) -> None:
+        from .netcdf_out import nc4_module
+
+        nc4 = nc4_module()
+        meta = self._metadata
+        if nc4 is not None:
+            ds = nc4.Dataset(filename, "w", format="NETCDF4")
+        else:
+            from scipy.io import netcdf_file
+
+            ds = netcdf_file(str(filename), "w", version=2)
+        try:
+            for k, n in self._dims.items():
+                ds.createDimension(k, int(n))
+            for name, arr in {**self._coords, **self._data}.items():
+                arr = np.asarray(arr)
+                dnames = tuple((meta.get(name) or {}).get("dims") or ())
+                if len(dnames) != arr.ndim:  # fall back on matching lengths
+                    dnames = tuple(next(k for k, n in self._dims.items() if n == m) for m in arr.shape)
+                if arr.dtype == np.int64:
+                    arr = arr.astype(np.int32)
+                v = ds.createVariable(name, arr.dtype.str[1:], dnames)
+                v[:] = arr
+        finally:
+            ds.close()
+
     def to_dict(self) -> dict:
         """Plain dict name -> ndarray incl. coordinates (what Engine takes)."""
         out = {k: np.asarray(v) for k, v in self._data.items()}

@@ -271,3 +271,27 @@ def test_model_accepts_the_reference_control_and_parameters():
     assert type(m.processes["PRMSRunoff"]).__module__.startswith("pywatershed_b200")
     np.testing.assert_array_equal(m._param_dict["hru_area"], params.parameters["hru_area"])
     assert m._param_dict["tmax_cbh_adj"].shape == (12, 765)
+
+
+def test_parameters_netcdf_round_trip(drb, tmp_path):
+    """Parameters.to_netcdf / from_netcdf (base/data_model.py:354-420)."""
+    import pywatershed_b200 as pwsb
+
+    p, f, start = drb
+    keep = ("hru_area", "tmax_cbh_adj", "cov_type", "tosegment", "seg_length", "snarea_curve")
+    params = pwsb.Parameters(
+        dims={"nhru": 765, "nsegment": 456, "nmonth": 12, "ndeplval": 55},
+        coords={"nhm_id": p["nhm_id"], "nhm_seg": p["nhm_seg"]},
+        data_vars={k: p[k] for k in keep},
+        metadata={"hru_area": {"dims": ("nhru",)}, "tmax_cbh_adj": {"dims": ("nmonth", "nhru")},
+                  "cov_type": {"dims": ("nhru",)}, "tosegment": {"dims": ("nsegment",)},
+                  "seg_length": {"dims": ("nsegment",)}, "snarea_curve": {"dims": ("ndeplval",)},
+                  "nhm_id": {"dims": ("nhru",)}, "nhm_seg": {"dims": ("nsegment",)}})
+    params.to_netcdf(tmp_path / "params.nc")
+    back = pwsb.Parameters.from_netcdf(tmp_path / "params.nc")
+    assert back.dims["nhru"] == 765 and back.dims["nmonth"] == 12
+    for k in keep:
+        np.testing.assert_array_equal(back.parameters[k], p[k], err_msg=k)
+    np.testing.assert_array_equal(back.coords["nhm_id"], p["nhm_id"])
+    sub = back.subset(["hru_area", "cov_type"])
+    assert set(sub.parameters) == {"hru_area", "cov_type"}
