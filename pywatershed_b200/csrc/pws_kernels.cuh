@@ -1,8 +1,13 @@
 // pws_kernels.cuh -- the CUDA kernels of libpwsb200 (sm_100a, fp64):
 //   k_soltab        PRMSSolarGeometry tables, once per run
 //   k_hru_init      derived parameters + initial conditions, once per run
-//   k_hru_column    the fused atmosphere..groundwater column, 1 thread / HRU,
-//                   state in registers across a block of days
+//   k_hru_column    the fused atmosphere..groundwater column over a block of
+//                   days: two warp groups per CTA (upper / lower half of the
+//                   column, one thread per HRU each) as a producer/consumer
+//                   pipeline, state in registers, parameters in per-thread
+//                   shared-memory columns, forcings staged by TMA bulk copies
+//   k_hru_column_ov one thread per HRU, any subset of the processes, the rest
+//                   replaced by caller-supplied inputs (compatibility path)
 //   k_route_chunks  Muskingum-Mann routing: one CTA per chunk of connected
 //                   segments, systolic hour-by-hour schedule over a block of
 //                   days, hand-over through double-buffered shared memory
