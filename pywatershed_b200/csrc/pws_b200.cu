@@ -148,6 +148,8 @@ struct pws_handle {
   int32_t* hs_oi[2] = {nullptr, nullptr};
   double* hs_os[2] = {nullptr, nullptr};
   int32_t* hs_viol[2] = {nullptr, nullptr};
+  int32_t* hs_viol_run = nullptr;  // pinned, whole run: the verdicts never block the pipeline
+  size_t hs_viol_run_cap = 0;
   // streams / events
   cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_col0 = nullptr, ev_col1 = nullptr, ev_ch1 = nullptr;
@@ -306,6 +308,7 @@ extern "C" int pws_destroy(pws_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
+  cudaFreeHost(h->hs_viol_run);
   free_device(h);
   clear_timing(h);
   cudaEventDestroy(h->ev_col0); cudaEventDestroy(h->ev_col1); cudaEventDestroy(h->ev_ch1);
@@ -1176,12 +1179,20 @@ extern "C" int pws_run_host(pws_handle* h, int ndays, const int32_t* h_cal, cons
       PWS_CUDA(h, cudaHostAlloc(&h->hs_of[b], h->ring_f64_elems * sizeof(double), 0));
       PWS_CUDA(h, cudaHostAlloc(&h->hs_oi[b], h->ring_i32_elems * sizeof(int32_t), 0));
       PWS_CUDA(h, cudaHostAlloc(&h->hs_os[b], h->ring_seg_elems * sizeof(double), 0));
-      PWS_CUDA(h, cudaHostAlloc(&h->hs_viol[b], (size_t)h->ring_days * BUD_N * sizeof(int32_t), 0));
     }
     h->stage_days = h->ring_days;
     h->stage_f64_elems = h->ring_f64_elems;
     h->stage_i32_elems = h->ring_i32_elems;
     h->stage_seg_elems = h->ring_seg_elems;
+  }
+  // budget verdicts: always through a pinned buffer (a pageable destination
+  // would make the copy, and with it the whole enqueue loop, synchronous)
+  if (h_budget_viol && h->hs_viol_run_cap < (size_t)ndays * BUD_N) {
+    cudaFreeHost(h->hs_viol_run);
+    h->hs_viol_run = nullptr;
+    h->hs_viol_run_cap = 0;
+    PWS_CUDA(h, cudaHostAlloc(&h->hs_viol_run, (size_t)ndays * BUD_N * sizeof(int32_t), 0));
+    h->hs_viol_run_cap = (size_t)ndays * BUD_N;
   }
   const int RT = h->ring_days;  // row capacity of the ring / stage slots
   const int nblocks = (ndays + T - 1) / T;
@@ -1198,8 +1209,6 @@ extern "C" int pws_run_host(pws_handle* h, int ndays, const int32_t* h_cal, cons
     if (want_seg)
       par_memcpy(h_seg_out + (size_t)d0 * h->n_seg_sel * h->nseg, h->hs_os[b],
                  (size_t)nd * h->n_seg_sel * h->nseg * sizeof(double));
-    if (h_budget_viol)
-      memcpy(h_budget_viol + (size_t)d0 * BUD_N, h->hs_viol[b], (size_t)nd * BUD_N * sizeof(int32_t));
     return 0;
   };
   for (int blk = 0; blk < nblocks; ++blk) {
@@ -1231,9 +1240,9 @@ extern "C" int pws_run_host(pws_handle* h, int ndays, const int32_t* h_cal, cons
                       h->stride, h->d_of64[b], h->d_oi32[b], h->d_oseg[b], h_budget_viol != nullptr))
       return 1;
     if (h_budget_viol)
-      PWS_CUDA(h, cudaMemcpyAsync(staged ? h->hs_viol[b] : h_budget_viol + (size_t)d0 * BUD_N,
-                                  h->d_viol, (size_t)nd * BUD_N * sizeof(int),
-                                  cudaMemcpyDeviceToHost, h->s_compute));
+      PWS_CUDA(h, cudaMemcpyAsync(h->hs_viol_run + (size_t)d0 * BUD_N, h->d_viol,
+                                  (size_t)nd * BUD_N * sizeof(int), cudaMemcpyDeviceToHost,
+                                  h->s_compute));
     PWS_CUDA(h, cudaEventRecord(h->ev_comp[b], h->s_compute));
     PWS_CUDA(h, cudaStreamWaitEvent(h->s_d2h, h->ev_comp[b], 0));
     if (want_f64)
@@ -1256,7 +1265,10 @@ extern "C" int pws_run_host(pws_handle* h, int ndays, const int32_t* h_cal, cons
   if (staged)
     for (int blk = std::max(0, nblocks - 2); blk < nblocks; ++blk)
       if (drain_stage(blk)) return 1;
-  return pws_sync(h);
+  const int rc = pws_sync(h);
+  if (h_budget_viol)
+    memcpy(h_budget_viol, h->hs_viol_run, (size_t)ndays * BUD_N * sizeof(int32_t));
+  return rc;
 }
 
 // --------------------------------------------------------------- sub-chains
