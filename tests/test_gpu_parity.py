@@ -69,6 +69,24 @@ def test_soltab(drb):
         np.testing.assert_allclose(st[k][:, g["hru_sample"]], g[k], rtol=1e-9, atol=1e-10)
 
 
+def test_soltab_on_the_device(drb):
+    """Option soltab_device: the PRMSSolarGeometry tables from k_soltab (CUDA's
+    sin / cos / acos, 1-2 ulp from the host libm) instead of the host threads."""
+    p, f, start = drb
+    e = _engine(p, start)
+    e._opt("soltab_device", 1)
+    e._check(e.L.pws_init(e.h))
+    st = e.soltab()
+    ref = po.Oracle(p, start=start).soltabs()
+    for k in st:
+        np.testing.assert_allclose(st[k], ref[k], rtol=1e-9, atol=1e-9, err_msg=k)
+    e.select_outputs(["swrad", "potet"], [])
+    got, _ = e.run_host(f["prcp"][:30], f["tmax"][:30], f["tmin"][:30])
+    r, _ = po.Oracle(p, start=start).run(f["prcp"][:30], f["tmax"][:30], f["tmin"][:30], ["swrad", "potet"], ())
+    for k in ("swrad", "potet"):
+        np.testing.assert_allclose(got[k], r[k], rtol=1e-9, atol=1e-9, err_msg=k)
+
+
 @pytest.mark.parametrize("scen", ["drb", "drbx"])
 def test_full_chain_parity(scen, drb, drbx):
     p, f, start = drb if scen == "drb" else drbx
