@@ -295,3 +295,39 @@ def test_parameters_netcdf_round_trip(drb, tmp_path):
     np.testing.assert_array_equal(back.coords["nhm_id"], p["nhm_id"])
     sub = back.subset(["hru_area", "cov_type"])
     assert set(sub.parameters) == {"hru_area", "cov_type"}
+
+
+def test_model_dict_construction(drb):
+    """The model_dict style of base/model.py:56-120: a Control, named
+    discretizations, one entry per process with its class, parameters and
+    discretization, and a model_order."""
+    import pywatershed_b200 as pwsb
+
+    p, f, start = drb
+    seg_keys = ("tosegment", "tosegment_nhm", "seg_length", "seg_slope", "seg_depth", "mann_n", "x_coef",
+                "segment_type", "segment_flow_init", "nhm_seg")
+    dis_hru = pwsb.Parameters(dims={"nhru": 765}, coords={"nhm_id": p["nhm_id"]},
+                              data_vars={k: p[k] for k in ("hru_area", "hru_lat", "hru_slope", "hru_aspect",
+                                                           "hru_type", "hru_in_to_cf")})
+    dis_both = pwsb.Parameters(dims={"nhru": 765, "nsegment": 456},
+                               coords={"nhm_id": p["nhm_id"], "nhm_seg": p["nhm_seg"]},
+                               data_vars={k: p[k] for k in ("hru_area", "hru_segment", "hru_in_to_cf")
+                                          + tuple(k for k in seg_keys if k in p and k != "nhm_seg")})
+    rest = pwsb.Parameters(dims={"nhru": 765}, data_vars={
+        k: v for k, v in p.items() if k not in dis_hru.parameters and k not in dis_both.parameters
+        and k not in ("nhm_id", "nhm_seg")})
+    control = _control(6, budget_type="warn")
+    model_dict = {
+        "control": control,
+        "dis_hru": dis_hru,
+        "dis_both": dis_both,
+        "groundwater": {"class": pwsb.PRMSGroundwater, "parameters": rest, "dis": "dis_hru"},
+        "channel": {"class": pwsb.PRMSChannel, "parameters": rest, "dis": "dis_both"},
+        "model_order": ["groundwater", "channel"],
+    }
+    m = pwsb.Model(model_dict, find_input_files=False)
+    assert list(m.processes) == ["PRMSGroundwater", "PRMSChannel"] and m._mode == "sub"
+    assert m.control is control
+    assert m._external_inputs() == ["soil_to_gw", "ssr_to_gw", "dprst_seep_hru", "sroff_vol", "ssres_flow_vol"]
+    assert m._param_dict["tosegment"].shape == (456,) and m._param_dict["gwflow_coef"].shape == (765,)
+    assert m.processes["PRMSChannel"].budget.basis == "global"
