@@ -58,6 +58,8 @@ int pws_set_param_i32(pws_handle *h, const char *name, const int32_t *h_v, int64
  * "block_days" (days per device time block of pws_run_host),
  * "tma" (1, default: the column kernel stages each day's forcing rows in shared
  * memory with TMA bulk copies when they are 16-byte aligned; 0: per-thread loads),
+ * "column_hrus" (HRUs per CTA of the column kernel: 0, default = by domain size,
+ * 128 or 256),
  * "soltab_device" (1: build the PRMSSolarGeometry tables with the CUDA kernel
  * k_soltab; 0, default: with the host libm the reference's tables come from),
  * "channel_chunk" (segments per routing chunk = per CTA of k_route_chunks,

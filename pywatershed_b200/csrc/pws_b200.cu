@@ -98,7 +98,8 @@ struct pws_handle {
   int block_days = 0;
   int soltab_device = 0;
   int tma = 1;  // option: stage forcings with TMA bulk copies when the rows are aligned
-  bool smem_attr_set = false;
+  bool smem_attr_set[6] = {false, false, false, false, false, false};
+  int column_hrus_opt = 0;  // option "column_hrus": 0 = by domain size, else 128 | 256
   double albset[4] = {0, 0, 0, 0};
   // host copies of the parameters (set before pws_init)
   std::map<std::string, std::vector<double>> pf;
@@ -375,6 +376,12 @@ extern "C" int pws_set_option(pws_handle* h, const char* name, double value) {
   else if (!strcmp(name, "block_days")) { h->block_days = (int)value; return 0; }
   else if (!strcmp(name, "soltab_device")) h->soltab_device = value != 0.0;
   else if (!strcmp(name, "tma")) { h->tma = value != 0.0; return 0; }
+  else if (!strcmp(name, "column_hrus")) {
+    if (value != 0 && value != 128 && value != PWS_COLUMN_HRUS)
+      PWS_FAIL(h, "pws_set_option: column_hrus must be 0, 128 or %d", PWS_COLUMN_HRUS);
+    h->column_hrus_opt = (int)value;
+    return 0;
+  }
   else if (!strcmp(name, "channel_chunk")) {
     if (value < 1 || value > PWS_CHUNK_THREADS)
       PWS_FAIL(h, "pws_set_option: channel_chunk must be in 1..%d", PWS_CHUNK_THREADS);
@@ -693,7 +700,7 @@ extern "C" int pws_init(pws_handle* h) {
   const size_t rows_f64 = t.hru_f64.size() + 12 * t.mon_f64.size() + t.derived.size() + 12;
   const size_t rows_i32 = t.hru_i32.size() + 12 * t.mon_i32.size();
   // + one CTA's worth of slack: lanes past the last HRU of the last CTA may read behind a row
-  const size_t slack = 2 * PWS_COLUMN_HRUS;
+  const size_t slack = 2 * PWS_COLUMN_HRUS;  // >= the largest CTA
   PWS_CUDA(h, cudaMalloc(&h->d_f64, (rows_f64 * S + slack) * sizeof(double)));
   PWS_CUDA(h, cudaMemset(h->d_f64, 0, (rows_f64 * S + slack) * sizeof(double)));
   PWS_CUDA(h, cudaMalloc(&h->d_i32, (rows_i32 * S + slack) * sizeof(int32_t)));
@@ -941,6 +948,15 @@ static int enqueue_channel(pws_handle* h, int ndays, const double* d_hru_lat,
   return 0;
 }
 
+// HRUs per CTA of k_hru_column: 128 while that is what it takes to give every SM a
+// CTA, PWS_COLUMN_HRUS (256) for domains that fill the GPU anyway
+static int column_hrus(pws_handle* h) {
+  if (h->column_hrus_opt == 128 || h->column_hrus_opt == PWS_COLUMN_HRUS) return h->column_hrus_opt;
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+  return h->nhru <= (int64_t)nsm * PWS_COLUMN_HRUS ? 128 : PWS_COLUMN_HRUS;
+}
+
 static void fill_column_args(pws_handle* h, ColumnArgs& a, int ndays, const double* d_prcp,
                              const double* d_tmax, const double* d_tmin, int64_t fstride,
                              double* d_out_f64, int32_t* d_out_i32, bool want_viol) {
@@ -978,15 +994,8 @@ static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const d
     PWS_CUDA(h, cudaMemsetAsync(h->d_viol, 0, (size_t)ndays * BUD_N * sizeof(int), h->s_compute));
   ColumnArgs a{};
   fill_column_args(h, a, ndays, d_prcp, d_tmax, d_tmin, fstride, d_out_f64, d_out_i32, want_viol);
-  if (kColumnSmemBytes > 48 * 1024 && !h->smem_attr_set) {
-    for (auto fn : {k_hru_column<SINK_SELECT>, k_hru_column<SINK_FULL>, k_hru_column<SINK_NONE>})
-      PWS_CUDA(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)kColumnSmemBytes));
-    h->smem_attr_set = true;
-  }
   cudaEvent_t e0 = new_event(h), e1 = new_event(h), e2 = new_event(h);
   cudaEventRecord(e0, h->s_compute);
-  const unsigned grid = (unsigned)((h->nhru + PWS_COLUMN_HRUS - 1) / PWS_COLUMN_HRUS);
   // sink: nothing selected / everything in registry order / a subset
   int mode = SINK_SELECT;
   if (h->n_f64 + h->n_i32 == 0) {
@@ -996,12 +1005,28 @@ static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const d
     for (int v = 0; v < PWS_N_HRU_VARS; ++v)
       if (h->slot_hru[v] != full_slot(v)) mode = SINK_SELECT;
   }
-  if (mode == SINK_FULL)
-    k_hru_column<SINK_FULL><<<grid, 2 * PWS_COLUMN_HRUS, kColumnSmemBytes, h->s_compute>>>(a);
-  else if (mode == SINK_NONE)
-    k_hru_column<SINK_NONE><<<grid, 2 * PWS_COLUMN_HRUS, kColumnSmemBytes, h->s_compute>>>(a);
-  else
-    k_hru_column<SINK_SELECT><<<grid, 2 * PWS_COLUMN_HRUS, kColumnSmemBytes, h->s_compute>>>(a);
+  const int H = column_hrus(h);
+  const unsigned grid = (unsigned)((h->nhru + H - 1) / H);
+#define PWS_LAUNCH_COLUMN(MODE, HH)                                                              \
+  do {                                                                                           \
+    if (!h->smem_attr_set[(MODE) * 2 + ((HH) == 128)]) {                                         \
+      PWS_CUDA(h, cudaFuncSetAttribute(k_hru_column<MODE, HH>,                                   \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                                       (int)column_smem_bytes(HH)));                             \
+      h->smem_attr_set[(MODE) * 2 + ((HH) == 128)] = true;                                       \
+    }                                                                                            \
+    k_hru_column<MODE, HH><<<grid, 2 * (HH), column_smem_bytes(HH), h->s_compute>>>(a);          \
+  } while (0)
+  if (H == 128) {
+    if (mode == SINK_FULL) PWS_LAUNCH_COLUMN(SINK_FULL, 128);
+    else if (mode == SINK_NONE) PWS_LAUNCH_COLUMN(SINK_NONE, 128);
+    else PWS_LAUNCH_COLUMN(SINK_SELECT, 128);
+  } else {
+    if (mode == SINK_FULL) PWS_LAUNCH_COLUMN(SINK_FULL, PWS_COLUMN_HRUS);
+    else if (mode == SINK_NONE) PWS_LAUNCH_COLUMN(SINK_NONE, PWS_COLUMN_HRUS);
+    else PWS_LAUNCH_COLUMN(SINK_SELECT, PWS_COLUMN_HRUS);
+  }
+#undef PWS_LAUNCH_COLUMN
   h->launches++;
   PWS_CUDA(h, cudaGetLastError());
   cudaEventRecord(e1, h->s_compute);
@@ -1405,14 +1430,23 @@ extern "C" int pws_last_timing(pws_handle* h, double* ms_column, double* ms_chan
 extern "C" int pws_column_kernel_info(pws_handle* h, int* regs, int* local_bytes,
                                       int* max_blocks_per_sm) {
   cudaFuncAttributes at{};
-  PWS_CUDA(h, cudaFuncGetAttributes(&at, k_hru_column<SINK_FULL>));
   int nb = 0;
-  if (kColumnSmemBytes > 48 * 1024)
-    PWS_CUDA(h, cudaFuncSetAttribute(k_hru_column<SINK_FULL>,
+  if (column_hrus(h) == 128) {
+    PWS_CUDA(h, cudaFuncGetAttributes(&at, k_hru_column<SINK_FULL, 128>));
+    PWS_CUDA(h, cudaFuncSetAttribute(k_hru_column<SINK_FULL, 128>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)kColumnSmemBytes));
-  PWS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_hru_column<SINK_FULL>,
-                                                            2 * PWS_COLUMN_HRUS, kColumnSmemBytes));
+                                     (int)column_smem_bytes(128)));
+    PWS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_hru_column<SINK_FULL, 128>,
+                                                              256, column_smem_bytes(128)));
+  } else {
+    PWS_CUDA(h, cudaFuncGetAttributes(&at, k_hru_column<SINK_FULL, PWS_COLUMN_HRUS>));
+    PWS_CUDA(h, cudaFuncSetAttribute(k_hru_column<SINK_FULL, PWS_COLUMN_HRUS>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)column_smem_bytes(PWS_COLUMN_HRUS)));
+    PWS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                    &nb, k_hru_column<SINK_FULL, PWS_COLUMN_HRUS>, 2 * PWS_COLUMN_HRUS,
+                    column_smem_bytes(PWS_COLUMN_HRUS)));
+  }
   if (regs) *regs = at.numRegs;
   if (local_bytes) *local_bytes = (int)at.localSizeBytes;
   if (max_blocks_per_sm) *max_blocks_per_sm = nb;

@@ -18,8 +18,9 @@
 #include "hru_column.cuh"
 
 // ---- build-time knobs of k_hru_column
-// HRUs per CTA; the CTA has twice as many threads (an upper-half and a
-// lower-half thread per HRU, see k_hru_column)
+// HRUs per CTA for large domains; the CTA has twice as many threads (an
+// upper-half and a lower-half thread per HRU, see k_hru_column).  Domains that
+// do not fill the GPU with such CTAs use 128 HRUs per CTA (twice as many CTAs).
 #ifndef PWS_COLUMN_HRUS
 #define PWS_COLUMN_HRUS 256
 #endif
@@ -157,7 +158,7 @@ struct FullSlot {
   static constexpr unsigned value = (unsigned)full_slot(var);
 };
 
-template <int kMode>
+template <int kMode, int H>
 struct GpuSink {
   const ColumnArgs& a;
   char* pf;
@@ -212,12 +213,12 @@ struct GpuSink {
   __device__ __forceinline__ int ovi(int v) const { return v; }
   __device__ __forceinline__ void sync() {
 #if PWS_COLUMN_SYNC >= 1
-    asm volatile("bar.sync %0, %1;" ::"r"(group_barrier), "n"(PWS_COLUMN_HRUS) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(group_barrier), "n"(H) : "memory");
 #endif
   }
   __device__ __forceinline__ void sync2() {
 #if PWS_COLUMN_SYNC >= 2
-    asm volatile("bar.sync %0, %1;" ::"r"(group_barrier), "n"(PWS_COLUMN_HRUS) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(group_barrier), "n"(H) : "memory");
 #endif
   }
 };
@@ -247,10 +248,16 @@ constexpr int kColI32 = kUpperI32 + kLowerI32 + kMidSlots * kMidI32;
 // forcing stage of the upper half: 2 days x {prcp, tmax, tmin, soltab_potsw row,
 // soltab_horad_potsw row} x H, filled by TMA bulk copies, + 2 mbarriers
 constexpr int kForcRows = 5;
-constexpr size_t kColumnParamBytes = (size_t)PWS_COLUMN_HRUS * (kColF64 * 8 + kColI32 * 4);
-constexpr size_t kColumnForcBytes = (size_t)2 * kForcRows * PWS_COLUMN_HRUS * 8;
-constexpr size_t kColumnSmemBytes = kColumnParamBytes + kColumnForcBytes + 16;
-static_assert(kColumnParamBytes % 16 == 0, "forcing stage must be 16-byte aligned");
+template <int H>
+struct ColumnSmem {
+  static constexpr size_t kParamBytes = (size_t)H * (kColF64 * 8 + kColI32 * 4);
+  static constexpr size_t kForcBytes = (size_t)2 * kForcRows * H * 8;
+  static constexpr size_t kBytes = kParamBytes + kForcBytes + 16;
+  static_assert(kParamBytes % 16 == 0, "forcing stage must be 16-byte aligned");
+};
+constexpr size_t column_smem_bytes(int H) {
+  return (size_t)H * (kColF64 * 8 + kColI32 * 4) + (size_t)2 * kForcRows * H * 8 + 16;
+}
 
 // named barriers of k_hru_column (0 is __syncthreads)
 enum { BAR_UPPER = 1, BAR_LOWER = 2, BAR_MID_FULL = 3, BAR_MID_EMPTY = 3 + PWS_COLUMN_MID_SLOTS };
@@ -312,12 +319,13 @@ struct LowerStateRef {
 // parameters, which doubles the number of resident warps for the same
 // register file and shared memory, and each warp walks only its half of the
 // code.
-template <int kMode>
-__global__ void __launch_bounds__(2 * PWS_COLUMN_HRUS, (2 * PWS_COLUMN_HRUS <= 256) ? 512 / (2 * PWS_COLUMN_HRUS) : 1)
+template <int kMode, int H>
+__global__ void __launch_bounds__(2 * H, (2 * H <= 256) ? 512 / (2 * H) : 1)
 k_hru_column(const __grid_constant__ ColumnArgs a) {
-  constexpr int H = PWS_COLUMN_HRUS;
   // setmaxnreg acts on whole warpgroups (4 warps): each half must be a multiple of one
-  static_assert(H % 128 == 0, "PWS_COLUMN_HRUS must be a multiple of 128");
+  static_assert(H % 128 == 0, "HRUs per CTA must be a multiple of 128");
+  constexpr size_t kColumnParamBytes = ColumnSmem<H>::kParamBytes;
+  constexpr size_t kColumnForcBytes = ColumnSmem<H>::kForcBytes;
   const int tid = threadIdx.x;
   const bool upper = tid < H;  // warpgroup-uniform
   const int r = upper ? tid : tid - H;
@@ -338,7 +346,7 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
   double* const sF = reinterpret_cast<double*>(smem_raw + kColumnParamBytes);  // [2][kForcRows][H]
   const uint32_t mbar0 = smem_u32(smem_raw + kColumnParamBytes + kColumnForcBytes);
 
-  GpuSink<kMode> out{a, nullptr, nullptr, nullptr, (unsigned)(a.ostride * 8),
+  GpuSink<kMode, H> out{a, nullptr, nullptr, nullptr, (unsigned)(a.ostride * 8),
                      (unsigned)(a.ostride * 4), 0u, 0, live, upper ? BAR_UPPER : BAR_LOWER};
   const int64_t day_f64 = (int64_t)a.n_f64 * a.ostride * 8;
   const int64_t day_i32 = (int64_t)a.n_i32 * a.ostride * 4;
