@@ -1,0 +1,68 @@
+"""Parity at BASELINE.json's full size through a size-independent property:
+the CONUS-scale synthetic domain (144 DRB tiles, 110,160 HRUs, 65,664
+segments, 3,653 days -- the bench workload) is a set of independent basins, so
+every tile of the big run must equal that tile simulated alone, bit for bit
+(same kernels, different grid / CTA size / forcing staging path), and the
+single tile is what the oracle tests pin to the reference.  GPU only."""
+import numpy as np
+import pytest
+
+import scenarios
+
+pytestmark = pytest.mark.gpu
+
+
+def test_conus_tiles_equal_single_tile_runs():
+    import torch
+
+    import bench
+    from pywatershed_b200 import Engine
+
+    spec = bench.workload_spec("conus")
+    p0, f0, pt, start = bench.build_domain(spec)
+    dev = torch.device("cuda:0")
+    forc = bench.device_forcings(f0, spec, 0, dev)
+    nd = spec["ndays"]
+    eng = Engine(pt, start, device=0)
+    hv = ["pkwater_equiv", "soil_moist", "sroff_vol", "gwres_stor", "newsnow", "transp_on"]
+    sv = ["seg_outflow"]
+    eng.select_outputs(hv, sv)
+    nhru, nseg = eng.nhru, eng.nseg
+    nb_h, nb_s = 765, 456
+    tiles = (0, 71, 143)
+    T = 256
+    nf, ni = len(eng.sel_f64), len(eng.sel_i32)
+    of = torch.empty((T, nf, nhru), dtype=torch.float64, device=dev)
+    oi = torch.empty((T, ni, nhru), dtype=torch.int32, device=dev)
+    osg = torch.empty((T, 1, nseg), dtype=torch.float64, device=dev)
+    viol = torch.zeros((nd, 6), dtype=torch.int32).pin_memory().numpy()
+    big = {t: {"f": [], "i": [], "s": []} for t in tiles}
+    d = 0
+    while d < nd:
+        n = min(T, nd - d)
+        o = d * nhru * 8
+        eng.run_device(n, forc["prcp"].data_ptr() + o, forc["tmax"].data_ptr() + o,
+                       forc["tmin"].data_ptr() + o, of.data_ptr(), oi.data_ptr(), osg.data_ptr(),
+                       viol=viol[d:d + n])
+        for t in tiles:
+            big[t]["f"].append(of[:n, :, t * nb_h:(t + 1) * nb_h].cpu().numpy())
+            big[t]["i"].append(oi[:n, :, t * nb_h:(t + 1) * nb_h].cpu().numpy())
+            big[t]["s"].append(osg[:n, :, t * nb_s:(t + 1) * nb_s].cpu().numpy())
+        d += n
+    assert viol.sum() == 0  # all six budgets close on every day of the 10-year run
+    for t in tiles:
+        ft = {k: forc[k][:, t * nb_h:(t + 1) * nb_h].cpu().numpy() for k in ("prcp", "tmax", "tmin")}
+        one = Engine(p0, start, device=0)
+        one.select_outputs(hv, sv)
+        got, v1 = one.run_host(ft["prcp"], ft["tmax"], ft["tmin"])
+        bf = np.concatenate(big[t]["f"])
+        bi = np.concatenate(big[t]["i"])
+        bs = np.concatenate(big[t]["s"])
+        for k, name in enumerate(one.sel_f64):
+            np.testing.assert_array_equal(bf[:, k], got[name], err_msg=f"tile {t} {name}")
+        for k, name in enumerate(one.sel_i32):
+            np.testing.assert_array_equal(bi[:, k], np.asarray(got[name], dtype=np.int32),
+                                          err_msg=f"tile {t} {name}")
+        np.testing.assert_array_equal(bs[:, 0], got["seg_outflow"], err_msg=f"tile {t} seg_outflow")
+        assert v1.sum() == 0
+        one.close()
