@@ -415,21 +415,29 @@ def main():
     achieved = units_per_launch * bpu / avg_launch_s / 1e9
     # DRAM bytes per launch from the committed ncu capture (profiles/), scaled to
     # this run's launch size; only meaningful for the output mode it was taken in
-    traffic = None
+    traffic, fp64 = None, None
     prof = ROOT / "profiles" / "r01_column_traffic.json"
-    if prof.exists() and args.outputs == "full":
+    if prof.exists():
         try:
             pj = json.loads(prof.read_text())
-            traffic = pj["dram_bytes_per_launch"] * units_per_launch / pj["hru_days_per_launch"]
+            if args.outputs == "full":
+                traffic = pj["dram_bytes_per_launch"] * units_per_launch / pj["hru_days_per_launch"]
+            # the other roofline of the kernel: FP64 work per HRU-day counted by ncu
+            # (DADD + DMUL + 2 DFMA thread instructions) against the FP64 pipe's peak
+            tf = pj["fp64_flops_per_hru_day"] * units_per_launch / avg_launch_s / 1e12
+            fp64 = {"achieved": tf, "peak": pj["fp64_peak_tflops"], "unit": "TFLOP/s",
+                    "frac": tf / pj["fp64_peak_tflops"],
+                    "flops_per_hru_day": pj["fp64_flops_per_hru_day"]}
         except Exception:
-            traffic = None
+            traffic, fp64 = None, None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "kernel": "k_hru_column",
                 "peak_source": peak_src, "bytes_per_hru_day": bpu,
                 "hru_days_per_launch": units_per_launch,
                 "avg_launch_ms": avg_launch_s * 1e3,
                 "share_of_step": col_ms / max(sum(step_ms), 1e-9),
-                "channel_share_of_step": ch_ms / max(sum(step_ms), 1e-9)}
+                "channel_share_of_step": ch_ms / max(sum(step_ms), 1e-9),
+                "fp64": fp64}
 
     cpu = None
     if not args.no_cpu and world == 1:
