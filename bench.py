@@ -1,6 +1,6 @@
 """bench.py -- simulated HRU-days/s of the full NHM chain on B200 (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload conus|ucb|drb]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload conus|ucb|drb|ensemble|ensemble128|channel|channel_chained]
                     [--outputs full|nhm_default|routing] [--impl reference]
 
 A *step* is one pass of the hot path over the whole workload: reset to the
@@ -251,6 +251,98 @@ def run_reference(args, spec):
     print(json.dumps(line))
 
 
+def chain_tiles(p0, pt, ntile):
+    """BASELINE.json configs[4], chained variant: every tile's main outlet drains
+    into the farthest headwater of the next tile (depth ~ ntile x 72 levels)."""
+    tos0 = np.asarray(p0["tosegment"], dtype=np.int64)
+    nseg0 = tos0.shape[0]
+    # distance to / id of the outlet by walking tosegment (456 segments: cheap)
+    dist = np.zeros(nseg0, dtype=np.int64)
+    outlet = np.zeros(nseg0, dtype=np.int64)
+    for s0 in range(nseg0):
+        j, n = s0, 0
+        while tos0[j] > 0:
+            j = tos0[j] - 1
+            n += 1
+        dist[s0], outlet[s0] = n, j
+    main_outlet = int(np.argmax(np.bincount(outlet)))
+    head = int(np.argmax(np.where(outlet == main_outlet, dist, -1)))
+    tos = np.asarray(pt["tosegment"]).copy()
+    for t in range(ntile - 1):
+        tos[t * nseg0 + main_outlet] = (t + 1) * nseg0 + head + 1
+    out = dict(pt)
+    out["tosegment"] = tos
+    return out, int(dist.max()) + 1
+
+
+def run_channel_only(args):
+    """--workload channel | channel_chained: BASELINE.json configs[4], PRMSChannel
+    alone (prms_channel.py:388-585) over 123 DRB tiles of segments (56,088), lateral
+    inflow LogNormal (seed 11) resident in HBM; metric = segment-days/s."""
+    import torch
+    import scenarios
+    import __graft_entry__ as g
+
+    g.build()
+    from pywatershed_b200 import Engine
+
+    dev = torch.device("cuda", 0)
+    p0, f0, start = scenarios.load_drb()
+    ntile, nd = 123, 3653
+    pt, _ = scenarios.tile(p0, {k: v[:2] for k, v in f0.items()}, ntile)
+    depth = 72
+    if args.workload == "channel_chained":
+        pt, d1 = chain_tiles(p0, pt, ntile)
+        depth = d1 * ntile
+    eng = Engine(pt, start, device=0)
+    nseg = eng.nseg
+    T = max(1, min(args.block_days, nd))
+    gen = torch.Generator(device=dev).manual_seed(11)
+    lat = torch.exp(torch.randn((nd, nseg), dtype=torch.float64, device=dev, generator=gen))
+    out = torch.empty((T, 5, nseg), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+
+    def one_pass():
+        eng.reset()
+        torch.cuda.synchronize()
+        eng.timer_mark(0)
+        d = 0
+        while d < nd:
+            n = min(T, nd - d)
+            eng.run_channel_device(n, lat.data_ptr() + d * nseg * 8, out.data_ptr(), sync=False)
+            d += n
+        eng.timer_mark(1)
+        torch.cuda.synchronize()
+        eng.timing()
+        return eng.timer_elapsed_ms()
+
+    for _ in range(args.warmup):
+        one_pass()
+    sampler = ClockSampler(0)
+    sampler.start()
+    ms = [one_pass() for _ in range(args.steps)]
+    clocks = sampler.stop()
+    t = sum(ms) / 1e3
+    units = nseg * nd * args.steps
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+    peak = float(peaks.get("hbm_gbs", 6548.8))
+    ach = units * 48 / t / 1e9
+    print(json.dumps({
+        "metric": "routed segment-days/sec, PRMSChannel alone", "value": units / t, "unit": "segment-days/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"channel-only, {nseg:,} segments ({ntile} DRB tiles"
+                               + (", chained outlet->headwater" if args.workload == "channel_chained" else "")
+                               + f"), depth ~{depth} levels, {nd} days x 24 hourly sub-steps",
+                   "block_days": T, "l2": "lateral inflow + outputs per block exceed L2"},
+        "segment_substeps_per_s": units * 24 / t,
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                     "traffic": None, "kernel": "k_route_chunks",
+                     "note": "48 B per segment-day (8 read + 5x8 written); the kernel is bound by the "
+                             "serial hourly recurrence along the network depth, not by HBM"},
+        "gpu_launches": eng.launch_count(), "clocks": clocks}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -264,6 +356,8 @@ def main():
     ap.add_argument("--e2e-block-days", type=int, default=128)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    if args.workload in ("channel", "channel_chained"):
+        return run_channel_only(args)
     spec = workload_spec(args.workload)
     if args.impl == "reference":
         return run_reference(args, spec)
