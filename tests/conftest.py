@@ -27,3 +27,10 @@ def drbx(drb):
     p, f, start = drb
     px, fx = scenarios.drbx(p, f)
     return px, fx, start
+
+
+@pytest.fixture(scope="session")
+def sagehen():
+    import scenarios
+
+    return scenarios.load_sagehen()

@@ -22,6 +22,22 @@ def load_drb():
     return params, forc, str(z["start"])
 
 
+def load_sagehen():
+    """sagehen_5yr (128 HRUs, Sierra Nevada, WY1981-85; the reference's
+    test_data/sagehen_5yr ASCII files, extracted by oracle/gen_golden_sagehen.py).
+    The parameter file has no depression-storage and no channel parameters (the
+    reference runs it with the *NoDprst processes and without PRMSChannel); they
+    are completed with the stand-ins the product uses for absent processes."""
+    from pywatershed_b200.engine import Engine
+
+    z = np.load(GOLDEN / "sagehen_inputs.npz")
+    params = {k[2:]: z[k] for k in z.files if k.startswith("p_")}
+    params = Engine._filled(params)
+    params.pop("tosegment", None)
+    forc = {k: z[k].astype(np.float64) for k in ("prcp", "tmax", "tmin")}
+    return params, forc, str(z["start"])
+
+
 def drbx(params: dict, forc: dict):
     """'drbx': DRB with the branches DRB never takes switched on for a
     pattern of HRUs: SWALE / LAKE / INACTIVE hru_type,

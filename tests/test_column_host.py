@@ -36,7 +36,7 @@ def shim():
     return L
 
 
-def _run(L, P, F, start, nd):
+def _run(L, P, F, start, nd, dprst_flag=True):
     n = P["hru_area"].shape[0]
     h = L.shim_create(n, P["snarea_curve"].size)
     for k in po.HRU_F8 + po.MON_F8 + ["snarea_curve"]:
@@ -48,7 +48,7 @@ def _run(L, P, F, start, nd):
     for k in po.SCALAR_F8:
         L.shim_set_opt(h, k.encode(), float(np.ravel(P[k])[0]))
     cal = po.calendar(start, nd)
-    L.shim_set_opt(h, b"dprst_flag", 1.0)
+    L.shim_set_opt(h, b"dprst_flag", 1.0 if dprst_flag else 0.0)
     L.shim_set_opt(h, b"temp_units", float(np.ravel(P["temp_units"])[0]))
     L.shim_set_opt(h, b"start_month", float(cal[0, 2]))
     L.shim_set_opt(h, b"start_doy", float(cal[0, 0]))
@@ -71,6 +71,21 @@ def test_device_physics_bit_identical_to_oracle(shim, scen, drb, drbx):
     o = po.Oracle(P, start=start)
     ref, oviol = o.run(F["prcp"][:nd], F["tmax"][:nd], F["tmin"][:nd], po.HRU_VARS, ())
     for k in po.HRU_VARS:
+        np.testing.assert_array_equal(got[k], ref[k], err_msg=k)
+    np.testing.assert_array_equal(viol[:, :5], oviol[:, :5])
+
+
+def test_device_physics_on_sagehen(shim, sagehen):
+    """The snow-dominated second domain (deep packs, two depletion curves),
+    NoDprst variant: device physics on the host == oracle, bit for bit."""
+    P, F, start = sagehen
+    nd = F["prcp"].shape[0]
+    got, viol = _run(shim, P, F, start, nd, dprst_flag=False)
+    o = po.Oracle(P, start=start, dprst_flag=False)
+    ref, oviol = o.run(F["prcp"], F["tmax"], F["tmin"], po.HRU_VARS, ())
+    for k in po.HRU_VARS:
+        if k.startswith("channel_"):
+            continue  # PRMSChannel's per-HRU variables: the process is not part of this model
         np.testing.assert_array_equal(got[k], ref[k], err_msg=k)
     np.testing.assert_array_equal(viol[:, :5], oviol[:, :5])
 

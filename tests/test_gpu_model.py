@@ -226,6 +226,48 @@ def test_nodprst_model_matches_the_reference(drb):
         assert m.processes[pname].budget._zero_sum
 
 
+def test_sagehen_model_through_the_api(sagehen):
+    """The reference's second test domain through the Model API exactly as its
+    sagehen_no_cascades_model.yaml composes it: seven processes, NoDprst
+    variants, no PRMSChannel, a parameter set WITHOUT depression-storage or
+    channel parameters; compared with the reference's outputs
+    (tests/golden/sagehen_golden.npz) on the sampled HRUs, all 1,826 days."""
+    import pywatershed_b200 as pwsb
+
+    z = np.load(scenarios.GOLDEN / "sagehen_inputs.npz")
+    raw = {k[2:]: z[k] for k in z.files if k.startswith("p_")}  # as in the parameter file
+    _, f, start = sagehen
+    nd = f["prcp"].shape[0]
+    names = ["PRMSSolarGeometry", "PRMSAtmosphere", "PRMSCanopy", "PRMSSnow", "PRMSRunoffNoDprst",
+             "PRMSSoilzoneNoDprst", "PRMSGroundwaterNoDprst"]
+    nhru = raw["hru_area"].shape[0]
+    params = pwsb.Parameters(dims={"nhru": nhru, "nmonth": 12, "ndoy": 366},
+                             coords={"nhm_id": np.arange(1, nhru + 1)},
+                             data_vars={k: v for k, v in raw.items() if k != "nhm_id"})
+    control = _control(start, nd, dprst_flag=False)
+    m = pwsb.Model([getattr(pwsb, n) for n in names], control=control, parameters=params,
+                   find_input_files=False)
+    for k in ("prcp", "tmax", "tmin"):
+        m.processes["PRMSAtmosphere"].set_input_to_adapter(k, f[k])
+    g = np.load(scenarios.GOLDEN / "sagehen_golden.npz")
+    hs = g["hru_sample"]
+    series = {}
+    for it in range(nd):
+        m.advance()
+        m.calculate()
+        for pname in names[2:]:
+            proc = m.processes[pname]
+            for v in proc.get_variables():
+                series.setdefault(v, []).append(np.asarray(proc[v], dtype=np.float64)[hs])
+    got = {v: np.stack(rows) for v, rows in series.items()}
+    ref = {v: np.asarray(g["ts_" + v], dtype=np.float64) for v in got}
+    rep = parity.compare_columns(got, ref, list(got), got["pkwater_equiv"], ref["pkwater_equiv"])
+    assert rep["mismatches"] == [], rep["mismatches"][:3]
+    assert got["pkwater_equiv"].max() > 30.0
+    for pname in names[2:]:
+        assert m.processes[pname].budget._zero_sum
+
+
 def _write_cbh(path, name, start, values):
     """PRMS CBH ASCII (utils/cbh_utils.py:32-122): header, '####', then one
     line per day: year month day hour minute second v1 ... vn."""

@@ -115,6 +115,35 @@ def test_full_chain_parity(scen, drb, drbx):
         assert rep2["mismatches"] == []
 
 
+def test_sagehen_parity(sagehen):
+    """Second domain, snow-dominated (the reference's test_data/sagehen_5yr as
+    sagehen_no_cascades_model.yaml runs it: NoDprst processes, no channel; packs up
+    to 79 inches, two depletion curves, 5 water years): the CUDA column against
+    the oracle on every HRU and against the reference's own outputs."""
+    p, f, start = sagehen
+    nd = f["prcp"].shape[0]
+    e = _engine(p, start, dprst_flag=False, channel=False)
+    e.select_outputs(e.reg.hru_vars, ())
+    got, viol = e.run_host(f["prcp"], f["tmax"], f["tmin"])
+    o = po.Oracle(p, start=start, dprst_flag=False)
+    ref, oviol = o.run(f["prcp"], f["tmax"], f["tmin"], po.HRU_VARS, ())
+    names = [k for k in po.HRU_VARS if not k.startswith("channel_")]  # PRMSChannel is not in this model
+    rep = parity.compare_columns(got, ref, names, got["pkwater_equiv"], ref["pkwater_equiv"])
+    assert rep["mismatches"] == [], rep["mismatches"][:5]
+    assert len(rep["ties"]) <= 6, rep["ties"]
+    print(f"sagehen ghost-pack ties: {len(rep['ties'])} of {got['pkwater_equiv'].shape[1]} HRUs")
+    assert got["pkwater_equiv"].max() > 70.0
+    if not rep["ties"]:
+        np.testing.assert_array_equal(viol[:, :5], oviol[:, :5])
+    assert viol[:, :5].sum() <= len(rep["ties"])
+    g = np.load(scenarios.GOLDEN / "sagehen_golden.npz")
+    hs = g["hru_sample"]
+    gnames = [k[3:] for k in g.files if k.startswith("ts_")]
+    rep2 = parity.compare_columns({k: got[k][:, hs] for k in gnames}, {k: g["ts_" + k] for k in gnames},
+                                  gnames, got["pkwater_equiv"][:, hs], g["ts_pkwater_equiv"])
+    assert rep2["mismatches"] == [], rep2["mismatches"][:5]
+
+
 @pytest.mark.parametrize("tma", [1, 0])
 def test_forcing_staging_paths_agree(drb, tma):
     """k_hru_column stages the forcing rows with TMA bulk copies when they are

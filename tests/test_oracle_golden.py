@@ -146,3 +146,29 @@ def test_nodprst_variants_match_reference(drb):
         np.testing.assert_allclose(np.asarray(res[k], dtype=np.float64).sum(axis=1), g["sum_" + k],
                                    rtol=1e-9, atol=1e-8, err_msg="sum " + k)
     assert viol.sum() == 0
+
+
+def test_sagehen_matches_reference(sagehen):
+    """A second, snow-dominated domain pins the oracle: the reference's
+    test_data/sagehen_5yr run as sagehen_no_cascades_model.yaml prescribes
+    (NoDprst processes, no channel), 1,826 days, packs up to 79 inches of water
+    equivalent, two depletion curves (oracle/gen_golden_sagehen.py)."""
+    p, f, start = sagehen
+    g = np.load(scenarios.GOLDEN / "sagehen_golden.npz")
+    o = po.Oracle(p, start=start, dprst_flag=False)
+    res, viol = o.run(f["prcp"], f["tmax"], f["tmin"], po.HRU_VARS, ())
+    sol = o.soltabs()
+    o.close()
+    hs, snap = g["hru_sample"], list(g["snap_days"])
+    names = [k[3:] for k in g.files if k.startswith("ts_")]
+    assert len(names) >= 120 and res["pkwater_equiv"].max() > 70.0
+    for k in names:
+        r = np.asarray(res[k], dtype=np.float64)
+        np.testing.assert_allclose(r[:, hs], np.asarray(g["ts_" + k], dtype=np.float64),
+                                   rtol=1e-9, atol=1e-10, err_msg=k)
+        np.testing.assert_allclose(r[snap], np.asarray(g["snap_" + k], dtype=np.float64),
+                                   rtol=1e-9, atol=1e-10, err_msg="snapshot " + k)
+        np.testing.assert_allclose(r.sum(axis=1), g["sum_" + k], rtol=1e-9, atol=1e-8, err_msg="sum " + k)
+    for k in ("soltab_potsw", "soltab_horad_potsw", "soltab_sunhrs"):
+        np.testing.assert_allclose(sol[k][:, hs], g[k], rtol=1e-12, atol=1e-12, err_msg=k)
+    assert viol.sum() == 0
