@@ -34,3 +34,10 @@ def sagehen():
     import scenarios
 
     return scenarios.load_sagehen()
+
+
+@pytest.fixture(scope="session")
+def hru1():
+    import scenarios
+
+    return scenarios.load_hru1()

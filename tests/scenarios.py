@@ -38,6 +38,15 @@ def load_sagehen():
     return params, forc, str(z["start"])
 
 
+def load_hru1():
+    """hru_1: one HRU, one segment, 1979-2019 (14,975 days); the reference's
+    test_data/hru_1 ASCII files, extracted by oracle/gen_golden_hru1.py."""
+    z = np.load(GOLDEN / "hru1_inputs.npz")
+    params = {k[2:]: z[k] for k in z.files if k.startswith("p_")}
+    forc = {k: z[k].astype(np.float64) for k in ("prcp", "tmax", "tmin")}
+    return params, forc, str(z["start"])
+
+
 def drbx(params: dict, forc: dict):
     """'drbx': DRB with the branches DRB never takes switched on for a
     pattern of HRUs: SWALE / LAKE / INACTIVE hru_type,

@@ -90,6 +90,18 @@ def test_device_physics_on_sagehen(shim, sagehen):
     np.testing.assert_array_equal(viol[:, :5], oviol[:, :5])
 
 
+def test_device_physics_on_hru1_41_years(shim, hru1):
+    """One HRU for 14,975 days: device physics on the host == oracle, bit for bit."""
+    P, F, start = hru1
+    nd = F["prcp"].shape[0]
+    got, viol = _run(shim, P, F, start, nd)
+    o = po.Oracle(P, start=start)
+    ref, oviol = o.run(F["prcp"], F["tmax"], F["tmin"], po.HRU_VARS, ())
+    for k in po.HRU_VARS:
+        np.testing.assert_array_equal(got[k], ref[k], err_msg=k)
+    np.testing.assert_array_equal(viol[:, :5], oviol[:, :5])
+
+
 def test_div_by_ts_is_the_division(shim):
     """k_route_chunks divides by the Muskingum sub-daily step with
     q = x r, q + fma(-q, ts, x) r (r = correctly rounded 1/ts): must be the

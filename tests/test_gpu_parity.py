@@ -144,6 +144,36 @@ def test_sagehen_parity(sagehen):
     assert rep2["mismatches"] == [], rep2["mismatches"][:5]
 
 
+def test_hru1_41_years(hru1):
+    """The reference's test_data/hru_1: ONE HRU draining to ONE segment for
+    14,975 days (1979-2019) through pws_run_host in blocks of days -- the
+    single-unit edge of every kernel and 41 years without drift, against the
+    oracle (all days) and the reference's own outputs (golden days)."""
+    p, f, start = hru1
+    e = _engine(p, start)
+    got, viol = e.run_host(f["prcp"], f["tmax"], f["tmin"])
+    o = po.Oracle(p, start=start)
+    ref, oviol = o.run(f["prcp"], f["tmax"], f["tmin"], po.HRU_VARS, po.SEG_VARS)
+    rep = parity.compare_columns(got, ref, po.HRU_VARS, got["pkwater_equiv"], ref["pkwater_equiv"])
+    assert rep["mismatches"] == [], rep["mismatches"][:5]
+    g = np.load(scenarios.GOLDEN / "hru1_golden.npz")
+    days = g["days"]
+    if not rep["ties"]:
+        np.testing.assert_array_equal(viol, oviol)
+        parity.assert_segments_close(got, ref, po.SEG_VARS)
+        for k in [k[3:] for k in g.files if k.startswith("ts_")]:
+            np.testing.assert_allclose(np.asarray(got[k], dtype=np.float64)[days],
+                                       np.asarray(g["ts_" + k], dtype=np.float64),
+                                       rtol=1e-9, atol=1e-10, err_msg=k)
+        assert viol.sum() == 0
+    else:
+        print("hru_1: ghost-pack tie on day", rep["ties"][0][1])
+        d = rep["ties"][0][1]
+        for k in po.HRU_VARS:
+            np.testing.assert_allclose(np.asarray(got[k], dtype=np.float64)[:d],
+                                       np.asarray(ref[k], dtype=np.float64)[:d], rtol=1e-9, atol=1e-10, err_msg=k)
+
+
 @pytest.mark.parametrize("tma", [1, 0])
 def test_forcing_staging_paths_agree(drb, tma):
     """k_hru_column stages the forcing rows with TMA bulk copies when they are

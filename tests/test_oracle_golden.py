@@ -172,3 +172,23 @@ def test_sagehen_matches_reference(sagehen):
     for k in ("soltab_potsw", "soltab_horad_potsw", "soltab_sunhrs"):
         np.testing.assert_allclose(sol[k][:, hs], g[k], rtol=1e-12, atol=1e-12, err_msg=k)
     assert viol.sum() == 0
+
+
+def test_hru1_41_years_match_reference(hru1):
+    """The reference's smallest and longest test domain (test_data/hru_1: one
+    HRU, one segment, 14,975 days): no drift over 41 years, ten leap years and
+    forty water-year resets; every variable, routing included
+    (oracle/gen_golden_hru1.py)."""
+    p, f, start = hru1
+    g = np.load(scenarios.GOLDEN / "hru1_golden.npz")
+    o = po.Oracle(p, start=start)
+    res, viol = o.run(f["prcp"], f["tmax"], f["tmin"], po.HRU_VARS, po.SEG_VARS)
+    o.close()
+    days = g["days"]
+    names = [k[3:] for k in g.files if k.startswith("ts_")]
+    assert len(names) >= 145 and days[-1] == 14974
+    for k in names:
+        np.testing.assert_allclose(np.asarray(res[k], dtype=np.float64)[days],
+                                   np.asarray(g["ts_" + k], dtype=np.float64),
+                                   rtol=1e-9, atol=1e-10, err_msg=k)
+    assert viol.sum() == 0
