@@ -110,6 +110,49 @@ class Control:
         dt_h = float(np.atleast_1d(raw.get("initial_deltat", [24.0]))[0])
         return cls(start, end, np.timedelta64(int(dt_h), "h"), options=opts)
 
+    @classmethod
+    def from_yaml(cls, yaml_file) -> "Control":
+        """Control from a yaml file (base/control.py:549-610): start_time, end_time,
+        time_step, time_step_units at the top level, every other key is an option;
+        input_dir is taken relative to the yaml file and must exist."""
+        import yaml
+
+        yaml_file = pl.Path(yaml_file)
+        with yaml_file.open("r") as fh:
+            d = yaml.load(fh, Loader=yaml.Loader)
+        start = np.datetime64(d.pop("start_time"))
+        end = np.datetime64(d.pop("end_time"))
+        step = np.timedelta64(int(d.pop("time_step")), d.pop("time_step_units"))
+        if "input_dir" in d:
+            path = pl.Path(d["input_dir"])
+            d["input_dir"] = path if path.is_absolute() else (yaml_file.parent / path).resolve()
+            if not d["input_dir"].exists():
+                raise FileNotFoundError(f"input_dir {d['input_dir']} does not exist")
+        return cls(start, end, step, options=d)
+
+    def to_dict(self, deep_copy: bool = True) -> dict:
+        """base/control.py:490-516."""
+        from copy import deepcopy
+
+        step_h = int(self._time_step / np.timedelta64(1, "h"))
+        opts = deepcopy(dict(self.options)) if deep_copy else dict(self.options)
+        return {"start_time": str(self._start_time), "end_time": str(self._end_time),
+                "time_step": step_h, "time_step_units": "h", "options": opts}
+
+    def to_yaml(self, yaml_file) -> None:
+        """Options flattened to the top level next to the four time keys
+        (base/control.py:518-547); `from_yaml` reads it back."""
+        import yaml
+
+        d = self.to_dict()
+        opts = d.pop("options")
+        for k, v in opts.items():
+            if k in d:
+                raise ValueError("Control option keys collide with non-option keys")
+            d[k] = str(v) if isinstance(v, pl.Path) else v
+        with open(yaml_file, "w") as fh:
+            yaml.dump(d, fh)
+
     # ---- clock
     @property
     def current_time(self):

@@ -171,9 +171,50 @@ class Model:
         self.block_days = self.control.options.get("block_days") or None
         return self
 
+    @staticmethod
+    def model_dict_from_yaml(yaml_file) -> dict:
+        """A model dictionary from a yaml file (base/model.py:541-593): string
+        values ending in .yaml/.yml are Control files, .nc are discretization
+        Parameters; dict values with a "class" key are processes whose
+        "parameters" is a parameter file.  Paths are relative to the yaml file.
+        Beyond the reference, a parameter / discretization file may also be a
+        PRMS ASCII parameter file (.param)."""
+        import yaml
+
+        yaml_file = pl.Path(yaml_file)
+
+        def rel(path):
+            path = pl.Path(path)
+            return path if path.is_absolute() else (yaml_file.parent / path).resolve()
+
+        def params(path):
+            path = rel(path)
+            if path.suffix == ".param":
+                return PrmsParameters.load(path)
+            if path.suffix == ".nc":
+                return Parameters.from_netcdf(path)
+            raise ValueError("Unsupported file extension for control (.yml/.yaml) and parameter "
+                             "(.nc) file paths in model yaml file")
+
+        with yaml_file.open("r") as fh:
+            md = yaml.load(fh, Loader=yaml.Loader)
+        for key, val in md.items():
+            if isinstance(val, str):
+                if val.endswith((".yml", ".yaml")):
+                    md[key] = Control.from_yaml(rel(val))
+                else:
+                    md[key] = params(val)
+            elif isinstance(val, dict) and "class" in val:
+                if val["class"] not in P.PROCESS_CLASSES:
+                    raise NotImplementedError(f"process {val['class']} is outside the NHM chain")
+                val["class"] = P.PROCESS_CLASSES[val["class"]]
+                val["parameters"] = params(val["parameters"])
+        return md
+
     @classmethod
     def from_yaml(cls, yaml_file):
-        raise NotImplementedError("Model.from_yaml is not implemented in pywatershed_b200")
+        """Model from a yaml file (base/model.py:595-664)."""
+        return cls(cls.model_dict_from_yaml(yaml_file))
 
     # ---------------------------------------------------------------- inputs
     def _load_input(self, name, nunits):

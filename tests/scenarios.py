@@ -128,3 +128,38 @@ def tile(params: dict, forc: dict, ntile: int, nhru_keep: int | None = None,
     p["nhm_id"] = np.arange(1, p["hru_area"].shape[0] + 1)
     p["nhm_seg"] = np.arange(1, p["tosegment"].shape[0] + 1)
     return p, f
+
+
+def write_prms_param_file(path, params: dict, nmonth_names=()):
+    """PRMS ASCII parameter file (utils/prms5_file_util.py:165-231): a
+    dimensions section and one record per parameter; [12, nhru] arrays are
+    written HRU-fastest as PRMS does."""
+    nhru = int(np.asarray(params["hru_area"]).shape[0])
+    nseg = int(np.asarray(params["tosegment"]).shape[0]) if "tosegment" in params else 0
+    dims = {"nhru": nhru, "nsegment": nseg, "nmonths": 12, "one": 1,
+            "ndeplval": int(np.asarray(params["snarea_curve"]).size)}
+    seg_names = ("tosegment", "tosegment_nhm", "seg_length", "seg_slope", "seg_depth", "mann_n", "x_coef",
+                 "segment_type", "segment_flow_init", "nhm_seg", "seg_lat", "seg_width", "obsin_segment",
+                 "obsout_segment", "seg_cum_area", "seg_elev", "seg_humidity")
+    with open(path, "w") as fh:
+        fh.write("written by tests/scenarios.py\nVersion: 1.7\n** Dimensions **\n")
+        for k, v in dims.items():
+            fh.write(f"####\n{k}\n{v}\n")
+        fh.write("** Parameters **\n")
+        for k, v in params.items():
+            v = np.asarray(v)
+            if v.dtype.kind not in "fiu":
+                continue
+            if v.ndim == 2:
+                dn, flat = ["nhru", "nmonths"], v.ravel()  # [12, nhru] C order == (nhru, nmonths) F order
+            elif k == "snarea_curve":
+                dn, flat = ["ndeplval"], v.ravel()
+            elif v.size == 1:
+                dn, flat = ["one"], v.ravel()
+            elif k in seg_names or (v.shape[0] == nseg and nseg != nhru):
+                dn, flat = ["nsegment"], v
+            else:
+                dn, flat = ["nhru"], v
+            tcode = 1 if v.dtype.kind in "iu" else 3
+            fh.write(f"####\n{k}\n{len(dn)}\n" + "\n".join(dn) + f"\n{flat.size}\n{tcode}\n")
+            fh.write("\n".join(repr(int(x)) if tcode == 1 else repr(float(x)) for x in flat) + "\n")

@@ -301,3 +301,27 @@ def test_model_finds_cbh_input_files(drb, tmp_path):
                                rtol=1e-9, atol=1e-10)
     np.testing.assert_allclose(m.processes["PRMSAtmosphere"]["hru_ppt"].data, ref["hru_ppt"],
                                rtol=1e-9, atol=1e-10)
+
+
+def test_model_from_yaml_runs(drb, tmp_path):
+    """Model.from_yaml (base/model.py:595-664) on files laid out like the
+    reference's test_data/drb_2yr/nhm_model.yaml: control yaml, parameter file,
+    CBH forcings found in input_dir; run and compared with the oracle."""
+    import pywatershed_b200 as pwsb
+    from test_host_layer import _write_model_yaml
+
+    p, f, start = drb
+    nd = 40
+    for k in ("prcp", "tmax", "tmin"):
+        _write_cbh(tmp_path / f"{k}.cbh", k, start, f[k][:nd])
+    m = pwsb.Model.from_yaml(_write_model_yaml(tmp_path, p, f, start, nd))
+    m.run(finalize=True)
+    o = po.Oracle(p, start=start)
+    ref, _ = o.run(f["prcp"][:nd], f["tmax"][:nd], f["tmin"][:nd], ["pkwater_equiv", "gwres_flow"],
+                   ["seg_outflow"])
+    np.testing.assert_allclose(m.processes["PRMSSnow"]["pkwater_equiv"], ref["pkwater_equiv"][-1],
+                               rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(m.processes["PRMSGroundwater"]["gwres_flow"], ref["gwres_flow"][-1],
+                               rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(m.processes["PRMSChannel"]["seg_outflow"], ref["seg_outflow"][-1],
+                               rtol=1e-9, atol=1e-10)

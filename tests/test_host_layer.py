@@ -331,3 +331,63 @@ def test_model_dict_construction(drb):
     assert m._external_inputs() == ["soil_to_gw", "ssr_to_gw", "dprst_seep_hru", "sroff_vol", "ssres_flow_vol"]
     assert m._param_dict["tosegment"].shape == (456,) and m._param_dict["gwflow_coef"].shape == (765,)
     assert m.processes["PRMSChannel"].budget.basis == "global"
+
+
+def test_control_yaml_round_trip(tmp_path):
+    """Control.to_yaml / from_yaml (base/control.py:518-610): options flattened
+    next to the four time keys, input_dir relative to the file."""
+    from pywatershed_b200 import Control
+
+    (tmp_path / "in").mkdir()
+    (tmp_path / "control.yaml").write_text(
+        "start_time: 1979-01-01T00:00:00\nend_time: 1979-01-10T00:00:00\ntime_step: 24\n"
+        "time_step_units: h\nverbosity: 0\ninput_dir: in\nbudget_type: warn\ncalc_method: cuda\n"
+        "netcdf_output_var_names:\n  - albedo\n  - seg_outflow\n")
+    c = Control.from_yaml(tmp_path / "control.yaml")
+    assert c.n_times == 10 and c.start_time == np.datetime64("1979-01-01T00:00:00")
+    assert c.options["input_dir"] == (tmp_path / "in").resolve()
+    assert c.options["netcdf_output_var_names"] == ["albedo", "seg_outflow"]
+    c.to_yaml(tmp_path / "again.yaml")
+    c2 = Control.from_yaml(tmp_path / "again.yaml")
+    assert c2.n_times == 10 and c2.time_step == c.time_step and dict(c2.options) == dict(c.options)
+    (tmp_path / "bad.yaml").write_text(
+        "start_time: 1979-01-01T00:00:00\nend_time: 1979-01-10T00:00:00\ntime_step: 24\n"
+        "time_step_units: h\nnot_an_option: 1\n")
+    with pytest.raises(NameError):  # base/control.py:630-636
+        Control.from_yaml(tmp_path / "bad.yaml")
+
+
+def _write_model_yaml(tmp_path, p, f, start, nd):
+    """A model yaml like the reference's test_data/drb_2yr/nhm_model.yaml."""
+    scenarios.write_prms_param_file(tmp_path / "myparam.param", p)
+    (tmp_path / "control.yaml").write_text(
+        f"start_time: {start}T00:00:00\nend_time: {np.datetime64(start) + nd - 1}T00:00:00\n"
+        "time_step: 24\ntime_step_units: h\nverbosity: 0\ninput_dir: .\nbudget_type: error\n"
+        "calc_method: cuda\n")
+    names = ["PRMSSolarGeometry", "PRMSAtmosphere", "PRMSCanopy", "PRMSSnow", "PRMSRunoff", "PRMSSoilzone",
+             "PRMSGroundwater", "PRMSChannel"]
+    txt = "control: control.yaml\ndis_both: myparam.param\n"
+    for n in names:
+        txt += f"{n[4:].lower()}:\n  class: {n}\n  parameters: myparam.param\n  dis: dis_both\n"
+    txt += "model_order:\n" + "".join(f"  - {n[4:].lower()}\n" for n in names)
+    (tmp_path / "nhm_model.yaml").write_text(txt)
+    return tmp_path / "nhm_model.yaml"
+
+
+def test_model_from_yaml_builds(drb, tmp_path):
+    """Model.from_yaml / model_dict_from_yaml (base/model.py:541-664)."""
+    import pywatershed_b200 as pwsb
+
+    p, f, start = drb
+    y = _write_model_yaml(tmp_path, p, f, start, 10)
+    md = pwsb.Model.model_dict_from_yaml(y)
+    assert md["snow"]["class"] is pwsb.PRMSSnow and md["model_order"][0] == "solargeometry"
+    assert isinstance(md["control"], pwsb.Control) and md["dis_both"].dims["nsegment"] == 456
+    m = pwsb.Model.from_yaml(y)
+    assert m._mode == "chain+channel" and list(m.processes)[-1] == "PRMSChannel"
+    assert m.control.n_times == 10
+    np.testing.assert_array_equal(m._param_dict["soil_moist_max"], p["soil_moist_max"])
+    np.testing.assert_array_equal(m._param_dict["tmax_cbh_adj"], p["tmax_cbh_adj"])
+    (tmp_path / "bad.yaml").write_text("control: control.yaml\nx:\n  class: PRMSEt\n  parameters: myparam.param\n")
+    with pytest.raises(NotImplementedError):
+        pwsb.Model.from_yaml(tmp_path / "bad.yaml")
