@@ -567,27 +567,7 @@ class Model:
 
 
 def _read_netcdf_var(path, name):
-    """[time, unit] variable + decoded times from a netCDF file (netCDF4 when
-    importable, scipy for classic files)."""
-    from .netcdf_out import nc4_module
+    """[time, unit] variable + decoded times from a netCDF file."""
+    from .netcdf_in import read_time_variable
 
-    nc4 = nc4_module()
-    if nc4 is not None:
-        with nc4.Dataset(path) as ds:
-            t = ds.variables["time"]
-            times = nc4.num2date(t[:], t.units, only_use_cftime_datetimes=False,
-                                 only_use_python_datetimes=True)
-            times = np.array(times, dtype="datetime64[s]")
-            return times, np.asarray(ds.variables[name][:], dtype=np.float64)
-    else:
-        from scipy.io import netcdf_file
-
-        with netcdf_file(str(path), "r", mmap=False) as ds:
-            t = ds.variables["time"]
-            units = t.units.decode() if isinstance(t.units, bytes) else t.units
-            unit, _, ref = units.partition(" since ")
-            ref = np.datetime64(ref.strip().replace(" ", "T"))
-            step = {"days": "D", "hours": "h", "seconds": "s"}[unit.strip()]
-            times = ref + (np.asarray(t[:]).astype(np.float64) * (
-                np.timedelta64(1, step) / np.timedelta64(1, "s"))).astype("timedelta64[s]")
-            return times.astype("datetime64[s]"), np.asarray(ds.variables[name][:], dtype=np.float64)
+    return read_time_variable(path, name)

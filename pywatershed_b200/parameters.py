@@ -86,30 +86,20 @@ class Parameters:
             meta.update(dict(getattr(p, "metadata", {})))
         return Parameters(dims=dims, coords=coords, data_vars=data, metadata=meta)
 
-    # ---- netCDF round trip (base/data_model.py:354-420).  netCDF4 when it is
-    # importable (HDF5 files, what pywatershed writes), else scipy's classic reader.
+    # ---- netCDF round trip (base/data_model.py:354-420).  Reading goes through
+    # netcdf_in.open_netcdf: netCDF4 when it is importable, else this package's own
+    # HDF5 reader (netCDF-4 files, what pywatershed writes) or scipy (classic files).
     @classmethod
     def from_netcdf(cls, nc_file, *args, **kwargs):
-        from .netcdf_out import nc4_module
+        from .netcdf_in import open_netcdf
 
-        nc4 = nc4_module()
-        dims, coords, data, meta = {}, {}, {}, {}
-        if nc4 is not None:
-            with nc4.Dataset(nc_file) as ds:
-                dims = {k: len(v) for k, v in ds.dimensions.items()}
-                for name, var in ds.variables.items():
-                    arr = np.asarray(var[:])
-                    meta[name] = {"dims": tuple(var.dimensions)}
-                    (coords if name in ("nhm_id", "nhm_seg", "doy") or name in dims else data)[name] = arr
-        else:
-            from scipy.io import netcdf_file
-
-            with netcdf_file(str(nc_file), "r", mmap=False) as ds:
-                dims = {k: (v if v is not None else 0) for k, v in ds.dimensions.items()}
-                for name, var in ds.variables.items():
-                    arr = np.array(var[:])
-                    meta[name] = {"dims": tuple(var.dimensions)}
-                    (coords if name in ("nhm_id", "nhm_seg", "doy") or name in dims else data)[name] = arr
+        coords, data, meta = {}, {}, {}
+        with open_netcdf(nc_file) as ds:
+            dims = dict(ds.dims)
+            for name, var in ds.variables.items():
+                arr = np.asarray(var.read())
+                meta[name] = {"dims": tuple(var.dims)}
+                (coords if name in ("nhm_id", "nhm_seg", "doy") or name in dims else data)[name] = arr
         return cls(dims=dims, coords=coords, data_vars=data, metadata=meta)
 
     def to_netcdf(self, filename, use_xr=False) -> None:

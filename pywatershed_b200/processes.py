@@ -152,11 +152,17 @@ class Process:
             setattr(self, "_" + name, val)
         cm = self._calc_method
         if cm not in (None, "cuda"):
-            if cm in ("numpy", "numba", "fortran"):
+            if cm not in ("numpy", "numba", "fortran"):
+                raise ValueError(f"{self.name}: invalid calc_method '{cm}'")
+            if kw.get("calc_method") is not None:
+                # asked for by name in the constructor: there is no such path here
                 raise ValueError(
                     f"{self.name}: calc_method='{cm}' names a CPU path of the reference; "
                     "pywatershed_b200 only has calc_method='cuda' (no CPU fallback)")
-            raise ValueError(f"{self.name}: invalid calc_method '{cm}'")
+            # inherited from a control file written for the reference: say what happens instead
+            warn(
+                f"{self.name}: control option calc_method='{cm}' names a CPU path of the reference; "
+                "pywatershed_b200 computes with calc_method='cuda'", UserWarning, stacklevel=3)
         self._calc_method = "cuda"
 
     def _n_units(self, var):

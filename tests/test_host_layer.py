@@ -391,3 +391,99 @@ def test_model_from_yaml_builds(drb, tmp_path):
     (tmp_path / "bad.yaml").write_text("control: control.yaml\nx:\n  class: PRMSEt\n  parameters: myparam.param\n")
     with pytest.raises(NotImplementedError):
         pwsb.Model.from_yaml(tmp_path / "bad.yaml")
+
+
+# ---------------------------------------------------------------- netCDF-4 (HDF5) inputs
+REF_TEST_DRB = pl.Path("/root/reference/test_data/drb_2yr")
+needs_ref_nc = pytest.mark.skipif(not (REF_TEST_DRB / "parameters_PRMSSnow.nc").exists(),
+                                  reason="reference netCDF files absent")
+
+
+@needs_ref_nc
+def test_hdf5_reader_on_the_reference_parameter_files(drb):
+    """The reference's per-process parameter files (netCDF-4 = HDF5: superblock
+    v2, dense links in a fractal heap, dense attributes) read by our own reader
+    equal the PRMS ASCII parameter file value for value."""
+    from pywatershed_b200 import Parameters
+    from pywatershed_b200.netcdf_out import nc4_module
+
+    assert nc4_module() is None  # this container has no netCDF4: the HDF5 reader is what runs
+    p, f, start = drb
+    checked = 0
+    for fn in sorted(REF_TEST_DRB.glob("parameters_*.nc")):
+        par = Parameters.from_netcdf(fn)
+        assert par.dims.get("nhru", 765) == 765 and par.dims.get("nsegment", 456) == 456
+        for k, v in par.to_dict().items():
+            if k in p:
+                np.testing.assert_array_equal(np.asarray(v).squeeze(), np.asarray(p[k]).squeeze(), err_msg=k)
+                checked += 1
+        if fn.name == "parameters_PRMSSnow.nc":
+            assert par.metadata["tmax_allsnow"]["dims"] == ("nmonth", "nhru")
+            assert par.metadata["snarea_curve"]["dims"] == ("ndeplval",)
+    assert checked > 150
+
+
+@needs_ref_nc
+def test_hdf5_reader_on_the_reference_forcing_files(drb):
+    """prcp.nc / tmax.nc / tmin.nc: chunked + shuffle + deflate float32 [time,
+    nhm_id] with a CF time axis; equal to the CBH ASCII values rounded to f32."""
+    from pywatershed_b200.netcdf_in import open_netcdf, read_time_variable
+
+    p, f, start = drb
+    for k in ("prcp", "tmax", "tmin"):
+        times, vals = read_time_variable(REF_TEST_DRB / f"{k}.nc", k)
+        assert times[0] == np.datetime64(start) and times[-1] == np.datetime64(start) + 730
+        assert vals.dtype == np.float64 and vals.shape == (731, 765)
+        np.testing.assert_array_equal(vals.astype(np.float32), f[k].astype(np.float32))
+    with open_netcdf(REF_TEST_DRB / "prcp.nc") as ds:
+        assert ds.dims == {"nhm_id": 765, "time": 731}
+        assert ds.variables["prcp"].dims == ("time", "nhm_id")
+        assert ds.variables["prcp"].attrs["units"] == "in"
+        np.testing.assert_array_equal(ds.variables["nhm_id"].read(), p["nhm_id"])
+    # test_data/hru_1/cbh.nc: eight variables in one file, unlimited time axis, `datetime` coordinate
+    hru1 = REF_TEST_DRB.parent / "hru_1" / "cbh.nc"
+    times, vals = read_time_variable(hru1, "tmax")
+    assert vals.shape == (14975, 1) and times[0] == np.datetime64("1979-01-01") and \
+        times[-1] == np.datetime64("2019-12-31")
+    z = np.load(scenarios.GOLDEN / "hru1_inputs.npz")
+    np.testing.assert_array_equal(vals.astype(np.float32), z["tmax"].astype(np.float32))
+
+
+@needs_ref_nc
+def test_model_from_the_reference_yaml(drb):
+    """Model.from_yaml on the reference's OWN test_data/drb_2yr/nhm_model.yaml
+    (control yaml + netCDF-4 discretization / parameter files), unmodified."""
+    import pywatershed_b200 as pwsb
+
+    p, f, start = drb
+    md = pwsb.Model.model_dict_from_yaml(REF_TEST_DRB / "nhm_model.yaml")
+    md["control"].options["input_dir"] = REF_TEST_DRB  # as autotest/test_prms_above_snow.py:128-170 does
+    with pytest.warns(UserWarning, match="calc_method='numba'"):  # the reference's control asks for numba
+        m = pwsb.Model(md)
+    assert m._mode == "chain+channel" and len(m.processes) == 8
+    assert m.processes["PRMSSnow"]._calc_method == "cuda"
+    # the forcings the engine would be given: input_dir/<name>.nc, sliced to the control period
+    for k in ("prcp", "tmax", "tmin"):
+        a = m._load_input(k, 765)
+        assert a.dtype == np.float64 and a.shape == (731, 765)
+        np.testing.assert_array_equal(a.astype(np.float32), f[k].astype(np.float32))
+    assert m.control.n_times == 731 and m.control.options["dprst_flag"] is True
+    for k in ("soil_moist_max", "tmax_cbh_adj", "tosegment", "snarea_curve", "hru_segment", "mann_n"):
+        np.testing.assert_array_equal(np.asarray(m._param_dict[k]).squeeze(), np.asarray(p[k]).squeeze(),
+                                      err_msg=k)
+
+
+@needs_ref_files
+def test_control_prms_to_yaml_round_trip(tmp_path):
+    """autotest/test_control.py:203-211."""
+    from pywatershed_b200 import Control
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        c = Control.load_prms(REF_DRB / "nhm.control", warn_unused_options=False)
+    c.to_yaml(tmp_path / "control.yaml")
+    c2 = Control.from_yaml(tmp_path / "control.yaml")
+    a, b = c.to_dict(), c2.to_dict()
+    a["options"] = {k: (str(v) if isinstance(v, pl.Path) else v) for k, v in a["options"].items()}
+    b["options"] = {k: (str(v) if isinstance(v, pl.Path) else v) for k, v in b["options"].items()}
+    np.testing.assert_equal(a, b)
