@@ -556,3 +556,62 @@ def test_missing_parameter_and_bad_option_raise(drb):
     q["albset_rna"] = np.full(p["hru_area"].shape[0], 0.8)
     with pytest.raises(ValueError, match="scalar"):
         Engine(q, start)
+
+
+@pytest.mark.parametrize("ntile,nhru_keep,nd,outputs", [(1, 257, 7, "full"), (2, None, 5, "full"),
+                                                       (1, 31, 9, "select"), (2, 1000, 3, "select")])
+def test_output_writes_stay_inside_their_buffers(drb, ntile, nhru_keep, nd, outputs):
+    """Guard bands around every device buffer the library writes into (HRU f64 /
+    i32 outputs, segment outputs) and reads from (forcings): after a run the
+    bands still hold their sentinel and the interior equals a run into exact-size
+    buffers.  Odd sizes so that the last CTA, the last warp and the TMA fallback
+    are all exercised."""
+    import torch
+
+    p, f, start = drb
+    pt, ft = scenarios.tile(p, {k: v[:nd] for k, v in f.items()}, ntile, nhru_keep=nhru_keep)
+    dev = torch.device("cuda:0")
+    e = _engine(pt, start)
+    if outputs == "select":
+        e.select_outputs(["pkwater_equiv", "soil_moist", "transp_on", "sroff_vol", "pptmix"], ["seg_outflow"])
+    nh, ns = e.nhru, e.nseg
+    nf, ni, nsv = len(e.sel_f64), len(e.sel_i32), len(e.sel_seg)
+    G = 4099  # guard elements on both sides (odd: the interior is not 16-byte aligned for i32)
+
+    def guarded(n, dtype, fill):
+        t = torch.full((n + 2 * G,), fill, dtype=dtype, device=dev)
+        return t, t[G:G + n]
+
+    SENT_F, SENT_I = -7.25e300, -1234567
+    of_all, of = guarded(nd * nf * nh, torch.float64, SENT_F)
+    oi_all, oi = guarded(nd * max(ni, 1) * nh, torch.int32, SENT_I)
+    os_all, osg = guarded(nd * nsv * ns, torch.float64, SENT_F)
+    forc = {}
+    for k in ("prcp", "tmax", "tmin"):
+        full, inner = guarded(nd * nh, torch.float64, float("nan"))  # a read outside would poison the results
+        inner.copy_(torch.from_numpy(np.ascontiguousarray(ft[k])).reshape(-1))
+        forc[k] = (full, inner)
+    viol = np.zeros((nd, 6), dtype=np.int32)
+    torch.cuda.synchronize()
+    e.run_device(nd, forc["prcp"][1].data_ptr(), forc["tmax"][1].data_ptr(), forc["tmin"][1].data_ptr(),
+                 of.data_ptr(), oi.data_ptr(), osg.data_ptr(), viol=viol)
+    for t_all, sent in ((of_all, SENT_F), (oi_all, SENT_I), (os_all, SENT_F)):
+        assert bool((t_all[:G] == sent).all()) and bool((t_all[-G:] == sent).all())
+    assert not bool((of == SENT_F).any()) and not bool((osg == SENT_F).any())
+    if ni:
+        assert not bool((oi[:nd * ni * nh] == SENT_I).any())
+    # the same run through the host entry point into exact-size buffers
+    e2 = _engine(pt, start)
+    if outputs == "select":
+        e2.select_outputs(["pkwater_equiv", "soil_moist", "transp_on", "sroff_vol", "pptmix"], ["seg_outflow"])
+    ref, rviol = e2.run_host(ft["prcp"], ft["tmax"], ft["tmin"])
+    got_f = of.reshape(nd, nf, nh).cpu().numpy()
+    for j, name in enumerate(e.sel_f64):
+        np.testing.assert_array_equal(got_f[:, j], ref[name], err_msg=name)
+    got_i = oi[:nd * ni * nh].reshape(nd, ni, nh).cpu().numpy() if ni else None
+    for j, name in enumerate(e.sel_i32):
+        np.testing.assert_array_equal(got_i[:, j], np.asarray(ref[name], dtype=np.int32), err_msg=name)
+    got_s = osg.reshape(nd, nsv, ns).cpu().numpy()
+    for j, name in enumerate(e.sel_seg):
+        np.testing.assert_array_equal(got_s[:, j], ref[name], err_msg=name)
+    np.testing.assert_array_equal(viol, rviol)
