@@ -43,6 +43,25 @@
 
 namespace pws {
 
+// a / b that skips the division when a is zero.  IEEE: (+-0) / b = +-0 for
+// every b > 0 (NaN and b <= 0 fall through to the division), so the result is
+// bit-identical.  CUDA's fp64 division leaves its inline fast path for an
+// out-of-line subroutine (~75 instructions) when the numerator is zero, and on
+// dry days most numerators of the runoff / soilzone fluxes are: ncu counted 5
+// such calls per HRU-day before this guard.
+PWS_HD double div0(double a, double b) {
+  if (a == 0.0 && b > 0.0) return a;
+#ifdef __CUDA_ARCH__
+  // volatile: otherwise the compiler divides unconditionally and selects afterwards
+  double q;
+  asm volatile("div.rn.f64 %0, %1, %2;" : "=d"(q) : "d"(a), "d"(b));
+  return q;
+#else
+  return a / b;
+#endif
+}
+
+
 // constants.py:30-44
 #define PWS_NEARZERO 1.0e-6
 #define PWS_DNEARZERO 2.23e-16
@@ -297,7 +316,7 @@ PWS_DEV void check_capacity(double soil_moist_prev, double soil_moist_max,
 PWS_DEV double dprst_area(double vol, double vol_max, double area_max, double va_exp) {
   double area = 0.0;
   if (vol > 0.0) {
-    const double r = vol / vol_max;
+    const double r = div0(vol, vol_max);
     double frac;
     if (r < PWS_NEARZERO) frac = 0.0;
     else if (r > 1.0) frac = 1.0;
@@ -320,7 +339,7 @@ PWS_DEV bool compute_interflow(double coef_lin, double coef_sq, double ssres_in,
     flow = ssres_in * (1.0 - c2 / coef_lin) + storage * c2;
   } else if (coef_sq > 0.0) {
     const double c3 = sqrt(coef_lin * coef_lin + 4.0 * coef_sq * ssres_in);
-    const double sos = storage - ((c3 - coef_lin) / (2.0 * coef_sq));
+    const double sos = storage - div0(c3 - coef_lin, 2.0 * coef_sq);
     if (c3 == 0.0) return false;
     const double c1 = coef_sq * sos / c3;
     const double c2 = 1.0 - exp(-c3);
@@ -1384,7 +1403,7 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, State& s,
           dprst_srp = dprst_srp + PER_AREA(v);
           s.dprst_vol_clos = s.dprst_vol_clos + v;
         }
-        srp = srp - dprst_srp / perv_frac;
+        srp = srp - div0(dprst_srp, perv_frac);
         if (srp < 0.0) srp = 0.0;
       }
       if (sri > 0.0) {
@@ -1399,7 +1418,7 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, State& s,
           dprst_sri = dprst_sri + PER_AREA(v);
           s.dprst_vol_clos = s.dprst_vol_clos + v;
         }
-        sri = sri - dprst_sri / imperv_frac;
+        sri = sri - div0(dprst_sri, imperv_frac);
         if (sri < 0.0) sri = 0.0;
       }
       dprst_insroff_hru = dprst_srp + dprst_sri;
@@ -1458,10 +1477,10 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, State& s,
         dprst_seep_hru = dprst_seep_hru + PER_AREA(seep_clos);
       }
       avail_et = avail_et - dprst_evap_hru;
-      if (vol_open_max > 0.0) dprst_vol_open_frac = s.dprst_vol_open / vol_open_max;
-      if (vol_clos_max > 0.0) dprst_vol_clos_frac = s.dprst_vol_clos / vol_clos_max;
+      if (vol_open_max > 0.0) dprst_vol_open_frac = div0(s.dprst_vol_open, vol_open_max);
+      if (vol_clos_max > 0.0) dprst_vol_clos_frac = div0(s.dprst_vol_clos, vol_clos_max);
       if (vol_open_max + vol_clos_max > 0.0)
-        dprst_vol_frac = (s.dprst_vol_open + s.dprst_vol_clos) / (vol_open_max + vol_clos_max);
+        dprst_vol_frac = div0(s.dprst_vol_open + s.dprst_vol_clos, vol_open_max + vol_clos_max);
       dprst_stor_hru = PER_AREA(s.dprst_vol_open + s.dprst_vol_clos);
       runoff = runoff + dprst_sroff_hru * hru_area;
       // the public dprst_area_clos never changes after init
@@ -1480,7 +1499,7 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, State& s,
         if (snowcov_area < 1.0) {
           if (potet < s.imperv_stor) imperv_evap = potet * (1.0 - snowcov_area);
           else imperv_evap = s.imperv_stor * (1.0 - snowcov_area);
-          if (imperv_evap * imperv_frac > avail_et) imperv_evap = avail_et / imperv_frac;
+          if (imperv_evap * imperv_frac > avail_et) imperv_evap = div0(avail_et, imperv_frac);
           s.imperv_stor = s.imperv_stor - imperv_evap;
         }
         hru_impervevap = imperv_evap * imperv_frac;
@@ -1489,7 +1508,7 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, State& s,
           hru_impervevap = hru_impervevap + avail_et;
           if (hru_impervevap < 0.0) hru_impervevap = 0.0;
           imperv_evap = imperv_evap / imperv_frac;
-          s.imperv_stor = s.imperv_stor - avail_et / imperv_frac;
+          s.imperv_stor = s.imperv_stor - div0(avail_et, imperv_frac);
           avail_et = 0.0;
         }
         s.hru_impervstor = s.imperv_stor * imperv_frac;
@@ -1546,7 +1565,7 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, State& s,
     const double snow_free = 1.0 - snowcov_area;
     double dunnianflw_pfr = 0.0, dunnianflw_gvr = 0.0, prefflow = 0.0;
     double avail_potet = fmax(0.0, potet - hru_actet);
-    double capwater_maxin = infil_hru / hru_frac_perv;
+    double capwater_maxin = div0(infil_hru, hru_frac_perv);
     const double pref_flow_infil_frac = PWS_LD(P.pref_flow_infil_frac + i);
     if (pref_flow_infil_frac != 0.0) {
       if (capwater_maxin > 0.0) {
@@ -1575,7 +1594,7 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, State& s,
           excess = excess - soil_to_gw;
         }
         if (excess > (wat * hru_frac_perv)) wat = 0.0;
-        else wat = wat - (excess / hru_frac_perv);
+        else wat = wat - div0(excess, hru_frac_perv);
         soil_to_ssr = fmax(0.0, excess);
       }
       cap_waterin = wat * hru_frac_perv;
@@ -1636,8 +1655,8 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, State& s,
         et_type = snow_free < 0.01 ? 1 : 2;
       }
       if (et_type != 1) {
-        const double pcts = s.soil_moist / soil_moist_max;
-        const double pctr = s.soil_rechr / soil_rechr_max;
+        const double pcts = div0(s.soil_moist, soil_moist_max);
+        const double pctr = div0(s.soil_rechr, soil_rechr_max);
         potet_lower = avail_potet;
         potet_rechr = avail_potet;
         const int soil_type = PWS_LD(P.soil_type + i);
@@ -1734,7 +1753,7 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, State& s,
   PWS_F(soil_lower_change, soil_lower_change);
   PWS_F(soil_lower_change_hru, soil_lower_change_hru);
   PWS_F(soil_lower_prev, soil_lower_prev);
-  PWS_F(soil_lower_ratio, soil_lower_max > 0.0 ? soil_lower / soil_lower_max
+  PWS_F(soil_lower_ratio, soil_lower_max > 0.0 ? div0(soil_lower, soil_lower_max)
                                                  : PWS_LD(P.soil_lower_ratio_init + i));
   PWS_F(soil_lower_max, soil_lower_max); PWS_F(soil_moist, s.soil_moist);
   PWS_F(soil_moist_tot, ssres_stor + s.soil_moist * hru_frac_perv);
@@ -1791,7 +1810,7 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, State& s,
   const double ch_gwres = has_seg ? gwres_flow_vol : 0.0;
   PWS_F(channel_sroff_vol, ch_sroff); PWS_F(channel_ssres_flow_vol, ch_ssres);
   PWS_F(channel_gwres_flow_vol, ch_gwres);
-  out.lateral((ch_sroff + ch_ssres + ch_gwres) / 86400.0);
+  out.lateral(div_r(ch_sroff + ch_ssres + ch_gwres, 86400.0, 1.0 / 86400.0));
 }
 
 #undef PER_AREA

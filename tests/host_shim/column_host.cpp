@@ -48,6 +48,10 @@ extern "C" {
 void shim_div_r(const double* a, const double* b, int64_t n, double* out) {
   for (int64_t k = 0; k < n; ++k) out[k] = pws::div_r(a[k], b[k], 1.0 / b[k]);
 }
+// the zero-numerator guard of the runoff / soilzone divisions
+void shim_div0(const double* a, const double* b, int64_t n, double* out) {
+  for (int64_t k = 0; k < n; ++k) out[k] = pws::div0(a[k], b[k]);
+}
 // Muskingum sub-daily division, exposed for tests/test_column_host.py
 void shim_div_by_ts(const double* x, int64_t n, double ts, double* out) {
   const double r = 1.0 / ts;

@@ -130,7 +130,36 @@ def test_div_r_is_the_division(shim):
     b = rng.lognormal(0.0, 8.0, n)
     b[: n // 4] = np.nextafter(2.0 ** rng.integers(-20, 20, n // 4), 0.0)  # all-ones significands
     a[::1000] = 0.0
+    b[1::7] = 86400.0  # seconds per day: the lateral-inflow conversion (prms_channel.py:423-425)
     out = np.empty_like(a)
     shim.shim_div_r.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     shim.shim_div_r(a.ctypes.data, b.ctypes.data, n, out.ctypes.data)
     np.testing.assert_array_equal(out, a / b)
+    assert np.array_equal(np.signbit(out[a == 0.0]), np.signbit((a / b)[a == 0.0]))
+
+
+def test_div0_is_the_division(shim):
+    """div0 skips the division for a zero numerator and a positive divisor:
+    same bits as IEEE division for zeros of either sign, zero / negative /
+    infinite / NaN divisors, and ordinary operands."""
+    rng = np.random.default_rng(5)
+    n = 200_000
+    a = rng.lognormal(0.0, 10.0, n) * rng.choice([-1.0, 1.0], n)
+    b = rng.lognormal(0.0, 8.0, n) * rng.choice([-1.0, 1.0], n)
+    a[::3] = 0.0
+    a[1::30] = -0.0
+    b[::11] = 0.0
+    b[5::101] = -0.0
+    b[7::103] = np.inf
+    b[9::107] = -np.inf
+    b[13::109] = np.nan
+    a[17::113] = np.nan
+    a[19::127] = np.inf
+    out = np.empty_like(a)
+    shim.shim_div0.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    shim.shim_div0(a.ctypes.data, b.ctypes.data, n, out.ctypes.data)
+    with np.errstate(all="ignore"):
+        ref = a / b
+    assert np.array_equal(np.isnan(out), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    np.testing.assert_array_equal(out[ok].view(np.uint64), ref[ok].view(np.uint64))  # incl. the sign of zero
