@@ -75,16 +75,20 @@ class Budget:
     def advance(self):
         pass
 
+    def block_terms(self, block: dict, dt_days: float):
+        """(component, term, [ndays, n] array, dt) for every budget term present in `block`."""
+        return [(c, v, block[v], dt_days) for c in self.components for v in self.terms[c] if v in block]
+
+    def accumulate_term(self, c, v, arr, dt_days: float):
+        """Add a block [ndays, n] of one term (times the step in days,
+        base/budget.py:262-269) to its accumulation."""
+        add = np.asarray(arr, dtype=np.float64).sum(axis=0) * dt_days
+        cur = self._accumulations[c][v]
+        self._accumulations[c][v] = add if cur is None else cur + add
+
     def accumulate_block(self, block: dict, dt_days: float):
-        """Add a whole block [ndays, n] of each term (times the step in days,
-        base/budget.py:262-269) to the accumulations."""
-        for c in self.components:
-            for v in self.terms[c]:
-                if v not in block:
-                    continue
-                add = np.asarray(block[v], dtype=np.float64).sum(axis=0) * dt_days
-                cur = self._accumulations[c][v]
-                self._accumulations[c][v] = add if cur is None else cur + add
+        for a in self.block_terms(block, dt_days):
+            self.accumulate_term(*a)
 
     def calculate(self, n_violations: int | None = None):
         """Verdict for the current day.  `n_violations` = the device's count of

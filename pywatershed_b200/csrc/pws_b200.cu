@@ -1192,20 +1192,36 @@ extern "C" int pws_run_host(pws_handle* h, int ndays, const int32_t* h_cal, cons
   if (ensure_scratch(h, T)) return 1;
   const bool want_f64 = h->n_f64 > 0 && h_out_f64, want_i32 = h->n_i32 > 0 && h_out_i32;
   const bool want_seg = h->n_seg_sel > 0 && h->nseg > 0 && h_seg_out;
-  const bool staged = !(is_pinned(h_prcp) && is_pinned(h_tmax) && is_pinned(h_tmin) &&
-                        is_pinned(want_f64 ? h_out_f64 : nullptr) &&
-                        is_pinned(want_i32 ? h_out_i32 : nullptr) &&
-                        is_pinned(want_seg ? h_seg_out : nullptr));
-  if (staged && (h->stage_days < h->ring_days || h->stage_f64_elems < h->ring_f64_elems ||
-                 h->stage_i32_elems < h->ring_i32_elems || h->stage_seg_elems < h->ring_seg_elems)) {
-    free_stage(h);
+  // Pageable caller buffers are staged through pinned slots, inputs and outputs
+  // independently (a Model keeps its forcings in ordinary numpy arrays but can
+  // hand in page-locked result buffers).
+  const bool stage_in = !(is_pinned(h_prcp) && is_pinned(h_tmax) && is_pinned(h_tmin));
+  const bool stage_out = !(is_pinned(want_f64 ? h_out_f64 : nullptr) &&
+                           is_pinned(want_i32 ? h_out_i32 : nullptr) &&
+                           is_pinned(want_seg ? h_seg_out : nullptr));
+  if (stage_in && h->stage_days < h->ring_days) {
     for (int b = 0; b < 2; ++b) {
+      cudaFreeHost(h->hs_in[b]);
+      h->hs_in[b] = nullptr;
+    }
+    h->stage_days = 0;
+    for (int b = 0; b < 2; ++b)
       PWS_CUDA(h, cudaHostAlloc(&h->hs_in[b], (size_t)h->ring_days * 3 * n * sizeof(double), 0));
+    h->stage_days = h->ring_days;
+  }
+  if (stage_out && (h->stage_f64_elems < h->ring_f64_elems || h->stage_i32_elems < h->ring_i32_elems ||
+                    h->stage_seg_elems < h->ring_seg_elems)) {
+    for (int b = 0; b < 2; ++b) {
+      cudaFreeHost(h->hs_of[b]); h->hs_of[b] = nullptr;
+      cudaFreeHost(h->hs_oi[b]); h->hs_oi[b] = nullptr;
+      cudaFreeHost(h->hs_os[b]); h->hs_os[b] = nullptr;
+    }
+    h->stage_f64_elems = h->stage_i32_elems = h->stage_seg_elems = 0;
+    for (int b = 0; b < 2; ++b) {
       PWS_CUDA(h, cudaHostAlloc(&h->hs_of[b], h->ring_f64_elems * sizeof(double), 0));
       PWS_CUDA(h, cudaHostAlloc(&h->hs_oi[b], h->ring_i32_elems * sizeof(int32_t), 0));
       PWS_CUDA(h, cudaHostAlloc(&h->hs_os[b], h->ring_seg_elems * sizeof(double), 0));
     }
-    h->stage_days = h->ring_days;
     h->stage_f64_elems = h->ring_f64_elems;
     h->stage_i32_elems = h->ring_i32_elems;
     h->stage_seg_elems = h->ring_seg_elems;
@@ -1241,9 +1257,10 @@ extern "C" int pws_run_host(pws_handle* h, int ndays, const int32_t* h_cal, cons
     const int d0 = blk * T;
     const int nd = std::min(T, ndays - d0);
     const double* srcs[3] = {h_prcp + (size_t)d0 * n, h_tmax + (size_t)d0 * n, h_tmin + (size_t)d0 * n};
-    if (staged) {
-      // slot b: block blk-2 must have drained before its stage buffers are reused
-      if (blk >= 2 && drain_stage(blk - 2)) return 1;
+    // slot b: block blk-2 must have drained before its stage buffers are reused
+    if (stage_out && blk >= 2 && drain_stage(blk - 2)) return 1;
+    if (stage_in) {
+      if (blk >= 2) PWS_CUDA(h, cudaEventSynchronize(h->ev_h2d[b]));  // hs_in[b] has been uploaded
       for (int k = 0; k < 3; ++k) {
         par_memcpy(h->hs_in[b] + (size_t)k * RT * n, srcs[k], (size_t)nd * n * sizeof(double));
         srcs[k] = h->hs_in[b] + (size_t)k * RT * n;
@@ -1271,15 +1288,15 @@ extern "C" int pws_run_host(pws_handle* h, int ndays, const int32_t* h_cal, cons
     PWS_CUDA(h, cudaEventRecord(h->ev_comp[b], h->s_compute));
     PWS_CUDA(h, cudaStreamWaitEvent(h->s_d2h, h->ev_comp[b], 0));
     if (want_f64)
-      PWS_CUDA(h, cudaMemcpyAsync(staged ? h->hs_of[b] : h_out_f64 + (size_t)d0 * h->n_f64 * n,
+      PWS_CUDA(h, cudaMemcpyAsync(stage_out ? h->hs_of[b] : h_out_f64 + (size_t)d0 * h->n_f64 * n,
                                   h->d_of64[b], (size_t)nd * h->n_f64 * n * sizeof(double),
                                   cudaMemcpyDeviceToHost, h->s_d2h));
     if (want_i32)
-      PWS_CUDA(h, cudaMemcpyAsync(staged ? h->hs_oi[b] : h_out_i32 + (size_t)d0 * h->n_i32 * n,
+      PWS_CUDA(h, cudaMemcpyAsync(stage_out ? h->hs_oi[b] : h_out_i32 + (size_t)d0 * h->n_i32 * n,
                                   h->d_oi32[b], (size_t)nd * h->n_i32 * n * sizeof(int32_t),
                                   cudaMemcpyDeviceToHost, h->s_d2h));
     if (want_seg)
-      PWS_CUDA(h, cudaMemcpyAsync(staged ? h->hs_os[b] : h_seg_out + (size_t)d0 * h->n_seg_sel * h->nseg,
+      PWS_CUDA(h, cudaMemcpyAsync(stage_out ? h->hs_os[b] : h_seg_out + (size_t)d0 * h->n_seg_sel * h->nseg,
                                   h->d_oseg[b], (size_t)nd * h->n_seg_sel * h->nseg * sizeof(double),
                                   cudaMemcpyDeviceToHost, h->s_d2h));
     PWS_CUDA(h, cudaEventRecord(h->ev_d2h[b], h->s_d2h));
@@ -1287,7 +1304,7 @@ extern "C" int pws_run_host(pws_handle* h, int ndays, const int32_t* h_cal, cons
     // enqueue reuses them in stream order on s_compute, which is safe; h_cal is
     // the caller's full-run array and stays valid.
   }
-  if (staged)
+  if (stage_out)
     for (int blk = std::max(0, nblocks - 2); blk < nblocks; ++blk)
       if (drain_stage(blk)) return 1;
   const int rc = pws_sync(h);

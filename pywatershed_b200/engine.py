@@ -286,25 +286,26 @@ class Engine:
         if not (prcp.shape == tmax.shape == tmin.shape == (nd, self.nhru)):
             raise ValueError("forcings must be [ndays, nhru]")
         cal = calendar(self.start + self.day, nd)
-        if pinned_outputs:
-            import torch
-
-            def alloc(shape, dt):
-                return torch.empty(shape, dtype=dt).pin_memory().numpy()
-            of = alloc((nd, len(self.sel_f64), self.nhru), torch.float64)
-            oi = alloc((nd, len(self.sel_i32), self.nhru), torch.int32)
-            os_ = alloc((nd, len(self.sel_seg), self.nseg), torch.float64)
+        shapes = ((nd, len(self.sel_f64), self.nhru), (nd, len(self.sel_i32), self.nhru),
+                  (nd, len(self.sel_seg), self.nseg))
+        key = (shapes, bool(pinned_outputs))
+        cache = getattr(self, "_out_cache", None)
+        if reuse_buffers and cache is not None and cache[0] == key:
+            of, oi, os_ = cache[1]
         else:
-            shapes = ((nd, len(self.sel_f64), self.nhru), (nd, len(self.sel_i32), self.nhru),
-                      (nd, len(self.sel_seg), self.nseg))
-            cache = getattr(self, "_out_cache", None)
-            if reuse_buffers and cache is not None and cache[0] == shapes:
-                of, oi, os_ = cache[1]
+            if pinned_outputs:
+                import torch
+
+                def alloc(shape, dt):
+                    return torch.empty(shape, dtype=dt).pin_memory().numpy()
+                of = alloc(shapes[0], torch.float64)
+                oi = alloc(shapes[1], torch.int32)
+                os_ = alloc(shapes[2], torch.float64)
             else:
                 of = np.empty(shapes[0])
                 oi = np.empty(shapes[1], dtype=np.int32)
                 os_ = np.empty(shapes[2])
-                self._out_cache = (shapes, (of, oi, os_)) if reuse_buffers else None
+            self._out_cache = (key, (of, oi, os_)) if reuse_buffers else None
         viol = np.zeros((nd, 6), dtype=np.int32) if budgets else None
         self._check(self.L.pws_run_host(
             self.h, nd, cal.ctypes.data, prcp.ctypes.data, tmax.ctypes.data, tmin.ctypes.data,

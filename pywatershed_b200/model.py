@@ -366,18 +366,27 @@ class Model:
             f = self._forcings
             # the block's arrays are consumed before the next block is computed
             blk, viol = eng.run_host(f["prcp"][t0:t0 + n], f["tmax"][t0:t0 + n], f["tmin"][t0:t0 + n],
-                                     reuse_buffers=True)
+                                     pinned_outputs=True, reuse_buffers=True)
         self._block, self._block_t0, self._block_n, self._block_viol = blk, t0, n, viol
-        # all-time variables of Atmosphere: fill the rows of this block
+        # all-time variables of Atmosphere: fill the rows of this block; budget terms: add
+        # the block to the accumulations.  Plain copies and sums over [n, nhru] arrays --
+        # numpy releases the GIL for them, so a few threads share the memory traffic.
+        jobs = []
         if "PRMSAtmosphere" in self.processes:
             atm = self.processes["PRMSAtmosphere"]
             for var in atm.get_variables():
                 if var in blk:
-                    atm[var].data[t0:t0 + n] = blk[var]
+                    jobs.append((_copy_rows, (atm[var].data, t0, n, blk[var])))
         dt = float(self.control.time_step / np.timedelta64(1, "D"))
         for name, proc in self.processes.items():
             if getattr(proc, "budget", None) is not None:
-                proc.budget.accumulate_block(blk, dt)
+                jobs.extend((proc.budget.accumulate_term, a) for a in proc.budget.block_terms(blk, dt))
+        big = n * max(self._engine.nhru, 1) >= 1 << 18
+        if big and len(jobs) > 1:
+            list(_pool().map(lambda j: j[0](*j[1]), jobs))
+        else:
+            for fn, a in jobs:
+                fn(*a)
 
     def _channel_block(self, t0, n):
         import torch
@@ -564,6 +573,24 @@ class Model:
         path.write_text(yaml.safe_dump({
             "start_time": str(self.control.start_time), "end_time": str(self.control.end_time),
             "time_step": str(self.control.time_step), "options": opts}))
+
+
+def _copy_rows(dst, t0, n, src):
+    dst[t0:t0 + n] = src
+
+
+_POOL = None
+
+
+def _pool():
+    """A small thread pool for the per-block host copies / sums of Model."""
+    global _POOL
+    if _POOL is None:
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+
+        _POOL = ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 2) // 2)))
+    return _POOL
 
 
 def _read_netcdf_var(path, name):

@@ -23,6 +23,25 @@ from .budget import Budget
 _DTYPES = {"float64": np.float64, "int32": np.int32, "bool": np.bool_, "int64": np.int64}
 
 
+def _full(shape, fill, dtype):
+    """np.full; large arrays (GBs at CONUS size) are first touched by a few threads."""
+    a = np.empty(shape, dtype=dtype)
+    if a.nbytes < (64 << 20):
+        a[...] = fill
+        return a
+    from concurrent.futures import ThreadPoolExecutor
+
+    nthr = 8
+    step = -(-shape[0] // nthr)
+
+    def fill_rows(k):
+        a[k * step:(k + 1) * step] = fill
+
+    with ThreadPoolExecutor(max_workers=nthr) as ex:
+        list(ex.map(fill_rows, range(nthr)))
+    return a
+
+
 class TimeseriesArray:
     """All-time variable with a `.current` row (base/timeseries.py:8-70).
 
@@ -302,7 +321,7 @@ class PRMSAtmosphere(Process):
             fill = init[var]
             if dt is not np.float64 and isinstance(fill, float) and np.isnan(fill):
                 fill = 0
-            self._vars[var] = TimeseriesArray(self.control, var, np.full((nt, self.nhru), fill, dtype=dt))
+            self._vars[var] = TimeseriesArray(self.control, var, _full((nt, self.nhru), fill, dt))
 
 
 class PRMSCanopy(ConservativeProcess):
