@@ -101,9 +101,11 @@ int pws_run_device(pws_handle *h, int ndays, const int32_t *h_cal,
                    double *d_out_f64, int32_t *d_out_i32, double *d_seg_out,
                    int32_t *h_budget_viol);
 
-/* forcings and outputs in host memory: staged through pinned-memory rings in
- * time blocks, H2D / compute / D2H overlapped on three streams; returns when
- * the last block has been drained */
+/* forcings and outputs in host memory, processed in time blocks with H2D /
+ * compute / D2H overlapped on three streams; returns when the last block has
+ * been drained.  Page-locked caller buffers are used directly; pageable ones
+ * are staged through the library's own pinned slots (inputs and outputs
+ * independently). */
 int pws_run_host(pws_handle *h, int ndays, const int32_t *h_cal,
                  const double *h_prcp, const double *h_tmax, const double *h_tmin,
                  double *h_out_f64, int32_t *h_out_i32, double *h_seg_out,
