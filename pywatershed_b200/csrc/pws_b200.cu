@@ -904,6 +904,14 @@ static int ensure_scratch(pws_handle* h, int ndays) {
   return 0;
 }
 
+// shared-memory carve-out (percent of the 228 KB maximum) that holds the
+// resident CTAs of k_hru_column<., H> (1 KB per CTA is reserved by the system)
+static int column_carveout_pct(int H) {
+  const size_t per_cta = column_smem_bytes(H) + 1024;
+  const size_t ctas = std::max<size_t>(1, std::min<size_t>((228 * 1024) / per_cta, 65536 / (2 * H * 128)));
+  return (int)std::min<size_t>(100, (per_cta * ctas * 100 + 228 * 1024 - 1) / (228 * 1024));
+}
+
 static cudaEvent_t new_event(pws_handle* /*h*/) {
   cudaEvent_t e = nullptr;
   cudaEventCreate(&e);
@@ -1013,6 +1021,10 @@ static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const d
       PWS_CUDA(h, cudaFuncSetAttribute(k_hru_column<MODE, HH>,                                   \
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,              \
                                        (int)column_smem_bytes(HH)));                             \
+      /* no more shared memory than the CTAs of one SM need: the rest is L1 */                   \
+      PWS_CUDA(h, cudaFuncSetAttribute(k_hru_column<MODE, HH>,                                   \
+                                       cudaFuncAttributePreferredSharedMemoryCarveout,           \
+                                       column_carveout_pct(HH)));                                \
       h->smem_attr_set[(MODE) * 2 + ((HH) == 128)] = true;                                       \
     }                                                                                            \
     k_hru_column<MODE, HH><<<grid, 2 * (HH), column_smem_bytes(HH), h->s_compute>>>(a);          \

@@ -42,21 +42,40 @@
 #ifndef PWS_COLUMN_MONTHLY_SMEM
 #define PWS_COLUMN_MONTHLY_SMEM 1
 #endif
-// 1: the lower half keeps its 10 prognostic values in shared memory instead of
-// registers (it is the critical path of the pipeline and spills otherwise)
+// The lower half is the critical path of the pipeline and spills at 120
+// registers.  1: all 10 of its prognostic values live in shared memory instead
+// of registers (20 KB, only fits with PWS_COLUMN_MONTHLY_SMEM 0); 2: the five
+// that are touched in one short stretch of the day (impervious and depression
+// storage) do, the five soil / groundwater stores stay in registers (10 KB:
+// the space a second forcing slot would take).
 #ifndef PWS_COLUMN_LOWER_STATE_SMEM
-#define PWS_COLUMN_LOWER_STATE_SMEM 0
+#define PWS_COLUMN_LOWER_STATE_SMEM 2
 #endif
+#define PWS_LOWER_STATE_IN_SMEM(X) \
+  X(imperv_stor) X(hru_impervstor) X(dprst_vol_open) X(dprst_vol_clos) X(dprst_area_open)
+#define PWS_LOWER_STATE_IN_REGS(X) \
+  X(soil_moist) X(soil_rechr) X(slow_stor) X(pref_flow_stor) X(gwres_stor)
 // Registers per thread of the two warp groups (setmaxnreg, multiples of 8;
 // with 256 HRUs per CTA, upper + lower must be <= 256).  Unconstrained, the
 // upper half wants 204 registers (29 prognostic values, the snow energy
 // balance) and the lower half 148.  Measured on the CONUS domain, ms per
-// 10-year pass: 104/152 142, 120/136 137, 128/128 131, 136/120 122, 144/112 130.
+// 10-year pass, all lower state in registers: 104/152 142, 120/136 137,
+// 128/128 131, 136/120 122, 144/112 130; with PWS_COLUMN_LOWER_STATE_SMEM 2
+// (and the later store / forcing-slot changes): 128/128 117, 136/120 109,
+// 144/112 104, 152/104 115, 160/96 117.
 #ifndef PWS_COLUMN_REGS_UPPER
-#define PWS_COLUMN_REGS_UPPER 136
+#define PWS_COLUMN_REGS_UPPER 144
 #endif
 #ifndef PWS_COLUMN_REGS_LOWER
-#define PWS_COLUMN_REGS_LOWER 120
+#define PWS_COLUMN_REGS_LOWER 112
+#endif
+
+// Cache hint of the output stores (PTX st.global.<hint>).  The 143 values a
+// thread writes per day must not displace the few spilled registers from the
+// 28 KB of L1 left beside the shared-memory carve-out.  CONUS domain, column
+// kernel ms per 10-year pass: cs 116.5, cg 121.5, wt 121.7, L1::no_allocate 112.5.
+#ifndef PWS_COLUMN_ST
+#define PWS_COLUMN_ST "L1::no_allocate"
 #endif
 
 namespace pws {
@@ -178,7 +197,7 @@ struct GpuSink {
       asm("mad.wide.u32 %0, %1, %2, %3;"
           : "=l"(addr)
           : "r"(stride8), "n"(slot), "l"((unsigned long long)pf));
-      if (live) asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(addr), "d"(v));
+      if (live) asm volatile("st.global." PWS_COLUMN_ST ".f64 [%0], %1;" ::"l"(addr), "d"(v));
     } else if constexpr (kMode == SINK_SELECT) {
       const int64_t o = a.off[var];
       if (o >= 0 && live) __stcs(reinterpret_cast<double*>(pf + o), v);
@@ -192,7 +211,7 @@ struct GpuSink {
       asm("mad.wide.u32 %0, %1, %2, %3;"
           : "=l"(addr)
           : "r"(stride4), "n"(slot), "l"((unsigned long long)pi));
-      if (live) asm volatile("st.global.cs.s32 [%0], %1;" ::"l"(addr), "r"(v));
+      if (live) asm volatile("st.global." PWS_COLUMN_ST ".s32 [%0], %1;" ::"l"(addr), "r"(v));
     } else if constexpr (kMode == SINK_SELECT) {
       const int64_t o = a.off[var];
       if (o >= 0 && live) __stcs(reinterpret_cast<int*>(pi + o), v);
@@ -241,22 +260,30 @@ constexpr int kLowerState = 0
 #undef X
     ;
 constexpr int kUpperMonStaged = PWS_COLUMN_MONTHLY_SMEM ? kUpperMonF64 : 0;
-constexpr int kLowerStateStaged = PWS_COLUMN_LOWER_STATE_SMEM ? kLowerState : 0;
+constexpr int kLowerStateSome = 0
+#define X(name) +1
+    PWS_LOWER_STATE_IN_SMEM(X)
+#undef X
+    ;
+constexpr int kLowerStateStaged =
+    PWS_COLUMN_LOWER_STATE_SMEM == 1 ? kLowerState : (PWS_COLUMN_LOWER_STATE_SMEM == 2 ? kLowerStateSome : 0);
 constexpr int kColF64 =
     kUpperF64 + kUpperMonStaged + kLowerF64 + kMidSlots * kMidF64 + kLowerStateStaged;
 constexpr int kColI32 = kUpperI32 + kLowerI32 + kMidSlots * kMidI32;
-// forcing stage of the upper half: 2 days x {prcp, tmax, tmin, soltab_potsw row,
-// soltab_horad_potsw row} x H, filled by TMA bulk copies, + 2 mbarriers
+// forcing stage of the upper half: one day x {prcp, tmax, tmin, soltab_potsw row,
+// soltab_horad_potsw row} x H, filled by TMA bulk copies, + its mbarrier.  A day's
+// five values are read into registers first thing in the morning, so the slot
+// can take the next day's rows while this day computes.
 constexpr int kForcRows = 5;
 template <int H>
 struct ColumnSmem {
   static constexpr size_t kParamBytes = (size_t)H * (kColF64 * 8 + kColI32 * 4);
-  static constexpr size_t kForcBytes = (size_t)2 * kForcRows * H * 8;
+  static constexpr size_t kForcBytes = (size_t)kForcRows * H * 8;
   static constexpr size_t kBytes = kParamBytes + kForcBytes + 16;
   static_assert(kParamBytes % 16 == 0, "forcing stage must be 16-byte aligned");
 };
 constexpr size_t column_smem_bytes(int H) {
-  return (size_t)H * (kColF64 * 8 + kColI32 * 4) + (size_t)2 * kForcRows * H * 8 + 16;
+  return (size_t)H * (kColF64 * 8 + kColI32 * 4) + (size_t)kForcRows * H * 8 + 16;
 }
 
 // named barriers of k_hru_column (0 is __syncthreads)
@@ -306,6 +333,15 @@ struct LowerStateRef {
   PWS_HRU_STATE_LOWER(X)
 #undef X
 };
+// ... or only part of it (PWS_COLUMN_LOWER_STATE_SMEM 2)
+struct LowerStateMixed {
+#define X(name) double& name;
+  PWS_LOWER_STATE_IN_SMEM(X)
+#undef X
+#define X(name) double name;
+  PWS_LOWER_STATE_IN_REGS(X)
+#undef X
+};
 
 // The fused column.  A CTA owns H = PWS_COLUMN_HRUS HRUs and has 2 H threads:
 // warps [0, H/32) run the UPPER half of the column (atmosphere, canopy, snow)
@@ -343,7 +379,7 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
   int32_t* const siU = reinterpret_cast<int32_t*>(spS + (size_t)kLowerStateStaged * H);
   int32_t* const siL = siU + (size_t)kUpperI32 * H;
   int32_t* const siM = siL + (size_t)kLowerI32 * H;
-  double* const sF = reinterpret_cast<double*>(smem_raw + kColumnParamBytes);  // [2][kForcRows][H]
+  double* const sF = reinterpret_cast<double*>(smem_raw + kColumnParamBytes);  // [kForcRows][H]
   const uint32_t mbar0 = smem_u32(smem_raw + kColumnParamBytes + kColumnForcBytes);
 
   GpuSink<kMode, H> out{a, nullptr, nullptr, nullptr, (unsigned)(a.ostride * 8),
@@ -421,7 +457,7 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
     // Forcings of day d+1 are in flight while day d computes.  When the rows
     // are 16-byte aligned (a.use_tma) one thread streams the five rows of the
     // CTA's HRUs into shared memory with TMA bulk copies that complete on an
-    // mbarrier (2 slots); otherwise every thread prefetches its own values
+    // mbarrier; otherwise every thread prefetches its own values
     // into registers.
     const bool tma = a.use_tma != 0;
     const int64_t hru0 = (int64_t)blockIdx.x * H;
@@ -429,9 +465,8 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
     const int64_t row_n = (a.P.nhru - hru0) < H ? (a.P.nhru - hru0) : H;
     const uint32_t row_bytes = (uint32_t)(((row_n + 1) & ~(int64_t)1) * 8);
     auto tma_issue = [&](int d) {  // one thread
-      const int slot = d & 1;
-      const uint32_t bar = mbar0 + 8u * slot;
-      const uint32_t dst = smem_u32(sF + (size_t)slot * kForcRows * H);
+      const uint32_t bar = mbar0;
+      const uint32_t dst = smem_u32(sF);
       const int doy = a.cal[d].x;
       const int64_t fo = (int64_t)d * a.fstride + hru0;
       const int64_t so = (int64_t)(doy - 1) * S + hru0;
@@ -446,10 +481,9 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
     if (tma) {
       if (r == 0) {
         mbar_init(mbar0, 1);
-        mbar_init(mbar0 + 8u, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       }
-      for (int k = 0; k < 2 * kForcRows; ++k) sF[k * H + r] = 0.0;  // lanes past the last HRU
+      for (int k = 0; k < kForcRows; ++k) sF[k * H + r] = 0.0;  // lanes past the last HRU
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       bar_sync(BAR_UPPER, H);
       if (r == 0) tma_issue(0);
@@ -465,19 +499,19 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
     for (int d = 0; d < a.ndays; ++d) {
       DayIn in;
       if (tma) {
-        // slot (d+1)&1 was last read at the top of day d-1: wait until every
-        // thread of the group has finished that day before overwriting it
-        if (d > 0) bar_sync(BAR_UPPER, H);
-        if (r == 0 && d + 1 < a.ndays) tma_issue(d + 1);
         const int4 c = a.cal[d];
         in.doy = c.x; in.dowy = c.y; in.month = c.z; in.dom = c.w;
-        mbar_wait(mbar0 + 8u * (d & 1), (uint32_t)((d >> 1) & 1));
-        const double* f = sF + (size_t)(d & 1) * kForcRows * H + r;
+        mbar_wait(mbar0, (uint32_t)(d & 1));
+        const double* f = sF + r;
         in.prcp = f[0 * H];
         in.tmax = f[1 * H];
         in.tmin = f[2 * H];
         in.potsw = f[3 * H];
         in.horad = f[4 * H];
+        // every thread of the group holds its day-d values in registers: the
+        // slot can take day d+1 while this day computes
+        bar_sync(BAR_UPPER, H);
+        if (r == 0 && d + 1 < a.ndays) tma_issue(d + 1);
       } else {
         in = nxt;
         if (d + 1 < a.ndays) {
@@ -535,7 +569,20 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
 #elif PWS_COLUMN_REGS_UPPER > PWS_COLUMN_REGS_LOWER
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PWS_COLUMN_REGS_LOWER));
 #endif
-#if PWS_COLUMN_LOWER_STATE_SMEM
+#if PWS_COLUMN_LOWER_STATE_SMEM == 2
+    int ks = 0;
+#define X(name) double& sm_##name = spS[(ks++) * H + r]; sm_##name = a.state[(int64_t)ST_##name * S + ii];
+    PWS_LOWER_STATE_IN_SMEM(X)
+#undef X
+    LowerStateMixed sl{
+#define X(name) sm_##name,
+        PWS_LOWER_STATE_IN_SMEM(X)
+#undef X
+#define X(name) a.state[(int64_t)ST_##name * S + ii],
+        PWS_LOWER_STATE_IN_REGS(X)
+#undef X
+    };
+#elif PWS_COLUMN_LOWER_STATE_SMEM
     // the lower half's state lives in this thread's shared-memory column
     int ks = 0;
 #define X(name, kind) double& sm_##name = spS[(ks++) * H + r]; sm_##name = a.state[(int64_t)ST_##name * S + ii];
