@@ -114,7 +114,40 @@ struct HruState {
 struct DayIn {
   double prcp, tmax, tmin, potsw, horad;
   int doy, dowy, month, dom;
+  const int* cal = nullptr;  // {doy, dowy, month, dom} in memory, see PWS_REREAD
 };
+
+// Small integers that are needed late in the day (calendar fields, HRU / cover
+// type, the transpiration flag handed to the lower half) live in a register
+// from the top of the column to their last use, and such registers are what
+// the compiler spills to local memory.  A sink with kReread (k_hru_column) has
+// them in shared memory, so the column can read them again where it uses them
+// (a volatile LDS) instead.  Measured per kind on the CONUS domain (column
+// kernel ms per 10-year pass, none = 103.9): parameters 103.0, lower-half
+// flags 104.9, calendar 107.0 (the re-read sits right in front of a branch
+// and cannot be scheduled early) -- so only the parameters are re-read.
+#ifdef __CUDA_ARCH__
+#define PWS_LDV(p) (*(const volatile int32_t*)(p))
+#define PWS_LDVB(p) ((int)*(const volatile unsigned char*)(p))
+#else
+#define PWS_LDV(p) (*(p))
+#define PWS_LDVB(p) ((int)*(p))
+#endif
+#ifndef PWS_REREAD_CAL
+#define PWS_REREAD_CAL 0
+#endif
+#ifndef PWS_REREAD_PARAM
+#define PWS_REREAD_PARAM 1
+#endif
+#ifndef PWS_REREAD_MID
+#define PWS_REREAD_MID 0
+#endif
+#define PWS_CAL(k, field) ((PWS_REREAD_CAL && Sink::kReread) ? (int)PWS_LDV(in.cal + (k)) : in.field)
+#define PWS_IN_DOY PWS_CAL(0, doy)
+#define PWS_IN_DOWY PWS_CAL(1, dowy)
+#define PWS_IN_MONTH PWS_CAL(2, month)
+#define PWS_IN_DOM PWS_CAL(3, dom)
+#define PWS_PARAM_I(name) ((PWS_REREAD_PARAM && Sink::kReread) ? (int)PWS_LDV(P.name + i) : (int)PWS_LD(P.name + i))
 
 // ---------------------------------------------------------------- helpers
 PWS_DEV bool budget_open(double in, double out_plus_ds) {
@@ -651,6 +684,7 @@ struct ColumnMid {
   double potet, net_rain, net_snow, hru_intcpevap, intcp_changeover;
   double snowmelt, snow_evap, pkwater_equiv, snowcov_area, through_rain;
   int transp_on, pptmix_nopack;
+  const unsigned char* flags = nullptr;  // bit 0 transp_on, bit 1 pptmix_nopack (PWS_REREAD)
 };
 
 // ---- upper half: PRMSAtmosphere, PRMSCanopy, PRMSSnow
@@ -658,8 +692,7 @@ template <class Sink>
 PWS_DEV void column_upper(const HruParams& P, const int64_t i, HruState& s,
                           const DayIn& in, Sink& out, ColumnMid& mid) {
   const int64_t mi = (int64_t)(in.month - 1) * P.stride + i;
-  const int hru_type = PWS_LD(P.hru_type + i);
-  const int cov_type = PWS_LD(P.cov_type + i);
+  // hru_type / cov_type: PWS_PARAM_I at their uses
 
   // ===================== PRMSAtmosphere ==================================
   // adjust_temperature prms_atmosphere.py:287-317
@@ -712,7 +745,7 @@ PWS_DEV void column_upper(const HruParams& P, const int64_t i, HruState& s,
     if (pptadj > 1.0) pptadj = 1.0;
     if (tmaxf < tmax_index) {
       const double allrain2 = allrain_off + allsnow;
-      const bool is_summer = (in.doy >= 79) && (in.doy <= 265);
+      const bool is_summer = (PWS_IN_DOY >= 79) && (PWS_IN_DOY <= 265);
       pptadj = PWS_LD(P.radj_sppt + i);
       if (tmaxf < allrain2 || !is_summer) pptadj = PWS_LD(P.radj_wppt + i);
     }
@@ -730,13 +763,13 @@ PWS_DEV void column_upper(const HruParams& P, const int64_t i, HruState& s,
   {
     double transp_tmax_f = PWS_LD(P.transp_tmax + i);
     if (P.temp_units != 0) transp_tmax_f = (transp_tmax_f * (9.0 / 5.0)) + 32.0;
-    if (in.dom == 1) {
-      if (in.month == PWS_LD(P.transp_end + i)) {
+    if (PWS_IN_DOM == 1) {
+      if (PWS_IN_MONTH == PWS_LD(P.transp_end + i)) {
         s.transp_on = 0;
         s.transp_check = 0;
         s.tmax_sum = 0.0;
       }
-      if (in.month == PWS_LD(P.transp_beg + i)) {
+      if (PWS_IN_MONTH == PWS_LD(P.transp_beg + i)) {
         s.transp_check = 1;
         s.tmax_sum = 0.0;
       }
@@ -785,7 +818,7 @@ PWS_DEV void column_upper(const HruParams& P, const int64_t i, HruState& s,
     double intcpstor = s.intcp_stor;
     double intcpevap = 0.0, changeover = 0.0, extra_water = 0.0;
     // hru_type is forced to LAND in the reference (prms_canopy.py:92)
-    if (cov_type == 0) {
+    if (PWS_PARAM_I(cov_type) == 0) {
       if (intcpstor > 0.0) extra_water = s.intcp_stor;
       intcpstor = 0.0;
     }
@@ -818,16 +851,16 @@ PWS_DEV void column_upper(const HruParams& P, const int64_t i, HruState& s,
         }
       }
     }
-    if (cov_type != 0 && cov > 0.0) {
+    if (PWS_PARAM_I(cov_type) != 0 && cov > 0.0) {
       if (hru_rain > 0.0) {
-        if (cov_type > 1) {
+        if (PWS_PARAM_I(cov_type) > 1) {
           intercept(hru_rain, stor_max_rain, cov, intcpstor, net_rain);
         } else if ((pk_ice_prev + freeh2o_prev) < PWS_DNEARZERO && net_snow < PWS_NEARZERO) {
           intercept(hru_rain, stor_max_rain, cov, intcpstor, net_rain);
         }
       }
     }
-    if (hru_snow > 0.0 && cov > 0.0 && cov_type > 1) {
+    if (hru_snow > 0.0 && cov > 0.0 && PWS_PARAM_I(cov_type) > 1) {
       intercept(hru_snow, PWS_LD(P.snow_intcp + i), cov, intcpstor, net_snow);
       if (net_snow < PWS_NEARZERO) {
         net_rain = net_rain + net_snow;
@@ -882,16 +915,16 @@ PWS_DEV void column_upper(const HruParams& P, const int64_t i, HruState& s,
   int pptmix_nopack = 0;
   const int newsnow = net_snow > 0.0;
   {
-    bool active = hru_type != HRU_LAKE;
+    bool active = PWS_PARAM_I(hru_type) != HRU_LAKE;
     if (active) {
-      if (in.dowy == 1) {
+      if (PWS_IN_DOWY == 1) {
         s.pss = 0.0;
         s.iso = 1;
         s.mso = 1;
         s.lso = 0;
       }
-      if (in.doy == PWS_LD(P.melt_force + i)) s.iso = 2;
-      if (in.doy == PWS_LD(P.melt_look + i)) s.mso = 2;
+      if (PWS_IN_DOY == PWS_LD(P.melt_force + i)) s.iso = 2;
+      if (PWS_IN_DOY == PWS_LD(P.melt_look + i)) s.mso = 2;
       if (s.pkwater_equiv < PWS_DNEARZERO && !newsnow) {
         s.snowcov_area = 0.0;
         active = false;
@@ -1104,7 +1137,7 @@ PWS_DEV void column_upper(const HruParams& P, const int64_t i, HruState& s,
         const double emis_noppt = PWS_LD(P.emis_noppt + i);
         const double esv = hru_ppt > 0.0 ? 1.0 : emis_noppt;
         double cec = PWS_LD(P.cecn_coef + mi) * 0.5;
-        if (cov_type > 2) cec = cec * 0.5;
+        if (PWS_PARAM_I(cov_type) > 2) cec = cec * 0.5;
         if (s.iso == 1 && s.mso == 2) {
           if (s.pk_temp >= 0.0) {
             s.lso = s.lso + 1;
@@ -1144,7 +1177,7 @@ PWS_DEV void column_upper(const HruParams& P, const int64_t i, HruState& s,
         }
         // ---- step 5: sublimation, prms_snow.py:3096-3222
         if (s.pkwater_equiv > 0.0) {
-          if (!transp_on || cov_type < 2) {
+          if (!transp_on || PWS_PARAM_I(cov_type) < 2) {
             const double ez = PWS_LD(P.potet_sublim + i) * potet * s.snowcov_area - hru_intcpevap;
             if (ez < PWS_CLOSEZERO) {
               snow_evap = 0.0;
@@ -1268,8 +1301,7 @@ PWS_DEV void column_upper(const HruParams& P, const int64_t i, HruState& s,
 template <class State, class Sink>
 PWS_DEV void column_lower(const HruParams& P, const int64_t i, State& s,
                           const ColumnMid& mid, Sink& out) {
-  const int hru_type = PWS_LD(P.hru_type + i);
-  const int cov_type = PWS_LD(P.cov_type + i);
+  // hru_type / cov_type: PWS_PARAM_I at their uses
   const double hru_area = PWS_LD(P.hru_area + i);
   const double hru_in_to_cf = PWS_LD(P.hru_in_to_cf + i);
   // x / hru_area occurs ~20 times a day: one true division for the correctly
@@ -1283,7 +1315,7 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, State& s,
   const double snowmelt = mid.snowmelt, snow_evap = mid.snow_evap;
   const double pkwater_equiv = mid.pkwater_equiv, snowcov_area = mid.snowcov_area;
   const double through_rain = mid.through_rain;
-  const int transp_on = mid.transp_on, pptmix_nopack = mid.pptmix_nopack;
+#define PWS_MID_FLAG(bit, field) ((PWS_REREAD_MID && Sink::kReread) ? ((PWS_LDVB(mid.flags) >> (bit)) & 1) : mid.field)
   // ===================== PRMSRunoff ======================================
   double soil_rechr_prev = s.soil_rechr;
   double soil_lower_prev = s.soil_moist - s.soil_rechr;  // = yesterday's soil_lower
@@ -1306,7 +1338,7 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, State& s,
     const double imperv_frac = hruarea_imperv > 0.0 ? PWS_LD(P.hru_percent_imperv + i) : 0.0;
     double avail_et = potet - snow_evap - hru_intcpevap;
     const double availh2o = intcp_changeover + net_rain;
-    const bool land = hru_type == HRU_LAND;
+    const bool land = PWS_PARAM_I(hru_type) == HRU_LAND;
     // compute_infil prms_runoff.py:819-989
     double avail_water = 0.0;
     const double carea_max = PWS_LD(P.carea_max + i);
@@ -1329,7 +1361,7 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, State& s,
           pptp = ptc = intcp_changeover;
         }
       } else if (stage == 1) {
-        if (pptmix_nopack != 0) {
+        if (PWS_MID_FLAG(1, pptmix_nopack) != 0) {
           avail_water = avail_water + through_rain;
           infil = infil + through_rain;
           kind = land ? 1 : 0;
@@ -1382,7 +1414,7 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, State& s,
       const double vol_open_max = PWS_LD(P.dprst_vol_open_max + i);
       const double vol_clos_max = PWS_LD(P.dprst_vol_clos_max + i);
       double inflow = 0.0;
-      if (pptmix_nopack) inflow = inflow + availh2o;
+      if (PWS_MID_FLAG(1, pptmix_nopack)) inflow = inflow + availh2o;
       if (snowmelt > 0.0) {
         inflow = inflow + snowmelt;
       } else if (pkwater_equiv < PWS_DNEARZERO) {
@@ -1602,7 +1634,7 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, State& s,
     out.sync2();
     double topfr = 0.0;
     double availh2o = s.slow_stor + soil_to_ssr;
-    if (hru_type == HRU_LAND) {
+    if (PWS_PARAM_I(hru_type) == HRU_LAND) {
       topfr = fmax(0.0, availh2o - PWS_LD(P.pref_flow_thrsh + i));
       const double ssresin = soil_to_ssr - topfr;
       s.slow_stor = fmax(0.0, availh2o - topfr);
@@ -1611,7 +1643,7 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, State& s,
                                s.slow_stor, slow_flow))
           out.error(1);
       }
-    } else if (hru_type == HRU_SWALE) {
+    } else if (PWS_PARAM_I(hru_type) == HRU_SWALE) {
       s.slow_stor = availh2o;
     }
     {
@@ -1637,7 +1669,7 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, State& s,
                                pref_flow_in, s.pref_flow_stor, prefflow))
           out.error(1);
       }
-    } else if (hru_type == HRU_LAND) {
+    } else if (PWS_PARAM_I(hru_type) == HRU_LAND) {
       dunnianflw_gvr = topfr;
     }
     out.sync2();
@@ -1647,9 +1679,9 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, State& s,
       if (avail_potet < PWS_NEARZERO) {
         et_type = 1;
         avail_potet = 0.0;
-      } else if (!transp_on) {
+      } else if (!PWS_MID_FLAG(0, transp_on)) {
         et_type = snow_free < 0.01 ? 1 : 2;
-      } else if (cov_type > 0) {
+      } else if (PWS_PARAM_I(cov_type) > 0) {
         et_type = 3;
       } else {
         et_type = snow_free < 0.01 ? 1 : 2;
@@ -1701,7 +1733,7 @@ PWS_DEV void column_lower(const HruParams& P, const int64_t i, State& s,
     }
     out.sync2();
     hru_actet = hru_actet + perv_actet * hru_frac_perv;
-    if (hru_type == HRU_LAND) {
+    if (PWS_PARAM_I(hru_type) == HRU_LAND) {
       dunnian_flow = dunnianflw_gvr + dunnianflw_pfr;
       ssres_flow = slow_flow;
       if (pref_flow_den > 0.0) {

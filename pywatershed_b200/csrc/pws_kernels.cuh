@@ -51,10 +51,12 @@
 #ifndef PWS_COLUMN_LOWER_STATE_SMEM
 #define PWS_COLUMN_LOWER_STATE_SMEM 2
 #endif
+#ifndef PWS_LOWER_STATE_IN_SMEM
 #define PWS_LOWER_STATE_IN_SMEM(X) \
   X(imperv_stor) X(hru_impervstor) X(dprst_vol_open) X(dprst_vol_clos) X(dprst_area_open)
 #define PWS_LOWER_STATE_IN_REGS(X) \
   X(soil_moist) X(soil_rechr) X(slow_stor) X(pref_flow_stor) X(gwres_stor)
+#endif
 // Registers per thread of the two warp groups (setmaxnreg, multiples of 8;
 // with 256 HRUs per CTA, upper + lower must be <= 256).  Unconstrained, the
 // upper half wants 204 registers (29 prognostic values, the snow energy
@@ -179,6 +181,7 @@ struct FullSlot {
 
 template <int kMode, int H>
 struct GpuSink {
+  static constexpr bool kReread = true;  // small integers are re-read from shared memory (hru_column.cuh)
   const ColumnArgs& a;
   char* pf;
   char* pi;
@@ -279,11 +282,12 @@ template <int H>
 struct ColumnSmem {
   static constexpr size_t kParamBytes = (size_t)H * (kColF64 * 8 + kColI32 * 4);
   static constexpr size_t kForcBytes = (size_t)kForcRows * H * 8;
-  static constexpr size_t kBytes = kParamBytes + kForcBytes + 16;
+  // + mbarrier (16) + two calendar rows (32) + one flag byte per HRU for the lower half
+  static constexpr size_t kBytes = kParamBytes + kForcBytes + 16 + 32 + (size_t)H;
   static_assert(kParamBytes % 16 == 0, "forcing stage must be 16-byte aligned");
 };
 constexpr size_t column_smem_bytes(int H) {
-  return (size_t)H * (kColF64 * 8 + kColI32 * 4) + (size_t)kForcRows * H * 8 + 16;
+  return (size_t)H * (kColF64 * 8 + kColI32 * 4) + (size_t)kForcRows * H * 8 + 16 + 32 + (size_t)H;
 }
 
 // named barriers of k_hru_column (0 is __syncthreads)
@@ -381,6 +385,9 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
   int32_t* const siM = siL + (size_t)kLowerI32 * H;
   double* const sF = reinterpret_cast<double*>(smem_raw + kColumnParamBytes);  // [kForcRows][H]
   const uint32_t mbar0 = smem_u32(smem_raw + kColumnParamBytes + kColumnForcBytes);
+  // {doy, dowy, month, dom} of today and tomorrow, and the lower half's flag bytes
+  int* const sCal = reinterpret_cast<int*>(smem_raw + kColumnParamBytes + kColumnForcBytes + 16);
+  unsigned char* const sFlag = smem_raw + kColumnParamBytes + kColumnForcBytes + 16 + 32;
 
   GpuSink<kMode, H> out{a, nullptr, nullptr, nullptr, (unsigned)(a.ostride * 8),
                      (unsigned)(a.ostride * 4), 0u, 0, live, upper ? BAR_UPPER : BAR_LOWER};
@@ -452,7 +459,6 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
       PWS_UPPER_MON_I32(X)
 #undef X
     };
-    int staged_month = 0;
 #endif
     // Forcings of day d+1 are in flight while day d computes.  When the rows
     // are 16-byte aligned (a.use_tma) one thread streams the five rows of the
@@ -470,7 +476,8 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
       const int doy = a.cal[d].x;
       const int64_t fo = (int64_t)d * a.fstride + hru0;
       const int64_t so = (int64_t)(doy - 1) * S + hru0;
-      mbar_expect_tx(bar, kForcRows * row_bytes);
+      mbar_expect_tx(bar, kForcRows * row_bytes + 16u);
+      tma_bulk_g2s(smem_u32(sCal + 4 * (d & 1)), a.cal + d, 16u, bar);
       tma_bulk_g2s(dst + 0 * H * 8, a.prcp + fo, row_bytes, bar);
       tma_bulk_g2s(dst + 1 * H * 8, a.tmax + fo, row_bytes, bar);
       tma_bulk_g2s(dst + 2 * H * 8, a.tmin + fo, row_bytes, bar);
@@ -499,9 +506,9 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
     for (int d = 0; d < a.ndays; ++d) {
       DayIn in;
       if (tma) {
-        const int4 c = a.cal[d];
-        in.doy = c.x; in.dowy = c.y; in.month = c.z; in.dom = c.w;
         mbar_wait(mbar0, (uint32_t)(d & 1));
+        in.cal = sCal + 4 * (d & 1);  // stays valid all day: tomorrow's row goes to the other entry
+        in.doy = in.cal[0]; in.dowy = in.cal[1]; in.month = in.cal[2]; in.dom = in.cal[3];
         const double* f = sF + r;
         in.prcp = f[0 * H];
         in.tmax = f[1 * H];
@@ -514,6 +521,7 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
         if (r == 0 && d + 1 < a.ndays) tma_issue(d + 1);
       } else {
         in = nxt;
+        in.cal = reinterpret_cast<const int*>(a.cal + d);
         if (d + 1 < a.ndays) {
           const int4 c = a.cal[d + 1];
           const int64_t fo = (int64_t)(d + 1) * a.fstride + ii;
@@ -526,10 +534,8 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
         }
       }
 #if PWS_COLUMN_MONTHLY_SMEM
-      if (in.month != staged_month) {  // warp-uniform
-        stage_month(in.month);
-        staged_month = in.month;
-      }
+      // a new month starts on day-of-month 1 (and the block may start anywhere); uniform
+      if (d == 0 || PWS_LDV(in.cal + 3) == 1) stage_month(in.month);
 #endif
       out.violmask = 0u;
       ColumnMid mid;
@@ -627,6 +633,10 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
       mid.through_rain = mf[9 * H];
       mid.transp_on = mi32[0 * H];
       mid.pptmix_nopack = mi32[1 * H];
+#if PWS_REREAD_MID
+      sFlag[r] = (unsigned char)((mid.transp_on & 1) | ((mid.pptmix_nopack & 1) << 1));
+      mid.flags = sFlag + r;
+#endif
       if (d + kMidSlots < a.ndays) bar_arrive(BAR_MID_EMPTY + slot, 2 * H);
       out.violmask = 0u;
       out.plat = a.hru_lat ? a.hru_lat + (int64_t)d * S + ii : nullptr;
@@ -658,6 +668,7 @@ struct OvArgs {
 };
 
 struct OvSink {
+  static constexpr bool kReread = false;
   const OvArgs& a;
   char* pf;
   char* pi;

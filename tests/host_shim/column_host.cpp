@@ -27,6 +27,7 @@ struct Shim {
 };
 
 struct HostSink {
+  static constexpr bool kReread = false;
   double* out;  // [PWS_N_HRU_VARS][nhru] for the current day, at this HRU
   int64_t nhru;
   int* pv;
