@@ -64,7 +64,9 @@ int pws_set_param_i32(pws_handle *h, const char *name, const int32_t *h_v, int64
  * k_soltab; 0, default: with the host libm the reference's tables come from),
  * "channel_chunk" (segments per routing chunk = per CTA of k_route_chunks,
  * default and maximum 512; outlet trees larger than a chunk are cut and linked
- * through HBM). */
+ * through HBM),
+ * "route_hours" (hours a segment advances per step of k_route_chunks: 0,
+ * default = 12 for segment graphs of at most 160 levels, else 4). */
 int pws_set_option(pws_handle *h, const char *name, double value);
 
 /* Everything the reference derives at construction: soltab tables

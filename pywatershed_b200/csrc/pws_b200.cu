@@ -98,6 +98,7 @@ struct pws_handle {
   int block_days = 0;
   int soltab_device = 0;
   int tma = 1;  // option: stage forcings with TMA bulk copies when the rows are aligned
+  bool route_attr_set = false;
   bool smem_attr_set[6] = {false, false, false, false, false, false};
   int column_hrus_opt = 0;  // option "column_hrus": 0 = by domain size, else 128 | 256
   double albset[4] = {0, 0, 0, 0};
@@ -120,6 +121,7 @@ struct pws_handle {
   // channel (level order)
   int nlevels = 0, nchunks = 0, n_cross_edges = 0, n_ext_rows = 0, max_dmax = 0;
   int channel_chunk = PWS_CHUNK_THREADS;  // option: segments per routing chunk (<= CTA size)
+  int route_hours_opt = 0;                // option "route_hours": 0 = by network depth
   int32_t *d_tsi = nullptr, *d_up_ptr = nullptr, *d_up_idx = nullptr, *d_hru_ptr = nullptr,
           *d_hru_idx = nullptr, *d_seg_flags = nullptr, *d_orig = nullptr,
           *d_chunk_begin = nullptr, *d_chunk_dmax = nullptr, *d_delay = nullptr,
@@ -382,6 +384,12 @@ extern "C" int pws_set_option(pws_handle* h, const char* name, double value) {
     h->column_hrus_opt = (int)value;
     return 0;
   }
+  else if (!strcmp(name, "route_hours")) {
+    if (value != 0 && value != PWS_ROUTE_HOURS && value != PWS_ROUTE_HOURS_SHALLOW)
+      PWS_FAIL(h, "pws_set_option: route_hours must be 0 (automatic), %d or %d", PWS_ROUTE_HOURS,
+               PWS_ROUTE_HOURS_SHALLOW);
+    h->route_hours_opt = (int)value;
+  }
   else if (!strcmp(name, "channel_chunk")) {
     if (value < 1 || value > PWS_CHUNK_THREADS)
       PWS_FAIL(h, "pws_set_option: channel_chunk must be in 1..%d", PWS_CHUNK_THREADS);
@@ -390,6 +398,14 @@ extern "C" int pws_set_option(pws_handle* h, const char* name, double value) {
   else PWS_FAIL(h, "pws_set_option: unknown option '%s'", name);
   h->inited = false;
   return 0;
+}
+
+// Hours per systolic step of k_route_chunks: long steps for shallow segment
+// graphs (fewer barriers), short ones for deep graphs (the pipeline fill is one
+// step per level; see PWS_ROUTE_HOURS in pws_kernels.cuh).
+static int route_hours(const pws_handle* h) {
+  if (h->route_hours_opt) return h->route_hours_opt;
+  return h->nlevels <= 160 ? PWS_ROUTE_HOURS_SHALLOW : PWS_ROUTE_HOURS;
 }
 
 // --------------------------------------------------------------- channel init
@@ -542,7 +558,7 @@ static int channel_build(pws_handle* h) {
   for (int64_t i = 0; i < nseg; ++i) bypos[i] = (int)i;
   std::stable_sort(bypos.begin(), bypos.end(), [&](int x, int y) {
     if (chunk_of[x] != chunk_of[y]) return chunk_of[x] < chunk_of[y];
-    constexpr int spd = 24 / PWS_ROUTE_HOURS;  // steps per day
+    const int spd = 24 / route_hours(h);  // steps per day
     if (delay_v[x] % spd != delay_v[y] % spd) return delay_v[x] % spd < delay_v[y] % spd;
     return delay_v[x] < delay_v[y];
   });
@@ -943,7 +959,21 @@ static int enqueue_channel(pws_handle* h, int ndays, const double* d_hru_lat,
   // progress counters (cross-chunk edges) and the chunk ticket start at 0
   PWS_CUDA(h, cudaMemsetAsync(h->d_progress, 0, (size_t)(h->sstride + 32) * sizeof(int),
                               h->s_compute));
-  k_route_chunks<<<(unsigned)h->nchunks, PWS_CHUNK_THREADS, 0, h->s_compute>>>(a);
+  if (!h->route_attr_set) {
+    PWS_CUDA(h, cudaFuncSetAttribute(k_route_chunks<PWS_ROUTE_HOURS>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)route_smem_bytes(PWS_ROUTE_HOURS)));
+    PWS_CUDA(h, cudaFuncSetAttribute(k_route_chunks<PWS_ROUTE_HOURS_SHALLOW>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)route_smem_bytes(PWS_ROUTE_HOURS_SHALLOW)));
+    h->route_attr_set = true;
+  }
+  if (route_hours(h) == PWS_ROUTE_HOURS_SHALLOW)
+    k_route_chunks<PWS_ROUTE_HOURS_SHALLOW><<<(unsigned)h->nchunks, PWS_CHUNK_THREADS,
+                                              route_smem_bytes(PWS_ROUTE_HOURS_SHALLOW), h->s_compute>>>(a);
+  else
+    k_route_chunks<PWS_ROUTE_HOURS><<<(unsigned)h->nchunks, PWS_CHUNK_THREADS,
+                                      route_smem_bytes(PWS_ROUTE_HOURS), h->s_compute>>>(a);
   h->launches++;
   h->last_channel_launches += 1;
   if (budget) {

@@ -387,7 +387,8 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
   const uint32_t mbar0 = smem_u32(smem_raw + kColumnParamBytes + kColumnForcBytes);
   // {doy, dowy, month, dom} of today and tomorrow, and the lower half's flag bytes
   int* const sCal = reinterpret_cast<int*>(smem_raw + kColumnParamBytes + kColumnForcBytes + 16);
-  unsigned char* const sFlag = smem_raw + kColumnParamBytes + kColumnForcBytes + 16 + 32;
+  [[maybe_unused]] unsigned char* const sFlag =
+      smem_raw + kColumnParamBytes + kColumnForcBytes + 16 + 32;
 
   GpuSink<kMode, H> out{a, nullptr, nullptr, nullptr, (unsigned)(a.ostride * 8),
                      (unsigned)(a.ostride * 4), 0u, 0, live, upper ? BAR_UPPER : BAR_LOWER};
@@ -835,20 +836,34 @@ enum {
 #ifndef PWS_ROUTE_MAX_IDLE
 #define PWS_ROUTE_MAX_IDLE (1 << 24)
 #endif
-// hours a segment advances per systolic step (divides 24): one barrier, one
-// shared-memory round trip and one set of loop overheads per PWS_ROUTE_HOURS
-// hourly updates; the pipeline fill grows to PWS_ROUTE_HOURS * dmax hours
+// Hours a segment advances per systolic step (G, divides 24): one barrier, one
+// shared-memory round trip and one set of loop overheads per G hourly updates,
+// but the pipeline fill is dmax steps of G hours each.  Per launch of T days a
+// chunk takes about (24 T / G + dmax) (0.39 + 0.2 G) us (fit to G = 4 .. 12 on the
+// CONUS domain, where G = 12 routes a 10-year pass in 24.2 ms against 28.4 for
+// G = 4), so shallow networks get G = 12 and deep ones G = 4 (pws_init picks by
+// the number of levels of the segment graph; option "route_hours").
 #ifndef PWS_ROUTE_HOURS
-#define PWS_ROUTE_HOURS 4
+#define PWS_ROUTE_HOURS 4    // deep networks
 #endif
+#ifndef PWS_ROUTE_HOURS_SHALLOW
+#define PWS_ROUTE_HOURS_SHALLOW 12
+#endif
+constexpr size_t route_smem_bytes(int G) {
+  return (size_t)2 * G * (PWS_CHUNK_THREADS + 1) * sizeof(double);
+}
 
+template <int G>
 __global__ void __launch_bounds__(PWS_CHUNK_THREADS, 1)
 k_route_chunks(const __grid_constant__ ChannelArgs a) {
   constexpr int kZero = PWS_CHUNK_THREADS;  // a slot that always holds 0.0
-  constexpr int G = PWS_ROUTE_HOURS;
   constexpr int kStepsPerDay = 24 / G;
-  static_assert(24 % G == 0, "PWS_ROUTE_HOURS must divide 24");
-  __shared__ double s_out[2][G][PWS_CHUNK_THREADS + 1];
+  static_assert(24 % G == 0, "hours per step must divide 24");
+  // double-buffered hand-over of the G hourly outflows of every segment (dynamic
+  // shared memory: 2 G (threads + 1) doubles, more than the 48 KB static limit for G > 5)
+  extern __shared__ __align__(16) unsigned char route_smem[];
+  double(*const s_out)[G][PWS_CHUNK_THREADS + 1] =
+      reinterpret_cast<double(*)[G][PWS_CHUNK_THREADS + 1]>(route_smem);
   __shared__ int s_chunk;
   const int tid = threadIdx.x;
   if (tid == 0) {

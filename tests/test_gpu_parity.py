@@ -615,3 +615,31 @@ def test_output_writes_stay_inside_their_buffers(drb, ntile, nhru_keep, nd, outp
     for j, name in enumerate(e.sel_seg):
         np.testing.assert_array_equal(got_s[:, j], ref[name], err_msg=name)
     np.testing.assert_array_equal(viol, rviol)
+
+
+@pytest.mark.parametrize("hours", [4, 12])
+def test_route_hours_are_equivalent(drb, hours):
+    """k_route_chunks advances 12 hours per systolic step on shallow segment
+    graphs and 4 on deep ones (option route_hours); the schedule must not
+    change a bit of the routing."""
+    import torch
+
+    p, f, start = drb
+    nd, nseg = 40, p["tosegment"].shape[0]
+    rng = np.random.default_rng(12)
+    lat = rng.lognormal(0.0, 1.0, size=(nd, nseg))
+    ref = po.Oracle(p, start=start).run_channel(lat)
+    from pywatershed_b200 import Engine
+
+    e = Engine(p, start, channel_chunk=96)  # several chunks per tree: cross-chunk edges too
+    e._opt("route_hours", hours)
+    e._check(e.L.pws_init(e.h))
+    e.select_outputs(e.reg.hru_vars, e.reg.seg_vars)
+    dev = torch.device("cuda:0")
+    dl = torch.from_numpy(lat).to(dev)
+    out = torch.empty((nd, 5, nseg), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    e.run_channel_device(nd, dl.data_ptr(), out.data_ptr())
+    out = out.cpu().numpy()
+    for k, v in enumerate(po.SEG_VARS):
+        np.testing.assert_array_equal(out[:, k], ref[v], err_msg=v)
