@@ -227,6 +227,18 @@ def test_pinned_and_pageable_host_buffers_agree(drb):
     for k in po.HRU_VARS + po.SEG_VARS:
         np.testing.assert_array_equal(np.asarray(a[k]), np.asarray(b[k]), err_msg=k)
     np.testing.assert_array_equal(va, vb)
+    # inputs and outputs are staged independently: the two mixed cases
+    e3 = _engine(p, start)
+    e3.set_block_days(20)
+    c, vc = e3.run_host(f["prcp"][:nd], f["tmax"][:nd], f["tmin"][:nd], pinned_outputs=True)  # what Model does
+    e4 = _engine(p, start)
+    e4.set_block_days(20)
+    d, vd = e4.run_host(pin["prcp"], pin["tmax"], pin["tmin"])
+    for k in po.HRU_VARS + po.SEG_VARS:
+        np.testing.assert_array_equal(np.asarray(a[k]), np.asarray(c[k]), err_msg=k)
+        np.testing.assert_array_equal(np.asarray(a[k]), np.asarray(d[k]), err_msg=k)
+    np.testing.assert_array_equal(va, vc)
+    np.testing.assert_array_equal(va, vd)
 
 
 def test_time_blocking_is_transparent(drb):
