@@ -194,7 +194,7 @@ struct GpuSink {
   template <int var>
   __device__ __forceinline__ void f(double v) {
     if constexpr (kMode == SINK_FULL) {
-      // one IMAD.WIDE (row * stride + pointer) and one STG.CS per value
+      // one IMAD.WIDE (row * stride + pointer) and one STG (L1::no_allocate) per value
       constexpr unsigned slot = FullSlot<var>::value;
       unsigned long long addr;
       asm("mad.wide.u32 %0, %1, %2, %3;"
