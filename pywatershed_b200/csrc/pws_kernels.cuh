@@ -203,7 +203,8 @@ struct GpuSink {
       if (live) asm volatile("st.global." PWS_COLUMN_ST ".f64 [%0], %1;" ::"l"(addr), "d"(v));
     } else if constexpr (kMode == SINK_SELECT) {
       const int64_t o = a.off[var];
-      if (o >= 0 && live) __stcs(reinterpret_cast<double*>(pf + o), v);
+      if (o >= 0 && live)
+        asm volatile("st.global." PWS_COLUMN_ST ".f64 [%0], %1;" ::"l"(pf + o), "d"(v));
     }
   }
   template <int var>
@@ -217,7 +218,8 @@ struct GpuSink {
       if (live) asm volatile("st.global." PWS_COLUMN_ST ".s32 [%0], %1;" ::"l"(addr), "r"(v));
     } else if constexpr (kMode == SINK_SELECT) {
       const int64_t o = a.off[var];
-      if (o >= 0 && live) __stcs(reinterpret_cast<int*>(pi + o), v);
+      if (o >= 0 && live)
+        asm volatile("st.global." PWS_COLUMN_ST ".s32 [%0], %1;" ::"l"(pi + o), "r"(v));
     }
   }
   __device__ __forceinline__ void viol(int proc, bool open) {
