@@ -226,7 +226,7 @@ struct GpuSink {
     if (open && live) violmask |= 1u << proc;
   }
   __device__ __forceinline__ void lateral(double v) {
-    if (plat && live) *plat = v;
+    if (plat && live) asm volatile("st.global." PWS_COLUMN_ST ".f64 [%0], %1;" ::"l"(plat), "d"(v));
   }
   __device__ __forceinline__ void error(int code) {
     if (live) errmask |= code;
