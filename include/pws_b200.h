@@ -136,6 +136,18 @@ int pws_run_channel_device(pws_handle *h, int ndays, const double *d_seg_lateral
 
 int pws_sync(pws_handle *h);
 
+/* Tiled result layout of pws_run_device, chosen with
+ * pws_set_option(h, "tiled_outputs", 1) when every HRU variable is selected in
+ * registry order: out_f64 is [day][tile][n_f64][tile_units], out_i32
+ * [day][tile][n_i32][tile_units], tile = unit / tile_units, the last tile
+ * padded (padded_units = tiles * tile_units >= nhru units per variable and
+ * day; the padding is never written).  A variable's row inside a tile is then
+ * a compile-time offset for the kernel: one store instruction per value, no
+ * address arithmetic.  The reference has no counterpart (its variables are
+ * separate [nhru] numpy arrays, base/process.py:324-372); the Python Engine
+ * hands out per-variable strided views of this buffer. */
+int pws_output_tile(pws_handle *h, int *tile_units, int64_t *padded_units);
+
 /* ---- state: get_restart_variables (prms_snow.py:269-293 etc.) ---------- */
 int pws_get_state(pws_handle *h, const char *name, double *h_out); /* [nhru] */
 int pws_set_state(pws_handle *h, const char *name, const double *h_in);

@@ -69,6 +69,7 @@ def lib():
         "pws_timer_elapsed_ms": (i32, [vp, C.POINTER(dbl)]),
         "pws_last_launches": (i32, [vp, C.POINTER(i32), C.POINTER(i32)]),
         "pws_reset_state": (i32, [vp]),
+        "pws_output_tile": (i32, [vp, C.POINTER(i32), C.POINTER(i64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError if the ABI lost a symbol
@@ -87,4 +88,5 @@ EXPORTED_SYMBOLS = (
     "pws_run_channel_device", "pws_n_inputs", "pws_input_name", "pws_run_host_inputs", "pws_sync", "pws_get_state", "pws_set_state",
     "pws_launch_count", "pws_last_timing", "pws_column_kernel_info",
     "pws_timer_mark", "pws_timer_elapsed_ms", "pws_last_launches", "pws_reset_state",
+    "pws_output_tile",
 )

@@ -99,7 +99,8 @@ struct pws_handle {
   int soltab_device = 0;
   int tma = 1;  // option: stage forcings with TMA bulk copies when the rows are aligned
   bool route_attr_set = false;
-  bool smem_attr_set[6] = {false, false, false, false, false, false};
+  bool smem_attr_set[8] = {false, false, false, false, false, false, false, false};
+  bool tiled_outputs = false;  // option "tiled_outputs": [day][tile][variable][H] (SINK_TILED)
   int column_hrus_opt = 0;  // option "column_hrus": 0 = by domain size, else 128 | 256
   double albset[4] = {0, 0, 0, 0};
   // host copies of the parameters (set before pws_init)
@@ -378,6 +379,7 @@ extern "C" int pws_set_option(pws_handle* h, const char* name, double value) {
   else if (!strcmp(name, "block_days")) { h->block_days = (int)value; return 0; }
   else if (!strcmp(name, "soltab_device")) h->soltab_device = value != 0.0;
   else if (!strcmp(name, "tma")) { h->tma = value != 0.0; return 0; }
+  else if (!strcmp(name, "tiled_outputs")) { h->tiled_outputs = value != 0.0; return 0; }
   else if (!strcmp(name, "column_hrus")) {
     if (value != 0 && value != 128 && value != PWS_COLUMN_HRUS)
       PWS_FAIL(h, "pws_set_option: column_hrus must be 0, 128 or %d", PWS_COLUMN_HRUS);
@@ -1025,15 +1027,6 @@ static void fill_column_args(pws_handle* h, ColumnArgs& a, int ndays, const doub
 static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const double* d_prcp,
                          const double* d_tmax, const double* d_tmin, int64_t fstride,
                          double* d_out_f64, int32_t* d_out_i32, double* d_seg_out, bool want_viol) {
-  if (ensure_scratch(h, ndays)) return 1;
-  PWS_CUDA(h, cudaMemcpyAsync(h->d_cal, h_cal, (size_t)ndays * sizeof(int4),
-                              cudaMemcpyHostToDevice, h->s_compute));
-  if (want_viol)
-    PWS_CUDA(h, cudaMemsetAsync(h->d_viol, 0, (size_t)ndays * BUD_N * sizeof(int), h->s_compute));
-  ColumnArgs a{};
-  fill_column_args(h, a, ndays, d_prcp, d_tmax, d_tmin, fstride, d_out_f64, d_out_i32, want_viol);
-  cudaEvent_t e0 = new_event(h), e1 = new_event(h), e2 = new_event(h);
-  cudaEventRecord(e0, h->s_compute);
   // sink: nothing selected / everything in registry order / a subset
   int mode = SINK_SELECT;
   if (h->n_f64 + h->n_i32 == 0) {
@@ -1043,6 +1036,20 @@ static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const d
     for (int v = 0; v < PWS_N_HRU_VARS; ++v)
       if (h->slot_hru[v] != full_slot(v)) mode = SINK_SELECT;
   }
+  if (h->tiled_outputs) {
+    if (mode != SINK_FULL)
+      PWS_FAIL(h, "tiled_outputs needs every HRU variable selected in registry order");
+    mode = SINK_TILED;
+  }
+  if (ensure_scratch(h, ndays)) return 1;
+  PWS_CUDA(h, cudaMemcpyAsync(h->d_cal, h_cal, (size_t)ndays * sizeof(int4),
+                              cudaMemcpyHostToDevice, h->s_compute));
+  if (want_viol)
+    PWS_CUDA(h, cudaMemsetAsync(h->d_viol, 0, (size_t)ndays * BUD_N * sizeof(int), h->s_compute));
+  ColumnArgs a{};
+  fill_column_args(h, a, ndays, d_prcp, d_tmax, d_tmin, fstride, d_out_f64, d_out_i32, want_viol);
+  cudaEvent_t e0 = new_event(h), e1 = new_event(h), e2 = new_event(h);
+  cudaEventRecord(e0, h->s_compute);
   const int H = column_hrus(h);
   const unsigned grid = (unsigned)((h->nhru + H - 1) / H);
 #define PWS_LAUNCH_COLUMN(MODE, HH)                                                              \
@@ -1061,10 +1068,12 @@ static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const d
   } while (0)
   if (H == 128) {
     if (mode == SINK_FULL) PWS_LAUNCH_COLUMN(SINK_FULL, 128);
+    else if (mode == SINK_TILED) PWS_LAUNCH_COLUMN(SINK_TILED, 128);
     else if (mode == SINK_NONE) PWS_LAUNCH_COLUMN(SINK_NONE, 128);
     else PWS_LAUNCH_COLUMN(SINK_SELECT, 128);
   } else {
     if (mode == SINK_FULL) PWS_LAUNCH_COLUMN(SINK_FULL, PWS_COLUMN_HRUS);
+    else if (mode == SINK_TILED) PWS_LAUNCH_COLUMN(SINK_TILED, PWS_COLUMN_HRUS);
     else if (mode == SINK_NONE) PWS_LAUNCH_COLUMN(SINK_NONE, PWS_COLUMN_HRUS);
     else PWS_LAUNCH_COLUMN(SINK_SELECT, PWS_COLUMN_HRUS);
   }
@@ -1198,6 +1207,7 @@ extern "C" int pws_run_host(pws_handle* h, int ndays, const int32_t* h_cal, cons
                             const double* h_tmax, const double* h_tmin, double* h_out_f64,
                             int32_t* h_out_i32, double* h_seg_out, int32_t* h_budget_viol) {
   if (!h->inited) PWS_FAIL(h, "pws_run_host before pws_init");
+  if (h->tiled_outputs) PWS_FAIL(h, "pws_run_host: tiled_outputs is a pws_run_device layout");
   if (ndays <= 0) return 0;
   PWS_CUDA(h, cudaSetDevice(h->device));
   clear_timing(h);
@@ -1509,6 +1519,14 @@ extern "C" int pws_column_kernel_info(pws_handle* h, int* regs, int* local_bytes
   if (regs) *regs = at.numRegs;
   if (local_bytes) *local_bytes = (int)at.localSizeBytes;
   if (max_blocks_per_sm) *max_blocks_per_sm = nb;
+  return 0;
+}
+
+extern "C" int pws_output_tile(pws_handle* h, int* tile_units, int64_t* padded_units) {
+  PWS_CUDA(h, cudaSetDevice(h->device));
+  const int H = column_hrus(h);
+  if (tile_units) *tile_units = H;
+  if (padded_units) *padded_units = (h->nhru + H - 1) / H * H;
   return 0;
 }
 

@@ -152,7 +152,11 @@ struct ColumnArgs {
 //   SINK_FULL    every variable, in registry order: the row of a variable is a
 //                compile-time constant, one IMAD.WIDE + one STG per value
 //   SINK_NONE    nothing (routing-only runs: the lateral inflow is the output)
-enum { SINK_SELECT = 0, SINK_FULL = 1, SINK_NONE = 2 };
+//   SINK_TILED   every variable, in registry order, laid out [day][CTA tile]
+//                [variable][H units]: the row of a variable is a compile-time
+//                byte offset inside the tile, so a value costs one STG with an
+//                immediate offset and no address arithmetic at all
+enum { SINK_SELECT = 0, SINK_FULL = 1, SINK_NONE = 2, SINK_TILED = 3 };
 
 constexpr int kHruVarKind[PWS_N_HRU_VARS] = {
 #define KIND_F 0
@@ -201,6 +205,10 @@ struct GpuSink {
           : "=l"(addr)
           : "r"(stride8), "n"(slot), "l"((unsigned long long)pf));
       if (live) asm volatile("st.global." PWS_COLUMN_ST ".f64 [%0], %1;" ::"l"(addr), "d"(v));
+    } else if constexpr (kMode == SINK_TILED) {
+      constexpr unsigned byte_off = FullSlot<var>::value * (unsigned)H * 8u;
+      if (live)
+        asm volatile("st.global." PWS_COLUMN_ST ".f64 [%0+%1], %2;" ::"l"(pf), "n"(byte_off), "d"(v));
     } else if constexpr (kMode == SINK_SELECT) {
       const int64_t o = a.off[var];
       if (o >= 0 && live)
@@ -216,6 +224,10 @@ struct GpuSink {
           : "=l"(addr)
           : "r"(stride4), "n"(slot), "l"((unsigned long long)pi));
       if (live) asm volatile("st.global." PWS_COLUMN_ST ".s32 [%0], %1;" ::"l"(addr), "r"(v));
+    } else if constexpr (kMode == SINK_TILED) {
+      constexpr unsigned byte_off = FullSlot<var>::value * (unsigned)H * 4u;
+      if (live)
+        asm volatile("st.global." PWS_COLUMN_ST ".s32 [%0+%1], %2;" ::"l"(pi), "n"(byte_off), "r"(v));
     } else if constexpr (kMode == SINK_SELECT) {
       const int64_t o = a.off[var];
       if (o >= 0 && live)
@@ -394,10 +406,17 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
 
   GpuSink<kMode, H> out{a, nullptr, nullptr, nullptr, (unsigned)(a.ostride * 8),
                      (unsigned)(a.ostride * 4), 0u, 0, live, upper ? BAR_UPPER : BAR_LOWER};
-  const int64_t day_f64 = (int64_t)a.n_f64 * a.ostride * 8;
-  const int64_t day_i32 = (int64_t)a.n_i32 * a.ostride * 4;
-  out.pf = reinterpret_cast<char*>(a.out_f64 + ii);
-  out.pi = reinterpret_cast<char*>(a.out_i32 + ii);
+  // bytes from one day to the next, and this thread's element of the first day
+  const int64_t day_units = kMode == SINK_TILED ? (int64_t)gridDim.x * H : a.ostride;
+  const int64_t day_f64 = (int64_t)a.n_f64 * day_units * 8;
+  const int64_t day_i32 = (int64_t)a.n_i32 * day_units * 4;
+  if constexpr (kMode == SINK_TILED) {
+    out.pf = reinterpret_cast<char*>(a.out_f64 + (int64_t)blockIdx.x * a.n_f64 * H + r);
+    out.pi = reinterpret_cast<char*>(a.out_i32 + (int64_t)blockIdx.x * a.n_i32 * H + r);
+  } else {
+    out.pf = reinterpret_cast<char*>(a.out_f64 + ii);
+    out.pi = reinterpret_cast<char*>(a.out_i32 + ii);
+  }
   auto reduce_violations = [&](int d) {
     if (a.viol != nullptr && __any_sync(0xffffffffu, out.violmask != 0u)) {
       for (int p = 0; p < BUD_CHANNEL; ++p) {

@@ -374,6 +374,26 @@ class Engine:
         if sync:
             self.sync()
 
+    # ---- tiled result layout of run_device (include/pws_b200.h: pws_output_tile)
+    def set_tiled_outputs(self, on: bool = True):
+        """Results of run_device as [day][tile][variable][tile_units] (every HRU
+        variable must be selected in registry order)."""
+        self._opt("tiled_outputs", 1.0 if on else 0.0)
+        self.tiled = bool(on)
+
+    def output_tile(self):
+        """(tile_units, padded_units): units per tile and per padded variable row."""
+        t, p = C.c_int(), C.c_int64()
+        self._check(self.L.pws_output_tile(self.h, C.byref(t), C.byref(p)))
+        return t.value, p.value
+
+    def tiled_view(self, out, var: str):
+        """[nd, nhru] strided view of variable `var` in a tiled result tensor
+        `out` = [nd, tiles, n_vars_of_its_kind, tile_units] (torch or numpy)."""
+        sel = self.sel_f64 if self.reg.dtype(var) is np.float64 else self.sel_i32
+        v = out[:, :, sel.index(var), :]
+        return v.reshape(v.shape[0], -1)[:, :self.nhru]
+
     def run_channel_device(self, nd, d_seg_lat, d_seg_out, sync=True):
         self._check(self.L.pws_run_channel_device(self.h, nd, d_seg_lat, d_seg_out))
         if sync:

@@ -655,3 +655,58 @@ def test_route_hours_are_equivalent(drb, hours):
     out = out.cpu().numpy()
     for k, v in enumerate(po.SEG_VARS):
         np.testing.assert_array_equal(out[:, k], ref[v], err_msg=v)
+
+
+@pytest.mark.parametrize("ntile,column_hrus", [(1, 0), (2, 256), (3, 128)])
+def test_tiled_result_layout(drb, ntile, column_hrus):
+    """pws_run_device with `tiled_outputs` writes [day][tile][variable][H]
+    (include/pws_b200.h: pws_output_tile): against the oracle, the same bits
+    as the row layout, for both CTA sizes, a partial last tile whose padding
+    stays untouched, two consecutive blocks, and refused by pws_run_host and
+    for a partial selection."""
+    import torch
+
+    p, f, start = drb
+    pt, ft = scenarios.tile(p, f, ntile) if ntile > 1 else (p, f)
+    nd = 60
+    ref = _oracle(pt, ft, start, nd)[1]
+    rows, _ = _engine(pt, start).run_host(ft["prcp"][:nd], ft["tmax"][:nd], ft["tmin"][:nd])
+    e = _engine(pt, start)
+    if column_hrus:
+        e._opt("column_hrus", column_hrus)
+    e.set_tiled_outputs(True)
+    H, padded = e.output_tile()
+    assert H == (column_hrus or 128) and padded % H == 0 and 0 <= padded - e.nhru < H
+    dev = torch.device("cuda:0")
+    t = {k: torch.from_numpy(np.ascontiguousarray(ft[k][:nd])).to(dev) for k in ("prcp", "tmax", "tmin")}
+    nf, ni = len(e.sel_f64), len(e.sel_i32)
+    SENT_F, SENT_I = -7.25e300, -1234567
+    of = torch.full((nd, padded // H, nf, H), SENT_F, dtype=torch.float64, device=dev)
+    oi = torch.full((nd, padded // H, ni, H), SENT_I, dtype=torch.int32, device=dev)
+    osg = torch.empty((nd, 5, e.nseg), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    n1 = 23  # two blocks: the second starts at a day offset of the same buffers
+    for d0, n in ((0, n1), (n1, nd - n1)):
+        o = d0 * e.nhru * 8
+        e.run_device(n, t["prcp"].data_ptr() + o, t["tmax"].data_ptr() + o, t["tmin"].data_ptr() + o,
+                     of[d0:].data_ptr(), oi[d0:].data_ptr(), osg[d0:].data_ptr())
+    of, oi, osg = of.cpu().numpy(), oi.cpu().numpy(), osg.cpu().numpy()
+    got = {}
+    for v in e.sel_f64 + e.sel_i32:
+        a = e.tiled_view(of if v in e.sel_f64 else oi, v)
+        got[v] = a.astype(np.bool_) if e.reg.dtype(v) is np.bool_ else a
+        np.testing.assert_array_equal(got[v], np.asarray(rows[v]), err_msg=v)
+    for k, v in enumerate(e.sel_seg):
+        got[v] = osg[:, k, :]
+        np.testing.assert_array_equal(got[v], np.asarray(rows[v]), err_msg=v)
+    _assert_chain_parity(got, ref)
+    # the padding of the last tile is never written
+    pad = padded - e.nhru
+    if pad:
+        assert (of[:, -1, :, H - pad:] == SENT_F).all() and (oi[:, -1, :, H - pad:] == SENT_I).all()
+    with pytest.raises(ValueError, match="tiled_outputs"):
+        e.run_host(ft["prcp"][:2], ft["tmax"][:2], ft["tmin"][:2])
+    e.select_outputs(["pkwater_equiv"], [])
+    one = torch.empty((padded,), dtype=torch.float64, device=dev)
+    with pytest.raises(ValueError, match="tiled_outputs"):
+        e.run_device(1, t["prcp"].data_ptr(), t["tmax"].data_ptr(), t["tmin"].data_ptr(), one.data_ptr(), 0, 0)
