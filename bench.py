@@ -355,8 +355,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-block-days", type=int, default=128)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--tiled", action="store_true",
-                    help="results in the tiled layout [day][tile][variable][H] (pws_output_tile)")
+    ap.add_argument("--layout", choices=("tiled", "rows"), default="tiled",
+                    help="device-resident results as [day][tile][variable][H] (pws_output_tile; needs "
+                         "--outputs full) or as [day][variable][nhru] rows")
     args = ap.parse_args()
     if args.workload in ("channel", "channel_chained"):
         return run_channel_only(args)
@@ -400,10 +401,11 @@ def main():
     T = max(1, min(args.block_days, nd))
     nf = len(eng.sel_f64)
     ni = len(eng.sel_i32)
-    if args.tiled:
+    tiled = args.layout == "tiled" and args.outputs == "full"
+    if tiled:
         eng.set_tiled_outputs(True)
     # (the tiled layout pads the last tile: [T, tiles, n, H] has the same size as [T, n, padded])
-    onhru = eng.output_tile()[1] if args.tiled else nhru
+    onhru = eng.output_tile()[1] if tiled else nhru
     of = torch.empty((T, max(nf, 1), onhru), dtype=torch.float64, device=dev)
     oi = torch.empty((T, max(ni, 1), onhru), dtype=torch.int32, device=dev)
     osg = torch.empty((T, max(len(seg_vars), 1), max(nseg, 1)), dtype=torch.float64, device=dev)
@@ -463,7 +465,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         e2e_seg = ["seg_outflow"]  # streamflow at every segment: the product of an NHM run
-        if args.tiled:
+        if tiled:
             eng.set_tiled_outputs(False)  # a pws_run_device layout
         eng.select_outputs([], e2e_seg)
         hf = {k: v.cpu().pin_memory() for k, v in forc.items()}
@@ -558,7 +560,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": spec["label"] + (f" per GPU x {world} GPUs" if world > 1 else ""),
-                   "outputs": args.outputs, "layout": "tiled" if args.tiled else "rows", "n_output_vars": len(hru_vars) + len(seg_vars),
+                   "outputs": args.outputs, "layout": "tiled" if tiled else "rows", "n_output_vars": len(hru_vars) + len(seg_vars),
                    "block_days": T, "nhru_per_gpu": nhru, "nsegment_per_gpu": nseg, "ndays": nd,
                    "l2": "inputs larger than L2 (forcings 3 x %.1f GB per GPU, streamed once per step)"
                          % (nd * nhru * 8 / 1e9),
