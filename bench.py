@@ -84,7 +84,10 @@ def tile_offsets(ntile, rank):
 
 def device_forcings(f0, spec, rank, dev):
     """[ndays, nhru] float64 tensors on `dev`: DRB CBH cycled in time, tiled in
-    space with the per-tile climate offsets of tests/scenarios.py:tile."""
+    space with the per-tile climate offsets of tests/scenarios.py:tile, rounded
+    to float32-representable values: the reference's forcing files are float32
+    netCDF (test_data/{drb_2yr,ucb_2yr}/prcp.nc), and the e2e leg uploads them
+    in that type (pws_run_host_f32)."""
     import torch
 
     nd, ntile = spec["ndays"], spec["ntile"]
@@ -102,7 +105,7 @@ def device_forcings(f0, spec, rank, dev):
                 full[:, sl] = base * float(pscale[t])
             else:
                 full[:, sl] = base + float(dtemp[t])
-        out[k] = full[:, :nh].contiguous()
+        out[k] = full[:, :nh].float().double().contiguous()
         del full, base
     return out
 
@@ -354,6 +357,9 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-block-days", type=int, default=128)
+    ap.add_argument("--e2e-forcing", choices=("f32", "f64"), default="f32",
+                    help="type of the host forcing arrays of the e2e leg: float32 as in the reference's "
+                         "forcing files (widened on the device, exact) or float64")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--layout", choices=("tiled", "rows"), default="tiled",
                     help="device-resident results as [day][tile][variable][H] (pws_output_tile; needs "
@@ -468,7 +474,9 @@ def main():
         if tiled:
             eng.set_tiled_outputs(False)  # a pws_run_device layout
         eng.select_outputs([], e2e_seg)
-        hf = {k: v.cpu().pin_memory() for k, v in forc.items()}
+        f32 = args.e2e_forcing == "f32"
+        hf = {k: (v.float() if f32 else v).cpu().pin_memory() for k, v in forc.items()}
+        run_host = eng.L.pws_run_host_f32 if f32 else eng.L.pws_run_host
         e2e_T = args.e2e_block_days
         eng.set_block_days(e2e_T)
         # pin the result buffers too (the library drains with cudaMemcpyAsync)
@@ -485,7 +493,7 @@ def main():
             eng.reset()
             barrier()
             t0 = time.perf_counter()
-            eng._check(eng.L.pws_run_host(
+            eng._check(run_host(
                 eng.h, nd, cal.ctypes.data, hf["prcp"].data_ptr(), hf["tmax"].data_ptr(),
                 hf["tmin"].data_ptr(), dummy_f.ctypes.data, dummy_i.ctypes.data,
                 res_seg.data_ptr(), res_viol.ctypes.data))
@@ -499,7 +507,9 @@ def main():
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": units_per_step * len(ts) / float(te.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(3 * nd * nhru * 8) * world,
+               "h2d_bytes_per_step": int(3 * nd * nhru * (4 if f32 else 8)) * world,
+               "forcing_dtype": "float32 (as stored in the reference's forcing files; widened on the "
+                                "device)" if f32 else "float64",
                "d2h_bytes_per_step": int(nd * (len(e2e_seg) * nseg * 8 + 24)) * world,
                "outputs": "seg_outflow [ndays, nsegment] + 6 budget verdicts per day",
                "block_days": e2e_T, "checksum_seg_outflow_last_day": float(res_seg[-1, 0].sum())}

@@ -113,6 +113,17 @@ int pws_run_host(pws_handle *h, int ndays, const int32_t *h_cal,
                  double *h_out_f64, int32_t *h_out_i32, double *h_seg_out,
                  int32_t *h_budget_viol);
 
+/* The same with the forcings as float32 arrays [ndays][nhru]: the storage type
+ * of the reference's forcing files (test_data/{drb_2yr,ucb_2yr,hru_1}/
+ * {prcp,tmax,tmin}.nc are NC_FLOAT; numpy promotes them to float64 in the
+ * reference's first arithmetic on them, prms_atmosphere.py:311-312,399).  Half
+ * the bytes cross PCIe; the rows are widened on the device, which is exact,
+ * so the results equal pws_run_host on the widened arrays bit for bit. */
+int pws_run_host_f32(pws_handle *h, int ndays, const int32_t *h_cal,
+                     const float *h_prcp, const float *h_tmax, const float *h_tmin,
+                     double *h_out_f64, int32_t *h_out_i32, double *h_seg_out,
+                     int32_t *h_budget_viol);
+
 /* A SUBSET of the chain's processes, the others replaced by the caller's
  * arrays: what the reference does when a process (or a partial chain) is
  * driven from files, e.g. autotest/test_self_drive.py:83-115,

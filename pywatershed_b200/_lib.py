@@ -55,6 +55,7 @@ def lib():
         "pws_n_selected": (i32, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
         "pws_run_device": (i32, [vp, i32] + [vp] * 8),
         "pws_run_host": (i32, [vp, i32] + [vp] * 8),
+        "pws_run_host_f32": (i32, [vp, i32] + [vp] * 8),
         "pws_run_channel_device": (i32, [vp, i32, vp, vp]),
         "pws_n_inputs": (i32, []),
         "pws_input_name": (cp, [i32]),
@@ -88,5 +89,5 @@ EXPORTED_SYMBOLS = (
     "pws_run_channel_device", "pws_n_inputs", "pws_input_name", "pws_run_host_inputs", "pws_sync", "pws_get_state", "pws_set_state",
     "pws_launch_count", "pws_last_timing", "pws_column_kernel_info",
     "pws_timer_mark", "pws_timer_elapsed_ms", "pws_last_launches", "pws_reset_state",
-    "pws_output_tile",
+    "pws_output_tile", "pws_run_host_f32",
 )

@@ -140,6 +140,8 @@ struct pws_handle {
   // host ring for pws_run_host
   int ring_days = 0;
   double* d_forc[2] = {nullptr, nullptr};
+  float* d_forc32[2] = {nullptr, nullptr};  // float32 forcings as uploaded (pws_run_host_f32)
+  int forc32_days = 0;
   double* d_of64[2] = {nullptr, nullptr};
   int32_t* d_oi32[2] = {nullptr, nullptr};
   double* d_oseg[2] = {nullptr, nullptr};
@@ -269,11 +271,13 @@ static void free_ring(pws_handle* h) {
   free_stage(h);
   for (int b = 0; b < 2; ++b) {
     cudaFree(h->d_forc[b]); h->d_forc[b] = nullptr;
+    cudaFree(h->d_forc32[b]); h->d_forc32[b] = nullptr;
     cudaFree(h->d_of64[b]); h->d_of64[b] = nullptr;
     cudaFree(h->d_oi32[b]); h->d_oi32[b] = nullptr;
     cudaFree(h->d_oseg[b]); h->d_oseg[b] = nullptr;
   }
   h->ring_days = 0;
+  h->forc32_days = 0;
   h->ring_f64_elems = h->ring_i32_elems = h->ring_seg_elems = 0;
 }
 
@@ -1203,9 +1207,13 @@ static bool is_pinned(const void* p) {
 // buffers are used directly; pageable ones (numpy arrays) would turn every
 // cudaMemcpyAsync into a blocking copy, so they are staged through two pinned
 // slots per direction, filled / emptied by the host while the GPU works.
-extern "C" int pws_run_host(pws_handle* h, int ndays, const int32_t* h_cal, const double* h_prcp,
-                            const double* h_tmax, const double* h_tmin, double* h_out_f64,
-                            int32_t* h_out_i32, double* h_seg_out, int32_t* h_budget_viol) {
+//
+// `esz` is the element size of the caller's forcing arrays: 8 (float64) or 4
+// (float32: half the upload; the rows are widened on the device into the same
+// float64 ring, k_widen_forcings, before the block's column kernel).
+static int run_host_impl(pws_handle* h, int ndays, const int32_t* h_cal, const void* h_prcp,
+                         const void* h_tmax, const void* h_tmin, size_t esz, double* h_out_f64,
+                         int32_t* h_out_i32, double* h_seg_out, int32_t* h_budget_viol) {
   if (!h->inited) PWS_FAIL(h, "pws_run_host before pws_init");
   if (h->tiled_outputs) PWS_FAIL(h, "pws_run_host: tiled_outputs is a pws_run_device layout");
   if (ndays <= 0) return 0;
@@ -1240,6 +1248,17 @@ extern "C" int pws_run_host(pws_handle* h, int ndays, const int32_t* h_cal, cons
       PWS_CUDA(h, cudaMalloc(&h->d_oseg[b], h->ring_seg_elems * sizeof(double)));
     }
     h->ring_days = days;
+  }
+  if (esz == 4 && h->forc32_days < h->ring_days) {
+    cudaDeviceSynchronize();
+    for (int b = 0; b < 2; ++b) {
+      cudaFree(h->d_forc32[b]);
+      h->d_forc32[b] = nullptr;
+    }
+    h->forc32_days = 0;
+    for (int b = 0; b < 2; ++b)
+      PWS_CUDA(h, cudaMalloc(&h->d_forc32[b], (size_t)h->ring_days * 3 * n * sizeof(float)));
+    h->forc32_days = h->ring_days;
   }
   if (ensure_scratch(h, T)) return 1;
   const bool want_f64 = h->n_f64 > 0 && h_out_f64, want_i32 = h->n_i32 > 0 && h_out_i32;
@@ -1308,14 +1327,17 @@ extern "C" int pws_run_host(pws_handle* h, int ndays, const int32_t* h_cal, cons
     const int b = blk & 1;
     const int d0 = blk * T;
     const int nd = std::min(T, ndays - d0);
-    const double* srcs[3] = {h_prcp + (size_t)d0 * n, h_tmax + (size_t)d0 * n, h_tmin + (size_t)d0 * n};
+    const char* srcs[3] = {(const char*)h_prcp + (size_t)d0 * n * esz,
+                           (const char*)h_tmax + (size_t)d0 * n * esz,
+                           (const char*)h_tmin + (size_t)d0 * n * esz};
     // slot b: block blk-2 must have drained before its stage buffers are reused
     if (stage_out && blk >= 2 && drain_stage(blk - 2)) return 1;
     if (stage_in) {
       if (blk >= 2) PWS_CUDA(h, cudaEventSynchronize(h->ev_h2d[b]));  // hs_in[b] has been uploaded
       for (int k = 0; k < 3; ++k) {
-        par_memcpy(h->hs_in[b] + (size_t)k * RT * n, srcs[k], (size_t)nd * n * sizeof(double));
-        srcs[k] = h->hs_in[b] + (size_t)k * RT * n;
+        char* const slot = (char*)h->hs_in[b] + (size_t)k * RT * n * esz;
+        par_memcpy(slot, srcs[k], (size_t)nd * n * esz);
+        srcs[k] = slot;
       }
     }
     // the ring slot is free once its previous outputs have drained
@@ -1323,12 +1345,23 @@ extern "C" int pws_run_host(pws_handle* h, int ndays, const int32_t* h_cal, cons
     // forcing rows go into the ring with the padded row stride (16-byte aligned
     // rows for the TMA staging of k_hru_column)
     const size_t S8 = (size_t)h->stride * sizeof(double), n8 = (size_t)n * sizeof(double);
-    for (int k = 0; k < 3; ++k)
-      PWS_CUDA(h, cudaMemcpy2DAsync(h->d_forc[b] + (size_t)k * RT * h->stride, S8, srcs[k], n8, n8,
-                                    (size_t)nd, cudaMemcpyHostToDevice, h->s_h2d));
+    for (int k = 0; k < 3; ++k) {
+      if (esz == 8)
+        PWS_CUDA(h, cudaMemcpy2DAsync(h->d_forc[b] + (size_t)k * RT * h->stride, S8, srcs[k], n8, n8,
+                                      (size_t)nd, cudaMemcpyHostToDevice, h->s_h2d));
+      else  // float32 rows go up as they are (slot b was last read by block blk-2's widening)
+        PWS_CUDA(h, cudaMemcpyAsync(h->d_forc32[b] + (size_t)k * RT * n, srcs[k],
+                                    (size_t)nd * n * sizeof(float), cudaMemcpyHostToDevice, h->s_h2d));
+    }
     PWS_CUDA(h, cudaEventRecord(h->ev_h2d[b], h->s_h2d));
     PWS_CUDA(h, cudaStreamWaitEvent(h->s_compute, h->ev_h2d[b], 0));
     if (blk >= 2) PWS_CUDA(h, cudaStreamWaitEvent(h->s_compute, h->ev_d2h[b], 0));
+    if (esz == 4) {
+      k_widen_forcings<<<dim3((unsigned)((n + 255) / 256), (unsigned)nd, 3), 256, 0, h->s_compute>>>(
+          h->d_forc32[b], h->d_forc[b], n, h->stride, RT, RT);
+      h->launches++;
+      PWS_CUDA(h, cudaGetLastError());
+    }
     if (enqueue_block(h, nd, h_cal + (size_t)d0 * 4, h->d_forc[b],
                       h->d_forc[b] + (size_t)RT * h->stride, h->d_forc[b] + (size_t)2 * RT * h->stride,
                       h->stride, h->d_of64[b], h->d_oi32[b], h->d_oseg[b], h_budget_viol != nullptr))
@@ -1363,6 +1396,20 @@ extern "C" int pws_run_host(pws_handle* h, int ndays, const int32_t* h_cal, cons
   if (h_budget_viol)
     memcpy(h_budget_viol, h->hs_viol_run, (size_t)ndays * BUD_N * sizeof(int32_t));
   return rc;
+}
+
+extern "C" int pws_run_host(pws_handle* h, int ndays, const int32_t* h_cal, const double* h_prcp,
+                            const double* h_tmax, const double* h_tmin, double* h_out_f64,
+                            int32_t* h_out_i32, double* h_seg_out, int32_t* h_budget_viol) {
+  return run_host_impl(h, ndays, h_cal, h_prcp, h_tmax, h_tmin, sizeof(double), h_out_f64,
+                       h_out_i32, h_seg_out, h_budget_viol);
+}
+
+extern "C" int pws_run_host_f32(pws_handle* h, int ndays, const int32_t* h_cal, const float* h_prcp,
+                                const float* h_tmax, const float* h_tmin, double* h_out_f64,
+                                int32_t* h_out_i32, double* h_seg_out, int32_t* h_budget_viol) {
+  return run_host_impl(h, ndays, h_cal, h_prcp, h_tmax, h_tmin, sizeof(float), h_out_f64,
+                       h_out_i32, h_seg_out, h_budget_viol);
 }
 
 // --------------------------------------------------------------- sub-chains

@@ -12,6 +12,7 @@
 //                   segments, systolic hour-by-hour schedule over a block of
 //                   days, hand-over through double-buffered shared memory
 //   k_channel_budget per-day global channel mass balance
+//   k_widen_forcings float32 forcing rows (as uploaded) -> the float64 forcing ring
 #pragma once
 #include <cuda_runtime.h>
 
@@ -1095,6 +1096,21 @@ k_route_chunks(const __grid_constant__ ChannelArgs a) {
     a.outflow_ts[pos] = outflow_ts;
     a.seg_inflow[pos] = seg_inflow_prev;
   }
+}
+
+// Forcings uploaded as float32 (pws_run_host_f32: the storage type of the
+// reference's prcp / tmax / tmin netCDF files) widened into the float64 ring
+// k_hru_column reads: grid (ceil(n / 256), days, 3 variables).  float -> double
+// is exact, so the column sees the numbers the reference gets from
+// `ds[var][:].astype(float64)`.  src rows are n floats apart, dst rows `stride`
+// doubles (the padded, TMA-aligned ring rows).
+__global__ void __launch_bounds__(256)
+k_widen_forcings(const float* __restrict__ src, double* __restrict__ dst, int64_t n, int64_t stride,
+                 int64_t src_var_rows, int64_t dst_var_rows) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const int64_t d = blockIdx.y, k = blockIdx.z;
+  dst[(k * dst_var_rows + d) * stride + i] = (double)__ldg(src + (k * src_var_rows + d) * n + i);
 }
 
 // Global-basis channel budget (prms_channel.py:115,165-174; budget.py:388-416):

@@ -217,9 +217,11 @@ class Model:
         return cls(cls.model_dict_from_yaml(yaml_file))
 
     # ---------------------------------------------------------------- inputs
-    def _load_input(self, name, nunits):
+    def _load_input(self, name, nunits, keep_f32=False):
         """An 'adaptable' (base/adapter.py:143-190): ndarray [ntime, n], path to a CBH
-        ASCII / netCDF file, or None -> input_dir/<name>.{nc,cbh}."""
+        ASCII / netCDF file, or None -> input_dir/<name>.{nc,cbh}.  float64, or with
+        `keep_f32` the float32 of the source (the reference's forcing files): the
+        engine uploads those as they are and widens them on the device."""
         nt = self.control.n_times
         src = None
         for proc in self.processes.values():
@@ -243,7 +245,7 @@ class Model:
             if src.suffix == ".cbh":
                 times, arr = read_cbh(src, nunits)
             else:
-                times, arr = _read_netcdf_var(src, name)
+                times, arr = _read_netcdf_var(src, name, keep_f32=keep_f32)
         else:
             arr, times = np.asarray(src, dtype=np.float64), None
         if times is not None:
@@ -254,7 +256,8 @@ class Model:
             arr = arr[i0[0]:]
         if arr.ndim != 2 or arr.shape[1] != nunits or arr.shape[0] < nt:
             raise ValueError(f"input '{name}' must be [>= {nt}, {nunits}], got {arr.shape}")
-        return np.ascontiguousarray(arr[:nt], dtype=np.float64)
+        dt = np.float32 if keep_f32 and arr.dtype == np.float32 else np.float64
+        return np.ascontiguousarray(arr[:nt], dtype=dt)
 
     def _ensure_engine(self):
         if self._engine is not None:
@@ -295,7 +298,7 @@ class Model:
                                   adjust_parameters=adj, dprst_flag=bool(dprst),
                                   fill_missing=not dprst)
             nh = self._engine.nhru
-            self._forcings = {k: self._load_input(k, nh) for k in FORCINGS}
+            self._forcings = {k: self._load_input(k, nh, keep_f32=True) for k in FORCINGS}
         reg = self._engine.reg
         hv = list(reg.hru_vars) if self._mode != "channel" else [
             "channel_sroff_vol", "channel_ssres_flow_vol", "channel_gwres_flow_vol"]
@@ -593,8 +596,8 @@ def _pool():
     return _POOL
 
 
-def _read_netcdf_var(path, name):
+def _read_netcdf_var(path, name, keep_f32=False):
     """[time, unit] variable + decoded times from a netCDF file."""
     from .netcdf_in import read_time_variable
 
-    return read_time_variable(path, name)
+    return read_time_variable(path, name, keep_f32=keep_f32)

@@ -112,10 +112,10 @@ def decode_times(values, units: str) -> np.ndarray:
     return ref + off.astype("timedelta64[s]")
 
 
-def read_time_variable(path, name):
-    """[time, unit] variable `name` as float64 + its times (datetime64[s]).  The
-    time coordinate is `time` (or `datetime`, as in the reference's
-    test_data/hru_1/cbh.nc)."""
+def read_time_variable(path, name, keep_f32=False):
+    """[time, unit] variable `name` as float64 (or, with `keep_f32`, as the
+    float32 it is stored as) + its times (datetime64[s]).  The time coordinate is
+    `time` (or `datetime`, as in the reference's test_data/hru_1/cbh.nc)."""
     with open_netcdf(path) as ds:
         if name not in ds.variables:
             raise KeyError(f"{path}: no variable '{name}' (has {sorted(ds.variables)})")
@@ -127,4 +127,7 @@ def read_time_variable(path, name):
             raise ValueError(f"{path}: no time coordinate with units for '{name}'")
         t = ds.variables[tname]
         times = decode_times(t.read(), t.attrs["units"])
-        return times, np.asarray(var.read(), dtype=np.float64)
+        data = np.asarray(var.read())
+        if not (keep_f32 and data.dtype == np.float32):
+            data = data.astype(np.float64)
+        return times, data

@@ -710,3 +710,43 @@ def test_tiled_result_layout(drb, ntile, column_hrus):
     one = torch.empty((padded,), dtype=torch.float64, device=dev)
     with pytest.raises(ValueError, match="tiled_outputs"):
         e.run_device(1, t["prcp"].data_ptr(), t["tmax"].data_ptr(), t["tmin"].data_ptr(), one.data_ptr(), 0, 0)
+
+
+def test_float32_forcings_are_widened_on_the_device(drb):
+    """pws_run_host_f32: forcings in the storage type of the reference's
+    forcing files (float32 netCDF) are uploaded as they are and widened on the
+    device.  Same bits as pws_run_host on the widened arrays -- pageable and
+    page-locked inputs, several blocks so that both ring slots are reused, an
+    odd number of HRUs -- and the oracle's numbers."""
+    import torch
+
+    p, f, start = drb
+    nd = 75
+    f32 = {k: np.ascontiguousarray(f[k][:nd], dtype=np.float32) for k in ("prcp", "tmax", "tmin")}
+    f64 = {k: v.astype(np.float64) for k, v in f32.items()}
+    assert p["hru_area"].shape[0] % 2 == 1
+    ref = _oracle(p, f64, start, nd)[1]
+    e = _engine(p, start)
+    e.set_block_days(20)
+    l0 = e.launch_count()
+    a, va = e.run_host(f64["prcp"], f64["tmax"], f64["tmin"])
+    l1 = e.launch_count()
+    _assert_chain_parity(a, ref)
+    e.reset()
+    l2 = e.launch_count()
+    b, vb = e.run_host(f32["prcp"], f32["tmax"], f32["tmin"])
+    assert e.launch_count() - l2 == (l1 - l0) + 4  # one widening kernel per block of 20 days
+    e2 = _engine(p, start)
+    e2.set_block_days(20)
+    pin = {k: torch.from_numpy(v).pin_memory().numpy() for k, v in f32.items()}
+    c, vc = e2.run_host(pin["prcp"], pin["tmax"], pin["tmin"], pinned_outputs=True)
+    for k in po.HRU_VARS + po.SEG_VARS:
+        np.testing.assert_array_equal(np.asarray(b[k]), np.asarray(a[k]), err_msg=k)
+        np.testing.assert_array_equal(np.asarray(c[k]), np.asarray(a[k]), err_msg=k)
+    np.testing.assert_array_equal(va, vb)
+    np.testing.assert_array_equal(va, vc)
+    # one float64 array among them: everything goes up as float64
+    e3 = _engine(p, start)
+    d, _ = e3.run_host(f32["prcp"], f64["tmax"], f32["tmin"])
+    for k in ("pkwater_equiv", "soil_moist", "seg_outflow"):
+        np.testing.assert_array_equal(np.asarray(d[k]), np.asarray(a[k]), err_msg=k)

@@ -435,6 +435,10 @@ def test_hdf5_reader_on_the_reference_forcing_files(drb):
         assert times[0] == np.datetime64(start) and times[-1] == np.datetime64(start) + 730
         assert vals.dtype == np.float64 and vals.shape == (731, 765)
         np.testing.assert_array_equal(vals.astype(np.float32), f[k].astype(np.float32))
+        # ... or as stored (what pws_run_host_f32 uploads): float32, the same numbers
+        _, stored = read_time_variable(REF_TEST_DRB / f"{k}.nc", k, keep_f32=True)
+        assert stored.dtype == np.float32
+        np.testing.assert_array_equal(stored.astype(np.float64), vals)
     with open_netcdf(REF_TEST_DRB / "prcp.nc") as ds:
         assert ds.dims == {"nhm_id": 765, "time": 731}
         assert ds.variables["prcp"].dims == ("time", "nhm_id")
@@ -467,6 +471,9 @@ def test_model_from_the_reference_yaml(drb):
         a = m._load_input(k, 765)
         assert a.dtype == np.float64 and a.shape == (731, 765)
         np.testing.assert_array_equal(a.astype(np.float32), f[k].astype(np.float32))
+        a32 = m._load_input(k, 765, keep_f32=True)  # the full chain keeps the stored type
+        assert a32.dtype == np.float32 and a32.flags.c_contiguous
+        np.testing.assert_array_equal(a32.astype(np.float64), a)
     assert m.control.n_times == 731 and m.control.options["dprst_flag"] is True
     for k in ("soil_moist_max", "tmax_cbh_adj", "tosegment", "snarea_curve", "hru_segment", "mann_n"):
         np.testing.assert_array_equal(np.asarray(m._param_dict[k]).squeeze(), np.asarray(p[k]).squeeze(),
