@@ -356,7 +356,9 @@ def main():
     ap.add_argument("--block-days", type=int, default=256)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-block-days", type=int, default=128)
+    # measured on the CONUS workload (float32 forcings, HRU-days/s): 64 -> 3.50e9, 128 -> 3.53e9,
+    # 256 -> 3.88e9, 384 -> 3.76e9, 512 -> 3.57e9 (profiles/r01_e2e_block_days.jsonl)
+    ap.add_argument("--e2e-block-days", type=int, default=256)
     ap.add_argument("--e2e-forcing", choices=("f32", "f64"), default="f32",
                     help="type of the host forcing arrays of the e2e leg: float32 as in the reference's "
                          "forcing files (widened on the device, exact) or float64")

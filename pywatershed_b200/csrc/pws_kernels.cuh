@@ -65,7 +65,8 @@
 // 10-year pass, all lower state in registers: 104/152 142, 120/136 137,
 // 128/128 131, 136/120 122, 144/112 130; with PWS_COLUMN_LOWER_STATE_SMEM 2
 // (and the later store / forcing-slot changes): 128/128 117, 136/120 109,
-// 144/112 104, 152/104 115, 160/96 117.
+// 144/112 104, 152/104 115, 160/96 117; with the tiled result layout
+// (SINK_TILED): 136/120 105.6, 144/112 98.4, 152/104 105.5.
 #ifndef PWS_COLUMN_REGS_UPPER
 #define PWS_COLUMN_REGS_UPPER 144
 #endif
