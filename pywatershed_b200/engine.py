@@ -12,6 +12,14 @@ import numpy as np
 from . import _lib
 
 
+def untile(out, slot: int, nhru: int):
+    """Variable number `slot` of a tiled result buffer [nd, tiles, n_vars,
+    tile_units] (include/pws_b200.h: pws_output_tile) as [nd, nhru]: the tiles'
+    rows of that variable side by side, the padding of the last tile cut off."""
+    v = out[:, :, slot, :]
+    return v.reshape(v.shape[0], -1)[:, :nhru]
+
+
 def calendar(start, ndays: int) -> np.ndarray:
     """[ndays, 4] int32 (doy, dowy, month, day of month): what the reference's
     Control exposes per step (base/control.py:439-453,
@@ -399,8 +407,7 @@ class Engine:
         """[nd, nhru] strided view of variable `var` in a tiled result tensor
         `out` = [nd, tiles, n_vars_of_its_kind, tile_units] (torch or numpy)."""
         sel = self.sel_f64 if self.reg.dtype(var) is np.float64 else self.sel_i32
-        v = out[:, :, sel.index(var), :]
-        return v.reshape(v.shape[0], -1)[:, :self.nhru]
+        return untile(out, sel.index(var), self.nhru)
 
     def run_channel_device(self, nd, d_seg_lat, d_seg_out, sync=True):
         self._check(self.L.pws_run_channel_device(self.h, nd, d_seg_lat, d_seg_out))

@@ -514,3 +514,22 @@ def test_hdf5_reader_sweeps_every_reference_netcdf_file():
                 assert all(ds.dims[d] >= n for d, n in zip(v.dims, a.shape)), (fn, k)
                 nvar += 1
     assert nvar > 800
+
+
+def test_untile_reads_the_tiled_result_layout():
+    """Engine.tiled_view / untile against the layout include/pws_b200.h documents
+    for pws_output_tile: element (day d, variable k, unit i) of a tiled buffer is
+    at [d][i // H][k][i % H]."""
+    from pywatershed_b200.engine import untile
+
+    nd, nhru, nvar, H = 3, 765, 5, 128
+    tiles = -(-nhru // H)
+    rows = np.arange(nd * nvar * nhru, dtype=np.float64).reshape(nd, nvar, nhru)
+    buf = np.full((nd, tiles, nvar, H), -1.0)
+    for i in range(nhru):
+        buf[:, i // H, :, i % H] = rows[:, :, i]
+    for k in range(nvar):
+        np.testing.assert_array_equal(untile(buf, k, nhru), rows[:, k, :])
+    import torch
+
+    np.testing.assert_array_equal(untile(torch.from_numpy(buf), 2, nhru).numpy(), rows[:, 2, :])
