@@ -13,9 +13,11 @@ SolarGeometry / Atmosphere variables are all-time arrays written once per block
 with the same dims (their time axis is `doy` for the soltab tables).
 
 Backend: netCDF4 (zlib level 4, chunks (1, n), exactly the reference's files)
-when it is importable; otherwise scipy.io.netcdf_file, i.e. NetCDF-3 64-bit
-offset with the same names, dims, dtypes and attributes but no compression.
-Whole blocks are written with `var[t0:t1, :] = block`.
+when it is importable; otherwise our own streaming writer of the classic
+format (cdf_out.py: NetCDF-3 64-bit offset with the same names, dims, dtypes
+and attributes but no compression; a block of days is one contiguous write and
+nothing is held in memory).  Whole blocks are written with
+`var[t0:t1, :] = block`; the files of a block are written by a few threads.
 """
 from __future__ import annotations
 
@@ -40,6 +42,7 @@ def nc4_module():
 _nc4 = nc4_module()
 
 _NC_TYPES = {"float64": "f8", "int32": "i4", "bool": "i4", "int64": "i8"}
+_THREAD_BYTES = 64 << 20  # blocks at least this large are written by one thread per file
 
 
 class _File:
@@ -74,40 +77,59 @@ class _File:
                         v.setncattr(k, m[k])
                 self.v[name] = v
         else:
-            from scipy.io import netcdf_file
+            from .cdf_out import Cdf2Writer
 
-            ds = netcdf_file(str(path), "w", version=2)
-            ds.Description = "pywatershed output data"
-            setattr(ds, "process_class", process_name)
+            ds = Cdf2Writer(path)
+            ds.setncattr("Description", "pywatershed output data")
+            ds.setncattr("process class", process_name)
             ds.createDimension(time_name, n_doy)
             ds.createDimension(coord_name, len(coord_vals))
-            tv = ds.createVariable(time_name, "f4", (time_name,))
-            if time_name == "time":
-                tv.units = "days since 1970-01-01 00:00:00"
-            cv = ds.createVariable(coord_name, "i4", (coord_name,))
-            cv[:] = np.asarray(coord_vals, dtype=np.int32)
+            tatts = {"units": "days since 1970-01-01 00:00:00"} if time_name == "time" else {}
+            tv = ds.createVariable(time_name, "f4", (time_name,), **tatts)
+            self._cv = ds.createVariable(coord_name, "i4", (coord_name,))
+            self._coord_vals = np.asarray(coord_vals, dtype=np.int32)
             self.v = {}
             for name in self.vars:
                 m = VARIABLE_META.get(name, {})
-                v = ds.createVariable(name, _NC_TYPES[m.get("type", "float64")],
-                                      (time_name, coord_name))
-                for k in ("desc", "units"):
-                    if k in m:
-                        setattr(v, k, m[k])
-                self.v[name] = v
+                atts = {k: m[k] for k in ("desc", "units") if k in m}
+                self.v[name] = ds.createVariable(name, _NC_TYPES[m.get("type", "float64")],
+                                                 (time_name, coord_name), **atts)
         self.ds = ds
         self.tv = tv
 
+    def create_variable(self, name, kind):
+        """One more [time, unit] variable (before the first write)."""
+        if _nc4 is not None:
+            return self.ds.createVariable(name, kind, (self.time_name, self.coord_name))
+        self.v[name] = self.ds.createVariable(name, kind, (self.time_name, self.coord_name))
+        return self.v[name]
+
     def write(self, t0, t1, times_days, blocks: dict):
-        self.tv[t0:t1] = np.asarray(times_days, dtype=np.float32)
-        for name, arr in blocks.items():
-            if name in self.v:
-                a = np.asarray(arr)
-                if a.dtype == np.bool_:
-                    a = a.astype(np.int32)
-                self.v[name][t0:t1, :] = a
+        """Rows [t0, t1) of the time axis and of the variables in `blocks`."""
+        if _nc4 is not None:
+            self.tv[t0:t1] = np.asarray(times_days, dtype=np.float32)
+            for name, arr in blocks.items():
+                if name in self.v:
+                    a = np.asarray(arr)
+                    if a.dtype == np.bool_:
+                        a = a.astype(np.int32)
+                    self.v[name][t0:t1, :] = a
+            return
+        if self._coord_vals is not None:  # the header is complete now: variables are all declared
+            self._cv[:] = self._coord_vals
+            self._coord_vals = None
+        arrays = {self.time_name: np.asarray(times_days, dtype=np.float32)}
+        arrays.update({k: np.asarray(a) for k, a in blocks.items() if k in self.v})
+        if self.ds.rec_dim is not None:
+            self.ds.write_record_block(t0, t1, arrays)  # one contiguous write when all variables are there
+        else:
+            for k, a in arrays.items():
+                self.ds.vars[k][t0:t1] = a
 
     def close(self):
+        if _nc4 is None and self._coord_vals is not None:
+            self._cv[:] = self._coord_vals
+            self._coord_vals = None
         self.ds.close()
 
 
@@ -152,16 +174,32 @@ class ModelNetcdfOutput:
         start = model.control.start_time.astype("datetime64[D]")
         epoch = np.datetime64("1970-01-01", "D")
         tdays = (start - epoch).astype(int) + np.arange(t0, t1)
+        jobs = []
         for pname, doy, f in self.files:
             if doy:
                 if not self._written_static:
                     sg = model.processes[pname]
-                    f.write(0, 366, np.arange(1, 367), {v: sg[v].data for v in f.vars})
+                    jobs.append((f.write, (0, 366, np.arange(1, 367), {v: sg[v].data for v in f.vars})))
                 continue
-            f.write(t0, t1, tdays, {v: blk[v][t0 - b0:t1 - b0] for v in f.vars if v in blk})
-        self._written_static = True
+            jobs.append((f.write, (t0, t1, tdays,
+                                   {v: blk[v][t0 - b0:t1 - b0] for v in f.vars if v in blk})))
         for pname, bf in self.budget_files.items():
-            bf.write(t0, t1, tdays, blk, t0 - b0, t1 - b0)
+            jobs.append((bf.write, (t0, t1, tdays, blk, t0 - b0, t1 - b0)))
+        self._written_static = True
+        # Each job touches one file.  The conversion to the file's byte order and
+        # the write itself release the GIL, so for blocks worth the trouble a few
+        # threads write the files side by side.
+        nbytes = sum(getattr(x, "nbytes", 0) for _, a in jobs if isinstance(a[3], dict)
+                     for x in a[3].values())
+        if len(jobs) > 1 and nbytes >= _THREAD_BYTES and _nc4 is None:
+            from concurrent.futures import ThreadPoolExecutor
+
+            with ThreadPoolExecutor(min(8, len(jobs))) as pool:
+                for fut in [pool.submit(fn, *a) for fn, a in jobs]:
+                    fut.result()
+        else:
+            for fn, a in jobs:
+                fn(*a)
 
     def close(self):
         for _, _, f in self.files:
@@ -179,16 +217,13 @@ class _BudgetFile:
         self.glob = budget.basis == "global"
         coord = np.array([0]) if self.glob else nhm_id
         self.f = _File(path, [], "one" if self.glob else "nhm_id", coord, pname)
-        ds = self.f.ds
         self.v = {}
         for name in ("inputs_sum", "outputs_sum", "storage_changes_sum"):
-            if _nc4 is not None:
-                self.v[name] = ds.createVariable(name, "f8", ("time", self.f.coord_name))
-            else:
-                self.v[name] = ds.createVariable(name, "f8", ("time", self.f.coord_name))
+            self.v[name] = self.f.create_variable(name, "f8")
+        self.f.v = dict(self.v)
 
     def write(self, t0, t1, tdays, blk, j0, j1):
-        self.f.tv[t0:t1] = np.asarray(tdays, dtype=np.float32)
+        sums = {}
         for comp, name in (("inputs", "inputs_sum"), ("outputs", "outputs_sum"),
                            ("storage_changes", "storage_changes_sum")):
             terms = [np.asarray(blk[v][j0:j1], dtype=np.float64) for v in self.budget.terms[comp]
@@ -199,7 +234,8 @@ class _BudgetFile:
                 tot = sum(t.sum(axis=1) for t in terms)[:, None]
             else:
                 tot = sum(terms)
-            self.v[name][t0:t1, :] = tot
+            sums[name] = tot
+        self.f.write(t0, t1, tdays, sums)
 
     def close(self):
         self.f.close()

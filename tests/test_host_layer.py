@@ -533,3 +533,138 @@ def test_untile_reads_the_tiled_result_layout():
     import torch
 
     np.testing.assert_array_equal(untile(torch.from_numpy(buf), 2, nhru).numpy(), rows[:, 2, :])
+
+
+def test_streaming_classic_writer_against_scipy(tmp_path):
+    """cdf_out.Cdf2Writer (the output backend without the netCDF4 module) read
+    back by an independent implementation, scipy.io.netcdf_file: several record
+    variables of different types in one file written block by block (one
+    contiguous write per block), a block with one variable missing (row-wise
+    path), blocks out of order, a fixed-size `doy` file, attributes with the
+    reference's names, and numrecs brought up to date by flush()."""
+    from scipy.io import netcdf_file
+
+    from pywatershed_b200.netcdf_out import _File, nc4_module
+
+    if nc4_module() is not None:
+        pytest.skip("netCDF4 is the backend here")
+    rng = np.random.default_rng(5)
+    n, nt = 37, 11
+    a = rng.normal(size=(nt, n))
+    b = rng.integers(-5, 5, size=(nt, n)).astype(np.int32)
+    c = rng.integers(0, 2, size=(nt, n)).astype(np.bool_)
+    names = ["pkwater_equiv", "newsnow", "iasw"]  # float64, int32, bool in the metadata
+    ids = np.arange(100, 100 + n)
+    f = _File(tmp_path / "PRMSSnow.nc", names, "nhm_id", ids, "PRMSSnow")
+    t = 3287.0 + np.arange(nt)
+    f.write(4, 8, t[4:8], {"pkwater_equiv": a[4:8], "newsnow": b[4:8], "iasw": c[4:8]})  # out of order
+    f.write(0, 4, t[0:4], {"pkwater_equiv": a[0:4], "newsnow": b[0:4], "iasw": c[0:4]})
+    f.ds.flush()
+    with netcdf_file(str(tmp_path / "PRMSSnow.nc"), "r", mmap=False) as ds:
+        assert ds.variables["time"].shape == (8,)  # numrecs is in the header before close
+    f.write(8, nt, t[8:], {"pkwater_equiv": a[8:], "iasw": c[8:]})  # newsnow missing: rows 8.. stay zero
+    f.close()
+    with netcdf_file(str(tmp_path / "PRMSSnow.nc"), "r", mmap=False) as ds:
+        assert ds.Description == b"pywatershed output data"
+        assert ds._attributes["process class"] == b"PRMSSnow"
+        assert ds.dimensions == {"time": None, "nhm_id": n}
+        v = ds.variables
+        assert v["pkwater_equiv"].dimensions == ("time", "nhm_id") and v["pkwater_equiv"].units == b"inches"
+        assert v["pkwater_equiv"][:].dtype == np.dtype(">f8") and v["newsnow"][:].dtype == np.dtype(">i4")
+        np.testing.assert_array_equal(v["pkwater_equiv"][:], a)
+        np.testing.assert_array_equal(v["newsnow"][:8], b[:8])
+        np.testing.assert_array_equal(v["newsnow"][8:], 0)
+        np.testing.assert_array_equal(v["iasw"][:], c.astype(np.int32))
+        np.testing.assert_array_equal(v["time"][:], t.astype(np.float32))
+        np.testing.assert_array_equal(v["nhm_id"][:], ids)
+    # our own reader opens it too (classic files go through scipy there)
+    from pywatershed_b200.netcdf_in import read_time_variable
+
+    times, vals = read_time_variable(tmp_path / "PRMSSnow.nc", "pkwater_equiv")
+    np.testing.assert_array_equal(vals, a)
+    assert times[0] == np.datetime64("1979-01-01")
+    # fixed-size file: the soltab tables on a `doy` axis
+    g = _File(tmp_path / "soltab_potsw.nc", ["soltab_potsw"], "nhm_id", ids, "PRMSSolarGeometry",
+              time_name="doy", n_doy=366)
+    s = rng.normal(size=(366, n))
+    g.write(0, 366, np.arange(1, 367), {"soltab_potsw": s})
+    g.close()
+    with netcdf_file(str(tmp_path / "soltab_potsw.nc"), "r", mmap=False) as ds:
+        assert ds.dimensions == {"doy": 366, "nhm_id": n}
+        np.testing.assert_array_equal(ds.variables["soltab_potsw"][:], s)
+        np.testing.assert_array_equal(ds.variables["doy"][:], np.arange(1, 367, dtype=np.float32))
+        np.testing.assert_array_equal(ds.variables["nhm_id"][:], ids)
+    # a single record variable besides nothing else: the unpadded lone-record case
+    from pywatershed_b200.cdf_out import Cdf2Writer
+
+    w = Cdf2Writer(tmp_path / "lone.nc")
+    w.createDimension("time", None)
+    w.createDimension("x", 3)
+    x = w.createVariable("x", "i4", ("x",))
+    q = w.createVariable("q", "f4", ("time", "x"), units="cfs")
+    x[:] = [7, 8, 9]
+    q[0:2] = np.array([[1, 2, 3], [4, 5, 6]], dtype=np.float64)
+    q[2] = [7.5, 8.5, 9.5]
+    w.close()
+    with netcdf_file(str(tmp_path / "lone.nc"), "r", mmap=False) as ds:
+        np.testing.assert_array_equal(ds.variables["q"][:], [[1, 2, 3], [4, 5, 6], [7.5, 8.5, 9.5]])
+        np.testing.assert_array_equal(ds.variables["x"][:], [7, 8, 9])
+        assert ds.variables["q"].units == b"cfs"
+
+
+def test_model_netcdf_output_on_a_stubbed_block(drb, tmp_path, monkeypatch):
+    """ModelNetcdfOutput.write_days over a block of results that did not come
+    from the GPU (the engine is a stub): the files and budget files of
+    tests/test_gpu_model.py::test_netcdf_output_files, written block by block
+    (in threads when the block is large) and read back with scipy."""
+    import types
+
+    from scipy.io import netcdf_file
+
+    import pywatershed_b200 as pwsb
+    from pywatershed_b200 import netcdf_out
+
+    if netcdf_out.nc4_module() is not None:
+        pytest.skip("netCDF4 is the backend here")
+    p, f, start = drb
+    nhru, nseg, nd = 765, 456, 9
+    params = pwsb.Parameters(dims={"nhru": nhru, "nsegment": nseg},
+                             coords={"nhm_id": np.arange(1, nhru + 1), "nhm_seg": np.arange(1, nseg + 1)},
+                             data_vars=p)
+    m = pwsb.Model([pwsb.PRMSSolarGeometry, pwsb.PRMSAtmosphere, pwsb.PRMSCanopy, pwsb.PRMSSnow,
+                    pwsb.PRMSRunoff, pwsb.PRMSSoilzone, pwsb.PRMSGroundwater, pwsb.PRMSChannel],
+                   control=_control(nd, budget_type="warn"), parameters=params, find_input_files=False)
+    m._engine = types.SimpleNamespace(nhru=nhru, nseg=nseg)
+    rng = np.random.default_rng(11)
+    out_vars = ["pkwater_equiv", "seg_outflow", "newsnow", "iasw", "soltab_potsw"]
+    snow_terms = [v for comp in m.processes["PRMSSnow"].budget.terms.values() for v in comp]
+    blk = {v: rng.normal(size=(nd, nhru)) for v in set(snow_terms) | {"pkwater_equiv"}}
+    blk["seg_outflow"] = rng.normal(size=(nd, 3, nseg))[:, 1, :]  # a strided view, as the engine hands out
+    blk["newsnow"] = rng.integers(0, 2, size=(nd, nhru)).astype(np.int32)
+    blk["iasw"] = rng.integers(0, 2, size=(nd, nhru)).astype(np.bool_)
+    m._block, m._block_t0 = blk, 0
+    monkeypatch.setattr(netcdf_out, "_THREAD_BYTES", 1)  # take the threaded path at this size too
+    out = netcdf_out.ModelNetcdfOutput(m, tmp_path, True, out_vars, None)
+    out.write_days(m, 0, 4)
+    out.write_days(m, 4, nd)
+    out.close()
+
+    def read(name, var):
+        with netcdf_file(str(tmp_path / name), "r", mmap=False) as ds:
+            return np.array(ds.variables[var][:]), ds.variables[var].dimensions
+
+    for v in ("pkwater_equiv", "seg_outflow", "newsnow", "iasw"):
+        a, dims = read(f"{v}.nc", v)
+        assert dims == ("time", "nhm_seg" if v == "seg_outflow" else "nhm_id")
+        np.testing.assert_array_equal(a, np.asarray(blk[v]).astype(a.dtype), err_msg=v)
+    a, dims = read("soltab_potsw.nc", "soltab_potsw")
+    assert dims == ("doy", "nhm_id") and a.shape == (366, nhru)
+    b = m.processes["PRMSSnow"].budget
+    for comp, name in (("inputs", "inputs_sum"), ("outputs", "outputs_sum"),
+                       ("storage_changes", "storage_changes_sum")):
+        a, dims = read("PRMSSnow_budget.nc", name)
+        assert dims == ("time", "nhm_id")
+        np.testing.assert_allclose(a, sum(blk[v] for v in b.terms[comp]), rtol=0, atol=1e-12)
+    t, _ = read("PRMSSnow_budget.nc", "time")
+    day0 = (m.control.start_time.astype("datetime64[D]") - np.datetime64("1970-01-01", "D")).astype(int)
+    np.testing.assert_array_equal(t, (day0 + np.arange(nd)).astype(np.float32))
