@@ -668,3 +668,21 @@ def test_model_netcdf_output_on_a_stubbed_block(drb, tmp_path, monkeypatch):
     t, _ = read("PRMSSnow_budget.nc", "time")
     day0 = (m.control.start_time.astype("datetime64[D]") - np.datetime64("1970-01-01", "D")).astype(int)
     np.testing.assert_array_equal(t, (day0 + np.arange(nd)).astype(np.float32))
+
+
+@needs_ref_nc
+def test_hdf5_reader_threads_give_the_same_arrays(monkeypatch):
+    """Large chunked variables are inflated / unshuffled by several threads
+    (hdf5_min._THREAD_BYTES); forced on for the reference's UCB forcing file
+    (25 chunks, shuffle + deflate) it returns the serial reader's array."""
+    from pywatershed_b200 import hdf5_min
+    from pywatershed_b200.netcdf_in import read_time_variable
+
+    path = REF_TEST_DRB.parent / "ucb_2yr" / "prcp.nc"
+    monkeypatch.setattr(hdf5_min, "_THREAD_BYTES", 1 << 60)
+    t0, serial = read_time_variable(path, "prcp", keep_f32=True)
+    monkeypatch.setattr(hdf5_min, "_THREAD_BYTES", 1)
+    t1, threaded = read_time_variable(path, "prcp", keep_f32=True)
+    assert serial.shape == (731, 3851) and serial.dtype == np.float32
+    np.testing.assert_array_equal(threaded, serial)
+    np.testing.assert_array_equal(t0, t1)
