@@ -1,0 +1,41 @@
+"""The JSON line of `bench.py --impl reference` (the CPU arm the driver runs
+beside the GPU arm): keys, units and the bounded sample, on this machine's host
+cores.  The GPU arm's line is checked by tests/test_gpu_fullsize.py."""
+import json
+import pathlib as pl
+import subprocess
+import sys
+
+ROOT = pl.Path(__file__).resolve().parent.parent
+
+
+def test_reference_arm_prints_one_json_line():
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"].startswith("simulated HRU-days/sec")
+    assert d["unit"] == "HRU-days/s" and d["higher_is_better"] is True and d["n_gpus"] == 1
+    assert d["steps"] == 1 and d["warmup"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["dtype"] == "f64" and d["data"] == "synthetic" and d["vs_baseline"] is None
+    assert "CONUS" in d["config"]["workload"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "DRB tile" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "HRU-days/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0
+
+
+def test_gpu_arm_fails_loudly_without_a_gpu():
+    """No CPU fallback: without a CUDA device the product arm must not print a number."""
+    import torch
+
+    if torch.cuda.is_available():
+        return
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "1", "--warmup", "1",
+                        "--workload", "ucb", "--no-cpu"], capture_output=True, text=True, timeout=600,
+                       cwd=ROOT)
+    assert r.returncode != 0
+    assert not any(ln.lstrip().startswith("{") for ln in r.stdout.splitlines())
