@@ -1,7 +1,9 @@
 """bench.py -- simulated HRU-days/s of the full NHM chain on B200 (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload conus|ucb|drb|ensemble|ensemble128|channel|channel_chained]
-                    [--outputs full|nhm_default|routing] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W]
+                    [--workload conus|ensemble|ucb|drb|channel|channel_chained]
+                    [--scaling strong|weak] [--outputs full|nhm_default|routing]
+                    [--impl reference [--ref port|numpy|numba]]
 
 A *step* is one pass of the hot path over the whole workload: reset to the
 initial conditions, then every day of the run (time-blocked).  Default
@@ -12,17 +14,28 @@ temperature offset / precipitation scale (tests/scenarios.py:tile).  It is the
 configuration north_star's target is quoted on and fits one GPU; configs[1]
 (3,851 HRUs) fills 30 of 148 SMs and is available as `--workload ucb`.
 
-  value   HRU-days/s, forcings already resident in HBM, every public variable
-          (143 HRU + 5 segment) written to HBM each day ("full" outputs)
-  e2e     the same run through the host-facing entry point (Engine.run_host ->
-          pws_run_host): forcings in pinned HOST memory, H2D every step,
-          segment outputs + budget verdicts drained D2H every step
-  N > 1   weak scaling: every rank simulates its own 144-tile set (independent
-          basins, no data-path collective); NCCL only reduces times/budgets
+  value   HRU-days/s of the whole job, forcings already resident in HBM, every
+          public variable (143 HRU + 5 segment) written to HBM each day
+  e2e     the same domain through the host-facing entry point (pws_run_host_f32):
+          forcings in pinned HOST memory, H2D every step, streamflow + budget
+          verdicts drained D2H every step
+  N > 1   STRONG scaling, as BASELINE.json configs[2] says ("basin-sharded
+          1/2/4/8 GPU"): the ONE 110,160-HRU domain is partitioned by outlet tree
+          (pywatershed_b200/sharding.py), every rank simulates its own basins
+          with no data-path collective, NCCL gathers the budget verdicts and a
+          streamflow checksum.  `--scaling weak` is the round-1 replica mode
+          (every rank its own 144-tile set).
+  extra   objects in the same JSON line: `ensemble` (configs[3]: the 1024-member
+          DRB parameter ensemble, members perturbed as SURVEY.md 8d says, the
+          members' common forcings uploaded once, sharded by member),
+          `e2e_nhm_default` (the reference control file's 74 output variables
+          drained to the host), `pcie` (the box's plain cudaMemcpyAsync ceiling),
+          `e2e_model` (the Model API, N = 1).
 
-`--impl reference` times the CPU oracle port (oracle/prms_oracle.c, the
-reference's algorithm restated in C; the Python reference cannot travel to the
-GPU box) on the host cores, one tile set per thread.
+`--impl reference` times the reference's CPU implementation on the host cores:
+`--ref port` (default) the C restatement oracle/prms_oracle.c on every core;
+`--ref numpy|numba` the unmodified pywatershed package packed into oracle/_ref
+by oracle/pack_ref.py (drb_2yr, one process per core).
 """
 from __future__ import annotations
 
@@ -45,6 +58,7 @@ for p in (ROOT, ROOT / "tests"):
 METRIC = "simulated HRU-days/sec, full NHM chain"
 UNIT = "HRU-days/s"
 BYTES_READ = 40  # prcp,tmax,tmin + 2 soltab rows, SURVEY.md 8(d)
+NB_HRU, NB_SEG = 765, 456  # drb_2yr
 
 
 def workload_spec(name):
@@ -56,15 +70,16 @@ def workload_spec(name):
                     "(3,851 HRUs, 2,736 segments, 731 days; real ucb_2yr inputs are HDF5 blobs)")
     if name in ("ensemble", "ensemble128"):
         nm = 1024 if name == "ensemble" else 128
-        return dict(ntile=nm, nhru_keep=None, ndays=731, label=f"{nm}-member DRB parameter ensemble "
-                    f"({nm * 765:,} HRUs, {nm * 456:,} segments member-major, 731 days)")
+        return dict(ntile=nm, nhru_keep=None, ndays=731, ensemble=True,
+                    label=f"{nm}-member DRB parameter ensemble ({nm * NB_HRU:,} HRUs, {nm * NB_SEG:,} "
+                          "segments member-major, perturbed soil/snow parameters, shared forcings, 731 days)")
     if name == "drb":
         return dict(ntile=1, nhru_keep=None, ndays=731, label="drb_2yr (765 HRUs, 456 segments, 731 days)")
     raise SystemExit(f"unknown workload {name}")
 
 
 def build_domain(spec, rank=0):
-    """Parameters (host, small) + base forcings; tile offsets differ per rank."""
+    """Parameters (host, small) + base forcings of the whole tiled domain."""
     import scenarios
 
     p0, f0, start = scenarios.load_drb()
@@ -82,32 +97,67 @@ def tile_offsets(ntile, rank):
     return dtemp, pscale
 
 
-def device_forcings(f0, spec, rank, dev):
-    """[ndays, nhru] float64 tensors on `dev`: DRB CBH cycled in time, tiled in
+def device_forcings(f0, spec, rank, dev, hru_idx=None):
+    """[ndays, n] float64 tensors on `dev`: DRB CBH cycled in time, tiled in
     space with the per-tile climate offsets of tests/scenarios.py:tile, rounded
     to float32-representable values: the reference's forcing files are float32
     netCDF (test_data/{drb_2yr,ucb_2yr}/prcp.nc), and the e2e leg uploads them
-    in that type (pws_run_host_f32)."""
+    in that type (pws_run_host_f32).  `hru_idx`: the HRUs of the tiled domain
+    to build columns for (a basin shard); default all."""
     import torch
 
     nd, ntile = spec["ndays"], spec["ntile"]
     nb = f0["prcp"].shape[1]
     nh = spec["nhru_keep"] or nb * ntile
+    if hru_idx is None:
+        hru_idx = np.arange(nh)
+    hru_idx = np.asarray(hru_idx, dtype=np.int64)
     dtemp, pscale = tile_offsets(ntile, rank)
+    tile_of = torch.from_numpy(hru_idx // nb).to(dev)
+    col_of = torch.from_numpy(hru_idx % nb).to(dev)
+    dt_h = torch.from_numpy(dtemp).to(dev)[tile_of]
+    ps_h = torch.from_numpy(pscale).to(dev)[tile_of]
     out = {}
     tidx = torch.arange(nd, device=dev) % f0["prcp"].shape[0]
     for k in ("prcp", "tmax", "tmin"):
         base = torch.from_numpy(f0[k]).to(dev)[tidx]  # [nd, nb]
-        full = torch.empty((nd, nb * ntile), dtype=torch.float64, device=dev)
-        for t in range(ntile):
-            sl = slice(t * nb, (t + 1) * nb)
-            if k == "prcp":
-                full[:, sl] = base * float(pscale[t])
-            else:
-                full[:, sl] = base + float(dtemp[t])
-        out[k] = full[:, :nh].float().double().contiguous()
+        full = base[:, col_of]
+        full = full * ps_h[None, :] if k == "prcp" else full + dt_h[None, :]
+        out[k] = full.float().double().contiguous()
         del full, base
     return out
+
+
+# SURVEY.md 8(d) config 4: member m scales these parameters by U(0.8, 1.2)
+# (seed = m), clipped to [minimum, maximum] of the reference's
+# static/metadata/parameters.yaml; forcings are shared by the members.
+ENSEMBLE_PARAMS = {
+    "soil_moist_max": (1e-05, 20.0), "soil_rechr_max_frac": (1e-05, 1.0), "soil2gw_max": (0.0, 5.0),
+    "ssr2gw_rate": (0.0001, 1.0), "slowcoef_lin": (0.0, 1.0), "slowcoef_sq": (0.0, 1.0),
+    "smidx_coef": (0.0, 1.0), "carea_max": (0.0, 1.0), "gwflow_coef": (0.0, 0.5),
+    "tmax_allsnow": (-10.0, 40.0), "freeh2o_cap": (0.01, 0.2), "emis_noppt": (0.757, 1.0),
+    "rad_trncf": (0.0, 1.0), "cecn_coef": (0.02, 20.0), "potet_sublim": (0.1, 0.75),
+}
+
+
+def ensemble_parameters(p0, members):
+    """Member-major parameters of the ensemble members `members` (global member
+    numbers): per-HRU / per-segment arrays repeated, the ENSEMBLE_PARAMS
+    scaled per member and HRU, tosegment / hru_segment offset per member."""
+    import scenarios
+
+    members = np.asarray(members)
+    nm = members.size
+    dummy = {k: np.zeros((2, NB_HRU)) for k in ("prcp", "tmax", "tmin")}
+    pt, _ = scenarios.tile(p0, dummy, nm, temp_shift=False)
+    for k, (lo, hi) in ENSEMBLE_PARAMS.items():
+        v = np.array(pt[k], dtype=np.float64, copy=True)
+        for j, m in enumerate(members):
+            rng = np.random.default_rng(int(m))
+            sl = slice(j * NB_HRU, (j + 1) * NB_HRU)
+            v[..., sl] = np.clip(v[..., sl] * rng.uniform(0.8, 1.2, size=v[..., sl].shape), lo, hi)
+        pt[k] = v
+    return pt
 
 
 def output_sets(reg, mode):
@@ -219,11 +269,70 @@ def cpu_oracle_rate(p0, f0, start, ntile_per_thread, ndays, nthreads):
     return units / dt, units, dt
 
 
+def _ref_worker(args):
+    """One process of the numpy / numba reference arm: the unmodified
+    pywatershed package from oracle/_ref, drb_2yr through pws.Model."""
+    calc_method, ndays, warm = args
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import ref_pack
+
+    return ref_pack.time_drb(calc_method, ndays, warm)
+
+
+def run_reference_python(args, spec, calc_method):
+    """--impl reference --ref numpy|numba: the UNMODIFIED reference package
+    (packed into oracle/_ref by oracle/pack_ref.py at build()), drb_2yr NHM chain
+    through pws.Model (asv_benchmarks/benchmarks/prms.py:146-171), one process
+    per host core as examples/05_parameter_ensemble.ipynb does, netCDF output
+    off; numba's JIT warm-up (a 5-day run) is outside the timed region."""
+    from concurrent.futures import ProcessPoolExecutor
+
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import ref_pack
+
+    if not ref_pack.available():
+        print(json.dumps({"impl": "reference", "unavailable":
+                          "oracle/_ref (the packed reference package) is missing: run build() where "
+                          "/root/reference exists"}))
+        return
+    ncores = os.cpu_count() or 1
+    nproc = max(1, min(ncores, 64))
+    ndays = 731
+    rates = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        with ProcessPoolExecutor(max_workers=nproc) as ex:
+            res = list(ex.map(_ref_worker, [(calc_method, ndays, calc_method == "numba")] * nproc))
+        wall = max(r["seconds"] for r in res)  # processes run side by side: the slowest one
+        if it >= args.warmup:
+            rates.append((nproc * NB_HRU * ndays, wall))
+        del t0
+    units = sum(u for u, _ in rates)
+    dt = sum(d for _, d in rates)
+    value = units / dt
+    one = res[0]
+    sample = (f"{nproc} processes x drb_2yr (765 HRUs, 456 segments) x {ndays} days, pywatershed "
+              f"{one.get('version', '?')} calc_method={calc_method}, pws.Model.run, no output; "
+              f"one process: {one['seconds']:.1f} s; last-day sum(seg_outflow)={one['sum_seg_outflow']:.6f}")
+    print(json.dumps({
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(len(rates), 1),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "impl": "reference",
+        "config": {"workload": spec["label"], "note": "bounded sample of the workload on host cores: "
+                   "independent drb_2yr basins, one per core"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nproc, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
 def run_reference(args, spec):
-    """--impl reference: the CPU oracle port on all host cores."""
+    """--impl reference: the CPU implementation on all host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.ref in ("numpy", "numba"):
+        return run_reference_python(args, spec, args.ref)
     import scenarios
 
     p0, f0, start = scenarios.load_drb()
@@ -244,7 +353,7 @@ def run_reference(args, spec):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(len(rates), 1),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "impl": "reference",
         "config": {"workload": spec["label"], "note": "bounded sample of the workload on host cores"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
@@ -315,8 +424,8 @@ def run_channel_only(args):
             eng.run_channel_device(n, lat.data_ptr() + d * nseg * 8, out.data_ptr(), sync=False)
             d += n
         eng.timer_mark(1)
+        eng.sync()
         torch.cuda.synchronize()
-        eng.timing()
         return eng.timer_elapsed_ms()
 
     for _ in range(args.warmup):
@@ -346,15 +455,213 @@ def run_channel_only(args):
         "gpu_launches": eng.launch_count(), "clocks": clocks}))
 
 
+# --------------------------------------------------------------------------- the chain
+class Dist:
+    """torch.distributed plumbing of one rank (NCCL; a single process when N = 1)."""
+
+    def __init__(self):
+        import torch
+
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: pywatershed_b200 has no CPU path")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            import torch.distributed as dist
+
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            # keep stdout to the one JSON line: NCCL prints its version banner to stdout at the
+            # VERSION and WARN levels; anything more verbose the user asked for goes to stderr
+            if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+                del os.environ["NCCL_DEBUG"]
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        import torch
+
+        torch.cuda.synchronize()
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max(self, x: float) -> float:
+        import torch
+
+        t = torch.tensor([x], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum(self, x) -> np.ndarray:
+        import torch
+
+        t = torch.as_tensor(np.asarray(x, dtype=np.float64), device=self.dev).clone()
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+    def close(self):
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
+
+
+def make_shard(spec, D: Dist, scaling: str):
+    """This rank's part of the workload: parameters, the HRUs / segments of the
+    whole domain it owns, and how many HRU-days the whole job is."""
+    from pywatershed_b200 import sharding
+    import scenarios
+
+    if spec.get("ensemble"):
+        p0, f0, start = scenarios.load_drb()
+        nm = spec["ntile"]
+        if scaling == "strong":
+            members = sharding.partition_members(nm, D.world, D.rank)
+            total = nm
+        else:
+            members = np.arange(nm) + D.rank * nm
+            total = nm * D.world
+        pt = ensemble_parameters(p0, members)
+        return dict(p0=p0, f0=f0, start=start, params=pt, hru_idx=None, members=members,
+                    forcing_period=NB_HRU, job_hrus=total * NB_HRU, job_segs=total * NB_SEG,
+                    parallelism=f"member-sharded x{D.world} ({members.size} members on this rank), "
+                                "no data-path collective")
+    p0, f0, pt, start = build_domain(spec, D.rank)
+    nhru, nseg = pt["hru_area"].shape[0], pt["tosegment"].shape[0]
+    if scaling == "weak" or D.world == 1:
+        return dict(p0=p0, f0=f0, start=start, params=pt, hru_idx=None, seg_idx=None,
+                    forcing_rank=D.rank if scaling == "weak" else 0,
+                    job_hrus=nhru * (D.world if scaling == "weak" else 1),
+                    job_segs=nseg * (D.world if scaling == "weak" else 1),
+                    parallelism=(f"replicas x{D.world}: one whole domain per GPU (weak scaling)"
+                                 if D.world > 1 else "one GPU"))
+    seg_rank, hru_rank = sharding.partition_basins(pt["tosegment"], pt["hru_segment"], D.world)
+    q, hru_idx, seg_idx = sharding.shard_parameters(pt, seg_rank, hru_rank, D.rank)
+    return dict(p0=p0, f0=f0, start=start, params=q, hru_idx=hru_idx, seg_idx=seg_idx, forcing_rank=0,
+                job_hrus=nhru, job_segs=nseg,
+                parallelism=f"basin-sharded x{D.world}: outlet trees of ONE domain dealt to the GPUs "
+                            f"(this rank: {hru_idx.size:,} HRUs, {seg_idx.size:,} segments), "
+                            "no data-path collective")
+
+
+def shard_forcings(spec, shard, dev):
+    import torch
+
+    if spec.get("ensemble"):
+        nd = spec["ndays"]
+        f0 = shard["f0"]
+        idx = np.arange(nd) % f0["prcp"].shape[0]
+        return {k: torch.from_numpy(np.ascontiguousarray(f0[k][idx])).to(dev).float().double().contiguous()
+                for k in ("prcp", "tmax", "tmin")}
+    return device_forcings(shard["f0"], spec, shard["forcing_rank"], dev, hru_idx=shard["hru_idx"])
+
+
+def time_device_passes(eng, forc, nd, T, bufs, viol, D, warmup, steps):
+    """W + K passes with the forcings resident in HBM; returns per-step device
+    ms (this rank) and the accumulated kernel timing."""
+    ncol = eng.ncol
+
+    def one_pass():
+        eng.reset()
+        D.barrier()
+        eng.timer_mark(0)
+        d = 0
+        while d < nd:
+            n = min(T, nd - d)
+            o = d * ncol * 8
+            eng.run_device(n, forc["prcp"].data_ptr() + o, forc["tmax"].data_ptr() + o,
+                           forc["tmin"].data_ptr() + o, bufs[0].data_ptr(), bufs[1].data_ptr(),
+                           bufs[2].data_ptr(), viol=viol[d:d + n], sync=False)
+            d += n
+        eng.timer_mark(1)
+        eng.sync()
+        D.barrier()
+        return eng.timer_elapsed_ms()
+
+    for _ in range(warmup):
+        one_pass()
+    acc = dict(step_ms=[], col_ms=0.0, ch_ms=0.0, ncol=0, nblk=0, lanes=0)
+    for _ in range(steps):
+        acc["step_ms"].append(one_pass())
+        c, h = eng.timing()
+        acc["col_ms"] += c
+        acc["ch_ms"] += h
+        acc["ncol"] += eng.last_launches()[0]
+        nb, ln = eng.last_blocks()
+        acc["nblk"] += nb
+        acc["lanes"] = ln
+    return acc
+
+
+def alloc_outputs(eng, T, hru_vars, seg_vars, tiled, dev):
+    import torch
+
+    nf, ni = len(eng.sel_f64), len(eng.sel_i32)
+    onhru = eng.output_tile()[1] if tiled else eng.nhru
+    of = torch.empty((T, max(nf, 1), onhru), dtype=torch.float64, device=dev)
+    oi = torch.empty((T, max(ni, 1), onhru), dtype=torch.int32, device=dev)
+    osg = torch.empty((T, max(len(seg_vars), 1), max(eng.nseg, 1)), dtype=torch.float64, device=dev)
+    return of, oi, osg
+
+
+def pcie_ceiling(D: Dist, nbytes=1 << 30, reps=3):
+    """Plain cudaMemcpyAsync between pinned host memory and the GPU, all ranks
+    at the same time: what the box gives, aggregate GB/s over the ranks."""
+    import torch
+
+    h_up = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    h_dn = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d_up = torch.empty(nbytes, dtype=torch.uint8, device=D.dev)
+    d_dn = torch.empty(nbytes, dtype=torch.uint8, device=D.dev)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def run(up, dn):
+        D.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if up:
+                with torch.cuda.stream(s1):
+                    d_up.copy_(h_up, non_blocking=True)
+            if dn:
+                with torch.cuda.stream(s2):
+                    h_dn.copy_(d_dn, non_blocking=True)
+        D.barrier()
+        return D.max(time.perf_counter() - t0)
+
+    run(True, True)
+    res = {}
+    for name, up, dn in (("h2d", True, False), ("d2h", False, True), ("both", True, True)):
+        dt = run(up, dn)
+        res[name + "_gbs"] = (reps * nbytes * D.world * (2 if up and dn else 1)) / dt / 1e9
+    res["note"] = (f"{D.world} rank(s) x {reps} x {nbytes >> 20} MiB per direction, pinned host memory, "
+                   "cudaMemcpyAsync, all ranks at once; 'both' = up and down at the same time (sum)")
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="conus")
+    ap.add_argument("--scaling", choices=("strong", "weak"), default="strong",
+                    help="N > 1: strong = ONE domain / ensemble split over the GPUs (BASELINE.json "
+                         "configs[2], configs[3]); weak = every GPU its own copy of the workload")
     ap.add_argument("--outputs", default="full")
     ap.add_argument("--block-days", type=int, default=256)
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--ref", choices=("port", "numpy", "numba"), default="port")
     ap.add_argument("--no-e2e", action="store_true")
     # measured on the CONUS workload (float32 forcings, HRU-days/s): 64 -> 3.50e9, 128 -> 3.53e9,
     # 256 -> 3.88e9, 384 -> 3.76e9, 512 -> 3.57e9 (profiles/r01_e2e_block_days.jsonl)
@@ -363,6 +670,10 @@ def main():
                     help="type of the host forcing arrays of the e2e leg: float32 as in the reference's "
                          "forcing files (widened on the device, exact) or float64")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the ensemble / e2e_nhm_default / pcie / e2e_model objects")
+    ap.add_argument("--lanes", type=int, default=None, help="column launches per block (library option)")
+    ap.add_argument("--no-overlap", action="store_true", help="serialise the blocks (library option)")
     ap.add_argument("--layout", choices=("tiled", "rows"), default="tiled",
                     help="device-resident results as [day][tile][variable][H] (pws_output_tile; needs "
                          "--outputs full) or as [day][variable][nhru] rows")
@@ -374,166 +685,195 @@ def main():
         return run_reference(args, spec)
 
     import torch
-    import torch.distributed as dist
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: pywatershed_b200 has no CPU path")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # keep stdout to the one JSON line: NCCL prints its version banner to stdout at the
-        # VERSION and WARN levels; anything more verbose the user asked for goes to stderr
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
-            del os.environ["NCCL_DEBUG"]
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
-
+    D = Dist()
     import __graft_entry__ as g
 
-    if rank == 0:
+    if D.rank == 0:
         g.build()
-    if world > 1:
-        dist.barrier()
+    D.barrier()
     from pywatershed_b200 import Engine
 
-    p0, f0, pt, start = build_domain(spec, rank)
-    eng = Engine(pt, start, device=local_rank)
-    hru_vars, seg_vars = output_sets(eng.reg, args.outputs)
-    eng.select_outputs(hru_vars, seg_vars)
-    nhru, nseg, nd = eng.nhru, eng.nseg, spec["ndays"]
-    forc = device_forcings(f0, spec, rank, dev)
-    T = max(1, min(args.block_days, nd))
-    nf = len(eng.sel_f64)
-    ni = len(eng.sel_i32)
-    tiled = args.layout == "tiled" and args.outputs == "full"
-    if tiled:
-        eng.set_tiled_outputs(True)
-    # (the tiled layout pads the last tile: [T, tiles, n, H] has the same size as [T, n, padded])
-    onhru = eng.output_tile()[1] if tiled else nhru
-    of = torch.empty((T, max(nf, 1), onhru), dtype=torch.float64, device=dev)
-    oi = torch.empty((T, max(ni, 1), onhru), dtype=torch.int32, device=dev)
-    osg = torch.empty((T, max(len(seg_vars), 1), max(nseg, 1)), dtype=torch.float64, device=dev)
-    viol_t = torch.zeros((nd, 6), dtype=torch.int32).pin_memory()
-    viol = viol_t.numpy()
-    torch.cuda.synchronize()
+    def engine_for(spec, shard):
+        eng = Engine(shard["params"], shard["start"], device=D.local_rank,
+                     forcing_period=shard.get("forcing_period"), lanes=args.lanes)
+        if args.no_overlap:
+            eng._opt("overlap_routing", 0)
+        return eng
 
-    def barrier():
+    def device_leg(spec, outputs, layout, block_days, warmup, steps, clocks=False):
+        """value-style measurement of one workload; returns a dict of results."""
+        shard = make_shard(spec, D, args.scaling)
+        eng = engine_for(spec, shard)
+        hru_vars, seg_vars = output_sets(eng.reg, outputs)
+        eng.select_outputs(hru_vars, seg_vars)
+        nd = spec["ndays"]
+        forc = shard_forcings(spec, shard, D.dev)
+        tiled = layout == "tiled" and outputs == "full"
+        if tiled:
+            eng.set_tiled_outputs(True)
+        # bound the result buffer of one block to ~35 GB
+        per_day = (8 * len(eng.sel_f64) + 4 * len(eng.sel_i32)) * max(eng.nhru, 1) + 1
+        T = int(max(1, min(block_days, nd, 35e9 // per_day)))
+        bufs = alloc_outputs(eng, T, hru_vars, seg_vars, tiled, D.dev)
+        viol_t = torch.zeros((nd, 6), dtype=torch.int32, pin_memory=True)
+        viol = viol_t.numpy()
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        sampler = ClockSampler(D.local_rank)
+        l0 = eng.launch_count()
+        if clocks and D.rank == 0:
+            sampler.start()
+        acc = time_device_passes(eng, forc, nd, T, bufs, viol, D, warmup, steps)
+        clk = sampler.stop() if clocks and D.rank == 0 else None
+        launches = eng.launch_count() - l0
+        total_ms = D.max(sum(acc["step_ms"]))
+        # the only communication of a sharded run: budget verdicts and a checksum of
+        # the last day's streamflow, summed over the ranks (NCCL all-reduce)
+        viol_total = int(D.sum(viol.sum(axis=0)).sum())
+        seg_last = float(D.sum([float(bufs[2][(nd - 1) % T, eng.sel_seg.index("seg_outflow")].sum())
+                                if "seg_outflow" in eng.sel_seg and eng.nseg else 0.0])[0])
+        units_per_step = shard["job_hrus"] * nd
+        res = dict(shard=shard, eng=eng, forc=forc, hru_vars=hru_vars, seg_vars=seg_vars, T=T, nd=nd,
+                   tiled=tiled, acc=acc, total_ms=total_ms, launches=launches, clocks=clk,
+                   viol_total=viol_total, seg_last=seg_last, units_per_step=units_per_step,
+                   value=units_per_step * steps / (total_ms * 1e-3), bufs=bufs)
+        return res
 
-    def one_pass(timed):
-        """reset (untimed) + every block of days; returns device ms."""
-        eng.reset()
-        barrier()
-        eng.timer_mark(0)
-        d = 0
-        while d < nd:
-            n = min(T, nd - d)
-            o = d * nhru * 8
-            eng.run_device(n, forc["prcp"].data_ptr() + o, forc["tmax"].data_ptr() + o,
-                           forc["tmin"].data_ptr() + o, of.data_ptr(), oi.data_ptr(),
-                           osg.data_ptr(), viol=viol[d:d + n], sync=False)
-            d += n
-        eng.timer_mark(1)
-        eng.sync()
-        barrier()
-        return eng.timer_elapsed_ms()
-
-    for _ in range(args.warmup):
-        one_pass(False)
-    sampler = ClockSampler(local_rank)
-    l0 = eng.launch_count()
-    if rank == 0:
-        sampler.start()
-    step_ms, col_ms, ch_ms, ncol = [], 0.0, 0.0, 0
-    for _ in range(args.steps):
-        ms = one_pass(True)
-        step_ms.append(ms)
-        c, h = eng.timing()
-        col_ms += c
-        ch_ms += h
-        ncol += eng.last_launches()[0]
-    clocks = sampler.stop() if rank == 0 else None
-    launches = eng.launch_count() - l0
-    viol_total = int(viol.sum())
-    t_dev = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    total_ms = float(t_dev.item())
-    units_per_step = nhru * nd * world
-    value = units_per_step * args.steps / (total_ms * 1e-3)
+    main_leg = device_leg(spec, args.outputs, args.layout, args.block_days, args.warmup, args.steps, clocks=True)
+    eng, shard, forc = main_leg["eng"], main_leg["shard"], main_leg["forc"]
+    hru_vars, seg_vars, nd, T = main_leg["hru_vars"], main_leg["seg_vars"], main_leg["nd"], main_leg["T"]
+    nhru, nseg = eng.nhru, eng.nseg
+    units_per_step = main_leg["units_per_step"]
+    del main_leg["bufs"]
+    torch.cuda.empty_cache()
 
     # ---- e2e: host-facing call, pinned host buffers, H2D + D2H inside the region
-    e2e = None
-    if not args.no_e2e:
-        e2e_seg = ["seg_outflow"]  # streamflow at every segment: the product of an NHM run
-        if tiled:
-            eng.set_tiled_outputs(False)  # a pws_run_device layout
-        eng.select_outputs([], e2e_seg)
-        f32 = args.e2e_forcing == "f32"
-        hf = {k: (v.float() if f32 else v).cpu().pin_memory() for k, v in forc.items()}
+    from pywatershed_b200.engine import calendar
+
+    def host_leg(hsel, ssel, ndays, block_days, passes, f32=True):
+        """pws_run_host[_f32] over the first `ndays` days with this output selection."""
+        eng.set_tiled_outputs(False)
+        eng.select_outputs(hsel, ssel)
+        hf = {k: (v[:ndays].float() if f32 else v[:ndays]).cpu().pin_memory() for k, v in forc.items()}
         run_host = eng.L.pws_run_host_f32 if f32 else eng.L.pws_run_host
-        e2e_T = args.e2e_block_days
-        eng.set_block_days(e2e_T)
-        # pin the result buffers too (the library drains with cudaMemcpyAsync)
-        cal_nd = nd
-        res_seg = torch.empty((cal_nd, len(e2e_seg), nseg), dtype=torch.float64).pin_memory()
-        res_viol = np.zeros((cal_nd, 6), dtype=np.int32)
-        from pywatershed_b200.engine import calendar
+        eng.set_block_days(block_days)
+        nf, ni = len(eng.sel_f64), len(eng.sel_i32)
+        res_f = torch.empty((ndays, max(nf, 1), nhru if nf else 1), dtype=torch.float64, pin_memory=True)
+        res_i = torch.empty((ndays, max(ni, 1), nhru if ni else 1), dtype=torch.int32, pin_memory=True)
+        res_seg = torch.empty((ndays, max(len(ssel), 1), max(nseg, 1)), dtype=torch.float64, pin_memory=True)
+        res_viol = np.zeros((ndays, 6), dtype=np.int32)
+        cal = calendar(shard["start"], ndays)
 
-        cal = calendar(start, nd)
-        dummy_f = np.empty(1)
-        dummy_i = np.empty(1, dtype=np.int32)
-
-        def e2e_pass():
+        def one():
             eng.reset()
-            barrier()
+            D.barrier()
             t0 = time.perf_counter()
             eng._check(run_host(
-                eng.h, nd, cal.ctypes.data, hf["prcp"].data_ptr(), hf["tmax"].data_ptr(),
-                hf["tmin"].data_ptr(), dummy_f.ctypes.data, dummy_i.ctypes.data,
+                eng.h, ndays, cal.ctypes.data, hf["prcp"].data_ptr(), hf["tmax"].data_ptr(),
+                hf["tmin"].data_ptr(), res_f.data_ptr(), res_i.data_ptr(),
                 res_seg.data_ptr(), res_viol.ctypes.data))
-            barrier()
+            D.barrier()
             return time.perf_counter() - t0
 
-        e2e_pass()
-        e2e_pass()
-        ts = [e2e_pass() for _ in range(max(1, min(args.steps, 3)))]
-        te = torch.tensor([sum(ts)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": units_per_step * len(ts) / float(te.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(3 * nd * nhru * (4 if f32 else 8)) * world,
+        one()
+        one()
+        ts = [one() for _ in range(passes)]
+        tot = D.max(sum(ts))
+        h2d = int(D.sum([3 * ndays * eng.ncol * (4 if f32 else 8)])[0])
+        d2h = int(D.sum([ndays * (nf * nhru * 8 + ni * nhru * 4 + len(ssel) * nseg * 8 + 24)])[0])
+        chk = float(D.sum([float(res_seg[-1, ssel.index("seg_outflow")].sum()) if "seg_outflow" in ssel else 0.0])[0])
+        return dict(value=shard["job_hrus"] * ndays * len(ts) / tot, seconds_per_pass=tot / len(ts),
+                    h2d=h2d, d2h=d2h, checksum=chk, viol=int(D.sum([int(res_viol.sum())])[0]))
+
+    e2e = None
+    pcie = None
+    if not args.no_e2e:
+        if not args.no_extras:
+            pcie = pcie_ceiling(D)
+        f32 = args.e2e_forcing == "f32"
+        r = host_leg([], ["seg_outflow"], nd, args.e2e_block_days, max(1, min(args.steps, 3)), f32)
+        e2e = {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": r["h2d"],
+               "d2h_bytes_per_step": r["d2h"],
                "forcing_dtype": "float32 (as stored in the reference's forcing files; widened on the "
                                 "device)" if f32 else "float64",
-               "d2h_bytes_per_step": int(nd * (len(e2e_seg) * nseg * 8 + 24)) * world,
-               "outputs": "seg_outflow [ndays, nsegment] + 6 budget verdicts per day",
-               "block_days": e2e_T, "checksum_seg_outflow_last_day": float(res_seg[-1, 0].sum())}
-        eng.select_outputs(hru_vars, seg_vars)
+               "outputs": "seg_outflow [ndays, nsegment] (streamflow at every segment, the product of an "
+                          "NHM run) + 6 budget verdicts per day; the `value` leg writes all 148 variables "
+                          "to HBM but drains none -- see e2e_nhm_default for HRU variables on the host",
+               "block_days": args.e2e_block_days, "checksum_seg_outflow_last_day": r["checksum"],
+               "budget_violations": r["viol"]}
+        if pcie:
+            e2e["pcie_gbs"] = (r["h2d"] + r["d2h"]) / r["seconds_per_pass"] / 1e9
+            e2e["pcie_frac_of_ceiling"] = e2e["pcie_gbs"] / pcie["both_gbs"]
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+    # ---- extras: the same JSON line carries the other measurements north_star names
+    extras = {}
+    if not args.no_extras and args.workload == "conus" and not args.no_e2e:
+        # the reference control file's output selection (74 HRU variables + the segment
+        # variables) drained to pinned host memory: a bounded sample of 366 days
+        names = json.loads((ROOT / "tests" / "golden" / "nhm_default_vars.json").read_text())
+        hsel = [v for v in eng.reg.hru_vars if v in names]
+        nd_s = 366
+        r = host_leg(hsel, list(eng.reg.seg_vars), nd_s, 64, 2, True)
+        x = {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": r["h2d"],
+             "d2h_bytes_per_step": r["d2h"], "sample": f"first {nd_s} days of the workload, 64-day blocks",
+             "outputs": f"{len(hsel)} HRU variables of pywatershed/data/drb_2yr/nhm.control + 5 segment "
+                        "variables, every day, to pinned host memory",
+             "bound": "PCIe (device-to-host drain)"}
+        if pcie:
+            x["pcie_gbs"] = (r["h2d"] + r["d2h"]) / r["seconds_per_pass"] / 1e9
+            x["pcie_frac_of_d2h_ceiling"] = (r["d2h"] / r["seconds_per_pass"] / 1e9) / pcie["d2h_gbs"]
+        extras["e2e_nhm_default"] = x
+    eng.close()
+    del forc, eng
+    main_leg["eng"] = main_leg["forc"] = None
+    torch.cuda.empty_cache()
+
+    if not args.no_extras and args.workload == "conus":
+        # BASELINE.json configs[3]: the 1024-member DRB parameter ensemble, by member
+        espec = workload_spec("ensemble")
+        el = device_leg(espec, "full", args.layout, 64, 2, max(1, min(args.steps, 3)))
+        ea = el["acc"]
+        ebpu = algorithmic_bytes_per_hru_day(el["eng"].reg, el["hru_vars"])
+        e_units_rank = el["eng"].nhru * el["nd"] * len(ea["step_ms"])
+        extras["ensemble"] = {
+            "metric": METRIC, "value": el["value"], "unit": UNIT, "scaling": args.scaling,
+            "ms_per_step": el["total_ms"] / len(ea["step_ms"]),
+            "config": {"workload": espec["label"], "parallelism": el["shard"]["parallelism"],
+                       "outputs": "full", "block_days": el["T"], "lanes": ea["lanes"],
+                       "forcings": "[ndays, 765] shared by the members (option forcing_period): "
+                                   "resident once, read through L2",
+                       "budget_violations": el["viol_total"]},
+            "column_hbm_frac": (e_units_rank * ebpu / max(ea["col_ms"] * 1e-3, 1e-12) / 1e9) /
+                               float(_peak()[0]),
+            "checksum_seg_outflow_last_day": el["seg_last"], "gpu_launches": int(el["launches"])}
+        el["eng"].close()
+        del el
+        torch.cuda.empty_cache()
+
+    if not args.no_extras and args.workload == "conus" and D.world == 1:
+        try:
+            extras["e2e_model"] = model_leg(spec)
+        except Exception as exc:  # the Model leg must not take the bench line down
+            extras["e2e_model"] = {"error": f"{type(exc).__name__}: {exc}"}
+
+    if D.rank != 0:
+        D.close()
         return
 
-    # ---- roofline of the dominant kernel (k_hru_column), measured live
-    peaks_path = ROOT / "MEASURED_PEAKS.json"
-    if peaks_path.exists():
-        peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    bpu = algorithmic_bytes_per_hru_day(eng.reg, hru_vars)
-    avg_launch_s = (col_ms / max(ncol, 1)) * 1e-3
-    units_per_launch = nhru * nd * args.steps / max(ncol, 1)
-    achieved = units_per_launch * bpu / avg_launch_s / 1e9
-    # DRAM bytes per launch from the committed ncu capture (profiles/), scaled to
-    # this run's launch size; only meaningful for the output mode it was taken in
+    # ---- roofline of the dominant kernel (k_hru_column), measured live.  The
+    # lanes of a block run concurrently (and beside the previous block's routing),
+    # so the kernel's time is the UNION of the launches' CUDA-event intervals on
+    # their streams (pws_last_timing), and `achieved` = the bytes of all launches of
+    # the timed region over that time.
+    acc = main_leg["acc"]
+    peak, peak_src = _peak()
+    reg = __import__("pywatershed_b200").Registry.get()
+    bpu = algorithmic_bytes_per_hru_day(reg, hru_vars)
+    step_ms = acc["step_ms"]
+    col_s = acc["col_ms"] * 1e-3
+    units_rank = nhru * nd * args.steps  # HRU-days this rank's kernels processed
+    achieved = units_rank * bpu / max(col_s, 1e-12) / 1e9
+    units_per_launch = units_rank / max(acc["ncol"], 1)
     traffic, fp64 = None, None
     prof = ROOT / "profiles" / "r01_column_traffic.json"
     if prof.exists():
@@ -541,49 +881,142 @@ def main():
             pj = json.loads(prof.read_text())
             if args.outputs == "full":
                 traffic = pj["dram_bytes_per_launch"] * units_per_launch / pj["hru_days_per_launch"]
-            # the other roofline of the kernel: FP64 work per HRU-day counted by ncu
-            # (DADD + DMUL + 2 DFMA thread instructions) against the FP64 pipe's peak
-            tf = pj["fp64_flops_per_hru_day"] * units_per_launch / avg_launch_s / 1e12
+            tf = pj["fp64_flops_per_hru_day"] * units_rank / max(col_s, 1e-12) / 1e12
             fp64 = {"achieved": tf, "peak": pj["fp64_peak_tflops"], "unit": "TFLOP/s",
                     "frac": tf / pj["fp64_peak_tflops"],
                     "flops_per_hru_day": pj["fp64_flops_per_hru_day"]}
         except Exception:
             traffic, fp64 = None, None
+    whole = units_rank * bpu / (sum(step_ms) * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "kernel": "k_hru_column",
                 "peak_source": peak_src, "bytes_per_hru_day": bpu,
                 "hru_days_per_launch": units_per_launch,
-                "avg_launch_ms": avg_launch_s * 1e3,
-                "share_of_step": col_ms / max(sum(step_ms), 1e-9),
-                "channel_share_of_step": ch_ms / max(sum(step_ms), 1e-9),
+                "avg_launch_ms": acc["col_ms"] / max(acc["ncol"], 1),
+                "launches_per_block": acc["lanes"],
+                "how": "algorithmic bytes of every k_hru_column launch of the timed region / union of "
+                       "the launches' CUDA-event intervals (lanes run concurrently); rank 0's kernels",
+                "share_of_step": acc["col_ms"] / max(sum(step_ms), 1e-9),
+                "channel_share_of_step": acc["ch_ms"] / max(sum(step_ms), 1e-9),
+                "whole_step_hbm_frac": whole / peak,
                 "fp64": fp64}
 
     cpu = None
-    if not args.no_cpu and world == 1:
+    if not args.no_cpu and D.world == 1:
         ncores = os.cpu_count() or 1
         nthreads = max(1, min(ncores, 64))
-        r, units, dt = cpu_oracle_rate(p0, f0, start, 1, min(nd, 3653), nthreads)
+        r, units, dt = cpu_oracle_rate(shard["p0"], shard["f0"], shard["start"], 1, min(nd, 3653), nthreads)
         cpu = {"value": r, "unit": UNIT, "cores": nthreads, "kind": "port",
                "sample": f"{nthreads} threads x 1 DRB tile x {min(nd, 3653)} days "
                          f"({units:.3g} HRU-days, {dt:.1f} s), C oracle, full chain + routing + budgets"}
 
+    kinfo = None
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": spec["label"] + (f" per GPU x {world} GPUs" if world > 1 else ""),
-                   "outputs": args.outputs, "layout": "tiled" if tiled else "rows", "n_output_vars": len(hru_vars) + len(seg_vars),
-                   "block_days": T, "nhru_per_gpu": nhru, "nsegment_per_gpu": nseg, "ndays": nd,
-                   "l2": "inputs larger than L2 (forcings 3 x %.1f GB per GPU, streamed once per step)"
+        "metric": METRIC, "value": main_leg["value"], "unit": UNIT, "n_gpus": D.world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": main_leg["total_ms"] / args.steps, "higher_is_better": True,
+        "scaling": args.scaling if D.world > 1 else "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": spec["label"], "outputs": args.outputs,
+                   "layout": "tiled" if main_leg["tiled"] else "rows",
+                   "n_output_vars": len(hru_vars) + len(seg_vars),
+                   "block_days": T, "nhru_rank0": nhru, "nsegment_rank0": nseg, "ndays": nd,
+                   "job_hrus": shard["job_hrus"], "job_segments": shard["job_segs"],
+                   "l2": "inputs larger than L2 (forcings 3 x %.1f GB on rank 0, streamed once per step)"
                          % (nd * nhru * 8 / 1e9),
-                   "parallelism": f"basin-sharded x{world}, no data-path collective",
-                   "kernel": eng.kernel_info(), "budget_violations": viol_total},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-        "clocks": clocks,
+                   "parallelism": shard["parallelism"],
+                   "budget_violations": main_leg["viol_total"],
+                   "checksum_seg_outflow_last_day": main_leg["seg_last"]},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(main_leg["launches"]),
+        "clocks": main_leg["clocks"],
     }
+    if pcie:
+        line["pcie"] = pcie
+    line.update(extras)
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    D.close()
+
+
+def _peak():
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        return float(json.loads(peaks_path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def model_leg(spec, ndays=731):
+    """e2e through the API a pywatershed user calls: pywatershed_b200.Model over
+    the whole CONUS-scale domain for `ndays` days, forcings as float32 numpy
+    arrays in host memory (what the reference's forcing files hold), (i) no
+    output files, (ii) the reference control file's output selection written to
+    netCDF.  Timed: Model.run() (engine creation, parameter upload and init
+    included in the first figure, excluded in the second)."""
+    import tempfile
+
+    import torch
+
+    import pywatershed_b200 as pwsb
+
+    p0, f0, pt, start = build_domain(spec)
+    nhru = pt["hru_area"].shape[0]
+    nseg = pt["tosegment"].shape[0]
+    dev = torch.device("cuda", 0)
+    sub = dict(spec)
+    sub["ndays"] = ndays
+    forc = {k: v.float().cpu().numpy() for k, v in device_forcings(f0, sub, 0, dev).items()}
+    torch.cuda.empty_cache()
+    procs = ["PRMSSolarGeometry", "PRMSAtmosphere", "PRMSCanopy", "PRMSSnow", "PRMSRunoff",
+             "PRMSSoilzone", "PRMSGroundwater", "PRMSChannel"]
+
+    def make(**opts):
+        t0 = np.datetime64(start, "s")
+        o = {"budget_type": "error", "calc_method": "cuda"}
+        o.update(opts)
+        control = pwsb.Control(t0, t0 + np.timedelta64(ndays - 1, "D"), np.timedelta64(24, "h"), options=o)
+        coords = {"nhm_id": pt["nhm_id"], "nhm_seg": pt["nhm_seg"]}
+        data = {k: v for k, v in pt.items() if k not in coords}
+        params = pwsb.Parameters(dims={"nhru": nhru, "nsegment": nseg, "nmonth": 12, "ndoy": 366},
+                                 coords=coords, data_vars=data)
+        m = pwsb.Model([getattr(pwsb, n) for n in procs], control=control, parameters=params,
+                       find_input_files=False)
+        atm = m.processes["PRMSAtmosphere"]
+        for k in ("prcp", "tmax", "tmin"):
+            atm.set_input_to_adapter(k, forc[k])
+        return m
+
+    out = {"unit": UNIT, "ndays": ndays, "nhru": nhru,
+           "api": "pywatershed_b200.Model([...8 processes...]).run(), forcings float32 numpy [ndays, nhru]"}
+    units = nhru * ndays
+    # (i) no output: first run (includes engine creation + init), then warm runs
+    m = make()
+    t0 = time.perf_counter()
+    m.run(finalize=True)
+    out["first_run_s"] = time.perf_counter() - t0
+    chk = float(m.processes["PRMSChannel"]["seg_outflow"].sum())
+    ts = []
+    for _ in range(2):
+        m = make()
+        m._ensure_engine()  # construction cost reported separately
+        t0 = time.perf_counter()
+        m.run(finalize=True)
+        ts.append(time.perf_counter() - t0)
+    out["value"] = units / min(ts)
+    out["run_s"] = min(ts)
+    out["checksum_seg_outflow_last_day"] = chk
+    out["h2d_bytes_per_step"] = int(3 * ndays * nhru * 4)
+    # (ii) the reference control file's variables to netCDF
+    names = json.loads((ROOT / "tests" / "golden" / "nhm_default_vars.json").read_text())
+    with tempfile.TemporaryDirectory(dir=os.environ.get("PWS_BENCH_TMP", None)) as td:
+        m = make(netcdf_output_var_names=list(names), netcdf_output_dir=td)
+        m._ensure_engine()
+        m.initialize_netcdf(td)
+        t0 = time.perf_counter()
+        m.run(finalize=True)
+        dt = time.perf_counter() - t0
+        nbytes = sum(f.stat().st_size for f in pl.Path(td).glob("*.nc"))
+    out["netcdf"] = {"value": units / dt, "unit": UNIT, "run_s": dt, "bytes_written": int(nbytes),
+                     "writer_gbs": nbytes / dt / 1e9, "n_vars": len(names),
+                     "bound": "host: device-to-host drain + file writes"}
+    return out
 
 
 if __name__ == "__main__":

@@ -60,8 +60,18 @@ int pws_set_param_i32(pws_handle *h, const char *name, const int32_t *h_v, int64
  * memory with TMA bulk copies when they are 16-byte aligned; 0: per-thread loads),
  * "column_hrus" (HRUs per CTA of the column kernel: 0, default = by domain size,
  * 128 or 256),
- * "soltab_device" (1: build the PRMSSolarGeometry tables with the CUDA kernel
- * k_soltab; 0, default: with the host libm the reference's tables come from),
+ * "soltab_device" (1, default: build the PRMSSolarGeometry tables with the CUDA
+ * kernel k_soltab; 0: on host threads with the host libm the reference's tables
+ * come from -- a debugging aid for last-bit comparisons, not a product path),
+ * "forcing_period" (P > 0: a parameter ensemble over one base domain, member-
+ * major -- nhru = nmember * P and the forcing arrays of every pws_run_* call are
+ * [ndays][P], HRU i reading column i mod P, so the members' common weather is
+ * uploaded and read once (examples/05_parameter_ensemble.ipynb cells 20-26
+ * re-read it per member); 0, default: forcings are [ndays][nhru]),
+ * "lanes" (column-kernel launches per block of days, each over a contiguous
+ * range of CTA tiles on its own stream: 0, default = by domain size, 1..8),
+ * "overlap_routing" (1, default: the routing of block b runs beside the column
+ * kernels of block b+1; 0: blocks are serialised),
  * "channel_chunk" (segments per routing chunk = per CTA of k_route_chunks,
  * default and maximum 512; outlet trees larger than a chunk are cut and linked
  * through HBM),
@@ -89,6 +99,20 @@ int pws_select_outputs(pws_handle *h, int n_hru_vars, const int32_t *hru_var_idx
                        int n_seg_vars, const int32_t *seg_var_idx);
 int pws_n_selected(pws_handle *h, int *n_f64, int *n_i32, int *n_seg);
 
+/* ---- budget accumulations: Budget.calculate, base/budget.py:262-269
+ * (`self._accumulations[component][var] += value * dt` every step).  The
+ * chosen float64 variables (indices into the registries) are summed per unit
+ * on the device over every day the handle computes, in day order; they need
+ * not be part of the drained selection (the kernels write them behind it: the
+ * device-side rows per day are what pws_n_selected reports, pws_run_host only
+ * drains the selected ones).  pws_get_accumulations: h_hru [n_hru_vars][nhru],
+ * h_seg [n_seg_vars][nsegment] (either may be NULL).  pws_reset_state and
+ * pws_clear_accumulations zero the sums; option "accumulate" 0 pauses them. */
+int pws_select_accumulations(pws_handle *h, int n_hru_vars, const int32_t *hru_var_idx,
+                             int n_seg_vars, const int32_t *seg_var_idx);
+int pws_get_accumulations(pws_handle *h, double *h_hru, double *h_seg);
+int pws_clear_accumulations(pws_handle *h);
+
 /* ---- the time loop: Model.run / advance / calculate,
  * base/model.py:678-743.  cal = [ndays][4] int32 (doy, dowy, month,
  * day-of-month) = control.current_doy/current_dowy/current_month
@@ -97,7 +121,8 @@ int pws_n_selected(pws_handle *h, int *n_f64, int *n_i32, int *n_seg);
  * Budget.calculate closure fails (base/budget.py:336-416) for canopy, snow,
  * runoff, soilzone, groundwater (unit basis) and channel (global basis). */
 
-/* forcings and outputs already resident in HBM; asynchronous (pws_sync) */
+/* forcings and outputs already resident in HBM; asynchronous (pws_sync).
+ * h_budget_viol must stay valid (and should be page-locked) until pws_sync. */
 int pws_run_device(pws_handle *h, int ndays, const int32_t *h_cal,
                    const double *d_prcp, const double *d_tmax, const double *d_tmin,
                    double *d_out_f64, int32_t *d_out_i32, double *d_seg_out,
@@ -147,7 +172,7 @@ int pws_run_channel_device(pws_handle *h, int ndays, const double *d_seg_lateral
 
 int pws_sync(pws_handle *h);
 
-/* Tiled result layout of pws_run_device, chosen with
+/* Tiled result layout of pws_run_device / pws_run_host[_f32], chosen with
  * pws_set_option(h, "tiled_outputs", 1) when every HRU variable is selected in
  * registry order: out_f64 is [day][tile][n_f64][tile_units], out_i32
  * [day][tile][n_i32][tile_units], tile = unit / tile_units, the last tile
@@ -159,14 +184,22 @@ int pws_sync(pws_handle *h);
  * hands out per-variable strided views of this buffer. */
 int pws_output_tile(pws_handle *h, int *tile_units, int64_t *padded_units);
 
-/* ---- state: get_restart_variables (prms_snow.py:269-293 etc.) ---------- */
-int pws_get_state(pws_handle *h, const char *name, double *h_out); /* [nhru] */
+/* ---- state: get_restart_variables (prms_snow.py:269-293 etc.) ----------
+ * name = a per-HRU state of the registry above ([nhru]) or one of PRMSChannel's
+ * two per-segment states ([nsegment], the caller's segment order): "outflow_ts"
+ * and "seg_inflow", what _advance_variables carries from day to day
+ * (prms_channel.py:384-386, 456-585).  Saving every state after a pws_run_* call
+ * and restoring it into a fresh handle continues the run bit for bit. */
+int pws_n_seg_state(void);
+const char *pws_seg_state_name(int idx);
+int pws_get_state(pws_handle *h, const char *name, double *h_out);
 int pws_set_state(pws_handle *h, const char *name, const double *h_in);
 
 /* ---- instrumentation ---------------------------------------------------- */
-/* kernels launched since create, and device milliseconds (CUDA events on the
- * compute stream) spent in the hru column kernel / channel kernels during
- * the last pws_run_* call (valid after pws_sync) */
+/* kernels launched since create, and device milliseconds spent in the hru
+ * column kernels / channel kernels since the last pws_sync: the length of the
+ * UNION of the kernels' (start, stop) CUDA-event intervals on their streams
+ * (the lanes of a block, and routing beside the next block, run concurrently) */
 int64_t pws_launch_count(pws_handle *h);
 int pws_last_timing(pws_handle *h, double *ms_column, double *ms_channel);
 int pws_column_kernel_info(pws_handle *h, int *regs, int *local_bytes, int *max_blocks_per_sm);
@@ -174,8 +207,10 @@ int pws_column_kernel_info(pws_handle *h, int *regs, int *local_bytes, int *max_
  * torch's stream): mark which = 0 (start) / 1 (stop); elapsed after pws_sync */
 int pws_timer_mark(pws_handle *h, int which);
 int pws_timer_elapsed_ms(pws_handle *h, double *ms);
-/* number of hru-column launches and channel launches in the last run */
+/* number of hru-column kernel launches and channel kernel launches in the last
+ * run; blocks of days it was cut into and column launches (lanes) per block */
 int pws_last_launches(pws_handle *h, int *n_column, int *n_channel);
+int pws_last_blocks(pws_handle *h, int *n_blocks, int *lanes);
 /* reset prognostic state to the initial conditions without rebuilding the
  * static tables (what re-instantiating the reference's processes would do) */
 int pws_reset_state(pws_handle *h);

@@ -69,6 +69,12 @@ def lib():
         "pws_timer_mark": (i32, [vp, i32]),
         "pws_timer_elapsed_ms": (i32, [vp, C.POINTER(dbl)]),
         "pws_last_launches": (i32, [vp, C.POINTER(i32), C.POINTER(i32)]),
+        "pws_last_blocks": (i32, [vp, C.POINTER(i32), C.POINTER(i32)]),
+        "pws_select_accumulations": (i32, [vp, i32, vp, i32, vp]),
+        "pws_get_accumulations": (i32, [vp, vp, vp]),
+        "pws_clear_accumulations": (i32, [vp]),
+        "pws_n_seg_state": (i32, []),
+        "pws_seg_state_name": (cp, [i32]),
         "pws_reset_state": (i32, [vp]),
         "pws_output_tile": (i32, [vp, C.POINTER(i32), C.POINTER(i64)]),
     }
@@ -89,5 +95,7 @@ EXPORTED_SYMBOLS = (
     "pws_run_channel_device", "pws_n_inputs", "pws_input_name", "pws_run_host_inputs", "pws_sync", "pws_get_state", "pws_set_state",
     "pws_launch_count", "pws_last_timing", "pws_column_kernel_info",
     "pws_timer_mark", "pws_timer_elapsed_ms", "pws_last_launches", "pws_reset_state",
-    "pws_output_tile", "pws_run_host_f32",
+    "pws_output_tile", "pws_run_host_f32", "pws_last_blocks", "pws_n_seg_state",
+    "pws_seg_state_name", "pws_select_accumulations", "pws_get_accumulations",
+    "pws_clear_accumulations",
 )

@@ -69,7 +69,19 @@ class Budget:
 
     @property
     def accumulations(self):
-        return self._accumulations
+        """component -> term -> per-unit sum over the steps so far
+        (base/budget.py:262-269).  Blocks computed by Model.run() are summed on
+        the device (pws_select_accumulations) and fetched when somebody looks;
+        blocks served day by day are summed on the host."""
+        model = getattr(self._proc, "_model", None)
+        dev = model._device_accumulations() if model is not None else {}
+        out = {}
+        for c in self.components:
+            out[c] = {}
+            for v in self.terms[c]:
+                host, d = self._accumulations[c][v], dev.get(v)
+                out[c][v] = host if d is None else (d if host is None else host + d)
+        return out
 
     # ---- stepping
     def advance(self):

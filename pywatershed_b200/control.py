@@ -227,13 +227,14 @@ class Control:
     def start_month(self):
         return int(self._cal(self._start_time)[2])
 
-    def advance(self):
-        """base/control.py:439-453"""
-        if self._current_time == self._end_time:
-            raise ValueError("End of time reached")
-        self._itime_step += 1
-        self._previous_time = self._current_time
-        self._current_time = self._current_time + self._time_step
+    def advance(self, n: int = 1):
+        """base/control.py:439-453; `n` steps at once (a time-blocked Model.run)."""
+        for _ in range(int(n)):
+            if self._current_time == self._end_time:
+                raise ValueError("End of time reached")
+            self._itime_step += 1
+            self._previous_time = self._current_time
+            self._current_time = self._current_time + self._time_step
 
     def edit_end_time(self, new_end_time: np.datetime64):
         self._end_time = new_end_time

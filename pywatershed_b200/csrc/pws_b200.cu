@@ -96,8 +96,11 @@ struct pws_handle {
   // options
   int dprst_flag = 1, temp_units = 0, start_month = 1, start_doy = 1, adjust_parameters = 1;
   int block_days = 0;
-  int soltab_device = 0;
+  int soltab_device = 1;
   int tma = 1;  // option: stage forcings with TMA bulk copies when the rows are aligned
+  int lanes_opt = 0;        // option "lanes": 0 = by domain size, else column launches per block
+  int overlap_routing = 1;  // option "overlap_routing": routing of block b beside the column of b+1
+  int64_t forcing_period = 0;  // option "forcing_period": forcings are [ndays][period], HRU i reads i % period
   bool route_attr_set = false;
   bool smem_attr_set[8] = {false, false, false, false, false, false, false, false};
   bool tiled_outputs = false;  // option "tiled_outputs": [day][tile][variable][H] (SINK_TILED)
@@ -118,7 +121,15 @@ struct pws_handle {
   // output selection
   short slot_hru[PWS_N_HRU_VARS];
   short slot_seg[PWS_N_SEG_VARS];
-  int n_f64 = 0, n_i32 = 0, n_seg_sel = 0;
+  // n_f64 / n_seg_sel count the slots the kernels write per day: the drained
+  // selection first (n_f64_drain, n_seg_drain), then variables that are only
+  // accumulated on the device (pws_select_accumulations)
+  int n_f64 = 0, n_i32 = 0, n_seg_sel = 0, n_f64_drain = 0, n_seg_drain = 0;
+  std::vector<int> sel_hru, sel_seg;   // drained selection, in the caller's order
+  std::vector<int> acc_hru, acc_seg;   // accumulated variables (float64), in the caller's order
+  std::vector<int> acc_hru_slot, acc_seg_slot;
+  double *d_acc_hru = nullptr, *d_acc_seg = nullptr;  // [n][stride], [n][sstride]
+  int accumulate_on = 1;  // option "accumulate": 0 pauses the accumulation (values are kept)
   // channel (level order)
   int nlevels = 0, nchunks = 0, n_cross_edges = 0, n_ext_rows = 0, max_dmax = 0;
   int channel_chunk = PWS_CHUNK_THREADS;  // option: segments per routing chunk (<= CTA size)
@@ -130,13 +141,16 @@ struct pws_handle {
   double* d_rts = nullptr;
   double *d_ts = nullptr, *d_c0 = nullptr, *d_c1 = nullptr, *d_c2 = nullptr;
   double *d_outflow_ts = nullptr, *d_seg_inflow = nullptr;
-  // per-block scratch (sized for scratch_days)
+  // per-block scratch (sized for scratch_days).  What a block's column kernels
+  // write and its routing reads is double-buffered by block parity, so the
+  // column of block b+1 runs beside the routing of block b.
   int scratch_days = 0;
-  double *d_hru_lat = nullptr, *d_ots = nullptr, *d_day_outvol = nullptr, *d_day_dstor = nullptr,
-         *d_day_lat = nullptr;
-  int4* d_cal = nullptr;
-  int* d_viol = nullptr;
+  double *d_hru_lat[2] = {nullptr, nullptr}, *d_ots = nullptr, *d_day_outvol = nullptr,
+         *d_day_dstor = nullptr, *d_day_lat = nullptr;
+  int4* d_cal[2] = {nullptr, nullptr};
+  int* d_viol[2] = {nullptr, nullptr};
   int* d_progress = nullptr;  // [sstride] days published + 1 ticket counter at the end
+  int64_t blocks_enqueued = 0;  // parity = scratch slot of the next block
   // host ring for pws_run_host
   int ring_days = 0;
   double* d_forc[2] = {nullptr, nullptr};
@@ -156,16 +170,30 @@ struct pws_handle {
   int32_t* hs_viol[2] = {nullptr, nullptr};
   int32_t* hs_viol_run = nullptr;  // pinned, whole run: the verdicts never block the pipeline
   size_t hs_viol_run_cap = 0;
-  // streams / events
-  cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+  // streams / events.  s_compute: per-block preparation (calendar, counters,
+  // forcing widening); s_lane[g]: the column kernels of lane g (a contiguous
+  // range of CTA tiles), one launch per block each; s_route: routing, channel
+  // budget and the verdict copy of a block, after all its lanes.
+  static constexpr int kMaxLanes = 8;
+  cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr, s_route = nullptr;
+  cudaStream_t s_lane[kMaxLanes] = {};
+  cudaEvent_t ev_prep[2] = {nullptr, nullptr};        // block's scratch slot is prepared
+  cudaEvent_t ev_lane[2][kMaxLanes] = {};             // lane g has finished the block in slot p
+  cudaEvent_t ev_block[2] = {nullptr, nullptr};       // everything of the block in slot p is done
   cudaEvent_t ev_col0 = nullptr, ev_col1 = nullptr, ev_ch1 = nullptr;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr},
               ev_d2h[2] = {nullptr, nullptr};
   double ms_column = 0.0, ms_channel = 0.0;
-  int n_col_launch = 0, n_ch_launch = 0, last_channel_launches = 0;
+  int n_col_launch = 0, n_ch_launch = 0, last_channel_launches = 0, last_col_blocks = 0,
+      n_col_kernels = 0;
   std::vector<double> h_seg_inflow_init;
+  std::vector<int32_t> h_orig;  // routing position -> original segment index
   bool timing_pending = false;
+  // (start, stop) of every column / channel launch since the last pws_sync; the
+  // device time of a kind is the UNION of its intervals (lanes run concurrently)
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pairs_col, ev_pairs_ch;
+  cudaEvent_t ev_base = nullptr;  // time origin of the intervals
+  double ms_union_all = 0.0;
 };
 
 #define PWS_FAIL(h, ...)                                \
@@ -235,15 +263,25 @@ extern "C" int pws_create(pws_handle** out, int device, int64_t nhru, int64_t ns
   for (int k = 0; k < PWS_N_HRU_VARS; ++k) h->slot_hru[k] = -1;
   for (int k = 0; k < PWS_N_SEG_VARS; ++k) h->slot_seg[k] = -1;
   auto ok = [&](cudaError_t ee) { return ee == cudaSuccess; };
+  int prio_lo = 0, prio_hi = 0;  // routing is the short, latency-bound tail of a block: first in line
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   bool good = ok(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking)) &&
               ok(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking)) &&
               ok(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking)) &&
+              ok(cudaStreamCreateWithPriority(&h->s_route, cudaStreamNonBlocking, prio_hi)) &&
               ok(cudaEventCreate(&h->ev_col0)) && ok(cudaEventCreate(&h->ev_col1)) &&
-              ok(cudaEventCreate(&h->ev_ch1));
-  for (int b = 0; b < 2 && good; ++b)
+              ok(cudaEventCreate(&h->ev_ch1)) && ok(cudaEventCreate(&h->ev_base));
+  for (int g = 0; g < pws_handle::kMaxLanes && good; ++g)
+    good = ok(cudaStreamCreateWithFlags(&h->s_lane[g], cudaStreamNonBlocking));
+  for (int b = 0; b < 2 && good; ++b) {
     good = ok(cudaEventCreateWithFlags(&h->ev_h2d[b], cudaEventDisableTiming)) &&
            ok(cudaEventCreateWithFlags(&h->ev_comp[b], cudaEventDisableTiming)) &&
-           ok(cudaEventCreateWithFlags(&h->ev_d2h[b], cudaEventDisableTiming));
+           ok(cudaEventCreateWithFlags(&h->ev_d2h[b], cudaEventDisableTiming)) &&
+           ok(cudaEventCreateWithFlags(&h->ev_prep[b], cudaEventDisableTiming)) &&
+           ok(cudaEventCreateWithFlags(&h->ev_block[b], cudaEventDisableTiming));
+    for (int g = 0; g < pws_handle::kMaxLanes && good; ++g)
+      good = ok(cudaEventCreateWithFlags(&h->ev_lane[b][g], cudaEventDisableTiming));
+  }
   if (!good) {
     g_create_error = "pws_create: stream/event creation failed";
     delete h;
@@ -254,6 +292,7 @@ extern "C" int pws_create(pws_handle** out, int device, int64_t nhru, int64_t ns
 }
 
 static void clear_timing(pws_handle* h);
+static cudaError_t sync_all(pws_handle* h);
 
 static void free_stage(pws_handle* h) {
   for (int b = 0; b < 2; ++b) {
@@ -282,13 +321,15 @@ static void free_ring(pws_handle* h) {
 }
 
 static void free_scratch(pws_handle* h) {
-  cudaFree(h->d_hru_lat); h->d_hru_lat = nullptr;
+  for (int b = 0; b < 2; ++b) {
+    cudaFree(h->d_hru_lat[b]); h->d_hru_lat[b] = nullptr;
+    cudaFree(h->d_cal[b]); h->d_cal[b] = nullptr;
+    cudaFree(h->d_viol[b]); h->d_viol[b] = nullptr;
+  }
   cudaFree(h->d_ots); h->d_ots = nullptr;
   cudaFree(h->d_day_outvol); h->d_day_outvol = nullptr;
   cudaFree(h->d_day_dstor); h->d_day_dstor = nullptr;
   cudaFree(h->d_day_lat); h->d_day_lat = nullptr;
-  cudaFree(h->d_cal); h->d_cal = nullptr;
-  cudaFree(h->d_viol); h->d_viol = nullptr;
   cudaFree(h->d_progress); h->d_progress = nullptr;
   h->scratch_days = 0;
 }
@@ -300,6 +341,8 @@ static void free_device(pws_handle* h) {
   for (auto& p : h->d_soltab) { cudaFree(p); p = nullptr; }
   cudaFree(h->d_snarea); h->d_snarea = nullptr;
   cudaFree(h->d_err); h->d_err = nullptr;
+  cudaFree(h->d_acc_hru); h->d_acc_hru = nullptr;
+  cudaFree(h->d_acc_seg); h->d_acc_seg = nullptr;
   void* ch[] = {h->d_tsi, h->d_up_ptr, h->d_up_idx, h->d_hru_ptr, h->d_hru_idx, h->d_seg_flags,
                 h->d_orig, h->d_chunk_begin, h->d_chunk_dmax, h->d_delay, h->d_ext_row, h->d_rts,
                 h->d_ts, h->d_c0, h->d_c1, h->d_c2, h->d_outflow_ts, h->d_seg_inflow};
@@ -320,10 +363,15 @@ extern "C" int pws_destroy(pws_handle* h) {
   free_device(h);
   clear_timing(h);
   cudaEventDestroy(h->ev_col0); cudaEventDestroy(h->ev_col1); cudaEventDestroy(h->ev_ch1);
+  cudaEventDestroy(h->ev_base);
   for (int b = 0; b < 2; ++b) {
     cudaEventDestroy(h->ev_h2d[b]); cudaEventDestroy(h->ev_comp[b]); cudaEventDestroy(h->ev_d2h[b]);
+    cudaEventDestroy(h->ev_prep[b]); cudaEventDestroy(h->ev_block[b]);
+    for (auto e : h->ev_lane[b]) cudaEventDestroy(e);
   }
   cudaStreamDestroy(h->s_compute); cudaStreamDestroy(h->s_h2d); cudaStreamDestroy(h->s_d2h);
+  cudaStreamDestroy(h->s_route);
+  for (auto st : h->s_lane) cudaStreamDestroy(st);
   delete h;
   return 0;
 }
@@ -384,6 +432,23 @@ extern "C" int pws_set_option(pws_handle* h, const char* name, double value) {
   else if (!strcmp(name, "soltab_device")) h->soltab_device = value != 0.0;
   else if (!strcmp(name, "tma")) { h->tma = value != 0.0; return 0; }
   else if (!strcmp(name, "tiled_outputs")) { h->tiled_outputs = value != 0.0; return 0; }
+  else if (!strcmp(name, "lanes")) {
+    if (value < 0 || value > pws_handle::kMaxLanes)
+      PWS_FAIL(h, "pws_set_option: lanes must be in 0..%d", pws_handle::kMaxLanes);
+    PWS_CUDA(h, sync_all(h));  // a lane's stream orders the blocks of ITS tiles
+    h->lanes_opt = (int)value;
+    return 0;
+  }
+  else if (!strcmp(name, "overlap_routing")) { h->overlap_routing = value != 0.0; return 0; }
+  else if (!strcmp(name, "accumulate")) { h->accumulate_on = value != 0.0; return 0; }
+  else if (!strcmp(name, "forcing_period")) {
+    if (value < 0 || (value > 0 && h->nhru % (int64_t)value != 0))
+      PWS_FAIL(h, "pws_set_option: forcing_period must divide nhru (%lld)", (long long)h->nhru);
+    PWS_CUDA(h, sync_all(h));
+    h->forcing_period = (int64_t)value;
+    free_ring(h);  // the forcing ring is sized by the number of forcing columns
+    return 0;
+  }
   else if (!strcmp(name, "column_hrus")) {
     if (value != 0 && value != 128 && value != PWS_COLUMN_HRUS)
       PWS_FAIL(h, "pws_set_option: column_hrus must be 0, 128 or %d", PWS_COLUMN_HRUS);
@@ -688,6 +753,7 @@ static int channel_build(pws_handle* h) {
   PWS_CUDA(h, up_f64(&h->d_outflow_ts, outflow_ts));
   PWS_CUDA(h, up_f64(&h->d_seg_inflow, seg_inflow));
   h->h_seg_inflow_init = seg_inflow;
+  h->h_orig = orig;
   return 0;
 }
 
@@ -871,34 +937,118 @@ extern "C" int pws_get_soltab(pws_handle* h, int which, double* out) {
 }
 
 // --------------------------------------------------------------- outputs
-extern "C" int pws_select_outputs(pws_handle* h, int n_hru, const int32_t* hru_idx, int n_seg,
-                                  const int32_t* seg_idx) {
-  short sh[PWS_N_HRU_VARS], ss[PWS_N_SEG_VARS];
-  for (auto& v : sh) v = -1;
-  for (auto& v : ss) v = -1;
+// slots of one day of results: drained variables first, in selection order
+// (float64 and int32 counted separately), then the accumulate-only ones
+static void rebuild_slots(pws_handle* h) {
+  for (auto& v : h->slot_hru) v = -1;
+  for (auto& v : h->slot_seg) v = -1;
   int nf = 0, ni = 0, ns = 0;
-  for (int k = 0; k < n_hru; ++k) {
-    const int v = hru_idx[k];
-    if (v < 0 || v >= PWS_N_HRU_VARS || sh[v] >= 0)
-      PWS_FAIL(h, "pws_select_outputs: bad or repeated HRU variable index %d", v);
-    sh[v] = (short)(names().hru_var_kind[v] == 0 ? nf++ : ni++);
+  for (int v : h->sel_hru) h->slot_hru[v] = (short)(names().hru_var_kind[v] == 0 ? nf++ : ni++);
+  for (int v : h->sel_seg) h->slot_seg[v] = (short)ns++;
+  h->n_f64_drain = nf;
+  h->n_seg_drain = ns;
+  h->acc_hru_slot.clear();
+  h->acc_seg_slot.clear();
+  for (int v : h->acc_hru) {
+    if (h->slot_hru[v] < 0) h->slot_hru[v] = (short)nf++;
+    h->acc_hru_slot.push_back(h->slot_hru[v]);
   }
-  for (int k = 0; k < n_seg; ++k) {
-    const int v = seg_idx[k];
-    if (v < 0 || v >= PWS_N_SEG_VARS || ss[v] >= 0)
-      PWS_FAIL(h, "pws_select_outputs: bad or repeated segment variable index %d", v);
-    ss[v] = (short)ns++;
+  for (int v : h->acc_seg) {
+    if (h->slot_seg[v] < 0) h->slot_seg[v] = (short)ns++;
+    h->acc_seg_slot.push_back(h->slot_seg[v]);
   }
-  memcpy(h->slot_hru, sh, sizeof sh);
-  memcpy(h->slot_seg, ss, sizeof ss);
   h->n_f64 = nf;
   h->n_i32 = ni;
   h->n_seg_sel = ns;
+}
+
+extern "C" int pws_select_outputs(pws_handle* h, int n_hru, const int32_t* hru_idx, int n_seg,
+                                  const int32_t* seg_idx) {
+  std::vector<char> seen_h(PWS_N_HRU_VARS, 0), seen_s(PWS_N_SEG_VARS, 0);
+  for (int k = 0; k < n_hru; ++k) {
+    const int v = hru_idx[k];
+    if (v < 0 || v >= PWS_N_HRU_VARS || seen_h[v])
+      PWS_FAIL(h, "pws_select_outputs: bad or repeated HRU variable index %d", v);
+    seen_h[v] = 1;
+  }
+  for (int k = 0; k < n_seg; ++k) {
+    const int v = seg_idx[k];
+    if (v < 0 || v >= PWS_N_SEG_VARS || seen_s[v])
+      PWS_FAIL(h, "pws_select_outputs: bad or repeated segment variable index %d", v);
+    seen_s[v] = 1;
+  }
+  h->sel_hru.assign(hru_idx, hru_idx + n_hru);
+  h->sel_seg.assign(seg_idx, seg_idx + n_seg);
+  rebuild_slots(h);
   // the rings of pws_run_host are kept: they are re-allocated only when a run
   // needs more room than they have
   return 0;
 }
 
+// Budget accumulations on the device (base/budget.py:262-269: every term of a
+// process's mass budget is summed over the steps, `acc += value * dt`): the
+// chosen float64 variables are written by the kernels like selected outputs
+// but need not be drained -- k_accumulate adds each block's days to a running
+// per-unit sum, in day order, exactly the reference's sequence of additions.
+extern "C" int pws_select_accumulations(pws_handle* h, int n_hru, const int32_t* hru_idx, int n_seg,
+                                        const int32_t* seg_idx) {
+  std::vector<char> seen_h(PWS_N_HRU_VARS, 0), seen_s(PWS_N_SEG_VARS, 0);
+  for (int k = 0; k < n_hru; ++k) {
+    const int v = hru_idx[k];
+    if (v < 0 || v >= PWS_N_HRU_VARS || seen_h[v] || names().hru_var_kind[v] != 0)
+      PWS_FAIL(h, "pws_select_accumulations: bad, repeated or non-float64 HRU variable index %d", v);
+    seen_h[v] = 1;
+  }
+  for (int k = 0; k < n_seg; ++k) {
+    const int v = seg_idx[k];
+    if (v < 0 || v >= PWS_N_SEG_VARS || seen_s[v])
+      PWS_FAIL(h, "pws_select_accumulations: bad or repeated segment variable index %d", v);
+    seen_s[v] = 1;
+  }
+  PWS_CUDA(h, cudaSetDevice(h->device));
+  PWS_CUDA(h, sync_all(h));
+  h->acc_hru.assign(hru_idx, hru_idx + n_hru);
+  h->acc_seg.assign(seg_idx, seg_idx + n_seg);
+  cudaFree(h->d_acc_hru); h->d_acc_hru = nullptr;
+  cudaFree(h->d_acc_seg); h->d_acc_seg = nullptr;
+  if (n_hru > 0) {
+    PWS_CUDA(h, cudaMalloc(&h->d_acc_hru, (size_t)n_hru * h->stride * sizeof(double)));
+    PWS_CUDA(h, cudaMemset(h->d_acc_hru, 0, (size_t)n_hru * h->stride * sizeof(double)));
+  }
+  if (n_seg > 0 && h->nseg > 0) {
+    PWS_CUDA(h, cudaMalloc(&h->d_acc_seg, (size_t)n_seg * h->sstride * sizeof(double)));
+    PWS_CUDA(h, cudaMemset(h->d_acc_seg, 0, (size_t)n_seg * h->sstride * sizeof(double)));
+  }
+  rebuild_slots(h);
+  return 0;
+}
+
+extern "C" int pws_get_accumulations(pws_handle* h, double* h_hru, double* h_seg) {
+  PWS_CUDA(h, cudaSetDevice(h->device));
+  PWS_CUDA(h, sync_all(h));
+  if (h_hru && h->d_acc_hru)
+    PWS_CUDA(h, cudaMemcpy2D(h_hru, (size_t)h->nhru * sizeof(double), h->d_acc_hru,
+                             (size_t)h->stride * sizeof(double), (size_t)h->nhru * sizeof(double),
+                             h->acc_hru.size(), cudaMemcpyDeviceToHost));
+  if (h_seg && h->d_acc_seg)
+    PWS_CUDA(h, cudaMemcpy2D(h_seg, (size_t)h->nseg * sizeof(double), h->d_acc_seg,
+                             (size_t)h->sstride * sizeof(double), (size_t)h->nseg * sizeof(double),
+                             h->acc_seg.size(), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int pws_clear_accumulations(pws_handle* h) {
+  PWS_CUDA(h, cudaSetDevice(h->device));
+  PWS_CUDA(h, sync_all(h));
+  if (h->d_acc_hru)
+    PWS_CUDA(h, cudaMemset(h->d_acc_hru, 0, h->acc_hru.size() * h->stride * sizeof(double)));
+  if (h->d_acc_seg)
+    PWS_CUDA(h, cudaMemset(h->d_acc_seg, 0, h->acc_seg.size() * h->sstride * sizeof(double)));
+  return 0;
+}
+
+// rows per day of the device-side result buffers (pws_run_device): the drained
+// selection plus the accumulate-only variables behind it
 extern "C" int pws_n_selected(pws_handle* h, int* n_f64, int* n_i32, int* n_seg) {
   if (n_f64) *n_f64 = h->n_f64;
   if (n_i32) *n_i32 = h->n_i32;
@@ -912,10 +1062,12 @@ static int ensure_scratch(pws_handle* h, int ndays) {
   cudaDeviceSynchronize();
   free_scratch(h);
   const size_t T = (size_t)ndays;
-  PWS_CUDA(h, cudaMalloc(&h->d_cal, T * sizeof(int4)));
-  PWS_CUDA(h, cudaMalloc(&h->d_viol, T * BUD_N * sizeof(int)));
+  for (int b = 0; b < 2; ++b) {
+    PWS_CUDA(h, cudaMalloc(&h->d_cal[b], T * sizeof(int4)));
+    PWS_CUDA(h, cudaMalloc(&h->d_viol[b], T * BUD_N * sizeof(int)));
+    if (h->nseg > 0) PWS_CUDA(h, cudaMalloc(&h->d_hru_lat[b], T * h->stride * sizeof(double)));
+  }
   if (h->nseg > 0) {
-    PWS_CUDA(h, cudaMalloc(&h->d_hru_lat, T * h->stride * sizeof(double)));
     PWS_CUDA(h, cudaMalloc(&h->d_ots, T * 24 * std::max(h->n_ext_rows, 1) * sizeof(double)));
     PWS_CUDA(h, cudaMalloc(&h->d_progress, (size_t)(h->sstride + 32) * sizeof(int)));
     PWS_CUDA(h, cudaMalloc(&h->d_day_outvol, T * h->sstride * sizeof(double)));
@@ -940,9 +1092,15 @@ static cudaEvent_t new_event(pws_handle* /*h*/) {
   return e;
 }
 
-// enqueue the channel kernels for one block on s_compute
-static int enqueue_channel(pws_handle* h, int ndays, const double* d_hru_lat,
-                           const double* d_seg_lat_in, double* d_seg_out, bool budget) {
+// first timed launch since the last pws_sync: the time origin of the intervals
+static void mark_base(pws_handle* h, cudaStream_t st) {
+  if (h->ev_pairs_col.empty() && h->ev_pairs_ch.empty()) cudaEventRecord(h->ev_base, st);
+}
+
+// enqueue the channel kernels for one block on stream `st`; `viol` = the
+// block's verdict rows (or null: no channel budget)
+static int enqueue_channel(pws_handle* h, cudaStream_t st, int ndays, const double* d_hru_lat,
+                           const double* d_seg_lat_in, double* d_seg_out, int* viol) {
   ChannelArgs a{};
   a.nseg = h->nseg;
   a.sstride = h->sstride;
@@ -963,8 +1121,7 @@ static int enqueue_channel(pws_handle* h, int ndays, const double* d_hru_lat,
   a.ticket = h->d_progress + h->sstride;
   a.err = h->d_err;
   // progress counters (cross-chunk edges) and the chunk ticket start at 0
-  PWS_CUDA(h, cudaMemsetAsync(h->d_progress, 0, (size_t)(h->sstride + 32) * sizeof(int),
-                              h->s_compute));
+  PWS_CUDA(h, cudaMemsetAsync(h->d_progress, 0, (size_t)(h->sstride + 32) * sizeof(int), st));
   if (!h->route_attr_set) {
     PWS_CUDA(h, cudaFuncSetAttribute(k_route_chunks<PWS_ROUTE_HOURS>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -974,20 +1131,25 @@ static int enqueue_channel(pws_handle* h, int ndays, const double* d_hru_lat,
                                      (int)route_smem_bytes(PWS_ROUTE_HOURS_SHALLOW)));
     h->route_attr_set = true;
   }
+  cudaEvent_t e0 = new_event(h), e1 = new_event(h);
+  mark_base(h, st);
+  cudaEventRecord(e0, st);
   if (route_hours(h) == PWS_ROUTE_HOURS_SHALLOW)
     k_route_chunks<PWS_ROUTE_HOURS_SHALLOW><<<(unsigned)h->nchunks, PWS_CHUNK_THREADS,
-                                              route_smem_bytes(PWS_ROUTE_HOURS_SHALLOW), h->s_compute>>>(a);
+                                              route_smem_bytes(PWS_ROUTE_HOURS_SHALLOW), st>>>(a);
   else
     k_route_chunks<PWS_ROUTE_HOURS><<<(unsigned)h->nchunks, PWS_CHUNK_THREADS,
-                                      route_smem_bytes(PWS_ROUTE_HOURS), h->s_compute>>>(a);
+                                      route_smem_bytes(PWS_ROUTE_HOURS), st>>>(a);
   h->launches++;
   h->last_channel_launches += 1;
-  if (budget) {
-    k_channel_budget<<<ndays, 256, 0, h->s_compute>>>(h->nseg, h->sstride, h->d_day_lat,
-                                                      h->d_day_outvol, h->d_day_dstor, h->d_viol);
+  if (viol) {
+    k_channel_budget<<<ndays, 256, 0, st>>>(h->nseg, h->sstride, h->d_day_lat, h->d_day_outvol,
+                                            h->d_day_dstor, viol);
     h->launches++;
     h->last_channel_launches += 1;
   }
+  cudaEventRecord(e1, st);
+  h->ev_pairs_ch.push_back({e0, e1});
   PWS_CUDA(h, cudaGetLastError());
   return 0;
 }
@@ -1001,25 +1163,61 @@ static int column_hrus(pws_handle* h) {
   return h->nhru <= (int64_t)nsm * PWS_COLUMN_HRUS ? 128 : PWS_COLUMN_HRUS;
 }
 
+// Column launches per block.  A CTA of the column kernel holds an SM's whole
+// register file for a block of days, so a launch whose grid is not a multiple
+// of the SM count leaves SMs idle in its last wave (CONUS: 431 CTAs = 2.9
+// waves, an 8-GPU share of the 1024-member ensemble: 2.58).  The grid is
+// therefore cut into `lanes` contiguous ranges of tiles, each on its own
+// stream: a lane's next block only depends on that lane's previous block
+// (HRUs are independent), so the tail of one lane's wave is filled by the head
+// of the others' next block.
+static int column_lanes(pws_handle* h, int ntiles, int H) {
+  if (h->lanes_opt > 0) return std::min(h->lanes_opt, std::max(1, ntiles));
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+  const int slots = nsm * (H == 128 ? 2 : 1);  // CTAs resident at a time
+  if (ntiles <= slots) return 1;               // one wave: nothing to smooth
+  const int g = (ntiles + (2 * slots) / 3 - 1) / ((2 * slots) / 3);
+  return std::max(1, std::min(g, pws_handle::kMaxLanes));
+}
+
+// number of forcing columns (the row length of prcp / tmax / tmin)
+static int64_t forcing_columns(const pws_handle* h) {
+  return h->forcing_period > 0 ? h->forcing_period : h->nhru;
+}
+
 static void fill_column_args(pws_handle* h, ColumnArgs& a, int ndays, const double* d_prcp,
                              const double* d_tmax, const double* d_tmin, int64_t fstride,
-                             double* d_out_f64, int32_t* d_out_i32, bool want_viol) {
+                             double* d_out_f64, int32_t* d_out_i32, int slot, bool want_viol) {
   a.P = h->P;
   a.state = h->d_state;
   a.prcp = d_prcp; a.tmax = d_tmax; a.tmin = d_tmin;
   a.fstride = fstride;
+  a.fperiod = h->forcing_period;
   // TMA bulk copies need 16-byte aligned rows of a multiple of 16 bytes
-  // (an odd row is copied with one padding element, which must exist: fstride > nhru)
-  a.use_tma = (h->tma && fstride % 2 == 0 && (h->nhru % 2 == 0 || fstride > h->nhru) &&
-               ((uintptr_t)d_prcp | (uintptr_t)d_tmax | (uintptr_t)d_tmin) % 16 == 0) ? 1 : 0;
-  a.cal = h->d_cal;
+  // (an odd row is copied with one padding element, which must exist: fstride > nhru);
+  // with a forcing period a CTA's row may wrap once: both pieces must stay aligned
+  const int H = (h->column_hrus_opt == 128 || h->column_hrus_opt == PWS_COLUMN_HRUS)
+                    ? h->column_hrus_opt : 0;
+  (void)H;
+  const int64_t ncol = forcing_columns(h);
+  bool tma = h->tma && fstride % 2 == 0 &&
+             ((uintptr_t)d_prcp | (uintptr_t)d_tmax | (uintptr_t)d_tmin) % 16 == 0;
+  if (h->forcing_period > 0)
+    tma = tma && ncol % 2 == 0 && ncol >= PWS_COLUMN_HRUS;
+  else
+    tma = tma && (h->nhru % 2 == 0 || fstride > h->nhru);
+  a.use_tma = tma ? 1 : 0;
+  a.cal = h->d_cal[slot];
   a.ndays = ndays;
   a.out_f64 = d_out_f64; a.out_i32 = d_out_i32;
   a.ostride = h->nhru;
   a.n_f64 = h->n_f64; a.n_i32 = h->n_i32;
-  a.hru_lat = h->nseg > 0 ? h->d_hru_lat : nullptr;
-  a.viol = want_viol ? h->d_viol : nullptr;
+  a.hru_lat = h->nseg > 0 ? h->d_hru_lat[slot] : nullptr;
+  a.viol = want_viol ? h->d_viol[slot] : nullptr;
   a.err = h->d_err;
+  a.tile0 = 0;
+  a.ntiles = 0;
   for (int v = 0; v < PWS_N_HRU_VARS; ++v) {
     const int sl = h->slot_hru[v];
     const int64_t esz = names().hru_var_kind[v] == 0 ? 8 : 4;
@@ -1027,10 +1225,23 @@ static void fill_column_args(pws_handle* h, ColumnArgs& a, int ndays, const doub
   }
 }
 
-// enqueue one block of days on s_compute (forcings/outputs are device pointers)
+// Enqueue one block of days (forcings / outputs are device pointers; what the
+// caller enqueued on s_compute before -- an upload wait, k_widen_forcings --
+// is ordered in front of it).  Stream structure per block, scratch slot p =
+// block parity:
+//   s_compute  wait(block in slot p done) -> calendar upload, counters := 0 -> ev_prep[p]
+//   s_lane[g]  wait(ev_prep[p]) -> k_hru_column over the lane's tiles -> ev_lane[p][g]
+//   s_route    wait(all ev_lane[p][.]) -> k_route_chunks, k_channel_budget,
+//              verdict copy -> ev_block[p]
+// so the column kernels of block b+1 run beside the routing of block b, and a
+// lane does not wait for the other lanes' tails.  With the option
+// "overlap_routing" 0 the lanes of block b+1 also wait for ev_block of block b.
+// h_viol_dst (pinned or null) receives the block's [ndays][6] verdict rows.
+// On return ev_block[p] marks the completion of the block; *slot_out = p.
 static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const double* d_prcp,
                          const double* d_tmax, const double* d_tmin, int64_t fstride,
-                         double* d_out_f64, int32_t* d_out_i32, double* d_seg_out, bool want_viol) {
+                         double* d_out_f64, int32_t* d_out_i32, double* d_seg_out,
+                         int32_t* h_viol_dst, int* slot_out) {
   // sink: nothing selected / everything in registry order / a subset
   int mode = SINK_SELECT;
   if (h->n_f64 + h->n_i32 == 0) {
@@ -1046,17 +1257,25 @@ static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const d
     mode = SINK_TILED;
   }
   if (ensure_scratch(h, ndays)) return 1;
-  PWS_CUDA(h, cudaMemcpyAsync(h->d_cal, h_cal, (size_t)ndays * sizeof(int4),
+  const bool want_viol = h_viol_dst != nullptr;
+  const int p = (int)(h->blocks_enqueued & 1);
+  const int prev = p ^ 1;
+  h->blocks_enqueued++;
+  if (slot_out) *slot_out = p;
+  // the slot's previous block (two blocks ago) must be complete
+  PWS_CUDA(h, cudaStreamWaitEvent(h->s_compute, h->ev_block[p], 0));
+  PWS_CUDA(h, cudaMemcpyAsync(h->d_cal[p], h_cal, (size_t)ndays * sizeof(int4),
                               cudaMemcpyHostToDevice, h->s_compute));
   if (want_viol)
-    PWS_CUDA(h, cudaMemsetAsync(h->d_viol, 0, (size_t)ndays * BUD_N * sizeof(int), h->s_compute));
+    PWS_CUDA(h, cudaMemsetAsync(h->d_viol[p], 0, (size_t)ndays * BUD_N * sizeof(int), h->s_compute));
+  PWS_CUDA(h, cudaEventRecord(h->ev_prep[p], h->s_compute));
   ColumnArgs a{};
-  fill_column_args(h, a, ndays, d_prcp, d_tmax, d_tmin, fstride, d_out_f64, d_out_i32, want_viol);
-  cudaEvent_t e0 = new_event(h), e1 = new_event(h), e2 = new_event(h);
-  cudaEventRecord(e0, h->s_compute);
+  fill_column_args(h, a, ndays, d_prcp, d_tmax, d_tmin, fstride, d_out_f64, d_out_i32, p, want_viol);
   const int H = column_hrus(h);
-  const unsigned grid = (unsigned)((h->nhru + H - 1) / H);
-#define PWS_LAUNCH_COLUMN(MODE, HH)                                                              \
+  const int ntiles = (int)((h->nhru + H - 1) / H);
+  const int lanes = column_lanes(h, ntiles, H);
+  a.ntiles = ntiles;
+#define PWS_LAUNCH_COLUMN(MODE, HH, GRID, ST)                                                    \
   do {                                                                                           \
     if (!h->smem_attr_set[(MODE) * 2 + ((HH) == 128)]) {                                         \
       PWS_CUDA(h, cudaFuncSetAttribute(k_hru_column<MODE, HH>,                                   \
@@ -1068,33 +1287,77 @@ static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const d
                                        column_carveout_pct(HH)));                                \
       h->smem_attr_set[(MODE) * 2 + ((HH) == 128)] = true;                                       \
     }                                                                                            \
-    k_hru_column<MODE, HH><<<grid, 2 * (HH), column_smem_bytes(HH), h->s_compute>>>(a);          \
+    k_hru_column<MODE, HH><<<(GRID), 2 * (HH), column_smem_bytes(HH), (ST)>>>(a);                \
   } while (0)
-  if (H == 128) {
-    if (mode == SINK_FULL) PWS_LAUNCH_COLUMN(SINK_FULL, 128);
-    else if (mode == SINK_TILED) PWS_LAUNCH_COLUMN(SINK_TILED, 128);
-    else if (mode == SINK_NONE) PWS_LAUNCH_COLUMN(SINK_NONE, 128);
-    else PWS_LAUNCH_COLUMN(SINK_SELECT, 128);
-  } else {
-    if (mode == SINK_FULL) PWS_LAUNCH_COLUMN(SINK_FULL, PWS_COLUMN_HRUS);
-    else if (mode == SINK_TILED) PWS_LAUNCH_COLUMN(SINK_TILED, PWS_COLUMN_HRUS);
-    else if (mode == SINK_NONE) PWS_LAUNCH_COLUMN(SINK_NONE, PWS_COLUMN_HRUS);
-    else PWS_LAUNCH_COLUMN(SINK_SELECT, PWS_COLUMN_HRUS);
+  for (int g = 0; g < lanes; ++g) {
+    const int t0 = (int)((int64_t)ntiles * g / lanes), t1 = (int)((int64_t)ntiles * (g + 1) / lanes);
+    if (t1 <= t0) {
+      PWS_CUDA(h, cudaEventRecord(h->ev_lane[p][g], h->s_lane[g]));
+      continue;
+    }
+    cudaStream_t st = h->s_lane[g];
+    PWS_CUDA(h, cudaStreamWaitEvent(st, h->ev_prep[p], 0));
+    if (!h->overlap_routing) PWS_CUDA(h, cudaStreamWaitEvent(st, h->ev_block[prev], 0));
+    a.tile0 = t0;
+    const unsigned grid = (unsigned)(t1 - t0);
+    cudaEvent_t e0 = new_event(h), e1 = new_event(h);
+    mark_base(h, st);
+    cudaEventRecord(e0, st);
+    if (H == 128) {
+      if (mode == SINK_FULL) PWS_LAUNCH_COLUMN(SINK_FULL, 128, grid, st);
+      else if (mode == SINK_TILED) PWS_LAUNCH_COLUMN(SINK_TILED, 128, grid, st);
+      else if (mode == SINK_NONE) PWS_LAUNCH_COLUMN(SINK_NONE, 128, grid, st);
+      else PWS_LAUNCH_COLUMN(SINK_SELECT, 128, grid, st);
+    } else {
+      if (mode == SINK_FULL) PWS_LAUNCH_COLUMN(SINK_FULL, PWS_COLUMN_HRUS, grid, st);
+      else if (mode == SINK_TILED) PWS_LAUNCH_COLUMN(SINK_TILED, PWS_COLUMN_HRUS, grid, st);
+      else if (mode == SINK_NONE) PWS_LAUNCH_COLUMN(SINK_NONE, PWS_COLUMN_HRUS, grid, st);
+      else PWS_LAUNCH_COLUMN(SINK_SELECT, PWS_COLUMN_HRUS, grid, st);
+    }
+    h->launches++;
+    PWS_CUDA(h, cudaGetLastError());
+    cudaEventRecord(e1, st);
+    h->ev_pairs_col.push_back({e0, e1});
+    PWS_CUDA(h, cudaEventRecord(h->ev_lane[p][g], st));
+    PWS_CUDA(h, cudaStreamWaitEvent(h->s_route, h->ev_lane[p][g], 0));
   }
 #undef PWS_LAUNCH_COLUMN
-  h->launches++;
-  PWS_CUDA(h, cudaGetLastError());
-  cudaEventRecord(e1, h->s_compute);
+  h->last_col_blocks++;
+  // (the routing of block b-1 precedes this block's on s_route: the segment
+  // state, the day_* rows and the progress counters are single-buffered)
   if (h->nseg > 0)
-    if (enqueue_channel(h, ndays, h->d_hru_lat, nullptr, d_seg_out, want_viol)) return 1;
-  cudaEventRecord(e2, h->s_compute);
-  h->ev_pairs_col.push_back({e0, e1});
-  h->ev_pairs_ch.push_back({e1, e2});
+    if (enqueue_channel(h, h->s_route, ndays, h->d_hru_lat[p], nullptr, d_seg_out,
+                        want_viol ? h->d_viol[p] : nullptr))
+      return 1;
+  if (want_viol)
+    PWS_CUDA(h, cudaMemcpyAsync(h_viol_dst, h->d_viol[p], (size_t)ndays * BUD_N * sizeof(int),
+                                cudaMemcpyDeviceToHost, h->s_route));
+  if (h->accumulate_on && (!h->acc_hru.empty() || (!h->acc_seg.empty() && h->nseg > 0))) {
+    if (mode == SINK_TILED) PWS_FAIL(h, "accumulations need the rows layout (tiled_outputs 0)");
+    AccSlots sl{};
+    if (!h->acc_hru.empty()) {
+      if (h->acc_hru.size() > (size_t)AccSlots::kMax) PWS_FAIL(h, "too many accumulated variables");
+      for (size_t k = 0; k < h->acc_hru.size(); ++k) sl.s[k] = h->acc_hru_slot[k];
+      k_accumulate<<<dim3((unsigned)((h->nhru + 255) / 256), (unsigned)h->acc_hru.size()), 256, 0,
+                     h->s_route>>>(sl, d_out_f64, (int64_t)h->n_f64 * h->nhru, h->nhru, ndays, h->nhru,
+                                   h->d_acc_hru, h->stride);
+      h->launches++;
+    }
+    if (!h->acc_seg.empty() && h->nseg > 0) {
+      for (size_t k = 0; k < h->acc_seg.size(); ++k) sl.s[k] = h->acc_seg_slot[k];
+      k_accumulate<<<dim3((unsigned)((h->nseg + 255) / 256), (unsigned)h->acc_seg.size()), 256, 0,
+                     h->s_route>>>(sl, d_seg_out, (int64_t)h->n_seg_sel * h->nseg, h->nseg, ndays,
+                                   h->nseg, h->d_acc_seg, h->sstride);
+      h->launches++;
+    }
+    PWS_CUDA(h, cudaGetLastError());
+  }
+  PWS_CUDA(h, cudaEventRecord(h->ev_block[p], h->s_route));
   return 0;
 }
 
 static void clear_timing(pws_handle* h) {
-  for (auto& pr : h->ev_pairs_col) cudaEventDestroy(pr.first);
+  for (auto& pr : h->ev_pairs_col) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   for (auto& pr : h->ev_pairs_ch) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   h->ev_pairs_col.clear();
   h->ev_pairs_ch.clear();
@@ -1115,26 +1378,56 @@ static int check_device_errors(pws_handle* h) {
   return 0;
 }
 
+// every stream of the handle is idle afterwards
+static cudaError_t sync_all(pws_handle* h) {
+  cudaError_t e = cudaStreamSynchronize(h->s_h2d);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->s_compute);
+  for (int g = 0; g < pws_handle::kMaxLanes && e == cudaSuccess; ++g)
+    e = cudaStreamSynchronize(h->s_lane[g]);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->s_route);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->s_d2h);
+  return e;
+}
+
+// length of the union of the (start, stop) intervals, in ms from ev_base
+static double union_ms(pws_handle* h, const std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& ev) {
+  std::vector<std::pair<float, float>> iv;
+  for (auto& pr : ev) {
+    float t0 = 0, t1 = 0;
+    if (cudaEventElapsedTime(&t0, h->ev_base, pr.first) != cudaSuccess ||
+        cudaEventElapsedTime(&t1, h->ev_base, pr.second) != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    iv.push_back({t0, t1});
+  }
+  std::sort(iv.begin(), iv.end());
+  double tot = 0.0;
+  float lo = 0, hi = -1;
+  for (auto& x : iv) {
+    if (hi < lo || x.first > hi) {
+      if (hi >= lo) tot += hi - lo;
+      lo = x.first;
+      hi = x.second;
+    } else {
+      hi = std::max(hi, x.second);
+    }
+  }
+  if (hi >= lo) tot += hi - lo;
+  return tot;
+}
+
 extern "C" int pws_sync(pws_handle* h) {
   PWS_CUDA(h, cudaSetDevice(h->device));
-  PWS_CUDA(h, cudaStreamSynchronize(h->s_h2d));
-  PWS_CUDA(h, cudaStreamSynchronize(h->s_compute));
-  PWS_CUDA(h, cudaStreamSynchronize(h->s_d2h));
-  if (!h->ev_pairs_col.empty()) {
-    h->ms_column = h->ms_channel = 0.0;
-    h->n_col_launch = (int)h->ev_pairs_col.size();
+  PWS_CUDA(h, sync_all(h));
+  if (!h->ev_pairs_col.empty() || !h->ev_pairs_ch.empty()) {
+    h->n_col_launch = h->last_col_blocks;
+    h->n_col_kernels = (int)h->ev_pairs_col.size();
     h->n_ch_launch = h->last_channel_launches;
     h->last_channel_launches = 0;
-    for (auto& pr : h->ev_pairs_col) {
-      float ms = 0;
-      cudaEventElapsedTime(&ms, pr.first, pr.second);
-      h->ms_column += ms;
-    }
-    for (auto& pr : h->ev_pairs_ch) {
-      float ms = 0;
-      cudaEventElapsedTime(&ms, pr.first, pr.second);
-      h->ms_channel += ms;
-    }
+    h->last_col_blocks = 0;
+    h->ms_column = union_ms(h, h->ev_pairs_col);
+    h->ms_channel = union_ms(h, h->ev_pairs_ch);
     clear_timing(h);
   }
   return check_device_errors(h);
@@ -1147,13 +1440,8 @@ extern "C" int pws_run_device(pws_handle* h, int ndays, const int32_t* h_cal,
   if (!h->inited) PWS_FAIL(h, "pws_run_device before pws_init");
   if (ndays <= 0) return 0;
   PWS_CUDA(h, cudaSetDevice(h->device));
-  if (enqueue_block(h, ndays, h_cal, d_prcp, d_tmax, d_tmin, h->nhru, d_out_f64, d_out_i32,
-                    d_seg_out, h_budget_viol != nullptr))
-    return 1;
-  if (h_budget_viol)
-    PWS_CUDA(h, cudaMemcpyAsync(h_budget_viol, h->d_viol, (size_t)ndays * BUD_N * sizeof(int),
-                                cudaMemcpyDeviceToHost, h->s_compute));
-  return 0;
+  return enqueue_block(h, ndays, h_cal, d_prcp, d_tmax, d_tmin, forcing_columns(h), d_out_f64,
+                       d_out_i32, d_seg_out, h_budget_viol, nullptr);
 }
 
 extern "C" int pws_run_channel_device(pws_handle* h, int ndays, const double* d_seg_lat,
@@ -1163,14 +1451,11 @@ extern "C" int pws_run_channel_device(pws_handle* h, int ndays, const double* d_
   if (ndays <= 0) return 0;
   PWS_CUDA(h, cudaSetDevice(h->device));
   if (ensure_scratch(h, ndays)) return 1;
-  cudaEvent_t e0 = new_event(h), e1 = new_event(h);
-  cudaEventRecord(e0, h->s_compute);
-  if (enqueue_channel(h, ndays, nullptr, d_seg_lat, d_seg_out, false)) return 1;
-  cudaEventRecord(e1, h->s_compute);
-  cudaEvent_t z = new_event(h);
-  cudaEventRecord(z, h->s_compute);
-  h->ev_pairs_col.push_back({z, z});
-  h->ev_pairs_ch.push_back({e0, e1});
+  const int p = (int)(h->blocks_enqueued & 1);
+  h->blocks_enqueued++;
+  PWS_CUDA(h, cudaStreamWaitEvent(h->s_route, h->ev_block[p ^ 1], 0));
+  if (enqueue_channel(h, h->s_route, ndays, nullptr, d_seg_lat, d_seg_out, nullptr)) return 1;
+  PWS_CUDA(h, cudaEventRecord(h->ev_block[p], h->s_route));
   return 0;
 }
 
@@ -1215,15 +1500,22 @@ static int run_host_impl(pws_handle* h, int ndays, const int32_t* h_cal, const v
                          const void* h_tmax, const void* h_tmin, size_t esz, double* h_out_f64,
                          int32_t* h_out_i32, double* h_seg_out, int32_t* h_budget_viol) {
   if (!h->inited) PWS_FAIL(h, "pws_run_host before pws_init");
-  if (h->tiled_outputs) PWS_FAIL(h, "pws_run_host: tiled_outputs is a pws_run_device layout");
   if (ndays <= 0) return 0;
   PWS_CUDA(h, cudaSetDevice(h->device));
   clear_timing(h);
-  const int64_t n = h->nhru;
+  // n: units per variable and day in the result buffers (the padded tile rows
+  // with tiled_outputs, see pws_output_tile); nc: forcing columns
+  int64_t n = h->nhru;
+  if (h->tiled_outputs) {
+    const int H = column_hrus(h);
+    n = (h->nhru + H - 1) / H * H;
+  }
+  const int64_t nc = forcing_columns(h);
+  const int64_t cstride = round_up(nc, 32);  // forcing rows in the ring: 256-byte aligned
   // block length: option, else bounded by ~2 GiB per output ring slot
   int T = h->block_days;
   if (T <= 0) {
-    const double bytes_per_day = (double)n * (24.0 + 8.0 * h->n_f64 + 4.0 * h->n_i32) +
+    const double bytes_per_day = (double)nc * 24.0 + (double)n * (8.0 * h->n_f64 + 4.0 * h->n_i32) +
                                  (double)h->nseg * (8.0 * h->n_seg_sel + 24 * 8.0);
     T = (int)std::max(1.0, std::min(366.0, 2.0e9 / bytes_per_day));
   }
@@ -1242,7 +1534,7 @@ static int run_host_impl(pws_handle* h, int ndays, const int32_t* h_cal, const v
     h->ring_i32_elems = ci;
     h->ring_seg_elems = cs;
     for (int b = 0; b < 2; ++b) {
-      PWS_CUDA(h, cudaMalloc(&h->d_forc[b], (size_t)days * 3 * h->stride * sizeof(double)));
+      PWS_CUDA(h, cudaMalloc(&h->d_forc[b], ((size_t)days * 3 * cstride + 2) * sizeof(double)));
       PWS_CUDA(h, cudaMalloc(&h->d_of64[b], h->ring_f64_elems * sizeof(double)));
       PWS_CUDA(h, cudaMalloc(&h->d_oi32[b], h->ring_i32_elems * sizeof(int32_t)));
       PWS_CUDA(h, cudaMalloc(&h->d_oseg[b], h->ring_seg_elems * sizeof(double)));
@@ -1257,12 +1549,13 @@ static int run_host_impl(pws_handle* h, int ndays, const int32_t* h_cal, const v
     }
     h->forc32_days = 0;
     for (int b = 0; b < 2; ++b)
-      PWS_CUDA(h, cudaMalloc(&h->d_forc32[b], (size_t)h->ring_days * 3 * n * sizeof(float)));
+      PWS_CUDA(h, cudaMalloc(&h->d_forc32[b], (size_t)h->ring_days * 3 * nc * sizeof(float)));
     h->forc32_days = h->ring_days;
   }
   if (ensure_scratch(h, T)) return 1;
-  const bool want_f64 = h->n_f64 > 0 && h_out_f64, want_i32 = h->n_i32 > 0 && h_out_i32;
-  const bool want_seg = h->n_seg_sel > 0 && h->nseg > 0 && h_seg_out;
+  const bool want_f64 = h->n_f64_drain > 0 && h_out_f64, want_i32 = h->n_i32 > 0 && h_out_i32;
+  const bool want_seg = h->n_seg_drain > 0 && h->nseg > 0 && h_seg_out;
+  const int nfd = h->n_f64_drain, nsd = h->n_seg_drain;  // drained rows per day
   // Pageable caller buffers are staged through pinned slots, inputs and outputs
   // independently (a Model keeps its forcings in ordinary numpy arrays but can
   // hand in page-locked result buffers).
@@ -1277,7 +1570,7 @@ static int run_host_impl(pws_handle* h, int ndays, const int32_t* h_cal, const v
     }
     h->stage_days = 0;
     for (int b = 0; b < 2; ++b)
-      PWS_CUDA(h, cudaHostAlloc(&h->hs_in[b], (size_t)h->ring_days * 3 * n * sizeof(double), 0));
+      PWS_CUDA(h, cudaHostAlloc(&h->hs_in[b], (size_t)h->ring_days * 3 * nc * sizeof(double), 0));
     h->stage_days = h->ring_days;
   }
   if (stage_out && (h->stage_f64_elems < h->ring_f64_elems || h->stage_i32_elems < h->ring_i32_elems ||
@@ -1313,81 +1606,82 @@ static int run_host_impl(pws_handle* h, int ndays, const int32_t* h_cal, const v
     const int b = blk & 1, d0 = blk * T, nd = std::min(T, ndays - d0);
     PWS_CUDA(h, cudaEventSynchronize(h->ev_d2h[b]));
     if (want_f64)
-      par_memcpy(h_out_f64 + (size_t)d0 * h->n_f64 * n, h->hs_of[b],
-                 (size_t)nd * h->n_f64 * n * sizeof(double));
+      par_memcpy(h_out_f64 + (size_t)d0 * nfd * n, h->hs_of[b], (size_t)nd * nfd * n * sizeof(double));
     if (want_i32)
       par_memcpy(h_out_i32 + (size_t)d0 * h->n_i32 * n, h->hs_oi[b],
                  (size_t)nd * h->n_i32 * n * sizeof(int32_t));
     if (want_seg)
-      par_memcpy(h_seg_out + (size_t)d0 * h->n_seg_sel * h->nseg, h->hs_os[b],
-                 (size_t)nd * h->n_seg_sel * h->nseg * sizeof(double));
+      par_memcpy(h_seg_out + (size_t)d0 * nsd * h->nseg, h->hs_os[b],
+                 (size_t)nd * nsd * h->nseg * sizeof(double));
     return 0;
   };
+  int ring_slot[2] = {0, 0};  // scratch slot (enqueue_block) of the last block in ring slot b
   for (int blk = 0; blk < nblocks; ++blk) {
     const int b = blk & 1;
     const int d0 = blk * T;
     const int nd = std::min(T, ndays - d0);
-    const char* srcs[3] = {(const char*)h_prcp + (size_t)d0 * n * esz,
-                           (const char*)h_tmax + (size_t)d0 * n * esz,
-                           (const char*)h_tmin + (size_t)d0 * n * esz};
+    const char* srcs[3] = {(const char*)h_prcp + (size_t)d0 * nc * esz,
+                           (const char*)h_tmax + (size_t)d0 * nc * esz,
+                           (const char*)h_tmin + (size_t)d0 * nc * esz};
     // slot b: block blk-2 must have drained before its stage buffers are reused
     if (stage_out && blk >= 2 && drain_stage(blk - 2)) return 1;
     if (stage_in) {
       if (blk >= 2) PWS_CUDA(h, cudaEventSynchronize(h->ev_h2d[b]));  // hs_in[b] has been uploaded
       for (int k = 0; k < 3; ++k) {
-        char* const slot = (char*)h->hs_in[b] + (size_t)k * RT * n * esz;
-        par_memcpy(slot, srcs[k], (size_t)nd * n * esz);
+        char* const slot = (char*)h->hs_in[b] + (size_t)k * RT * nc * esz;
+        par_memcpy(slot, srcs[k], (size_t)nd * nc * esz);
         srcs[k] = slot;
       }
     }
-    // the ring slot is free once its previous outputs have drained
-    if (blk >= 2) PWS_CUDA(h, cudaStreamWaitEvent(h->s_h2d, h->ev_comp[b], 0));
+    // the ring slot is free once the block that last used it is complete
+    if (blk >= 2) PWS_CUDA(h, cudaStreamWaitEvent(h->s_h2d, h->ev_block[ring_slot[b]], 0));
     // forcing rows go into the ring with the padded row stride (16-byte aligned
     // rows for the TMA staging of k_hru_column)
-    const size_t S8 = (size_t)h->stride * sizeof(double), n8 = (size_t)n * sizeof(double);
+    const size_t S8 = (size_t)cstride * sizeof(double), n8 = (size_t)nc * sizeof(double);
     for (int k = 0; k < 3; ++k) {
       if (esz == 8)
-        PWS_CUDA(h, cudaMemcpy2DAsync(h->d_forc[b] + (size_t)k * RT * h->stride, S8, srcs[k], n8, n8,
+        PWS_CUDA(h, cudaMemcpy2DAsync(h->d_forc[b] + (size_t)k * RT * cstride, S8, srcs[k], n8, n8,
                                       (size_t)nd, cudaMemcpyHostToDevice, h->s_h2d));
       else  // float32 rows go up as they are (slot b was last read by block blk-2's widening)
-        PWS_CUDA(h, cudaMemcpyAsync(h->d_forc32[b] + (size_t)k * RT * n, srcs[k],
-                                    (size_t)nd * n * sizeof(float), cudaMemcpyHostToDevice, h->s_h2d));
+        PWS_CUDA(h, cudaMemcpyAsync(h->d_forc32[b] + (size_t)k * RT * nc, srcs[k],
+                                    (size_t)nd * nc * sizeof(float), cudaMemcpyHostToDevice, h->s_h2d));
     }
     PWS_CUDA(h, cudaEventRecord(h->ev_h2d[b], h->s_h2d));
     PWS_CUDA(h, cudaStreamWaitEvent(h->s_compute, h->ev_h2d[b], 0));
     if (blk >= 2) PWS_CUDA(h, cudaStreamWaitEvent(h->s_compute, h->ev_d2h[b], 0));
     if (esz == 4) {
-      k_widen_forcings<<<dim3((unsigned)((n + 255) / 256), (unsigned)nd, 3), 256, 0, h->s_compute>>>(
-          h->d_forc32[b], h->d_forc[b], n, h->stride, RT, RT);
+      // (the float64 ring slot was last read by block blk-2: wait for it here,
+      // enqueue_block only orders the scratch slot)
+      if (blk >= 2) PWS_CUDA(h, cudaStreamWaitEvent(h->s_compute, h->ev_block[ring_slot[b]], 0));
+      k_widen_forcings<<<dim3((unsigned)((nc + 255) / 256), (unsigned)nd, 3), 256, 0, h->s_compute>>>(
+          h->d_forc32[b], h->d_forc[b], nc, cstride, RT, RT);
       h->launches++;
       PWS_CUDA(h, cudaGetLastError());
     }
+    int p = 0;
     if (enqueue_block(h, nd, h_cal + (size_t)d0 * 4, h->d_forc[b],
-                      h->d_forc[b] + (size_t)RT * h->stride, h->d_forc[b] + (size_t)2 * RT * h->stride,
-                      h->stride, h->d_of64[b], h->d_oi32[b], h->d_oseg[b], h_budget_viol != nullptr))
+                      h->d_forc[b] + (size_t)RT * cstride, h->d_forc[b] + (size_t)2 * RT * cstride,
+                      cstride, h->d_of64[b], h->d_oi32[b], h->d_oseg[b],
+                      h_budget_viol ? h->hs_viol_run + (size_t)d0 * BUD_N : nullptr, &p))
       return 1;
-    if (h_budget_viol)
-      PWS_CUDA(h, cudaMemcpyAsync(h->hs_viol_run + (size_t)d0 * BUD_N, h->d_viol,
-                                  (size_t)nd * BUD_N * sizeof(int), cudaMemcpyDeviceToHost,
-                                  h->s_compute));
-    PWS_CUDA(h, cudaEventRecord(h->ev_comp[b], h->s_compute));
-    PWS_CUDA(h, cudaStreamWaitEvent(h->s_d2h, h->ev_comp[b], 0));
-    if (want_f64)
-      PWS_CUDA(h, cudaMemcpyAsync(stage_out ? h->hs_of[b] : h_out_f64 + (size_t)d0 * h->n_f64 * n,
-                                  h->d_of64[b], (size_t)nd * h->n_f64 * n * sizeof(double),
-                                  cudaMemcpyDeviceToHost, h->s_d2h));
+    ring_slot[b] = p;
+    PWS_CUDA(h, cudaStreamWaitEvent(h->s_d2h, h->ev_block[p], 0));
+    if (want_f64)  // the first nfd of the n_f64 rows of every day
+      PWS_CUDA(h, cudaMemcpy2DAsync(stage_out ? h->hs_of[b] : h_out_f64 + (size_t)d0 * nfd * n,
+                                    (size_t)nfd * n * sizeof(double), h->d_of64[b],
+                                    (size_t)h->n_f64 * n * sizeof(double), (size_t)nfd * n * sizeof(double),
+                                    (size_t)nd, cudaMemcpyDeviceToHost, h->s_d2h));
     if (want_i32)
       PWS_CUDA(h, cudaMemcpyAsync(stage_out ? h->hs_oi[b] : h_out_i32 + (size_t)d0 * h->n_i32 * n,
                                   h->d_oi32[b], (size_t)nd * h->n_i32 * n * sizeof(int32_t),
                                   cudaMemcpyDeviceToHost, h->s_d2h));
     if (want_seg)
-      PWS_CUDA(h, cudaMemcpyAsync(stage_out ? h->hs_os[b] : h_seg_out + (size_t)d0 * h->n_seg_sel * h->nseg,
-                                  h->d_oseg[b], (size_t)nd * h->n_seg_sel * h->nseg * sizeof(double),
-                                  cudaMemcpyDeviceToHost, h->s_d2h));
+      PWS_CUDA(h, cudaMemcpy2DAsync(stage_out ? h->hs_os[b] : h_seg_out + (size_t)d0 * nsd * h->nseg,
+                                    (size_t)nsd * h->nseg * sizeof(double), h->d_oseg[b],
+                                    (size_t)h->n_seg_sel * h->nseg * sizeof(double),
+                                    (size_t)nsd * h->nseg * sizeof(double), (size_t)nd,
+                                    cudaMemcpyDeviceToHost, h->s_d2h));
     PWS_CUDA(h, cudaEventRecord(h->ev_d2h[b], h->s_d2h));
-    // d_cal / d_viol / channel scratch are single-buffered: the next block's
-    // enqueue reuses them in stream order on s_compute, which is safe; h_cal is
-    // the caller's full-run array and stays valid.
   }
   if (stage_out)
     for (int blk = std::max(0, nblocks - 2); blk < nblocks; ++blk)
@@ -1431,8 +1725,11 @@ extern "C" int pws_run_host_inputs(pws_handle* h, int ndays, const int32_t* h_ca
                                    uint32_t process_mask, double* h_out_f64, int32_t* h_out_i32,
                                    double* h_seg_out, int32_t* h_budget_viol) {
   if (!h->inited) PWS_FAIL(h, "pws_run_host_inputs before pws_init");
+  if (h->n_f64 != h->n_f64_drain || h->n_seg_sel != h->n_seg_drain)
+    PWS_FAIL(h, "pws_run_host_inputs: device accumulations are not available for sub-chains");
   if (ndays <= 0) return 0;
   PWS_CUDA(h, cudaSetDevice(h->device));
+  PWS_CUDA(h, sync_all(h));
   for (int k = 0; k < n_in; ++k)
     if (in_idx[k] < 0 || in_idx[k] >= 3 + PWS_N_OV || h_in[k] == nullptr)
       PWS_FAIL(h, "pws_run_host_inputs: bad input index %d", in_idx[k]);
@@ -1472,19 +1769,21 @@ extern "C" int pws_run_host_inputs(pws_handle* h, int ndays, const int32_t* h_ca
       if (in_idx[k] < 3) forc[in_idx[k]] = dst;
       else a.ov[in_idx[k] - 3] = dst;
     }
-    cudaMemcpyAsync(h->d_cal, h_cal + (size_t)d0 * 4, (size_t)nd * sizeof(int4),
+    cudaMemcpyAsync(h->d_cal[0], h_cal + (size_t)d0 * 4, (size_t)nd * sizeof(int4),
                     cudaMemcpyHostToDevice, h->s_compute);
     if (h_budget_viol)
-      cudaMemsetAsync(h->d_viol, 0, (size_t)nd * BUD_N * sizeof(int), h->s_compute);
-    fill_column_args(h, a.c, nd, forc[0], forc[1], forc[2], n, d_of, d_oi, h_budget_viol != nullptr);
+      cudaMemsetAsync(h->d_viol[0], 0, (size_t)nd * BUD_N * sizeof(int), h->s_compute);
+    fill_column_args(h, a.c, nd, forc[0], forc[1], forc[2], n, d_of, d_oi, 0, h_budget_viol != nullptr);
+    a.c.fperiod = 0;  // every input of this path is [ndays][nhru]
     a.ovstride = n;
     a.proc_mask = process_mask;
     k_hru_column_ov<<<(unsigned)((n + 127) / 128), 128, 0, h->s_compute>>>(a);
     h->launches++;
     if (channel && rc == 0)
-      rc = enqueue_channel(h, nd, h->d_hru_lat, nullptr, d_os, h_budget_viol != nullptr);
+      rc = enqueue_channel(h, h->s_compute, nd, h->d_hru_lat[0], nullptr, d_os,
+                           h_budget_viol ? h->d_viol[0] : nullptr);
     if (h_budget_viol)
-      cudaMemcpyAsync(h_budget_viol + (size_t)d0 * BUD_N, h->d_viol, (size_t)nd * BUD_N * sizeof(int),
+      cudaMemcpyAsync(h_budget_viol + (size_t)d0 * BUD_N, h->d_viol[0], (size_t)nd * BUD_N * sizeof(int),
                       cudaMemcpyDeviceToHost, h->s_compute);
     if (h->n_f64 > 0 && h_out_f64)
       cudaMemcpyAsync(h_out_f64 + (size_t)d0 * h->n_f64 * n, d_of,
@@ -1502,6 +1801,8 @@ extern "C" int pws_run_host_inputs(pws_handle* h, int ndays, const int32_t* h_ca
     }
   }
   cleanup();
+  clear_timing(h);
+  h->last_channel_launches = 0;
   if (rc) return rc;
   // budget verdicts of processes that are not part of the model are not reported
   if (h_budget_viol)
@@ -1512,12 +1813,33 @@ extern "C" int pws_run_host_inputs(pws_handle* h, int ndays, const int32_t* h_ca
 }
 
 // --------------------------------------------------------------- state
+// PRMSChannel's prognostic state (prms_channel.py:384-386, 456-585: `outflow_ts`
+// and yesterday's `seg_inflow`, carried from day to day), [nsegment] in the
+// caller's segment order; the device keeps them in routing order.
+static const char* const kSegStateNames[] = {"outflow_ts", "seg_inflow"};
+extern "C" int pws_n_seg_state(void) { return 2; }
+extern "C" const char* pws_seg_state_name(int i) { return (i >= 0 && i < 2) ? kSegStateNames[i] : nullptr; }
+
+static double* seg_state_ptr(pws_handle* h, const char* name) {
+  if (h->nseg == 0) return nullptr;
+  if (!strcmp(name, "outflow_ts")) return h->d_outflow_ts;
+  if (!strcmp(name, "seg_inflow")) return h->d_seg_inflow;
+  return nullptr;
+}
+
 extern "C" int pws_get_state(pws_handle* h, const char* name, double* out) {
   if (!h->inited) PWS_FAIL(h, "pws_get_state before pws_init");
+  PWS_CUDA(h, cudaSetDevice(h->device));
+  if (double* d = seg_state_ptr(h, name)) {
+    PWS_CUDA(h, sync_all(h));
+    std::vector<double> tmp((size_t)h->nseg);
+    PWS_CUDA(h, cudaMemcpy(tmp.data(), d, (size_t)h->nseg * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int64_t p = 0; p < h->nseg; ++p) out[h->h_orig[(size_t)p]] = tmp[(size_t)p];
+    return 0;
+  }
   const int k = find(names().states, name);
   if (k < 0) PWS_FAIL(h, "pws_get_state: unknown state '%s'", name);
-  PWS_CUDA(h, cudaSetDevice(h->device));
-  PWS_CUDA(h, cudaStreamSynchronize(h->s_compute));
+  PWS_CUDA(h, sync_all(h));
   PWS_CUDA(h, cudaMemcpy(out, h->d_state + (size_t)k * h->stride, (size_t)h->nhru * sizeof(double),
                          cudaMemcpyDeviceToHost));
   return 0;
@@ -1525,10 +1847,17 @@ extern "C" int pws_get_state(pws_handle* h, const char* name, double* out) {
 
 extern "C" int pws_set_state(pws_handle* h, const char* name, const double* in) {
   if (!h->inited) PWS_FAIL(h, "pws_set_state before pws_init");
+  PWS_CUDA(h, cudaSetDevice(h->device));
+  if (double* d = seg_state_ptr(h, name)) {
+    PWS_CUDA(h, sync_all(h));
+    std::vector<double> tmp((size_t)h->nseg);
+    for (int64_t p = 0; p < h->nseg; ++p) tmp[(size_t)p] = in[h->h_orig[(size_t)p]];
+    PWS_CUDA(h, cudaMemcpy(d, tmp.data(), (size_t)h->nseg * sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+  }
   const int k = find(names().states, name);
   if (k < 0) PWS_FAIL(h, "pws_set_state: unknown state '%s'", name);
-  PWS_CUDA(h, cudaSetDevice(h->device));
-  PWS_CUDA(h, cudaStreamSynchronize(h->s_compute));
+  PWS_CUDA(h, sync_all(h));
   PWS_CUDA(h, cudaMemcpy(h->d_state + (size_t)k * h->stride, in, (size_t)h->nhru * sizeof(double),
                          cudaMemcpyHostToDevice));
   return 0;
@@ -1579,6 +1908,8 @@ extern "C" int pws_output_tile(pws_handle* h, int* tile_units, int64_t* padded_u
 
 extern "C" int pws_timer_mark(pws_handle* h, int which) {
   PWS_CUDA(h, cudaSetDevice(h->device));
+  // blocks complete on s_route (and, without segments, on the lanes): join them
+  for (int b = 0; b < 2; ++b) PWS_CUDA(h, cudaStreamWaitEvent(h->s_compute, h->ev_block[b], 0));
   PWS_CUDA(h, cudaEventRecord(which == 0 ? h->ev_col0 : h->ev_col1, h->s_compute));
   return 0;
 }
@@ -1592,14 +1923,21 @@ extern "C" int pws_timer_elapsed_ms(pws_handle* h, double* ms) {
 }
 
 extern "C" int pws_last_launches(pws_handle* h, int* n_column, int* n_channel) {
-  if (n_column) *n_column = h->n_col_launch;
+  if (n_column) *n_column = h->n_col_kernels;
   if (n_channel) *n_channel = h->n_ch_launch;
+  return 0;
+}
+
+extern "C" int pws_last_blocks(pws_handle* h, int* n_blocks, int* lanes) {
+  if (n_blocks) *n_blocks = h->n_col_launch;
+  if (lanes) *lanes = h->n_col_launch > 0 ? h->n_col_kernels / h->n_col_launch : 0;
   return 0;
 }
 
 extern "C" int pws_reset_state(pws_handle* h) {
   if (!h->inited) PWS_FAIL(h, "pws_reset_state before pws_init");
   PWS_CUDA(h, cudaSetDevice(h->device));
+  PWS_CUDA(h, sync_all(h));
   k_hru_init<<<(unsigned)((h->nhru + 127) / 128), 128, 0, h->s_compute>>>(
       h->P, h->D, h->d_state, h->start_month, h->start_doy, h->adjust_parameters, h->d_err);
   h->launches++;
@@ -1609,6 +1947,10 @@ extern "C" int pws_reset_state(pws_handle* h) {
                                 (size_t)h->nseg * sizeof(double), cudaMemcpyHostToDevice,
                                 h->s_compute));
   }
+  if (h->d_acc_hru)
+    PWS_CUDA(h, cudaMemsetAsync(h->d_acc_hru, 0, h->acc_hru.size() * h->stride * sizeof(double), h->s_compute));
+  if (h->d_acc_seg)
+    PWS_CUDA(h, cudaMemsetAsync(h->d_acc_seg, 0, h->acc_seg.size() * h->sstride * sizeof(double), h->s_compute));
   PWS_CUDA(h, cudaGetLastError());
   PWS_CUDA(h, cudaStreamSynchronize(h->s_compute));
   return 0;

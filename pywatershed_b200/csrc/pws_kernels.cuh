@@ -134,7 +134,14 @@ struct ColumnArgs {
   const double* tmax;
   const double* tmin;
   int64_t fstride;
+  // > 0: the forcing arrays are [ndays][fperiod] and HRU i reads column i mod
+  // fperiod (a parameter ensemble over one base domain, member-major: every
+  // member sees the same weather, examples/05_parameter_ensemble.ipynb)
+  int64_t fperiod;
   int use_tma;              // forcing rows are 16-byte aligned: stage them with cp.async.bulk
+  // this launch covers CTA tiles [tile0, tile0 + gridDim.x) of the domain's
+  // ntiles (a launch per lane, see enqueue_block in pws_b200.cu)
+  int tile0, ntiles;
   const int4* cal;          // [ndays] (doy, dowy, month, dom), device
   int ndays;
   double* out_f64;          // [ndays][n_f64][ostride]
@@ -385,7 +392,8 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
   const int tid = threadIdx.x;
   const bool upper = tid < H;  // warpgroup-uniform
   const int r = upper ? tid : tid - H;
-  const int64_t i = (int64_t)blockIdx.x * H + r;
+  const int64_t tile = (int64_t)blockIdx.x + a.tile0;
+  const int64_t i = tile * H + r;
   const bool live = i < a.P.nhru;
   const int64_t ii = live ? i : a.P.nhru - 1;  // dead lanes shadow the last HRU, never store
   const int64_t S = a.P.stride;
@@ -409,12 +417,12 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
   GpuSink<kMode, H> out{a, nullptr, nullptr, nullptr, (unsigned)(a.ostride * 8),
                      (unsigned)(a.ostride * 4), 0u, 0, live, upper ? BAR_UPPER : BAR_LOWER};
   // bytes from one day to the next, and this thread's element of the first day
-  const int64_t day_units = kMode == SINK_TILED ? (int64_t)gridDim.x * H : a.ostride;
+  const int64_t day_units = kMode == SINK_TILED ? (int64_t)a.ntiles * H : a.ostride;
   const int64_t day_f64 = (int64_t)a.n_f64 * day_units * 8;
   const int64_t day_i32 = (int64_t)a.n_i32 * day_units * 4;
   if constexpr (kMode == SINK_TILED) {
-    out.pf = reinterpret_cast<char*>(a.out_f64 + (int64_t)blockIdx.x * a.n_f64 * H + r);
-    out.pi = reinterpret_cast<char*>(a.out_i32 + (int64_t)blockIdx.x * a.n_i32 * H + r);
+    out.pf = reinterpret_cast<char*>(a.out_f64 + tile * a.n_f64 * H + r);
+    out.pi = reinterpret_cast<char*>(a.out_i32 + tile * a.n_i32 * H + r);
   } else {
     out.pf = reinterpret_cast<char*>(a.out_f64 + ii);
     out.pi = reinterpret_cast<char*>(a.out_i32 + ii);
@@ -456,7 +464,7 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
       // monthly rows straight from global memory: row (month - 1) * S, element
       // hru0 + r (the slabs are padded so lanes past the last HRU stay inside)
       Q.stride = S;
-#define X(n) Q.n = a.P.n + (int64_t)blockIdx.x * H;
+#define X(n) Q.n = a.P.n + tile * H;
       PWS_UPPER_MON_F64(X)
       PWS_UPPER_MON_I32(X)
 #undef X
@@ -490,21 +498,35 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
     // mbarrier; otherwise every thread prefetches its own values
     // into registers.
     const bool tma = a.use_tma != 0;
-    const int64_t hru0 = (int64_t)blockIdx.x * H;
+    const int64_t hru0 = tile * H;
     // an odd tail is copied with the padding element behind it (see fill_column_args)
     const int64_t row_n = (a.P.nhru - hru0) < H ? (a.P.nhru - hru0) : H;
     const uint32_t row_bytes = (uint32_t)(((row_n + 1) & ~(int64_t)1) * 8);
+    // forcing column of the CTA's first HRU, and of this thread's HRU; with a
+    // forcing period the CTA's row may wrap around the end of the period once
+    // (fill_column_args only allows TMA for an even period >= H)
+    const int64_t fcol0 = a.fperiod > 0 ? hru0 % a.fperiod : hru0;
+    const int64_t fcol = a.fperiod > 0 ? ii % a.fperiod : ii;
+    const int64_t n_head = (a.fperiod > 0 && fcol0 + row_n > a.fperiod) ? a.fperiod - fcol0 : row_n;
+    auto tma_forcing_row = [&](uint32_t dst, const double* row, uint32_t bar) {
+      if (n_head == row_n) {
+        tma_bulk_g2s(dst, row + fcol0, row_bytes, bar);
+      } else {  // both pieces are even: period, fcol0 and row_n are
+        tma_bulk_g2s(dst, row + fcol0, (uint32_t)(n_head * 8), bar);
+        tma_bulk_g2s(dst + (uint32_t)(n_head * 8), row, row_bytes - (uint32_t)(n_head * 8), bar);
+      }
+    };
     auto tma_issue = [&](int d) {  // one thread
       const uint32_t bar = mbar0;
       const uint32_t dst = smem_u32(sF);
       const int doy = a.cal[d].x;
-      const int64_t fo = (int64_t)d * a.fstride + hru0;
+      const int64_t fo = (int64_t)d * a.fstride;
       const int64_t so = (int64_t)(doy - 1) * S + hru0;
       mbar_expect_tx(bar, kForcRows * row_bytes + 16u);
       tma_bulk_g2s(smem_u32(sCal + 4 * (d & 1)), a.cal + d, 16u, bar);
-      tma_bulk_g2s(dst + 0 * H * 8, a.prcp + fo, row_bytes, bar);
-      tma_bulk_g2s(dst + 1 * H * 8, a.tmax + fo, row_bytes, bar);
-      tma_bulk_g2s(dst + 2 * H * 8, a.tmin + fo, row_bytes, bar);
+      tma_forcing_row(dst + 0 * H * 8, a.prcp + fo, bar);
+      tma_forcing_row(dst + 1 * H * 8, a.tmax + fo, bar);
+      tma_forcing_row(dst + 2 * H * 8, a.tmin + fo, bar);
       tma_bulk_g2s(dst + 3 * H * 8, a.P.soltab_potsw + so, row_bytes, bar);
       tma_bulk_g2s(dst + 4 * H * 8, a.P.soltab_horad_potsw + so, row_bytes, bar);
     };
@@ -521,9 +543,9 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
     } else {
       const int4 c = a.cal[0];
       nxt.doy = c.x; nxt.dowy = c.y; nxt.month = c.z; nxt.dom = c.w;
-      nxt.prcp = __ldcs(a.prcp + ii);
-      nxt.tmax = __ldcs(a.tmax + ii);
-      nxt.tmin = __ldcs(a.tmin + ii);
+      nxt.prcp = __ldcs(a.prcp + fcol);
+      nxt.tmax = __ldcs(a.tmax + fcol);
+      nxt.tmin = __ldcs(a.tmin + fcol);
       nxt.potsw = __ldg(a.P.soltab_potsw + (int64_t)(c.x - 1) * S + ii);
       nxt.horad = __ldg(a.P.soltab_horad_potsw + (int64_t)(c.x - 1) * S + ii);
     }
@@ -548,7 +570,7 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
         in.cal = reinterpret_cast<const int*>(a.cal + d);
         if (d + 1 < a.ndays) {
           const int4 c = a.cal[d + 1];
-          const int64_t fo = (int64_t)(d + 1) * a.fstride + ii;
+          const int64_t fo = (int64_t)(d + 1) * a.fstride + fcol;
           nxt.doy = c.x; nxt.dowy = c.y; nxt.month = c.z; nxt.dom = c.w;
           nxt.prcp = __ldcs(a.prcp + fo);
           nxt.tmax = __ldcs(a.tmax + fo);
@@ -752,7 +774,7 @@ k_hru_column_ov(const __grid_constant__ OvArgs a) {
     const int4 c = a.c.cal[d];
     DayIn in;
     in.doy = c.x; in.dowy = c.y; in.month = c.z; in.dom = c.w;
-    const int64_t fo = (int64_t)d * a.c.fstride + ii;
+    const int64_t fo = (int64_t)d * a.c.fstride + (a.c.fperiod > 0 ? ii % a.c.fperiod : ii);
     in.prcp = a.c.prcp[fo];
     in.tmax = a.c.tmax[fo];
     in.tmin = a.c.tmin[fo];
@@ -1112,6 +1134,25 @@ k_widen_forcings(const float* __restrict__ src, double* __restrict__ dst, int64_
   if (i >= n) return;
   const int64_t d = blockIdx.y, k = blockIdx.z;
   dst[(k * dst_var_rows + d) * stride + i] = (double)__ldg(src + (k * src_var_rows + d) * n + i);
+}
+
+// Budget accumulations (base/budget.py:262-269): `acc += value` for every day of
+// a block, in day order, per unit; grid (ceil(n / 256), variables).  buf is the
+// block's result buffer [ndays][rows][units]; slot = the variable's row.
+struct AccSlots {
+  static constexpr int kMax = 64;
+  short s[kMax];
+};
+__global__ void __launch_bounds__(256)
+k_accumulate(const AccSlots slots, const double* __restrict__ buf, int64_t day_stride, int64_t units,
+             int ndays, int64_t n, double* __restrict__ acc, int64_t acc_stride) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const int k = blockIdx.y;
+  const double* p = buf + (int64_t)slots.s[k] * units + i;
+  double a = acc[(int64_t)k * acc_stride + i];
+  for (int d = 0; d < ndays; ++d) a += __ldcs(p + (int64_t)d * day_stride);
+  acc[(int64_t)k * acc_stride + i] = a;
 }
 
 // Global-basis channel budget (prms_channel.py:115,165-174; budget.py:388-416):

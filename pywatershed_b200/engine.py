@@ -116,6 +116,38 @@ _FILL_I32 = {"cov_type": 1, "hru_type": 1, "hru_deplcrv": 1, "soil_type": 1, "tr
              "transp_end": 13, "melt_force": 140, "melt_look": 90}
 
 
+class TiledBlock(dict):
+    """Results of a run in the tiled layout ([day][tile][variable][tile_units],
+    include/pws_b200.h: pws_output_tile): a dict that un-tiles an HRU variable
+    into a [ndays, nhru] array the first time it is looked up.  Segment
+    variables are ordinary entries."""
+
+    def __init__(self, eng, of, oi):
+        super().__init__()
+        self._eng, self._of, self._oi = eng, of, oi
+        self._f64 = {v: k for k, v in enumerate(eng.sel_f64)}
+        self._i32 = {v: k for k, v in enumerate(eng.sel_i32)}
+
+    def __missing__(self, var):
+        if var in self._f64:
+            a = np.ascontiguousarray(untile(self._of, self._f64[var], self._eng.nhru))
+        elif var in self._i32:
+            a = np.ascontiguousarray(untile(self._oi, self._i32[var], self._eng.nhru))
+            if self._eng.reg.dtype(var) is np.bool_:
+                a = a.astype(np.bool_)
+        else:
+            raise KeyError(var)
+        self[var] = a
+        return a
+
+    def __contains__(self, var):
+        return dict.__contains__(self, var) or var in self._f64 or var in self._i32
+
+    def keys(self):
+        return list(self._f64) + list(self._i32) + [k for k in dict.keys(self)
+                                                     if k not in self._f64 and k not in self._i32]
+
+
 class Engine:
     """A PRMS/NHM domain on one GPU.
 
@@ -125,7 +157,12 @@ class Engine:
 
     def __init__(self, params: dict, start, device: int = 0, dprst_flag: bool = True,
                  adjust_parameters: bool = True, channel: bool = True,
-                 channel_chunk: int | None = None, fill_missing: bool = False):
+                 channel_chunk: int | None = None, fill_missing: bool = False,
+                 forcing_period: int | None = None, soltab_device: bool | None = None,
+                 lanes: int | None = None):
+        """`forcing_period` = P: a member-major parameter ensemble over a base
+        domain of P HRUs (nhru = nmember * P); forcings are then [ndays, P] and
+        shared by the members."""
         self.L = _lib.lib()
         self.reg = Registry.get()
         if fill_missing:
@@ -167,6 +204,15 @@ class Engine:
         self._opt("adjust_parameters", 1.0 if adjust_parameters else 0.0)
         if channel_chunk is not None:
             self._opt("channel_chunk", channel_chunk)
+        if soltab_device is not None:
+            self._opt("soltab_device", 1.0 if soltab_device else 0.0)
+        if lanes is not None:
+            self._opt("lanes", lanes)
+        self.ncol = self.nhru  # forcing columns
+        if forcing_period:
+            self._opt("forcing_period", int(forcing_period))
+            self.ncol = int(forcing_period)
+        self.tiled = False
         self._check(self.L.pws_init(self.h))
         self.day = 0
         self.sel_hru: list[str] = []
@@ -239,8 +285,15 @@ class Engine:
         return ms.value
 
     def last_launches(self):
+        """(column kernel launches, channel kernel launches) of the last run."""
         a, b = C.c_int(), C.c_int()
         self.L.pws_last_launches(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def last_blocks(self):
+        """(blocks of days, column launches per block) of the last run."""
+        a, b = C.c_int(), C.c_int()
+        self.L.pws_last_blocks(self.h, C.byref(a), C.byref(b))
         return a.value, b.value
 
     def close(self):
@@ -266,6 +319,30 @@ class Engine:
         self.sel_f64 = [v for v in hru_vars if self.reg.dtype(v) is np.float64]
         self.sel_i32 = [v for v in hru_vars if self.reg.dtype(v) is not np.float64]
 
+    def select_accumulations(self, hru_vars=(), seg_vars=()):
+        """Budget terms summed per unit on the device over every day computed
+        from now on (base/budget.py:262-269); they need not be selected outputs."""
+        hru_vars, seg_vars = list(hru_vars), list(seg_vars) if self.nseg else []
+        hi = np.array([self.reg.hru_index[v] for v in hru_vars], dtype=np.int32)
+        si = np.array([self.reg.seg_index[v] for v in seg_vars], dtype=np.int32)
+        self._check(self.L.pws_select_accumulations(self.h, len(hi), hi.ctypes.data, len(si),
+                                                    si.ctypes.data))
+        self.acc_hru, self.acc_seg = hru_vars, seg_vars
+
+    def accumulations(self) -> dict:
+        """var -> per-unit sum over the days computed since the last reset."""
+        hv, sv = getattr(self, "acc_hru", []), getattr(self, "acc_seg", [])
+        ah = np.empty((len(hv), self.nhru))
+        as_ = np.empty((len(sv), self.nseg))
+        self._check(self.L.pws_get_accumulations(self.h, ah.ctypes.data if hv else None,
+                                                 as_.ctypes.data if sv else None))
+        out = {v: ah[k] for k, v in enumerate(hv)}
+        out.update({v: as_[k] for k, v in enumerate(sv)})
+        return out
+
+    def set_accumulate(self, on: bool):
+        self._opt("accumulate", 1.0 if on else 0.0)
+
     def soltab(self):
         out = {}
         for k, name in enumerate(("soltab_potsw", "soltab_horad_potsw", "soltab_sunhrs")):
@@ -286,7 +363,8 @@ class Engine:
         torch) so the drain needs no staging copy; with `reuse_buffers` the
         result arrays of the previous call with the same shapes are written
         again (the caller must be done with them), which avoids first-touch
-        page faults on every block of a long run.
+        page faults on every block of a long run; a number > 1 names another
+        set of buffers, so a caller can alternate between two.
 
         Forcings that are all float32 (the storage type of the reference's
         forcing netCDF files) are uploaded as they are -- half the PCIe
@@ -298,14 +376,21 @@ class Engine:
         tmax = np.ascontiguousarray(tmax, dtype=ft)
         tmin = np.ascontiguousarray(tmin, dtype=ft)
         nd = prcp.shape[0]
-        if not (prcp.shape == tmax.shape == tmin.shape == (nd, self.nhru)):
-            raise ValueError("forcings must be [ndays, nhru]")
+        if not (prcp.shape == tmax.shape == tmin.shape == (nd, self.ncol)):
+            raise ValueError(f"forcings must be [ndays, {self.ncol}]")
         cal = calendar(self.start + self.day, nd)
-        shapes = ((nd, len(self.sel_f64), self.nhru), (nd, len(self.sel_i32), self.nhru),
-                  (nd, len(self.sel_seg), self.nseg))
+        if self.tiled:
+            # [day][tile][variable][tile_units], the last tile padded (pws_output_tile)
+            H, padded = self.output_tile()
+            shapes = ((nd, padded // H, len(self.sel_f64), H), (nd, padded // H, len(self.sel_i32), H),
+                      (nd, len(self.sel_seg), self.nseg))
+        else:
+            shapes = ((nd, len(self.sel_f64), self.nhru), (nd, len(self.sel_i32), self.nhru),
+                      (nd, len(self.sel_seg), self.nseg))
         key = (shapes, bool(pinned_outputs))
-        cache = getattr(self, "_out_cache", None)
-        if reuse_buffers and cache is not None and cache[0] == key:
+        caches = self.__dict__.setdefault("_out_caches", {})
+        cache = caches.get(int(reuse_buffers)) if reuse_buffers else None
+        if cache is not None and cache[0] == key:
             of, oi, os_ = cache[1]
         else:
             if pinned_outputs:
@@ -320,7 +405,8 @@ class Engine:
                 of = np.empty(shapes[0])
                 oi = np.empty(shapes[1], dtype=np.int32)
                 os_ = np.empty(shapes[2])
-            self._out_cache = (key, (of, oi, os_)) if reuse_buffers else None
+            if reuse_buffers:
+                caches[int(reuse_buffers)] = (key, (of, oi, os_))
         viol = np.zeros((nd, 6), dtype=np.int32) if budgets else None
         run = self.L.pws_run_host_f32 if f32 else self.L.pws_run_host
         self._check(run(
@@ -328,10 +414,13 @@ class Engine:
             of.ctypes.data, oi.ctypes.data, os_.ctypes.data,
             viol.ctypes.data if budgets else None))
         self.day += nd
-        res = {v: of[:, k, :] for k, v in enumerate(self.sel_f64)}
-        for k, v in enumerate(self.sel_i32):
-            a = oi[:, k, :]
-            res[v] = a.astype(np.bool_) if self.reg.dtype(v) is np.bool_ else a
+        if self.tiled:
+            res = TiledBlock(self, of, oi)
+        else:
+            res = {v: of[:, k, :] for k, v in enumerate(self.sel_f64)}
+            for k, v in enumerate(self.sel_i32):
+                a = oi[:, k, :]
+                res[v] = a.astype(np.bool_) if self.reg.dtype(v) is np.bool_ else a
         res.update({v: os_[:, k, :] for k, v in enumerate(self.sel_seg)})
         return res, viol
 
@@ -418,15 +507,33 @@ class Engine:
         self._check(self.L.pws_sync(self.h))
 
     # ---- state / instrumentation
+    @property
+    def seg_states(self):
+        L = self.L
+        return [L.pws_seg_state_name(i).decode() for i in range(L.pws_n_seg_state())] if self.nseg else []
+
     def get_state(self, name):
-        a = np.empty(self.nhru)
+        a = np.empty(self.nseg if name in self.seg_states else self.nhru)
         self._check(self.L.pws_get_state(self.h, name.encode(), a.ctypes.data))
         return a
 
     def set_state(self, name, val):
         a = np.ascontiguousarray(val, dtype=np.float64)
-        assert a.shape == (self.nhru,)
+        assert a.shape == ((self.nseg if name in self.seg_states else self.nhru),)
         self._check(self.L.pws_set_state(self.h, name.encode(), a.ctypes.data))
+
+    def save_state(self) -> dict:
+        """Every prognostic value of the domain (the union of the processes'
+        get_restart_variables(), prms_snow.py:269-293, plus PRMSChannel's
+        outflow_ts / seg_inflow) and the day it belongs to: a restart point."""
+        st = {name: self.get_state(name) for name in self.reg.states + self.seg_states}
+        st["_day"] = np.array(self.day)
+        return st
+
+    def load_state(self, st: dict):
+        for name in self.reg.states + self.seg_states:
+            self.set_state(name, st[name])
+        self.day = int(st["_day"])
 
     def timing(self):
         a, b = C.c_double(), C.c_double()

@@ -72,6 +72,7 @@ class Model:
         self._block_n = 0
         self._block_viol = None
         self._calculated_step = -1
+        self._init_runtime()
         # True when a single process is stepped by its caller, who advances
         # the Control (autotest/test_prms_snow.py:122-132)
         self._control_is_external = False
@@ -80,6 +81,15 @@ class Model:
         self.block_days = self.control.options.get("block_days") or None
         if write_control:
             self._write_control(write_control)
+
+    def _init_runtime(self):
+        self._engine_kwargs = None
+        self._pending_writes = []      # futures of the netCDF writer thread (<= 2 blocks in flight)
+        self._writer = None
+        self._buf_slot = 0             # result buffers alternate so a block can be written while the next computes
+        self._device_acc_on = None     # what the engine's "accumulate" option was last set to
+        self._device_acc_cache = (None, {})
+        self._days_on_device = 0       # days computed so far (rows an all-time array may be missing)
 
     # ---------------------------------------------------------------- spec
     def _parse_spec(self, spec):
@@ -165,6 +175,7 @@ class Model:
         self._block_t0 = self._block_n = 0
         self._block_viol = None
         self._calculated_step = -1
+        self._init_runtime()
         self._control_is_external = True
         # days per host-side block (what one engine call brings back); None = sized
         # from the domain when the engine exists (about 2 GB of results, <= 366 days)
@@ -263,42 +274,50 @@ class Model:
         if self._engine is not None:
             return
         pd = self._param_dict
-        dprst = self.processes[self.process_order[-1]]._dprst_flag
-        for n in self.process_order:
-            f = getattr(self.processes[n], "_dprst_flag", None)
-            if f is not None:
-                dprst = f
-        if dprst is None:
-            dprst = True
-        flags = {bool(getattr(self.processes[n], "_dprst_flag")) for n in self.process_order
+        # dprst_flag lives on Runoff / Soilzone / Groundwater only (base/process.py:339-358:
+        # an option exists where the constructor names it); their NoDprst variants say False
+        flags = {bool(self.processes[n]._dprst_flag) for n in self.process_order
                  if getattr(self.processes[n], "_dprst_flag", None) is not None}
         if len(flags) > 1:
             raise ValueError("dprst_flag must be the same for every process of the model "
                              "(mixing PRMSRunoff with PRMSSoilzoneNoDprst, ...)")
-        adj = True
+        dprst = flags.pop() if flags else True
+        # adjust_parameters: Soilzone's decides whether the device edits the soil
+        # parameters / initial storages (prms_soilzone.py:361-463); Channel's only warns
+        # or raises (its slope edit comes after the velocity, prms_channel.py:234-260).
+        # The checks themselves run here, on the parameters, with the reference's messages.
+        sz_mode, ch_mode = "no", "no"
         for n in self.process_order:
-            if P.base_name(n) in ("PRMSSoilzone", "PRMSChannel") and \
-                    self.processes[n]._adjust_parameters == "no":
-                adj = False
+            if P.base_name(n) == "PRMSSoilzone":
+                sz_mode = self.processes[n]._adjust_parameters or "warn"
+            if n == "PRMSChannel":
+                ch_mode = self.processes[n]._adjust_parameters or "warn"
+        P.check_adjusted_parameters(pd, sz_mode if any(
+            P.base_name(n) == "PRMSSoilzone" for n in self.process_order) else None,
+            ch_mode if "PRMSChannel" in self.process_order else None, dprst)
+        adj = sz_mode != "no"
         start = self.control.start_time
         dev = int(self.control.options.get("device", 0) or 0)
         if self._mode == "channel":
             # the HRU column is not run; its tables get stand-in values
-            self._engine = Engine(pd, start, device=dev, channel=True, fill_missing=True)
+            kw = dict(device=dev, channel=True, fill_missing=True)
+            self._engine = Engine(pd, start, **kw)
             nh = self._engine.nhru
             self._forcings = {k: self._load_input(k, nh) for k in
                               ("sroff_vol", "ssres_flow_vol", "gwres_flow_vol")}
         elif self._mode == "sub":
-            self._engine = Engine(pd, start, device=dev, channel="PRMSChannel" in self.processes,
-                                  adjust_parameters=adj, fill_missing=True, dprst_flag=bool(dprst))
+            kw = dict(device=dev, channel="PRMSChannel" in self.processes, adjust_parameters=adj,
+                      fill_missing=True, dprst_flag=bool(dprst))
+            self._engine = Engine(pd, start, **kw)
             nh = self._engine.nhru
             self._forcings = {k: self._load_input(k, nh) for k in self._external_inputs()}
         else:
-            self._engine = Engine(pd, start, device=dev, channel=self._mode == "chain+channel",
-                                  adjust_parameters=adj, dprst_flag=bool(dprst),
-                                  fill_missing=not dprst)
+            kw = dict(device=dev, channel=self._mode == "chain+channel", adjust_parameters=adj,
+                      dprst_flag=bool(dprst), fill_missing=not dprst)
+            self._engine = Engine(pd, start, **kw)
             nh = self._engine.nhru
             self._forcings = {k: self._load_input(k, nh, keep_f32=True) for k in FORCINGS}
+        self._engine_kwargs = kw
         reg = self._engine.reg
         hv = list(reg.hru_vars) if self._mode != "channel" else [
             "channel_sroff_vol", "channel_ssres_flow_vol", "channel_gwres_flow_vol"]
@@ -311,39 +330,113 @@ class Model:
             sv = sv if "PRMSChannel" in self.processes else []
         self._full_selection = (list(hv), list(sv))
         self._selection_is_full = True
+        self._block_days_user = self.block_days
         if self.block_days is None:
-            per_day = 8.0 * (len(hv) * self._engine.nhru + len(sv) * self._engine.nseg) + 1.0
-            self.block_days = int(max(8, min(366, 2.0e9 / per_day)))
+            self.block_days = self._days_for(hv, sv, 366)
         self.block_days = int(self.block_days)
         if self._mode != "channel":
             self._engine.select_outputs(hv, sv)
-            if "PRMSSolarGeometry" in self.processes:
-                st = self._engine.soltab()
-                sg = self.processes["PRMSSolarGeometry"]
-                for k, v in st.items():
-                    sg[k].data[:] = v
         else:
             self._engine.select_outputs([], sv)
+        # all-time variables are materialised when somebody looks (processes.TimeseriesArray)
+        if "PRMSSolarGeometry" in self.processes and self._mode != "channel":
+            for ts in self.processes["PRMSSolarGeometry"]._vars.values():
+                ts._loader = self._load_soltab
+                ts.mark_stale()
+        if "PRMSAtmosphere" in self.processes:
+            for ts in self.processes["PRMSAtmosphere"]._vars.values():
+                if self._mode in ("chain", "chain+channel"):
+                    ts._loader = self._replay_all_time
+                else:  # a partial chain: every block is complete, the rows are kept as they come
+                    ts.data
+        # budget terms are summed on the device during run() (pws_select_accumulations)
+        if self._mode in ("chain", "chain+channel"):
+            th, tsg = self._budget_terms()
+            self._engine.select_accumulations(th, tsg)
+            self._set_device_acc(False)
+
+    def _days_for(self, hv, sv, cap):
+        """Days per host-side block so that one block of these variables is ~2 GB."""
+        per_day = 8.0 * (len(hv) * self._engine.nhru + len(sv) * self._engine.nseg) + 1.0
+        return int(max(8, min(cap, 2.0e9 / per_day)))
+
+    def _budget_terms(self):
+        """(HRU variables, segment variables) that are a term of some budget of the model."""
+        reg = self._engine.reg
+        th, tsg = [], []
+        for proc in self.processes.values():
+            b = getattr(proc, "budget", None)
+            if b is None:
+                continue
+            for comp in b.components:
+                for v in b.terms[comp]:
+                    if v in reg.hru_index and v not in th:
+                        th.append(v)
+                    elif v in reg.seg_index and v not in tsg:
+                        tsg.append(v)
+        return th, tsg
+
+    def _set_device_acc(self, on: bool):
+        if self._device_acc_on is not on and self._mode in ("chain", "chain+channel"):
+            self._engine.set_accumulate(on)
+            self._device_acc_on = on
+
+    def _device_accumulations(self) -> dict:
+        """Budget-term sums held on the device (days computed by run())."""
+        eng = self._engine
+        if eng is None or not getattr(eng, "acc_hru", None):
+            return {}
+        if self._device_acc_cache[0] != eng.day:
+            self._device_acc_cache = (eng.day, eng.accumulations())
+        return self._device_acc_cache[1]
+
+    def _load_soltab(self, ts):
+        sg = self.processes["PRMSSolarGeometry"]
+        for k, v in self._engine.soltab().items():
+            t = sg._vars[k]
+            if t._array is None:
+                t._array = v
+            else:
+                t._array[:] = v
+            t._stale = False
+
+    def _replay_all_time(self, ts):
+        """Fill `ts` (an all-time Atmosphere variable) for the days computed so
+        far: a second handle replays them from the initial conditions with only
+        that variable selected.  The reference holds these arrays from the first
+        advance on (prms_atmosphere.py:264-285); here they cost nothing until read."""
+        nd = self._days_on_device
+        if nd <= 0:
+            return
+        eng = Engine(self._param_dict, self.control.start_time, **self._engine_kwargs)
+        try:
+            eng.select_outputs([ts.variable_name], [])
+            f = self._forcings
+            blk, _ = eng.run_host(f["prcp"][:nd], f["tmax"][:nd], f["tmin"][:nd], budgets=False)
+            ts._array[:nd] = blk[ts.variable_name]
+        finally:
+            eng.close()
 
     # ---------------------------------------------------------------- blocks
     def _reduced_selection(self):
-        """What run() has to bring back for a block nobody looks into: the
-        all-time Atmosphere variables, the budget terms (accumulations) and
-        whatever goes to netCDF.  Everything else is only observable for the
-        last day of a run, i.e. in its last block."""
+        """What run() has to bring back for a block nobody looks into: only what
+        goes to netCDF (the variable files, and every budget term when budget
+        files are written).  The budget accumulations are summed on the device,
+        the all-time Atmosphere variables are recomputed if somebody reads them,
+        and everything else is only observable for the last day of a run, i.e.
+        in its last block."""
         hv_full, sv = self._full_selection
         want = set()
-        if "PRMSAtmosphere" in self.processes:
-            want.update(self.processes["PRMSAtmosphere"].get_variables())
-        for proc in self.processes.values():
-            b = getattr(proc, "budget", None)
-            if b is not None:
-                for comp in b.components:
-                    want.update(b.terms[comp])
         if self._netcdf is not None:
             for _, _, f in self._netcdf.files:
                 want.update(f.vars)
-        return [v for v in hv_full if v in want], sv
+            if self._netcdf.budget_files:
+                for proc in self.processes.values():
+                    b = getattr(proc, "budget", None)
+                    if b is not None:
+                        for comp in b.components:
+                            want.update(b.terms[comp])
+        return [v for v in hv_full if v in want], [v for v in sv if v in want]
 
     def _select(self, full: bool):
         if self._mode == "channel" or full == self._selection_is_full:
@@ -352,12 +445,13 @@ class Model:
         self._engine.select_outputs(hv, sv)
         self._selection_is_full = full
 
-    def _compute_block(self, t0, n, reduced: bool = False):
+    def _compute_block(self, t0, n, reduced: bool = False, device_acc: bool = False):
         self._ensure_engine()
         eng = self._engine
         if eng.day != t0:
             raise RuntimeError(f"engine is at day {eng.day}, block starts at {t0}")
         self._select(full=not reduced)
+        self._set_device_acc(device_acc)
         if self._mode == "channel":
             blk, viol = self._channel_block(t0, n)
         elif self._mode == "sub":
@@ -365,25 +459,33 @@ class Model:
             blk, viol = eng.run_host_inputs({k: v[t0:t0 + n] for k, v in self._forcings.items()},
                                             [P.base_name(x) for x in self.process_order], ndays=n)
         else:
-            eng.set_block_days(min(n, 16))
+            eng.set_block_days(0)  # the library sizes its device blocks (~2 GB of results each)
             f = self._forcings
-            # the block's arrays are consumed before the next block is computed
+            # result buffers alternate between two sets: block b may still be on its
+            # way to the netCDF files while block b+1 is computed
+            self._buf_slot ^= 1
             blk, viol = eng.run_host(f["prcp"][t0:t0 + n], f["tmax"][t0:t0 + n], f["tmin"][t0:t0 + n],
-                                     pinned_outputs=True, reuse_buffers=True)
+                                     pinned_outputs=True, reuse_buffers=1 + self._buf_slot)
         self._block, self._block_t0, self._block_n, self._block_viol = blk, t0, n, viol
-        # all-time variables of Atmosphere: fill the rows of this block; budget terms: add
-        # the block to the accumulations.  Plain copies and sums over [n, nhru] arrays --
+        self._days_on_device = max(self._days_on_device, t0 + n)
+        # all-time variables of Atmosphere: rows are kept when the array exists, else
+        # recomputed on demand; budget terms: added to the host-side accumulations
+        # unless the device sums them.  Plain copies and sums over [n, nhru] arrays --
         # numpy releases the GIL for them, so a few threads share the memory traffic.
         jobs = []
         if "PRMSAtmosphere" in self.processes:
             atm = self.processes["PRMSAtmosphere"]
             for var in atm.get_variables():
-                if var in blk:
-                    jobs.append((_copy_rows, (atm[var].data, t0, n, blk[var])))
-        dt = float(self.control.time_step / np.timedelta64(1, "D"))
-        for name, proc in self.processes.items():
-            if getattr(proc, "budget", None) is not None:
-                jobs.extend((proc.budget.accumulate_term, a) for a in proc.budget.block_terms(blk, dt))
+                ts = atm._vars[var]
+                if var in blk and ts.allocated:
+                    jobs.append((ts.set_rows, (t0, blk[var])))
+                else:
+                    ts.mark_stale()
+        if not device_acc:
+            dt = float(self.control.time_step / np.timedelta64(1, "D"))
+            for name, proc in self.processes.items():
+                if getattr(proc, "budget", None) is not None:
+                    jobs.extend((proc.budget.accumulate_term, a) for a in proc.budget.block_terms(blk, dt))
         big = n * max(self._engine.nhru, 1) >= 1 << 18
         if big and len(jobs) > 1:
             list(_pool().map(lambda j: j[0](*j[1]), jobs))
@@ -422,24 +524,46 @@ class Model:
             self._ensure_engine()
         if not self._control_is_external:
             self.control.advance()
-        for name in ("PRMSSolarGeometry", "PRMSAtmosphere"):
-            if name in self.processes:
-                proc = self.processes[name]
-                if name == "PRMSAtmosphere":
-                    self._ensure_block(self.control.itime_step)
-                for var in proc.get_variables():
-                    proc[var].advance()
+        if "PRMSSolarGeometry" in self.processes:
+            for ts in self.processes["PRMSSolarGeometry"]._vars.values():
+                ts.advance()
+        if "PRMSAtmosphere" in self.processes:
+            self._ensure_block(self.control.itime_step)
+            self._serve_all_time_current()
 
-    def _ensure_block(self, it, limit=None, reduced_unless_last=False):
+    def _serve_all_time_current(self):
+        """`.current` of the all-time Atmosphere variables for the control's day."""
+        it = self.control.itime_step
+        j = it - self._block_t0
+        for var, ts in self.processes["PRMSAtmosphere"]._vars.items():
+            if self._block is not None and var in self._block and 0 <= j < self._block_n:
+                ts.set_current(self._block[var][j])
+            else:
+                ts.advance()
+
+    def _ensure_block(self, it, limit=None, fast=False):
+        """Make `_block` cover day `it`.  `fast` (run()): every block but the
+        run's last few days is computed with the reduced selection and large
+        blocks, its budget terms summed on the device; the last days form a block
+        with every variable, because that is what a caller can look at afterwards."""
         if self._block is not None and self._block_t0 <= it < self._block_t0 + self._block_n:
             return
         self._ensure_engine()
+        self._drain_writes(keep=1)  # the buffers of the block before the current one are reused now
         remaining = self.control.n_times - it
-        n = min(self.block_days, remaining)
         if limit is not None:
-            n = min(n, limit)
-        last = n == (remaining if limit is None else min(remaining, limit))
-        self._compute_block(it, n, reduced=reduced_unless_last and not last)
+            remaining = min(remaining, limit)
+        n_full = min(self.block_days, remaining)
+        if not fast or self._mode in ("channel", "sub"):
+            self._compute_block(it, n_full)
+            return
+        if remaining <= n_full:
+            self._compute_block(it, remaining, reduced=False, device_acc=True)
+            return
+        hv, sv = self._reduced_selection()
+        cap = self._block_days_user or self._days_for(hv, sv, 1024)
+        n = min(cap, remaining - n_full)
+        self._compute_block(it, n, reduced=True, device_acc=True)
 
     def calculate(self):
         """base/model.py:739-743: after this call every process shows day itime_step."""
@@ -473,7 +597,26 @@ class Model:
             it = self.control.itime_step
             self._netcdf.write_days(self, it, it + 1)
 
+    def _write_async(self, t0, t1):
+        """Days [t0, t1) of the current block go to the netCDF files on the
+        writer thread while the next block is computed (its results land in the
+        other set of buffers)."""
+        if self._writer is None:
+            from concurrent.futures import ThreadPoolExecutor
+
+            self._writer = ThreadPoolExecutor(max_workers=1)
+        blk, b0 = self._block, self._block_t0
+        self._pending_writes.append(self._writer.submit(self._netcdf.write_days, self, t0, t1, blk, b0))
+
+    def _drain_writes(self, keep=0):
+        while len(self._pending_writes) > keep:
+            self._pending_writes.pop(0).result()
+
     def finalize(self):
+        self._drain_writes()
+        if self._writer is not None:
+            self._writer.shutdown()
+            self._writer = None
         if self._netcdf is not None:
             self._netcdf.close()
             self._netcdf = None
@@ -520,8 +663,7 @@ class Model:
         done = 0
         while done < n_time_steps:
             it = self.control.itime_step + 1
-            # only the last block of a run is observable variable by variable
-            self._ensure_block(it, limit=n_time_steps - done, reduced_unless_last=True)
+            self._ensure_block(it, limit=n_time_steps - done, fast=True)
             t1 = min(self._block_t0 + self._block_n, it + (n_time_steps - done))
             nd = t1 - it
             # budgets for the whole block: any violating day raises / warns as the
@@ -530,21 +672,25 @@ class Model:
                 v = self._block_viol[it - self._block_t0:t1 - self._block_t0]
                 if v.any():
                     bad_day = int(np.argwhere(v.any(axis=1))[0, 0])
+                    self._drain_writes()
+                    if self._netcdf is not None and bad_day > 0:
+                        self._netcdf.write_days(self, it, it + bad_day)
                     for _ in range(bad_day + 1):
                         self.advance()
                     self.calculate()  # raises ValueError / warns through Budget
                     if self._netcdf is not None:
-                        self._netcdf.write_days(self, it, it + bad_day + 1)
+                        self._netcdf.write_days(self, it + bad_day, it + bad_day + 1)
                     done += bad_day + 1
                     continue
             if self._netcdf is not None:
-                self._netcdf.write_days(self, it, t1)
-            for _ in range(nd):
-                self.control.advance()
-            for name in ("PRMSSolarGeometry", "PRMSAtmosphere"):
-                if name in self.processes:
-                    for var in self.processes[name].get_variables():
-                        self.processes[name][var].advance()
+                self._write_async(it, t1)
+            self.control.advance(nd)
+            if "PRMSSolarGeometry" in self.processes:
+                for ts in self.processes["PRMSSolarGeometry"]._vars.values():
+                    if ts.allocated:
+                        ts.advance()
+            if "PRMSAtmosphere" in self.processes:
+                self._serve_all_time_current()
             self.calculate_last_only()
             done += nd
         if finalize:

@@ -168,9 +168,10 @@ class ModelNetcdfOutput:
                 self.budget_files[pname] = _BudgetFile(self.dir / f"{pname}_budget.nc", pname, b,
                                                        nhm_seg if False else nhm_id)
 
-    def write_days(self, model, t0, t1):
-        """Write days [t0, t1) of the model's current block."""
-        blk, b0 = model._block, model._block_t0
+    def write_days(self, model, t0, t1, blk=None, b0=None):
+        """Write days [t0, t1) of a block (default: the model's current one)."""
+        if blk is None:
+            blk, b0 = model._block, model._block_t0
         start = model.control.start_time.astype("datetime64[D]")
         epoch = np.datetime64("1970-01-01", "D")
         tdays = (start - epoch).astype(int) + np.arange(t0, t1)

@@ -45,16 +45,62 @@ def _full(shape, fill, dtype):
 class TimeseriesArray:
     """All-time variable with a `.current` row (base/timeseries.py:8-70).
 
-    `.data` is [ntime or 366, nhru]; rows are filled as blocks are computed
-    (SolarGeometry tables are complete from the start)."""
+    `.data` is [ntime or 366, nhru].  The reference computes these arrays up
+    front (SolarGeometry at construction, Atmosphere on the first advance); here
+    they are materialised when somebody looks: the array is allocated on first
+    access and `loader(self)` -- the owning Model -- fills whatever rows were
+    computed on the device without being brought to the host (a fast
+    `Model.run()` does not drain 18 [ntime, nhru] arrays nobody reads)."""
 
-    def __init__(self, control, var_name, array, doy_indexed=False):
+    def __init__(self, control, var_name, array=None, doy_indexed=False, shape=None,
+                 dtype=np.float64, fill=np.nan):
         self.name = "TimeseriresArray"
         self.control = control
         self.variable_name = var_name
-        self.data = array
+        self._array = array
+        self._shape = tuple(array.shape) if array is not None else tuple(shape)
+        self._dtype = array.dtype if array is not None else np.dtype(dtype)
+        self._fill = fill
         self._doy = doy_indexed
-        self._current = self.data[0, :].copy()
+        self._current = np.full(self._shape[1], fill, dtype=self._dtype)
+        self._loader = None
+        self._stale = False   # rows exist on the device side that `_array` does not hold
+
+    @property
+    def shape(self):
+        return self._shape
+
+    @property
+    def allocated(self) -> bool:
+        return self._array is not None
+
+    @property
+    def data(self):
+        if self._array is None:
+            self._array = _full(self._shape, self._fill, self._dtype)
+        if self._stale and self._loader is not None:
+            self._stale = False
+            self._loader(self)
+        return self._array
+
+    @data.setter
+    def data(self, value):
+        self._array = value
+        self._stale = False
+
+    def set_rows(self, t0, rows):
+        """Rows [t0, t0 + len(rows)) as delivered by a block; kept only when the
+        array exists already (otherwise they are recomputed on demand)."""
+        if self._array is None:
+            self._stale = True
+        else:
+            self._array[t0:t0 + len(rows)] = rows
+
+    def mark_stale(self):
+        self._stale = True
+
+    def set_current(self, row):
+        self._current[:] = row
 
     def advance(self):
         if self._doy:
@@ -163,9 +209,17 @@ class Process:
 
     # ---- options: per-process kwargs override control (base/process.py:339-360)
     def _set_options(self, kw):
+        # base/process.py:339-358: an option exists on a process only when its
+        # constructor names it; the constructor argument wins over the control
+        import inspect
+
         opts = getattr(self.control, "options", {}) or {}
+        own = inspect.signature(type(self).__init__).parameters
         for name in ("budget_type", "calc_method", "dprst_flag", "adjust_parameters"):
             val = kw.get(name)
+            if name not in own and val is None:
+                setattr(self, "_" + name, None)
+                continue
             if val is None and name in opts:
                 val = opts[name]
             setattr(self, "_" + name, val)
@@ -299,8 +353,8 @@ class PRMSSolarGeometry(Process):
 
     def _allocate(self):
         for var in self.get_variables():
-            self._vars[var] = TimeseriesArray(
-                self.control, var, np.full((366, self.nhru), np.nan), doy_indexed=True)
+            self._vars[var] = TimeseriesArray(self.control, var, shape=(366, self.nhru),
+                                              doy_indexed=True)
 
 
 class PRMSAtmosphere(Process):
@@ -321,7 +375,8 @@ class PRMSAtmosphere(Process):
             fill = init[var]
             if dt is not np.float64 and isinstance(fill, float) and np.isnan(fill):
                 fill = 0
-            self._vars[var] = TimeseriesArray(self.control, var, _full((nt, self.nhru), fill, dt))
+            self._vars[var] = TimeseriesArray(self.control, var, shape=(nt, self.nhru), dtype=dt,
+                                              fill=fill)
 
 
 class PRMSCanopy(ConservativeProcess):
@@ -419,6 +474,65 @@ class PRMSGroundwaterNoDprst(PRMSGroundwater):
                  budget_type=None, calc_method=None, verbose: bool = None):
         kw = _kw(locals())
         ConservativeProcess.__init__(self, control, discretization, parameters, dprst_flag=False, **kw)
+
+
+def check_adjusted_parameters(pd: dict, soilzone_mode, channel_mode, dprst_flag=True):
+    """The parameter checks PRMSSoilzone and PRMSChannel make at construction
+    (prms_soilzone.py:361-463, prms_channel.py:246-260), on the parameters, in
+    the reference's order and with its messages: mode "warn" -> UserWarning (the
+    device then applies the same edits), "error" -> the warnings, then
+    ValueError, "no" / None -> nothing.  The edits cascade, so each mask is
+    evaluated on the values the previous edits left."""
+    def arr(k):
+        return np.asarray(pd[k], dtype=np.float64)
+
+    if soilzone_mode in ("warn", "error") and "soil_moist_max" in pd:
+        hru_type = np.asarray(pd["hru_type"])
+        soil_moist_max = arr("soil_moist_max").copy()
+        soil_rechr_max = arr("soil_rechr_max_frac") * soil_moist_max
+        soil_moist = arr("soil_moist_init_frac") * soil_moist_max
+        soil_rechr = arr("soil_rechr_init_frac") * soil_rechr_max
+        sat = arr("sat_threshold").copy()
+        sat[(hru_type == 0) | (hru_type == 2)] = 0.0
+        ssres_stor = arr("ssstor_init_frac") * sat
+        ssres_stor[(hru_type == 0) | (hru_type == 2)] = 0.0
+        edited = False
+
+        def check(mask, msg):
+            nonlocal edited
+            if mask.any():
+                edited = True
+                if msg:
+                    warn(f"{msg} at indices: {np.where(mask)[0]}", UserWarning, stacklevel=4)
+            return mask
+
+        m = check(soil_moist_max < 1.0e-5, "soil_moist_max < 1.0e-5, set to 1.0e-5")
+        soil_moist_max = np.where(m, 1.0e-5, soil_moist_max)
+        m = check(soil_rechr_max < 1.0e-5, "soil_rechr_max < 1.0e-5, set to 1.0e-5")
+        soil_rechr_max = np.where(m, 1.0e-5, soil_rechr_max)
+        m = check(soil_rechr_max > soil_moist_max,
+                  "soil_rechr_max > soil_moist_max, soil_rechr_max set to soil_moist_max")
+        soil_rechr_max = np.where(m, soil_moist_max, soil_rechr_max)
+        m = check(soil_rechr > soil_rechr_max,
+                  "soil_rechr_init > soil_rechr_max, setting soil_rechr_init to soil_rechr_max")
+        soil_rechr = np.where(m, soil_rechr_max, soil_rechr)
+        m = check(soil_moist > soil_moist_max,
+                  "soil_moist_init > soil_moist_max, setting soil_moist to soil_moist max")
+        soil_moist = np.where(m, soil_moist_max, soil_moist)
+        m = check(soil_rechr > soil_moist, "soil_rechr > soil_moist, setting soil_rechr to soil_moist")
+        # (the ssres_stor edit counts for "error" but is not announced, prms_soilzone.py:440-452)
+        check(ssres_stor > sat, None)
+        if edited and soilzone_mode == "error":
+            raise ValueError("Some parameter values were edited and an error was requested."
+                             " See warnings for additional details.")
+    if channel_mode in ("warn", "error") and "seg_slope" in pd:
+        flat = np.asarray(pd["seg_slope"], dtype=np.float64) < 1e-7
+        if flat.any():
+            warn(f"seg_slope < 1.0e-7, set to 1.0e-4 at indices:{np.where(flat)[0]}", UserWarning,
+                 stacklevel=4)
+            if channel_mode == "error":
+                raise ValueError("seg_slope parameter values were edited and an error was "
+                                 "requested. See warnings for additional details.")
 
 
 def base_name(name: str) -> str:
