@@ -150,13 +150,14 @@ def ensemble_parameters(p0, members):
     nm = members.size
     dummy = {k: np.zeros((2, NB_HRU)) for k in ("prcp", "tmax", "tmin")}
     pt, _ = scenarios.tile(p0, dummy, nm, temp_shift=False)
-    for k, (lo, hi) in ENSEMBLE_PARAMS.items():
-        v = np.array(pt[k], dtype=np.float64, copy=True)
-        for j, m in enumerate(members):
-            rng = np.random.default_rng(int(m))
-            sl = slice(j * NB_HRU, (j + 1) * NB_HRU)
+    for k in ENSEMBLE_PARAMS:
+        pt[k] = np.array(pt[k], dtype=np.float64, copy=True)
+    for j, m in enumerate(members):
+        rng = np.random.default_rng(int(m))  # one stream per member, parameters in table order
+        sl = slice(j * NB_HRU, (j + 1) * NB_HRU)
+        for k, (lo, hi) in ENSEMBLE_PARAMS.items():
+            v = pt[k]
             v[..., sl] = np.clip(v[..., sl] * rng.uniform(0.8, 1.2, size=v[..., sl].shape), lo, hi)
-        pt[k] = v
     return pt
 
 

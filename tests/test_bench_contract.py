@@ -6,6 +6,8 @@ import pathlib as pl
 import subprocess
 import sys
 
+import numpy as np
+
 ROOT = pl.Path(__file__).resolve().parent.parent
 
 
@@ -39,3 +41,24 @@ def test_gpu_arm_fails_loudly_without_a_gpu():
                        cwd=ROOT)
     assert r.returncode != 0
     assert not any(ln.lstrip().startswith("{") for ln in r.stdout.splitlines())
+
+
+def test_ensemble_parameters_follow_the_recipe(drb):
+    """bench.ensemble_parameters: member m scales the
+    listed soil / snow parameters by U(0.8, 1.2) from seed m, inside the
+    reference's parameter bounds; everything else is the base domain's."""
+    import bench
+
+    p, f, start = drb
+    pt = bench.ensemble_parameters(p, [3, 900])
+    again = bench.ensemble_parameters(p, [900])
+    for k, (lo, hi) in bench.ENSEMBLE_PARAMS.items():
+        v = np.asarray(pt[k], dtype=np.float64)
+        assert v.min() >= lo and v.max() <= hi, k
+        base = np.asarray(p[k], dtype=np.float64)
+        ratio = v[..., :765] / np.where(base == 0, 1.0, base)
+        inside = (base != 0) & (v[..., :765] > lo) & (v[..., :765] < hi)
+        assert ((ratio[inside] >= 0.8 - 1e-12) & (ratio[inside] <= 1.2 + 1e-12)).all(), k
+        np.testing.assert_array_equal(v[..., 765:], np.asarray(again[k]))  # a member does not depend on its rank
+    np.testing.assert_array_equal(pt["hru_area"][:765], pt["hru_area"][765:])
+    assert pt["tosegment"][456:].max() <= 2 * 456 and pt["hru_segment"][765:].max() > 456

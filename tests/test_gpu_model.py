@@ -325,3 +325,100 @@ def test_model_from_yaml_runs(drb, tmp_path):
                                rtol=1e-9, atol=1e-10)
     np.testing.assert_allclose(m.processes["PRMSChannel"]["seg_outflow"], ref["seg_outflow"][-1],
                                rtol=1e-9, atol=1e-10)
+
+
+def test_run_accumulates_budgets_on_the_device_like_stepping(drb):
+    """Model.run() sums the budget terms on the device (pws_select_accumulations)
+    and leaves the all-time Atmosphere arrays on the device side until somebody
+    reads them; a model stepped day by day sums on the host.  Same numbers."""
+    p, f, start = drb
+    nd = 50
+    m1 = _model(p, f, start, nd, block_days=16)
+    m1.run(finalize=False)
+    atm = m1.processes["PRMSAtmosphere"]
+    assert not atm._vars["tmaxf"].allocated  # nothing was drained for it
+    m2 = _model(p, f, start, nd, block_days=16)
+    for _ in range(nd):
+        m2.advance()
+        m2.calculate()
+    for name in NHM[2:]:
+        a1, a2 = m1.processes[name].budget.accumulations, m2.processes[name].budget.accumulations
+        for comp in a1:
+            for v in a1[comp]:
+                np.testing.assert_allclose(a1[comp][v], a2[comp][v], rtol=1e-12, atol=1e-12,
+                                           err_msg=f"{name} {comp} {v}")
+    # the lazily replayed all-time arrays equal the ones filled block by block
+    for k in ("tmaxf", "swrad", "potet", "pptmix", "transp_on"):
+        np.testing.assert_array_equal(atm[k].data, m2.processes["PRMSAtmosphere"][k].data, err_msg=k)
+        np.testing.assert_array_equal(atm[k].current, m2.processes["PRMSAtmosphere"][k].current)
+    # and run() in pieces continues where it stopped
+    m3 = _model(p, f, start, nd, block_days=16)
+    m3.run(n_time_steps=20, finalize=False)
+    m3.run(finalize=False)
+    a3 = m3.processes["PRMSSoilzone"].budget.accumulations
+    np.testing.assert_allclose(a3["outputs"]["perv_actet_hru"],
+                               m1.processes["PRMSSoilzone"].budget.accumulations["outputs"]["perv_actet_hru"],
+                               rtol=1e-12)
+    for m in (m1, m2, m3):
+        m.finalize()
+
+
+def test_adjust_parameters_follows_the_reference(drb):
+    """prms_soilzone.py:361-463 / prms_channel.py:246-260: "warn" announces the
+    edits with the reference's messages, "error" raises after announcing, "no"
+    is silent -- per process (the channel's choice does not switch off the
+    soilzone's), and a control with dprst_flag=True runs the NoDprst classes."""
+    import warnings
+
+    import pywatershed_b200 as pwsb
+
+    p, f, start = drb
+    q = {k: np.array(v, copy=True) for k, v in p.items()}
+    q["soil_rechr_init_frac"] = np.asarray(q["soil_rechr_init_frac"], dtype=np.float64).copy()
+    q["soil_rechr_init_frac"][7] = 1.5       # soil_rechr_init > soil_rechr_max
+    q["seg_slope"] = np.asarray(q["seg_slope"], dtype=np.float64).copy()
+    q["seg_slope"][3] = 1e-9
+    nd = 5
+
+    def model(sz, ch):
+        control = _control(start, nd)
+        md = {"control": control, "dis": _parameters(q)}
+        for n in NHM:
+            kw = {"class": getattr(pwsb, n), "parameters": _parameters(q), "dis": "dis"}
+            if n == "PRMSSoilzone":
+                kw["adjust_parameters"] = sz
+            if n == "PRMSChannel":
+                kw["adjust_parameters"] = ch
+            md[n] = kw
+        md["model_order"] = list(NHM)
+        m = pwsb.Model(md, find_input_files=False)
+        for k in ("prcp", "tmax", "tmin"):
+            m.processes["PRMSAtmosphere"].set_input_to_adapter(k, f[k][:nd])
+        return m
+
+    with pytest.warns(UserWarning) as rec:
+        m = model("warn", "warn")
+        m.run(finalize=True)
+    msgs = [str(w.message) for w in rec]
+    assert any("soil_rechr_init > soil_rechr_max" in s and "[7]" in s for s in msgs), msgs
+    assert any("seg_slope < 1.0e-7" in s and "[3]" in s for s in msgs), msgs
+    with pytest.warns(UserWarning), pytest.raises(ValueError, match="an error was requested"):
+        model("error", "no").run()
+    with pytest.warns(UserWarning), pytest.raises(ValueError, match="seg_slope parameter values"):
+        model("no", "error").run()
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        model("no", "no").run(finalize=True)
+    # "no" on the channel leaves the soilzone's adjustment on: same result as warn/warn
+    with pytest.warns(UserWarning, match="soil_rechr_init"):
+        m2 = model("warn", "no")
+        m2.run(finalize=True)
+    np.testing.assert_array_equal(m.processes["PRMSSoilzone"]["soil_rechr"],
+                                  m2.processes["PRMSSoilzone"]["soil_rechr"])
+    # a control that says dprst_flag=True with the NoDprst classes (the reference runs it)
+    nod = ["PRMSSolarGeometry", "PRMSAtmosphere", "PRMSCanopy", "PRMSSnow", "PRMSRunoffNoDprst",
+           "PRMSSoilzoneNoDprst", "PRMSGroundwaterNoDprst", "PRMSChannel"]
+    m3 = _model(p, f, start, nd, procs=nod, dprst_flag=True)
+    m3.run(finalize=True)
+    assert m3.processes["PRMSRunoffNoDprst"]._dprst_flag is False
+    assert m3.processes["PRMSCanopy"]._dprst_flag is None

@@ -69,22 +69,28 @@ def test_soltab(drb):
         np.testing.assert_allclose(st[k][:, g["hru_sample"]], g[k], rtol=1e-9, atol=1e-10)
 
 
-def test_soltab_on_the_device(drb):
-    """Option soltab_device: the PRMSSolarGeometry tables from k_soltab (CUDA's
-    sin / cos / acos, 1-2 ulp from the host libm) instead of the host threads."""
+def test_soltab_host_option(drb):
+    """Option soltab_device 0: the PRMSSolarGeometry tables from host threads and
+    the host libm (a debugging aid for last-bit comparisons; the default is the
+    CUDA kernel k_soltab, which test_soltab and every other test here exercise).
+    Both agree with the oracle at the north-star tolerance."""
     p, f, start = drb
-    e = _engine(p, start)
-    e._opt("soltab_device", 1)
-    e._check(e.L.pws_init(e.h))
+    from pywatershed_b200 import Engine
+
+    e = Engine(p, start, soltab_device=False)
     st = e.soltab()
     ref = po.Oracle(p, start=start).soltabs()
     for k in st:
-        np.testing.assert_allclose(st[k], ref[k], rtol=1e-9, atol=1e-9, err_msg=k)
+        np.testing.assert_allclose(st[k], ref[k], rtol=1e-9, atol=1e-10, err_msg=k)
     e.select_outputs(["swrad", "potet"], [])
     got, _ = e.run_host(f["prcp"][:30], f["tmax"][:30], f["tmin"][:30])
     r, _ = po.Oracle(p, start=start).run(f["prcp"][:30], f["tmax"][:30], f["tmin"][:30], ["swrad", "potet"], ())
     for k in ("swrad", "potet"):
-        np.testing.assert_allclose(got[k], r[k], rtol=1e-9, atol=1e-9, err_msg=k)
+        np.testing.assert_allclose(got[k], r[k], rtol=1e-9, atol=1e-10, err_msg=k)
+    d = _engine(p, start).soltab()
+    worst = max(float(np.abs(d[k] - st[k]).max() / max(np.abs(st[k]).max(), 1.0)) for k in st)
+    print(f"k_soltab vs host libm tables: largest difference {worst:.3g} of the table's range")
+    assert worst < 1e-12
 
 
 @pytest.mark.parametrize("scen", ["drb", "drbx"])
