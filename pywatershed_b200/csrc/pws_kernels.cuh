@@ -498,35 +498,34 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
     // mbarrier; otherwise every thread prefetches its own values
     // into registers.
     const bool tma = a.use_tma != 0;
-    const int64_t hru0 = tile * H;
-    // an odd tail is copied with the padding element behind it (see fill_column_args)
-    const int64_t row_n = (a.P.nhru - hru0) < H ? (a.P.nhru - hru0) : H;
-    const uint32_t row_bytes = (uint32_t)(((row_n + 1) & ~(int64_t)1) * 8);
-    // forcing column of the CTA's first HRU, and of this thread's HRU; with a
-    // forcing period the CTA's row may wrap around the end of the period once
-    // (fill_column_args only allows TMA for an even period >= H)
-    const int64_t fcol0 = a.fperiod > 0 ? hru0 % a.fperiod : hru0;
-    const int64_t fcol = a.fperiod > 0 ? ii % a.fperiod : ii;
-    const int64_t n_head = (a.fperiod > 0 && fcol0 + row_n > a.fperiod) ? a.fperiod - fcol0 : row_n;
-    auto tma_forcing_row = [&](uint32_t dst, const double* row, uint32_t bar) {
-      if (n_head == row_n) {
-        tma_bulk_g2s(dst, row + fcol0, row_bytes, bar);
-      } else {  // both pieces are even: period, fcol0 and row_n are
-        tma_bulk_g2s(dst, row + fcol0, (uint32_t)(n_head * 8), bar);
-        tma_bulk_g2s(dst + (uint32_t)(n_head * 8), row, row_bytes - (uint32_t)(n_head * 8), bar);
-      }
-    };
+    // Everything the copies need is recomputed from the kernel arguments inside
+    // tma_issue (one thread, once a day): a value kept across the day loop would
+    // cost every thread of the group a register, and this kernel spills.
     auto tma_issue = [&](int d) {  // one thread
+      const int64_t hru0 = ((int64_t)blockIdx.x + a.tile0) * H;
+      // an odd tail is copied with the padding element behind it (see fill_column_args)
+      const int64_t row_n = (a.P.nhru - hru0) < H ? (a.P.nhru - hru0) : H;
+      const uint32_t row_bytes = (uint32_t)(((row_n + 1) & ~(int64_t)1) * 8);
+      // forcing column of the CTA's first HRU; with a forcing period the CTA's row
+      // may wrap around the end of the period once (fill_column_args only allows
+      // TMA for an even period >= H, so both pieces stay 16-byte aligned)
+      const int64_t fcol0 = a.fperiod > 0 ? hru0 % a.fperiod : hru0;
+      const uint32_t head_bytes =
+          (a.fperiod > 0 && fcol0 + row_n > a.fperiod) ? (uint32_t)((a.fperiod - fcol0) * 8) : row_bytes;
       const uint32_t bar = mbar0;
       const uint32_t dst = smem_u32(sF);
       const int doy = a.cal[d].x;
       const int64_t fo = (int64_t)d * a.fstride;
-      const int64_t so = (int64_t)(doy - 1) * S + hru0;
+      const int64_t so = (int64_t)(doy - 1) * a.P.stride + hru0;
       mbar_expect_tx(bar, kForcRows * row_bytes + 16u);
       tma_bulk_g2s(smem_u32(sCal + 4 * (d & 1)), a.cal + d, 16u, bar);
-      tma_forcing_row(dst + 0 * H * 8, a.prcp + fo, bar);
-      tma_forcing_row(dst + 1 * H * 8, a.tmax + fo, bar);
-      tma_forcing_row(dst + 2 * H * 8, a.tmin + fo, bar);
+      const double* const rows[3] = {a.prcp + fo, a.tmax + fo, a.tmin + fo};
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        tma_bulk_g2s(dst + k * H * 8, rows[k] + fcol0, head_bytes, bar);
+        if (head_bytes != row_bytes)
+          tma_bulk_g2s(dst + k * H * 8 + head_bytes, rows[k], row_bytes - head_bytes, bar);
+      }
       tma_bulk_g2s(dst + 3 * H * 8, a.P.soltab_potsw + so, row_bytes, bar);
       tma_bulk_g2s(dst + 4 * H * 8, a.P.soltab_horad_potsw + so, row_bytes, bar);
     };
@@ -543,6 +542,7 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
     } else {
       const int4 c = a.cal[0];
       nxt.doy = c.x; nxt.dowy = c.y; nxt.month = c.z; nxt.dom = c.w;
+      const int64_t fcol = a.fperiod > 0 ? ii % a.fperiod : ii;
       nxt.prcp = __ldcs(a.prcp + fcol);
       nxt.tmax = __ldcs(a.tmax + fcol);
       nxt.tmin = __ldcs(a.tmin + fcol);
@@ -570,7 +570,7 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
         in.cal = reinterpret_cast<const int*>(a.cal + d);
         if (d + 1 < a.ndays) {
           const int4 c = a.cal[d + 1];
-          const int64_t fo = (int64_t)(d + 1) * a.fstride + fcol;
+          const int64_t fo = (int64_t)(d + 1) * a.fstride + (a.fperiod > 0 ? ii % a.fperiod : ii);
           nxt.doy = c.x; nxt.dowy = c.y; nxt.month = c.z; nxt.dom = c.w;
           nxt.prcp = __ldcs(a.prcp + fo);
           nxt.tmax = __ldcs(a.tmax + fo);

@@ -531,14 +531,16 @@ class Model:
             self._ensure_block(self.control.itime_step)
             self._serve_all_time_current()
 
-    def _serve_all_time_current(self):
-        """`.current` of the all-time Atmosphere variables for the control's day."""
+    def _serve_all_time_current(self, lazy=False):
+        """`.current` of the all-time Atmosphere variables for the control's day:
+        from the block when it holds them; else from `.data` (which recomputes the
+        array), unless `lazy` -- run() passes over blocks nobody looks into."""
         it = self.control.itime_step
         j = it - self._block_t0
         for var, ts in self.processes["PRMSAtmosphere"]._vars.items():
             if self._block is not None and var in self._block and 0 <= j < self._block_n:
                 ts.set_current(self._block[var][j])
-            else:
+            elif not lazy or (ts.allocated and not ts._stale):
                 ts.advance()
 
     def _ensure_block(self, it, limit=None, fast=False):
@@ -690,7 +692,7 @@ class Model:
                     if ts.allocated:
                         ts.advance()
             if "PRMSAtmosphere" in self.processes:
-                self._serve_all_time_current()
+                self._serve_all_time_current(lazy=True)
             self.calculate_last_only()
             done += nd
         if finalize:
