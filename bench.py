@@ -460,9 +460,10 @@ def run_channel_only(args):
 class Dist:
     """torch.distributed plumbing of one rank (NCCL; a single process when N = 1)."""
 
-    def __init__(self):
+    def __init__(self, shard_of=None):
         import torch
 
+        self.shard_of = shard_of
         self.rank = int(os.environ.get("RANK", "0"))
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -524,11 +525,12 @@ def make_shard(spec, D: Dist, scaling: str):
     from pywatershed_b200 import sharding
     import scenarios
 
+    world = D.shard_of or D.world  # --shard-of: rank 0's share of an N-way split, on one GPU
     if spec.get("ensemble"):
         p0, f0, start = scenarios.load_drb()
         nm = spec["ntile"]
         if scaling == "strong":
-            members = sharding.partition_members(nm, D.world, D.rank)
+            members = sharding.partition_members(nm, world, D.rank)
             total = nm
         else:
             members = np.arange(nm) + D.rank * nm
@@ -536,22 +538,22 @@ def make_shard(spec, D: Dist, scaling: str):
         pt = ensemble_parameters(p0, members)
         return dict(p0=p0, f0=f0, start=start, params=pt, hru_idx=None, members=members,
                     forcing_period=NB_HRU, job_hrus=total * NB_HRU, job_segs=total * NB_SEG,
-                    parallelism=f"member-sharded x{D.world} ({members.size} members on this rank), "
+                    parallelism=f"member-sharded x{world} ({members.size} members on this rank), "
                                 "no data-path collective")
     p0, f0, pt, start = build_domain(spec, D.rank)
     nhru, nseg = pt["hru_area"].shape[0], pt["tosegment"].shape[0]
-    if scaling == "weak" or D.world == 1:
+    if scaling == "weak" or world == 1:
         return dict(p0=p0, f0=f0, start=start, params=pt, hru_idx=None, seg_idx=None,
                     forcing_rank=D.rank if scaling == "weak" else 0,
                     job_hrus=nhru * (D.world if scaling == "weak" else 1),
                     job_segs=nseg * (D.world if scaling == "weak" else 1),
                     parallelism=(f"replicas x{D.world}: one whole domain per GPU (weak scaling)"
                                  if D.world > 1 else "one GPU"))
-    seg_rank, hru_rank = sharding.partition_basins(pt["tosegment"], pt["hru_segment"], D.world)
+    seg_rank, hru_rank = sharding.partition_basins(pt["tosegment"], pt["hru_segment"], world)
     q, hru_idx, seg_idx = sharding.shard_parameters(pt, seg_rank, hru_rank, D.rank)
     return dict(p0=p0, f0=f0, start=start, params=q, hru_idx=hru_idx, seg_idx=seg_idx, forcing_rank=0,
                 job_hrus=nhru, job_segs=nseg,
-                parallelism=f"basin-sharded x{D.world}: outlet trees of ONE domain dealt to the GPUs "
+                parallelism=f"basin-sharded x{world}: outlet trees of ONE domain dealt to the GPUs "
                             f"(this rank: {hru_idx.size:,} HRUs, {seg_idx.size:,} segments), "
                             "no data-path collective")
 
@@ -674,7 +676,11 @@ def main():
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the ensemble / e2e_nhm_default / pcie / e2e_model objects")
     ap.add_argument("--lanes", type=int, default=None, help="column launches per block (library option)")
-    ap.add_argument("--no-overlap", action="store_true", help="serialise the blocks (library option)")
+    ap.add_argument("--overlap", type=int, default=None, choices=(0, 1),
+                    help="routing beside the next block's column (library option; default: by domain size)")
+    ap.add_argument("--shard-of", type=int, default=None,
+                    help="tuning aid on ONE GPU: run rank 0's share of an N-way split; `value` is then "
+                         "what N GPUs would give if every rank took as long as this one")
     ap.add_argument("--layout", choices=("tiled", "rows"), default="tiled",
                     help="device-resident results as [day][tile][variable][H] (pws_output_tile; needs "
                          "--outputs full) or as [day][variable][nhru] rows")
@@ -687,7 +693,7 @@ def main():
 
     import torch
 
-    D = Dist()
+    D = Dist(args.shard_of)
     import __graft_entry__ as g
 
     if D.rank == 0:
@@ -698,8 +704,8 @@ def main():
     def engine_for(spec, shard):
         eng = Engine(shard["params"], shard["start"], device=D.local_rank,
                      forcing_period=shard.get("forcing_period"), lanes=args.lanes)
-        if args.no_overlap:
-            eng._opt("overlap_routing", 0)
+        if args.overlap is not None:
+            eng._opt("overlap_routing", args.overlap)
         return eng
 
     def device_leg(spec, outputs, layout, block_days, warmup, steps, clocks=False):
@@ -924,7 +930,9 @@ def main():
                    "job_hrus": shard["job_hrus"], "job_segments": shard["job_segs"],
                    "l2": "inputs larger than L2 (forcings 3 x %.1f GB on rank 0, streamed once per step)"
                          % (nd * nhru * 8 / 1e9),
-                   "parallelism": shard["parallelism"],
+                   "parallelism": shard["parallelism"] + (
+                       f" [EMULATED on one GPU with --shard-of {args.shard_of}: rank 0's share only]"
+                       if args.shard_of else ""),
                    "budget_violations": main_leg["viol_total"],
                    "checksum_seg_outflow_last_day": main_leg["seg_last"]},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(main_leg["launches"]),

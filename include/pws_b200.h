@@ -70,8 +70,9 @@ int pws_set_param_i32(pws_handle *h, const char *name, const int32_t *h_v, int64
  * re-read it per member); 0, default: forcings are [ndays][nhru]),
  * "lanes" (column-kernel launches per block of days, each over a contiguous
  * range of CTA tiles on its own stream: 0, default = by domain size, 1..8),
- * "overlap_routing" (1, default: the routing of block b runs beside the column
- * kernels of block b+1; 0: blocks are serialised),
+ * "overlap_routing" (1: the routing of block b runs beside the column kernels
+ * of block b+1; 0: blocks are serialised; -1, default: by domain size -- on when
+ * the column grid leaves SMs idle or lanes are in use),
  * "channel_chunk" (segments per routing chunk = per CTA of k_route_chunks,
  * default and maximum 512; outlet trees larger than a chunk are cut and linked
  * through HBM),

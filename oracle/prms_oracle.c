@@ -114,6 +114,12 @@ const char *orc_seg_var_name(int i) {
 }
 const char *orc_last_error(Orc *o) { return o->err; }
 const double *orc_hru_var(Orc *o, int idx) { return o->v[idx]; }
+/* one-step parity (tests/parity.py): continue from the caller's values */
+int orc_set_hru_var(Orc *o, int idx, const double *v) {
+  if (idx < 0 || idx >= ORC_N_HRU_VARS) return -1;
+  memcpy(o->v[idx], v, sizeof(double) * (size_t)o->nhru);
+  return 0;
+}
 const double *orc_seg_var(Orc *o, int idx) { return o->s[idx]; }
 const double *orc_soltab_potsw(Orc *o) { return o->soltab_potsw; }
 const double *orc_soltab_horad_potsw(Orc *o) { return o->soltab_horad_potsw; }

@@ -186,6 +186,12 @@ int orc_run_channel(Orc *o, int ndays, const double *seg_lateral_inflow,
 
 /* current value of one public variable (pointer into oracle storage) */
 const double *orc_hru_var(Orc *o, int idx);
+/* Overwrite the current value of one public HRU variable ([nhru]; integer
+ * variables as doubles).  Every prognostic quantity of the column is a public
+ * variable (the reference's state IS its public arrays, process.py:324-372), so
+ * setting all of them makes the oracle continue from somebody else's day: the
+ * one-step ("teacher-forced") parity check of tests/parity.py. */
+int orc_set_hru_var(Orc *o, int idx, const double *v);
 const double *orc_seg_var(Orc *o, int idx);
 
 #ifdef __cplusplus

@@ -81,6 +81,8 @@ def lib(omp: bool = False):
                                       C.c_void_p, C.c_void_p]
         L.orc_hru_var.restype = C.c_void_p
         L.orc_hru_var.argtypes = [C.c_void_p, C.c_int]
+        L.orc_set_hru_var.restype = C.c_int
+        L.orc_set_hru_var.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.orc_seg_var.restype = C.c_void_p
         L.orc_seg_var.argtypes = [C.c_void_p, C.c_int]
         assert [L.orc_hru_var_name(i).decode() for i in range(L.orc_n_hru_vars())] == HRU_VARS
@@ -173,6 +175,28 @@ class Oracle:
         res = {v: hout[:, k, :] for k, v in enumerate(hru_vars)}
         res.update({v: sout[:, k, :] for k, v in enumerate(seg_vars)})
         return res, viol
+
+    def set_hru_vars(self, values: dict):
+        """Overwrite the current value of public HRU variables (name -> [nhru])."""
+        for k, v in values.items():
+            a = np.ascontiguousarray(v, dtype=np.float64)
+            assert a.shape == (self.nhru,)
+            rc = self.L.orc_set_hru_var(self.h, HRU_VARS.index(k), a.ctypes.data)
+            assert rc == 0, k
+
+    def run_forced(self, prcp, tmax, tmin, series: dict):
+        """One-step parity: day d is computed from `series`' day d-1 (every
+        public HRU variable overwritten before the step) instead of from the
+        oracle's own day d-1.  Returns var -> [ndays, nhru]."""
+        nd = np.asarray(prcp).shape[0]
+        out = {k: np.empty((nd, self.nhru)) for k in HRU_VARS}
+        for d in range(nd):
+            if d > 0:
+                self.set_hru_vars({k: np.asarray(series[k][d - 1], dtype=np.float64) for k in HRU_VARS})
+            res, _ = self.run(prcp[d:d + 1], tmax[d:d + 1], tmin[d:d + 1], HRU_VARS, (), budgets=False)
+            for k in HRU_VARS:
+                out[k][d] = res[k][0]
+        return out
 
     def run_channel(self, seg_lateral_inflow, seg_vars=SEG_VARS):
         lat = np.ascontiguousarray(seg_lateral_inflow, dtype=np.float64)

@@ -99,10 +99,10 @@ struct pws_handle {
   int soltab_device = 1;
   int tma = 1;  // option: stage forcings with TMA bulk copies when the rows are aligned
   int lanes_opt = 0;        // option "lanes": 0 = by domain size, else column launches per block
-  int overlap_routing = 1;  // option "overlap_routing": routing of block b beside the column of b+1
+  int overlap_routing = -1;  // option "overlap_routing": routing of block b beside the column of b+1 (-1: by domain size)
   int64_t forcing_period = 0;  // option "forcing_period": forcings are [ndays][period], HRU i reads i % period
   bool route_attr_set = false;
-  bool smem_attr_set[8] = {false, false, false, false, false, false, false, false};
+  bool smem_attr_set[16] = {};
   bool tiled_outputs = false;  // option "tiled_outputs": [day][tile][variable][H] (SINK_TILED)
   int column_hrus_opt = 0;  // option "column_hrus": 0 = by domain size, else 128 | 256
   double albset[4] = {0, 0, 0, 0};
@@ -439,11 +439,11 @@ extern "C" int pws_set_option(pws_handle* h, const char* name, double value) {
     h->lanes_opt = (int)value;
     return 0;
   }
-  else if (!strcmp(name, "overlap_routing")) { h->overlap_routing = value != 0.0; return 0; }
+  else if (!strcmp(name, "overlap_routing")) { h->overlap_routing = value < 0 ? -1 : (value != 0.0); return 0; }
   else if (!strcmp(name, "accumulate")) { h->accumulate_on = value != 0.0; return 0; }
   else if (!strcmp(name, "forcing_period")) {
-    if (value < 0 || (value > 0 && h->nhru % (int64_t)value != 0))
-      PWS_FAIL(h, "pws_set_option: forcing_period must divide nhru (%lld)", (long long)h->nhru);
+    if (value < 0 || (value > 0 && h->nhru % (int64_t)value != 0) || h->nhru >= ((int64_t)1 << 31))
+      PWS_FAIL(h, "pws_set_option: forcing_period must divide nhru (%lld < 2^31)", (long long)h->nhru);
     PWS_CUDA(h, sync_all(h));
     h->forcing_period = (int64_t)value;
     free_ring(h);  // the forcing ring is sized by the number of forcing columns
@@ -1177,8 +1177,23 @@ static int column_lanes(pws_handle* h, int ntiles, int H) {
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
   const int slots = nsm * (H == 128 ? 2 : 1);  // CTAs resident at a time
   if (ntiles <= slots) return 1;               // one wave: nothing to smooth
+  const int tail = ntiles % slots;             // CTAs of the last wave
+  if (tail == 0 || tail * 5 >= slots * 4) return 1;  // the last wave is (nearly) full
   const int g = (ntiles + (2 * slots) / 3 - 1) / ((2 * slots) / 3);
   return std::max(1, std::min(g, pws_handle::kMaxLanes));
+}
+
+// Routing of block b beside the column kernels of block b+1?  A column CTA and a
+// routing CTA each take a whole SM, so on a domain whose column grid fills the GPU
+// the overlap only re-orders the same SM-time (measured on the CONUS domain: 130
+// ms per pass against 128 serialised); it pays when the column grid leaves SMs
+// idle (a basin shard of a multi-GPU run) or when lanes are on anyway.
+static bool overlap_routing(pws_handle* h, int ntiles, int H, int lanes) {
+  if (h->overlap_routing >= 0) return h->overlap_routing != 0;
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+  const int slots = nsm * (H == 128 ? 2 : 1);
+  return lanes > 1 || ntiles * 10 < slots * 9;
 }
 
 // number of forcing columns (the row length of prcp / tmax / tmin)
@@ -1193,7 +1208,7 @@ static void fill_column_args(pws_handle* h, ColumnArgs& a, int ndays, const doub
   a.state = h->d_state;
   a.prcp = d_prcp; a.tmax = d_tmax; a.tmin = d_tmin;
   a.fstride = fstride;
-  a.fperiod = h->forcing_period;
+  a.fperiod = (uint32_t)h->forcing_period;
   // TMA bulk copies need 16-byte aligned rows of a multiple of 16 bytes
   // (an odd row is copied with one padding element, which must exist: fstride > nhru);
   // with a forcing period a CTA's row may wrap once: both pieces must stay aligned
@@ -1216,13 +1231,45 @@ static void fill_column_args(pws_handle* h, ColumnArgs& a, int ndays, const doub
   a.hru_lat = h->nseg > 0 ? h->d_hru_lat[slot] : nullptr;
   a.viol = want_viol ? h->d_viol[slot] : nullptr;
   a.err = h->d_err;
-  a.tile0 = 0;
   a.ntiles = 0;
+  a.hru_base = 0;
   for (int v = 0; v < PWS_N_HRU_VARS; ++v) {
     const int sl = h->slot_hru[v];
     const int64_t esz = names().hru_var_kind[v] == 0 ? 8 : 4;
     a.off[v] = sl < 0 ? -1 : (int64_t)sl * a.ostride * esz;
   }
+}
+
+// The arguments of a launch over the HRUs [h0, h0 + n) of the domain: every
+// per-HRU pointer advanced by h0, P.nhru = the HRUs of the range that exist.
+// With `offset_forcings` false (a forcing period) the forcing pointers stay and
+// the kernel is told where the range starts (hru_base).
+static void lane_view(ColumnArgs& a, int64_t h0, int64_t n, bool tiled, int H, bool offset_forcings) {
+  HruParams& P = a.P;
+#define X(nm) P.nm += h0;
+  PWS_HRU_F64_PARAMS(X)
+  PWS_MON_F64_PARAMS(X)
+  PWS_HRU_F64_DERIVED(X)
+  PWS_HRU_I32_PARAMS(X)
+  PWS_MON_I32_PARAMS(X)
+#undef X
+  P.tmax_allsnow_c += h0;
+  P.soltab_potsw += h0;
+  P.soltab_horad_potsw += h0;
+  P.nhru = std::min<int64_t>(P.nhru - h0, n);
+  a.state += h0;
+  if (offset_forcings) {
+    a.prcp += h0; a.tmax += h0; a.tmin += h0;
+  }
+  a.hru_base = (uint32_t)h0;
+  if (tiled) {  // [day][tile][variable][H]: the range's first tile
+    if (a.out_f64) a.out_f64 += (h0 / H) * a.n_f64 * H;
+    if (a.out_i32) a.out_i32 += (h0 / H) * a.n_i32 * H;
+  } else {
+    if (a.out_f64) a.out_f64 += h0;
+    if (a.out_i32) a.out_i32 += h0;
+  }
+  if (a.hru_lat) a.hru_lat += h0;
 }
 
 // Enqueue one block of days (forcings / outputs are device pointers; what the
@@ -1274,21 +1321,29 @@ static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const d
   const int H = column_hrus(h);
   const int ntiles = (int)((h->nhru + H - 1) / H);
   const int lanes = column_lanes(h, ntiles, H);
+  const bool overlap = overlap_routing(h, ntiles, H, lanes);
   a.ntiles = ntiles;
-#define PWS_LAUNCH_COLUMN(MODE, HH, GRID, ST)                                                    \
+#define PWS_LAUNCH_COLUMN_P(MODE, HH, PER, GRID, ST)                                             \
   do {                                                                                           \
-    if (!h->smem_attr_set[(MODE) * 2 + ((HH) == 128)]) {                                         \
-      PWS_CUDA(h, cudaFuncSetAttribute(k_hru_column<MODE, HH>,                                   \
+    const int key_ = ((MODE) * 2 + ((HH) == 128)) * 2 + (PER);                                   \
+    if (!h->smem_attr_set[key_]) {                                                               \
+      PWS_CUDA(h, cudaFuncSetAttribute(k_hru_column<MODE, HH, PER>,                              \
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,              \
                                        (int)column_smem_bytes(HH)));                             \
       /* no more shared memory than the CTAs of one SM need: the rest is L1 */                   \
-      PWS_CUDA(h, cudaFuncSetAttribute(k_hru_column<MODE, HH>,                                   \
+      PWS_CUDA(h, cudaFuncSetAttribute(k_hru_column<MODE, HH, PER>,                              \
                                        cudaFuncAttributePreferredSharedMemoryCarveout,           \
                                        column_carveout_pct(HH)));                                \
-      h->smem_attr_set[(MODE) * 2 + ((HH) == 128)] = true;                                       \
+      h->smem_attr_set[key_] = true;                                                             \
     }                                                                                            \
-    k_hru_column<MODE, HH><<<(GRID), 2 * (HH), column_smem_bytes(HH), (ST)>>>(a);                \
+    k_hru_column<MODE, HH, PER><<<(GRID), 2 * (HH), column_smem_bytes(HH), (ST)>>>(al);          \
   } while (0)
+#define PWS_LAUNCH_COLUMN(MODE, HH, GRID, ST)                                                    \
+  do {                                                                                           \
+    if (period) PWS_LAUNCH_COLUMN_P(MODE, HH, true, GRID, ST);                                   \
+    else PWS_LAUNCH_COLUMN_P(MODE, HH, false, GRID, ST);                                         \
+  } while (0)
+  const bool period = h->forcing_period > 0;
   for (int g = 0; g < lanes; ++g) {
     const int t0 = (int)((int64_t)ntiles * g / lanes), t1 = (int)((int64_t)ntiles * (g + 1) / lanes);
     if (t1 <= t0) {
@@ -1297,8 +1352,9 @@ static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const d
     }
     cudaStream_t st = h->s_lane[g];
     PWS_CUDA(h, cudaStreamWaitEvent(st, h->ev_prep[p], 0));
-    if (!h->overlap_routing) PWS_CUDA(h, cudaStreamWaitEvent(st, h->ev_block[prev], 0));
-    a.tile0 = t0;
+    if (!overlap) PWS_CUDA(h, cudaStreamWaitEvent(st, h->ev_block[prev], 0));
+    ColumnArgs al = a;  // the lane's view: a sub-domain starting at its first HRU
+    lane_view(al, (int64_t)t0 * H, (int64_t)(t1 - t0) * H, mode == SINK_TILED, H, !period);
     const unsigned grid = (unsigned)(t1 - t0);
     cudaEvent_t e0 = new_event(h), e1 = new_event(h);
     mark_base(h, st);
@@ -1321,6 +1377,7 @@ static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const d
     PWS_CUDA(h, cudaEventRecord(h->ev_lane[p][g], st));
     PWS_CUDA(h, cudaStreamWaitEvent(h->s_route, h->ev_lane[p][g], 0));
   }
+#undef PWS_LAUNCH_COLUMN_P
 #undef PWS_LAUNCH_COLUMN
   h->last_col_blocks++;
   // (the routing of block b-1 precedes this block's on s_route: the segment

@@ -137,11 +137,18 @@ struct ColumnArgs {
   // > 0: the forcing arrays are [ndays][fperiod] and HRU i reads column i mod
   // fperiod (a parameter ensemble over one base domain, member-major: every
   // member sees the same weather, examples/05_parameter_ensemble.ipynb)
-  int64_t fperiod;
+  uint32_t fperiod;         // (32-bit: a 64-bit remainder is a subroutine call inside the day loop)
   int use_tma;              // forcing rows are 16-byte aligned: stage them with cp.async.bulk
-  // this launch covers CTA tiles [tile0, tile0 + gridDim.x) of the domain's
-  // ntiles (a launch per lane, see enqueue_block in pws_b200.cu)
-  int tile0, ntiles;
+  // A launch covers a contiguous range of the domain's CTA tiles (a launch per
+  // lane, see enqueue_block in pws_b200.cu): every pointer above and below is
+  // advanced to the range's first HRU on the host and P.nhru counts the HRUs of
+  // the range, so the kernel indexes from 0 as if the range were the domain
+  // (an offset added to blockIdx.x in the kernel cost 8 bytes of spills and 56
+  // instructions).  ntiles = tiles of the WHOLE domain (the day stride of the
+  // tiled layout); hru_base = domain index of the range's first HRU, only read
+  // by the forcing-period variant.
+  int ntiles;
+  uint32_t hru_base;
   const int4* cal;          // [ndays] (doy, dowy, month, dom), device
   int ndays;
   double* out_f64;          // [ndays][n_f64][ostride]
@@ -382,7 +389,10 @@ struct LowerStateMixed {
 // parameters, which doubles the number of resident warps for the same
 // register file and shared memory, and each warp walks only its half of the
 // code.
-template <int kMode, int H>
+// kPeriod: the forcing arrays are [ndays][fperiod] (shared-forcing ensembles); a
+// separate instantiation because the wrap-around addressing costs the plain
+// kernel 16 bytes of spills and 120 instructions even when it is not taken.
+template <int kMode, int H, bool kPeriod = false>
 __global__ void __launch_bounds__(2 * H, (2 * H <= 256) ? 512 / (2 * H) : 1)
 k_hru_column(const __grid_constant__ ColumnArgs a) {
   // setmaxnreg acts on whole warpgroups (4 warps): each half must be a multiple of one
@@ -392,7 +402,7 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
   const int tid = threadIdx.x;
   const bool upper = tid < H;  // warpgroup-uniform
   const int r = upper ? tid : tid - H;
-  const int64_t tile = (int64_t)blockIdx.x + a.tile0;
+  const int64_t tile = (int64_t)blockIdx.x;
   const int64_t i = tile * H + r;
   const bool live = i < a.P.nhru;
   const int64_t ii = live ? i : a.P.nhru - 1;  // dead lanes shadow the last HRU, never store
@@ -498,33 +508,32 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
     // mbarrier; otherwise every thread prefetches its own values
     // into registers.
     const bool tma = a.use_tma != 0;
-    // Everything the copies need is recomputed from the kernel arguments inside
-    // tma_issue (one thread, once a day): a value kept across the day loop would
-    // cost every thread of the group a register, and this kernel spills.
+    const int64_t hru0 = tile * H;
+    // an odd tail is copied with the padding element behind it (see fill_column_args)
+    const int64_t row_n = (a.P.nhru - hru0) < H ? (a.P.nhru - hru0) : H;
+    const uint32_t row_bytes = (uint32_t)(((row_n + 1) & ~(int64_t)1) * 8);
+    // forcing column of the CTA's first HRU; with a forcing period the CTA's row
+    // may wrap around the end of the period once (fill_column_args only allows
+    // TMA for an even period >= H, so both pieces stay 16-byte aligned)
+    const uint32_t fcol0 = kPeriod ? (a.hru_base + (uint32_t)hru0) % a.fperiod : (uint32_t)hru0;
+    const uint32_t head_bytes =
+        (kPeriod && fcol0 + (uint32_t)row_n > a.fperiod) ? (a.fperiod - fcol0) * 8u : row_bytes;
     auto tma_issue = [&](int d) {  // one thread
-      const int64_t hru0 = ((int64_t)blockIdx.x + a.tile0) * H;
-      // an odd tail is copied with the padding element behind it (see fill_column_args)
-      const int64_t row_n = (a.P.nhru - hru0) < H ? (a.P.nhru - hru0) : H;
-      const uint32_t row_bytes = (uint32_t)(((row_n + 1) & ~(int64_t)1) * 8);
-      // forcing column of the CTA's first HRU; with a forcing period the CTA's row
-      // may wrap around the end of the period once (fill_column_args only allows
-      // TMA for an even period >= H, so both pieces stay 16-byte aligned)
-      const int64_t fcol0 = a.fperiod > 0 ? hru0 % a.fperiod : hru0;
-      const uint32_t head_bytes =
-          (a.fperiod > 0 && fcol0 + row_n > a.fperiod) ? (uint32_t)((a.fperiod - fcol0) * 8) : row_bytes;
       const uint32_t bar = mbar0;
       const uint32_t dst = smem_u32(sF);
       const int doy = a.cal[d].x;
-      const int64_t fo = (int64_t)d * a.fstride;
-      const int64_t so = (int64_t)(doy - 1) * a.P.stride + hru0;
+      const int64_t fo = (int64_t)d * a.fstride + fcol0;
+      const int64_t so = (int64_t)(doy - 1) * S + hru0;
       mbar_expect_tx(bar, kForcRows * row_bytes + 16u);
       tma_bulk_g2s(smem_u32(sCal + 4 * (d & 1)), a.cal + d, 16u, bar);
-      const double* const rows[3] = {a.prcp + fo, a.tmax + fo, a.tmin + fo};
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        tma_bulk_g2s(dst + k * H * 8, rows[k] + fcol0, head_bytes, bar);
-        if (head_bytes != row_bytes)
-          tma_bulk_g2s(dst + k * H * 8 + head_bytes, rows[k], row_bytes - head_bytes, bar);
+      tma_bulk_g2s(dst + 0 * H * 8, a.prcp + fo, head_bytes, bar);
+      tma_bulk_g2s(dst + 1 * H * 8, a.tmax + fo, head_bytes, bar);
+      tma_bulk_g2s(dst + 2 * H * 8, a.tmin + fo, head_bytes, bar);
+      if (kPeriod && head_bytes != row_bytes) {  // the rest of the row starts the period again
+        const int64_t f0 = (int64_t)d * a.fstride;
+        tma_bulk_g2s(dst + 0 * H * 8 + head_bytes, a.prcp + f0, row_bytes - head_bytes, bar);
+        tma_bulk_g2s(dst + 1 * H * 8 + head_bytes, a.tmax + f0, row_bytes - head_bytes, bar);
+        tma_bulk_g2s(dst + 2 * H * 8 + head_bytes, a.tmin + f0, row_bytes - head_bytes, bar);
       }
       tma_bulk_g2s(dst + 3 * H * 8, a.P.soltab_potsw + so, row_bytes, bar);
       tma_bulk_g2s(dst + 4 * H * 8, a.P.soltab_horad_potsw + so, row_bytes, bar);
@@ -542,7 +551,7 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
     } else {
       const int4 c = a.cal[0];
       nxt.doy = c.x; nxt.dowy = c.y; nxt.month = c.z; nxt.dom = c.w;
-      const int64_t fcol = a.fperiod > 0 ? ii % a.fperiod : ii;
+      const uint32_t fcol = kPeriod ? (a.hru_base + (uint32_t)ii) % a.fperiod : (uint32_t)ii;
       nxt.prcp = __ldcs(a.prcp + fcol);
       nxt.tmax = __ldcs(a.tmax + fcol);
       nxt.tmin = __ldcs(a.tmin + fcol);
@@ -570,7 +579,8 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
         in.cal = reinterpret_cast<const int*>(a.cal + d);
         if (d + 1 < a.ndays) {
           const int4 c = a.cal[d + 1];
-          const int64_t fo = (int64_t)(d + 1) * a.fstride + (a.fperiod > 0 ? ii % a.fperiod : ii);
+          const int64_t fo = (int64_t)(d + 1) * a.fstride +
+                             (kPeriod ? (a.hru_base + (uint32_t)ii) % a.fperiod : (uint32_t)ii);
           nxt.doy = c.x; nxt.dowy = c.y; nxt.month = c.z; nxt.dom = c.w;
           nxt.prcp = __ldcs(a.prcp + fo);
           nxt.tmax = __ldcs(a.tmax + fo);
@@ -774,7 +784,7 @@ k_hru_column_ov(const __grid_constant__ OvArgs a) {
     const int4 c = a.c.cal[d];
     DayIn in;
     in.doy = c.x; in.dowy = c.y; in.month = c.z; in.dom = c.w;
-    const int64_t fo = (int64_t)d * a.c.fstride + (a.c.fperiod > 0 ? ii % a.c.fperiod : ii);
+    const int64_t fo = (int64_t)d * a.c.fstride + (a.c.fperiod > 0 ? (uint32_t)ii % a.c.fperiod : (uint32_t)ii);
     in.prcp = a.c.prcp[fo];
     in.tmax = a.c.tmax[fo];
     in.tmin = a.c.tmin[fo];

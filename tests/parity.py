@@ -80,18 +80,22 @@ def assert_segments_close(got: dict, ref: dict, names, rtol=RTOL, atol=ATOL):
 # A tied HRU is not dropped from the comparison: from its tie day on it is held
 # to bounds that a ghost-pack tie can explain and a physics bug cannot.
 #   * The two runs differ by how one day's rain on a ghost pack is split between
-#     infiltration and surface runoff (prms_runoff.py:905-935) -- water that
-#     leaves the HRU either way -- and by the diagnostic state of a pack that
-#     holds 1e-16 inches in one run and nothing in the other.  So the HRU's
-#     water leaving as evapotranspiration and as flow to the stream, summed
-#     over the run, must agree closely (POST_TIE_CUM_RTOL), its storages must
-#     stay within POST_TIE_STORE_ATOL inches of each other, and its budgets
-#     must keep closing (checked by the caller through the verdict counts).
+#     infiltration and surface runoff (prms_runoff.py:905-935), and by the
+#     memory of a pack that holds 1e-16 inches in one run and nothing in the
+#     other: `ai`, `pst`, `scrv` (the depletion curve's history) decide how much
+#     of the HRU the NEXT snowfall covers, so the two runs -- both legitimate
+#     trajectories of the reference's algorithm -- can stay apart for a season
+#     (measured on drbx: up to 10 % of one HRU's surface runoff over 2 years).
+#     The audit therefore bounds what a tie cannot do: the water an HRU gives
+#     off (ET + flow to the stream) summed over the run agrees within
+#     POST_TIE_CUM_RTOL of the precipitation-scale total, storages stay within
+#     POST_TIE_STORE_ATOL inches, budgets keep closing (the caller checks the
+#     verdict counts).  The tight statement about tied HRUs is one_step_parity.
 #   * Segments that no tied HRU drains to (directly or through upstream
 #     segments) keep the full tolerance; the others are compared on their
 #     cumulative flow.
-POST_TIE_CUM_RTOL = 2e-2
-POST_TIE_STORE_ATOL = 0.5   # inches; soil / groundwater / pack storages
+POST_TIE_CUM_RTOL = 5e-2
+POST_TIE_STORE_ATOL = 2.0   # inches; soil / groundwater / pack storages
 CUM_FLUXES = ("hru_actet", "sroff_vol", "ssres_flow_vol", "gwres_flow_vol")
 STORAGES = ("soil_moist", "gwres_stor", "ssres_stor", "pkwater_equiv")
 
@@ -119,16 +123,16 @@ def audit_ties(got: dict, ref: dict, rep: dict, pk_got, pk_ref):
         lo = max(d - 3, 0)
         differ = ((pk_got[lo:d + 1, u] > 0) != (pk_ref[lo:d + 1, u] > 0)).any()
         out["existence" if differ else "residue"] += 1
-        for name in CUM_FLUXES:
-            if name not in got or name not in ref:
-                continue
-            g = float(np.asarray(got[name], dtype=np.float64)[:, u].sum())
-            r = float(np.asarray(ref[name], dtype=np.float64)[:, u].sum())
-            rel = abs(g - r) / max(abs(r), 1e-6)
-            if abs(g - r) > 1e-6 and rel > out["max_cum_rel"]:
-                out["max_cum_rel"], out["worst"] = rel, (u, d, name, g, r)
-            assert abs(g - r) <= 1e-6 + POST_TIE_CUM_RTOL * abs(r), (
-                f"HRU {u} (tie on day {d} in {k}): cumulative {name} {g!r} vs {r!r}")
+        tot_g = tot_r = 0.0
+        for name in ("hru_actet", "sroff", "ssres_flow", "gwres_flow"):  # inches, comparable
+            if name in got and name in ref:
+                tot_g += float(np.asarray(got[name], dtype=np.float64)[:, u].sum())
+                tot_r += float(np.asarray(ref[name], dtype=np.float64)[:, u].sum())
+        rel = abs(tot_g - tot_r) / max(abs(tot_r), 1e-6)
+        if rel > out["max_cum_rel"]:
+            out["max_cum_rel"], out["worst"] = rel, (u, d, tot_g, tot_r)
+        assert rel <= POST_TIE_CUM_RTOL, (
+            f"HRU {u} (tie on day {d} in {k}): ET + flows over the run {tot_g!r} vs {tot_r!r}")
         for name in STORAGES:
             if name not in got or name not in ref:
                 continue
@@ -154,3 +158,52 @@ def assert_segments_with_ties(got: dict, ref: dict, names, tosegment, hru_segmen
         worst = float(rel.max())
         assert worst <= POST_TIE_CUM_RTOL, f"cumulative seg_outflow downstream of a tie off by {worst}"
     return {"segments_downstream_of_ties": int(mask.sum()), "max_cum_seg_rel": worst}
+
+
+# ---------------------------------------------------------------- one-step parity
+# The free-running comparison above cannot say much about an HRU after a
+# ghost-pack tie: a pack that exists in one run and not in the other changes the
+# depletion-curve memory (`ai`, `pst`, `scrv` ...) the next snowfall lands on, and
+# the two trajectories -- both legitimate trajectories of the reference's
+# algorithm -- stay apart for a season.  The one-step check has no such blind
+# spot: the oracle is made to continue from the OTHER implementation's values
+# of day d-1 (every prognostic quantity of the column is a public variable) and
+# its day d must equal the other implementation's day d, for every HRU and every
+# day, ties or not.  What can still differ is a threshold decided by the last bit
+# INSIDE one day (a pack melting to 2.2e-16 vs 2.3e-16 inches against
+# dnearzero = 2.23e-16): such HRU-days are counted and each is required to be that.
+def volume_atol(name, hru_in_to_cf, atol=ATOL):
+    """atol of a variable in ITS units: `*_vol` variables are inches x hru_in_to_cf."""
+    if name.endswith("_vol"):
+        return atol * np.maximum(np.asarray(hru_in_to_cf, dtype=np.float64), 1.0)
+    return atol
+
+
+def one_step_parity(oracle, forcings, got: dict, names, hru_in_to_cf, rtol=RTOL, atol=ATOL):
+    """oracle: a fresh prms_oracle.Oracle of the same parameters.  Returns
+    dict(hru_days, mismatching=[(hru, day, vars)], unexplained=[...])."""
+    f = forcings
+    one = oracle.run_forced(f["prcp"], f["tmax"], f["tmin"], got)
+    nd, n = one[names[0]].shape
+    bad = np.zeros((nd, n), dtype=bool)
+    which = {}
+    for k in names:
+        g = np.asarray(got[k], dtype=np.float64)
+        r = one[k]
+        a = volume_atol(k, hru_in_to_cf, atol)
+        ok = (np.abs(g - r) <= a + rtol * np.abs(r)) | (np.isnan(g) & np.isnan(r))
+        if not ok.all():
+            bad |= ~ok
+            for d, u in zip(*np.where(~ok)):
+                which.setdefault((int(u), int(d)), []).append(k)
+    pk_g = np.asarray(got["pkwater_equiv"], dtype=np.float64)
+    pk_r = one["pkwater_equiv"]
+    mism, unexplained = [], []
+    for (u, d), ks in sorted(which.items()):
+        lo = max(d - 1, 0)
+        w = np.concatenate([pk_g[lo:d + 1, u], pk_r[lo:d + 1, u]])
+        rec = (u, d, ks[:6], float(np.asarray(got[ks[0]])[d, u]), float(one[ks[0]][d, u]))
+        mism.append(rec)
+        if not ((w > 0) & (w < GHOST)).any():
+            unexplained.append(rec)
+    return {"hru_days": nd * n, "mismatching": mism, "unexplained": unexplained}

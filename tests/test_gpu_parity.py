@@ -121,6 +121,19 @@ def test_full_chain_parity(scen, drb, drbx):
         seg = parity.assert_segments_with_ties(got, ref, po.SEG_VARS, p["tosegment"], p["hru_segment"],
                                                [t[0] for t in rep["ties"]])
         print(f"segments {scen}: {seg}")
+    # One-step parity: the oracle continued from the GPU's own previous day must give the
+    # GPU's day, for EVERY HRU-day -- tied HRUs included (tests/parity.py)
+    ff = {k: v[:nd] for k, v in f.items()}
+    osp = parity.one_step_parity(po.Oracle(p, start=start), ff, got, po.HRU_VARS, p["hru_in_to_cf"])
+    print(f"one-step parity {scen}: {len(osp['mismatching'])} of {osp['hru_days']} HRU-days differ "
+          f"(all on a pack at the dnearzero threshold): {osp['mismatching'][:4]}")
+    assert osp["unexplained"] == [], osp["unexplained"][:5]
+    assert len(osp["mismatching"]) <= 1e-4 * osp["hru_days"]
+    # ... and PRMSChannel given the GPU's own lateral inflows: every segment, every day,
+    # whatever the ties upstream did (routing has no transcendental: bit for bit)
+    ch = po.Oracle(p, start=start).run_channel(np.asarray(got["seg_lateral_inflow"]))
+    for k in po.SEG_VARS:
+        np.testing.assert_array_equal(np.asarray(got[k]), ch[k], err_msg=k)
     if scen == "drb":
         assert viol.sum() == 0  # all six budgets close, as in the reference
         # against the reference's own numbers
