@@ -274,90 +274,104 @@ def _ref_worker(args):
     """One process of the numpy / numba reference arm: the unmodified
     pywatershed package from oracle/_ref, drb_2yr through pws.Model."""
     calc_method, ndays, warm = args
+    os.dup2(2, 1)  # the reference prints ("... jit compiling with numba"): stdout is for the JSON line
     sys.path.insert(0, str(ROOT / "oracle"))
     import ref_pack
 
     return ref_pack.time_drb(calc_method, ndays, warm)
 
 
-def run_reference_python(args, spec, calc_method):
-    """--impl reference --ref numpy|numba: the UNMODIFIED reference package
-    (packed into oracle/_ref by oracle/pack_ref.py at build()), drb_2yr NHM chain
-    through pws.Model (asv_benchmarks/benchmarks/prms.py:146-171), one process
-    per host core as examples/05_parameter_ensemble.ipynb does, netCDF output
-    off; numba's JIT warm-up (a 5-day run) is outside the timed region."""
+def reference_python_rate(calc_method, ndays, nproc, passes=1, warmup=0):
+    """HRU-days/s of the UNMODIFIED reference package (oracle/_ref), drb_2yr NHM
+    chain through pws.Model (asv_benchmarks/benchmarks/prms.py:146-171), one
+    process per host core as examples/05_parameter_ensemble.ipynb does, netCDF
+    output off; the first 5 days of every model (numba's JIT) are untimed.
+    Spawned processes: the caller may hold a CUDA context."""
+    import multiprocessing as mp
     from concurrent.futures import ProcessPoolExecutor
 
+    rates, res = [], None
+    for it in range(warmup + passes):
+        with ProcessPoolExecutor(max_workers=nproc, mp_context=mp.get_context("spawn")) as ex:
+            res = list(ex.map(_ref_worker, [(calc_method, ndays, True)] * nproc))
+        wall = max(r["seconds"] for r in res)  # processes run side by side: the slowest one
+        if it >= warmup:
+            rates.append((nproc * NB_HRU * res[0]["ndays"], wall))
+    units = sum(u for u, _ in rates)
+    dt = sum(d for _, d in rates)
+    one = res[0]
+    sample = (f"{nproc} processes x drb_2yr (765 HRUs, 456 segments) x {one['ndays']} days (after 5 untimed "
+              f"days: numba's JIT), pywatershed {one.get('version', '?')} calc_method={calc_method}, "
+              f"pws.Model.run, no output; one process: {one['seconds']:.1f} s; last-day "
+              f"sum(seg_outflow)={one['sum_seg_outflow']:.6f}")
+    return units / dt, dt / max(len(rates), 1), sample
+
+
+def reference_available():
     sys.path.insert(0, str(ROOT / "oracle"))
     import ref_pack
 
-    if not ref_pack.available():
+    return ref_pack.available()
+
+
+def run_reference(args, spec):
+    """--impl reference: the reference's CPU implementation on all host cores.
+    Default path: the real reference package from oracle/_ref with its fastest
+    calc_method (numba) when it was packed, else the C port; the line also
+    carries one bounded pass of the other CPU paths (`other_cpu_paths`)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import scenarios
+
+    ncores = os.cpu_count() or 1
+    nthreads = max(1, min(ncores, 64))
+    have_ref = reference_available()
+    ref = args.ref or ("numba" if have_ref else "port")
+    if ref in ("numpy", "numba") and not have_ref:
         print(json.dumps({"impl": "reference", "unavailable":
                           "oracle/_ref (the packed reference package) is missing: run build() where "
                           "/root/reference exists"}))
         return
-    ncores = os.cpu_count() or 1
-    nproc = max(1, min(ncores, 64))
-    ndays = 731
-    rates = []
-    for it in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        with ProcessPoolExecutor(max_workers=nproc) as ex:
-            res = list(ex.map(_ref_worker, [(calc_method, ndays, calc_method == "numba")] * nproc))
-        wall = max(r["seconds"] for r in res)  # processes run side by side: the slowest one
-        if it >= args.warmup:
-            rates.append((nproc * NB_HRU * ndays, wall))
-        del t0
-    units = sum(u for u, _ in rates)
-    dt = sum(d for _, d in rates)
-    value = units / dt
-    one = res[0]
-    sample = (f"{nproc} processes x drb_2yr (765 HRUs, 456 segments) x {ndays} days, pywatershed "
-              f"{one.get('version', '?')} calc_method={calc_method}, pws.Model.run, no output; "
-              f"one process: {one['seconds']:.1f} s; last-day sum(seg_outflow)={one['sum_seg_outflow']:.6f}")
-    print(json.dumps({
+    p0, f0, start = scenarios.load_drb()
+
+    def port_rate(passes, warmup):
+        ndays = min(spec["ndays"], 3653)
+        rates = []
+        for it in range(warmup + passes):
+            r, units, dt = cpu_oracle_rate(p0, f0, start, 1, ndays, nthreads)
+            if it >= warmup:
+                rates.append((units, dt))
+        units, dt = sum(u for u, _ in rates), sum(d for _, d in rates)
+        return units / dt, dt / len(rates), (
+            f"{nthreads} threads x 1 DRB tile (765 HRUs, 456 segments) x {ndays} days per step, C "
+            "restatement oracle/prms_oracle.c, full chain incl. routing and budgets, segment outputs kept")
+
+    if ref == "port":
+        value, step_s, sample = port_rate(args.steps, args.warmup)
+        kind = "port"
+    else:
+        value, step_s, sample = reference_python_rate(ref, 731 if ref == "numba" else 200, nthreads,
+                                                      args.steps, args.warmup)
+        kind = "reference"
+    others = {}
+    for other in ("port", "numba", "numpy"):
+        if other == ref or (other != "port" and not have_ref):
+            continue
+        if other == "port":
+            v, _, smp = port_rate(1, 0)
+        else:
+            v, _, smp = reference_python_rate(other, 731 if other == "numba" else 120, nthreads)
+        others[other] = {"value": v, "unit": UNIT, "cores": nthreads, "sample": smp}
+    line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(len(rates), 1),
+        "warmup": args.warmup, "ms_per_step": 1e3 * step_s,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "impl": "reference",
         "config": {"workload": spec["label"], "note": "bounded sample of the workload on host cores: "
-                   "independent drb_2yr basins, one per core"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nproc, "kind": "reference", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
-
-
-def run_reference(args, spec):
-    """--impl reference: the CPU implementation on all host cores."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    if args.ref in ("numpy", "numba"):
-        return run_reference_python(args, spec, args.ref)
-    import scenarios
-
-    p0, f0, start = scenarios.load_drb()
-    ncores = os.cpu_count() or 1
-    nthreads = max(1, min(ncores, 64))
-    tiles_per_thread = 1
-    ndays = min(spec["ndays"], 3653)
-    rates = []
-    for it in range(args.warmup + args.steps):
-        r, units, dt = cpu_oracle_rate(p0, f0, start, tiles_per_thread, ndays, nthreads)
-        if it >= args.warmup:
-            rates.append((units, dt))
-    units = sum(u for u, _ in rates)
-    dt = sum(d for _, d in rates)
-    value = units / dt
-    sample = (f"{nthreads} threads x {tiles_per_thread} DRB tile(s) (765 HRUs, 456 segments) x "
-              f"{ndays} days per step, full chain incl. routing and budgets, segment outputs kept")
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(len(rates), 1),
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "impl": "reference",
-        "config": {"workload": spec["label"], "note": "bounded sample of the workload on host cores"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
+                   "independent drb_2yr basins, one per core", "cpu_path": ref},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": kind, "sample": sample},
+        "other_cpu_paths": others,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -664,7 +678,9 @@ def main():
     ap.add_argument("--outputs", default="full")
     ap.add_argument("--block-days", type=int, default=256)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--ref", choices=("port", "numpy", "numba"), default="port")
+    ap.add_argument("--ref", choices=("port", "numpy", "numba"), default=None,
+                    help="--impl reference: which CPU path is the line's value (default: numba from "
+                         "oracle/_ref when packed, else the C port)")
     ap.add_argument("--no-e2e", action="store_true")
     # measured on the CONUS workload (float32 forcings, HRU-days/s): 64 -> 3.50e9, 128 -> 3.53e9,
     # 256 -> 3.88e9, 384 -> 3.76e9, 512 -> 3.57e9 (profiles/r01_e2e_block_days.jsonl)
@@ -916,6 +932,15 @@ def main():
         cpu = {"value": r, "unit": UNIT, "cores": nthreads, "kind": "port",
                "sample": f"{nthreads} threads x 1 DRB tile x {min(nd, 3653)} days "
                          f"({units:.3g} HRU-days, {dt:.1f} s), C oracle, full chain + routing + budgets"}
+        if reference_available() and not args.no_extras:
+            # north_star: the reference's numpy and numba paths on this box's cores, same run
+            for cm, ndr in (("numba", 731), ("numpy", 120)):
+                try:
+                    v, _, smp = reference_python_rate(cm, ndr, nthreads)
+                    cpu["reference_" + cm] = {"value": v, "unit": UNIT, "cores": nthreads,
+                                              "kind": "reference", "sample": smp}
+                except Exception as exc:
+                    cpu["reference_" + cm] = {"error": f"{type(exc).__name__}: {exc}"}
 
     kinfo = None
     line = {

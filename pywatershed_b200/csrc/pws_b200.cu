@@ -1178,7 +1178,11 @@ static int column_lanes(pws_handle* h, int ntiles, int H) {
   const int slots = nsm * (H == 128 ? 2 : 1);  // CTAs resident at a time
   if (ntiles <= slots) return 1;               // one wave: nothing to smooth
   const int tail = ntiles % slots;             // CTAs of the last wave
-  if (tail == 0 || tail * 5 >= slots * 4) return 1;  // the last wave is (nearly) full
+  const int waves = (ntiles + slots - 1) / slots;
+  // SM-time the last wave leaves idle, as a share of the launch: lanes cost a few
+  // percent themselves (measured: 4 lanes on 2.58 waves 24.9 -> 23.9 ms, on 20.7
+  // waves 194 -> 199 ms), so they are for launches that lose more than that
+  if (tail == 0 || (slots - tail) * 12 < waves * slots) return 1;
   const int g = (ntiles + (2 * slots) / 3 - 1) / ((2 * slots) / 3);
   return std::max(1, std::min(g, pws_handle::kMaxLanes));
 }

@@ -12,8 +12,9 @@ ROOT = pl.Path(__file__).resolve().parent.parent
 
 
 def test_reference_arm_prints_one_json_line():
-    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1",
-                        "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--ref", "port",
+                        "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=900,
+                       cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, lines
@@ -28,6 +29,13 @@ def test_reference_arm_prints_one_json_line():
     assert d["e2e"] == {"value": d["value"], "unit": "HRU-days/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
+    # the other CPU paths ride along: the reference package's own numba / numpy when it was
+    # packed into oracle/_ref (this container), known answers included
+    if (ROOT / "oracle" / "_ref" / "pywatershed" / "__init__.py").exists():
+        for k in ("numba", "numpy"):
+            o = d["other_cpu_paths"][k]
+            assert o["value"] > 0 and "pywatershed" in o["sample"] and f"calc_method={k}" in o["sample"]
+        assert d["other_cpu_paths"]["numba"]["value"] > d["other_cpu_paths"]["numpy"]["value"]
 
 
 def test_gpu_arm_fails_loudly_without_a_gpu():
