@@ -171,6 +171,18 @@ int pws_run_host_inputs(pws_handle *h, int ndays, const int32_t *h_cal, int n_in
 int pws_run_channel_device(pws_handle *h, int ndays, const double *d_seg_lateral_inflow,
                            double *d_seg_out);
 
+/* PRMSEt (hydrology/prms_et.py:22-181), the bookkeeping process that turns the
+ * other processes' evaporative losses into hru_actet / unused_potet: inputs
+ * h_* [ndays][nhru] as PRMSEt.get_inputs() (:101-116), parameters [nhru]
+ * (:88-99), outputs [ndays][nhru] as get_variables() (:118-126).  Stateless,
+ * needs no handle; on failure pws_last_error(NULL) tells why. */
+int pws_et_host(int device, int ndays, int64_t nhru, const double *h_potet,
+                const double *h_hru_impervevap, const double *h_hru_intcpevap,
+                const double *h_snow_evap, const double *h_dprst_evap_hru,
+                const double *h_perv_actet, const double *h_hru_percent_imperv,
+                const double *h_dprst_frac, double *h_unused_potet,
+                double *h_hru_perv_actet, double *h_hru_actet);
+
 int pws_sync(pws_handle *h);
 
 /* Tiled result layout of pws_run_device / pws_run_host[_f32], chosen with

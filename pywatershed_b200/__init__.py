@@ -11,6 +11,7 @@ from .processes import (  # noqa: F401
     PRMSAtmosphere,
     PRMSCanopy,
     PRMSChannel,
+    PRMSEt,
     PRMSGroundwater,
     PRMSGroundwaterNoDprst,
     PRMSRunoff,
@@ -28,5 +29,5 @@ __all__ = [
     "PrmsParameters", "Process", "ConservativeProcess", "TimeseriesArray",
     "PRMSSolarGeometry", "PRMSAtmosphere", "PRMSCanopy", "PRMSSnow", "PRMSRunoff",
     "PRMSSoilzone", "PRMSGroundwater", "PRMSChannel", "PRMSRunoffNoDprst", "PRMSSoilzoneNoDprst",
-    "PRMSGroundwaterNoDprst",
+    "PRMSGroundwaterNoDprst", "PRMSEt",
 ]

@@ -73,6 +73,7 @@ def lib():
         "pws_select_accumulations": (i32, [vp, i32, vp, i32, vp]),
         "pws_get_accumulations": (i32, [vp, vp, vp]),
         "pws_clear_accumulations": (i32, [vp]),
+        "pws_et_host": (i32, [i32, i32, i64] + [vp] * 11),
         "pws_n_seg_state": (i32, []),
         "pws_seg_state_name": (cp, [i32]),
         "pws_reset_state": (i32, [vp]),
@@ -97,5 +98,5 @@ EXPORTED_SYMBOLS = (
     "pws_timer_mark", "pws_timer_elapsed_ms", "pws_last_launches", "pws_reset_state",
     "pws_output_tile", "pws_run_host_f32", "pws_last_blocks", "pws_n_seg_state",
     "pws_seg_state_name", "pws_select_accumulations", "pws_get_accumulations",
-    "pws_clear_accumulations",
+    "pws_clear_accumulations", "pws_et_host",
 )

@@ -1924,6 +1924,52 @@ extern "C" int pws_set_state(pws_handle* h, const char* name, const double* in) 
   return 0;
 }
 
+// --------------------------------------------------------------- PRMSEt
+// hydrology/prms_et.py:22-181 for a block of days: six [ndays][nhru] inputs and
+// two [nhru] parameters in host memory -> the three public variables.  No
+// handle: PRMSEt has no state and belongs to no NHM model (the reference keeps
+// it as "an intermediate class that should not exist in the future", :13-20).
+extern "C" int pws_et_host(int device, int ndays, int64_t nhru, const double* h_potet,
+                           const double* h_hru_impervevap, const double* h_hru_intcpevap,
+                           const double* h_snow_evap, const double* h_dprst_evap_hru,
+                           const double* h_perv_actet, const double* h_hru_percent_imperv,
+                           const double* h_dprst_frac, double* h_unused_potet,
+                           double* h_hru_perv_actet, double* h_hru_actet) {
+  if (ndays <= 0 || nhru <= 0) return 0;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+    g_create_error = "pws_et_host: no CUDA device; libpwsb200 has no CPU path";
+    return 1;
+  }
+  cudaSetDevice(device);
+  const size_t n = (size_t)ndays * (size_t)nhru, nb = n * sizeof(double), pb = (size_t)nhru * sizeof(double);
+  double* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, 9 * nb + 2 * pb);
+  if (e == cudaSuccess) {
+    const double* src[6] = {h_potet, h_hru_impervevap, h_hru_intcpevap, h_snow_evap, h_dprst_evap_hru,
+                            h_perv_actet};
+    for (int k = 0; k < 6 && e == cudaSuccess; ++k) e = cudaMemcpy(d + k * n, src[k], nb, cudaMemcpyHostToDevice);
+    double* dp = d + 9 * n;
+    if (e == cudaSuccess) e = cudaMemcpy(dp, h_hru_percent_imperv, pb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dp + nhru, h_dprst_frac, pb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+      const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16);
+      k_prms_et<<<grid, 256>>>((int64_t)n, nhru, d, d + n, d + 2 * n, d + 3 * n, d + 4 * n, d + 5 * n, dp,
+                               dp + nhru, d + 6 * n, d + 7 * n, d + 8 * n);
+      e = cudaGetLastError();
+    }
+    double* dst[3] = {h_unused_potet, h_hru_perv_actet, h_hru_actet};
+    for (int k = 0; k < 3 && e == cudaSuccess; ++k)
+      e = cudaMemcpy(dst[k], d + (6 + k) * n, nb, cudaMemcpyDeviceToHost);
+  }
+  cudaFree(d);
+  if (e != cudaSuccess) {
+    g_create_error = std::string("pws_et_host: ") + cudaGetErrorString(e);
+    return 1;
+  }
+  return 0;
+}
+
 // --------------------------------------------------------------- instrumentation
 extern "C" int64_t pws_launch_count(pws_handle* h) { return h->launches; }
 

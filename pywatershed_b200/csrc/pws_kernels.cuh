@@ -1165,6 +1165,33 @@ k_accumulate(const AccSlots slots, const double* __restrict__ buf, int64_t day_s
   acc[(int64_t)k * acc_stride + i] = a;
 }
 
+// PRMSEt (hydrology/prms_et.py:140-181): the bookkeeping process that sums the
+// evaporative losses of the other processes.  Elementwise over [ndays][nhru], in
+// the reference's order of operations (frac_perv :145, available_potet :160-181,
+// hru_actet :157).
+__global__ void __launch_bounds__(256)
+k_prms_et(int64_t n_total, int64_t nhru, const double* __restrict__ potet,
+          const double* __restrict__ hru_impervevap, const double* __restrict__ hru_intcpevap,
+          const double* __restrict__ snow_evap, const double* __restrict__ dprst_evap_hru,
+          const double* __restrict__ perv_actet, const double* __restrict__ hru_percent_imperv,
+          const double* __restrict__ dprst_frac, double* __restrict__ unused_potet,
+          double* __restrict__ hru_perv_actet, double* __restrict__ hru_actet) {
+  for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < n_total; j += (int64_t)gridDim.x * 256) {
+    const int64_t i = j % nhru;
+    const double frac_perv = 1.0 - hru_percent_imperv[i] - dprst_frac[i];
+    const double hpa = perv_actet[j] * frac_perv;
+    double loss = hru_intcpevap[j];
+    loss += snow_evap[j];
+    loss += dprst_evap_hru[j];
+    loss += hru_impervevap[j];
+    loss += hpa;
+    const double unused = fmax(potet[j] - loss, 0.0);
+    hru_perv_actet[j] = hpa;
+    unused_potet[j] = unused;
+    hru_actet[j] = potet[j] - unused;
+  }
+}
+
 // Global-basis channel budget (prms_channel.py:115,165-174; budget.py:388-416):
 // one CTA per day, fixed-order tree reduction so the sums are reproducible.
 __global__ void __launch_bounds__(256)

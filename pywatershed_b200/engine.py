@@ -116,6 +116,38 @@ _FILL_I32 = {"cov_type": 1, "hru_type": 1, "hru_deplcrv": 1, "soil_type": 1, "tr
              "transp_end": 13, "melt_force": 140, "melt_look": 90}
 
 
+class _PinnedPool:
+    """Page-locked host buffers for drained results.  Pinning memory costs about
+    a second per GB (cudaHostAlloc), more than a 2-year CONUS-scale run takes, so
+    buffers are handed back when an Engine closes and re-used by the next one
+    (a model that is re-created per scenario, a service that keeps running).
+    A buffer belongs to one Engine at a time."""
+
+    CAP = 6 << 30  # bytes kept for re-use
+
+    def __init__(self):
+        self.free = {}
+        self.held = 0
+
+    def take(self, nbytes: int):
+        lst = self.free.get(nbytes)
+        if lst:
+            self.held -= nbytes
+            return lst.pop()
+        import torch
+
+        return torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
+
+    def give(self, buf):
+        n = int(buf.numel())
+        if self.held + n <= self.CAP:
+            self.free.setdefault(n, []).append(buf)
+            self.held += n
+
+
+_PINNED = _PinnedPool()
+
+
 class TiledBlock(dict):
     """Results of a run in the tiled layout ([day][tile][variable][tile_units],
     include/pws_b200.h: pws_output_tile): a dict that un-tiles an HRU variable
@@ -300,6 +332,9 @@ class Engine:
         if getattr(self, "h", None):
             self.L.pws_destroy(self.h)
             self.h = None
+            for buf in self.__dict__.pop("_pinned", []):
+                _PINNED.give(buf)
+            self.__dict__.pop("_out_caches", None)
 
     def __del__(self):
         try:
@@ -394,13 +429,14 @@ class Engine:
             of, oi, os_ = cache[1]
         else:
             if pinned_outputs:
-                import torch
-
                 def alloc(shape, dt):
-                    return torch.empty(shape, dtype=dt).pin_memory().numpy()
-                of = alloc(shapes[0], torch.float64)
-                oi = alloc(shapes[1], torch.int32)
-                os_ = alloc(shapes[2], torch.float64)
+                    n = int(np.prod(shape)) * np.dtype(dt).itemsize
+                    buf = _PINNED.take(n)
+                    self.__dict__.setdefault("_pinned", []).append(buf)
+                    return buf.numpy()[:n].view(dt).reshape(shape)
+                of = alloc(shapes[0], np.float64)
+                oi = alloc(shapes[1], np.int32)
+                os_ = alloc(shapes[2], np.float64)
             else:
                 of = np.empty(shapes[0])
                 oi = np.empty(shapes[1], dtype=np.int32)
@@ -547,3 +583,39 @@ class Engine:
         r, l, b = C.c_int(), C.c_int(), C.c_int()
         self._check(self.L.pws_column_kernel_info(self.h, C.byref(r), C.byref(l), C.byref(b)))
         return {"regs": r.value, "local_bytes": l.value, "max_blocks_per_sm": b.value}
+
+
+class EtEngine:
+    """PRMSEt on the GPU (pws_et_host): stateless, driven in blocks of days like
+    an Engine so the Model treats it the same way."""
+
+    INPUTS = ("potet", "hru_impervevap", "hru_intcpevap", "snow_evap", "dprst_evap_hru", "perv_actet")
+    VARS = ("unused_potet", "hru_perv_actet", "hru_actet")
+
+    def __init__(self, params: dict, start, device: int = 0):
+        self.L = _lib.lib()
+        self.reg = Registry.get()
+        self.device = device
+        self.imperv = np.ascontiguousarray(params["hru_percent_imperv"], dtype=np.float64)
+        self.dprst = np.ascontiguousarray(params["dprst_frac"], dtype=np.float64)
+        self.nhru, self.nseg, self.day = int(self.imperv.shape[0]), 0, 0
+        self.start = np.datetime64(start, "D")
+        self.sel_seg = []
+
+    def run(self, inputs: dict):
+        arrs = [np.ascontiguousarray(inputs[k], dtype=np.float64) for k in self.INPUTS]
+        nd = arrs[0].shape[0]
+        for k, a in zip(self.INPUTS, arrs):
+            if a.shape != (nd, self.nhru):
+                raise ValueError(f"input '{k}' must be [ndays, nhru] = {(nd, self.nhru)}, got {a.shape}")
+        outs = [np.empty((nd, self.nhru)) for _ in self.VARS]
+        rc = self.L.pws_et_host(self.device, nd, self.nhru, *[a.ctypes.data for a in arrs],
+                                self.imperv.ctypes.data, self.dprst.ctypes.data,
+                                *[o.ctypes.data for o in outs])
+        if rc != 0:
+            raise _lib.PwsLibraryError(self.L.pws_last_error(None).decode())
+        self.day += nd
+        return dict(zip(self.VARS, outs))
+
+    def close(self):
+        pass

@@ -23,7 +23,7 @@ import numpy as np
 from . import processes as P
 from ._process_meta import PROCESS_META, VARIABLE_META
 from .control import Control
-from .engine import Engine, Registry
+from .engine import Engine, EtEngine, Registry
 from .parameters import Parameters, PrmsParameters, as_param_dict
 from .prms_files import read_cbh
 
@@ -134,6 +134,12 @@ class Model:
         slots = [P.base_name(n) for n in order]
         if len(set(slots)) != len(slots):
             raise ValueError(f"two variants of the same process in one model: {order}")
+        if "PRMSEt" in slots:
+            if slots != ["PRMSEt"]:
+                # its variables hru_actet / unused_potet are PRMSSoilzone's too: the two do
+                # not live in one model (no NHM configuration of the reference uses PRMSEt)
+                raise NotImplementedError("PRMSEt runs on its own, fed from arrays or files")
+            return "et"
         has_col = [n in slots for n in COLUMN_CHAIN]
         if all(has_col):
             return "chain+channel" if "PRMSChannel" in order else "chain"
@@ -298,6 +304,17 @@ class Model:
         adj = sz_mode != "no"
         start = self.control.start_time
         dev = int(self.control.options.get("device", 0) or 0)
+        if self._mode == "et":
+            self._engine = EtEngine(pd, start, device=dev)
+            self._forcings = {k: self._load_input(k, self._engine.nhru) for k in EtEngine.INPUTS}
+            self._engine_kwargs = {}
+            self._full_selection = (list(EtEngine.VARS), [])
+            self._selection_is_full = True
+            self._block_days_user = self.block_days
+            if self.block_days is None:
+                self.block_days = self._days_for(EtEngine.INPUTS + EtEngine.VARS, [], 366)
+            self.block_days = int(self.block_days)
+            return
         if self._mode == "channel":
             # the HRU column is not run; its tables get stand-in values
             kw = dict(device=dev, channel=True, fill_missing=True)
@@ -316,7 +333,8 @@ class Model:
                       dprst_flag=bool(dprst), fill_missing=not dprst)
             self._engine = Engine(pd, start, **kw)
             nh = self._engine.nhru
-            self._forcings = {k: self._load_input(k, nh, keep_f32=True) for k in FORCINGS}
+            self._forcings = {k: self._page_locked(self._load_input(k, nh, keep_f32=True))
+                              for k in FORCINGS}
         self._engine_kwargs = kw
         reg = self._engine.reg
         hv = list(reg.hru_vars) if self._mode != "channel" else [
@@ -354,6 +372,27 @@ class Model:
             th, tsg = self._budget_terms()
             self._engine.select_accumulations(th, tsg)
             self._set_device_acc(False)
+
+    def _page_locked(self, arr):
+        """The forcings of a run in page-locked memory (from the pool of
+        engine._PINNED, handed back when the model goes away): pws_run_host then
+        uploads them in place instead of staging every block through pinned slots."""
+        from .engine import _PINNED
+
+        buf = _PINNED.take(arr.nbytes)
+        self.__dict__.setdefault("_pinned", []).append(buf)
+        out = buf.numpy()[:arr.nbytes].view(arr.dtype).reshape(arr.shape)
+        np.copyto(out, arr)
+        return out
+
+    def __del__(self):
+        try:
+            from .engine import _PINNED
+
+            for buf in self.__dict__.pop("_pinned", []):
+                _PINNED.give(buf)
+        except Exception:
+            pass
 
     def _days_for(self, hv, sv, cap):
         """Days per host-side block so that one block of these variables is ~2 GB."""
@@ -439,7 +478,7 @@ class Model:
         return [v for v in hv_full if v in want], [v for v in sv if v in want]
 
     def _select(self, full: bool):
-        if self._mode == "channel" or full == self._selection_is_full:
+        if self._mode in ("channel", "et") or full == self._selection_is_full:
             return
         hv, sv = self._full_selection if full else self._reduced_selection()
         self._engine.select_outputs(hv, sv)
@@ -452,7 +491,9 @@ class Model:
             raise RuntimeError(f"engine is at day {eng.day}, block starts at {t0}")
         self._select(full=not reduced)
         self._set_device_acc(device_acc)
-        if self._mode == "channel":
+        if self._mode == "et":
+            blk, viol = eng.run({k: v[t0:t0 + n] for k, v in self._forcings.items()}), None
+        elif self._mode == "channel":
             blk, viol = self._channel_block(t0, n)
         elif self._mode == "sub":
             eng.set_block_days(min(n, 16))
@@ -556,9 +597,12 @@ class Model:
         if limit is not None:
             remaining = min(remaining, limit)
         n_full = min(self.block_days, remaining)
-        if not fast or self._mode in ("channel", "sub"):
+        if not fast or self._mode in ("channel", "sub", "et"):
             self._compute_block(it, n_full)
             return
+        # after run() a caller sees ONE day, the last (the process arrays hold a day):
+        # only that day is drained with every variable
+        n_full = 1
         if remaining <= n_full:
             self._compute_block(it, remaining, reduced=False, device_acc=True)
             return

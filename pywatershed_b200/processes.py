@@ -145,7 +145,11 @@ class Process:
             raise ValueError(f"{self.name}: parameters missing: {sorted(missing)}")
         self._param_dict = merged
         self.params = parameters
-        self.nhru = int(np.asarray(merged["hru_area"]).shape[0]) if "hru_area" in merged else 0
+        self.nhru = 0
+        for key in ("hru_area", "hru_percent_imperv", "nhm_id"):
+            if key in merged:
+                self.nhru = int(np.asarray(merged[key]).shape[0])
+                break
         self.nsegment = int(np.asarray(merged["tosegment"]).shape[0]) if "tosegment" in merged else 0
         self._input_variables_dict = {k: kwargs.get(k) for k in meta["inputs"]}
         self._vars = {}
@@ -442,6 +446,22 @@ class PRMSChannel(ConservativeProcess):
         super().__init__(control, discretization, parameters, **_kw(locals()))
 
 
+class PRMSEt(Process):
+    """hydrology/prms_et.py:22-48.  The reference builds this process's Budget
+    with keyword arguments its Budget class no longer has (:57-76), so only
+    budget_type=None / "defer" can be constructed there; here any budget_type is
+    accepted and no budget is kept."""
+
+    def __init__(self, control, discretization, parameters, potet=None, hru_impervevap=None,
+                 hru_intcpevap=None, snow_evap=None, dprst_evap_hru=None, perv_actet=None,
+                 verbose: bool = False, budget_type="defer"):
+        super().__init__(control, discretization, parameters, potet=potet,
+                         hru_impervevap=hru_impervevap, hru_intcpevap=hru_intcpevap,
+                         snow_evap=snow_evap, dprst_evap_hru=dprst_evap_hru, perv_actet=perv_actet,
+                         verbose=verbose)
+        self.budget = None
+
+
 class PRMSRunoffNoDprst(PRMSRunoff):
     """hydrology/prms_runoff_no_dprst.py:68-91: PRMSRunoff without depression storage"""
 
@@ -547,7 +567,8 @@ def _kw(loc):
 
 PROCESS_CLASSES = {c.__name__: c for c in (
     PRMSSolarGeometry, PRMSAtmosphere, PRMSCanopy, PRMSSnow, PRMSRunoff, PRMSSoilzone,
-    PRMSGroundwater, PRMSChannel, PRMSRunoffNoDprst, PRMSSoilzoneNoDprst, PRMSGroundwaterNoDprst)}
+    PRMSGroundwater, PRMSChannel, PRMSRunoffNoDprst, PRMSSoilzoneNoDprst, PRMSGroundwaterNoDprst,
+    PRMSEt)}
 
 # base/model.py:15-28
 PROCESS_ORDER_NHM = ("PRMSSolarGeometry", "PRMSAtmosphere", "PRMSCanopy", "PRMSSnow",

@@ -91,3 +91,38 @@ def test_process_stepped_on_its_own(drb, full):
         np.testing.assert_allclose(gw["gwres_stor"], full["gwres_stor"][it], rtol=1e-9, atol=1e-10)
         np.testing.assert_allclose(gw.gwres_flow_vol, full["gwres_flow_vol"][it], rtol=1e-9, atol=1e-10)
     assert gw.budget._zero_sum
+
+
+def test_prms_et_alone(drb):
+    """PRMSEt (hydrology/prms_et.py:22-181) driven on its own from the other
+    processes' outputs, as autotest/test_prms_et.py:29-110 does: bit-identical to
+    the reference's arithmetic restated in numpy (there is no transcendental in
+    it), and its hru_actet agrees with PRMSSoilzone's own within the tolerance of
+    the reference's test (:99-107)."""
+    import pywatershed_b200 as pwsb
+    from test_gpu_model import _control, _parameters
+
+    p, f, start = drb
+    nd = 120
+    o = po.Oracle(p, start=start)
+    names = list(pwsb.PRMSEt.get_inputs()) + ["hru_actet", "unused_potet"]
+    ref, _ = o.run(f["prcp"][:nd], f["tmax"][:nd], f["tmin"][:nd], names, ())
+    control = _control(start, nd, block_days=50)
+    et = pwsb.PRMSEt(control, None, _parameters(p), budget_type=None,
+                     **{k: ref[k] for k in pwsb.PRMSEt.get_inputs()})
+    frac_perv = 1.0 - p["hru_percent_imperv"] - p["dprst_frac"]
+    for it in range(nd):
+        control.advance()
+        et.advance()
+        et.calculate(1.0)
+        hpa = ref["perv_actet"][it] * frac_perv
+        loss = ref["hru_intcpevap"][it].copy()
+        for k in ("snow_evap", "dprst_evap_hru", "hru_impervevap"):
+            loss += ref[k][it]
+        loss += hpa
+        unused = np.maximum(ref["potet"][it] - loss, 0.0)
+        np.testing.assert_array_equal(et["hru_perv_actet"], hpa)
+        np.testing.assert_array_equal(et["unused_potet"], unused)
+        np.testing.assert_array_equal(et["hru_actet"], ref["potet"][it] - unused)
+        np.testing.assert_allclose(et["hru_actet"], ref["hru_actet"][it], rtol=1e-6, atol=1e-9)
+    assert id(et["hru_actet"]) == id(et.hru_actet)

@@ -171,7 +171,7 @@ def test_descriptors_equal_the_reference_classes():
     import pywatershed_b200 as pwsb
 
     pws = rh.import_reference()
-    for name in rh.NHM_PROCESS_NAMES:
+    for name in rh.NHM_PROCESS_NAMES + ("PRMSEt",):
         ref, mine = getattr(pws, name), getattr(pwsb, name)
         assert tuple(ref.get_inputs()) == tuple(mine.get_inputs()), name
         assert tuple(ref.get_variables()) == tuple(mine.get_variables()), name
@@ -388,9 +388,12 @@ def test_model_from_yaml_builds(drb, tmp_path):
     assert m.control.n_times == 10
     np.testing.assert_array_equal(m._param_dict["soil_moist_max"], p["soil_moist_max"])
     np.testing.assert_array_equal(m._param_dict["tmax_cbh_adj"], p["tmax_cbh_adj"])
-    (tmp_path / "bad.yaml").write_text("control: control.yaml\nx:\n  class: PRMSEt\n  parameters: myparam.param\n")
+    (tmp_path / "bad.yaml").write_text("control: control.yaml\nx:\n  class: StarfitFlowNode\n  parameters: myparam.param\n")
     with pytest.raises(NotImplementedError):
         pwsb.Model.from_yaml(tmp_path / "bad.yaml")
+    # PRMSEt is a process of its own (hydrology/prms_et.py), not mixed into the NHM chain
+    (tmp_path / "et.yaml").write_text("control: control.yaml\nx:\n  class: PRMSEt\n  parameters: myparam.param\n")
+    assert pwsb.Model.from_yaml(tmp_path / "et.yaml")._mode == "et"
 
 
 # ---------------------------------------------------------------- netCDF-4 (HDF5) inputs
