@@ -328,13 +328,19 @@ class Engine:
         self.L.pws_last_blocks(self.h, C.byref(a), C.byref(b))
         return a.value, b.value
 
+    def release_buffers(self):
+        """Hand the page-locked result buffers back to the pool (the arrays
+        returned by earlier run_host(pinned_outputs=True) calls must not be used
+        any more)."""
+        for buf in self.__dict__.pop("_pinned", []):
+            _PINNED.give(buf)
+        self.__dict__.pop("_out_caches", None)
+
     def close(self):
         if getattr(self, "h", None):
             self.L.pws_destroy(self.h)
             self.h = None
-            for buf in self.__dict__.pop("_pinned", []):
-                _PINNED.give(buf)
-            self.__dict__.pop("_out_caches", None)
+            self.release_buffers()
 
     def __del__(self):
         try:

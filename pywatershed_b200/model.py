@@ -667,6 +667,11 @@ class Model:
             self._netcdf.close()
             self._netcdf = None
         self._netcdf_initialized = False
+        # the process arrays hold copies of the last day: the drained block and its
+        # page-locked buffers can go back to the pool (a later step computes a new block)
+        self._block, self._block_n = None, 0
+        if self._engine is not None and hasattr(self._engine, "release_buffers"):
+            self._engine.release_buffers()
 
     # ---------------------------------------------------------------- netcdf
     def initialize_netcdf(self, output_dir=None, separate_files: bool = None,
