@@ -184,15 +184,30 @@ class Oracle:
             rc = self.L.orc_set_hru_var(self.h, HRU_VARS.index(k), a.ctypes.data)
             assert rc == 0, k
 
-    def run_forced(self, prcp, tmax, tmin, series: dict):
+    def current(self, var):
+        """Current value of a public HRU variable ([nhru] copy)."""
+        p = self.L.orc_hru_var(self.h, HRU_VARS.index(var))
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(self.nhru,)).copy()
+
+    def run_forced(self, prcp, tmax, tmin, series: dict, columns=None):
         """One-step parity: day d is computed from `series`' day d-1 (every
         public HRU variable overwritten before the step) instead of from the
-        oracle's own day d-1.  Returns var -> [ndays, nhru]."""
+        oracle's own day d-1.  With `columns` (HRU indices) the series are
+        [ndays, len(columns)] and only those HRUs are overwritten.  Returns
+        var -> [ndays, nhru]."""
         nd = np.asarray(prcp).shape[0]
         out = {k: np.empty((nd, self.nhru)) for k in HRU_VARS}
         for d in range(nd):
             if d > 0:
-                self.set_hru_vars({k: np.asarray(series[k][d - 1], dtype=np.float64) for k in HRU_VARS})
+                if columns is None:
+                    vals = {k: np.asarray(series[k][d - 1], dtype=np.float64) for k in HRU_VARS}
+                else:
+                    vals = {}
+                    for k in HRU_VARS:
+                        v = self.current(k)
+                        v[columns] = np.asarray(series[k][d - 1], dtype=np.float64)
+                        vals[k] = v
+                self.set_hru_vars(vals)
             res, _ = self.run(prcp[d:d + 1], tmax[d:d + 1], tmin[d:d + 1], HRU_VARS, (), budgets=False)
             for k in HRU_VARS:
                 out[k][d] = res[k][0]

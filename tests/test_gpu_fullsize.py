@@ -66,3 +66,28 @@ def test_conus_tiles_equal_single_tile_runs():
         np.testing.assert_array_equal(bs[:, 0], got["seg_outflow"], err_msg=f"tile {t} seg_outflow")
         assert v1.sum() == 0
         one.close()
+        if t != 71:
+            continue
+        # ... and that tile, in its shifted climate, against the ORACLE over the whole
+        # 3,653 days: every variable free-running (ties audited), every HRU-day one
+        # step at a time, and the routing given the GPU's own lateral inflows
+        import parity
+        import prms_oracle as po
+
+        allv = Engine(p0, start, device=0)
+        allv.select_outputs(allv.reg.hru_vars, allv.reg.seg_vars)
+        g_all, _ = allv.run_host(ft["prcp"], ft["tmax"], ft["tmin"])
+        allv.close()
+        ref, _ = po.Oracle(p0, start=start).run(ft["prcp"], ft["tmax"], ft["tmin"], po.HRU_VARS, po.SEG_VARS)
+        rep = parity.compare_columns(g_all, ref, po.HRU_VARS, g_all["pkwater_equiv"], ref["pkwater_equiv"])
+        assert rep["mismatches"] == [], rep["mismatches"][:5]
+        assert len(rep["ties"]) <= 0.1 * 765
+        osp = parity.one_step_parity(po.Oracle(p0, start=start), ft, g_all, po.HRU_VARS, p0["hru_in_to_cf"])
+        print(f"tile {t} of the CONUS domain, 3,653 days vs the oracle: {len(rep['ties'])} free-running ties, "
+              f"one-step {len(osp['mismatching'])} of {osp['hru_days']} HRU-days differ")
+        assert osp["unexplained"] == [], osp["unexplained"][:5]
+        assert len(osp["mismatching"]) <= 1e-4 * osp["hru_days"]
+        ch = po.Oracle(p0, start=start).run_channel(np.asarray(g_all["seg_lateral_inflow"]))
+        for k in po.SEG_VARS:
+            np.testing.assert_array_equal(np.asarray(g_all[k]), ch[k], err_msg=k)
+        np.testing.assert_array_equal(np.asarray(g_all["seg_outflow"]), got["seg_outflow"])

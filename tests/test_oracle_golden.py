@@ -192,3 +192,38 @@ def test_hru1_41_years_match_reference(hru1):
                                    np.asarray(g["ts_" + k], dtype=np.float64),
                                    rtol=1e-9, atol=1e-10, err_msg=k)
     assert viol.sum() == 0
+
+
+def test_drbx_tie_free_sums_and_tied_hrus_one_step(drbx, drbx_run):
+    """tests/golden/drbx_ties.npz (oracle/gen_golden_drbx_ties.py, from the
+    unmodified reference): (a) the checksum of checksums on drbx -- per-day sums
+    of every variable over the HRUs that no ghost-pack tie touches; (b) the HRUs a
+    tie does touch, where the free-running comparison stops being meaningful,
+    checked ONE STEP at a time: the oracle continued from the reference's own
+    previous day must give the reference's day (tests/parity.py)."""
+    p, f, start = drbx
+    _, res, _ = drbx_run
+    g = np.load(scenarios.GOLDEN / "drbx_ties.npz")
+    tied = g["tied_hrus"]
+    nd = res["pkwater_equiv"].shape[0]
+    clean = np.ones(res["pkwater_equiv"].shape[1], dtype=bool)
+    clean[tied] = False
+    # the tie set is what this oracle build sees too
+    rep = parity.compare_columns({k: res[k][:, tied] for k in po.HRU_VARS},
+                                 {k: g["tied_ts_" + k] for k in po.HRU_VARS}, po.HRU_VARS,
+                                 res["pkwater_equiv"][:, tied], g["tied_ts_pkwater_equiv"])
+    assert rep["mismatches"] == [] and 1 <= len(rep["ties"]) <= len(tied)
+    for k in po.HRU_VARS:
+        np.testing.assert_allclose(res[k][:, clean].sum(axis=1), g["sumc_" + k], rtol=1e-9, atol=1e-7,
+                                   equal_nan=True, err_msg=k)
+    o = po.Oracle(p, start=start)
+    one = o.run_forced(f["prcp"][:nd], f["tmax"][:nd], f["tmin"][:nd],
+                       {k: g["tied_ts_" + k] for k in po.HRU_VARS}, columns=tied)
+    nbad = 0
+    for k in po.HRU_VARS:
+        a = parity.volume_atol(k, np.asarray(p["hru_in_to_cf"])[tied])
+        r = g["tied_ts_" + k]
+        ok = (np.abs(one[k][:, tied] - r) <= a + 1e-9 * np.abs(r)) | (np.isnan(r) & np.isnan(one[k][:, tied]))
+        nbad += int((~ok).any(axis=None))
+        assert ok.all(), (k, np.argwhere(~ok)[:3], one[k][:, tied][~ok][:3], r[~ok][:3])
+    assert nbad == 0
