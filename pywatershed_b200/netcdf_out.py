@@ -42,6 +42,22 @@ def nc4_module():
 _nc4 = nc4_module()
 
 _NC_TYPES = {"float64": "f8", "int32": "i4", "bool": "i4", "int64": "i8"}
+# netCDF4.default_fillvals, what the reference passes as fill_value (utils/netcdf_utils.py:607)
+_FILL = {"f8": 9.969209968386869e36, "f4": 9.969209968386869e36, "i4": -2147483647, "i8": -9223372036854775806}
+
+
+def _var_attrs(name):
+    """Every scalar metadata item of a variable (the reference copies all of
+    them, utils/netcdf_utils.py:613-616: desc, units, type, var_category, ...;
+    `dims` is a list and is written as the reference's netCDF4 would, an array of
+    strings is not representable in the classic format, so it is joined)."""
+    m = VARIABLE_META.get(name, {})
+    out = {}
+    for k, v in m.items():
+        if isinstance(v, dict):
+            continue
+        out[k] = " ".join(v) if isinstance(v, (list, tuple)) else v
+    return out
 _THREAD_BYTES = 64 << 20  # blocks at least this large are written by one thread per file
 
 
@@ -61,20 +77,19 @@ class _File:
             ds.setncattr("process class", process_name)
             ds.createDimension(time_name, n_doy)
             ds.createDimension(coord_name, len(coord_vals))
-            tv = ds.createVariable(time_name, "f4", (time_name,))
-            if time_name == "time":
-                tv.units = "days since 1970-01-01 00:00:00"
+            # utils/netcdf_utils.py:474-489: time is f4 "days since ...", doy is i4 "Day of year"
+            tv = ds.createVariable(time_name, "f4" if time_name == "time" else "i4", (time_name,))
+            tv.units = "days since 1970-01-01 00:00:00" if time_name == "time" else "Day of year"
             cv = ds.createVariable(coord_name, "i4", (coord_name,))
             cv[:] = np.asarray(coord_vals, dtype=np.int32)
             self.v = {}
             for name in self.vars:
                 m = VARIABLE_META.get(name, {})
-                v = ds.createVariable(name, _NC_TYPES[m.get("type", "float64")],
-                                      (time_name, coord_name), zlib=True, complevel=4,
-                                      chunksizes=(1, len(coord_vals)))
-                for k in ("desc", "units"):
-                    if k in m:
-                        v.setncattr(k, m[k])
+                kind = _NC_TYPES[m.get("type", "float64")]
+                v = ds.createVariable(name, kind, (time_name, coord_name), fill_value=_FILL[kind],
+                                      zlib=True, complevel=4, chunksizes=(1, len(coord_vals)))
+                for k, val in _var_attrs(name).items():
+                    v.setncattr(k, val)
                 self.v[name] = v
         else:
             from .cdf_out import Cdf2Writer
@@ -84,16 +99,19 @@ class _File:
             ds.setncattr("process class", process_name)
             ds.createDimension(time_name, n_doy)
             ds.createDimension(coord_name, len(coord_vals))
-            tatts = {"units": "days since 1970-01-01 00:00:00"} if time_name == "time" else {}
-            tv = ds.createVariable(time_name, "f4", (time_name,), **tatts)
+            tatts = {"units": "days since 1970-01-01 00:00:00" if time_name == "time" else "Day of year"}
+            tv = ds.createVariable(time_name, "f4" if time_name == "time" else "i4", (time_name,), **tatts)
             self._cv = ds.createVariable(coord_name, "i4", (coord_name,))
             self._coord_vals = np.asarray(coord_vals, dtype=np.int32)
             self.v = {}
             for name in self.vars:
                 m = VARIABLE_META.get(name, {})
-                atts = {k: m[k] for k in ("desc", "units") if k in m}
-                self.v[name] = ds.createVariable(name, _NC_TYPES[m.get("type", "float64")],
-                                                 (time_name, coord_name), **atts)
+                kind = _NC_TYPES[m.get("type", "float64")]
+                atts = _var_attrs(name)
+                atts["_FillValue"] = np.array(_FILL[kind], dtype={"f8": np.float64, "i4": np.int32}[kind])
+                self.v[name] = ds.createVariable(name, kind, (time_name, coord_name))
+                for k, val in atts.items():  # ("dims" is a metadata key: not a keyword argument)
+                    self.v[name].setncattr(k, val)
         self.ds = ds
         self.tv = tv
 
@@ -106,8 +124,9 @@ class _File:
 
     def write(self, t0, t1, times_days, blocks: dict):
         """Rows [t0, t1) of the time axis and of the variables in `blocks`."""
+        tdt = np.float32 if self.time_name == "time" else np.int32
         if _nc4 is not None:
-            self.tv[t0:t1] = np.asarray(times_days, dtype=np.float32)
+            self.tv[t0:t1] = np.asarray(times_days, dtype=tdt)
             for name, arr in blocks.items():
                 if name in self.v:
                     a = np.asarray(arr)
@@ -118,7 +137,7 @@ class _File:
         if self._coord_vals is not None:  # the header is complete now: variables are all declared
             self._cv[:] = self._coord_vals
             self._coord_vals = None
-        arrays = {self.time_name: np.asarray(times_days, dtype=np.float32)}
+        arrays = {self.time_name: np.asarray(times_days, dtype=tdt)}
         arrays.update({k: np.asarray(a) for k, a in blocks.items() if k in self.v})
         if self.ds.rec_dim is not None:
             self.ds.write_record_block(t0, t1, arrays)  # one contiguous write when all variables are there

@@ -662,6 +662,21 @@ def test_model_netcdf_output_on_a_stubbed_block(drb, tmp_path, monkeypatch):
         np.testing.assert_array_equal(a, np.asarray(blk[v]).astype(a.dtype), err_msg=v)
     a, dims = read("soltab_potsw.nc", "soltab_potsw")
     assert dims == ("doy", "nhm_id") and a.shape == (366, nhru)
+    # coordinate and attribute conventions of the reference's NetCdfWrite
+    # (utils/netcdf_utils.py:474-489, 600-616): doy is i4 "Day of year", every scalar
+    # metadata item of a variable is an attribute, _FillValue is netCDF's default
+    with netcdf_file(str(tmp_path / "soltab_potsw.nc"), "r", mmap=False) as ds:
+        doy = ds.variables["doy"]
+        assert doy.data.dtype.kind == "i" and doy.units == b"Day of year"
+        np.testing.assert_array_equal(doy[:], np.arange(1, 367))
+        assert ds.variables["soltab_potsw"].units == b"Langleys"
+    with netcdf_file(str(tmp_path / "pkwater_equiv.nc"), "r", mmap=False) as ds:
+        v = ds.variables["pkwater_equiv"]
+        assert v.var_category == b"mass storage" and v.type == b"float64" and v.units == b"inches"
+        assert v._FillValue == pytest.approx(9.969209968386869e36)
+        assert ds.variables["time"].units == b"days since 1970-01-01 00:00:00"
+    with netcdf_file(str(tmp_path / "newsnow.nc"), "r", mmap=False) as ds:
+        assert ds.variables["newsnow"]._FillValue == -2147483647
     b = m.processes["PRMSSnow"].budget
     for comp, name in (("inputs", "inputs_sum"), ("outputs", "outputs_sum"),
                        ("storage_changes", "storage_changes_sum")):
