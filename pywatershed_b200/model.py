@@ -765,6 +765,63 @@ class Model:
                 b._itime_accumulated = it
         self._calculated_step = it
 
+    # ---------------------------------------------------------------- restart
+    def save_state(self, path=None) -> dict:
+        """A restart point at the model's current day: every prognostic value of
+        the chain (the union of the processes' get_restart_variables(),
+        prms_snow.py:269-293, PRMSChannel's outflow_ts / seg_inflow included) plus
+        the budget accumulations.  The reference declares restart but raises
+        "restart capability not implemented" (prms_soilzone.py:331); here
+        `Model.load_state()` on a freshly built model of the same control and
+        parameters continues the run bit for bit.  `path`: also write an .npz."""
+        self._ensure_engine()
+        if self._mode not in ("chain", "chain+channel"):
+            raise NotImplementedError("save_state needs the full NHM chain")
+        it = self.control.itime_step
+        if self._engine.day != it + 1:
+            raise RuntimeError(
+                f"save_state at a block boundary only: the control is at day {it}, the device at "
+                f"{self._engine.day - 1} (run(n_time_steps=...) ends on one; a model stepped day by day "
+                "computes ahead of the control)")
+        st = self._engine.save_state()
+        for name, proc in self.processes.items():
+            b = getattr(proc, "budget", None)
+            if b is None:
+                continue
+            for comp, terms in b.accumulations.items():
+                for v, a in terms.items():
+                    if a is not None:
+                        st[f"_acc/{name}/{comp}/{v}"] = np.asarray(a)
+        if path is not None:
+            np.savez(path, **st)
+        return st
+
+    def load_state(self, state):
+        """Continue from `save_state()`'s dict (or its .npz file)."""
+        if not isinstance(state, dict):
+            with np.load(state) as z:
+                state = {k: z[k] for k in z.files}
+        self._ensure_engine()
+        day = int(state["_day"])
+        self._engine.reset()  # zeroes the device-side accumulations
+        self._engine.load_state({k: v for k, v in state.items() if not k.startswith("_acc/")})
+        while self.control.itime_step < day - 1:
+            self.control.advance()
+        self._days_on_device = day
+        self._block, self._block_n = None, 0
+        self._device_acc_cache = (None, {})
+        for name, proc in self.processes.items():
+            b = getattr(proc, "budget", None)
+            if b is None:
+                continue
+            for comp in b.components:
+                for v in b.terms[comp]:
+                    key = f"_acc/{name}/{comp}/{v}"
+                    b._accumulations[comp][v] = np.array(state[key]) if key in state else None
+        if "PRMSAtmosphere" in self.processes:
+            for ts in self.processes["PRMSAtmosphere"]._vars.values():
+                ts.mark_stale()
+
     def _write_control(self, where):
         path = pl.Path(where) if not isinstance(where, bool) else pl.Path("control.yaml")
         import yaml
