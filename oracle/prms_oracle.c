@@ -77,6 +77,7 @@ struct Orc {
   int32_t *ch_order, *ch_tsi;
   double *ch_ts, *ch_c0, *ch_c1, *ch_c2, *ch_seg_inflow, *ch_seg_inflow0,
       *ch_inflow_ts, *ch_outflow_ts, *ch_seg_current_sum, *ch_up;
+  int fg_started; /* orc_run_flow_graph has zeroed the node states */
   int32_t *ch_outflow_mask;
   /* budget scratch */
   int64_t itime;
@@ -2391,5 +2392,117 @@ int orc_run_channel(Orc *o, int ndays, const double *seg_lateral_inflow,
       memcpy(seg_out + ((int64_t)t * n_seg_out + k) * nseg, o->s[seg_idx[k]],
              sizeof(double) * (size_t)nseg);
   }
+  return 0;
+}
+
+/* ====================================================================== */
+/* FlowGraph (base/flow_graph.py:576-657) over PRMSChannelFlowNode          */
+/* (hydrology/prms_channel_flow_graph.py:30-160, 367-414), PassThroughFlowNode */
+/* (hydrology/pass_through_flow_node.py:6-53) and ObsInFlowNode             */
+/* (hydrology/obsin_flow_node.py:8-82).  The nodes are this handle's        */
+/* segments (tosegment = to_graph_index + 1; the Muskingum coefficients of  */
+/* channel_init = PRMSChannelFlowNodeMaker._init_data :230-330); kind[j]:   */
+/* 0 Muskingum-Mann, 1 pass-through, 2 observed flow.  obs[t][j] is the day's */
+/* observation of an ObsIn node (negative = pass the inflow through).       */
+/* out: [ndays][7][nnodes] in get_init_values order (flow_graph.py:425-436): */
+/* outflows, node_upstream_inflows, node_outflows, node_storage_changes,    */
+/* node_storages, node_sink_source, node_negative_sink_source.              */
+/* ====================================================================== */
+int orc_run_flow_graph(Orc *o, int ndays, const double *inflows, const int32_t *kind,
+                       const double *obs, double *out) {
+  if (!o->inited) {
+    snprintf(o->err, sizeof o->err, "orc_run_flow_graph before orc_init");
+    return -1;
+  }
+  const int nn = o->nseg;
+  double *seg_inflow = o->ch_seg_inflow, *seg_inflow0 = o->ch_seg_inflow0;
+  double *inflow_ts = o->ch_inflow_ts, *outflow_ts = o->ch_outflow_ts;
+  double *up_acc = o->ch_seg_current_sum, *up = o->ch_up;
+  double *seg_outflow = dalloc(nn, 0.0), *sub = dalloc(nn, 0.0), *ss_sum = dalloc(nn, 0.0);
+  double *sink = dalloc(nn, 0.0);
+  if (!o->fg_started) { /* PRMSChannelFlowNode.__init__ :63-69: every node state starts at zero */
+    for (int j = 0; j < nn; ++j) {
+      seg_inflow[j] = 0.0;
+      seg_inflow0[j] = 0.0;
+      outflow_ts[j] = 0.0;
+      inflow_ts[j] = 0.0;
+    }
+    o->fg_started = 1;
+  }
+  for (int t = 0; t < ndays; ++t) {
+    const double *lat = inflows + (int64_t)t * nn;
+    const double *ob = obs ? obs + (int64_t)t * nn : NULL;
+    for (int j = 0; j < nn; ++j) {
+      /* FlowGraph._advance_variables -> node.advance() (:569-573) */
+      if (kind[j] == 0) seg_inflow0[j] = seg_inflow[j];
+      /* node.prepare_timestep() (:579-580) */
+      seg_inflow[j] = 0.0;  /* MM: _seg_inflow; pass-through: _accum_inflow */
+      seg_outflow[j] = kind[j] == 2 ? ob[j] : 0.0; /* ObsIn: _seg_outflow = the day's observation */
+      inflow_ts[j] = 0.0;
+      ss_sum[j] = 0.0;
+      sink[j] = 0.0;
+      up_acc[j] = 0.0;
+    }
+    for (int ihr = 0; ihr < 24; ++ihr) {
+      for (int j = 0; j < nn; ++j) up[j] = 0.0;
+      for (int k = 0; k < nn; ++k) {
+        const int j = o->ch_order[k];
+        if (kind[j] == 0) { /* _calculate_subtimestep_numpy :333-364 */
+          const double cur = lat[j] + up[j];
+          seg_inflow[j] += cur;
+          inflow_ts[j] += cur;
+          const int tsi = o->ch_tsi[j];
+          const int rem = (tsi < 0) ? 0 : (ihr + 1) % tsi;
+          if (rem == 0) {
+            inflow_ts[j] /= o->ch_ts[j];
+            if (tsi > 0)
+              outflow_ts[j] = inflow_ts[j] * o->ch_c0[j] + seg_inflow0[j] * o->ch_c1[j] +
+                              outflow_ts[j] * o->ch_c2[j];
+            else
+              outflow_ts[j] = inflow_ts[j];
+            seg_inflow0[j] = inflow_ts[j];
+            inflow_ts[j] = 0.0;
+          }
+          seg_outflow[j] += outflow_ts[j];
+          sub[j] = outflow_ts[j];
+        } else if (kind[j] == 1) { /* pass_through_flow_node.py:24-33 */
+          const double in = up[j] + lat[j];
+          seg_inflow[j] += in;
+          seg_outflow[j] = seg_inflow[j] / (double)(ihr + 1);
+          sub[j] = in;
+        } else { /* obsin_flow_node.py:43-57 */
+          const double in = up[j] + lat[j];
+          if (seg_outflow[j] >= 0.0) {
+            ss_sum[j] += seg_outflow[j] - in;
+          } else {
+            seg_outflow[j] = in;
+            ss_sum[j] += 0.0;
+          }
+          sink[j] = ss_sum[j] / (double)(ihr + 1);
+          sub[j] = seg_outflow[j];
+        }
+        const int to = o->tosegment[j] - 1;
+        if (to >= 0) up[to] += sub[j];
+      }
+      for (int j = 0; j < nn; ++j) up_acc[j] += up[j];
+    }
+    double *q = out + (int64_t)t * 7 * nn;
+    for (int j = 0; j < nn; ++j) {
+      double stor_change = 0.0;
+      if (kind[j] == 0) { /* finalize_timestep :107-111 */
+        seg_outflow[j] = seg_outflow[j] / 24.0;
+        seg_inflow[j] = seg_inflow[j] / 24.0;
+        stor_change = seg_inflow[j] - seg_outflow[j];
+      }
+      q[0 * nn + j] = o->ch_outflow_mask[j] ? seg_outflow[j] : 0.0;
+      q[1 * nn + j] = up_acc[j] / 24.0;
+      q[2 * nn + j] = seg_outflow[j];
+      q[3 * nn + j] = stor_change;
+      q[4 * nn + j] = NAN;
+      q[5 * nn + j] = sink[j];
+      q[6 * nn + j] = -1.0 * sink[j];
+    }
+  }
+  free(seg_outflow); free(sub); free(ss_sum); free(sink);
   return 0;
 }

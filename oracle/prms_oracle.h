@@ -183,6 +183,11 @@ int orc_run(Orc *o, int ndays, const int32_t *cal, const double *prcp,
 /* Channel alone: lateral inflows given per day [ndays][nseg] (config 5) */
 int orc_run_channel(Orc *o, int ndays, const double *seg_lateral_inflow,
                     int n_seg_out, const int32_t *seg_idx, double *seg_out);
+/* FlowGraph (base/flow_graph.py) over this handle's segments as nodes: kind[j]
+ * 0 PRMSChannelFlowNode, 1 PassThroughFlowNode, 2 ObsInFlowNode (obs[t][j]);
+ * out [ndays][7][nnodes] in FlowGraph.get_init_values order. */
+int orc_run_flow_graph(Orc *o, int ndays, const double *inflows, const int32_t *kind,
+                       const double *obs, double *out);
 
 /* current value of one public variable (pointer into oracle storage) */
 const double *orc_hru_var(Orc *o, int idx);

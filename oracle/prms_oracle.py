@@ -40,6 +40,9 @@ SEG_F8 = _macro_names("ORC_SEG_F8_PARAMS")
 SEG_I4 = _macro_names("ORC_SEG_I4_PARAMS")
 HRU_VARS = _macro_names("ORC_HRU_VARS")
 SEG_VARS = _macro_names("ORC_SEG_VARS")
+# FlowGraph.get_init_values order (base/flow_graph.py:425-436)
+FLOW_GRAPH_VARS = ["outflows", "node_upstream_inflows", "node_outflows", "node_storage_changes",
+                   "node_storages", "node_sink_source", "node_negative_sink_source"]
 SCALAR_F8 = ["albset_rna", "albset_rnm", "albset_sna", "albset_snm"]
 ALL_PARAM_NAMES = (
     HRU_F8 + HRU_I4 + MON_F8 + MON_I4 + SEG_F8 + SEG_I4 + SCALAR_F8
@@ -79,6 +82,8 @@ def lib(omp: bool = False):
             C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_run_channel.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                       C.c_void_p, C.c_void_p]
+        L.orc_run_flow_graph.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p]
         L.orc_hru_var.restype = C.c_void_p
         L.orc_hru_var.argtypes = [C.c_void_p, C.c_int]
         L.orc_set_hru_var.restype = C.c_int
@@ -221,6 +226,25 @@ class Oracle:
         self._check(self.L.orc_run_channel(self.h, nd, lat.ctypes.data, len(sidx),
                                            sidx.ctypes.data, sout.ctypes.data))
         return {v: sout[:, k, :] for k, v in enumerate(seg_vars)}
+
+    def run_flow_graph(self, inflows, kind, obs=None):
+        """FlowGraph over this oracle's segments as nodes (orc_run_flow_graph):
+        inflows [ndays, nnodes], kind [nnodes] (0 Muskingum-Mann, 1 pass-through,
+        2 observed flow), obs [ndays, nnodes] for the ObsIn nodes.  Returns
+        var -> [ndays, nnodes] for FlowGraph's seven variables."""
+        lat = np.ascontiguousarray(inflows, dtype=np.float64)
+        nd = lat.shape[0]
+        kind = np.ascontiguousarray(kind, dtype=np.int32)
+        if obs is None:
+            if (kind == 2).any():
+                raise ValueError("ObsIn nodes need obs")
+            obs = np.zeros((nd, self.nseg))
+        obs = np.ascontiguousarray(obs, dtype=np.float64)
+        assert lat.shape == obs.shape == (nd, self.nseg) and kind.shape == (self.nseg,)
+        out = np.empty((nd, len(FLOW_GRAPH_VARS), self.nseg))
+        self._check(self.L.orc_run_flow_graph(self.h, nd, lat.ctypes.data, kind.ctypes.data,
+                                              obs.ctypes.data, out.ctypes.data))
+        return {v: out[:, k, :] for k, v in enumerate(FLOW_GRAPH_VARS)}
 
     def close(self):
         if self.h:

@@ -26,6 +26,7 @@
 #include <stdint.h>
 
 #include "pws_registry.h"
+#include "pws_crmath.cuh"
 
 #if defined(__CUDACC__)
 #define PWS_DEV __device__ __forceinline__
@@ -415,61 +416,83 @@ constexpr double kPi = 3.141592653589793;
 // ---------------------------------------------------------------- soltab
 // PRMSSolarGeometry (atmosphere/prms_solar_geometry.py:176-408), split into the
 // per-HRU part (slope/aspect/latitude geometry) and the per-(doy, HRU) part.
-// Host+device: pws_init evaluates it with the host libm by default, because the
-// reference's own tables come from a host libm and PRMSSnow's melt-out is
-// sensitive to their last bit (see tests/parity.py); k_soltab is the device
-// version of the same code.
+// Host+device, with the elementary functions as a policy M: k_soltab (the
+// default) instantiates it with CrMath -- correctly rounded sin / cos / tan /
+// asin / acos / atan (pws_crmath.cuh), because the reference's own tables come
+// from a host libm and PRMSSnow's melt-out is sensitive to their last bit
+// (tests/parity.py) -- and the host variant (option "soltab_device" 0, and the
+// host shim of tests/test_column_host.py) with LibmMath, the machine's libm.
+struct LibmMath {
+  static PWS_HD double sin(double x) { return ::sin(x); }
+  static PWS_HD double cos(double x) { return ::cos(x); }
+  static PWS_HD double tan(double x) { return ::tan(x); }
+  static PWS_HD double asin(double x) { return ::asin(x); }
+  static PWS_HD double acos(double x) { return ::acos(x); }
+  static PWS_HD double atan(double x) { return ::atan(x); }
+};
+struct CrMath {
+  static PWS_HD double sin(double x) { return cr::sin(x); }
+  static PWS_HD double cos(double x) { return cr::cos(x); }
+  static PWS_HD double tan(double x) { return cr::tan(x); }
+  static PWS_HD double asin(double x) { return cr::asin(x); }
+  static PWS_HD double acos(double x) { return cr::acos(x); }
+  static PWS_HD double atan(double x) { return cr::atan(x); }
+};
 struct SolHru {
   double sl, x0, x1, x2, sin_x1, cos_x1, tan_x1, sin_x0, cos_x0, tan_x0;
 };
 
+template <class M = LibmMath>
 PWS_HD SolHru sol_hru(double slope, double aspect, double lat) {
   const double deg2rad = kPi / 180.0;
   SolHru h;
-  h.sl = atan(slope);
-  const double sl_sin = sin(h.sl), sl_cos = cos(h.sl);
+  h.sl = M::atan(slope);
+  const double sl_sin = M::sin(h.sl), sl_cos = M::cos(h.sl);
   const double aspects_rad = aspect * deg2rad;
-  const double aspects_cos = cos(aspects_rad);
+  const double aspects_cos = M::cos(aspects_rad);
   h.x0 = lat * deg2rad;
-  h.cos_x0 = cos(h.x0);
-  h.sin_x0 = sin(h.x0);
+  h.cos_x0 = M::cos(h.x0);
+  h.sin_x0 = M::sin(h.x0);
   // x1: latitude of the equivalent slope (Lee 1963 eq. 13), :207
-  h.x1 = asin(sl_cos * h.sin_x0 + sl_sin * h.cos_x0 * aspects_cos);
+  h.x1 = M::asin(sl_cos * h.sin_x0 + sl_sin * h.cos_x0 * aspects_cos);
   double d1 = sl_cos * h.cos_x0 - sl_sin * h.sin_x0 * aspects_cos;  // :210-211
   if (fabs(d1) < PWS_DNEARZERO) d1 = PWS_DNEARZERO;
-  h.x2 = atan(sl_sin * sin(aspects_rad) / d1);  // :216
+  h.x2 = M::atan(sl_sin * M::sin(aspects_rad) / d1);  // :216
   if (d1 < 0.0) h.x2 = h.x2 + kPi;
-  h.sin_x1 = sin(h.x1);
-  h.cos_x1 = cos(h.x1);
-  h.tan_x1 = tan(h.x1);
-  h.tan_x0 = tan(h.x0);
+  h.sin_x1 = M::sin(h.x1);
+  h.cos_x1 = M::cos(h.x1);
+  h.tan_x1 = M::tan(h.x1);
+  h.tan_x0 = M::tan(h.x0);
   return h;
 }
 
 // compute_t :319-358 with tan(lat), tan(decl) hoisted
+template <class M = LibmMath>
 PWS_HD double sol_compute_t(double tan_lat, double tan_decl) {
   const double tx = (-1 * tan_lat) * tan_decl;
   if (tx < -1.0) return kPi;
   if (tx > 1.0) return 0.0;
-  return acos(tx);
+  return M::acos(tx);
 }
 
 // func3 :361-408 with sin/cos of the declination and of w hoisted
+template <class M = LibmMath>
 PWS_HD double sol_func3(double v, double sin_w, double cos_w, double x, double y, double r1,
                         double sin_d, double cos_d) {
   const double pi_12 = 12 / kPi;
-  return r1 * pi_12 * (sin_d * sin_w * (x - y) + cos_d * cos_w * (sin(x + v) - sin(y + v)));
+  return r1 * pi_12 * (sin_d * sin_w * (x - y) + cos_d * cos_w * (M::sin(x + v) - M::sin(y + v)));
 }
 
 // One (doy, HRU) of compute_soltab :230-316.  t3/t7 and t2/t6 are ALIASES in
 // the reference (:255-272), so the clamped values feed t6' and t7'.
+template <class M = LibmMath>
 PWS_HD void sol_day(const SolHru& h, double sin_d, double cos_d, double tan_d, double r1,
                     double& solt, double& sunh) {
   const double two_pi = 2 * kPi, pi_12 = 12 / kPi;
-  double tt = sol_compute_t(h.tan_x1, tan_d);
+  double tt = sol_compute_t<M>(h.tan_x1, tan_d);
   double t6 = (-1 * tt) - h.x2;
   double t7 = tt - h.x2;
-  tt = sol_compute_t(h.tan_x0, tan_d);
+  tt = sol_compute_t<M>(h.tan_x0, tan_d);
   const double t0 = -1 * tt, t1 = tt;
   if (t7 > t1) t7 = t1;
   double t3 = t7;
@@ -481,19 +504,19 @@ PWS_HD void sol_day(const SolHru& h, double sin_d, double cos_d, double tan_d, d
     t2 = 0.0;
     t3 = 0.0;
   }
-  const double base = sol_func3(h.x2, h.sin_x1, h.cos_x1, t3, t2, r1, sin_d, cos_d);
+  const double base = sol_func3<M>(h.x2, h.sin_x1, h.cos_x1, t3, t2, r1, sin_d, cos_d);
   solt = base;
   sunh = (t3 - t2) * pi_12;
   if (t7 > t0) {
-    solt = base + sol_func3(h.x2, h.sin_x1, h.cos_x1, t7, t0, r1, sin_d, cos_d);
+    solt = base + sol_func3<M>(h.x2, h.sin_x1, h.cos_x1, t7, t0, r1, sin_d, cos_d);
     sunh = (t3 - t2 + t7 - t0) * pi_12;
   }
   if (t6 < t1) {
-    solt = base + sol_func3(h.x2, h.sin_x1, h.cos_x1, t1, t6, r1, sin_d, cos_d);
+    solt = base + sol_func3<M>(h.x2, h.sin_x1, h.cos_x1, t1, t6, r1, sin_d, cos_d);
     sunh = (t3 - t2 + t1 - t6) * pi_12;
   }
   if (fabs(h.sl) < PWS_DNEARZERO) {
-    solt = sol_func3(0.0, h.sin_x0, h.cos_x0, t1, t0, r1, sin_d, cos_d);
+    solt = sol_func3<M>(0.0, h.sin_x0, h.cos_x0, t1, t0, r1, sin_d, cos_d);
     sunh = (t1 - t0) * pi_12;
   }
   if (sunh < PWS_DNEARZERO) sunh = 0.0;
@@ -501,13 +524,14 @@ PWS_HD void sol_day(const SolHru& h, double sin_d, double cos_d, double tan_d, d
 }
 
 // solar_constants.py:10-43 for julian day j+1: declination and r1
+template <class M = LibmMath>
 PWS_HD void sol_constants(int j, double& decl, double& r1) {
   const double rad_day = (2 * kPi) / 365.242;
   const double jd = (double)(j + 1);
-  const double obliquity = 1 - (0.01671 * cos((jd - 3) * rad_day));
+  const double obliquity = 1 - (0.01671 * M::cos((jd - 3) * rad_day));
   const double yy = (jd - 1) * rad_day, yy2 = yy * 2, yy3 = yy * 3;
-  decl = 0.006918 - 0.399912 * cos(yy) + 0.070257 * sin(yy) - 0.006758 * cos(yy2) +
-         0.000907 * sin(yy2) - 0.002697 * cos(yy3) + 0.00148 * sin(yy3);
+  decl = 0.006918 - 0.399912 * M::cos(yy) + 0.070257 * M::sin(yy) - 0.006758 * M::cos(yy2) +
+         0.000907 * M::sin(yy2) - 0.002697 * M::cos(yy3) + 0.00148 * M::sin(yy3);
   r1 = (60.0 * 2.0) / (obliquity * obliquity);
 }
 

@@ -852,17 +852,26 @@ extern "C" int pws_init(pws_handle* h) {
   P.dprst_flag = h->dprst_flag;
   P.temp_units = h->temp_units;
   PWS_CUDA(h, cudaGetLastError());
-  // PRMSSolarGeometry tables + hru_cossl.  Default: host libm, threaded over
-  // HRUs (init-time, ~12 libm calls per (doy, HRU)); option "soltab_device"
-  // runs k_soltab instead (same code, CUDA's libm, 1-2 ulp from the host's).
+  // PRMSSolarGeometry tables + hru_cossl.  Default: k_soltab, with correctly
+  // rounded elementary functions (pws_crmath.cuh; the 366 declination constants
+  // come from the same functions here).  Option "soltab_device" 0: host threads
+  // and the machine's libm -- the bits an oracle or reference on THIS machine
+  // produces, a debugging aid for last-bit comparisons.
   {
     double sin_d[kNdoy], cos_d[kNdoy], tan_d[kNdoy], r1[kNdoy];
     for (int j = 0; j < kNdoy; ++j) {
       double decl;
-      sol_constants(j, decl, r1[j]);
-      sin_d[j] = std::sin(decl);
-      cos_d[j] = std::cos(decl);
-      tan_d[j] = std::tan(decl);
+      if (h->soltab_device) {
+        sol_constants<CrMath>(j, decl, r1[j]);
+        sin_d[j] = CrMath::sin(decl);
+        cos_d[j] = CrMath::cos(decl);
+        tan_d[j] = CrMath::tan(decl);
+      } else {
+        sol_constants(j, decl, r1[j]);
+        sin_d[j] = std::sin(decl);
+        cos_d[j] = std::cos(decl);
+        tan_d[j] = std::tan(decl);
+      }
     }
     if (h->soltab_device) {
       PWS_CUDA(h, cudaMemcpyToSymbol(c_sol_sin_d, sin_d, sizeof sin_d));

@@ -94,8 +94,10 @@ __constant__ double c_sol_cos_d[kNdoy];
 __constant__ double c_sol_tan_d[kNdoy];
 __constant__ double c_sol_r1[kNdoy];
 
-// Device version of the soltab tables (option "soltab_device"): grid
-// (ceil(nhru/128), 366), one (doy, HRU) per thread.
+// PRMSSolarGeometry's tables on the device (the default; option "soltab_device"
+// 0 computes them on host threads with the machine's libm instead): grid
+// (ceil(nhru/128), 366), one (doy, HRU) per thread, every elementary function
+// correctly rounded (CrMath, pws_crmath.cuh).
 __global__ void __launch_bounds__(128)
 k_soltab(int64_t nhru, int64_t stride, const double* __restrict__ hru_slope,
          const double* __restrict__ hru_aspect, const double* __restrict__ hru_lat,
@@ -106,14 +108,14 @@ k_soltab(int64_t nhru, int64_t stride, const double* __restrict__ hru_slope,
   if (i >= nhru) return;
   double solt, sunh;
   // horizontal surface (prms_solar_geometry.py:141-147), then slope/aspect
-  const SolHru flat = sol_hru(0.0, 0.0, hru_lat[i]);
-  sol_day(flat, c_sol_sin_d[j], c_sol_cos_d[j], c_sol_tan_d[j], c_sol_r1[j], solt, sunh);
+  const SolHru flat = sol_hru<CrMath>(0.0, 0.0, hru_lat[i]);
+  sol_day<CrMath>(flat, c_sol_sin_d[j], c_sol_cos_d[j], c_sol_tan_d[j], c_sol_r1[j], solt, sunh);
   horad[(int64_t)j * stride + i] = solt;
-  const SolHru h = sol_hru(hru_slope[i], hru_aspect[i], hru_lat[i]);
-  sol_day(h, c_sol_sin_d[j], c_sol_cos_d[j], c_sol_tan_d[j], c_sol_r1[j], solt, sunh);
+  const SolHru h = sol_hru<CrMath>(hru_slope[i], hru_aspect[i], hru_lat[i]);
+  sol_day<CrMath>(h, c_sol_sin_d[j], c_sol_cos_d[j], c_sol_tan_d[j], c_sol_r1[j], solt, sunh);
   potsw[(int64_t)j * stride + i] = solt;
   sunhrs[(int64_t)j * stride + i] = sunh;
-  if (j == 0) hru_cossl[i] = cos(atan(hru_slope[i]));  // prms_atmosphere.py:519
+  if (j == 0) hru_cossl[i] = CrMath::cos(CrMath::atan(hru_slope[i]));  // prms_atmosphere.py:519
 }
 
 // ---------------------------------------------------------------- init

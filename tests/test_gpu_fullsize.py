@@ -81,10 +81,11 @@ def test_conus_tiles_equal_single_tile_runs():
         ref, _ = po.Oracle(p0, start=start).run(ft["prcp"], ft["tmax"], ft["tmin"], po.HRU_VARS, po.SEG_VARS)
         rep = parity.compare_columns(g_all, ref, po.HRU_VARS, g_all["pkwater_equiv"], ref["pkwater_equiv"])
         assert rep["mismatches"] == [], rep["mismatches"][:5]
-        # ghost-pack ties accumulate with the number of melt-outs: DRB in its own climate has
-        # 14 tied HRUs of 765 in 2 years (0.9 % per HRU-year); this tile (a marginal-snow climate,
-        # 10 years) 164 = 2.1 % per HRU-year.  Every one is verified to BE such a tie above.
-        assert len(rep["ties"]) <= 0.03 * 765 * (nd / 365.25)
+        # ghost-pack ties accumulate with the number of melt-outs.  With the tables of k_soltab
+        # correctly rounded (pws_crmath.cuh: 0.2 % of their entries differ from glibc's, in the
+        # last bit) this tile has 2 tied HRUs of 765 in 10 years; with CUDA's own sin / cos / ...
+        # it had 164.  Every one is verified to BE such a tie above.
+        assert len(rep["ties"]) <= 0.001 * 765 * (nd / 365.25)
         osp = parity.one_step_parity(po.Oracle(p0, start=start), ft, g_all, po.HRU_VARS, p0["hru_in_to_cf"])
         print(f"tile {t} of the CONUS domain, 3,653 days vs the oracle: {len(rep['ties'])} free-running ties, "
               f"one-step {len(osp['mismatching'])} of {osp['hru_days']} HRU-days differ")
