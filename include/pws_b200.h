@@ -171,6 +171,24 @@ int pws_run_host_inputs(pws_handle *h, int ndays, const int32_t *h_cal, int n_in
 int pws_run_channel_device(pws_handle *h, int ndays, const double *d_seg_lateral_inflow,
                            double *d_seg_out);
 
+/* FlowGraph (base/flow_graph.py:131-657): the handle's segments are the NODES of
+ * a flow graph (tosegment = to_graph_index + 1; the channel parameters of a node
+ * that is not a Muskingum node are stand-ins).  pws_set_flow_graph, before
+ * pws_init: kind[node] = 0 PRMSChannelFlowNode (prms_channel_flow_graph.py:30-160),
+ * 1 PassThroughFlowNode (pass_through_flow_node.py:6-53), 2 ObsInFlowNode
+ * (obsin_flow_node.py:8-90, obs_col[node] = its column of the observations);
+ * kind == NULL turns the handle back into a PRMSChannel one.
+ * pws_run_flow_graph_host = FlowGraph.calculate for ndays days: inflows
+ * [ndays][nnodes] (the `inflows` input), obs [ndays][n_obs] (the day's observed flow
+ * of every ObsIn node, negative = pass the inflow on; NULL without ObsIn nodes),
+ * out [ndays][5][nnodes]: outflows, node_upstream_inflows, node_outflows,
+ * node_storage_changes, node_sink_source (node_negative_sink_source is its
+ * negative, node_storages is NaN for these node kinds: flow_graph.py:629-650).
+ * StarfitFlowNode (hydrology/starfit.py) is not built. */
+int pws_set_flow_graph(pws_handle *h, const int32_t *kind, const int32_t *obs_col, int n_obs);
+int pws_run_flow_graph_host(pws_handle *h, int ndays, const double *inflows, const double *obs,
+                            double *out);
+
 /* PRMSEt (hydrology/prms_et.py:22-181), the bookkeeping process that turns the
  * other processes' evaporative losses into hru_actet / unused_potet: inputs
  * h_* [ndays][nhru] as PRMSEt.get_inputs() (:101-116), parameters [nhru]

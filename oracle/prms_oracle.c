@@ -2395,6 +2395,27 @@ int orc_run_channel(Orc *o, int ndays, const double *seg_lateral_inflow,
   return 0;
 }
 
+/* Test aid: replace the Muskingum coefficients channel_init derived (tsi, ts,
+ * c0, c1, c2 per segment) with given ones.  The reference computes
+ * seg_depth ** (2/3) with numpy's vectorised power, which is not the libm pow
+ * of channel_init in the last bit for some segments; with the reference's own
+ * coefficients the routing restatements can be held to its results bit for bit. */
+int orc_set_channel_coefficients(Orc *o, const int32_t *tsi, const double *ts, const double *c0,
+                                 const double *c1, const double *c2) {
+  if (!o->inited) {
+    snprintf(o->err, sizeof o->err, "orc_set_channel_coefficients before orc_init");
+    return -1;
+  }
+  for (int j = 0; j < o->nseg; ++j) {
+    o->ch_tsi[j] = tsi[j];
+    o->ch_ts[j] = ts[j];
+    o->ch_c0[j] = c0[j];
+    o->ch_c1[j] = c1[j];
+    o->ch_c2[j] = c2[j];
+  }
+  return 0;
+}
+
 /* ====================================================================== */
 /* FlowGraph (base/flow_graph.py:576-657) over PRMSChannelFlowNode          */
 /* (hydrology/prms_channel_flow_graph.py:30-160, 367-414), PassThroughFlowNode */

@@ -183,6 +183,9 @@ int orc_run(Orc *o, int ndays, const int32_t *cal, const double *prcp,
 /* Channel alone: lateral inflows given per day [ndays][nseg] (config 5) */
 int orc_run_channel(Orc *o, int ndays, const double *seg_lateral_inflow,
                     int n_seg_out, const int32_t *seg_idx, double *seg_out);
+/* test aid: override the Muskingum coefficients derived at orc_init */
+int orc_set_channel_coefficients(Orc *o, const int32_t *tsi, const double *ts, const double *c0,
+                                 const double *c1, const double *c2);
 /* FlowGraph (base/flow_graph.py) over this handle's segments as nodes: kind[j]
  * 0 PRMSChannelFlowNode, 1 PassThroughFlowNode, 2 ObsInFlowNode (obs[t][j]);
  * out [ndays][7][nnodes] in FlowGraph.get_init_values order. */

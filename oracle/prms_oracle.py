@@ -84,6 +84,7 @@ def lib(omp: bool = False):
                                       C.c_void_p, C.c_void_p]
         L.orc_run_flow_graph.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p]
+        L.orc_set_channel_coefficients.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         L.orc_hru_var.restype = C.c_void_p
         L.orc_hru_var.argtypes = [C.c_void_p, C.c_int]
         L.orc_set_hru_var.restype = C.c_int
@@ -226,6 +227,13 @@ class Oracle:
         self._check(self.L.orc_run_channel(self.h, nd, lat.ctypes.data, len(sidx),
                                            sidx.ctypes.data, sout.ctypes.data))
         return {v: sout[:, k, :] for k, v in enumerate(seg_vars)}
+
+    def set_channel_coefficients(self, tsi, ts, c0, c1, c2):
+        """Override the Muskingum coefficients (a test aid, see prms_oracle.c)."""
+        a = [np.ascontiguousarray(tsi, dtype=np.int32)] + [np.ascontiguousarray(v, dtype=np.float64)
+                                                           for v in (ts, c0, c1, c2)]
+        assert all(v.shape == (self.nseg,) for v in a)
+        self._check(self.L.orc_set_channel_coefficients(self.h, *[v.ctypes.data for v in a]))
 
     def run_flow_graph(self, inflows, kind, obs=None):
         """FlowGraph over this oracle's segments as nodes (orc_run_flow_graph):

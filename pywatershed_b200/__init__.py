@@ -4,6 +4,18 @@ Process / Model API.  See DESIGN.md and INTEGRATION.md."""
 from .budget import Budget  # noqa: F401
 from .control import Control  # noqa: F401
 from .engine import Engine, Registry, calendar  # noqa: F401
+from .flow_graph import (  # noqa: F401
+    FlowGraph,
+    FlowNode,
+    FlowNodeMaker,
+    HruSegmentFlowAdapter,
+    ObsInFlowNodeMaker,
+    ObsInNodeMaker,
+    PassThroughFlowNodeMaker,
+    PassThroughNodeMaker,
+    PRMSChannelFlowNodeMaker,
+    prms_channel_flow_graph_postprocess,
+)
 from .model import Model  # noqa: F401
 from .parameters import Parameters, PrmsParameters  # noqa: F401
 from .processes import (  # noqa: F401
@@ -29,5 +41,8 @@ __all__ = [
     "PrmsParameters", "Process", "ConservativeProcess", "TimeseriesArray",
     "PRMSSolarGeometry", "PRMSAtmosphere", "PRMSCanopy", "PRMSSnow", "PRMSRunoff",
     "PRMSSoilzone", "PRMSGroundwater", "PRMSChannel", "PRMSRunoffNoDprst", "PRMSSoilzoneNoDprst",
-    "PRMSGroundwaterNoDprst", "PRMSEt",
+    "PRMSGroundwaterNoDprst", "PRMSEt", "FlowGraph", "FlowNode", "FlowNodeMaker",
+    "PRMSChannelFlowNodeMaker", "PassThroughFlowNodeMaker", "PassThroughNodeMaker",
+    "ObsInFlowNodeMaker", "ObsInNodeMaker", "HruSegmentFlowAdapter",
+    "prms_channel_flow_graph_postprocess",
 ]

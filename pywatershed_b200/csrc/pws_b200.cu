@@ -141,6 +141,11 @@ struct pws_handle {
   double* d_rts = nullptr;
   double *d_ts = nullptr, *d_c0 = nullptr, *d_c1 = nullptr, *d_c2 = nullptr;
   double *d_outflow_ts = nullptr, *d_seg_inflow = nullptr;
+  // FlowGraph (pws_set_flow_graph): node kinds / observation columns, caller's node order
+  bool flow_graph = false;
+  std::vector<int32_t> fg_kind, fg_obs_col;
+  int fg_n_obs = 0;
+  int32_t *d_fg_kind = nullptr, *d_fg_obs_col = nullptr;  // pos order
   // per-block scratch (sized for scratch_days).  What a block's column kernels
   // write and its routing reads is double-buffered by block parity, so the
   // column of block b+1 runs beside the routing of block b.
@@ -347,6 +352,8 @@ static void free_device(pws_handle* h) {
                 h->d_orig, h->d_chunk_begin, h->d_chunk_dmax, h->d_delay, h->d_ext_row, h->d_rts,
                 h->d_ts, h->d_c0, h->d_c1, h->d_c2, h->d_outflow_ts, h->d_seg_inflow};
   for (void* p : ch) cudaFree(p);
+  cudaFree(h->d_fg_kind); cudaFree(h->d_fg_obs_col);
+  h->d_fg_kind = h->d_fg_obs_col = nullptr;
   h->d_tsi = h->d_up_ptr = h->d_up_idx = h->d_hru_ptr = h->d_hru_idx = h->d_seg_flags = h->d_orig =
       h->d_chunk_begin = h->d_chunk_dmax = h->d_delay = h->d_ext_row = nullptr;
   h->d_rts = nullptr;
@@ -665,6 +672,9 @@ static int channel_build(pws_handle* h) {
     else if (K < 12.0) { tsv = 8.0; tsiv = 8; }
     else if (K < 24.0) { tsv = 12.0; tsiv = 12; }
     else { tsv = 24.0; tsiv = 24; }
+    // FlowGraph: a PassThroughFlowNode puts out what comes in, every hour -- the
+    // recurrence of a K < 1 h segment; an ObsIn node's routed value is never used
+    if (h->flow_graph && h->fg_kind[i] != NODE_MUSKINGUM) { tsv = 1.0; tsiv = -1; }
     const double x = x_coef[i];
     double d = K - (K * x) + (0.5 * tsv);
     if (std::fabs(d) < 1e-6) d = 0.0001;
@@ -686,7 +696,8 @@ static int channel_build(pws_handle* h) {
   // initial _seg_inflow: assignment, not sum, in index order (prms_channel.py:336-340)
   for (int64_t i = 0; i < nseg; ++i) {
     const int to = toseg[i] - 1;
-    if (to >= 0) seg_inflow[pos_of[to]] = flow_init[i];
+    // (a PRMSChannelFlowNode starts from zero: prms_channel_flow_graph.py:63-69)
+    if (to >= 0 && !h->flow_graph) seg_inflow[pos_of[to]] = flow_init[i];
   }
   // upstream CSR, each list ordered by topological rank
   std::vector<std::vector<int>> ups(nseg);
@@ -752,6 +763,15 @@ static int channel_build(pws_handle* h) {
   PWS_CUDA(h, up_f64(&h->d_c2, c2));
   PWS_CUDA(h, up_f64(&h->d_outflow_ts, outflow_ts));
   PWS_CUDA(h, up_f64(&h->d_seg_inflow, seg_inflow));
+  if (h->flow_graph) {
+    std::vector<int32_t> kind(nseg), col(nseg);
+    for (int64_t p = 0; p < nseg; ++p) {
+      kind[p] = h->fg_kind[bypos[p]];
+      col[p] = h->fg_obs_col[bypos[p]];
+    }
+    PWS_CUDA(h, up_i32(&h->d_fg_kind, kind));
+    PWS_CUDA(h, up_i32(&h->d_fg_obs_col, col));
+  }
   h->h_seg_inflow_init = seg_inflow;
   h->h_orig = orig;
   return 0;
@@ -1109,8 +1129,15 @@ static void mark_base(pws_handle* h, cudaStream_t st) {
 // enqueue the channel kernels for one block on stream `st`; `viol` = the
 // block's verdict rows (or null: no channel budget)
 static int enqueue_channel(pws_handle* h, cudaStream_t st, int ndays, const double* d_hru_lat,
-                           const double* d_seg_lat_in, double* d_seg_out, int* viol) {
+                           const double* d_seg_lat_in, double* d_seg_out, int* viol,
+                           const double* d_fg_obs = nullptr, double* d_fg_out = nullptr) {
   ChannelArgs a{};
+  const bool graph = d_fg_out != nullptr;
+  if (graph != h->flow_graph)
+    PWS_FAIL(h, graph ? "FlowGraph run on a handle without pws_set_flow_graph"
+                      : "this handle routes a FlowGraph (pws_set_flow_graph): use pws_run_flow_graph_host");
+  a.kind = h->d_fg_kind; a.obs_col = h->d_fg_obs_col; a.obs = d_fg_obs; a.n_obs = h->fg_n_obs;
+  a.fg_out = d_fg_out;
   a.nseg = h->nseg;
   a.sstride = h->sstride;
   a.ndays = ndays;
@@ -1138,12 +1165,24 @@ static int enqueue_channel(pws_handle* h, cudaStream_t st, int ndays, const doub
     PWS_CUDA(h, cudaFuncSetAttribute(k_route_chunks<PWS_ROUTE_HOURS_SHALLOW>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)route_smem_bytes(PWS_ROUTE_HOURS_SHALLOW)));
+    PWS_CUDA(h, (cudaFuncSetAttribute(k_route_chunks<PWS_ROUTE_HOURS, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)route_smem_bytes(PWS_ROUTE_HOURS))));
+    PWS_CUDA(h, (cudaFuncSetAttribute(k_route_chunks<PWS_ROUTE_HOURS_SHALLOW, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)route_smem_bytes(PWS_ROUTE_HOURS_SHALLOW))));
     h->route_attr_set = true;
   }
   cudaEvent_t e0 = new_event(h), e1 = new_event(h);
   mark_base(h, st);
   cudaEventRecord(e0, st);
-  if (route_hours(h) == PWS_ROUTE_HOURS_SHALLOW)
+  if (graph && route_hours(h) == PWS_ROUTE_HOURS_SHALLOW)
+    k_route_chunks<PWS_ROUTE_HOURS_SHALLOW, true><<<(unsigned)h->nchunks, PWS_CHUNK_THREADS,
+                                                    route_smem_bytes(PWS_ROUTE_HOURS_SHALLOW), st>>>(a);
+  else if (graph)
+    k_route_chunks<PWS_ROUTE_HOURS, true><<<(unsigned)h->nchunks, PWS_CHUNK_THREADS,
+                                            route_smem_bytes(PWS_ROUTE_HOURS), st>>>(a);
+  else if (route_hours(h) == PWS_ROUTE_HOURS_SHALLOW)
     k_route_chunks<PWS_ROUTE_HOURS_SHALLOW><<<(unsigned)h->nchunks, PWS_CHUNK_THREADS,
                                               route_smem_bytes(PWS_ROUTE_HOURS_SHALLOW), st>>>(a);
   else
@@ -1512,6 +1551,76 @@ extern "C" int pws_run_device(pws_handle* h, int ndays, const int32_t* h_cal,
   PWS_CUDA(h, cudaSetDevice(h->device));
   return enqueue_block(h, ndays, h_cal, d_prcp, d_tmax, d_tmin, forcing_columns(h), d_out_f64,
                        d_out_i32, d_seg_out, h_budget_viol, nullptr);
+}
+
+extern "C" int pws_set_flow_graph(pws_handle* h, const int32_t* kind, const int32_t* obs_col,
+                                  int n_obs) {
+  if (kind == nullptr) {
+    h->flow_graph = false;
+    h->fg_kind.clear();
+    h->fg_obs_col.clear();
+    h->fg_n_obs = 0;
+    h->inited = false;
+    return 0;
+  }
+  if (h->nseg == 0) PWS_FAIL(h, "pws_set_flow_graph: the handle has no segments (= nodes)");
+  if (n_obs < 0) PWS_FAIL(h, "pws_set_flow_graph: n_obs < 0");
+  h->fg_kind.assign(kind, kind + h->nseg);
+  h->fg_obs_col.assign((size_t)h->nseg, -1);
+  for (int64_t i = 0; i < h->nseg; ++i) {
+    if (kind[i] < NODE_MUSKINGUM || kind[i] > NODE_OBSIN)
+      PWS_FAIL(h, "pws_set_flow_graph: kind[%lld] = %d (0 Muskingum-Mann, 1 pass-through, 2 observed flow)",
+               (long long)i, kind[i]);
+    if (kind[i] == NODE_OBSIN) {
+      if (obs_col == nullptr || obs_col[i] < 0 || obs_col[i] >= n_obs)
+        PWS_FAIL(h, "pws_set_flow_graph: node %lld is an ObsIn node without a column of observations",
+                 (long long)i);
+      h->fg_obs_col[(size_t)i] = obs_col[i];
+    }
+  }
+  h->fg_n_obs = n_obs;
+  h->flow_graph = true;
+  h->inited = false;
+  return 0;
+}
+
+// FlowGraph.calculate for `ndays` days (base/flow_graph.py:576-657): host arrays in,
+// host arrays out, one launch of k_route_chunks<G, true>.  A compatibility path
+// (the reference steps a Python object per node and hour); blocks of a year or so
+// are what the Python FlowGraph class sends.
+extern "C" int pws_run_flow_graph_host(pws_handle* h, int ndays, const double* inflows,
+                                       const double* obs, double* out) {
+  if (!h->inited) PWS_FAIL(h, "pws_run_flow_graph_host before pws_init");
+  if (!h->flow_graph) PWS_FAIL(h, "pws_run_flow_graph_host: pws_set_flow_graph was not called");
+  if (ndays <= 0) return 0;
+  if (h->fg_n_obs > 0 && obs == nullptr) PWS_FAIL(h, "pws_run_flow_graph_host: ObsIn nodes need obs");
+  PWS_CUDA(h, cudaSetDevice(h->device));
+  PWS_CUDA(h, sync_all(h));
+  if (ensure_scratch(h, ndays)) return 1;
+  const size_t nn = (size_t)h->nseg, T = (size_t)ndays;
+  double *d_in = nullptr, *d_obs = nullptr, *d_out = nullptr;
+  auto release = [&]() { cudaFree(d_in); cudaFree(d_obs); cudaFree(d_out); };
+  cudaError_t e = cudaMalloc(&d_in, T * nn * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&d_obs, std::max<size_t>(1, T * h->fg_n_obs) * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&d_out, T * FG_N * nn * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpy(d_in, inflows, T * nn * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && h->fg_n_obs > 0)
+    e = cudaMemcpy(d_obs, obs, T * h->fg_n_obs * sizeof(double), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    release();
+    PWS_CUDA(h, e);
+  }
+  const int rc = enqueue_channel(h, h->s_route, ndays, nullptr, d_in, nullptr, nullptr, d_obs, d_out);
+  if (rc == 0) e = cudaStreamSynchronize(h->s_route);
+  if (rc == 0 && e == cudaSuccess)
+    e = cudaMemcpy(out, d_out, T * FG_N * nn * sizeof(double), cudaMemcpyDeviceToHost);
+  release();
+  if (rc) return rc;
+  PWS_CUDA(h, e);
+  int errflag = 0;
+  PWS_CUDA(h, cudaMemcpy(&errflag, h->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (errflag & 16) PWS_FAIL(h, "pws_run_flow_graph_host: a chunk of nodes waited for its upstream chunk in vain");
+  return 0;
 }
 
 extern "C" int pws_run_channel_device(pws_handle* h, int ndays, const double* d_seg_lat,

@@ -879,7 +879,22 @@ struct ChannelArgs {
   int n_seg_sel;
   int* err;
   short slot[PWS_N_SEG_VARS];
+  // FlowGraph runs (k_route_chunks<G, true>; base/flow_graph.py): nodes are segments
+  const int32_t* kind;       // [nseg] pos order: NODE_MUSKINGUM / NODE_PASS / NODE_OBSIN
+  const int32_t* obs_col;    // [nseg] pos order: column of `obs` of an ObsIn node, else -1
+  const double* obs;         // [ndays][n_obs] observed flows of the ObsIn nodes
+  int n_obs;
+  double* fg_out;            // [ndays][FG_N][nseg], original node order
 };
+
+// FlowNode kinds (base/flow_graph.py:16-99): PRMSChannelFlowNode
+// (prms_channel_flow_graph.py:30-160), PassThroughFlowNode (pass_through_flow_node.py,
+// routed as a Muskingum node with K < 1 h: outflow = inflow every hour, the daily
+// values are the same sums), ObsInFlowNode (obsin_flow_node.py)
+enum { NODE_MUSKINGUM = 0, NODE_PASS = 1, NODE_OBSIN = 2 };
+// rows of fg_out
+enum { FG_outflows = 0, FG_node_upstream_inflows, FG_node_outflows, FG_node_storage_changes,
+       FG_node_sink_source, FG_N };
 
 enum {
   SEG_HAS_DOWN = 1,     // tosegment > 0
@@ -910,7 +925,12 @@ constexpr size_t route_smem_bytes(int G) {
   return (size_t)2 * G * (PWS_CHUNK_THREADS + 1) * sizeof(double);
 }
 
-template <int G>
+// kGraph: the segments are the nodes of a FlowGraph (base/flow_graph.py:576-657):
+// node states start from zero every day (FlowNode.prepare_timestep), ObsIn nodes
+// put their observation out instead of the routed flow and account the difference
+// as sink / source, and the results are FlowGraph's variables in flow units
+// (a.fg_out) instead of PRMSChannel's.
+template <int G, bool kGraph = false>
 __global__ void __launch_bounds__(PWS_CHUNK_THREADS, 1)
 k_route_chunks(const __grid_constant__ ChannelArgs a) {
   constexpr int kZero = PWS_CHUNK_THREADS;  // a slot that always holds 0.0
@@ -978,6 +998,14 @@ k_route_chunks(const __grid_constant__ ChannelArgs a) {
     c2 = 0.0;
   }
   const bool down = (flags & SEG_HAS_DOWN) != 0;
+  [[maybe_unused]] int kind = NODE_MUSKINGUM, obs_col = -1;
+  [[maybe_unused]] double obs_q = 0.0, ss_sum = 0.0, st_sink = 0.0;
+  if constexpr (kGraph) {
+    if (live) {
+      kind = a.kind[pos];
+      obs_col = a.obs_col[pos];
+    }
+  }
 
   // Lateral inflow of day k as up to three raw addends (summed a window later,
   // so the loads stay in flight): HRU contributions in ascending HRU order
@@ -1007,6 +1035,16 @@ k_route_chunks(const __grid_constant__ ChannelArgs a) {
   int st_day = -1;
   auto flush_day = [&]() {
     if (st_day < 0) return;
+    if constexpr (kGraph) {
+      double* q = a.fg_out + (int64_t)st_day * FG_N * a.nseg + orig;
+      q[(int64_t)FG_outflows * a.nseg] = st_outvol;
+      q[(int64_t)FG_node_upstream_inflows * a.nseg] = st_up;
+      q[(int64_t)FG_node_outflows * a.nseg] = st_out;
+      q[(int64_t)FG_node_storage_changes * a.nseg] = st_dstor;
+      q[(int64_t)FG_node_sink_source * a.nseg] = st_sink;
+      st_day = -1;
+      return;
+    }
     const int64_t drow = (int64_t)st_day * a.sstride + pos;
     a.day_outvol[drow] = st_outvol;
     a.day_dstor[drow] = st_dstor;
@@ -1055,10 +1093,20 @@ k_route_chunks(const __grid_constant__ ChannelArgs a) {
       if (h == 0) {
         lateral = lat_window;
         seg_inflow0 = seg_inflow_prev;  // _advance_variables, prms_channel.py:384-386
-        seg_inflow = seg_inflow0 * 0.0;
-        seg_outflow = seg_inflow0 * 0.0;
-        inflow_ts = seg_inflow0 * 0.0;
-        cur_sum = seg_inflow0 * 0.0;
+        if constexpr (kGraph) {
+          // PRMSChannelFlowNode.advance / prepare_timestep (prms_channel_flow_graph.py:76-82, 113-115)
+          seg_inflow = 0.0;
+          seg_outflow = 0.0;
+          inflow_ts = 0.0;
+          cur_sum = 0.0;
+          ss_sum = 0.0;
+          if (obs_col >= 0) obs_q = __ldcg(a.obs + (int64_t)d * a.n_obs + obs_col);  // obsin_flow_node.py:37-41
+        } else {
+          seg_inflow = seg_inflow0 * 0.0;
+          seg_outflow = seg_inflow0 * 0.0;
+          inflow_ts = seg_inflow0 * 0.0;
+          cur_sum = seg_inflow0 * 0.0;
+        }
         if (!(flags & SEG_UPS_LOCAL)) {
           // upstream chunks must have published this day
           for (int k = ub; k < ue; ++k) {
@@ -1100,6 +1148,17 @@ k_route_chunks(const __grid_constant__ ChannelArgs a) {
         outflow_ts = upd ? routed : outflow_ts;
         seg_inflow0 = upd ? xq : seg_inflow0;
         inflow_ts = upd ? 0.0 : acc;
+        if constexpr (kGraph) {
+          if (kind == NODE_OBSIN) {  // obsin_flow_node.py:43-57
+            if (obs_q >= 0.0) {
+              ss_sum += obs_q - cur;
+            } else {
+              obs_q = cur;  // a missing observation: the first hour's inflow goes out all day
+              ss_sum += 0.0;
+            }
+            outflow_ts = obs_q;
+          }
+        }
         seg_outflow += outflow_ts;
         wr[g][tid] = outflow_ts;
         if (ext_row >= 0)
@@ -1110,8 +1169,17 @@ k_route_chunks(const __grid_constant__ ChannelArgs a) {
         seg_outflow = div_by_ts(seg_outflow, 24.0, 1.0 / 24.0);
         seg_inflow = div_by_ts(seg_inflow, 24.0, 1.0 / 24.0);
         st_up = div_by_ts(cur_sum, 24.0, 1.0 / 24.0);
-        st_dstor = (seg_inflow - seg_outflow) * 86400.0;
-        st_outvol = (down ? 0.0 : seg_outflow) * 86400.0;
+        if constexpr (kGraph) {
+          // flow units; an ObsIn node reports its observation and no storage change
+          // (obsin_flow_node.py:65-90), flow_graph.py:629-650
+          if (kind == NODE_OBSIN) seg_outflow = obs_q;
+          st_sink = kind == NODE_OBSIN ? div_by_ts(ss_sum, 24.0, 1.0 / 24.0) : 0.0;
+          st_dstor = kind == NODE_OBSIN ? 0.0 : seg_inflow - seg_outflow;
+          st_outvol = down ? 0.0 : seg_outflow;
+        } else {
+          st_dstor = (seg_inflow - seg_outflow) * 86400.0;
+          st_outvol = (down ? 0.0 : seg_outflow) * 86400.0;
+        }
         st_out = seg_outflow;
         st_lat = lateral;
         st_day = d;

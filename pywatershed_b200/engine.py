@@ -191,6 +191,7 @@ class Engine:
                  adjust_parameters: bool = True, channel: bool = True,
                  channel_chunk: int | None = None, fill_missing: bool = False,
                  forcing_period: int | None = None, soltab_device: bool | None = None,
+                 flow_graph: tuple | None = None,
                  lanes: int | None = None):
         """`forcing_period` = P: a member-major parameter ensemble over a base
         domain of P HRUs (nhru = nmember * P); forcings are then [ndays, P] and
@@ -245,6 +246,15 @@ class Engine:
             self._opt("forcing_period", int(forcing_period))
             self.ncol = int(forcing_period)
         self.tiled = False
+        self.n_obs = 0
+        if flow_graph is not None:
+            # the segments are the nodes of a FlowGraph: (kind [nnodes], obs_col [nnodes], n_obs)
+            kind, col, self.n_obs = flow_graph
+            kind = np.ascontiguousarray(kind, dtype=np.int32)
+            col = np.ascontiguousarray(col, dtype=np.int32)
+            if kind.shape != (self.nseg,) or col.shape != (self.nseg,):
+                raise ValueError("flow_graph: kind and obs_col must be [nnodes]")
+            self._check(self.L.pws_set_flow_graph(self.h, kind.ctypes.data, col.ctypes.data, int(self.n_obs)))
         self._check(self.L.pws_init(self.h))
         self.day = 0
         self.sel_hru: list[str] = []
@@ -539,6 +549,26 @@ class Engine:
         `out` = [nd, tiles, n_vars_of_its_kind, tile_units] (torch or numpy)."""
         sel = self.sel_f64 if self.reg.dtype(var) is np.float64 else self.sel_i32
         return untile(out, sel.index(var), self.nhru)
+
+    FLOW_GRAPH_OUT = ("outflows", "node_upstream_inflows", "node_outflows", "node_storage_changes",
+                      "node_sink_source")
+
+    def run_flow_graph(self, inflows, obs=None) -> dict:
+        """FlowGraph.calculate for len(inflows) days (pws_run_flow_graph_host):
+        inflows [ndays, nnodes], obs [ndays, n_obs].  Returns var -> [ndays, nnodes]."""
+        lat = np.ascontiguousarray(inflows, dtype=np.float64)
+        nd = lat.shape[0]
+        if lat.shape != (nd, self.nseg):
+            raise ValueError(f"inflows must be [ndays, {self.nseg}]")
+        if self.n_obs:
+            obs = np.ascontiguousarray(obs, dtype=np.float64)
+            if obs.shape != (nd, self.n_obs):
+                raise ValueError(f"obs must be [ndays, {self.n_obs}]")
+        out = np.empty((nd, len(self.FLOW_GRAPH_OUT), self.nseg))
+        self._check(self.L.pws_run_flow_graph_host(
+            self.h, nd, lat.ctypes.data, obs.ctypes.data if self.n_obs else None, out.ctypes.data))
+        self.day += nd
+        return {v: out[:, k, :] for k, v in enumerate(self.FLOW_GRAPH_OUT)}
 
     def run_channel_device(self, nd, d_seg_lat, d_seg_out, sync=True):
         self._check(self.L.pws_run_channel_device(self.h, nd, d_seg_lat, d_seg_out))

@@ -163,3 +163,28 @@ def write_prms_param_file(path, params: dict, nmonth_names=()):
             tcode = 1 if v.dtype.kind in "iu" else 3
             fh.write(f"####\n{k}\n{len(dn)}\n" + "\n".join(dn) + f"\n{flat.size}\n{tcode}\n")
             fh.write("\n".join(repr(int(x)) if tcode == 1 else repr(float(x)) for x in flat) + "\n")
+
+
+def flow_graph_params(params: dict, to_graph_index) -> dict:
+    """The parameter set of a FlowGraph whose first nsegment nodes are the
+    domain's PRMSChannel segments (base/flow_graph.py; the layout of
+    prms_channel_flow_graph.py:_build_flow_graph_inputs): nodes are segments,
+    tosegment = to_graph_index + 1, and the nodes behind the segments get
+    stand-in channel parameters (their kind says they are not Muskingum nodes)."""
+    tgi = np.asarray(to_graph_index, dtype=np.int64)
+    nn = tgi.shape[0]
+    nseg = np.asarray(params["tosegment"]).shape[0]
+    p = {}
+    for k, v in params.items():
+        v = np.asarray(v)
+        if k in ("tosegment", "tosegment_nhm"):
+            p[k] = (tgi + 1).astype(v.dtype)
+        elif v.ndim == 1 and v.shape[0] == nseg and k not in ("hru_segment",) and nseg != np.asarray(
+                params["hru_area"]).shape[0]:
+            fill = {"mann_n": 0.04, "seg_depth": 1.0, "seg_length": 1000.0, "seg_slope": 0.001,
+                    "x_coef": 0.2}.get(k, 0)
+            p[k] = np.concatenate([v, np.full(nn - nseg, fill, dtype=v.dtype)])
+        else:
+            p[k] = v.copy()
+    p["nhm_seg"] = np.arange(1, nn + 1)
+    return p
