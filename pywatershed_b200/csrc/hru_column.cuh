@@ -31,12 +31,14 @@
 #if defined(__CUDACC__)
 #define PWS_DEV __device__ __forceinline__
 #define PWS_HD __host__ __device__ __forceinline__
+#define PWS_HDM __host__ __device__ __forceinline__
 #define PWS_LD(p) (*(p))
 #define PWS_TABLE static __device__ const
 #define PWS_EXP10(x) exp10(x)
 #else
 #define PWS_DEV static inline
 #define PWS_HD static inline
+#define PWS_HDM inline
 #define PWS_LD(p) (*(p))
 #define PWS_TABLE static const
 #define PWS_EXP10(x) pow(10.0, (x))
@@ -423,20 +425,20 @@ constexpr double kPi = 3.141592653589793;
 // (tests/parity.py) -- and the host variant (option "soltab_device" 0, and the
 // host shim of tests/test_column_host.py) with LibmMath, the machine's libm.
 struct LibmMath {
-  static PWS_HD double sin(double x) { return ::sin(x); }
-  static PWS_HD double cos(double x) { return ::cos(x); }
-  static PWS_HD double tan(double x) { return ::tan(x); }
-  static PWS_HD double asin(double x) { return ::asin(x); }
-  static PWS_HD double acos(double x) { return ::acos(x); }
-  static PWS_HD double atan(double x) { return ::atan(x); }
+  static PWS_HDM double sin(double x) { return ::sin(x); }
+  static PWS_HDM double cos(double x) { return ::cos(x); }
+  static PWS_HDM double tan(double x) { return ::tan(x); }
+  static PWS_HDM double asin(double x) { return ::asin(x); }
+  static PWS_HDM double acos(double x) { return ::acos(x); }
+  static PWS_HDM double atan(double x) { return ::atan(x); }
 };
 struct CrMath {
-  static PWS_HD double sin(double x) { return cr::sin(x); }
-  static PWS_HD double cos(double x) { return cr::cos(x); }
-  static PWS_HD double tan(double x) { return cr::tan(x); }
-  static PWS_HD double asin(double x) { return cr::asin(x); }
-  static PWS_HD double acos(double x) { return cr::acos(x); }
-  static PWS_HD double atan(double x) { return cr::atan(x); }
+  static PWS_HDM double sin(double x) { return cr::sin(x); }
+  static PWS_HDM double cos(double x) { return cr::cos(x); }
+  static PWS_HDM double tan(double x) { return cr::tan(x); }
+  static PWS_HDM double asin(double x) { return cr::asin(x); }
+  static PWS_HDM double acos(double x) { return cr::acos(x); }
+  static PWS_HDM double atan(double x) { return cr::atan(x); }
 };
 struct SolHru {
   double sl, x0, x1, x2, sin_x1, cos_x1, tan_x1, sin_x0, cos_x0, tan_x0;
