@@ -18,7 +18,8 @@ import numpy as np
 
 class Budget:
     def __init__(self, control, process, terms: dict, budget_type, basis: str = "unit",
-                 rtol: float = 1e-5, atol: float = 1e-5, description: str = None):
+                 rtol: float = 1e-5, atol: float = 1e-5, description: str = None,
+                 units: str = None):
         self.name = "Budget"
         self.control = control
         self._proc = process
@@ -34,6 +35,30 @@ class Budget:
         self._itime_accumulated = -1
         self._accumulations = {
             c: {v: None for v in self.terms[c]} for c in self.components}
+        self._acc_baseline = {}
+        self._accum_start_time = getattr(control, "init_time", None)
+        self.time_unit = "D"
+        self._unit_desc = "volumes"
+        # units: the common unit of the terms' metadata (base/budget.py:79-100)
+        from ._process_meta import VARIABLE_META
+
+        all_vars = [v for c in self.components for v in self.terms[c]]
+        self.meta = {v: dict(VARIABLE_META[v]) for v in all_vars if v in VARIABLE_META}
+        if units is None and len(self.meta) == len(all_vars) and all_vars:
+            us = [m.get("units") for m in self.meta.values()]
+            if any(u != us[0] for u in us):
+                raise ValueError("Units not consistent over all terms")
+            units = us[0]
+        self.units = units
+        # the derived output variables of <Process>_budget.nc (base/budget.py:102-127)
+        self.output_vars_desc = {
+            c + "_sum": f"Sum of {d} ({basis})"
+            for c, d in (("inputs", "input fluxes"), ("outputs", "output fluxes"),
+                         ("storage_changes", "storage changes")) if self.terms[c]}
+        for k, desc in self.output_vars_desc.items():
+            t0 = self.terms[k[:-4]][0]
+            if t0 in self.meta:
+                self.meta[k] = dict(self.meta[t0], desc=desc, units=self.units)
 
     # ---- component views (dict var -> current-day array), like budget[component]
     def __getitem__(self, key):
@@ -67,6 +92,35 @@ class Budget:
     def _balance(self):
         return self.balance
 
+    # the reference's public names for the three sums (base/budget.py:188-198)
+    @property
+    def inputs_sum(self):
+        return self._inputs_sum
+
+    @property
+    def outputs_sum(self):
+        return self._outputs_sum
+
+    @property
+    def storage_changes_sum(self):
+        return self._storage_changes_sum
+
+    @property
+    def inputs(self):
+        return self["inputs"]
+
+    @property
+    def outputs(self):
+        return self["outputs"]
+
+    @property
+    def storage_changes(self):
+        return self["storage_changes"]
+
+    @staticmethod
+    def get_components():
+        return ("inputs", "outputs", "storage_changes")
+
     @property
     def accumulations(self):
         """component -> term -> per-unit sum over the steps so far
@@ -80,7 +134,72 @@ class Budget:
             out[c] = {}
             for v in self.terms[c]:
                 host, d = self._accumulations[c][v], dev.get(v)
+                base = self._acc_baseline.get((c, v))
+                if d is not None and base is not None:
+                    d = d - base
                 out[c][v] = host if d is None else (d if host is None else host + d)
+        return out
+
+    def _n_units(self):
+        for c in self.components:
+            for v in self.terms[c]:
+                try:
+                    return int(np.asarray(self._proc[v]).shape[-1])
+                except Exception:
+                    continue
+        return 1
+
+    def set_initial_accumulations(self, init_accumulations, accum_start_time=None):
+        """base/budget.py:204-228: start the accumulations from zero, or from
+        `init_accumulations[component][term]` (a restart), counted since
+        `accum_start_time`."""
+        self.reset_accumulations()
+        if init_accumulations is None:
+            self._accum_start_time = getattr(self.control, "init_time", None)
+            return
+        self._accum_start_time = accum_start_time
+        for c in self.components:
+            for v in self.terms[c]:
+                if v in init_accumulations.get(c, {}):
+                    self._accumulations[c][v] = np.array(init_accumulations[c][v], dtype=np.float64)
+
+    def reset_accumulations(self):
+        """base/budget.py:230-237: every accumulation back to zero, counted from
+        the last accumulated time.  Sums living on the device are not touched
+        (other budgets of the model may share the term): their current value
+        becomes the baseline subtracted from now on."""
+        self._accum_start_time = self._time_accumulated()
+        model = getattr(self._proc, "_model", None)
+        dev = model._device_accumulations() if model is not None else {}
+        n = self._n_units()
+        for c in self.components:
+            for v in self.terms[c]:
+                self._accumulations[c][v] = np.zeros(n) if dev.get(v) is None else None
+                if dev.get(v) is not None:
+                    self._acc_baseline[(c, v)] = np.array(dev[v])
+
+    def _time_accumulated(self):
+        return self.control.current_time if self._itime_accumulated >= 0 else None
+
+    @property
+    def _accumulations_sum(self):
+        return self._sum_component_accumulations()
+
+    def _sum_component_accumulations(self):
+        """base/budget.py:283-307: per component, the sum of its terms'
+        accumulations -- per unit, or one number for a global-basis budget."""
+        acc = self.accumulations
+        out = {}
+        for c in self.components:
+            tot = None
+            for v in self.terms[c]:
+                a = acc[c][v]
+                if a is None:
+                    continue
+                a = np.asarray(a, dtype=np.float64)
+                a = a.copy() if self.basis == "unit" else a.sum()
+                tot = a if tot is None else tot + a
+            out[c] = tot
         return out
 
     # ---- stepping
@@ -130,5 +249,60 @@ class Budget:
             warn(msg, UserWarning)
 
     def __repr__(self):
-        return (f"Budget({self.description}, basis={self.basis}, zero_sum={self._zero_sum}, "
-                f"terms={self.terms})")
+        """The reference's report (base/budget.py:422-648): the step's rates and
+        the accumulated volumes, spatial sums per term in three columns, with
+        the balance line under each table."""
+        it = self.control.itime_step
+        if it < 0:
+            return f"Budget of {self.description} only initialized. Check back later."
+        cols = []
+        acc = self.accumulations
+        for c in self.components:
+            keys = self.terms[c]
+            cols.append((c, keys, max([len(k) for k in keys] + [len(c) + 14]) + 12))
+        indent, sep = " " * 9, " " * 4
+        width = sum(w for _, _, w in cols) + 2 * len(sep)
+
+        def fmt(x):
+            return "--" if x is None else np.format_float_scientific(float(np.sum(x)), precision=4)
+
+        def table(values):
+            lines = []
+            for r in range(max(len(k) for _, k, _ in cols)):
+                line = indent
+                for (c, keys, w) in cols:
+                    cell = f"{keys[r]}: {fmt(values[c][keys[r]])}" if r < len(keys) else ""
+                    line += cell.ljust(w) + sep
+                lines.append(line.rstrip())
+            return lines
+
+        def balance(sums):
+            op = "=" if self._zero_sum else "!=!"
+            line = "Balance: "
+            for (c, _, w), o in zip(cols, ("", "-", op)):
+                line += (o + " " + fmt(sums[c])).ljust(w) + sep
+            return line.rstrip()
+
+        head = ("Individual spatial unit budget" if self.basis == "unit" else "Global budget")
+        out = ["*-" * ((len(indent) + width) // 2),
+               f"{head} for {self.description} (units: {self.units}).",
+               ("Budget is checked on each spatial unit. This summary shows spatial sums for the "
+                "entire model domain." if self.basis == "unit" else
+                "Budget is checked on full domain: spatially summed fluxes and storage changes are "
+                "checked for balance."),
+               f"@ time: {self.control.current_time} (itime_step: {it})", "",
+               "This timestep, rates:",
+               indent + sep.join(f"{n} rates".ljust(w) for n, (_, _, w) in zip(
+                   ("input", "output", "storage change"), cols)),
+               indent + sep.join("-" * w for _, _, w in cols)]
+        out += table({c: {v: self._proc[v] for v in self.terms[c]} for c in self.components})
+        out += [indent + "-" * width,
+                balance({"inputs": self._inputs_sum, "outputs": self._outputs_sum,
+                         "storage_changes": self._storage_changes_sum}), "",
+                f"Accumulated volumes (since {self._accum_start_time}):",
+                indent + sep.join(f"{n} volumes".ljust(w) for n, (_, _, w) in zip(
+                    ("input", "output", "storage change"), cols)),
+                indent + sep.join("-" * w for _, _, w in cols)]
+        out += table(acc)
+        out += [indent + "-" * width, balance(self._sum_component_accumulations()), ""]
+        return "\n".join(out)

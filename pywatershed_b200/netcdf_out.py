@@ -3,7 +3,8 @@ base/process.py:463-592, base/budget.py:661-748):
 
   <output_dir>/<var>.nc          separate_files=True (default)
   <output_dir>/<Process>.nc      separate_files=False
-  <output_dir>/<Process>_budget.nc   inputs_sum / outputs_sum / storage_changes_sum
+  <output_dir>/<Process>_budget.nc   inputs_sum / outputs_sum / storage_changes_sum (+ every term
+                                     with budget_args={'write_individual_vars': True})
 
 dims `time` (unlimited) x `nhm_id` | `nhm_seg`; coordinate variables
 nhm_id / nhm_seg (i4) and time (f4, "days since 1970-01-01 00:00:00");
@@ -65,7 +66,7 @@ class _File:
     """One netCDF file holding one or more [time, unit] variables."""
 
     def __init__(self, path: pl.Path, var_names, coord_name, coord_vals, process_name,
-                 time_name="time", n_doy=None):
+                 time_name="time", n_doy=None, global_attrs=None):
         self.path = path
         self.vars = list(var_names)
         self.coord_name = coord_name
@@ -75,6 +76,8 @@ class _File:
             ds = _nc4.Dataset(path, "w", format="NETCDF4")
             ds.setncattr("Description", "pywatershed output data")
             ds.setncattr("process class", process_name)
+            for k, val in (global_attrs or {}).items():
+                ds.setncattr(k, val)
             ds.createDimension(time_name, n_doy)
             ds.createDimension(coord_name, len(coord_vals))
             # utils/netcdf_utils.py:474-489: time is f4 "days since ...", doy is i4 "Day of year"
@@ -97,6 +100,8 @@ class _File:
             ds = Cdf2Writer(path)
             ds.setncattr("Description", "pywatershed output data")
             ds.setncattr("process class", process_name)
+            for k, val in (global_attrs or {}).items():
+                ds.setncattr(k, val)
             ds.createDimension(time_name, n_doy)
             ds.createDimension(coord_name, len(coord_vals))
             tatts = {"units": "days since 1970-01-01 00:00:00" if time_name == "time" else "Day of year"}
@@ -115,12 +120,29 @@ class _File:
         self.ds = ds
         self.tv = tv
 
-    def create_variable(self, name, kind):
-        """One more [time, unit] variable (before the first write)."""
+    def group_name(self, group, name):
+        """Name of variable `name` of netCDF-4 group `group` (created on demand);
+        the classic format has no groups: `<group>__<name>` there."""
         if _nc4 is not None:
-            return self.ds.createVariable(name, kind, (self.time_name, self.coord_name))
-        self.v[name] = self.ds.createVariable(name, kind, (self.time_name, self.coord_name))
-        return self.v[name]
+            if group not in self.ds.groups:
+                self.ds.createGroup(group)
+            return f"{group}/{name}"
+        return f"{group}__{name}"
+
+    def create_variable(self, name, kind, meta=None):
+        """One more [time, unit] variable (before the first write)."""
+        atts = {}
+        for k, val in (meta or {}).items():
+            if val is None or isinstance(val, dict):
+                continue
+            atts[k] = " ".join(val) if isinstance(val, (list, tuple)) else val
+        if _nc4 is not None:
+            v = self.ds.createVariable(name, kind, (self.time_name, self.coord_name))
+        else:
+            v = self.v[name] = self.ds.createVariable(name, kind, (self.time_name, self.coord_name))
+        for k, val in atts.items():
+            v.setncattr(k, val)
+        return v
 
     def write(self, t0, t1, times_days, blocks: dict):
         """Rows [t0, t1) of the time axis and of the variables in `blocks`."""
@@ -184,8 +206,9 @@ class ModelNetcdfOutput:
                         time_name="doy" if doy else "time", n_doy=366 if doy else None)))
             b = getattr(proc, "budget", None)
             if b is not None:
-                self.budget_files[pname] = _BudgetFile(self.dir / f"{pname}_budget.nc", pname, b,
-                                                       nhm_seg if False else nhm_id)
+                bf = _BudgetFile(self.dir / f"{pname}_budget.nc", pname, b, nhm_id, **(budget_args or {}))
+                if bf.v:
+                    self.budget_files[pname] = bf
 
     def write_days(self, model, t0, t1, blk=None, b0=None):
         """Write days [t0, t1) of a block (default: the model's current one)."""
@@ -229,33 +252,66 @@ class ModelNetcdfOutput:
 
 
 class _BudgetFile:
-    """<Process>_budget.nc: the three component sums per unit (or per domain
-    for a global-basis budget), base/budget.py:661-748."""
+    """<Process>_budget.nc (base/budget.py:661-748): the component sums per unit
+    (or per domain for a global-basis budget) named by `write_sum_vars` (True:
+    all three, a list: those, False / None: none) and, with
+    `write_individual_vars`, every term of every component.  The reference puts
+    a component's terms into a netCDF-4 group of its name (`inputs/net_rain`);
+    NetCDF-3 has no groups, so without the netCDF4 module they are variables
+    named `<component>__<term>`."""
 
-    def __init__(self, path, pname, budget, nhm_id):
+    def __init__(self, path, pname, budget, nhm_id, write_sum_vars=True, write_individual_vars=False,
+                 **_ignored):
         self.budget = budget
         self.glob = budget.basis == "global"
+        if write_sum_vars is True:
+            sums = list(budget.output_vars_desc)
+        elif isinstance(write_sum_vars, (list, tuple)):
+            sums = [v for v in budget.output_vars_desc if v in write_sum_vars]
+        elif write_sum_vars in (False, None):
+            sums = []
+        else:
+            raise ValueError(f"Unexpected value of write_sum_vars: {write_sum_vars}")
+        self.v, self.term_vars = {}, {}
+        self.f = None
+        if not sums and not write_individual_vars:
+            import warnings
+
+            warnings.warn(f"Budget for {pname} has no requested output, no {pname}_budget.nc is written")
+            return
         coord = np.array([0]) if self.glob else nhm_id
-        self.f = _File(path, [], "one" if self.glob else "nhm_id", coord, pname)
-        self.v = {}
-        for name in ("inputs_sum", "outputs_sum", "storage_changes_sum"):
-            self.v[name] = self.f.create_variable(name, "f8")
+        attrs = {"Description": f"pywatershed ({budget.basis}) budget for {budget.description}",
+                 "Budget basis": f"{budget.basis} (unit or global)"}
+        for c in budget.components:
+            attrs[c] = "[" + ", ".join(budget.terms[c]) + "]"
+        self.f = _File(path, [], "one" if self.glob else "nhm_id", coord, pname, global_attrs=attrs)
+        for name in sums:
+            self.v[name] = self.f.create_variable(name, "f8", meta=budget.meta.get(name))
+        if write_individual_vars:
+            for c in budget.components:
+                for t in budget.terms[c]:
+                    key = self.f.group_name(c, t)
+                    self.term_vars[key] = (c, t)
+                    self.v[key] = self.f.create_variable(key, "f8", meta=budget.meta.get(t))
         self.f.v = dict(self.v)
 
     def write(self, t0, t1, tdays, blk, j0, j1):
-        sums = {}
-        for comp, name in (("inputs", "inputs_sum"), ("outputs", "outputs_sum"),
-                           ("storage_changes", "storage_changes_sum")):
-            terms = [np.asarray(blk[v][j0:j1], dtype=np.float64) for v in self.budget.terms[comp]
+        out = {}
+        for name in self.v:
+            if name in self.term_vars:
+                t = self.term_vars[name][1]
+                if t not in blk:
+                    continue
+                a = np.asarray(blk[t][j0:j1], dtype=np.float64)
+                out[name] = a.sum(axis=1)[:, None] if self.glob else a
+                continue
+            terms = [np.asarray(blk[v][j0:j1], dtype=np.float64) for v in self.budget.terms[name[:-4]]
                      if v in blk]
             if not terms:
                 continue
-            if self.glob:
-                tot = sum(t.sum(axis=1) for t in terms)[:, None]
-            else:
-                tot = sum(terms)
-            sums[name] = tot
-        self.f.write(t0, t1, tdays, sums)
+            out[name] = sum(t.sum(axis=1) for t in terms)[:, None] if self.glob else sum(terms)
+        self.f.write(t0, t1, tdays, out)
 
     def close(self):
-        self.f.close()
+        if self.f is not None:
+            self.f.close()

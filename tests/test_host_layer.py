@@ -139,6 +139,50 @@ def test_budget_imbalance_error_and_warn():
         b.calculate(n_violations=3)  # the device's verdict
 
 
+def test_budget_accumulation_surface_of_the_reference():
+    """base/budget.py:204-237, 283-310, 422-648: set_initial_accumulations /
+    reset_accumulations / _sum_component_accumulations and the report."""
+    c, b, proc = _budget("error", 1.0)
+    assert "only initialized" in repr(b)
+    assert b.units is None and set(b.output_vars_desc) == {"inputs_sum", "outputs_sum", "storage_changes_sum"}
+    b.set_initial_accumulations(None)
+    assert (b.accumulations["inputs"]["in1"] == 0).all()
+    c.advance()
+    b.calculate()
+    b.accumulate_block({k: np.stack([v, v, v]) for k, v in proc.items()}, 1.0)
+    sums = b._sum_component_accumulations()
+    assert (sums["inputs"] == 6).all() and (sums["outputs"] == 3).all() and (sums["storage_changes"] == 3).all()
+    assert (b.inputs_sum == 2).all() and (b.outputs_sum == 1).all() and (b.storage_changes_sum == 1).all()
+    text = repr(b)
+    assert "Individual spatial unit budget for simple_test" in text
+    assert "This timestep, rates:" in text and "Accumulated volumes" in text
+    assert "in1: 5.e+00" in text and "in1: 1.5e+01" in text  # spatial sums of the rate and the volume
+    assert "Balance: " in text and "!=!" not in text
+    b.reset_accumulations()
+    assert (b.accumulations["outputs"]["out2"] == 0).all()
+    b.set_initial_accumulations({"inputs": {"in1": np.full(5, 7.0)}}, np.datetime64("1979-01-01"))
+    assert (b.accumulations["inputs"]["in1"] == 7).all() and (b.accumulations["inputs"]["in2"] == 0).all()
+    assert b._accum_start_time == np.datetime64("1979-01-01")
+    # a global-basis budget sums over the units
+    from pywatershed_b200 import Budget
+
+    g = Budget(c, proc, b.terms, "warn", basis="global", description="glob")
+    g.accumulate_block({k: np.stack([v, v]) for k, v in proc.items()}, 1.0)
+    assert g._sum_component_accumulations()["inputs"] == 20.0
+    assert "Global budget for glob" in repr(g)
+
+
+def test_budget_units_come_from_the_terms_metadata():
+    import pywatershed_b200 as pwsb
+
+    c = _control(3, budget_type="warn")
+    terms = pwsb.PRMSSnow.get_mass_budget_terms()
+    proc = _FakeProc({v: np.zeros(2) for comp in terms.values() for v in comp})
+    b = pwsb.Budget(c, proc, terms, "warn", description="PRMSSnow")
+    assert b.units == "inches"
+    assert b.meta["inputs_sum"]["desc"] == "Sum of input fluxes (unit)"
+
+
 # ---------------------------------------------------------------- processes
 def test_process_descriptors_and_variable_registry():
     import pywatershed_b200 as pwsb
@@ -686,6 +730,24 @@ def test_model_netcdf_output_on_a_stubbed_block(drb, tmp_path, monkeypatch):
     t, _ = read("PRMSSnow_budget.nc", "time")
     day0 = (m.control.start_time.astype("datetime64[D]") - np.datetime64("1970-01-01", "D")).astype(int)
     np.testing.assert_array_equal(t, (day0 + np.arange(nd)).astype(np.float32))
+    # budget_args (base/budget.py:661-706): chosen sums, and every term of every component
+    out = netcdf_out.ModelNetcdfOutput(m, tmp_path / "b2", True, ["pkwater_equiv"],
+                                       {"write_sum_vars": ["outputs_sum"], "write_individual_vars": True})
+    out.write_days(m, 0, nd)
+    out.close()
+    with netcdf_file(str(tmp_path / "b2" / "PRMSSnow_budget.nc"), "r", mmap=False) as ds:
+        assert "outputs_sum" in ds.variables and "inputs_sum" not in ds.variables
+        assert ds.inputs == ("[" + ", ".join(b.terms["inputs"]) + "]").encode()
+        assert getattr(ds, "Budget basis") == b"unit (unit or global)"
+        for comp in b.components:
+            for v in b.terms[comp]:
+                np.testing.assert_array_equal(ds.variables[f"{comp}__{v}"][:], blk[v])
+        assert ds.variables["outputs_sum"].units == b"inches"
+    with pytest.warns(UserWarning, match="no requested output"):
+        out = netcdf_out.ModelNetcdfOutput(m, tmp_path / "b3", True, ["pkwater_equiv"],
+                                           {"write_sum_vars": False})
+    assert not out.budget_files
+    out.close()
 
 
 @needs_ref_nc
