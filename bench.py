@@ -695,6 +695,10 @@ def main():
     ap.add_argument("--lanes", type=int, default=None, help="column launches per block (library option)")
     ap.add_argument("--overlap", type=int, default=None, choices=(0, 1),
                     help="routing beside the next block's column (library option; default: by domain size)")
+    ap.add_argument("--channel-chunk", type=int, default=None,
+                    help="segments per routing CTA (library option channel_chunk; default 512)")
+    ap.add_argument("--column-hrus", type=int, default=None, choices=(128, 256),
+                    help="HRUs per column CTA (library option column_hrus; default: by domain size)")
     ap.add_argument("--shard-of", type=int, default=None,
                     help="tuning aid on ONE GPU: run rank 0's share of an N-way split; `value` is then "
                          "what N GPUs would give if every rank took as long as this one")
@@ -720,7 +724,10 @@ def main():
 
     def engine_for(spec, shard):
         eng = Engine(shard["params"], shard["start"], device=D.local_rank,
-                     forcing_period=shard.get("forcing_period"), lanes=args.lanes)
+                     forcing_period=shard.get("forcing_period"), lanes=args.lanes,
+                     channel_chunk=args.channel_chunk)
+        if args.column_hrus is not None:
+            eng._opt("column_hrus", args.column_hrus)
         if args.overlap is not None:
             eng._opt("overlap_routing", args.overlap)
         return eng

@@ -176,16 +176,23 @@ int pws_run_channel_device(pws_handle *h, int ndays, const double *d_seg_lateral
  * that is not a Muskingum node are stand-ins).  pws_set_flow_graph, before
  * pws_init: kind[node] = 0 PRMSChannelFlowNode (prms_channel_flow_graph.py:30-160),
  * 1 PassThroughFlowNode (pass_through_flow_node.py:6-53), 2 ObsInFlowNode
- * (obsin_flow_node.py:8-90, obs_col[node] = its column of the observations);
+ * (obsin_flow_node.py:8-90, obs_col[node] = its column of the observations),
+ * 3 SourceSinkFlowNode (source_sink_flow_node.py:10-125, obs_col[node] = its column
+ * of the requested sources (+) / sinks (-), pws_set_flow_node_params: its flow_min);
  * kind == NULL turns the handle back into a PRMSChannel one.
  * pws_run_flow_graph_host = FlowGraph.calculate for ndays days: inflows
  * [ndays][nnodes] (the `inflows` input), obs [ndays][n_obs] (the day's observed flow
- * of every ObsIn node, negative = pass the inflow on; NULL without ObsIn nodes),
+ * of every ObsIn node, negative = pass the inflow on; the day's request of every
+ * SourceSink node; NULL without such nodes),
  * out [ndays][5][nnodes]: outflows, node_upstream_inflows, node_outflows,
  * node_storage_changes, node_sink_source (node_negative_sink_source is its
  * negative, node_storages is NaN for these node kinds: flow_graph.py:629-650).
  * StarfitFlowNode (hydrology/starfit.py) is not built. */
 int pws_set_flow_graph(pws_handle *h, const int32_t *kind, const int32_t *obs_col, int n_obs);
+/* flow_min [nnodes] (SourceSinkFlowNodeMaker's `flow_min` parameter,
+ * source_sink_flow_node.py:155-159; read for kind 3 only); after
+ * pws_set_flow_graph, before pws_init; NULL = zero everywhere */
+int pws_set_flow_node_params(pws_handle *h, const double *flow_min);
 int pws_run_flow_graph_host(pws_handle *h, int ndays, const double *inflows, const double *obs,
                             double *out);
 

@@ -2430,7 +2430,7 @@ int orc_set_channel_coefficients(Orc *o, const int32_t *tsi, const double *ts, c
 /* node_storages, node_sink_source, node_negative_sink_source.              */
 /* ====================================================================== */
 int orc_run_flow_graph(Orc *o, int ndays, const double *inflows, const int32_t *kind,
-                       const double *obs, double *out) {
+                       const double *obs, const double *flow_min, double *out) {
   if (!o->inited) {
     snprintf(o->err, sizeof o->err, "orc_run_flow_graph before orc_init");
     return -1;
@@ -2459,6 +2459,8 @@ int orc_run_flow_graph(Orc *o, int ndays, const double *inflows, const int32_t *
       /* node.prepare_timestep() (:579-580) */
       seg_inflow[j] = 0.0;  /* MM: _seg_inflow; pass-through: _accum_inflow */
       seg_outflow[j] = kind[j] == 2 ? ob[j] : 0.0; /* ObsIn: _seg_outflow = the day's observation */
+      /* SourceSink (kind 3): ob[j] is the day's requested source (+) / sink (-),
+       * source_sink_flow_node.py:54-58 */
       inflow_ts[j] = 0.0;
       ss_sum[j] = 0.0;
       sink[j] = 0.0;
@@ -2491,6 +2493,28 @@ int orc_run_flow_graph(Orc *o, int ndays, const double *inflows, const int32_t *
           seg_inflow[j] += in;
           seg_outflow[j] = seg_inflow[j] / (double)(ihr + 1);
           sub[j] = in;
+        } else if (kind[j] == 3) { /* source_sink_flow_node.py:60-92 */
+          const double in = up[j] + lat[j];
+          double ss = ob[j];
+          const double fmin = flow_min ? flow_min[j] : 0.0;
+          double outq = in;
+          if (ss >= 0.0) { /* a source is always applied */
+            outq = in + ss;
+          } else if (ss < 0.0 && in < fmin) { /* no sink below the minimum flow */
+            outq = in;
+            ss = 0.0;
+          } else if (ss < 0.0 && in >= fmin) {
+            if (in + ss < fmin) {
+              ss = fmin - in;
+              outq = fmin;
+            } else {
+              outq = in + ss;
+            }
+          }
+          seg_outflow[j] = outq; /* the node's outflow is the LAST substep's (:105-110) */
+          ss_sum[j] += ss;
+          sink[j] = ss_sum[j] / (double)(ihr + 1);
+          sub[j] = outq;
         } else { /* obsin_flow_node.py:43-57 */
           const double in = up[j] + lat[j];
           if (seg_outflow[j] >= 0.0) {

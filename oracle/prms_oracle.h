@@ -187,10 +187,12 @@ int orc_run_channel(Orc *o, int ndays, const double *seg_lateral_inflow,
 int orc_set_channel_coefficients(Orc *o, const int32_t *tsi, const double *ts, const double *c0,
                                  const double *c1, const double *c2);
 /* FlowGraph (base/flow_graph.py) over this handle's segments as nodes: kind[j]
- * 0 PRMSChannelFlowNode, 1 PassThroughFlowNode, 2 ObsInFlowNode (obs[t][j]);
- * out [ndays][7][nnodes] in FlowGraph.get_init_values order. */
+ * 0 PRMSChannelFlowNode, 1 PassThroughFlowNode, 2 ObsInFlowNode (obs[t][j]),
+ * 3 SourceSinkFlowNode (obs[t][j] = the day's requested source / sink,
+ * flow_min[j], may be NULL = 0); out [ndays][7][nnodes] in
+ * FlowGraph.get_init_values order. */
 int orc_run_flow_graph(Orc *o, int ndays, const double *inflows, const int32_t *kind,
-                       const double *obs, double *out);
+                       const double *obs, const double *flow_min, double *out);
 
 /* current value of one public variable (pointer into oracle storage) */
 const double *orc_hru_var(Orc *o, int idx);

@@ -83,7 +83,7 @@ def lib(omp: bool = False):
         L.orc_run_channel.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                       C.c_void_p, C.c_void_p]
         L.orc_run_flow_graph.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
-                                         C.c_void_p]
+                                         C.c_void_p, C.c_void_p]
         L.orc_set_channel_coefficients.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         L.orc_hru_var.restype = C.c_void_p
         L.orc_hru_var.argtypes = [C.c_void_p, C.c_int]
@@ -235,23 +235,26 @@ class Oracle:
         assert all(v.shape == (self.nseg,) for v in a)
         self._check(self.L.orc_set_channel_coefficients(self.h, *[v.ctypes.data for v in a]))
 
-    def run_flow_graph(self, inflows, kind, obs=None):
+    def run_flow_graph(self, inflows, kind, obs=None, flow_min=None):
         """FlowGraph over this oracle's segments as nodes (orc_run_flow_graph):
         inflows [ndays, nnodes], kind [nnodes] (0 Muskingum-Mann, 1 pass-through,
-        2 observed flow), obs [ndays, nnodes] for the ObsIn nodes.  Returns
+        2 observed flow, 3 source / sink), obs [ndays, nnodes]: the ObsIn nodes'
+        observations and the SourceSink nodes' requests, flow_min [nnodes].  Returns
         var -> [ndays, nnodes] for FlowGraph's seven variables."""
         lat = np.ascontiguousarray(inflows, dtype=np.float64)
         nd = lat.shape[0]
         kind = np.ascontiguousarray(kind, dtype=np.int32)
         if obs is None:
-            if (kind == 2).any():
+            if (kind >= 2).any():
                 raise ValueError("ObsIn nodes need obs")
             obs = np.zeros((nd, self.nseg))
         obs = np.ascontiguousarray(obs, dtype=np.float64)
         assert lat.shape == obs.shape == (nd, self.nseg) and kind.shape == (self.nseg,)
         out = np.empty((nd, len(FLOW_GRAPH_VARS), self.nseg))
+        fm = np.zeros(self.nseg) if flow_min is None else np.ascontiguousarray(flow_min, dtype=np.float64)
+        assert fm.shape == (self.nseg,)
         self._check(self.L.orc_run_flow_graph(self.h, nd, lat.ctypes.data, kind.ctypes.data,
-                                              obs.ctypes.data, out.ctypes.data))
+                                              obs.ctypes.data, fm.ctypes.data, out.ctypes.data))
         return {v: out[:, k, :] for k, v in enumerate(FLOW_GRAPH_VARS)}
 
     def close(self):

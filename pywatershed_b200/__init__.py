@@ -14,6 +14,7 @@ from .flow_graph import (  # noqa: F401
     PassThroughFlowNodeMaker,
     PassThroughNodeMaker,
     PRMSChannelFlowNodeMaker,
+    SourceSinkFlowNodeMaker,
     prms_channel_flow_graph_postprocess,
 )
 from .model import Model  # noqa: F401
@@ -43,6 +44,6 @@ __all__ = [
     "PRMSSoilzone", "PRMSGroundwater", "PRMSChannel", "PRMSRunoffNoDprst", "PRMSSoilzoneNoDprst",
     "PRMSGroundwaterNoDprst", "PRMSEt", "FlowGraph", "FlowNode", "FlowNodeMaker",
     "PRMSChannelFlowNodeMaker", "PassThroughFlowNodeMaker", "PassThroughNodeMaker",
-    "ObsInFlowNodeMaker", "ObsInNodeMaker", "HruSegmentFlowAdapter",
+    "ObsInFlowNodeMaker", "ObsInNodeMaker", "SourceSinkFlowNodeMaker", "HruSegmentFlowAdapter",
     "prms_channel_flow_graph_postprocess",
 ]

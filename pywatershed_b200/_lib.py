@@ -79,6 +79,7 @@ def lib():
         "pws_reset_state": (i32, [vp]),
         "pws_output_tile": (i32, [vp, C.POINTER(i32), C.POINTER(i64)]),
         "pws_set_flow_graph": (i32, [vp, vp, vp, i32]),
+        "pws_set_flow_node_params": (i32, [vp, vp]),
         "pws_run_flow_graph_host": (i32, [vp, i32, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
@@ -100,5 +101,5 @@ EXPORTED_SYMBOLS = (
     "pws_timer_mark", "pws_timer_elapsed_ms", "pws_last_launches", "pws_reset_state",
     "pws_output_tile", "pws_run_host_f32", "pws_last_blocks", "pws_n_seg_state",
     "pws_seg_state_name", "pws_select_accumulations", "pws_get_accumulations",
-    "pws_clear_accumulations", "pws_et_host", "pws_set_flow_graph", "pws_run_flow_graph_host",
+    "pws_clear_accumulations", "pws_et_host", "pws_set_flow_graph", "pws_set_flow_node_params", "pws_run_flow_graph_host",
 )

@@ -144,8 +144,10 @@ struct pws_handle {
   // FlowGraph (pws_set_flow_graph): node kinds / observation columns, caller's node order
   bool flow_graph = false;
   std::vector<int32_t> fg_kind, fg_obs_col;
+  std::vector<double> fg_flow_min;  // pws_set_flow_node_params: SourceSink nodes' minimum flow
   int fg_n_obs = 0;
   int32_t *d_fg_kind = nullptr, *d_fg_obs_col = nullptr;  // pos order
+  double* d_fg_flow_min = nullptr;                         // pos order
   // per-block scratch (sized for scratch_days).  What a block's column kernels
   // write and its routing reads is double-buffered by block parity, so the
   // column of block b+1 runs beside the routing of block b.
@@ -352,8 +354,9 @@ static void free_device(pws_handle* h) {
                 h->d_orig, h->d_chunk_begin, h->d_chunk_dmax, h->d_delay, h->d_ext_row, h->d_rts,
                 h->d_ts, h->d_c0, h->d_c1, h->d_c2, h->d_outflow_ts, h->d_seg_inflow};
   for (void* p : ch) cudaFree(p);
-  cudaFree(h->d_fg_kind); cudaFree(h->d_fg_obs_col);
+  cudaFree(h->d_fg_kind); cudaFree(h->d_fg_obs_col); cudaFree(h->d_fg_flow_min);
   h->d_fg_kind = h->d_fg_obs_col = nullptr;
+  h->d_fg_flow_min = nullptr;
   h->d_tsi = h->d_up_ptr = h->d_up_idx = h->d_hru_ptr = h->d_hru_idx = h->d_seg_flags = h->d_orig =
       h->d_chunk_begin = h->d_chunk_dmax = h->d_delay = h->d_ext_row = nullptr;
   h->d_rts = nullptr;
@@ -765,12 +768,15 @@ static int channel_build(pws_handle* h) {
   PWS_CUDA(h, up_f64(&h->d_seg_inflow, seg_inflow));
   if (h->flow_graph) {
     std::vector<int32_t> kind(nseg), col(nseg);
+    std::vector<double> fmin(nseg, 0.0);
     for (int64_t p = 0; p < nseg; ++p) {
       kind[p] = h->fg_kind[bypos[p]];
       col[p] = h->fg_obs_col[bypos[p]];
+      if (!h->fg_flow_min.empty()) fmin[p] = h->fg_flow_min[bypos[p]];
     }
     PWS_CUDA(h, up_i32(&h->d_fg_kind, kind));
     PWS_CUDA(h, up_i32(&h->d_fg_obs_col, col));
+    PWS_CUDA(h, up_f64(&h->d_fg_flow_min, fmin));
   }
   h->h_seg_inflow_init = seg_inflow;
   h->h_orig = orig;
@@ -1137,6 +1143,7 @@ static int enqueue_channel(pws_handle* h, cudaStream_t st, int ndays, const doub
     PWS_FAIL(h, graph ? "FlowGraph run on a handle without pws_set_flow_graph"
                       : "this handle routes a FlowGraph (pws_set_flow_graph): use pws_run_flow_graph_host");
   a.kind = h->d_fg_kind; a.obs_col = h->d_fg_obs_col; a.obs = d_fg_obs; a.n_obs = h->fg_n_obs;
+  a.flow_min = h->d_fg_flow_min;
   a.fg_out = d_fg_out;
   a.nseg = h->nseg;
   a.sstride = h->sstride;
@@ -1559,6 +1566,7 @@ extern "C" int pws_set_flow_graph(pws_handle* h, const int32_t* kind, const int3
     h->flow_graph = false;
     h->fg_kind.clear();
     h->fg_obs_col.clear();
+    h->fg_flow_min.clear();
     h->fg_n_obs = 0;
     h->inited = false;
     return 0;
@@ -1568,18 +1576,28 @@ extern "C" int pws_set_flow_graph(pws_handle* h, const int32_t* kind, const int3
   h->fg_kind.assign(kind, kind + h->nseg);
   h->fg_obs_col.assign((size_t)h->nseg, -1);
   for (int64_t i = 0; i < h->nseg; ++i) {
-    if (kind[i] < NODE_MUSKINGUM || kind[i] > NODE_OBSIN)
-      PWS_FAIL(h, "pws_set_flow_graph: kind[%lld] = %d (0 Muskingum-Mann, 1 pass-through, 2 observed flow)",
-               (long long)i, kind[i]);
-    if (kind[i] == NODE_OBSIN) {
+    if (kind[i] < NODE_MUSKINGUM || kind[i] > NODE_SOURCESINK)
+      PWS_FAIL(h, "pws_set_flow_graph: kind[%lld] = %d (0 Muskingum-Mann, 1 pass-through, 2 observed flow, "
+                  "3 source / sink)", (long long)i, kind[i]);
+    if (kind[i] >= NODE_OBSIN) {
       if (obs_col == nullptr || obs_col[i] < 0 || obs_col[i] >= n_obs)
-        PWS_FAIL(h, "pws_set_flow_graph: node %lld is an ObsIn node without a column of observations",
-                 (long long)i);
+        PWS_FAIL(h, "pws_set_flow_graph: node %lld is an ObsIn / SourceSink node without a column of "
+                    "observations / requests", (long long)i);
       h->fg_obs_col[(size_t)i] = obs_col[i];
     }
   }
   h->fg_n_obs = n_obs;
   h->flow_graph = true;
+  h->inited = false;
+  return 0;
+}
+
+// SourceSinkFlowNode's flow_min (hydrology/source_sink_flow_node.py:16-34), one value per
+// node (read for kind 3 only); after pws_set_flow_graph, before pws_init.  NULL = all zero.
+extern "C" int pws_set_flow_node_params(pws_handle* h, const double* flow_min) {
+  if (!h->flow_graph) PWS_FAIL(h, "pws_set_flow_node_params before pws_set_flow_graph");
+  if (flow_min == nullptr) h->fg_flow_min.clear();
+  else h->fg_flow_min.assign(flow_min, flow_min + h->nseg);
   h->inited = false;
   return 0;
 }
@@ -1593,7 +1611,7 @@ extern "C" int pws_run_flow_graph_host(pws_handle* h, int ndays, const double* i
   if (!h->inited) PWS_FAIL(h, "pws_run_flow_graph_host before pws_init");
   if (!h->flow_graph) PWS_FAIL(h, "pws_run_flow_graph_host: pws_set_flow_graph was not called");
   if (ndays <= 0) return 0;
-  if (h->fg_n_obs > 0 && obs == nullptr) PWS_FAIL(h, "pws_run_flow_graph_host: ObsIn nodes need obs");
+  if (h->fg_n_obs > 0 && obs == nullptr) PWS_FAIL(h, "pws_run_flow_graph_host: ObsIn / SourceSink nodes need obs");
   PWS_CUDA(h, cudaSetDevice(h->device));
   PWS_CUDA(h, sync_all(h));
   if (ensure_scratch(h, ndays)) return 1;

@@ -15,6 +15,7 @@
 //   k_widen_forcings float32 forcing rows (as uploaded) -> the float64 forcing ring
 #pragma once
 #include <cuda_runtime.h>
+#include <type_traits>
 
 #include "hru_column.cuh"
 
@@ -881,8 +882,9 @@ struct ChannelArgs {
   short slot[PWS_N_SEG_VARS];
   // FlowGraph runs (k_route_chunks<G, true>; base/flow_graph.py): nodes are segments
   const int32_t* kind;       // [nseg] pos order: NODE_MUSKINGUM / NODE_PASS / NODE_OBSIN
-  const int32_t* obs_col;    // [nseg] pos order: column of `obs` of an ObsIn node, else -1
-  const double* obs;         // [ndays][n_obs] observed flows of the ObsIn nodes
+  const int32_t* obs_col;    // [nseg] pos order: column of `obs` of an ObsIn / SourceSink node, else -1
+  const double* obs;         // [ndays][n_obs] observed flows of the ObsIn nodes, requests of the SourceSink nodes
+  const double* flow_min;    // [nseg] pos order: minimum flow of a SourceSink node
   int n_obs;
   double* fg_out;            // [ndays][FG_N][nseg], original node order
 };
@@ -890,8 +892,9 @@ struct ChannelArgs {
 // FlowNode kinds (base/flow_graph.py:16-99): PRMSChannelFlowNode
 // (prms_channel_flow_graph.py:30-160), PassThroughFlowNode (pass_through_flow_node.py,
 // routed as a Muskingum node with K < 1 h: outflow = inflow every hour, the daily
-// values are the same sums), ObsInFlowNode (obsin_flow_node.py)
-enum { NODE_MUSKINGUM = 0, NODE_PASS = 1, NODE_OBSIN = 2 };
+// values are the same sums), ObsInFlowNode (obsin_flow_node.py), SourceSinkFlowNode
+// (source_sink_flow_node.py)
+enum { NODE_MUSKINGUM = 0, NODE_PASS = 1, NODE_OBSIN = 2, NODE_SOURCESINK = 3 };
 // rows of fg_out
 enum { FG_outflows = 0, FG_node_upstream_inflows, FG_node_outflows, FG_node_storage_changes,
        FG_node_sink_source, FG_N };
@@ -999,11 +1002,12 @@ k_route_chunks(const __grid_constant__ ChannelArgs a) {
   }
   const bool down = (flags & SEG_HAS_DOWN) != 0;
   [[maybe_unused]] int kind = NODE_MUSKINGUM, obs_col = -1;
-  [[maybe_unused]] double obs_q = 0.0, ss_sum = 0.0, st_sink = 0.0;
+  [[maybe_unused]] double obs_q = 0.0, ss_sum = 0.0, st_sink = 0.0, flow_min = 0.0;
   if constexpr (kGraph) {
     if (live) {
       kind = a.kind[pos];
       obs_col = a.obs_col[pos];
+      flow_min = a.flow_min[pos];
     }
   }
 
@@ -1124,46 +1128,84 @@ k_route_chunks(const __grid_constant__ ChannelArgs a) {
           __threadfence();  // acquire: the rows are visible after the counter
         }
       }
+      // The G hours of the step, as straight-line code: the per-segment cases
+      // (upstream slots in registers or the general CSR walk, an outflow row for
+      // another chunk or not) are decided ONCE per step and the hour loop is
+      // instantiated per case, so nothing inside it branches and the compiler
+      // schedules the shared-memory reads and the non-recurrent sums of all G
+      // hours ahead of the outflow recurrence.
+      const unsigned fbits = fire >> h;  // bit g: hour h + g is a routing update
+      auto hours = [&](auto fast_c, auto ext_c) {
+        constexpr bool kFast = decltype(fast_c)::value, kExt = decltype(ext_c)::value;
+        double upv[G];
+        if constexpr (kFast) {
 #pragma unroll
-      for (int g = 0; g < G; ++g) {
-        double up;
-        if (fast_up) {
-          up = (rd[g][u0] + rd[g][u1]) + rd[g][u2];  // absent ones read the 0.0 slot
+          for (int g = 0; g < G; ++g)
+            upv[g] = (rd[g][u0] + rd[g][u1]) + rd[g][u2];  // absent ones read the 0.0 slot
         } else {
-          up = 0.0;
-          for (int k = ub; k < ue; ++k) {
-            const int u = a.up_idx[k];
-            if (u >= cb && u < ce) up += rd[g][u - cb];
-            else up += __ldcg(a.ots + (int64_t)a.ext_row[u] * row_len + d * 24 + h + g);
-          }
-        }
-        const double cur = lateral + up;
-        seg_inflow += cur;
-        cur_sum += up;
-        const double acc = inflow_ts + cur;
-        // routing update (branch-free; most segments update every hour)
-        const bool upd = (fire >> (h + g)) & 1u;
-        const double xq = div_by_ts(acc, ts, rts);
-        const double routed = (xq * c0 + seg_inflow0 * c1) + outflow_ts * c2;
-        outflow_ts = upd ? routed : outflow_ts;
-        seg_inflow0 = upd ? xq : seg_inflow0;
-        inflow_ts = upd ? 0.0 : acc;
-        if constexpr (kGraph) {
-          if (kind == NODE_OBSIN) {  // obsin_flow_node.py:43-57
-            if (obs_q >= 0.0) {
-              ss_sum += obs_q - cur;
-            } else {
-              obs_q = cur;  // a missing observation: the first hour's inflow goes out all day
-              ss_sum += 0.0;
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            double up = 0.0;
+            for (int k = ub; k < ue; ++k) {
+              const int u = a.up_idx[k];
+              if (u >= cb && u < ce) up += rd[g][u - cb];
+              else up += __ldcg(a.ots + (int64_t)a.ext_row[u] * row_len + d * 24 + h + g);
             }
-            outflow_ts = obs_q;
+            upv[g] = up;
           }
         }
-        seg_outflow += outflow_ts;
-        wr[g][tid] = outflow_ts;
-        if (ext_row >= 0)
-          __stcg(a.ots + (int64_t)ext_row * row_len + d * 24 + h + g, outflow_ts);
-      }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const double up = upv[g];
+          const double cur = lateral + up;
+          seg_inflow += cur;
+          cur_sum += up;
+          const double acc = inflow_ts + cur;
+          // routing update (branch-free; most segments update every hour)
+          const bool upd = (fbits >> g) & 1u;
+          const double xq = div_by_ts(acc, ts, rts);
+          const double routed = (xq * c0 + seg_inflow0 * c1) + outflow_ts * c2;
+          outflow_ts = upd ? routed : outflow_ts;
+          seg_inflow0 = upd ? xq : seg_inflow0;
+          inflow_ts = upd ? 0.0 : acc;
+          if constexpr (kGraph) {
+            if (kind == NODE_OBSIN) {  // obsin_flow_node.py:43-57
+              if (obs_q >= 0.0) {
+                ss_sum += obs_q - cur;
+              } else {
+                obs_q = cur;  // a missing observation: the first hour's inflow goes out all day
+                ss_sum += 0.0;
+              }
+              outflow_ts = obs_q;
+            } else if (kind == NODE_SOURCESINK) {  // source_sink_flow_node.py:60-92
+              double ss = obs_q, outq = cur;       // obs_q: the day's request, source > 0 > sink
+              if (ss >= 0.0) {
+                outq = cur + ss;                   // a source is always applied
+              } else if (ss < 0.0 && cur < flow_min) {
+                ss = 0.0;                          // no sink below the minimum flow
+              } else if (ss < 0.0 && cur >= flow_min) {
+                if (cur + ss < flow_min) {
+                  ss = flow_min - cur;             // the sink takes what the minimum flow leaves
+                  outq = flow_min;
+                } else {
+                  outq = cur + ss;
+                }
+              }
+              ss_sum += ss;
+              outflow_ts = outq;
+            }
+          }
+          seg_outflow += outflow_ts;
+          wr[g][tid] = outflow_ts;
+          if constexpr (kExt) {
+            if (ext_row >= 0)
+              __stcg(a.ots + (int64_t)ext_row * row_len + d * 24 + h + g, outflow_ts);
+          }
+        }
+      };
+      if (fast_up && ext_row < 0) hours(std::true_type{}, std::false_type{});
+      else if (fast_up) hours(std::true_type{}, std::true_type{});
+      else hours(std::false_type{}, std::true_type{});
       h += G;
       if (h == 24) {
         seg_outflow = div_by_ts(seg_outflow, 24.0, 1.0 / 24.0);
@@ -1172,9 +1214,11 @@ k_route_chunks(const __grid_constant__ ChannelArgs a) {
         if constexpr (kGraph) {
           // flow units; an ObsIn node reports its observation and no storage change
           // (obsin_flow_node.py:65-90), flow_graph.py:629-650
+          // a SourceSink node reports its LAST substep's outflow (:105-110)
           if (kind == NODE_OBSIN) seg_outflow = obs_q;
-          st_sink = kind == NODE_OBSIN ? div_by_ts(ss_sum, 24.0, 1.0 / 24.0) : 0.0;
-          st_dstor = kind == NODE_OBSIN ? 0.0 : seg_inflow - seg_outflow;
+          if (kind == NODE_SOURCESINK) seg_outflow = outflow_ts;
+          st_sink = kind >= NODE_OBSIN ? div_by_ts(ss_sum, 24.0, 1.0 / 24.0) : 0.0;
+          st_dstor = kind >= NODE_OBSIN ? 0.0 : seg_inflow - seg_outflow;
           st_outvol = down ? 0.0 : seg_outflow;
         } else {
           st_dstor = (seg_inflow - seg_outflow) * 86400.0;

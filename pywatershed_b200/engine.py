@@ -248,13 +248,19 @@ class Engine:
         self.tiled = False
         self.n_obs = 0
         if flow_graph is not None:
-            # the segments are the nodes of a FlowGraph: (kind [nnodes], obs_col [nnodes], n_obs)
-            kind, col, self.n_obs = flow_graph
+            # the segments are the nodes of a FlowGraph: (kind [nnodes], obs_col [nnodes], n_obs
+            # [, flow_min [nnodes]])
+            kind, col, self.n_obs = flow_graph[:3]
             kind = np.ascontiguousarray(kind, dtype=np.int32)
             col = np.ascontiguousarray(col, dtype=np.int32)
             if kind.shape != (self.nseg,) or col.shape != (self.nseg,):
                 raise ValueError("flow_graph: kind and obs_col must be [nnodes]")
             self._check(self.L.pws_set_flow_graph(self.h, kind.ctypes.data, col.ctypes.data, int(self.n_obs)))
+            if len(flow_graph) > 3 and flow_graph[3] is not None:
+                fmin = np.ascontiguousarray(flow_graph[3], dtype=np.float64)
+                if fmin.shape != (self.nseg,):
+                    raise ValueError("flow_graph: flow_min must be [nnodes]")
+                self._check(self.L.pws_set_flow_node_params(self.h, fmin.ctypes.data))
         self._check(self.L.pws_init(self.h))
         self.day = 0
         self.sel_hru: list[str] = []

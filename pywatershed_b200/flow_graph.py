@@ -10,7 +10,8 @@ kernel (k_route_chunks<G, true>, include/pws_b200.h: pws_set_flow_graph):
     Muskingum-Mann recurrence, coefficients as PRMSChannelFlowNodeMaker._init_data
     (:230-330) derives them;
   * PassThroughFlowNode (hydrology/pass_through_flow_node.py:6-53);
-  * ObsInFlowNode (hydrology/obsin_flow_node.py:8-90).
+  * ObsInFlowNode (hydrology/obsin_flow_node.py:8-90);
+  * SourceSinkFlowNode (hydrology/source_sink_flow_node.py:10-125).
 
 Same constructor signatures, variable names, budget terms and helper functions
 (prms_channel_flow_graph_postprocess, prms_channel_flow_graph_to_model_dict,
@@ -33,7 +34,7 @@ import numpy as np
 from .budget import Budget
 from .parameters import Parameters, as_param_dict
 
-KIND_MUSKINGUM, KIND_PASS, KIND_OBSIN = 0, 1, 2
+KIND_MUSKINGUM, KIND_PASS, KIND_OBSIN, KIND_SOURCESINK = 0, 1, 2, 3
 
 
 class FlowNode:
@@ -109,19 +110,53 @@ class ObsInFlowNodeMaker(FlowNodeMaker):
         if isinstance(gid, bytes):
             gid = gid.decode()
         col = self._obs_data[gid]
-        days = times.astype("datetime64[D]")
         if hasattr(col, "index"):  # pandas Series
             src_t = np.asarray(col.index.values).astype("datetime64[D]")
             src_v = np.asarray(col.values, dtype=np.float64)
         else:
             src_t = np.asarray(col[0]).astype("datetime64[D]")
             src_v = np.asarray(col[1], dtype=np.float64)
-        order = np.argsort(src_t)
-        src_t, src_v = src_t[order], src_v[order]
-        j = np.searchsorted(src_t, days)
-        if (j >= src_t.size).any() or (src_t[np.minimum(j, src_t.size - 1)] != days).any():
-            raise KeyError(f"observations of {gid!r} do not cover the simulation days")
-        return src_v[j]
+        return _values_on_days(src_t, src_v, times, f"observations of {gid!r}")
+
+
+class SourceSinkFlowNodeMaker(FlowNodeMaker):
+    """hydrology/source_sink_flow_node.py:128-166: `parameters` holds `flow_min`
+    [n], `source_sink_df` a pandas DataFrame (index = dates) whose columns are
+    collated with `flow_min` by POSITION (the names are not used), or a
+    sequence of (times, values) pairs.  Sources are positive, sinks negative; a
+    sink only takes what leaves `flow_min` in the channel."""
+
+    kind = KIND_SOURCESINK
+
+    def __init__(self, parameters: Parameters, source_sink_df) -> None:
+        self.name = "SourceSinkNodeMaker"
+        self._parameters = parameters
+        self._source_sink_df = source_sink_df
+
+    def flow_min(self, index: int) -> float:
+        return float(np.asarray(as_param_dict(self._parameters)["flow_min"])[index])
+
+    def series(self, index: int, times: np.ndarray) -> np.ndarray:
+        """The requests of node `index` on the days `times` (datetime64)."""
+        df = self._source_sink_df
+        if hasattr(df, "columns"):
+            col = df[df.columns[index]]
+            src_t = np.asarray(col.index.values).astype("datetime64[D]")
+            src_v = np.asarray(col.values, dtype=np.float64)
+        else:
+            src_t = np.asarray(df[index][0]).astype("datetime64[D]")
+            src_v = np.asarray(df[index][1], dtype=np.float64)
+        return _values_on_days(src_t, src_v, times, f"requests of source/sink column {index}")
+
+
+def _values_on_days(src_t, src_v, times, what):
+    days = times.astype("datetime64[D]")
+    order = np.argsort(src_t)
+    src_t, src_v = src_t[order], src_v[order]
+    j = np.searchsorted(src_t, days)
+    if (j >= src_t.size).any() or (src_t[np.minimum(j, src_t.size - 1)] != days).any():
+        raise KeyError(f"{what} do not cover the simulation days")
+    return src_v[j]
 
 
 # the reference exports both spellings
@@ -253,6 +288,7 @@ class FlowGraph:
         self._to_graph_index = tgi
         kind = np.zeros(self.nnodes, dtype=np.int32)
         obs_col = np.full(self.nnodes, -1, dtype=np.int32)
+        flow_min = np.zeros(self.nnodes)
         # stand-in channel parameters for the nodes that are not Muskingum nodes
         seg = {"mann_n": np.full(self.nnodes, 0.04), "seg_depth": np.ones(self.nnodes),
                "seg_length": np.full(self.nnodes, 1000.0), "seg_slope": np.full(self.nnodes, 0.001),
@@ -265,16 +301,18 @@ class FlowGraph:
             mk = self._node_maker_dict[nm]
             if mk.kind is None:
                 raise NotImplementedError(
-                    f"FlowNodeMaker {type(mk).__name__}: only PRMSChannelFlowNodeMaker, PassThroughFlowNodeMaker "
-                    "and ObsInFlowNodeMaker nodes run on the device; there is no CPU path")
+                    f"FlowNodeMaker {type(mk).__name__}: only PRMSChannelFlowNodeMaker, PassThroughFlowNodeMaker, "
+                    "ObsInFlowNodeMaker and SourceSinkFlowNodeMaker nodes run on the device; there is no CPU path")
             kind[j] = mk.kind
             if mk.kind == KIND_MUSKINGUM:
                 for k in seg:
                     seg[k][j] = np.asarray(mk._params[k])[ix]
-            elif mk.kind == KIND_OBSIN:
+            elif mk.kind in (KIND_OBSIN, KIND_SOURCESINK):
                 obs_col[j] = len(self._obs_nodes)
                 self._obs_nodes.append((j, mk, int(ix)))
-        self._kind, self._obs_col = kind, obs_col
+                if mk.kind == KIND_SOURCESINK:
+                    flow_min[j] = mk.flow_min(int(ix))
+        self._kind, self._obs_col, self._flow_min = kind, obs_col, flow_min
         seg["tosegment"] = (tgi + 1).astype(np.int64)
         seg["hru_segment"] = np.zeros(1, dtype=np.int64)
         seg["hru_area"] = np.ones(1)
@@ -287,7 +325,8 @@ class FlowGraph:
 
         p = Engine._filled(self._engine_params)
         self._engine = Engine(p, self.control.start_time, device=self._device, channel=True,
-                              fill_missing=True, flow_graph=(self._kind, self._obs_col, len(self._obs_nodes)))
+                              fill_missing=True,
+                              flow_graph=(self._kind, self._obs_col, len(self._obs_nodes), self._flow_min))
         nt = self.control.n_times
         times = self.control.start_time + np.arange(nt) * self.control.time_step
         self._obs = None

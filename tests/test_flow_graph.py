@@ -58,6 +58,48 @@ def test_oracle_flow_graph_with_its_own_coefficients(drb, golden):
         np.testing.assert_allclose(got[k][:, s], z["ts_" + k], rtol=1e-9, atol=1e-10, err_msg=k)
 
 
+def test_oracle_source_sink_nodes_bit_exact_with_the_reference_coefficients(drb):
+    """SourceSinkFlowNode (hydrology/source_sink_flow_node.py:60-92), every branch
+    of calculate_subtimestep taken, against the fixture of
+    oracle/gen_golden_flowgraph_ss.py (unmodified reference, 240 days)."""
+    p, _, start = drb
+    z = np.load(scenarios.GOLDEN / "drb_flowgraph_ss_golden.npz")
+    inflows = z["inflows_f32"].astype(np.float64)
+    nd, nn = inflows.shape
+    nseg = nn - 3
+    req = np.zeros((nd, nn))
+    req[:, nseg:nseg + 2] = z["requests"]
+    fmin = np.zeros(nn)
+    fmin[nseg:nseg + 2] = z["flow_min"]
+    o = po.Oracle(scenarios.flow_graph_params(p, z["to_graph_index"]), start=start)
+    o.set_channel_coefficients(z["coef_tsi"], z["coef_ts"], z["coef_c0"], z["coef_c1"], z["coef_c2"])
+    got = o.run_flow_graph(inflows, z["kind"], req, fmin)
+    s = z["node_sample"]
+    for k in po.FLOW_GRAPH_VARS:
+        np.testing.assert_array_equal(got[k][:, s], z["ts_" + k], err_msg=k)
+        np.testing.assert_allclose(np.nansum(got[k], axis=1), z["sum_" + k], rtol=1e-12, atol=1e-9, err_msg=k)
+    ss = got["node_sink_source"][:, nseg]
+    assert (ss < 0).any() and (ss > 0).any() and (ss == 0).any()
+    assert (got["node_storage_changes"][:, nseg:nseg + 2] == 0).all()
+
+
+def test_source_sink_maker_series_and_flow_min():
+    import pywatershed_b200 as pwsb
+
+    t = np.datetime64("1979-01-01") + np.arange(5)
+    mk = pwsb.SourceSinkFlowNodeMaker({"flow_min": np.array([2.0, 0.5])},
+                                      [(t, np.arange(5.0)), (t[::-1], -np.arange(5.0))])
+    assert mk.kind == 3 and mk.flow_min(1) == 0.5
+    np.testing.assert_array_equal(mk.series(1, t[1:3].astype("datetime64[s]")), [-3.0, -2.0])
+    with pytest.raises(KeyError, match="do not cover"):
+        mk.series(0, t + 3)
+    import pandas as pd
+
+    df = pd.DataFrame({"a": np.arange(5.0), "b": np.ones(5)}, index=pd.DatetimeIndex(t))
+    mk = pwsb.SourceSinkFlowNodeMaker({"flow_min": np.zeros(2)}, df)
+    np.testing.assert_array_equal(mk.series(0, t), np.arange(5.0))
+
+
 def test_graph_construction_follows_the_reference_helper(drb, golden):
     """_build_flow_graph_inputs (prms_channel_flow_graph.py:985-1100): the same
     to_graph_index as the reference's helper produced for the fixture."""

@@ -154,3 +154,47 @@ def test_flow_graph_netcdf_output(drb, golden, tmp_path):
     _, a = read_time_variable(tmp_path / "node_outflows.nc", "node_outflows")
     np.testing.assert_array_equal(a, np.array(rows))
     assert (tmp_path / "node_sink_source.nc").exists() and not (tmp_path / "outflows.nc").exists()
+
+
+def test_source_sink_nodes_equal_the_oracle_bit_for_bit_and_the_reference(drb):
+    """SourceSinkFlowNode (hydrology/source_sink_flow_node.py): a sink whose requests
+    exceed what the minimum flow leaves on 97 of 240 days (cut back), are refused on
+    low-flow days and are sources on others, a source node, and a pass-through node,
+    against the oracle (same bits) and the fixture from the unmodified reference
+    (oracle/gen_golden_flowgraph_ss.py)."""
+    import pywatershed_b200 as pwsb
+    from pywatershed_b200.flow_graph import _build_flow_graph_inputs
+
+    z = np.load(scenarios.GOLDEN / "drb_flowgraph_ss_golden.npz")
+    p, _, start = drb
+    inflows = z["inflows_f32"].astype(np.float64)
+    nd, nn = inflows.shape
+    nseg = nn - 3
+    req = np.zeros((nd, nn))
+    req[:, nseg:nseg + 2] = z["requests"]
+    fmin = np.zeros(nn)
+    fmin[nseg:nseg + 2] = z["flow_min"]
+    ref = po.Oracle(scenarios.flow_graph_params(p, z["to_graph_index"]), start=start).run_flow_graph(
+        inflows, z["kind"], req, fmin)
+    control = _control(start, nd)
+    times = control.start_time + np.arange(nd) * control.time_step
+    makers = {"ss": pwsb.SourceSinkFlowNodeMaker({"flow_min": z["flow_min"]},
+                                                 [(times, z["requests"][:, 0]), (times, z["requests"][:, 1])]),
+              "pass": pwsb.PassThroughFlowNodeMaker()}
+    pfg, node_makers = _build_flow_graph_inputs(p, p, makers, ["ss", "ss", "pass"], [0, 1, 0],
+                                                [9001, 9002, 9003], [1766, 1829, int(z["pass_above_nhm_seg"])])
+    np.testing.assert_array_equal(pfg.parameters["to_graph_index"], z["to_graph_index"])
+    fg = pwsb.FlowGraph(control, None, pfg, inflows, node_makers, budget_type="error")
+    got = fg.run_all()
+    assert fg.budget._zero_sum
+    fg.finalize()
+    s = z["node_sample"]
+    for k in po.FLOW_GRAPH_VARS:
+        np.testing.assert_array_equal(got[k], ref[k], err_msg=k)
+        np.testing.assert_allclose(got[k][:, s], z["ts_" + k], rtol=1e-9, atol=1e-10, err_msg=k)
+    ss = got["node_sink_source"][:, nseg]
+    want = z["requests"][:, 0]
+    assert ((ss < 0) & (ss != want)).sum() > 50 and (ss == want).sum() > 20 and (ss > 0).any()
+    # the sink never takes the flow below the minimum flow it found
+    took = ss < 0
+    assert (got["node_outflows"][took, nseg] >= z["flow_min"][0] - 1e-12).all()
