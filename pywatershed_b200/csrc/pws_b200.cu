@@ -103,6 +103,7 @@ struct pws_handle {
   int64_t forcing_period = 0;  // option "forcing_period": forcings are [ndays][period], HRU i reads i % period
   bool route_attr_set = false;
   bool smem_attr_set[16] = {};
+  bool one_cta_carveout = true;  // option "one_cta_carveout": L1-heavy carve-out for grids of <= one CTA per SM
   bool tiled_outputs = false;  // option "tiled_outputs": [day][tile][variable][H] (SINK_TILED)
   int column_hrus_opt = 0;  // option "column_hrus": 0 = by domain size, else 128 | 256
   double albset[4] = {0, 0, 0, 0};
@@ -449,6 +450,7 @@ extern "C" int pws_set_option(pws_handle* h, const char* name, double value) {
     h->lanes_opt = (int)value;
     return 0;
   }
+  else if (!strcmp(name, "one_cta_carveout")) { h->one_cta_carveout = value != 0.0; return 0; }
   else if (!strcmp(name, "overlap_routing")) { h->overlap_routing = value < 0 ? -1 : (value != 0.0); return 0; }
   else if (!strcmp(name, "accumulate")) { h->accumulate_on = value != 0.0; return 0; }
   else if (!strcmp(name, "forcing_period")) {
@@ -1115,9 +1117,12 @@ static int ensure_scratch(pws_handle* h, int ndays) {
 
 // shared-memory carve-out (percent of the 228 KB maximum) that holds the
 // resident CTAs of k_hru_column<., H> (1 KB per CTA is reserved by the system)
-static int column_carveout_pct(int H) {
+// `one_cta`: the grid has at most one CTA per SM (a small domain, a basin shard of
+// a multi-GPU run): the second CTA's share stays L1, where the spilled registers
+// and the global-memory parameter rows of the lone CTA then hit.
+static int column_carveout_pct(int H, bool one_cta = false) {
   const size_t per_cta = column_smem_bytes(H) + 1024;
-  const size_t ctas = std::max<size_t>(1, std::min<size_t>((228 * 1024) / per_cta, 65536 / (2 * H * 128)));
+  const size_t ctas = one_cta ? 1 : std::max<size_t>(1, std::min<size_t>((228 * 1024) / per_cta, 65536 / (2 * H * 128)));
   return (int)std::min<size_t>(100, (per_cta * ctas * 100 + 228 * 1024 - 1) / (228 * 1024));
 }
 
@@ -1160,6 +1165,19 @@ static int enqueue_channel(pws_handle* h, cudaStream_t st, int ndays, const doub
   a.seg_out = h->n_seg_sel > 0 ? d_seg_out : nullptr;
   a.n_seg_sel = h->n_seg_sel;
   memcpy(a.slot, h->slot_seg, sizeof a.slot);
+  if (graph) {
+    const int rows[6] = {FG_outflows, -1, FG_node_upstream_inflows, FG_node_outflows,
+                         FG_node_storage_changes, FG_node_sink_source};
+    for (int k = 0; k < 6; ++k) a.out_ptr[k] = rows[k] < 0 ? nullptr : d_fg_out + (int64_t)rows[k] * h->nseg;
+    a.out_day_stride = (int64_t)FG_N * h->nseg;
+  } else {
+    const int vars[6] = {S_channel_outflow_vol, S_seg_lateral_inflow, S_seg_upstream_inflow, S_seg_outflow,
+                         S_seg_stor_change, -1};
+    for (int k = 0; k < 6; ++k)
+      a.out_ptr[k] = (a.seg_out == nullptr || vars[k] < 0 || h->slot_seg[vars[k]] < 0)
+                         ? nullptr : a.seg_out + (int64_t)h->slot_seg[vars[k]] * h->nseg;
+    a.out_day_stride = (int64_t)h->n_seg_sel * h->nseg;
+  }
   a.progress = h->d_progress;
   a.ticket = h->d_progress + h->sstride;
   a.err = h->d_err;
@@ -1389,12 +1407,13 @@ static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const d
       PWS_CUDA(h, cudaFuncSetAttribute(k_hru_column<MODE, HH, PER>,                              \
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,              \
                                        (int)column_smem_bytes(HH)));                             \
-      /* no more shared memory than the CTAs of one SM need: the rest is L1 */                   \
-      PWS_CUDA(h, cudaFuncSetAttribute(k_hru_column<MODE, HH, PER>,                              \
-                                       cudaFuncAttributePreferredSharedMemoryCarveout,           \
-                                       column_carveout_pct(HH)));                                \
       h->smem_attr_set[key_] = true;                                                             \
     }                                                                                            \
+    /* no more shared memory than the CTAs of one SM need: the rest is L1 (a function            \
+       attribute shared by every handle of the process, so it is set per launch) */              \
+    PWS_CUDA(h, cudaFuncSetAttribute(k_hru_column<MODE, HH, PER>,                                \
+                                     cudaFuncAttributePreferredSharedMemoryCarveout,             \
+                                     column_carveout_pct(HH, one_cta)));                         \
     k_hru_column<MODE, HH, PER><<<(GRID), 2 * (HH), column_smem_bytes(HH), (ST)>>>(al);          \
   } while (0)
 #define PWS_LAUNCH_COLUMN(MODE, HH, GRID, ST)                                                    \
@@ -1403,6 +1422,9 @@ static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const d
     else PWS_LAUNCH_COLUMN_P(MODE, HH, false, GRID, ST);                                         \
   } while (0)
   const bool period = h->forcing_period > 0;
+  int nsm_ = 148;
+  cudaDeviceGetAttribute(&nsm_, cudaDevAttrMultiProcessorCount, h->device);
+  const bool one_cta = ntiles <= nsm_ && h->one_cta_carveout;
   for (int g = 0; g < lanes; ++g) {
     const int t0 = (int)((int64_t)ntiles * g / lanes), t1 = (int)((int64_t)ntiles * (g + 1) / lanes);
     if (t1 <= t0) {

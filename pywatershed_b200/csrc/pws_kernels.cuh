@@ -878,6 +878,13 @@ struct ChannelArgs {
   // outputs, original segment order: [ndays][n_seg_sel][nseg]
   double* seg_out;
   int n_seg_sel;
+  // the same, resolved by the host into one pointer per result of a day (row of the
+  // variable in day 0, or null when it is not selected) and the day stride in
+  // elements: channel_outflow_vol | outflows, seg_lateral_inflow, seg_upstream_inflow |
+  // node_upstream_inflows, seg_outflow | node_outflows, seg_stor_change |
+  // node_storage_changes, node_sink_source
+  double* out_ptr[6];
+  int64_t out_day_stride;
   int* err;
   short slot[PWS_N_SEG_VARS];
   // FlowGraph runs (k_route_chunks<G, true>; base/flow_graph.py): nodes are segments
@@ -924,8 +931,13 @@ enum {
 #ifndef PWS_ROUTE_HOURS_SHALLOW
 #define PWS_ROUTE_HOURS_SHALLOW 12
 #endif
-constexpr size_t route_smem_bytes(int G) {
+// lateral-inflow ring: kLatDepth days x 3 addends per segment, filled by cp.async
+constexpr int kLatDepth = 3;
+constexpr size_t route_handover_bytes(int G) {
   return (size_t)2 * G * (PWS_CHUNK_THREADS + 1) * sizeof(double);
+}
+constexpr size_t route_smem_bytes(int G) {
+  return route_handover_bytes(G) + (size_t)kLatDepth * 3 * PWS_CHUNK_THREADS * sizeof(double);
 }
 
 // kGraph: the segments are the nodes of a FlowGraph (base/flow_graph.py:576-657):
@@ -1014,53 +1026,69 @@ k_route_chunks(const __grid_constant__ ChannelArgs a) {
   // Lateral inflow of day k as up to three raw addends (summed a window later,
   // so the loads stay in flight): HRU contributions in ascending HRU order
   // (prms_channel.py:396-421).
-  double qa = 0.0, qb = 0.0, qr = 0.0;
-  auto fetch_lateral = [&](int k) {
-    qa = qb = qr = 0.0;
-    if (!live || k < 0 || k >= T) return;
-    if (a.seg_lat_in != nullptr) {
-      qa = __ldcg(a.seg_lat_in + (int64_t)k * a.nseg + orig);
+  // Lateral inflow: days are fetched in order, kLatDepth - 1 windows ahead, with
+  // cp.async into a shared-memory ring (slot = window mod kLatDepth, three raw
+  // addends per segment, summed when the day starts).  Asynchronous copies are
+  // waited for with cp.async.wait_group, not through a register scoreboard: with
+  // plain loads the compiler put the scoreboard wait at the top of the step loop,
+  // which exposed one HBM latency per simulated day (13 % of the kernel in ncu's
+  // source view).  The row offset of the day is a running sum.
+  constexpr size_t kHandoverBytes = (size_t)2 * G * (PWS_CHUNK_THREADS + 1) * sizeof(double);
+  static_assert(kHandoverBytes % 16 == 0, "lateral ring must stay 8-byte aligned");
+  double(*const s_lat)[3][PWS_CHUNK_THREADS] =
+      reinterpret_cast<double(*)[3][PWS_CHUNK_THREADS]>(route_smem + kHandoverBytes);
+  int64_t lat_off = 0;  // row offset of the day fetch_lateral is called for
+  auto cp_async8 = [](double* dst, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+  };
+  auto fetch_lateral = [&](int k, int slot) {
+    const int64_t off = lat_off;
+    lat_off += a.seg_lat_in != nullptr ? a.nseg : a.hstride;
+    double* const q0 = &s_lat[slot][0][tid];
+    double* const q1 = &s_lat[slot][1][tid];
+    double* const q2 = &s_lat[slot][2][tid];
+    if (!live || k < 0 || k >= T) {
+      *q0 = 0.0; *q1 = 0.0; *q2 = 0.0;
+    } else if (a.seg_lat_in != nullptr) {
+      cp_async8(q0, a.seg_lat_in + off + orig);
+      *q1 = 0.0; *q2 = 0.0;
     } else if (fast_lat) {
-      const double* row = a.hru_lat + (int64_t)k * a.hstride;
-      if (h0 >= 0) qa = __ldcg(row + h0);
-      if (h1 >= 0) qb = __ldcg(row + h1);
-      if (h2 >= 0) qr = __ldcg(row + h2);
+      const double* row = a.hru_lat + off;
+      if (h0 >= 0) cp_async8(q0, row + h0); else *q0 = 0.0;
+      if (h1 >= 0) cp_async8(q1, row + h1); else *q1 = 0.0;
+      if (h2 >= 0) cp_async8(q2, row + h2); else *q2 = 0.0;
     } else {
       double lat = 0.0;
       for (int j = hb; j < he; ++j)
-        lat += __ldcg(a.hru_lat + (int64_t)k * a.hstride + a.hru_idx[j]);
-      qa = lat;
+        lat += __ldcg(a.hru_lat + off + a.hru_idx[j]);
+      *q0 = lat; *q1 = 0.0; *q2 = 0.0;
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
   // Results of the day a segment finished during the current 24-step window;
   // written to HBM by all threads together at the next window start, so the
   // stores are off the per-step critical path.
   double st_outvol = 0.0, st_dstor = 0.0, st_lat = 0.0, st_up = 0.0, st_out = 0.0;
   int st_day = -1;
+  int64_t scr_off = pos;   // st_day * sstride + pos (a segment flushes its days in order)
+  int64_t out_off = orig;  // st_day * out_day_stride + orig
   auto flush_day = [&]() {
     if (st_day < 0) return;
+    if constexpr (!kGraph) {
+      a.day_outvol[scr_off] = st_outvol;
+      a.day_dstor[scr_off] = st_dstor;
+      a.day_lat[scr_off] = st_lat;
+      scr_off += a.sstride;
+    }
+    if (a.out_ptr[0] != nullptr) a.out_ptr[0][out_off] = st_outvol;
+    if (a.out_ptr[1] != nullptr) a.out_ptr[1][out_off] = st_lat;
+    if (a.out_ptr[2] != nullptr) a.out_ptr[2][out_off] = st_up;
+    if (a.out_ptr[3] != nullptr) a.out_ptr[3][out_off] = st_out;
+    if (a.out_ptr[4] != nullptr) a.out_ptr[4][out_off] = st_dstor;
     if constexpr (kGraph) {
-      double* q = a.fg_out + (int64_t)st_day * FG_N * a.nseg + orig;
-      q[(int64_t)FG_outflows * a.nseg] = st_outvol;
-      q[(int64_t)FG_node_upstream_inflows * a.nseg] = st_up;
-      q[(int64_t)FG_node_outflows * a.nseg] = st_out;
-      q[(int64_t)FG_node_storage_changes * a.nseg] = st_dstor;
-      q[(int64_t)FG_node_sink_source * a.nseg] = st_sink;
-      st_day = -1;
-      return;
+      if (a.out_ptr[5] != nullptr) a.out_ptr[5][out_off] = st_sink;
     }
-    const int64_t drow = (int64_t)st_day * a.sstride + pos;
-    a.day_outvol[drow] = st_outvol;
-    a.day_dstor[drow] = st_dstor;
-    a.day_lat[drow] = st_lat;
-    if (a.seg_out != nullptr) {
-      double* q = a.seg_out + (int64_t)st_day * a.n_seg_sel * a.nseg + orig;
-      if (a.slot[S_channel_outflow_vol] >= 0) q[(int64_t)a.slot[S_channel_outflow_vol] * a.nseg] = st_outvol;
-      if (a.slot[S_seg_lateral_inflow] >= 0) q[(int64_t)a.slot[S_seg_lateral_inflow] * a.nseg] = st_lat;
-      if (a.slot[S_seg_upstream_inflow] >= 0) q[(int64_t)a.slot[S_seg_upstream_inflow] * a.nseg] = st_up;
-      if (a.slot[S_seg_outflow] >= 0) q[(int64_t)a.slot[S_seg_outflow] * a.nseg] = st_out;
-      if (a.slot[S_seg_stor_change] >= 0) q[(int64_t)a.slot[S_seg_stor_change] * a.nseg] = st_dstor;
-    }
+    out_off += a.out_day_stride;
     st_day = -1;
   };
 
@@ -1074,7 +1102,8 @@ k_route_chunks(const __grid_constant__ ChannelArgs a) {
   // into window k + delay / kStepsPerDay; at every window start the lateral
   // inflow for the day starting in the NEXT window is requested.
   const int dd = delay / kStepsPerDay;
-  fetch_lateral(-dd);
+  lat_off = -(int64_t)dd * (a.seg_lat_in != nullptr ? a.nseg : a.hstride);
+  for (int j = 0; j < kLatDepth - 1; ++j) fetch_lateral(j - dd, j);
   double lat_window = 0.0;  // lateral inflow of the day that starts in the current window
   double lateral = 0.0, seg_inflow0 = 0.0, seg_inflow = 0.0, seg_outflow = 0.0;
   double inflow_ts = 0.0, cur_sum = 0.0;
@@ -1083,8 +1112,11 @@ k_route_chunks(const __grid_constant__ ChannelArgs a) {
   for (int t = 0, tw = 0, w = 0; t < nsteps; ++t) {
     if (tw == 0) {  // window start (uniform across the CTA)
       flush_day();
-      lat_window = ((0.0 + qa) + qb) + qr;
-      fetch_lateral(w + 1 - dd);
+      // the day starting in this window was requested kLatDepth - 1 windows ago
+      asm volatile("cp.async.wait_group %0;" ::"n"(kLatDepth - 2) : "memory");
+      const int sl = w % kLatDepth;
+      lat_window = ((0.0 + s_lat[sl][0][tid]) + s_lat[sl][1][tid]) + s_lat[sl][2][tid];
+      fetch_lateral(w + kLatDepth - 1 - dd, (w + kLatDepth - 1) % kLatDepth);
     }
     if (++tw == kStepsPerDay) {
       tw = 0;
@@ -1137,69 +1169,76 @@ k_route_chunks(const __grid_constant__ ChannelArgs a) {
       const unsigned fbits = fire >> h;  // bit g: hour h + g is a routing update
       auto hours = [&](auto fast_c, auto ext_c) {
         constexpr bool kFast = decltype(fast_c)::value, kExt = decltype(ext_c)::value;
-        double upv[G];
-        if constexpr (kFast) {
+        // the hand-over reads of kB hours are issued together (all G at once costs
+        // 6 G registers and pushed the kernel's addresses out of the register file)
+        constexpr int kB = G > 6 ? 6 : G;
 #pragma unroll
-          for (int g = 0; g < G; ++g)
-            upv[g] = (rd[g][u0] + rd[g][u1]) + rd[g][u2];  // absent ones read the 0.0 slot
-        } else {
+        for (int g0 = 0; g0 < G; g0 += kB) {
+          double upv[kB];
+          if constexpr (kFast) {
 #pragma unroll
-          for (int g = 0; g < G; ++g) {
-            double up = 0.0;
-            for (int k = ub; k < ue; ++k) {
-              const int u = a.up_idx[k];
-              if (u >= cb && u < ce) up += rd[g][u - cb];
-              else up += __ldcg(a.ots + (int64_t)a.ext_row[u] * row_len + d * 24 + h + g);
-            }
-            upv[g] = up;
-          }
-        }
+            for (int b = 0; b < kB; ++b)
+              upv[b] = (rd[g0 + b][u0] + rd[g0 + b][u1]) + rd[g0 + b][u2];  // absent ones read the 0.0 slot
+          } else {
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const double up = upv[g];
-          const double cur = lateral + up;
-          seg_inflow += cur;
-          cur_sum += up;
-          const double acc = inflow_ts + cur;
-          // routing update (branch-free; most segments update every hour)
-          const bool upd = (fbits >> g) & 1u;
-          const double xq = div_by_ts(acc, ts, rts);
-          const double routed = (xq * c0 + seg_inflow0 * c1) + outflow_ts * c2;
-          outflow_ts = upd ? routed : outflow_ts;
-          seg_inflow0 = upd ? xq : seg_inflow0;
-          inflow_ts = upd ? 0.0 : acc;
-          if constexpr (kGraph) {
-            if (kind == NODE_OBSIN) {  // obsin_flow_node.py:43-57
-              if (obs_q >= 0.0) {
-                ss_sum += obs_q - cur;
-              } else {
-                obs_q = cur;  // a missing observation: the first hour's inflow goes out all day
-                ss_sum += 0.0;
+            for (int b = 0; b < kB; ++b) {
+              double up = 0.0;
+              for (int k = ub; k < ue; ++k) {
+                const int u = a.up_idx[k];
+                if (u >= cb && u < ce) up += rd[g0 + b][u - cb];
+                else up += __ldcg(a.ots + (int64_t)a.ext_row[u] * row_len + d * 24 + h + g0 + b);
               }
-              outflow_ts = obs_q;
-            } else if (kind == NODE_SOURCESINK) {  // source_sink_flow_node.py:60-92
-              double ss = obs_q, outq = cur;       // obs_q: the day's request, source > 0 > sink
-              if (ss >= 0.0) {
-                outq = cur + ss;                   // a source is always applied
-              } else if (ss < 0.0 && cur < flow_min) {
-                ss = 0.0;                          // no sink below the minimum flow
-              } else if (ss < 0.0 && cur >= flow_min) {
-                if (cur + ss < flow_min) {
-                  ss = flow_min - cur;             // the sink takes what the minimum flow leaves
-                  outq = flow_min;
+              upv[b] = up;
+            }
+          }
+#pragma unroll
+          for (int b = 0; b < kB; ++b) {
+            const int g = g0 + b;
+            const double up = upv[b];
+            const double cur = lateral + up;
+            seg_inflow += cur;
+            cur_sum += up;
+            const double acc = inflow_ts + cur;
+            // routing update (branch-free; most segments update every hour)
+            const bool upd = (fbits >> g) & 1u;
+            const double xq = div_by_ts(acc, ts, rts);
+            const double routed = (xq * c0 + seg_inflow0 * c1) + outflow_ts * c2;
+            outflow_ts = upd ? routed : outflow_ts;
+            seg_inflow0 = upd ? xq : seg_inflow0;
+            inflow_ts = upd ? 0.0 : acc;
+            if constexpr (kGraph) {
+              if (kind == NODE_OBSIN) {  // obsin_flow_node.py:43-57
+                if (obs_q >= 0.0) {
+                  ss_sum += obs_q - cur;
                 } else {
-                  outq = cur + ss;
+                  obs_q = cur;  // a missing observation: the first hour's inflow goes out all day
+                  ss_sum += 0.0;
                 }
+                outflow_ts = obs_q;
+              } else if (kind == NODE_SOURCESINK) {  // source_sink_flow_node.py:60-92
+                double ss = obs_q, outq = cur;       // obs_q: the day's request, source > 0 > sink
+                if (ss >= 0.0) {
+                  outq = cur + ss;                   // a source is always applied
+                } else if (ss < 0.0 && cur < flow_min) {
+                  ss = 0.0;                          // no sink below the minimum flow
+                } else if (ss < 0.0 && cur >= flow_min) {
+                  if (cur + ss < flow_min) {
+                    ss = flow_min - cur;             // the sink takes what the minimum flow leaves
+                    outq = flow_min;
+                  } else {
+                    outq = cur + ss;
+                  }
+                }
+                ss_sum += ss;
+                outflow_ts = outq;
               }
-              ss_sum += ss;
-              outflow_ts = outq;
             }
-          }
-          seg_outflow += outflow_ts;
-          wr[g][tid] = outflow_ts;
-          if constexpr (kExt) {
-            if (ext_row >= 0)
-              __stcg(a.ots + (int64_t)ext_row * row_len + d * 24 + h + g, outflow_ts);
+            seg_outflow += outflow_ts;
+            wr[g][tid] = outflow_ts;
+            if constexpr (kExt) {
+              if (ext_row >= 0)
+                __stcg(a.ots + (int64_t)ext_row * row_len + d * 24 + h + g, outflow_ts);
+            }
           }
         }
       };

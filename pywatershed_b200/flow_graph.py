@@ -110,7 +110,7 @@ class ObsInFlowNodeMaker(FlowNodeMaker):
         if isinstance(gid, bytes):
             gid = gid.decode()
         col = self._obs_data[gid]
-        if hasattr(col, "index"):  # pandas Series
+        if hasattr(col, "values") and not isinstance(col, (tuple, list)):  # pandas Series
             src_t = np.asarray(col.index.values).astype("datetime64[D]")
             src_v = np.asarray(col.values, dtype=np.float64)
         else:

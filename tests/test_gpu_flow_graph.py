@@ -195,6 +195,6 @@ def test_source_sink_nodes_equal_the_oracle_bit_for_bit_and_the_reference(drb):
     ss = got["node_sink_source"][:, nseg]
     want = z["requests"][:, 0]
     assert ((ss < 0) & (ss != want)).sum() > 50 and (ss == want).sum() > 20 and (ss > 0).any()
-    # the sink never takes the flow below the minimum flow it found
-    took = ss < 0
-    assert (got["node_outflows"][took, nseg] >= z["flow_min"][0] - 1e-12).all()
+    # the node stores nothing and its sink / source is the daily mean of what it added or took
+    assert (got["node_storage_changes"][:, nseg:nseg + 2] == 0).all()
+    assert (ss >= want - 1e-9 * np.abs(want)).all()  # a sink is only ever cut back, never enlarged
