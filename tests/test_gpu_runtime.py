@@ -357,3 +357,20 @@ def test_cross_chunk_deadlock_guard_reports(drb):
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "waited too long for its upstream segments" in r.stdout, r.stdout
+
+
+def test_sanitize_case_runs_clean():
+    """tools/sanitize_case.py -- the small case written for compute-sanitizer (every
+    kernel variant: several column tiles, two lanes, routing beside the next block,
+    cross-chunk edges, a shared-forcing ensemble in the tiled layout, accumulations,
+    PRMSEt) -- checked against the oracle.  The sanitizer itself is closed on the
+    build pool (profiles/r02_sanitizer_closed.log); this keeps the case alive."""
+    import pathlib as pl
+    import subprocess
+    import sys
+
+    root = pl.Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, str(root / "tools" / "sanitize_case.py")], capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "sanitize case ok" in r.stdout
