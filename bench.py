@@ -699,6 +699,8 @@ def main():
                     help="segments per routing CTA (library option channel_chunk; default 512)")
     ap.add_argument("--column-hrus", type=int, default=None, choices=(128, 256),
                     help="HRUs per column CTA (library option column_hrus; default: by domain size)")
+    ap.add_argument("--lib-opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="pws_set_option(NAME, VALUE) on every engine (tuning aid), e.g. wide_column=0")
     ap.add_argument("--shard-of", type=int, default=None,
                     help="tuning aid on ONE GPU: run rank 0's share of an N-way split; `value` is then "
                          "what N GPUs would give if every rank took as long as this one")
@@ -728,6 +730,9 @@ def main():
                      channel_chunk=args.channel_chunk)
         if args.column_hrus is not None:
             eng._opt("column_hrus", args.column_hrus)
+        for kv in args.lib_opt:
+            k, v = kv.split("=", 1)
+            eng._opt(k, float(v))
         if args.overlap is not None:
             eng._opt("overlap_routing", args.overlap)
         return eng

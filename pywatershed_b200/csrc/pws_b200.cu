@@ -102,7 +102,8 @@ struct pws_handle {
   int overlap_routing = -1;  // option "overlap_routing": routing of block b beside the column of b+1 (-1: by domain size)
   int64_t forcing_period = 0;  // option "forcing_period": forcings are [ndays][period], HRU i reads i % period
   bool route_attr_set = false;
-  bool smem_attr_set[16] = {};
+  bool smem_attr_set[32] = {};
+  bool wide_column = true;  // option "wide_column": the uncapped-register column variant on grids of <= one CTA per SM
   bool one_cta_carveout = true;  // option "one_cta_carveout": L1-heavy carve-out for grids of <= one CTA per SM
   bool tiled_outputs = false;  // option "tiled_outputs": [day][tile][variable][H] (SINK_TILED)
   int column_hrus_opt = 0;  // option "column_hrus": 0 = by domain size, else 128 | 256
@@ -450,6 +451,7 @@ extern "C" int pws_set_option(pws_handle* h, const char* name, double value) {
     h->lanes_opt = (int)value;
     return 0;
   }
+  else if (!strcmp(name, "wide_column")) { h->wide_column = value != 0.0; return 0; }
   else if (!strcmp(name, "one_cta_carveout")) { h->one_cta_carveout = value != 0.0; return 0; }
   else if (!strcmp(name, "overlap_routing")) { h->overlap_routing = value < 0 ? -1 : (value != 0.0); return 0; }
   else if (!strcmp(name, "accumulate")) { h->accumulate_on = value != 0.0; return 0; }
@@ -1400,31 +1402,32 @@ static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const d
   const int lanes = column_lanes(h, ntiles, H);
   const bool overlap = overlap_routing(h, ntiles, H, lanes);
   a.ntiles = ntiles;
-#define PWS_LAUNCH_COLUMN_P(MODE, HH, PER, GRID, ST)                                             \
+#define PWS_LAUNCH_COLUMN_P(MODE, HH, PER, WIDE, GRID, ST)                                       \
   do {                                                                                           \
-    const int key_ = ((MODE) * 2 + ((HH) == 128)) * 2 + (PER);                                   \
+    const int key_ = (((MODE) * 2 + ((HH) == 128)) * 2 + (PER)) * 2 + (WIDE);                    \
     if (!h->smem_attr_set[key_]) {                                                               \
-      PWS_CUDA(h, cudaFuncSetAttribute(k_hru_column<MODE, HH, PER>,                              \
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize,              \
-                                       (int)column_smem_bytes(HH)));                             \
+      PWS_CUDA(h, (cudaFuncSetAttribute(k_hru_column<MODE, HH, PER, WIDE>,                       \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,             \
+                                        (int)column_smem_bytes(HH))));                           \
       h->smem_attr_set[key_] = true;                                                             \
     }                                                                                            \
     /* no more shared memory than the CTAs of one SM need: the rest is L1 (a function            \
        attribute shared by every handle of the process, so it is set per launch) */              \
-    PWS_CUDA(h, cudaFuncSetAttribute(k_hru_column<MODE, HH, PER>,                                \
-                                     cudaFuncAttributePreferredSharedMemoryCarveout,             \
-                                     column_carveout_pct(HH, one_cta)));                         \
-    k_hru_column<MODE, HH, PER><<<(GRID), 2 * (HH), column_smem_bytes(HH), (ST)>>>(al);          \
+    PWS_CUDA(h, (cudaFuncSetAttribute(k_hru_column<MODE, HH, PER, WIDE>,                         \
+                                      cudaFuncAttributePreferredSharedMemoryCarveout,            \
+                                      column_carveout_pct(HH, one_cta))));                       \
+    k_hru_column<MODE, HH, PER, WIDE><<<(GRID), 2 * (HH), column_smem_bytes(HH), (ST)>>>(al);    \
   } while (0)
 #define PWS_LAUNCH_COLUMN(MODE, HH, GRID, ST)                                                    \
   do {                                                                                           \
-    if (period) PWS_LAUNCH_COLUMN_P(MODE, HH, true, GRID, ST);                                   \
-    else PWS_LAUNCH_COLUMN_P(MODE, HH, false, GRID, ST);                                         \
+    if (period) PWS_LAUNCH_COLUMN_P(MODE, HH, true, false, GRID, ST);                            \
+    else PWS_LAUNCH_COLUMN_P(MODE, HH, false, false, GRID, ST);                                  \
   } while (0)
   const bool period = h->forcing_period > 0;
   int nsm_ = 148;
   cudaDeviceGetAttribute(&nsm_, cudaDevAttrMultiProcessorCount, h->device);
   const bool one_cta = ntiles <= nsm_ && h->one_cta_carveout;
+  const bool wide = one_cta && !period && h->wide_column;
   for (int g = 0; g < lanes; ++g) {
     const int t0 = (int)((int64_t)ntiles * g / lanes), t1 = (int)((int64_t)ntiles * (g + 1) / lanes);
     if (t1 <= t0) {
@@ -1440,7 +1443,12 @@ static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const d
     cudaEvent_t e0 = new_event(h), e1 = new_event(h);
     mark_base(h, st);
     cudaEventRecord(e0, st);
-    if (H == 128) {
+    if (H == 128 && wide) {  // at most one CTA per SM: the variant without a register cap
+      if (mode == SINK_FULL) PWS_LAUNCH_COLUMN_P(SINK_FULL, 128, false, true, grid, st);
+      else if (mode == SINK_TILED) PWS_LAUNCH_COLUMN_P(SINK_TILED, 128, false, true, grid, st);
+      else if (mode == SINK_NONE) PWS_LAUNCH_COLUMN_P(SINK_NONE, 128, false, true, grid, st);
+      else PWS_LAUNCH_COLUMN_P(SINK_SELECT, 128, false, true, grid, st);
+    } else if (H == 128) {
       if (mode == SINK_FULL) PWS_LAUNCH_COLUMN(SINK_FULL, 128, grid, st);
       else if (mode == SINK_TILED) PWS_LAUNCH_COLUMN(SINK_TILED, 128, grid, st);
       else if (mode == SINK_NONE) PWS_LAUNCH_COLUMN(SINK_NONE, 128, grid, st);

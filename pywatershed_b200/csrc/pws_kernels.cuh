@@ -395,9 +395,13 @@ struct LowerStateMixed {
 // kPeriod: the forcing arrays are [ndays][fperiod] (shared-forcing ensembles); a
 // separate instantiation because the wrap-around addressing costs the plain
 // kernel 16 bytes of spills and 120 instructions even when it is not taken.
-template <int kMode, int H, bool kPeriod = false>
-__global__ void __launch_bounds__(2 * H, (2 * H <= 256) ? 512 / (2 * H) : 1)
+// kWide: one CTA per SM (launch bounds (2 H, 1), no setmaxnreg): for grids of at
+// most one CTA per SM -- small domains, the basin shard of a multi-GPU run -- where
+// the register file is not what limits residency, so neither half needs to spill.
+template <int kMode, int H, bool kPeriod = false, bool kWide = false>
+__global__ void __launch_bounds__(2 * H, (2 * H <= 256 && !kWide) ? 512 / (2 * H) : 1)
 k_hru_column(const __grid_constant__ ColumnArgs a) {
+  static_assert(!kWide || H == 128, "the wide variant is built for 128 HRUs per CTA");
   // setmaxnreg acts on whole warpgroups (4 warps): each half must be a multiple of one
   static_assert(H % 128 == 0, "HRUs per CTA must be a multiple of 128");
   constexpr size_t kColumnParamBytes = ColumnSmem<H>::kParamBytes;
@@ -454,11 +458,13 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
   Q.stride = 0;  // monthly rows: only the current month is staged
 
   if (upper) {
+    if constexpr (!kWide) {
 #if PWS_COLUMN_REGS_UPPER < PWS_COLUMN_REGS_LOWER
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PWS_COLUMN_REGS_UPPER));
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PWS_COLUMN_REGS_UPPER));
 #elif PWS_COLUMN_REGS_UPPER > PWS_COLUMN_REGS_LOWER
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PWS_COLUMN_REGS_UPPER));
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PWS_COLUMN_REGS_UPPER));
 #endif
+    }
 #define PWS_LOADST_F(name) s.name = a.state[(int64_t)ST_##name * S + ii];
 #define PWS_LOADST_I(name) s.name = (int)a.state[(int64_t)ST_##name * S + ii];
 #define X(name, kind) PWS_LOADST_##kind(name)
@@ -629,11 +635,13 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
 #undef X
     }
   } else {
+    if constexpr (!kWide) {
 #if PWS_COLUMN_REGS_UPPER < PWS_COLUMN_REGS_LOWER
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PWS_COLUMN_REGS_LOWER));
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PWS_COLUMN_REGS_LOWER));
 #elif PWS_COLUMN_REGS_UPPER > PWS_COLUMN_REGS_LOWER
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PWS_COLUMN_REGS_LOWER));
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PWS_COLUMN_REGS_LOWER));
 #endif
+    }
 #if PWS_COLUMN_LOWER_STATE_SMEM == 2
     int ks = 0;
 #define X(name) double& sm_##name = spS[(ks++) * H + r]; sm_##name = a.state[(int64_t)ST_##name * S + ii];
