@@ -524,25 +524,34 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
     // forcing column of the CTA's first HRU; with a forcing period the CTA's row
     // may wrap around the end of the period once (fill_column_args only allows
     // TMA for an even period >= H, so both pieces stay 16-byte aligned)
-    const uint32_t fcol0 = kPeriod ? (a.hru_base + (uint32_t)hru0) % a.fperiod : (uint32_t)hru0;
-    const uint32_t head_bytes =
-        (kPeriod && fcol0 + (uint32_t)row_n > a.fperiod) ? (a.fperiod - fcol0) * 8u : row_bytes;
+    [[maybe_unused]] uint32_t fcol0 = 0, head_bytes = row_bytes;
+    if constexpr (kPeriod) {
+      fcol0 = (a.hru_base + (uint32_t)hru0) % a.fperiod;
+      if (fcol0 + (uint32_t)row_n > a.fperiod) head_bytes = (a.fperiod - fcol0) * 8u;
+    }
     auto tma_issue = [&](int d) {  // one thread
       const uint32_t bar = mbar0;
       const uint32_t dst = smem_u32(sF);
       const int doy = a.cal[d].x;
-      const int64_t fo = (int64_t)d * a.fstride + fcol0;
       const int64_t so = (int64_t)(doy - 1) * S + hru0;
       mbar_expect_tx(bar, kForcRows * row_bytes + 16u);
       tma_bulk_g2s(smem_u32(sCal + 4 * (d & 1)), a.cal + d, 16u, bar);
-      tma_bulk_g2s(dst + 0 * H * 8, a.prcp + fo, head_bytes, bar);
-      tma_bulk_g2s(dst + 1 * H * 8, a.tmax + fo, head_bytes, bar);
-      tma_bulk_g2s(dst + 2 * H * 8, a.tmin + fo, head_bytes, bar);
-      if (kPeriod && head_bytes != row_bytes) {  // the rest of the row starts the period again
-        const int64_t f0 = (int64_t)d * a.fstride;
-        tma_bulk_g2s(dst + 0 * H * 8 + head_bytes, a.prcp + f0, row_bytes - head_bytes, bar);
-        tma_bulk_g2s(dst + 1 * H * 8 + head_bytes, a.tmax + f0, row_bytes - head_bytes, bar);
-        tma_bulk_g2s(dst + 2 * H * 8 + head_bytes, a.tmin + f0, row_bytes - head_bytes, bar);
+      if constexpr (!kPeriod) {
+        const int64_t fo = (int64_t)d * a.fstride + hru0;
+        tma_bulk_g2s(dst + 0 * H * 8, a.prcp + fo, row_bytes, bar);
+        tma_bulk_g2s(dst + 1 * H * 8, a.tmax + fo, row_bytes, bar);
+        tma_bulk_g2s(dst + 2 * H * 8, a.tmin + fo, row_bytes, bar);
+      } else {
+        const int64_t fo = (int64_t)d * a.fstride + fcol0;
+        tma_bulk_g2s(dst + 0 * H * 8, a.prcp + fo, head_bytes, bar);
+        tma_bulk_g2s(dst + 1 * H * 8, a.tmax + fo, head_bytes, bar);
+        tma_bulk_g2s(dst + 2 * H * 8, a.tmin + fo, head_bytes, bar);
+        if (head_bytes != row_bytes) {  // the rest of the row starts the period again
+          const int64_t f0 = (int64_t)d * a.fstride;
+          tma_bulk_g2s(dst + 0 * H * 8 + head_bytes, a.prcp + f0, row_bytes - head_bytes, bar);
+          tma_bulk_g2s(dst + 1 * H * 8 + head_bytes, a.tmax + f0, row_bytes - head_bytes, bar);
+          tma_bulk_g2s(dst + 2 * H * 8 + head_bytes, a.tmin + f0, row_bytes - head_bytes, bar);
+        }
       }
       tma_bulk_g2s(dst + 3 * H * 8, a.P.soltab_potsw + so, row_bytes, bar);
       tma_bulk_g2s(dst + 4 * H * 8, a.P.soltab_horad_potsw + so, row_bytes, bar);
@@ -560,7 +569,8 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
     } else {
       const int4 c = a.cal[0];
       nxt.doy = c.x; nxt.dowy = c.y; nxt.month = c.z; nxt.dom = c.w;
-      const uint32_t fcol = kPeriod ? (a.hru_base + (uint32_t)ii) % a.fperiod : (uint32_t)ii;
+      int64_t fcol = ii;
+      if constexpr (kPeriod) fcol = (a.hru_base + (uint32_t)ii) % a.fperiod;
       nxt.prcp = __ldcs(a.prcp + fcol);
       nxt.tmax = __ldcs(a.tmax + fcol);
       nxt.tmin = __ldcs(a.tmin + fcol);
@@ -588,8 +598,9 @@ k_hru_column(const __grid_constant__ ColumnArgs a) {
         in.cal = reinterpret_cast<const int*>(a.cal + d);
         if (d + 1 < a.ndays) {
           const int4 c = a.cal[d + 1];
-          const int64_t fo = (int64_t)(d + 1) * a.fstride +
-                             (kPeriod ? (a.hru_base + (uint32_t)ii) % a.fperiod : (uint32_t)ii);
+          int64_t fo = (int64_t)(d + 1) * a.fstride;
+          if constexpr (kPeriod) fo += (a.hru_base + (uint32_t)ii) % a.fperiod;
+          else fo += ii;
           nxt.doy = c.x; nxt.dowy = c.y; nxt.month = c.z; nxt.dom = c.w;
           nxt.prcp = __ldcs(a.prcp + fo);
           nxt.tmax = __ldcs(a.tmax + fo);
