@@ -230,6 +230,50 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def parity_check(device=0, ndays=731):
+    """The checker beside the CPU baseline: the reference's own drb_2yr case
+    (BASELINE.json configs[0]) through the C ABI against the oracle -- every
+    public variable of every day at rtol 1e-9 / atol 1e-10, ghost-pack ties
+    (tests/parity.py) counted and audited.  The oracle is only the checker here."""
+    for q in (ROOT / "oracle", ROOT / "tests"):
+        if str(q) not in sys.path:
+            sys.path.insert(0, str(q))
+    import parity
+    import prms_oracle as po
+    import scenarios
+    from pywatershed_b200 import Engine
+
+    p, f, start = scenarios.load_drb()
+    nd = min(ndays, f["prcp"].shape[0])
+    eng = Engine(p, start, device=device)
+    eng.select_outputs(eng.reg.hru_vars, eng.reg.seg_vars)
+    got, viol = eng.run_host(f["prcp"][:nd], f["tmax"][:nd], f["tmin"][:nd])
+    eng.close()
+    ref, oviol = po.Oracle(p, start=start).run(f["prcp"][:nd], f["tmax"][:nd], f["tmin"][:nd],
+                                               po.HRU_VARS, po.SEG_VARS)
+    rep = parity.compare_columns(got, ref, po.HRU_VARS, got["pkwater_equiv"], ref["pkwater_equiv"])
+    out = {"domain": f"drb_2yr: 765 HRUs x {nd} days x {len(po.HRU_VARS)} HRU + {len(po.SEG_VARS)} segment "
+                     "variables, GPU (C ABI) against the C oracle pinned to the reference",
+           "rtol": parity.RTOL, "atol": parity.ATOL, "ghost_pack_ties": len(rep["ties"]),
+           "mismatches": len(rep["mismatches"]), "max_post_tie_cum_rel": 0.0,
+           "budget_verdicts_equal": bool((np.asarray(viol) == np.asarray(oviol)).all())}
+    if rep["ties"]:
+        try:
+            out["max_post_tie_cum_rel"] = parity.audit_ties(got, ref, rep, got["pkwater_equiv"],
+                                                            ref["pkwater_equiv"])["max_cum_rel"]
+        except AssertionError as exc:
+            out["audit_failed"] = str(exc)[:200]
+    tied = [t[0] for t in rep["ties"]]
+    try:
+        seg = parity.assert_segments_with_ties(got, ref, po.SEG_VARS, p["tosegment"], p["hru_segment"], tied)
+        out["segments_within_tolerance"] = True
+        out["max_cum_seg_rel_downstream_of_ties"] = seg["max_cum_seg_rel"]
+    except AssertionError as exc:
+        out["segments_within_tolerance"] = False
+        out["segment_error"] = str(exc)[:200]
+    return out
+
+
 def cpu_oracle_rate(p0, f0, start, ntile_per_thread, ndays, nthreads):
     """HRU-days/s of the C oracle (oracle/prms_oracle.c): `nthreads` threads,
     each simulating `ntile_per_thread` DRB tiles for `ndays` days (ctypes
@@ -945,6 +989,11 @@ def main():
         cpu = {"value": r, "unit": UNIT, "cores": nthreads, "kind": "port",
                "sample": f"{nthreads} threads x 1 DRB tile x {min(nd, 3653)} days "
                          f"({units:.3g} HRU-days, {dt:.1f} s), C oracle, full chain + routing + budgets"}
+        if not args.no_extras:
+            try:
+                extras["parity"] = parity_check(D.local_rank)
+            except Exception as exc:  # the checker must not take the bench line down
+                extras["parity"] = {"error": f"{type(exc).__name__}: {exc}"}
         if reference_available() and not args.no_extras:
             # north_star: the reference's numpy and numba paths on this box's cores, same run
             for cm, ndr in (("numba", 731), ("numpy", 120)):

@@ -22,7 +22,8 @@ def _tiled(drb, ntile, nd):
 def _run(pt, ft, start, hv, sv, block_days=None, **kw):
     from pywatershed_b200 import Engine
 
-    opts = {k: kw.pop(k) for k in ("overlap_routing", "column_hrus") if k in kw}
+    opts = {k: kw.pop(k) for k in ("overlap_routing", "column_hrus", "wide_column", "one_cta_carveout")
+            if k in kw}
     e = Engine(pt, start, **kw)
     for k, v in opts.items():
         e._opt(k, v)
@@ -56,6 +57,27 @@ def test_lanes_and_routing_overlap_are_transparent(drb, lanes, overlap):
         np.testing.assert_array_equal(np.asarray(got[k]), np.asarray(base[k]), err_msg=k)
     np.testing.assert_array_equal(vg, vb)
     assert vb.sum() == 0
+
+
+@pytest.mark.parametrize("outputs", ["full", "select", "none"])
+def test_column_kernel_variants_agree(drb, outputs):
+    """The instantiations of k_hru_column a domain may be run with -- 256 or 128
+    HRUs per CTA, and for grids of at most one CTA per SM the uncapped-register
+    `wide` variant with the one-CTA carve-out (the default at this size) or the
+    capped one -- are the same arithmetic: bit-identical results in every sink mode."""
+    nd = 45
+    pt, ft, start = _tiled(drb, 2, nd)
+    reg_h, reg_s = po.HRU_VARS, po.SEG_VARS
+    hv = {"full": list(reg_h), "select": ["pkwater_equiv", "soil_moist", "newsnow", "sroff", "gwres_stor"],
+          "none": []}[outputs]
+    sv = list(reg_s)
+    base, vb, _ = _run(pt, ft, start, hv, sv, block_days=16, column_hrus=256)
+    for opts in (dict(column_hrus=128, wide_column=1), dict(column_hrus=128, wide_column=0),
+                 dict(column_hrus=128, wide_column=0, one_cta_carveout=0)):
+        got, vg, _ = _run(pt, ft, start, hv, sv, block_days=16, **opts)
+        for k in hv + sv:
+            np.testing.assert_array_equal(np.asarray(got[k]), np.asarray(base[k]), err_msg=f"{k} {opts}")
+        np.testing.assert_array_equal(vg, vb)
 
 
 def test_device_resident_blocks_overlap_safely(drb):
