@@ -8,6 +8,7 @@ from .flow_graph import (  # noqa: F401
     FlowGraph,
     FlowNode,
     FlowNodeMaker,
+    HruNodeFlowExchange,
     HruSegmentFlowAdapter,
     ObsInFlowNodeMaker,
     ObsInNodeMaker,
@@ -16,6 +17,7 @@ from .flow_graph import (  # noqa: F401
     PRMSChannelFlowNodeMaker,
     SourceSinkFlowNodeMaker,
     prms_channel_flow_graph_postprocess,
+    prms_channel_flow_graph_to_model_dict,
 )
 from .model import Model  # noqa: F401
 from .parameters import Parameters, PrmsParameters  # noqa: F401
@@ -45,5 +47,5 @@ __all__ = [
     "PRMSGroundwaterNoDprst", "PRMSEt", "FlowGraph", "FlowNode", "FlowNodeMaker",
     "PRMSChannelFlowNodeMaker", "PassThroughFlowNodeMaker", "PassThroughNodeMaker",
     "ObsInFlowNodeMaker", "ObsInNodeMaker", "SourceSinkFlowNodeMaker", "HruSegmentFlowAdapter",
-    "prms_channel_flow_graph_postprocess",
+    "prms_channel_flow_graph_postprocess", "prms_channel_flow_graph_to_model_dict", "HruNodeFlowExchange",
 ]

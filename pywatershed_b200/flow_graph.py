@@ -532,6 +532,160 @@ class HruSegmentFlowAdapter:
         return self._current_value
 
 
+class HruNodeFlowExchange:
+    """hydrology/prms_channel_flow_graph.py:501-620: maps the three HRU outflow
+    volumes of the PRMS column onto the lateral inflows of a FlowGraph's nodes
+    inside a Model (HRUs without a segment go to `sinks`; nodes that are not PRMS
+    segments get nothing).  Global-basis budget.  Under `Model` it is evaluated
+    for a whole block of days at once (`block()`); it has no state."""
+
+    _all_time = False
+    VARIABLES = ("inflows", "inflows_vol", "sinks", "sinks_vol")
+
+    def __init__(self, control, discretization, parameters, sroff_vol=None, ssres_flow_vol=None,
+                 gwres_flow_vol=None, budget_type="defer", verbose: bool = None, name: str = None):
+        self.name = name or "HruNodeFlowExchange"
+        self.control = control
+        self.params = parameters
+        p = {}
+        for src in (discretization, parameters):
+            if src is not None:
+                p.update(as_param_dict(src))
+        for k in self.get_parameters():
+            if k not in p:
+                raise ValueError(f"{self.name}: parameters missing: ['{k}']")  # base/process.py:233-237
+        self._param_dict = p
+        self._hru_segment = np.asarray(p["hru_segment"], dtype=np.int64) - 1
+        self.nhru = int(self._hru_segment.shape[0])
+        self.nnodes = int(np.asarray(p["node_coord"]).shape[0])
+        self._input_variables_dict = {"sroff_vol": sroff_vol, "ssres_flow_vol": ssres_flow_vol,
+                                      "gwres_flow_vol": gwres_flow_vol}
+        self._vars = {"inflows": np.full(self.nnodes, np.nan), "inflows_vol": np.full(self.nnodes, np.nan),
+                      "sinks": np.full(self.nhru, np.nan), "sinks_vol": np.full(self.nhru, np.nan)}
+        if budget_type == "defer":
+            budget_type = control.options.get("budget_type", "warn") if hasattr(control, "options") else "warn"
+        self._budget_type = budget_type
+        self._model = None
+        self._netcdf_initialized = False
+        self.budget = None
+        if budget_type is not None:
+            self.budget = Budget(control, self, self.get_mass_budget_terms(), budget_type, basis="global",
+                                 description=self.name)
+
+    @staticmethod
+    def get_dimensions() -> tuple:
+        return ("nhru", "nnodes")
+
+    @staticmethod
+    def get_parameters() -> tuple:
+        return ("hru_segment", "node_coord")
+
+    @staticmethod
+    def get_inputs() -> tuple:
+        return ("sroff_vol", "ssres_flow_vol", "gwres_flow_vol")
+
+    @staticmethod
+    def get_init_values() -> dict:
+        return {k: np.nan for k in HruNodeFlowExchange.VARIABLES}
+
+    @classmethod
+    def get_variables(cls) -> tuple:
+        return tuple(cls.VARIABLES)
+
+    @staticmethod
+    def get_mass_budget_terms():
+        return {"inputs": ["sroff_vol", "ssres_flow_vol", "gwres_flow_vol"],
+                "outputs": ["inflows_vol", "sinks_vol"], "storage_changes": []}
+
+    @staticmethod
+    def get_restart_variables() -> tuple:
+        return ()
+
+    def block(self, sroff_vol, ssres_flow_vol, gwres_flow_vol) -> dict:
+        """The exchange for [ndays, nhru] input volumes (:593-618), day by day the
+        arithmetic of _calculate: sum of the three / seconds per step, added per
+        node in ascending HRU order."""
+        s_per_time = float(self.control.time_step / np.timedelta64(1, "s"))
+        total = (0 + np.asarray(sroff_vol, dtype=np.float64) + np.asarray(ssres_flow_vol, dtype=np.float64)
+                 + np.asarray(gwres_flow_vol, dtype=np.float64)) / s_per_time
+        nd = total.shape[0]
+        inflows = np.zeros((nd, self.nnodes))
+        sinks = np.zeros((nd, self.nhru))
+        for ihru in range(self.nhru):
+            iseg = self._hru_segment[ihru]
+            if iseg < 0:
+                sinks[:, ihru] += total[:, ihru]
+            else:
+                inflows[:, iseg] += total[:, ihru]
+        return {"inflows": inflows, "inflows_vol": inflows * s_per_time, "sinks": sinks,
+                "sinks_vol": sinks * s_per_time}
+
+    def __getitem__(self, key):
+        if key in self._vars:
+            return self._vars[key]
+        if key in self._input_variables_dict and self._model is not None:
+            for proc in self._model.processes.values():
+                if proc is not self and key in getattr(proc, "_vars", {}):
+                    return proc._vars[key]
+        if key in self._param_dict:
+            return self._param_dict[key]
+        return getattr(self, key)
+
+    def __getattr__(self, key):
+        v = self.__dict__.get("_vars")
+        if v is not None and key in v:
+            return v[key]
+        raise AttributeError(key)
+
+    def advance(self):
+        pass
+
+    def calculate(self, time_length: float = 1.0, **kwargs):
+        if self._model is None:
+            raise RuntimeError("HruNodeFlowExchange computes inside a Model")
+
+    def output(self):
+        pass
+
+    def finalize(self):
+        pass
+
+
+def prms_channel_flow_graph_to_model_dict(model_dict: dict, prms_channel_dis, prms_channel_dis_name: str,
+                                          prms_channel_params, new_nodes_maker_dict: dict,
+                                          new_nodes_maker_names: list, new_nodes_maker_indices: list,
+                                          new_nodes_maker_ids: list, new_nodes_flow_to_nhm_seg: list,
+                                          addtl_output_vars: list = None, graph_budget_type="defer",
+                                          allow_disconnected_nodes: bool = False,
+                                          type_check_nodes: bool = False) -> dict:
+    """hydrology/prms_channel_flow_graph.py:746-895: add an exchange
+    (`inflow_exchange`) and a FlowGraph (`prms_channel_flow_graph`) of
+    PRMSChannel's segments + new nodes to a model_dict whose processes produce
+    sroff_vol / ssres_flow_vol / gwres_flow_vol; the new nodes get no lateral
+    inflow."""
+    params_fg, makers = _build_flow_graph_inputs(
+        prms_channel_dis, prms_channel_params, new_nodes_maker_dict, new_nodes_maker_names,
+        new_nodes_maker_indices, new_nodes_maker_ids, new_nodes_flow_to_nhm_seg)
+    nnodes = params_fg.dims["nnodes"]
+    pc = as_param_dict(prms_channel_params)
+    ex_data = dict(pc)
+    ex_data["node_coord"] = np.arange(nnodes)
+    params_exchange = Parameters(dims={"nnodes": nnodes, "nhru": int(np.asarray(ex_data["hru_segment"]).shape[0])},
+                                 coords={"node_coord": ex_data.pop("node_coord")}, data_vars=ex_data)
+    graph_dict = {
+        "inflow_exchange": {"class": HruNodeFlowExchange, "parameters": params_exchange,
+                            "dis": prms_channel_dis_name},
+        "prms_channel_flow_graph": {"class": FlowGraph, "node_maker_dict": makers, "parameters": params_fg,
+                                    "dis": None, "budget_type": graph_budget_type,
+                                    "addtl_output_vars": addtl_output_vars,
+                                    "allow_disconnected_nodes": allow_disconnected_nodes},
+    }
+    out = dict(model_dict)
+    out["model_order"] = list(model_dict["model_order"]) + list(graph_dict.keys())
+    out.update(graph_dict)
+    return out
+
+
 def _build_flow_graph_inputs(prms_channel_dis, prms_channel_params, new_nodes_maker_dict: dict,
                              new_nodes_maker_names: list, new_nodes_maker_indices: list,
                              new_nodes_maker_ids: list, new_nodes_flow_to_nhm_seg: list):

@@ -65,6 +65,7 @@ class Model:
         self._param_dict = {}
         for n in order:
             self._param_dict.update(self.processes[n]._param_dict)
+        self._build_tail(proc_kwargs)
         self._engine = None
         self._forcings = None
         self._block = None
@@ -81,6 +82,76 @@ class Model:
         self.block_days = self.control.options.get("block_days") or None
         if write_control:
             self._write_control(write_control)
+
+    def _build_tail(self, proc_kwargs):
+        """A FlowGraph behind the PRMS column (model_dict entries made by
+        flow_graph.prms_channel_flow_graph_to_model_dict, the reference's
+        nhm + obsin / starfit configurations): `inflow_exchange` maps the column's
+        three outflow volumes to node inflows, the FlowGraph routes them.  Both are
+        evaluated per block of days right after the column's block."""
+        self._tail = []
+        spec = getattr(self, "_tail_spec", [])
+        if not spec:
+            return
+        from .flow_graph import FlowGraph, HruNodeFlowExchange
+
+        if self._mode != "chain":
+            raise NotImplementedError("a FlowGraph in a Model follows the full PRMS column without PRMSChannel")
+        exchange = graph = None
+        for key, cls, kw in spec:
+            kw = dict(kw)
+            dis = kw.pop("dis", None)
+            par = kw.pop("parameters", self.parameters)
+            if issubclass(cls, HruNodeFlowExchange):
+                exchange = cls(self.control, dis, par, name=key, **kw)
+                obj = exchange
+            else:
+                if exchange is None:
+                    raise ValueError("model_dict: the FlowGraph needs an inflow exchange before it")
+                kw.pop("addtl_output_vars", None)
+                nn = int(np.asarray(as_param_dict(par)["to_graph_index"]).shape[0])
+                graph = cls(self.control, dis, par, np.zeros((self.control.n_times, nn)), device=None, **kw)
+                graph.name = key
+                graph._inflow_valid = 0  # days of inflows the column has produced so far
+                obj = graph
+            obj._model = self
+            self.processes[key] = obj
+            self.process_order.append(key)
+            self._tail.append(obj)
+        if graph is None:
+            raise ValueError("model_dict: an inflow exchange without a FlowGraph")
+        self._tail_exchange, self._tail_graph = exchange, graph
+
+    def _tail_block(self, blk, t0, n):
+        """The exchange and the FlowGraph for the block the column just computed."""
+        ex, fg = self._tail_exchange, self._tail_graph
+        blk.update(ex.block(blk["sroff_vol"], blk["ssres_flow_vol"], blk["gwres_flow_vol"]))
+        fg._ensure_engine()
+        fg._inflow_data[t0:t0 + n] = blk["inflows"]
+        if fg._engine.day != t0:
+            raise RuntimeError(f"FlowGraph engine is at day {fg._engine.day}, block starts at {t0}")
+        obs = fg._obs[t0:t0 + n] if fg._obs is not None else None
+        res = fg._engine.run_flow_graph(np.ascontiguousarray(blk["inflows"]), obs)
+        res["node_negative_sink_source"] = -1 * res["node_sink_source"]
+        for k in fg.VARIABLES:
+            if k in res:
+                blk[k] = res[k]
+        # global-basis budgets of the two, for every day of the block at once
+        # (base/budget.py:388-416); a failing day raises / warns like Budget.calculate
+        for obj in (ex, fg):
+            b = obj.budget
+            if b is None:
+                continue
+            tot = {c: sum(np.asarray(blk[v], dtype=np.float64).sum(axis=1) for v in b.terms[c])
+                   if b.terms[c] else 0.0 for c in b.components}
+            ok = np.isclose(tot["inputs"], tot["outputs"] + tot["storage_changes"], rtol=b.rtol, atol=b.atol)
+            if not np.all(ok):
+                day = t0 + int(np.argmin(ok))
+                msg = (f"The global flux balance not equal to the change in global storage: {b.description} "
+                       f"(day {day})")
+                if b.imbalance_fatal:
+                    raise ValueError(msg)
+                warn(msg, UserWarning)
 
     def _init_runtime(self):
         self._engine_kwargs = None
@@ -102,9 +173,18 @@ class Model:
                 self.control = ctl[0]
             classes, kwargs = [], {}
             keys = md.get("model_order", [k for k, v in md.items() if isinstance(v, dict) and "class" in v])
+            from .flow_graph import FlowGraph, HruNodeFlowExchange
+
+            self._tail_spec = []
             for k in keys:
                 d = md[k]
                 cls = d["class"]
+                if isinstance(cls, type) and issubclass(cls, (FlowGraph, HruNodeFlowExchange)):
+                    kw = {kk: vv for kk, vv in d.items() if kk != "class"}
+                    if isinstance(kw.get("dis"), str):
+                        kw["dis"] = md[kw["dis"]]
+                    self._tail_spec.append((k, cls, kw))
+                    continue
                 cls = P.PROCESS_CLASSES[cls.__name__ if not isinstance(cls, str) else cls]
                 classes.append(cls)
                 kw = {kk: vv for kk, vv in d.items() if kk not in ("class",)}
@@ -181,6 +261,7 @@ class Model:
         self._block_t0 = self._block_n = 0
         self._block_viol = None
         self._calculated_step = -1
+        self._tail = []
         self._init_runtime()
         self._control_is_external = True
         # days per host-side block (what one engine call brings back); None = sized
@@ -475,6 +556,8 @@ class Model:
                     if b is not None:
                         for comp in b.components:
                             want.update(b.terms[comp])
+        if self._tail:
+            want.update(("sroff_vol", "ssres_flow_vol", "gwres_flow_vol"))
         return [v for v in hv_full if v in want], [v for v in sv if v in want]
 
     def _select(self, full: bool):
@@ -507,6 +590,8 @@ class Model:
             self._buf_slot ^= 1
             blk, viol = eng.run_host(f["prcp"][t0:t0 + n], f["tmax"][t0:t0 + n], f["tmin"][t0:t0 + n],
                                      pinned_outputs=True, reuse_buffers=1 + self._buf_slot)
+        if self._tail:
+            self._tail_block(blk, t0, n)
         self._block, self._block_t0, self._block_n, self._block_viol = blk, t0, n, viol
         self._days_on_device = max(self._days_on_device, t0 + n)
         # all-time variables of Atmosphere: rows are kept when the array exists, else
@@ -527,6 +612,13 @@ class Model:
             for name, proc in self.processes.items():
                 if getattr(proc, "budget", None) is not None:
                     jobs.extend((proc.budget.accumulate_term, a) for a in proc.budget.block_terms(blk, dt))
+        if device_acc and self._tail:
+            on_device = set(getattr(eng, "acc_hru", ()) or ()) | set(getattr(eng, "acc_seg", ()) or ())
+            dt = float(self.control.time_step / np.timedelta64(1, "D"))
+            for obj in self._tail:
+                if obj.budget is not None:
+                    jobs.extend((obj.budget.accumulate_term, a) for a in obj.budget.block_terms(blk, dt)
+                                if a[1] not in on_device)
         big = n * max(self._engine.nhru, 1) >= 1 << 18
         if big and len(jobs) > 1:
             list(_pool().map(lambda j: j[0](*j[1]), jobs))
@@ -625,15 +717,15 @@ class Model:
             for var in proc.get_variables():
                 if var in blk:
                     proc._vars[var][:] = blk[var][j]
-        if "PRMSRunoff" in self.processes and "PRMSSoilzone" not in self.processes:
-            pass
+        if self._tail:
+            self._tail_graph.inflows[:] = blk["inflows"][j]
         self._calculated_step = it
         for name, proc in self.processes.items():
             b = getattr(proc, "budget", None)
             if b is None:
                 continue
             nv = None
-            if self._block_viol is not None:
+            if self._block_viol is not None and P.base_name(name) in BUDGET_INDEX:
                 nv = int(self._block_viol[j, BUDGET_INDEX[P.base_name(name)]])
             b.calculate(nv)
 
@@ -672,6 +764,8 @@ class Model:
         self._block, self._block_n = None, 0
         if self._engine is not None and hasattr(self._engine, "release_buffers"):
             self._engine.release_buffers()
+        if self._tail:
+            self._tail_graph.finalize()
 
     # ---------------------------------------------------------------- netcdf
     def initialize_netcdf(self, output_dir=None, separate_files: bool = None,
@@ -758,6 +852,8 @@ class Model:
             for var in proc.get_variables():
                 if var in self._block:
                     proc._vars[var][:] = self._block[var][j]
+        if self._tail:
+            self._tail_graph.inflows[:] = self._block["inflows"][j]
             b = getattr(proc, "budget", None)
             if b is not None and self._block_viol is not None:
                 b._n_violations = int(self._block_viol[j, BUDGET_INDEX[P.base_name(name)]])
@@ -775,8 +871,8 @@ class Model:
         `Model.load_state()` on a freshly built model of the same control and
         parameters continues the run bit for bit.  `path`: also write an .npz."""
         self._ensure_engine()
-        if self._mode not in ("chain", "chain+channel"):
-            raise NotImplementedError("save_state needs the full NHM chain")
+        if self._mode not in ("chain", "chain+channel") or self._tail:
+            raise NotImplementedError("save_state needs the full NHM chain (without a FlowGraph behind it)")
         it = self.control.itime_step
         if self._engine.day != it + 1:
             raise RuntimeError(

@@ -188,6 +188,17 @@ class ModelNetcdfOutput:
             names = [v for v in proc.get_variables() if output_vars is None or v in output_vars]
             if not names:
                 continue
+            if any(v not in VARIABLE_META for v in names):
+                # a FlowGraph / exchange behind the column (flow_graph.py): its variables are
+                # per node (coordinate node_coord, base/flow_graph.py:542-567) or per HRU
+                for v in names:
+                    n = int(np.asarray(proc[v]).shape[0])
+                    per_hru = n == len(nhm_id) and not hasattr(proc, "nnodes") or (
+                        hasattr(proc, "nhru") and n == getattr(proc, "nhru") and n != getattr(proc, "nnodes", -1))
+                    self.files.append((pname, False, _File(
+                        self.dir / (f"{v}.nc" if separate_files else f"{pname}_{v}.nc"), [v],
+                        "nhm_id" if per_hru else "node_coord", nhm_id if per_hru else np.arange(n), pname)))
+                continue
             doy = pname == "PRMSSolarGeometry"
             groups = [[v] for v in names] if separate_files else [names]
             for g in groups:

@@ -164,3 +164,43 @@ def test_flow_graph_descriptors_and_checks(drb):
 
     with pytest.raises(NotImplementedError, match="no CPU path"):
         pwsb.FlowGraph(control, None, par, np.zeros(3), {"pass": Mine()}, allow_disconnected_nodes=True)
+
+
+def test_hru_node_flow_exchange_and_model_dict_helper(drb):
+    """HruNodeFlowExchange (prms_channel_flow_graph.py:501-620) for a block of days =
+    the reference's per-day loop: inflows per node in ascending HRU order (the
+    PRMS segments' part is HruSegmentFlowAdapter's / PRMSChannel's lateral inflow,
+    bit for bit), HRUs without a segment go to `sinks`, new nodes get nothing; and
+    prms_channel_flow_graph_to_model_dict (:746-895) appends the two entries."""
+    import pywatershed_b200 as pwsb
+
+    p, f, start = drb
+    nd = 12
+    res, _ = po.Oracle(p, start=start).run(f["prcp"][:nd], f["tmax"][:nd], f["tmin"][:nd],
+                                           ("sroff_vol", "ssres_flow_vol", "gwres_flow_vol"),
+                                           ("seg_lateral_inflow",))
+    t0 = np.datetime64(start, "s")
+    control = pwsb.Control(t0, t0 + np.timedelta64(nd - 1, "D"), np.timedelta64(24, "h"),
+                           options={"budget_type": "error"})
+    md = {"control": control, "dis_hru": p, "model_order": ["prms_runoff"],
+          "prms_runoff": {"class": pwsb.PRMSRunoff, "parameters": p, "dis": "dis_hru"}}
+    out = pwsb.prms_channel_flow_graph_to_model_dict(
+        md, p, "dis_hru", p, {"pass": pwsb.PassThroughFlowNodeMaker()}, ["pass"], [0], [9001], [1829])
+    assert out["model_order"] == ["prms_runoff", "inflow_exchange", "prms_channel_flow_graph"]
+    assert md["model_order"] == ["prms_runoff"]  # the caller's dict is not edited
+    assert out["inflow_exchange"]["class"] is pwsb.HruNodeFlowExchange
+    assert out["prms_channel_flow_graph"]["class"] is pwsb.FlowGraph
+    nseg = np.asarray(p["tosegment"]).shape[0]
+    ex = pwsb.HruNodeFlowExchange(control, p, out["inflow_exchange"]["parameters"])
+    assert ex.nnodes == nseg + 1 and ex.budget.basis == "global"
+    blk = ex.block(res["sroff_vol"], res["ssres_flow_vol"], res["gwres_flow_vol"])
+    np.testing.assert_array_equal(blk["inflows"][:, :nseg], res["seg_lateral_inflow"])
+    assert (blk["inflows"][:, nseg] == 0).all()
+    no_seg = np.asarray(p["hru_segment"]) == 0
+    tot = (0 + res["sroff_vol"] + res["ssres_flow_vol"] + res["gwres_flow_vol"]) / 86400.0
+    np.testing.assert_array_equal(blk["sinks"][:, no_seg], tot[:, no_seg])
+    assert (blk["sinks"][:, ~no_seg] == 0).all() and no_seg.sum() == 4
+    np.testing.assert_array_equal(blk["inflows_vol"], blk["inflows"] * 86400.0)
+    # the global budget of the exchange closes: what comes in goes to nodes or sinks
+    lhs = (res["sroff_vol"] + res["ssres_flow_vol"] + res["gwres_flow_vol"]).sum(axis=1)
+    np.testing.assert_allclose(blk["inflows_vol"].sum(axis=1) + blk["sinks_vol"].sum(axis=1), lhs, rtol=1e-12)

@@ -198,3 +198,83 @@ def test_source_sink_nodes_equal_the_oracle_bit_for_bit_and_the_reference(drb):
     # the node stores nothing and its sink / source is the daily mean of what it added or took
     assert (got["node_storage_changes"][:, nseg:nseg + 2] == 0).all()
     assert (ss >= want - 1e-9 * np.abs(want)).all()  # a sink is only ever cut back, never enlarged
+
+
+def test_flow_graph_behind_the_prms_column_in_a_model(drb, tmp_path):
+    """prms_channel_flow_graph_to_model_dict (prms_channel_flow_graph.py:746-895): the
+    PRMS column without PRMSChannel + `inflow_exchange` + a FlowGraph with a
+    pass-through node above nhm_seg 1829, as ONE Model.  The flows on the PRMSChannel
+    nodes are those of the NHM model with PRMSChannel (the reference's notebook
+    checks 1e-10; here: the same bits), through run() (blocks) and day by day, with
+    the exchange's and the graph's global budgets closed and netCDF files written."""
+    import pywatershed_b200 as pwsb
+
+    p, f, start = drb
+    nd = 75
+    chain = ["PRMSSolarGeometry", "PRMSAtmosphere", "PRMSCanopy", "PRMSSnow", "PRMSRunoff",
+             "PRMSSoilzone", "PRMSGroundwater"]
+    nhru, nseg = p["hru_area"].shape[0], p["tosegment"].shape[0]
+    par = pwsb.Parameters(dims={"nhru": nhru, "nsegment": nseg, "nmonth": 12, "ndoy": 366},
+                          coords={"nhm_id": p["nhm_id"], "nhm_seg": p["nhm_seg"]},
+                          data_vars={k: v for k, v in p.items() if k not in ("nhm_id", "nhm_seg")})
+
+    def control():
+        return _control(start, nd, calc_method="cuda")
+
+    def build(ctl):
+        md = {"control": ctl, "dis_both": par, "model_order": [n.lower() for n in chain]}
+        for n in chain:
+            md[n.lower()] = {"class": getattr(pwsb, n), "parameters": par, "dis": "dis_both"}
+        md = pwsb.prms_channel_flow_graph_to_model_dict(
+            md, par, "dis_both", par, {"pass_throughs": pwsb.PassThroughNodeMaker()}, ["pass_throughs"],
+            [0], [9001], [1829], graph_budget_type="error")
+        m = pwsb.Model(md, find_input_files=False)
+        for k in ("prcp", "tmax", "tmin"):
+            m.processes["PRMSAtmosphere"].set_input_to_adapter(k, f[k][:nd])
+        return m
+
+    # the NHM model with PRMSChannel: the flows to reproduce
+    ctl0 = control()
+    m0 = pwsb.Model([getattr(pwsb, n) for n in chain + ["PRMSChannel"]], control=ctl0, parameters=par,
+                    find_input_files=False)
+    for k in ("prcp", "tmax", "tmin"):
+        m0.processes["PRMSAtmosphere"].set_input_to_adapter(k, f[k][:nd])
+    want = []
+    for _ in range(nd):
+        m0.advance()
+        m0.calculate()
+        want.append(m0.processes["PRMSChannel"]["seg_outflow"].copy())
+    want = np.array(want)
+    m0.finalize()
+
+    # day by day
+    m = build(control())
+    assert list(m.processes)[-2:] == ["inflow_exchange", "prms_channel_flow_graph"]
+    fg, ex = m.processes["prms_channel_flow_graph"], m.processes["inflow_exchange"]
+    got = []
+    for _ in range(nd):
+        m.advance()
+        m.calculate()
+        got.append(fg["node_outflows"].copy())
+        assert fg.budget._zero_sum and ex.budget._zero_sum
+    got = np.array(got)
+    m.finalize()
+    np.testing.assert_array_equal(got[:, :nseg], want)
+    below = int(np.where(np.asarray(p["nhm_seg"]) == 1829)[0][0])
+    assert (got[:, nseg] > 0).any()
+
+    # run(): blocks, fast path, netCDF
+    m = build(control())
+    m.run(netcdf_dir=tmp_path, finalize=False, output_vars=["node_outflows", "inflows", "sroff_vol"])
+    fg = m.processes["prms_channel_flow_graph"]
+    np.testing.assert_array_equal(fg["node_outflows"][:nseg], want[-1])
+    np.testing.assert_array_equal(fg["node_upstream_inflows"][below], got[-1, nseg])
+    acc = fg.budget.accumulations
+    np.testing.assert_allclose(acc["outputs"]["outflows"].sum(), np.where(
+        np.asarray(fg.outflow_mask), got, 0.0).sum(), rtol=1e-12)
+    m.finalize()
+    from pywatershed_b200.netcdf_in import read_time_variable
+
+    _, a = read_time_variable(tmp_path / "node_outflows.nc", "node_outflows")
+    np.testing.assert_array_equal(a, got)
+    assert (tmp_path / "sroff_vol.nc").exists() and (tmp_path / "inflows.nc").exists()
