@@ -15,7 +15,8 @@ kernel (k_route_chunks<G, true>, include/pws_b200.h: pws_set_flow_graph):
 
 Same constructor signatures, variable names, budget terms and helper functions
 (prms_channel_flow_graph_postprocess, prms_channel_flow_graph_to_model_dict,
-HruSegmentFlowAdapter, HruNodeFlowExchange).  A node maker of any other class
+HruSegmentFlowAdapter, HruNodeFlowExchange; inside a Model the exchange and the
+graph are evaluated per block of days behind the PRMS column, model.py:_tail_block).  A node maker of any other class
 (StarfitFlowNodeMaker, user-defined nodes computed in Python) is rejected: there
 is no CPU path in this package.
 

@@ -852,13 +852,18 @@ class Model:
             for var in proc.get_variables():
                 if var in self._block:
                     proc._vars[var][:] = self._block[var][j]
-        if self._tail:
-            self._tail_graph.inflows[:] = self._block["inflows"][j]
             b = getattr(proc, "budget", None)
-            if b is not None and self._block_viol is not None:
+            if b is not None and self._block_viol is not None and P.base_name(name) in BUDGET_INDEX:
                 b._n_violations = int(self._block_viol[j, BUDGET_INDEX[P.base_name(name)]])
                 b._zero_sum = b._n_violations == 0
                 b._itime_accumulated = it
+        if self._tail:
+            # (their global budgets were checked for every day of the block in _tail_block)
+            self._tail_graph.inflows[:] = self._block["inflows"][j]
+            for obj in self._tail:
+                if obj.budget is not None:
+                    obj.budget._n_violations, obj.budget._zero_sum = 0, True
+                    obj.budget._itime_accumulated = it
         self._calculated_step = it
 
     # ---------------------------------------------------------------- restart
