@@ -77,7 +77,16 @@ int pws_set_param_i32(pws_handle *h, const char *name, const int32_t *h_v, int64
  * default and maximum 512; outlet trees larger than a chunk are cut and linked
  * through HBM),
  * "route_hours" (hours a segment advances per step of k_route_chunks: 0,
- * default = 12 for segment graphs of at most 160 levels, else 4). */
+ * default = 12 for segment graphs of at most 160 levels, else 4),
+ * "route_overlap" (1: the routing launch of block b+1 may start while that of
+ * block b still runs, on a second stream, each chunk of connected segments
+ * continuing from the state the same chunk of the previous launch stored -- a deep
+ * network then pays its pipeline fill once per run, not per block; only while all
+ * chunks of a launch fit the GPU with room to spare; 0: launches are serialised;
+ * -1, default: on for segment graphs deeper than 160 levels),
+ * "wide_column" / "one_cta_carveout" (1, default: grids of at most one CTA per SM
+ * run the column kernel variant without a register cap, with the shared-memory
+ * carve-out of one CTA). */
 int pws_set_option(pws_handle *h, const char *name, double value);
 
 /* Everything the reference derives at construction: soltab tables

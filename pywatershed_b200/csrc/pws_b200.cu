@@ -154,11 +154,19 @@ struct pws_handle {
   // write and its routing reads is double-buffered by block parity, so the
   // column of block b+1 runs beside the routing of block b.
   int scratch_days = 0;
-  double *d_hru_lat[2] = {nullptr, nullptr}, *d_ots = nullptr, *d_day_outvol = nullptr,
-         *d_day_dstor = nullptr, *d_day_lat = nullptr;
+  int scratch_copies = 0;  // copies of the routing scratch (2 when routing launches may overlap)
+  // (the routing scratch exists twice when consecutive routing launches may overlap,
+  // see route_overlap(): index = the block's slot, else 0)
+  double *d_hru_lat[2] = {nullptr, nullptr}, *d_ots[2] = {nullptr, nullptr},
+         *d_day_outvol[2] = {nullptr, nullptr}, *d_day_dstor[2] = {nullptr, nullptr},
+         *d_day_lat[2] = {nullptr, nullptr};
   int4* d_cal[2] = {nullptr, nullptr};
   int* d_viol[2] = {nullptr, nullptr};
-  int* d_progress = nullptr;  // [sstride] days published + 1 ticket counter at the end
+  int* d_progress[2] = {nullptr, nullptr};  // [sstride] days published + 1 ticket counter at the end
+  int* d_chunk_done = nullptr;  // [nchunks] serial of the last routing launch whose state a chunk has written
+  int route_serial = 0;         // routing launches so far
+  int route_overlap_opt = -1;   // option "route_overlap": -1 by network, 0 off, 1 on where it is safe
+  cudaStream_t s_route2 = nullptr;
   int64_t blocks_enqueued = 0;  // parity = scratch slot of the next block
   // host ring for pws_run_host
   int ring_days = 0;
@@ -278,6 +286,7 @@ extern "C" int pws_create(pws_handle** out, int device, int64_t nhru, int64_t ns
               ok(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking)) &&
               ok(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking)) &&
               ok(cudaStreamCreateWithPriority(&h->s_route, cudaStreamNonBlocking, prio_hi)) &&
+              ok(cudaStreamCreateWithPriority(&h->s_route2, cudaStreamNonBlocking, prio_hi)) &&
               ok(cudaEventCreate(&h->ev_col0)) && ok(cudaEventCreate(&h->ev_col1)) &&
               ok(cudaEventCreate(&h->ev_ch1)) && ok(cudaEventCreate(&h->ev_base));
   for (int g = 0; g < pws_handle::kMaxLanes && good; ++g)
@@ -335,12 +344,15 @@ static void free_scratch(pws_handle* h) {
     cudaFree(h->d_cal[b]); h->d_cal[b] = nullptr;
     cudaFree(h->d_viol[b]); h->d_viol[b] = nullptr;
   }
-  cudaFree(h->d_ots); h->d_ots = nullptr;
-  cudaFree(h->d_day_outvol); h->d_day_outvol = nullptr;
-  cudaFree(h->d_day_dstor); h->d_day_dstor = nullptr;
-  cudaFree(h->d_day_lat); h->d_day_lat = nullptr;
-  cudaFree(h->d_progress); h->d_progress = nullptr;
+  for (int b = 0; b < 2; ++b) {
+    cudaFree(h->d_ots[b]); h->d_ots[b] = nullptr;
+    cudaFree(h->d_day_outvol[b]); h->d_day_outvol[b] = nullptr;
+    cudaFree(h->d_day_dstor[b]); h->d_day_dstor[b] = nullptr;
+    cudaFree(h->d_day_lat[b]); h->d_day_lat[b] = nullptr;
+    cudaFree(h->d_progress[b]); h->d_progress[b] = nullptr;
+  }
   h->scratch_days = 0;
+  h->scratch_copies = 0;
 }
 
 static void free_device(pws_handle* h) {
@@ -357,6 +369,7 @@ static void free_device(pws_handle* h) {
                 h->d_ts, h->d_c0, h->d_c1, h->d_c2, h->d_outflow_ts, h->d_seg_inflow};
   for (void* p : ch) cudaFree(p);
   cudaFree(h->d_fg_kind); cudaFree(h->d_fg_obs_col); cudaFree(h->d_fg_flow_min);
+  cudaFree(h->d_chunk_done); h->d_chunk_done = nullptr;
   h->d_fg_kind = h->d_fg_obs_col = nullptr;
   h->d_fg_flow_min = nullptr;
   h->d_tsi = h->d_up_ptr = h->d_up_idx = h->d_hru_ptr = h->d_hru_idx = h->d_seg_flags = h->d_orig =
@@ -383,6 +396,7 @@ extern "C" int pws_destroy(pws_handle* h) {
   }
   cudaStreamDestroy(h->s_compute); cudaStreamDestroy(h->s_h2d); cudaStreamDestroy(h->s_d2h);
   cudaStreamDestroy(h->s_route);
+  cudaStreamDestroy(h->s_route2);
   for (auto st : h->s_lane) cudaStreamDestroy(st);
   delete h;
   return 0;
@@ -469,6 +483,7 @@ extern "C" int pws_set_option(pws_handle* h, const char* name, double value) {
     h->column_hrus_opt = (int)value;
     return 0;
   }
+  else if (!strcmp(name, "route_overlap")) { h->route_overlap_opt = value < 0 ? -1 : (value != 0.0); return 0; }
   else if (!strcmp(name, "route_hours")) {
     if (value != 0 && value != PWS_ROUTE_HOURS && value != PWS_ROUTE_HOURS_SHALLOW)
       PWS_FAIL(h, "pws_set_option: route_hours must be 0 (automatic), %d or %d", PWS_ROUTE_HOURS,
@@ -491,6 +506,21 @@ extern "C" int pws_set_option(pws_handle* h, const char* name, double value) {
 static int route_hours(const pws_handle* h) {
   if (h->route_hours_opt) return h->route_hours_opt;
   return h->nlevels <= 160 ? PWS_ROUTE_HOURS_SHALLOW : PWS_ROUTE_HOURS;
+}
+
+// May the routing launch of block b+1 start while that of block b still runs?
+// A deep network pays its systolic fill (levels x one step, ~25 ms for 8,856
+// levels) per launch; with two routing streams a chunk of launch b+1 starts as
+// soon as the SAME chunk of launch b has stored its state (d_chunk_done), so the
+// fill is paid once per run.  Safe only while the spinning CTAs of the younger
+// launch cannot keep the older launch's CTAs off the SMs: every chunk of a launch
+// must fit the GPU with room to spare (a CTA of k_route_chunks takes a whole SM).
+static bool route_overlap(const pws_handle* h) {
+  if (h->route_overlap_opt == 0 || h->nseg == 0) return false;
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+  if (h->nchunks > nsm - 8) return false;
+  return h->route_overlap_opt == 1 || h->nlevels > 160;
 }
 
 // --------------------------------------------------------------- channel init
@@ -756,6 +786,15 @@ static int channel_build(pws_handle* h) {
   PWS_CUDA(h, up_i32(&h->d_hru_idx, hru_idx));
   PWS_CUDA(h, up_i32(&h->d_seg_flags, seg_flags));
   PWS_CUDA(h, up_i32(&h->d_chunk_begin, chunk_begin));
+  {
+    // serial of the last launch that stored a chunk's state: none yet
+    std::vector<int32_t> zero((size_t)std::max(h->nchunks, 1), 0);
+    int32_t* p = nullptr;
+    PWS_CUDA(h, up_i32(&p, zero));
+    cudaFree(h->d_chunk_done);
+    h->d_chunk_done = p;
+    h->route_serial = 0;
+  }
   {
     std::vector<int32_t> dm(chunk_dmax_v.begin(), chunk_dmax_v.end());
     PWS_CUDA(h, up_i32(&h->d_chunk_dmax, dm));
@@ -1097,7 +1136,9 @@ extern "C" int pws_n_selected(pws_handle* h, int* n_f64, int* n_i32, int* n_seg)
 
 // --------------------------------------------------------------- run
 static int ensure_scratch(pws_handle* h, int ndays) {
-  if (ndays <= h->scratch_days) return 0;
+  const int copies = (route_overlap(h) && h->nseg > 0) ? 2 : 1;
+  if (ndays <= h->scratch_days && copies <= h->scratch_copies) return 0;
+  ndays = std::max(ndays, h->scratch_days);
   cudaDeviceSynchronize();
   free_scratch(h);
   const size_t T = (size_t)ndays;
@@ -1106,14 +1147,15 @@ static int ensure_scratch(pws_handle* h, int ndays) {
     PWS_CUDA(h, cudaMalloc(&h->d_viol[b], T * BUD_N * sizeof(int)));
     if (h->nseg > 0) PWS_CUDA(h, cudaMalloc(&h->d_hru_lat[b], T * h->stride * sizeof(double)));
   }
-  if (h->nseg > 0) {
-    PWS_CUDA(h, cudaMalloc(&h->d_ots, T * 24 * std::max(h->n_ext_rows, 1) * sizeof(double)));
-    PWS_CUDA(h, cudaMalloc(&h->d_progress, (size_t)(h->sstride + 32) * sizeof(int)));
-    PWS_CUDA(h, cudaMalloc(&h->d_day_outvol, T * h->sstride * sizeof(double)));
-    PWS_CUDA(h, cudaMalloc(&h->d_day_dstor, T * h->sstride * sizeof(double)));
-    PWS_CUDA(h, cudaMalloc(&h->d_day_lat, T * h->sstride * sizeof(double)));
+  for (int b = 0; b < copies && h->nseg > 0; ++b) {
+    PWS_CUDA(h, cudaMalloc(&h->d_ots[b], T * 24 * std::max(h->n_ext_rows, 1) * sizeof(double)));
+    PWS_CUDA(h, cudaMalloc(&h->d_progress[b], (size_t)(h->sstride + 32) * sizeof(int)));
+    PWS_CUDA(h, cudaMalloc(&h->d_day_outvol[b], T * h->sstride * sizeof(double)));
+    PWS_CUDA(h, cudaMalloc(&h->d_day_dstor[b], T * h->sstride * sizeof(double)));
+    PWS_CUDA(h, cudaMalloc(&h->d_day_lat[b], T * h->sstride * sizeof(double)));
   }
   h->scratch_days = ndays;
+  h->scratch_copies = copies;
   return 0;
 }
 
@@ -1143,8 +1185,14 @@ static void mark_base(pws_handle* h, cudaStream_t st) {
 // block's verdict rows (or null: no channel budget)
 static int enqueue_channel(pws_handle* h, cudaStream_t st, int ndays, const double* d_hru_lat,
                            const double* d_seg_lat_in, double* d_seg_out, int* viol,
-                           const double* d_fg_obs = nullptr, double* d_fg_out = nullptr) {
+                           const double* d_fg_obs = nullptr, double* d_fg_out = nullptr, int q = 0,
+                           bool chained = false) {
+  // q: which copy of the routing scratch; chained: the launch may start before the
+  // previous one (on the other routing stream) has finished, chunk by chunk
   ChannelArgs a{};
+  a.chunk_done = h->d_chunk_done;
+  a.epoch = ++h->route_serial;
+  a.wait_prev = chained ? 1 : 0;
   const bool graph = d_fg_out != nullptr;
   if (graph != h->flow_graph)
     PWS_FAIL(h, graph ? "FlowGraph run on a handle without pws_set_flow_graph"
@@ -1162,8 +1210,8 @@ static int enqueue_channel(pws_handle* h, cudaStream_t st, int ndays, const doub
   a.chunk_dmax = h->d_chunk_dmax; a.delay = h->d_delay; a.ext_row = h->d_ext_row; a.rts = h->d_rts;
   a.outflow_ts = h->d_outflow_ts; a.seg_inflow = h->d_seg_inflow;
   a.hru_lat = d_hru_lat; a.hstride = h->stride; a.seg_lat_in = d_seg_lat_in;
-  a.ots = h->d_ots; a.day_outvol = h->d_day_outvol; a.day_dstor = h->d_day_dstor;
-  a.day_lat = h->d_day_lat;
+  a.ots = h->d_ots[q]; a.day_outvol = h->d_day_outvol[q]; a.day_dstor = h->d_day_dstor[q];
+  a.day_lat = h->d_day_lat[q];
   a.seg_out = h->n_seg_sel > 0 ? d_seg_out : nullptr;
   a.n_seg_sel = h->n_seg_sel;
   memcpy(a.slot, h->slot_seg, sizeof a.slot);
@@ -1180,11 +1228,11 @@ static int enqueue_channel(pws_handle* h, cudaStream_t st, int ndays, const doub
                          ? nullptr : a.seg_out + (int64_t)h->slot_seg[vars[k]] * h->nseg;
     a.out_day_stride = (int64_t)h->n_seg_sel * h->nseg;
   }
-  a.progress = h->d_progress;
-  a.ticket = h->d_progress + h->sstride;
+  a.progress = h->d_progress[q];
+  a.ticket = h->d_progress[q] + h->sstride;
   a.err = h->d_err;
   // progress counters (cross-chunk edges) and the chunk ticket start at 0
-  PWS_CUDA(h, cudaMemsetAsync(h->d_progress, 0, (size_t)(h->sstride + 32) * sizeof(int), st));
+  PWS_CUDA(h, cudaMemsetAsync(h->d_progress[q], 0, (size_t)(h->sstride + 32) * sizeof(int), st));
   if (!h->route_attr_set) {
     PWS_CUDA(h, cudaFuncSetAttribute(k_route_chunks<PWS_ROUTE_HOURS>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1218,8 +1266,8 @@ static int enqueue_channel(pws_handle* h, cudaStream_t st, int ndays, const doub
   h->launches++;
   h->last_channel_launches += 1;
   if (viol) {
-    k_channel_budget<<<ndays, 256, 0, st>>>(h->nseg, h->sstride, h->d_day_lat, h->d_day_outvol,
-                                            h->d_day_dstor, viol);
+    k_channel_budget<<<ndays, 256, 0, st>>>(h->nseg, h->sstride, h->d_day_lat[q], h->d_day_outvol[q],
+                                            h->d_day_dstor[q], viol);
     h->launches++;
     h->last_channel_launches += 1;
   }
@@ -1423,6 +1471,10 @@ static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const d
     if (period) PWS_LAUNCH_COLUMN_P(MODE, HH, true, false, GRID, ST);                            \
     else PWS_LAUNCH_COLUMN_P(MODE, HH, false, false, GRID, ST);                                  \
   } while (0)
+  // routing stream of this block: alternating when consecutive routing launches may
+  // overlap (deep networks, route_overlap()); block b+2 then follows block b on its stream
+  const bool chain_route = route_overlap(h);
+  cudaStream_t sr = (chain_route && p == 1) ? h->s_route2 : h->s_route;
   const bool period = h->forcing_period > 0;
   int nsm_ = 148;
   cudaDeviceGetAttribute(&nsm_, cudaDevAttrMultiProcessorCount, h->device);
@@ -1464,20 +1516,23 @@ static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const d
     cudaEventRecord(e1, st);
     h->ev_pairs_col.push_back({e0, e1});
     PWS_CUDA(h, cudaEventRecord(h->ev_lane[p][g], st));
-    PWS_CUDA(h, cudaStreamWaitEvent(h->s_route, h->ev_lane[p][g], 0));
+    PWS_CUDA(h, cudaStreamWaitEvent(sr, h->ev_lane[p][g], 0));
   }
 #undef PWS_LAUNCH_COLUMN_P
 #undef PWS_LAUNCH_COLUMN
   h->last_col_blocks++;
-  // (the routing of block b-1 precedes this block's on s_route: the segment
-  // state, the day_* rows and the progress counters are single-buffered)
+  // (without route_overlap the routing of block b-1 precedes this block's on s_route:
+  // the segment state is handed over by stream order and the scratch is single)
   if (h->nseg > 0)
-    if (enqueue_channel(h, h->s_route, ndays, h->d_hru_lat[p], nullptr, d_seg_out,
-                        want_viol ? h->d_viol[p] : nullptr))
+    if (enqueue_channel(h, sr, ndays, h->d_hru_lat[p], nullptr, d_seg_out,
+                        want_viol ? h->d_viol[p] : nullptr, nullptr, nullptr, chain_route ? p : 0,
+                        chain_route))
       return 1;
   if (want_viol)
     PWS_CUDA(h, cudaMemcpyAsync(h_viol_dst, h->d_viol[p], (size_t)ndays * BUD_N * sizeof(int),
-                                cudaMemcpyDeviceToHost, h->s_route));
+                                cudaMemcpyDeviceToHost, sr));
+  // the sums below are read-modify-write: behind the previous block's
+  if (chain_route) PWS_CUDA(h, cudaStreamWaitEvent(sr, h->ev_block[prev], 0));
   if (h->accumulate_on && (!h->acc_hru.empty() || (!h->acc_seg.empty() && h->nseg > 0))) {
     if (mode == SINK_TILED) PWS_FAIL(h, "accumulations need the rows layout (tiled_outputs 0)");
     AccSlots sl{};
@@ -1485,20 +1540,20 @@ static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const d
       if (h->acc_hru.size() > (size_t)AccSlots::kMax) PWS_FAIL(h, "too many accumulated variables");
       for (size_t k = 0; k < h->acc_hru.size(); ++k) sl.s[k] = h->acc_hru_slot[k];
       k_accumulate<<<dim3((unsigned)((h->nhru + 255) / 256), (unsigned)h->acc_hru.size()), 256, 0,
-                     h->s_route>>>(sl, d_out_f64, (int64_t)h->n_f64 * h->nhru, h->nhru, ndays, h->nhru,
+                     sr>>>(sl, d_out_f64, (int64_t)h->n_f64 * h->nhru, h->nhru, ndays, h->nhru,
                                    h->d_acc_hru, h->stride);
       h->launches++;
     }
     if (!h->acc_seg.empty() && h->nseg > 0) {
       for (size_t k = 0; k < h->acc_seg.size(); ++k) sl.s[k] = h->acc_seg_slot[k];
       k_accumulate<<<dim3((unsigned)((h->nseg + 255) / 256), (unsigned)h->acc_seg.size()), 256, 0,
-                     h->s_route>>>(sl, d_seg_out, (int64_t)h->n_seg_sel * h->nseg, h->nseg, ndays,
+                     sr>>>(sl, d_seg_out, (int64_t)h->n_seg_sel * h->nseg, h->nseg, ndays,
                                    h->nseg, h->d_acc_seg, h->sstride);
       h->launches++;
     }
     PWS_CUDA(h, cudaGetLastError());
   }
-  PWS_CUDA(h, cudaEventRecord(h->ev_block[p], h->s_route));
+  PWS_CUDA(h, cudaEventRecord(h->ev_block[p], sr));
   return 0;
 }
 
@@ -1531,6 +1586,7 @@ static cudaError_t sync_all(pws_handle* h) {
   for (int g = 0; g < pws_handle::kMaxLanes && e == cudaSuccess; ++g)
     e = cudaStreamSynchronize(h->s_lane[g]);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->s_route);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->s_route2);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->s_d2h);
   return e;
 }
@@ -1680,9 +1736,15 @@ extern "C" int pws_run_channel_device(pws_handle* h, int ndays, const double* d_
   if (ensure_scratch(h, ndays)) return 1;
   const int p = (int)(h->blocks_enqueued & 1);
   h->blocks_enqueued++;
-  PWS_CUDA(h, cudaStreamWaitEvent(h->s_route, h->ev_block[p ^ 1], 0));
-  if (enqueue_channel(h, h->s_route, ndays, nullptr, d_seg_lat, d_seg_out, nullptr)) return 1;
-  PWS_CUDA(h, cudaEventRecord(h->ev_block[p], h->s_route));
+  const bool chain_route = route_overlap(h);
+  cudaStream_t sr = (chain_route && p == 1) ? h->s_route2 : h->s_route;
+  // serialised: behind the previous call; overlapped: only behind the call before it
+  // (stream order), the segment state being handed over chunk by chunk on the device
+  if (!chain_route) PWS_CUDA(h, cudaStreamWaitEvent(sr, h->ev_block[p ^ 1], 0));
+  if (enqueue_channel(h, sr, ndays, nullptr, d_seg_lat, d_seg_out, nullptr, nullptr, nullptr,
+                      chain_route ? p : 0, chain_route))
+    return 1;
+  PWS_CUDA(h, cudaEventRecord(h->ev_block[p], sr));
   return 0;
 }
 

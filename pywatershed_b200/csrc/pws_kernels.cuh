@@ -882,6 +882,11 @@ struct ChannelArgs {
   const int32_t* chunk_dmax;   // [nchunks] largest delay in the chunk
   int nchunks;
   int* ticket;               // chunk ticket counter, zeroed before each launch
+  // consecutive launches on two streams (pws_b200.cu: route_overlap): a chunk stores
+  // `epoch` here after its state; with wait_prev it first waits for epoch - 1
+  int* chunk_done;           // [nchunks]
+  int epoch;
+  int wait_prev;
   // state, in pos order
   double* outflow_ts;
   double* seg_inflow;        // yesterday's daily mean inflow (prms_channel.py:384-386)
@@ -984,6 +989,22 @@ k_route_chunks(const __grid_constant__ ChannelArgs a) {
   __syncthreads();
   const int chunk = s_chunk;
   if (chunk >= a.nchunks) return;
+  if (a.wait_prev) {
+    // the previous launch may still be routing this chunk: its state (outflow_ts,
+    // seg_inflow) is ours to continue from once it says so
+    if (tid == 0) {
+      int idle = 0;
+      while (*reinterpret_cast<volatile const int*>(a.chunk_done + chunk) < a.epoch - 1) {
+        if (++idle > PWS_ROUTE_MAX_IDLE) {
+          atomicOr(a.err, 16);
+          break;
+        }
+        __nanosleep(256);
+      }
+      __threadfence();
+    }
+    __syncthreads();
+  }
   const int cb = a.chunk_begin[chunk], ce = a.chunk_begin[chunk + 1];
   const int dmax = a.chunk_dmax[chunk];
   const int pos = cb + tid;
@@ -1010,12 +1031,26 @@ k_route_chunks(const __grid_constant__ ChannelArgs a) {
       if (tsi < 0 || ((h + 1) % tsi) == 0) fire |= 1u << h;
   }
   const int nup = ue - ub, nh = he - hb;
-  const bool fast_up = (flags & SEG_UPS_LOCAL) && nup <= 3;
+  // up to three upstream segments sit in registers: a local one as its slot of the
+  // hand-over buffer, one in another chunk as its row of `ots` (x >= 0).  A segment
+  // below a chunk boundary used to walk the CSR with three dependent global loads per
+  // hour, and the whole chunk waited for it at every step's barrier: that, not the
+  // Muskingum recurrence, set the pace of a deep chained network.
+  // (an external one is kept as -(row + 1) in the same register as a local slot).
+  // Only in the G <= 6 kernels, i.e. for deep networks: in the 12-hour kernel the
+  // extra instantiation of the hour loop costs registers (8 bytes of spills).
+  constexpr bool kRegXup = G <= 6;
+  const bool fast_up = nup <= 3 && (kRegXup || (flags & SEG_UPS_LOCAL));
   if (live && fast_up) {
-    if (nup > 0) u0 = a.up_idx[ub] - cb;
-    if (nup > 1) u1 = a.up_idx[ub + 1] - cb;
-    if (nup > 2) u2 = a.up_idx[ub + 2] - cb;
+    auto slot = [&](int k) {
+      const int s = a.up_idx[ub + k];
+      return (s >= cb && s < ce) ? s - cb : -(a.ext_row[s] + 1);
+    };
+    if (nup > 0) u0 = slot(0);
+    if (nup > 1) u1 = slot(1);
+    if (nup > 2) u2 = slot(2);
   }
+  const bool xup = kRegXup && live && !(flags & SEG_UPS_LOCAL);  // an upstream segment in another chunk
   const bool fast_lat = a.seg_lat_in != nullptr || nh <= 3;
   if (live && a.seg_lat_in == nullptr && nh <= 3) {
     if (nh > 0) h0 = a.hru_idx[hb];
@@ -1186,18 +1221,30 @@ k_route_chunks(const __grid_constant__ ChannelArgs a) {
       // schedules the shared-memory reads and the non-recurrent sums of all G
       // hours ahead of the outflow recurrence.
       const unsigned fbits = fire >> h;  // bit g: hour h + g is a routing update
-      auto hours = [&](auto fast_c, auto ext_c) {
+      auto hours = [&](auto fast_c, auto ext_c, auto xup_c) {
         constexpr bool kFast = decltype(fast_c)::value, kExt = decltype(ext_c)::value;
+        constexpr bool kXup = decltype(xup_c)::value;  // some upstream segment is in another chunk
         // the hand-over reads of kB hours are issued together (all G at once costs
         // 6 G registers and pushed the kernel's addresses out of the register file)
         constexpr int kB = G > 6 ? 6 : G;
 #pragma unroll
         for (int g0 = 0; g0 < G; g0 += kB) {
           double upv[kB];
-          if constexpr (kFast) {
+          if constexpr (kFast && !kXup) {
 #pragma unroll
             for (int b = 0; b < kB; ++b)
               upv[b] = (rd[g0 + b][u0] + rd[g0 + b][u1]) + rd[g0 + b][u2];  // absent ones read the 0.0 slot
+          } else if constexpr (kFast) {
+            // the day's 24 values of an external upstream are complete (the progress
+            // wait at h == 0), so the loads of a batch are independent and go out together
+            const int64_t hh = (int64_t)d * 24 + h + g0;
+#pragma unroll
+            for (int b = 0; b < kB; ++b) {
+              const double v0 = u0 < 0 ? __ldcg(a.ots + (int64_t)(-u0 - 1) * row_len + hh + b) : rd[g0 + b][u0];
+              const double v1 = u1 < 0 ? __ldcg(a.ots + (int64_t)(-u1 - 1) * row_len + hh + b) : rd[g0 + b][u1];
+              const double v2 = u2 < 0 ? __ldcg(a.ots + (int64_t)(-u2 - 1) * row_len + hh + b) : rd[g0 + b][u2];
+              upv[b] = (v0 + v1) + v2;
+            }
           } else {
 #pragma unroll
             for (int b = 0; b < kB; ++b) {
@@ -1261,9 +1308,10 @@ k_route_chunks(const __grid_constant__ ChannelArgs a) {
           }
         }
       };
-      if (fast_up && ext_row < 0) hours(std::true_type{}, std::false_type{});
-      else if (fast_up) hours(std::true_type{}, std::true_type{});
-      else hours(std::false_type{}, std::true_type{});
+      if (kRegXup && fast_up && xup) hours(std::true_type{}, std::true_type{}, std::bool_constant<kRegXup>{});
+      else if (fast_up && ext_row < 0) hours(std::true_type{}, std::false_type{}, std::false_type{});
+      else if (fast_up) hours(std::true_type{}, std::true_type{}, std::false_type{});
+      else hours(std::false_type{}, std::true_type{}, std::false_type{});
       h += G;
       if (h == 24) {
         seg_outflow = div_by_ts(seg_outflow, 24.0, 1.0 / 24.0);
@@ -1301,6 +1349,10 @@ k_route_chunks(const __grid_constant__ ChannelArgs a) {
     a.outflow_ts[pos] = outflow_ts;
     a.seg_inflow[pos] = seg_inflow_prev;
   }
+  // release: every thread's state stores before the chunk's serial
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) *reinterpret_cast<volatile int*>(a.chunk_done + chunk) = a.epoch;
 }
 
 // Forcings uploaded as float32 (pws_run_host_f32: the storage type of the

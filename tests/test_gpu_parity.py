@@ -428,6 +428,51 @@ def test_deep_chained_network(drb):
         np.testing.assert_array_equal(out[:, k], ref[v], err_msg=v)
 
 
+@pytest.mark.parametrize("chunk", [512, 100])
+def test_overlapped_routing_launches_equal_one_launch(drb, chunk):
+    """Deep networks pay their systolic fill per launch, so consecutive routing
+    launches may overlap on two streams (option route_overlap; a chunk of launch b+1
+    continues from the state the same chunk of launch b stored, d_chunk_done): the
+    chained network in launches of 1..7 days, issued without a sync in between,
+    equals the oracle bit for bit, with whole trees per chunk and with cut trees."""
+    import torch
+
+    p, f, start = drb
+    ntile = 4
+    pt, _ = scenarios.tile(p, {k: v[:2] for k, v in f.items()}, ntile)
+    nseg0 = p["tosegment"].shape[0]
+    tos = pt["tosegment"].copy()
+    main_outlet = int(np.argmax(np.bincount(_basin_of(p["tosegment"]))))
+    head = int(np.argmax(np.where(_basin_of(p["tosegment"]) == main_outlet,
+                                  _dist_to_outlet(p["tosegment"]), -1)))
+    for t in range(ntile - 1):
+        tos[t * nseg0 + main_outlet] = (t + 1) * nseg0 + head + 1
+    pt["tosegment"] = tos
+    nd, nseg = 45, tos.shape[0]
+    rng = np.random.default_rng(12)
+    lat = rng.lognormal(0.0, 1.0, size=(nd, nseg))
+    ref = po.Oracle(pt, start=start).run_channel(lat)
+    dev = torch.device("cuda:0")
+    dl = torch.from_numpy(lat).to(dev)
+    for overlap in (1, 0):
+        e = _engine(pt, start, channel_chunk=chunk)
+        e._opt("route_overlap", overlap)
+        out = torch.zeros((nd, 5, nseg), dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        d, k = 0, 0
+        while d < nd:
+            n = min((1, 7, 3, 5, 2)[k % 5], nd - d)
+            e.run_channel_device(n, dl.data_ptr() + d * nseg * 8, out.data_ptr() + d * 5 * nseg * 8,
+                                 sync=False)
+            d += n
+            k += 1
+        e.sync()
+        got = out.cpu().numpy()
+        e.close()
+        for j, v in enumerate(po.SEG_VARS):
+            np.testing.assert_array_equal(got[:, j], ref[v], err_msg=f"{v} overlap={overlap}")
+
+
 @pytest.mark.parametrize("seed,chunk", [(1, 512), (2, 96), (3, 17)])
 def test_random_forests_route_bit_exact(drb, seed, chunk):
     """Random segment forests (fan-in up to 6, chains, isolated outlets, every

@@ -80,6 +80,53 @@ def test_column_kernel_variants_agree(drb, outputs):
         np.testing.assert_array_equal(vg, vb)
 
 
+def test_full_chain_with_overlapped_routing_launches(drb):
+    """The full chain over a deep (chained) network in 8-day blocks: routing launches
+    of consecutive blocks on two streams (route_overlap 1, the default for networks
+    deeper than 160 levels) against serialised ones -- results, budget verdicts and
+    device accumulations bit-identical."""
+    nd = 41
+    pt, ft, start = _tiled(drb, 3, nd)
+    p = drb[0]
+    nseg0 = p["tosegment"].shape[0]
+    tos0 = np.asarray(p["tosegment"], dtype=np.int64)
+    dist = np.zeros(nseg0, dtype=np.int64)
+    outlet = np.zeros(nseg0, dtype=np.int64)
+    for s0 in range(nseg0):
+        j, n = s0, 0
+        while tos0[j] > 0:
+            j, n = tos0[j] - 1, n + 1
+        dist[s0], outlet[s0] = n, j
+    main = int(np.argmax(np.bincount(outlet)))
+    head = int(np.argmax(np.where(outlet == main, dist, -1)))
+    tos = np.asarray(pt["tosegment"]).copy()
+    for t in range(2):
+        tos[t * nseg0 + main] = (t + 1) * nseg0 + head + 1
+    pt = dict(pt)
+    pt["tosegment"] = tos
+    hv = ["sroff_vol", "gwres_flow_vol", "soil_moist"]
+    sv = list(po.SEG_VARS)
+    from pywatershed_b200 import Engine
+
+    res = {}
+    for overlap in (0, 1):
+        e = Engine(pt, start)
+        e._opt("route_overlap", overlap)
+        e.select_outputs(hv, sv)
+        e.select_accumulations(["sroff_vol"], ["seg_outflow", "seg_stor_change"])
+        e.set_block_days(8)
+        got, viol = e.run_host(ft["prcp"], ft["tmax"], ft["tmin"])
+        res[overlap] = ({k: np.array(got[k]) for k in hv + sv}, np.array(viol), e.accumulations())
+        e.close()
+    for k in hv + sv:
+        np.testing.assert_array_equal(res[1][0][k], res[0][0][k], err_msg=k)
+    np.testing.assert_array_equal(res[1][1], res[0][1])
+    for k, v in res[0][2].items():
+        np.testing.assert_array_equal(res[1][2][k], v, err_msg=k)
+    ref, _ = po.Oracle(pt, start=start).run(ft["prcp"], ft["tmax"], ft["tmin"], (), ("seg_outflow",))
+    np.testing.assert_allclose(res[1][0]["seg_outflow"], ref["seg_outflow"], rtol=1e-9, atol=1e-10)
+
+
 def test_device_resident_blocks_overlap_safely(drb):
     """pws_run_device called block after block without a sync in between (what
     bench.py does): the scratch of a block (calendar, verdict counters, lateral
