@@ -947,7 +947,7 @@ extern "C" int pws_init(pws_handle* h) {
       PWS_CUDA(h, cudaMemcpyToSymbol(c_sol_cos_d, cos_d, sizeof cos_d));
       PWS_CUDA(h, cudaMemcpyToSymbol(c_sol_tan_d, tan_d, sizeof tan_d));
       PWS_CUDA(h, cudaMemcpyToSymbol(c_sol_r1, r1, sizeof r1));
-      dim3 grid((unsigned)((n + 127) / 128), kNdoy);
+      dim3 grid((unsigned)((n + 127) / 128), kSoltabSlices);
       k_soltab<<<grid, 128, 0, h->s_compute>>>(n, S, P.hru_slope, P.hru_aspect, P.hru_lat,
                                                h->d_soltab[0], h->d_soltab[1], h->d_soltab[2],
                                                h->D.hru_cossl);

@@ -97,26 +97,29 @@ __constant__ double c_sol_r1[kNdoy];
 
 // PRMSSolarGeometry's tables on the device (the default; option "soltab_device"
 // 0 computes them on host threads with the machine's libm instead): grid
-// (ceil(nhru/128), 366), one (doy, HRU) per thread, every elementary function
-// correctly rounded (CrMath, pws_crmath.cuh).
+// (ceil(nhru/128), kSoltabSlices), a thread = one HRU and every kSoltabSlices-th day
+// of the year, so the per-HRU geometry (24 of the ~34 correctly rounded elementary
+// functions of a table entry, CrMath, pws_crmath.cuh) is computed once per thread.
+constexpr int kSoltabSlices = 6;
 __global__ void __launch_bounds__(128)
 k_soltab(int64_t nhru, int64_t stride, const double* __restrict__ hru_slope,
          const double* __restrict__ hru_aspect, const double* __restrict__ hru_lat,
          double* __restrict__ potsw, double* __restrict__ horad,
          double* __restrict__ sunhrs, double* __restrict__ hru_cossl) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = blockIdx.y;
   if (i >= nhru) return;
-  double solt, sunh;
   // horizontal surface (prms_solar_geometry.py:141-147), then slope/aspect
   const SolHru flat = sol_hru<CrMath>(0.0, 0.0, hru_lat[i]);
-  sol_day<CrMath>(flat, c_sol_sin_d[j], c_sol_cos_d[j], c_sol_tan_d[j], c_sol_r1[j], solt, sunh);
-  horad[(int64_t)j * stride + i] = solt;
   const SolHru h = sol_hru<CrMath>(hru_slope[i], hru_aspect[i], hru_lat[i]);
-  sol_day<CrMath>(h, c_sol_sin_d[j], c_sol_cos_d[j], c_sol_tan_d[j], c_sol_r1[j], solt, sunh);
-  potsw[(int64_t)j * stride + i] = solt;
-  sunhrs[(int64_t)j * stride + i] = sunh;
-  if (j == 0) hru_cossl[i] = CrMath::cos(CrMath::atan(hru_slope[i]));  // prms_atmosphere.py:519
+  for (int j = blockIdx.y; j < kNdoy; j += kSoltabSlices) {
+    double solt, sunh;
+    sol_day<CrMath>(flat, c_sol_sin_d[j], c_sol_cos_d[j], c_sol_tan_d[j], c_sol_r1[j], solt, sunh);
+    horad[(int64_t)j * stride + i] = solt;
+    sol_day<CrMath>(h, c_sol_sin_d[j], c_sol_cos_d[j], c_sol_tan_d[j], c_sol_r1[j], solt, sunh);
+    potsw[(int64_t)j * stride + i] = solt;
+    sunhrs[(int64_t)j * stride + i] = sunh;
+  }
+  if (blockIdx.y == 0) hru_cossl[i] = CrMath::cos(CrMath::atan(hru_slope[i]));  // prms_atmosphere.py:519
 }
 
 // ---------------------------------------------------------------- init
