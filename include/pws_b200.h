@@ -84,6 +84,9 @@ int pws_set_param_i32(pws_handle *h, const char *name, const int32_t *h_v, int64
  * network then pays its pipeline fill once per run, not per block; only while all
  * chunks of a launch fit the GPU with room to spare; 0: launches are serialised;
  * -1, default: on for segment graphs deeper than 160 levels),
+ * "nhm_sink" (1, default: the reference's default output selection -- the 71 HRU
+ * variables of drb_2yr/nhm.control's netcdf_output_var_names, selected in registry
+ * order -- runs the kernel variant that knows this selection at compile time),
  * "wide_column" / "one_cta_carveout" (1, default: grids of at most one CTA per SM
  * run the column kernel variant without a register cap, with the shared-memory
  * carve-out of one CTA). */

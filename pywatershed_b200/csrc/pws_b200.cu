@@ -102,7 +102,8 @@ struct pws_handle {
   int overlap_routing = -1;  // option "overlap_routing": routing of block b beside the column of b+1 (-1: by domain size)
   int64_t forcing_period = 0;  // option "forcing_period": forcings are [ndays][period], HRU i reads i % period
   bool route_attr_set = false;
-  bool smem_attr_set[32] = {};
+  bool smem_attr_set[64] = {};
+  bool nhm_sink = true;     // option "nhm_sink": SINK_NHM for the default output selection
   bool wide_column = true;  // option "wide_column": the uncapped-register column variant on grids of <= one CTA per SM
   bool one_cta_carveout = true;  // option "one_cta_carveout": L1-heavy carve-out for grids of <= one CTA per SM
   bool tiled_outputs = false;  // option "tiled_outputs": [day][tile][variable][H] (SINK_TILED)
@@ -465,6 +466,7 @@ extern "C" int pws_set_option(pws_handle* h, const char* name, double value) {
     h->lanes_opt = (int)value;
     return 0;
   }
+  else if (!strcmp(name, "nhm_sink")) { h->nhm_sink = value != 0.0; return 0; }
   else if (!strcmp(name, "wide_column")) { h->wide_column = value != 0.0; return 0; }
   else if (!strcmp(name, "one_cta_carveout")) { h->one_cta_carveout = value != 0.0; return 0; }
   else if (!strcmp(name, "overlap_routing")) { h->overlap_routing = value < 0 ? -1 : (value != 0.0); return 0; }
@@ -1430,6 +1432,13 @@ static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const d
       PWS_FAIL(h, "tiled_outputs needs every HRU variable selected in registry order");
     mode = SINK_TILED;
   }
+  if (mode == SINK_SELECT && h->nhm_sink) {
+    // the reference's default output selection, in registry order: the kernel variant
+    // that knows the selection at compile time
+    bool same = true;
+    for (int v = 0; v < PWS_N_HRU_VARS && same; ++v) same = h->slot_hru[v] == nhm_slot(v);
+    if (same) mode = SINK_NHM;
+  }
   if (ensure_scratch(h, ndays)) return 1;
   const bool want_viol = h_viol_dst != nullptr;
   const int p = (int)(h->blocks_enqueued & 1);
@@ -1499,16 +1508,19 @@ static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const d
       if (mode == SINK_FULL) PWS_LAUNCH_COLUMN_P(SINK_FULL, 128, false, true, grid, st);
       else if (mode == SINK_TILED) PWS_LAUNCH_COLUMN_P(SINK_TILED, 128, false, true, grid, st);
       else if (mode == SINK_NONE) PWS_LAUNCH_COLUMN_P(SINK_NONE, 128, false, true, grid, st);
+      else if (mode == SINK_NHM) PWS_LAUNCH_COLUMN_P(SINK_NHM, 128, false, true, grid, st);
       else PWS_LAUNCH_COLUMN_P(SINK_SELECT, 128, false, true, grid, st);
     } else if (H == 128) {
       if (mode == SINK_FULL) PWS_LAUNCH_COLUMN(SINK_FULL, 128, grid, st);
       else if (mode == SINK_TILED) PWS_LAUNCH_COLUMN(SINK_TILED, 128, grid, st);
       else if (mode == SINK_NONE) PWS_LAUNCH_COLUMN(SINK_NONE, 128, grid, st);
+      else if (mode == SINK_NHM) PWS_LAUNCH_COLUMN(SINK_NHM, 128, grid, st);
       else PWS_LAUNCH_COLUMN(SINK_SELECT, 128, grid, st);
     } else {
       if (mode == SINK_FULL) PWS_LAUNCH_COLUMN(SINK_FULL, PWS_COLUMN_HRUS, grid, st);
       else if (mode == SINK_TILED) PWS_LAUNCH_COLUMN(SINK_TILED, PWS_COLUMN_HRUS, grid, st);
       else if (mode == SINK_NONE) PWS_LAUNCH_COLUMN(SINK_NONE, PWS_COLUMN_HRUS, grid, st);
+      else if (mode == SINK_NHM) PWS_LAUNCH_COLUMN(SINK_NHM, PWS_COLUMN_HRUS, grid, st);
       else PWS_LAUNCH_COLUMN(SINK_SELECT, PWS_COLUMN_HRUS, grid, st);
     }
     h->launches++;

@@ -178,7 +178,11 @@ struct ColumnArgs {
 //                [variable][H units]: the row of a variable is a compile-time
 //                byte offset inside the tile, so a value costs one STG with an
 //                immediate offset and no address arithmetic at all
-enum { SINK_SELECT = 0, SINK_FULL = 1, SINK_NONE = 2, SINK_TILED = 3 };
+//   SINK_NHM     the reference's default output selection (PWS_NHM_DEFAULT_HRU_VARS,
+//                71 variables) in registry order, rows layout: the selection is
+//                a compile-time fact, so the values nobody asked for are not
+//                computed at all and the rows are constants as in SINK_FULL
+enum { SINK_SELECT = 0, SINK_FULL = 1, SINK_NONE = 2, SINK_TILED = 3, SINK_NHM = 4 };
 
 constexpr int kHruVarKind[PWS_N_HRU_VARS] = {
 #define KIND_F 0
@@ -203,6 +207,24 @@ constexpr int full_slot(int var) {
 template <int var>
 struct FullSlot {
   static constexpr unsigned value = (unsigned)full_slot(var);
+};
+// ... and among the default output selection (-1: not part of it)
+constexpr bool nhm_selected(int var) {
+#define X(name) if (var == V_##name) return true;
+  PWS_NHM_DEFAULT_HRU_VARS(X)
+#undef X
+  return false;
+}
+constexpr int nhm_slot(int var) {
+  if (!nhm_selected(var)) return -1;
+  int n = 0;
+  for (int k = 0; k < var; ++k)
+    if (nhm_selected(k) && kHruVarKind[k] == kHruVarKind[var]) ++n;
+  return n;
+}
+template <int var>
+struct NhmSlot {
+  static constexpr int value = nhm_slot(var);
 };
 
 template <int kMode, int H>
@@ -231,6 +253,15 @@ struct GpuSink {
       constexpr unsigned byte_off = FullSlot<var>::value * (unsigned)H * 8u;
       if (live)
         asm volatile("st.global." PWS_COLUMN_ST ".f64 [%0+%1], %2;" ::"l"(pf), "n"(byte_off), "d"(v));
+    } else if constexpr (kMode == SINK_NHM) {
+      constexpr int slot = NhmSlot<var>::value;
+      if constexpr (slot >= 0) {
+        unsigned long long addr;
+        asm("mad.wide.u32 %0, %1, %2, %3;"
+            : "=l"(addr)
+            : "r"(stride8), "n"(slot), "l"((unsigned long long)pf));
+        if (live) asm volatile("st.global." PWS_COLUMN_ST ".f64 [%0], %1;" ::"l"(addr), "d"(v));
+      }
     } else if constexpr (kMode == SINK_SELECT) {
       const int64_t o = a.off[var];
       if (o >= 0 && live)
@@ -250,6 +281,15 @@ struct GpuSink {
       constexpr unsigned byte_off = FullSlot<var>::value * (unsigned)H * 4u;
       if (live)
         asm volatile("st.global." PWS_COLUMN_ST ".s32 [%0+%1], %2;" ::"l"(pi), "n"(byte_off), "r"(v));
+    } else if constexpr (kMode == SINK_NHM) {
+      constexpr int slot = NhmSlot<var>::value;
+      if constexpr (slot >= 0) {
+        unsigned long long addr;
+        asm("mad.wide.u32 %0, %1, %2, %3;"
+            : "=l"(addr)
+            : "r"(stride4), "n"(slot), "l"((unsigned long long)pi));
+        if (live) asm volatile("st.global." PWS_COLUMN_ST ".s32 [%0], %1;" ::"l"(addr), "r"(v));
+      }
     } else if constexpr (kMode == SINK_SELECT) {
       const int64_t o = a.off[var];
       if (o >= 0 && live)

@@ -127,6 +127,27 @@
   X(channel_sroff_vol, F, PWS_NAN) X(channel_ssres_flow_vol, F, PWS_NAN)      \
   X(channel_gwres_flow_vol, F, PWS_NAN)
 
+// ---- the HRU variables of the reference's default output selection
+// (`netcdf_output_var_names` of pywatershed/data/drb_2yr/nhm.control intersected with
+// the public variables: tests/golden/nhm_default_vars.json), in registry order: the
+// compile-time selection of k_hru_column<SINK_NHM> -------------------------
+#define PWS_NHM_DEFAULT_HRU_VARS(X)                                           \
+  X(tmaxf) X(tminf) X(prmx) X(hru_ppt) X(hru_rain) X(hru_snow) X(swrad)       \
+  X(potet) X(transp_on) X(tmaxc) X(tavgc) X(tminc) X(pptmix) X(orad_hru)      \
+  X(net_ppt) X(net_rain) X(net_snow) X(intcp_changeover) X(intcp_evap)        \
+  X(intcp_stor) X(hru_intcpevap) X(hru_intcpstor) X(albedo) X(freeh2o)        \
+  X(iso) X(newsnow) X(pk_ice) X(pkwater_equiv) X(pptmix_nopack) X(pst)        \
+  X(salb) X(snow_evap) X(snowcov_area) X(snowmelt) X(tcal)                    \
+  X(contrib_fraction) X(infil) X(sroff) X(hru_sroffp) X(hru_sroffi)           \
+  X(hru_impervevap) X(hru_impervstor) X(dprst_sroff_hru) X(dprst_seep_hru)    \
+  X(dprst_evap_hru) X(dprst_stor_hru) X(cap_infil_tot) X(hru_actet)           \
+  X(perv_actet) X(potet_lower) X(potet_rechr) X(pref_flow)                    \
+  X(pref_flow_infil) X(pref_flow_stor) X(recharge) X(slow_flow)               \
+  X(slow_stor) X(soil_lower) X(soil_lower_ratio) X(soil_moist)                \
+  X(soil_moist_tot) X(soil_rechr) X(soil_to_gw) X(soil_to_ssr) X(ssr_to_gw)   \
+  X(ssres_flow) X(ssres_in) X(ssres_stor) X(gwres_flow) X(gwres_sink)         \
+  X(gwres_stor)
+
 // ---- public per-segment variables (all float64) -------------------------
 #define PWS_SEG_VARS(X)                                                       \
   X(channel_outflow_vol) X(seg_lateral_inflow) X(seg_upstream_inflow)         \

@@ -22,8 +22,8 @@ def _tiled(drb, ntile, nd):
 def _run(pt, ft, start, hv, sv, block_days=None, **kw):
     from pywatershed_b200 import Engine
 
-    opts = {k: kw.pop(k) for k in ("overlap_routing", "column_hrus", "wide_column", "one_cta_carveout")
-            if k in kw}
+    opts = {k: kw.pop(k) for k in ("overlap_routing", "column_hrus", "wide_column", "one_cta_carveout",
+                                   "nhm_sink") if k in kw}
     e = Engine(pt, start, **kw)
     for k, v in opts.items():
         e._opt(k, v)
@@ -125,6 +125,36 @@ def test_full_chain_with_overlapped_routing_launches(drb):
         np.testing.assert_array_equal(res[1][2][k], v, err_msg=k)
     ref, _ = po.Oracle(pt, start=start).run(ft["prcp"], ft["tmax"], ft["tmin"], (), ("seg_outflow",))
     np.testing.assert_allclose(res[1][0]["seg_outflow"], ref["seg_outflow"], rtol=1e-9, atol=1e-10)
+
+
+def test_default_output_selection_kernel_equals_the_general_one(drb):
+    """The reference's default output selection (nhm.control's netcdf_output_var_names,
+    71 HRU variables) in registry order runs k_hru_column<SINK_NHM>, which knows the
+    selection at compile time and does not compute what nobody asked for: the same
+    bits as the general SINK_SELECT kernel, in every launch shape; any other order or
+    subset takes the general kernel."""
+    import json
+    import pathlib as pl
+
+    from pywatershed_b200 import Engine
+
+    nd = 45
+    pt, ft, start = _tiled(drb, 2, nd)
+    names = json.loads((pl.Path(__file__).parent / "golden" / "nhm_default_vars.json").read_text())
+    reg = Engine(pt, start).reg
+    hv = [v for v in reg.hru_vars if v in names]
+    sv = [v for v in reg.seg_vars if v in names]
+    assert len(hv) == 71
+    base, vb, _ = _run(pt, ft, start, hv, sv, block_days=16, nhm_sink=0, column_hrus=256)
+    for opts in (dict(column_hrus=256), dict(column_hrus=128, wide_column=1), dict(column_hrus=128, wide_column=0)):
+        got, vg, _ = _run(pt, ft, start, hv, sv, block_days=16, nhm_sink=1, **opts)
+        for k in hv + sv:
+            np.testing.assert_array_equal(np.asarray(got[k]), np.asarray(base[k]), err_msg=f"{k} {opts}")
+        np.testing.assert_array_equal(vg, vb)
+    # reversed order: not the compile-time layout, the general kernel serves it
+    got, _, _ = _run(pt, ft, start, hv[::-1], sv, block_days=16, nhm_sink=1)
+    for k in hv:
+        np.testing.assert_array_equal(np.asarray(got[k]), np.asarray(base[k]), err_msg=k)
 
 
 def test_device_resident_blocks_overlap_safely(drb):
