@@ -59,7 +59,8 @@ int pws_set_param_i32(pws_handle *h, const char *name, const int32_t *h_v, int64
  * "tma" (1, default: the column kernel stages each day's forcing rows in shared
  * memory with TMA bulk copies when they are 16-byte aligned; 0: per-thread loads),
  * "column_hrus" (HRUs per CTA of the column kernel: 0, default = by domain size,
- * 128 or 256),
+ * 128, 192 (one uncapped-register CTA per SM; picked for domains of 128..192 HRUs per SM)
+ * or 256),
  * "soltab_device" (1, default: build the PRMSSolarGeometry tables with the CUDA
  * kernel k_soltab; 0: on host threads with the host libm the reference's tables
  * come from -- a debugging aid for last-bit comparisons, not a product path),

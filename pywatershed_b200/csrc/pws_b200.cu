@@ -102,7 +102,7 @@ struct pws_handle {
   int overlap_routing = -1;  // option "overlap_routing": routing of block b beside the column of b+1 (-1: by domain size)
   int64_t forcing_period = 0;  // option "forcing_period": forcings are [ndays][period], HRU i reads i % period
   bool route_attr_set = false;
-  bool smem_attr_set[64] = {};
+  bool smem_attr_set[64] = {};  // (mode 5) x (H 3) x period x wide
   bool nhm_sink = true;     // option "nhm_sink": SINK_NHM for the default output selection
   bool wide_column = true;  // option "wide_column": the uncapped-register column variant on grids of <= one CTA per SM
   bool one_cta_carveout = true;  // option "one_cta_carveout": L1-heavy carve-out for grids of <= one CTA per SM
@@ -480,8 +480,8 @@ extern "C" int pws_set_option(pws_handle* h, const char* name, double value) {
     return 0;
   }
   else if (!strcmp(name, "column_hrus")) {
-    if (value != 0 && value != 128 && value != PWS_COLUMN_HRUS)
-      PWS_FAIL(h, "pws_set_option: column_hrus must be 0, 128 or %d", PWS_COLUMN_HRUS);
+    if (value != 0 && value != 128 && value != 192 && value != PWS_COLUMN_HRUS)
+      PWS_FAIL(h, "pws_set_option: column_hrus must be 0, 128, 192 or %d", PWS_COLUMN_HRUS);
     h->column_hrus_opt = (int)value;
     return 0;
   }
@@ -1279,12 +1279,23 @@ static int enqueue_channel(pws_handle* h, cudaStream_t st, int ndays, const doub
   return 0;
 }
 
-// HRUs per CTA of k_hru_column: 128 while that is what it takes to give every SM a
-// CTA, PWS_COLUMN_HRUS (256) for domains that fill the GPU anyway
+// HRUs per CTA of k_hru_column.  Domains that fill the GPU several times: 256.  A
+// smaller one is ONE wave and takes as long as its fullest SM, so the grid should (i)
+// put one CTA on an SM, not two of 128 on some and one on others, and (ii) leave SMs
+// for the routing CTAs of the previous block (a chunk takes a whole SM too): the
+// smallest of 128, 192 (both with uncapped registers) and 256 whose grid fits beside
+// the routing chunks; when none does, 128.  A quarter of the CONUS domain (27,540 HRUs, 36 chunks) per 256-day
+// block: CTAs of 128 40.5 ms per pass, 192 without room for the routing 45.2, 256 with
+// the routing on the 40 SMs it leaves 33.2 (profiles/r02_column_hrus_experiment.log).
 static int column_hrus(pws_handle* h) {
   if (h->column_hrus_opt == 128 || h->column_hrus_opt == PWS_COLUMN_HRUS) return h->column_hrus_opt;
+  if (h->column_hrus_opt == 192 && h->forcing_period == 0) return 192;
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+  const int64_t room = nsm - (h->nseg > 0 ? h->nchunks : 0);
+  if ((h->nhru + 127) / 128 <= room) return 128;
+  if (h->wide_column && h->forcing_period == 0 && (h->nhru + 191) / 192 <= room) return 192;
+  if ((h->nhru + PWS_COLUMN_HRUS - 1) / PWS_COLUMN_HRUS <= room) return PWS_COLUMN_HRUS;
   return h->nhru <= (int64_t)nsm * PWS_COLUMN_HRUS ? 128 : PWS_COLUMN_HRUS;
 }
 
@@ -1322,7 +1333,8 @@ static bool overlap_routing(pws_handle* h, int ntiles, int H, int lanes) {
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
   const int slots = nsm * (H == 128 ? 2 : 1);
-  return lanes > 1 || ntiles * 10 < slots * 9;
+  // (also when the routing chunks fit on the SMs the column grid leaves: column_hrus())
+  return lanes > 1 || ntiles * 10 < slots * 9 || ntiles + h->nchunks <= nsm;
 }
 
 // number of forcing columns (the row length of prcp / tmax / tmin)
@@ -1461,7 +1473,7 @@ static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const d
   a.ntiles = ntiles;
 #define PWS_LAUNCH_COLUMN_P(MODE, HH, PER, WIDE, GRID, ST)                                       \
   do {                                                                                           \
-    const int key_ = (((MODE) * 2 + ((HH) == 128)) * 2 + (PER)) * 2 + (WIDE);                    \
+    const int key_ = (((MODE) * 3 + ((HH) == 128 ? 1 : (HH) == 192 ? 2 : 0)) * 2 + (PER)) * 2 + (WIDE); \
     if (!h->smem_attr_set[key_]) {                                                               \
       PWS_CUDA(h, (cudaFuncSetAttribute(k_hru_column<MODE, HH, PER, WIDE>,                       \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,             \
@@ -1504,7 +1516,13 @@ static int enqueue_block(pws_handle* h, int ndays, const int32_t* h_cal, const d
     cudaEvent_t e0 = new_event(h), e1 = new_event(h);
     mark_base(h, st);
     cudaEventRecord(e0, st);
-    if (H == 128 && wide) {  // at most one CTA per SM: the variant without a register cap
+    if (H == 192) {  // one uncapped-register CTA of 192 HRUs per SM
+      if (mode == SINK_FULL) PWS_LAUNCH_COLUMN_P(SINK_FULL, 192, false, true, grid, st);
+      else if (mode == SINK_TILED) PWS_LAUNCH_COLUMN_P(SINK_TILED, 192, false, true, grid, st);
+      else if (mode == SINK_NONE) PWS_LAUNCH_COLUMN_P(SINK_NONE, 192, false, true, grid, st);
+      else if (mode == SINK_NHM) PWS_LAUNCH_COLUMN_P(SINK_NHM, 192, false, true, grid, st);
+      else PWS_LAUNCH_COLUMN_P(SINK_SELECT, 192, false, true, grid, st);
+    } else if (H == 128 && wide) {  // at most one CTA per SM: the variant without a register cap
       if (mode == SINK_FULL) PWS_LAUNCH_COLUMN_P(SINK_FULL, 128, false, true, grid, st);
       else if (mode == SINK_TILED) PWS_LAUNCH_COLUMN_P(SINK_TILED, 128, false, true, grid, st);
       else if (mode == SINK_NONE) PWS_LAUNCH_COLUMN_P(SINK_NONE, 128, false, true, grid, st);

@@ -444,9 +444,9 @@ struct LowerStateMixed {
 template <int kMode, int H, bool kPeriod = false, bool kWide = false>
 __global__ void __launch_bounds__(2 * H, (2 * H <= 256 && !kWide) ? 512 / (2 * H) : 1)
 k_hru_column(const __grid_constant__ ColumnArgs a) {
-  static_assert(!kWide || H == 128, "the wide variant is built for 128 HRUs per CTA");
+  static_assert(!kWide || H == 128 || H == 192, "the wide variant is built for 128 or 192 HRUs per CTA");
   // setmaxnreg acts on whole warpgroups (4 warps): each half must be a multiple of one
-  static_assert(H % 128 == 0, "HRUs per CTA must be a multiple of 128");
+  static_assert(kWide ? H % 32 == 0 : H % 128 == 0, "HRUs per CTA must be a multiple of 128 (wide: of 32)");
   constexpr size_t kColumnParamBytes = ColumnSmem<H>::kParamBytes;
   constexpr size_t kColumnForcBytes = ColumnSmem<H>::kForcBytes;
   const int tid = threadIdx.x;

@@ -73,7 +73,7 @@ def test_column_kernel_variants_agree(drb, outputs):
     sv = list(reg_s)
     base, vb, _ = _run(pt, ft, start, hv, sv, block_days=16, column_hrus=256)
     for opts in (dict(column_hrus=128, wide_column=1), dict(column_hrus=128, wide_column=0),
-                 dict(column_hrus=128, wide_column=0, one_cta_carveout=0)):
+                 dict(column_hrus=128, wide_column=0, one_cta_carveout=0), dict(column_hrus=192)):
         got, vg, _ = _run(pt, ft, start, hv, sv, block_days=16, **opts)
         for k in hv + sv:
             np.testing.assert_array_equal(np.asarray(got[k]), np.asarray(base[k]), err_msg=f"{k} {opts}")
@@ -146,7 +146,8 @@ def test_default_output_selection_kernel_equals_the_general_one(drb):
     sv = [v for v in reg.seg_vars if v in names]
     assert len(hv) == 71
     base, vb, _ = _run(pt, ft, start, hv, sv, block_days=16, nhm_sink=0, column_hrus=256)
-    for opts in (dict(column_hrus=256), dict(column_hrus=128, wide_column=1), dict(column_hrus=128, wide_column=0)):
+    for opts in (dict(column_hrus=256), dict(column_hrus=128, wide_column=1), dict(column_hrus=128, wide_column=0),
+                 dict(column_hrus=192)):
         got, vg, _ = _run(pt, ft, start, hv, sv, block_days=16, nhm_sink=1, **opts)
         for k in hv + sv:
             np.testing.assert_array_equal(np.asarray(got[k]), np.asarray(base[k]), err_msg=f"{k} {opts}")
@@ -276,7 +277,7 @@ def test_device_accumulations_are_the_reference_sums(drb):
     e.close()
 
 
-@pytest.mark.parametrize("ntile,column_hrus", [(1, 0), (3, 128), (2, 256)])
+@pytest.mark.parametrize("ntile,column_hrus", [(1, 0), (3, 128), (2, 256), (2, 192)])
 def test_tiled_results_through_run_host(drb, ntile, column_hrus):
     """The tiled result layout ([day][tile][variable][H]) drained by pws_run_host:
     every variable un-tiled on the host equals the rows layout."""
