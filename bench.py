@@ -1089,7 +1089,7 @@ def model_leg(spec, ndays=731):
     out["first_run_s"] = time.perf_counter() - t0
     chk = float(m.processes["PRMSChannel"]["seg_outflow"].sum())
     ts = []
-    for _ in range(2):
+    for _ in range(4):
         m = make()
         m._ensure_engine()  # construction cost reported separately
         t0 = time.perf_counter()
