@@ -1192,8 +1192,10 @@ k_route_chunks(const __grid_constant__ ChannelArgs a) {
   // ---- prognostic state
   double outflow_ts = 0.0, seg_inflow_prev = 0.0;
   if (live) {
-    outflow_ts = a.outflow_ts[pos];
-    seg_inflow_prev = a.seg_inflow[pos];
+    // (L2 loads: with overlapped launches the previous launch stored these while this
+    // kernel was already running, and L1 is not coherent)
+    outflow_ts = __ldcg(a.outflow_ts + pos);
+    seg_inflow_prev = __ldcg(a.seg_inflow + pos);
   }
   // A window = the kStepsPerDay steps of one day.  The start of day k falls
   // into window k + delay / kStepsPerDay; at every window start the lateral
