@@ -23,6 +23,9 @@ PWS_OPTIONS = (
     "time_step_units", "verbosity", "streamflow_module",
     # pywatershed_b200 additions
     "block_days", "device",
+    # "netcdf4": netCDF-4 / HDF5 files like the reference's (zlib 4, shuffle, one chunk per day) from
+    # our own writer (hdf5_out.py) when the netCDF4 module is absent; default "classic" (NetCDF-3)
+    "netcdf_output_format",
 )
 
 # base/control.py:47-72: PRMS legacy option -> pywatershed option

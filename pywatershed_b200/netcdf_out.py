@@ -19,6 +19,9 @@ format (cdf_out.py: NetCDF-3 64-bit offset with the same names, dims, dtypes
 and attributes but no compression; a block of days is one contiguous write and
 nothing is held in memory).  Whole blocks are written with
 `var[t0:t1, :] = block`; the files of a block are written by a few threads.
+With the control option `netcdf_output_format: netcdf4` (and no netCDF4 module) the
+files are netCDF-4 / HDF5 from hdf5_out.H5Writer instead: zlib 4, shuffle, one chunk
+per day, dimension scales -- the reference's form, at zlib's pace.
 """
 from __future__ import annotations
 
@@ -41,6 +44,10 @@ def nc4_module():
 
 
 _nc4 = nc4_module()
+# without the netCDF4 module: "classic" = cdf_out.Cdf2Writer (NetCDF-3 64-bit offset,
+# uncompressed, the fast default), "netcdf4" = hdf5_out.H5Writer (netCDF-4 / HDF5 as the
+# reference writes it: zlib 4, shuffle, one chunk per day); control option netcdf_output_format
+_FORMAT = "classic"
 
 _NC_TYPES = {"float64": "f8", "int32": "i4", "bool": "i4", "int64": "i8"}
 # netCDF4.default_fillvals, what the reference passes as fill_value (utils/netcdf_utils.py:607)
@@ -95,7 +102,10 @@ class _File:
                     v.setncattr(k, val)
                 self.v[name] = v
         else:
-            from .cdf_out import Cdf2Writer
+            if _FORMAT == "netcdf4":
+                from .hdf5_out import H5Writer as Cdf2Writer
+            else:
+                from .cdf_out import Cdf2Writer
 
             ds = Cdf2Writer(path)
             ds.setncattr("Description", "pywatershed output data")
@@ -176,6 +186,12 @@ class _File:
 
 class ModelNetcdfOutput:
     def __init__(self, model, output_dir: pl.Path, separate_files: bool, output_vars, budget_args):
+        global _FORMAT
+        fmt = (getattr(model.control, "options", {}) or {}).get("netcdf_output_format")
+        if fmt is not None:
+            if fmt not in ("classic", "netcdf4"):
+                raise ValueError("netcdf_output_format must be 'classic' or 'netcdf4'")
+            _FORMAT = fmt
         self.model = model
         self.dir = pl.Path(output_dir)
         self.files = []
