@@ -147,6 +147,42 @@ def test_netcdf_output_files(drb, tmp_path):
     assert a.shape == (366, 765)
 
 
+def test_netcdf4_output_files_from_our_writer(drb, tmp_path, monkeypatch):
+    """`netcdf_output_format: netcdf4` without the netCDF4 module: the same files as
+    netCDF-4 / HDF5 from hdf5_out.H5Writer (zlib 4, shuffle, a chunk per day), written
+    block by block on the writer thread; read back with the HDF5 reader."""
+    from pywatershed_b200 import hdf5_min, netcdf_out
+
+    if netcdf_out.nc4_module() is not None:
+        pytest.skip("netCDF4 is the backend here")
+    monkeypatch.setattr(netcdf_out, "_FORMAT", "classic")
+    p, f, start = drb
+    nd = 40
+    out_vars = ["pkwater_equiv", "seg_outflow", "newsnow", "soltab_potsw"]
+    m = _model(p, f, start, nd, netcdf_output_var_names=out_vars, netcdf_output_format="netcdf4")
+    m.block_days = 16
+    m.initialize_netcdf(tmp_path)
+    m.run(finalize=True)
+    ref, _ = po.Oracle(p, start=start).run(f["prcp"][:nd], f["tmax"][:nd], f["tmin"][:nd],
+                                           ["pkwater_equiv", "newsnow"], ["seg_outflow"])
+    with hdf5_min.File(tmp_path / "pkwater_equiv.nc") as h:
+        d = h["pkwater_equiv"]
+        assert d.dims == ("time", "nhm_id") and d.shape == (nd, 765)
+        np.testing.assert_allclose(d.read(), ref["pkwater_equiv"], rtol=1e-9, atol=1e-10)
+        day0 = (np.datetime64(start, "D") - np.datetime64("1970-01-01", "D")).astype(int)
+        np.testing.assert_array_equal(h["time"].read(), (day0 + np.arange(nd)).astype(np.float32))
+        assert d.attrs["units"] == "inches" and h["time"].attrs["units"] == "days since 1970-01-01 00:00:00"
+    with hdf5_min.File(tmp_path / "seg_outflow.nc") as h:
+        np.testing.assert_allclose(h["seg_outflow"].read(), ref["seg_outflow"], rtol=1e-9, atol=1e-10)
+        assert h["seg_outflow"].dims == ("time", "nhm_seg")
+    with hdf5_min.File(tmp_path / "newsnow.nc") as h:
+        np.testing.assert_array_equal(h["newsnow"].read(), ref["newsnow"])
+    with hdf5_min.File(tmp_path / "soltab_potsw.nc") as h:
+        assert h["soltab_potsw"].shape == (366, 765) and h["soltab_potsw"].dims == ("doy", "nhm_id")
+        np.testing.assert_array_equal(h["doy"].read(), np.arange(1, 367))
+    assert (tmp_path / "PRMSSnow_budget.nc").read_bytes()[:4] == b"\x89HDF"
+
+
 def test_channel_only_model(drb):
     """examples/05_parameter_ensemble.ipynb cell 20: Model([PRMSChannel]) fed
     with the three volume fluxes."""
