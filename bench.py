@@ -467,6 +467,7 @@ def run_channel_only(args):
         pt, d1 = chain_tiles(p0, pt, ntile)
         depth = d1 * ntile
     eng = Engine(pt, start, device=0)
+    eng.select_outputs((), eng.reg.seg_vars)   # all five public variables are written each day
     nseg = eng.nseg
     T = max(1, min(args.block_days, nd))
     gen = torch.Generator(device=dev).manual_seed(11)
