@@ -509,6 +509,7 @@ def run_channel_only(args):
                                + f"), depth ~{depth} levels, {nd} days x 24 hourly sub-steps",
                    "block_days": T, "l2": "lateral inflow + outputs per block exceed L2"},
         "segment_substeps_per_s": units * 24 / t,
+        "checksum_seg_outflow_last_day": float(out[(nd - 1) % T, eng.sel_seg.index("seg_outflow")].sum()),
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": None, "kernel": "k_route_chunks",
                      "note": "48 B per segment-day (8 read + 5x8 written); the kernel is bound by the "

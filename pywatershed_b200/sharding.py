@@ -10,6 +10,16 @@ segments), and `gather_outputs` puts per-rank results back into the domain's
 order with torch.distributed (gloo on CPU, NCCL on GPUs) -- the only
 communication of a sharded run.  Ensembles shard by member
 (`partition_members`).
+
+A segment graph that does NOT split (the real DRB: 434 of its 456 segments are
+one outlet tree; a chained network) still leaves the HRU columns independent:
+`partition_hrus` deals the HRUs to the ranks segment by segment,
+`lateral_inflow` restates the HRU side of PRMSChannel (prms_channel.py:396-421)
+on a rank's three volume fluxes, `exchange_lateral` is the ONE exchange step of
+that variant (a reduce of seg_lateral_inflow [T, nsegment] per
+block of days to the rank that owns the network), and `SplitColumnsOneRouter`
+drives it: every rank computes its columns, the router rank routes the whole
+network with PRMSChannel alone (pws_run_channel_device) beside its own columns.
 """
 from __future__ import annotations
 
@@ -136,3 +146,188 @@ def reduce_budget_violations(viol: np.ndarray, group=None) -> np.ndarray:
     t = torch.from_numpy(np.ascontiguousarray(viol, dtype=np.int64)).to(dev)
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t.cpu().numpy()
+
+
+# ------------------------------------------------------ HRUs split, one router
+_SEG_NAMES = ("mann_n", "seg_depth", "seg_length", "seg_slope", "x_coef", "segment_flow_init",
+              "segment_type", "tosegment", "tosegment_nhm", "nhm_seg", "seg_lat", "seg_width",
+              "seg_cum_area", "seg_elev", "obsin_segment", "obsout_segment", "seg_humidity")
+
+
+def partition_hrus(hru_segment, nranks: int) -> np.ndarray:
+    """hru_rank [nhru] for a domain whose segment graph stays on one rank: all HRUs
+    of a segment go to the same rank (so each segment's lateral inflow is summed by
+    ONE rank, in the reference's order: ascending HRU index, prms_channel.py:396-421),
+    segments are dealt in runs of consecutive numbers holding about nhru / nranks HRUs;
+    HRUs without a segment are dealt round-robin."""
+    hs = np.asarray(hru_segment, dtype=np.int64)
+    att = hs > 0
+    nseg = int(hs.max(initial=0))
+    cnt = np.bincount(hs[att] - 1, minlength=nseg)
+    before = np.cumsum(cnt) - cnt
+    total = max(int(cnt.sum()), 1)
+    seg_rank = np.minimum((before * nranks) // total, nranks - 1)
+    hru_rank = np.empty(hs.shape[0], dtype=np.int64)
+    hru_rank[att] = seg_rank[hs[att] - 1]
+    loose = np.where(~att)[0]
+    hru_rank[loose] = np.arange(loose.size) % nranks
+    return hru_rank
+
+
+def shard_hru_parameters(params: dict, hru_rank, rank: int):
+    """The HRU side of one rank (no segment parameter: a domain for an Engine with
+    channel=False) + hru_idx, the global indices of its HRUs, ascending."""
+    nhru = np.asarray(params["hru_area"]).shape[0]
+    hru_idx = np.where(np.asarray(hru_rank) == rank)[0]
+    out = {}
+    for k, v in params.items():
+        if k in _SEG_NAMES or k == "hru_segment":
+            continue
+        v = np.asarray(v)
+        if k != "snarea_curve" and v.ndim >= 1 and v.shape[-1] == nhru:
+            out[k] = np.ascontiguousarray(v[..., hru_idx])
+        else:
+            out[k] = v
+    return out, hru_idx
+
+
+LATERAL_TERMS = ("sroff_vol", "ssres_flow_vol", "gwres_flow_vol")
+
+
+def lateral_plan(hru_segment, hru_idx):
+    """Passes of the lateral-inflow sum of one rank: [(local HRU positions, global
+    segment indices)] -- pass k holds the k-th HRU (ascending HRU index) of every
+    segment this rank feeds, so a pass touches a segment at most once and the passes
+    in order add a segment's HRUs in the reference's order."""
+    seg = np.asarray(hru_segment, dtype=np.int64)[np.asarray(hru_idx)] - 1
+    att = np.where(seg >= 0)[0]
+    order = np.lexsort((att, seg[att]))
+    h, sg = att[order], seg[att][order]
+    n = sg.shape[0]
+    first = np.ones(n, dtype=bool)
+    first[1:] = sg[1:] != sg[:-1]
+    occ = np.arange(n) - np.maximum.accumulate(np.where(first, np.arange(n), 0))
+    return [(h[occ == k], sg[occ == k]) for k in range(int(occ.max(initial=-1)) + 1)]
+
+
+def lateral_inflow(sroff_vol, ssres_flow_vol, gwres_flow_vol, plan, nseg: int, out=None):
+    """seg_lateral_inflow [T, nseg] (cfs) of this rank's HRUs, zero on segments it does
+    not feed: prms_channel.py:396-421 on arrays [T, nhru_local] (numpy, or torch tensors
+    on any device with `plan` as index tensors of that device).  Same operations in the
+    same order as the fused kernel's HRU side (hru_column.cuh, "PRMSChannel, HRU side"):
+    ((sroff_vol + ssres_flow_vol) + gwres_flow_vol) / 86400 per HRU, HRUs of a segment
+    added in ascending order starting from 0."""
+    q = (sroff_vol + ssres_flow_vol) + gwres_flow_vol
+    if isinstance(q, np.ndarray):
+        q = q / 86400.0
+    else:
+        # a tensor divisor: torch turns division by a Python scalar into a multiplication
+        # by its reciprocal on CUDA, which is not the correctly rounded quotient
+        q = q / q.new_full((1,), 86400.0)
+    if out is None:
+        out = np.zeros((q.shape[0], nseg)) if isinstance(q, np.ndarray) else q.new_zeros((q.shape[0], nseg))
+    else:
+        out[...] = 0.0
+    for h, sg in plan:
+        out[:, sg] = out[:, sg] + q[:, h]
+    return out
+
+
+def exchange_lateral(lat, router: int = 0, group=None):
+    """The exchange step: every segment's lateral inflow was summed by exactly one rank
+    and is zero elsewhere, so a SUM-reduce to the router (x + 0 is exact in any order)
+    delivers the whole network's [T, nseg] rows bit for bit.  `lat`: a torch tensor,
+    reduced in place on the router (NCCL on GPUs, gloo on CPU)."""
+    import torch.distributed as dist
+
+    dist.reduce(lat, dst=router, op=dist.ReduceOp.SUM, group=group)
+    return lat
+
+
+class SplitColumnsOneRouter:
+    """One domain on N GPUs when its segment graph does not split: rank r computes the
+    columns of its HRUs (Engine over `shard_hru_parameters`, no channel), the router
+    rank also owns an Engine over the whole domain's segments and routes every block
+    with PRMSChannel alone after the exchange.  The next block's columns are enqueued
+    before a block's exchange, so columns, exchange and routing of neighbouring blocks
+    overlap on the device."""
+
+    def __init__(self, params: dict, start, rank: int, world: int, device: int, router: int = 0,
+                 hru_vars=(), seg_vars=None, block_days: int = 256, group=None, **engine_kw):
+        import torch
+
+        from .engine import Engine
+
+        self.rank, self.world, self.router, self.group = rank, world, router, group
+        self.dev = torch.device("cuda", device)
+        self.T = int(block_days)
+        self.nseg = int(np.asarray(params["tosegment"]).shape[0])
+        hru_rank = partition_hrus(params["hru_segment"], world)
+        q, self.hru_idx = shard_hru_parameters(params, hru_rank, rank)
+        self.cols = Engine(q, start, device=device, channel=False, **engine_kw)
+        self.hru_vars = list(hru_vars)
+        sel = self.hru_vars + [v for v in LATERAL_TERMS if v not in self.hru_vars]
+        self.cols.select_outputs(sel, ())
+        if self.cols.sel_i32:
+            raise ValueError("SplitColumnsOneRouter: float64 HRU variables only")
+        self._term = [self.cols.sel_f64.index(v) for v in LATERAL_TERMS]
+        self.plan = [(torch.from_numpy(h).to(self.dev), torch.from_numpy(s).to(self.dev))
+                     for h, s in lateral_plan(params["hru_segment"], self.hru_idx)]
+        self.route = None
+        if rank == router:
+            self.route = Engine(params, start, device=device, **engine_kw)
+            self.seg_vars = list(self.route.reg.seg_vars if seg_vars is None else seg_vars)
+            self.route.select_outputs((), self.seg_vars)
+        nv = len(self.cols.sel_f64)
+        self.out = [torch.empty((self.T, nv, self.cols.nhru), dtype=torch.float64, device=self.dev)
+                    for _ in range(2)]
+        self.lat = [torch.empty((self.T, self.nseg), dtype=torch.float64, device=self.dev) for _ in range(2)]
+
+    def reset(self):
+        self.cols.reset()
+        if self.route is not None:
+            self.route.reset()
+
+    def close(self):
+        self.cols.close()
+        if self.route is not None:
+            self.route.close()
+
+    def run_device(self, prcp, tmax, tmin, seg_out=None, hru_out=None):
+        """Advance len(prcp) days: forcings = torch tensors [nd, nhru_local] on this
+        rank's GPU; `seg_out` (router only): [nd, len(seg_vars), nseg] on the GPU;
+        `hru_out` (optional): [nd, len(hru_vars), nhru_local].  Returns when the
+        device has finished."""
+        import torch
+
+        nd, nloc = prcp.shape[0], self.cols.nhru
+        blocks = [(d, min(self.T, nd - d)) for d in range(0, nd, self.T)]
+
+        def columns(b):
+            d, n = blocks[b]
+            o = d * nloc * 8
+            self.cols.run_device(n, prcp.data_ptr() + o, tmax.data_ptr() + o, tmin.data_ptr() + o,
+                                 self.out[b % 2].data_ptr(), sync=False)
+
+        columns(0)
+        for b, (d, n) in enumerate(blocks):
+            self.cols.sync()                          # block b's columns are in self.out[b % 2]
+            if b + 1 < len(blocks):
+                columns(b + 1)                        # runs beside the exchange and the routing of b
+            if self.route is not None:
+                self.route.sync()                     # the routing that read self.lat[b % 2] is done
+            o = self.out[b % 2][:n]
+            lat = self.lat[b % 2][:n]
+            lateral_inflow(o[:, self._term[0]], o[:, self._term[1]], o[:, self._term[2]], self.plan,
+                           self.nseg, out=lat)
+            if hru_out is not None and self.hru_vars:
+                hru_out[d:d + n] = o[:, :len(self.hru_vars)]
+            if self.world > 1:
+                exchange_lateral(lat, self.router, self.group)
+            torch.cuda.current_stream().synchronize()
+            if self.route is not None:
+                self.route.run_channel_device(n, lat.data_ptr(),
+                                              seg_out[d:d + n].data_ptr() if seg_out is not None else 0,
+                                              sync=False)
+        if self.route is not None:
+            self.route.sync()

@@ -103,3 +103,108 @@ def test_two_gpu_sharded_run_equals_unsharded():
     mp.spawn(_worker, args=(2, port, 30, ret), nprocs=2, join=True)
     assert ret.get("ok") is True
     assert 0 < ret["nlocal"] < 5 * 765
+
+
+# ---------------------------------------------------------------- HRUs split, one router
+def _split_case(nd, ntile=4):
+    import bench
+    import scenarios as sc
+
+    p, f, start = sc.load_drb()
+    pt, ft = sc.tile(p, {k: v[:nd] for k, v in f.items()}, ntile)
+    pt, _ = bench.chain_tiles(p, pt, ntile)               # ONE outlet tree: basin sharding cannot split it
+    return pt, ft, start
+
+
+def _run_split(pt, ft, start, rank, world, device, block_days):
+    import torch
+
+    from pywatershed_b200 import sharding
+
+    hv = ["pkwater_equiv", "soil_moist", "sroff_vol"]
+    run = sharding.SplitColumnsOneRouter(pt, start, rank, world, device, hru_vars=hv, block_days=block_days)
+    dev = torch.device("cuda", device)
+    hi = run.hru_idx
+    forc = [torch.from_numpy(np.ascontiguousarray(ft[k][:, hi])).to(dev) for k in ("prcp", "tmax", "tmin")]
+    nd = forc[0].shape[0]
+    seg = torch.zeros((nd, 5, run.nseg), dtype=torch.float64, device=dev) if run.route is not None else None
+    hru = torch.zeros((nd, len(hv), hi.size), dtype=torch.float64, device=dev)
+    run.run_device(*forc, seg_out=seg, hru_out=hru)
+    sv = list(run.seg_vars) if run.route is not None else []
+    run.close()
+    return hv, sv, hi, hru.cpu().numpy(), (seg.cpu().numpy() if seg is not None else None)
+
+
+def _reference(pt, ft, start, hv, sv):
+    from pywatershed_b200 import Engine
+
+    one = Engine(pt, start, device=0)
+    one.select_outputs(hv, sv)
+    ref, _ = one.run_host(ft["prcp"], ft["tmax"], ft["tmin"])
+    one.close()
+    return ref
+
+
+def test_split_columns_one_router_on_one_gpu_equals_the_chain():
+    """world = 1: columns through an Engine without a channel, lateral inflow restated in
+    torch (sharding.lateral_inflow), PRMSChannel alone on a second handle, blocks of 7
+    days pipelined -- every segment variable equals the fused chain bit for bit."""
+    pt, ft, start = _split_case(30)
+    hv, sv, hi, hru, seg = _run_split(pt, ft, start, 0, 1, 0, 7)
+    ref = _reference(pt, ft, start, hv, sv)
+    assert float(seg[-1, sv.index("seg_outflow")].sum()) > 0.0
+    for k, v in enumerate(hv):
+        np.testing.assert_array_equal(hru[:, k], np.asarray(ref[v]), err_msg=v)
+    for k, v in enumerate(sv):
+        np.testing.assert_array_equal(seg[:, k], np.asarray(ref[v]), err_msg=v)
+
+
+def _worker_split(rank, world, port, nd, ret):
+    import pathlib as pl
+    import sys
+
+    root = pl.Path(__file__).resolve().parent.parent
+    for q in (root, root / "tests"):
+        if str(q) not in sys.path:
+            sys.path.insert(0, str(q))
+    import torch
+    import torch.distributed as dist
+
+    from pywatershed_b200 import sharding
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        pt, ft, start = _split_case(nd)
+        hv, sv, hi, hru, seg = _run_split(pt, ft, start, rank, world, rank, 8)
+        nhru = pt["hru_area"].shape[0]
+        full = {v: sharding.gather_outputs(hru[:, k], hi, nhru) for k, v in enumerate(hv)}
+        if rank == 0:
+            ref = _reference(pt, ft, start, hv, sv)
+            ok = all(np.array_equal(full[v], np.asarray(ref[v])) for v in hv)
+            ok = ok and all(np.array_equal(seg[:, k], np.asarray(ref[v])) for k, v in enumerate(sv))
+            ret["ok"] = bool(ok)
+            ret["nlocal"] = int(hi.size)
+            ret["flow"] = float(seg[-1, sv.index("seg_outflow")].sum())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_gpu_split_columns_one_router_equals_unsharded():
+    """The exchange-step variant on two GPUs (NCCL reduce of seg_lateral_inflow to the
+    router): one chained tree of four tiles, equal to the unsharded chain bit for bit."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_split, args=(2, port, 30, ret), nprocs=2, join=True)
+    assert ret.get("ok") is True
+    assert 0 < ret["nlocal"] < 4 * 765 and ret["flow"] > 0.0

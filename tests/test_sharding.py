@@ -98,3 +98,111 @@ def test_two_rank_gloo_run_equals_unsharded():
     mp.spawn(_worker, args=(2, port, 25, ret), nprocs=2, join=True)
     assert ret.get("ok") is True
     assert 0 < ret["nlocal"] < 3 * 765
+
+
+# ---------------------------------------------------------------- HRUs split, one router
+def test_partition_hrus_keeps_a_segments_hrus_together(drb):
+    from pywatershed_b200 import sharding
+
+    p, f, start = drb
+    pt, _ = scenarios.tile(p, {k: v[:2] for k, v in f.items()}, 3)
+    hs = pt["hru_segment"]
+    for nranks in (1, 2, 3, 8):
+        hru_rank = sharding.partition_hrus(hs, nranks)
+        att = hs > 0
+        for sgm in np.unique(hs[att]):
+            assert np.unique(hru_rank[hs == sgm]).size == 1
+        load = np.bincount(hru_rank, minlength=nranks)
+        assert load.sum() == hs.size and load.max() - load.min() <= 8 + hs.size // 100
+        seen = np.zeros(hs.size, dtype=int)
+        for r in range(nranks):
+            q, hi = sharding.shard_hru_parameters(pt, hru_rank, r)
+            seen[hi] += 1
+            assert "tosegment" not in q and "hru_segment" not in q and "seg_length" not in q
+            assert q["tmax_cbh_adj"].shape == (12, hi.size) and q["snarea_curve"].shape == pt["snarea_curve"].shape
+            plan = sharding.lateral_plan(hs, hi)
+            touched = np.concatenate([sg for _, sg in plan]) if plan else np.zeros(0, int)
+            assert np.array_equal(np.sort(np.concatenate([h for h, _ in plan])), np.where(hs[hi] > 0)[0])
+            for _, sg in plan:
+                assert np.unique(sg).size == sg.size          # a pass touches a segment once
+            assert np.array_equal(np.unique(touched), np.unique(hs[hi][hs[hi] > 0] - 1))
+        assert (seen == 1).all()
+
+
+def test_lateral_inflow_is_the_channels_hru_side(drb):
+    """lateral_inflow on the oracle's three fluxes = the oracle's seg_lateral_inflow, bit for bit."""
+    import prms_oracle as po
+    from pywatershed_b200 import sharding
+
+    p, f, start = drb
+    nd = 20
+    o = po.Oracle(p, start=start)
+    res, _ = o.run(f["prcp"][:nd], f["tmax"][:nd], f["tmin"][:nd], sharding.LATERAL_TERMS, ["seg_lateral_inflow"])
+    o.close()
+    plan = sharding.lateral_plan(p["hru_segment"], np.arange(p["hru_area"].shape[0]))
+    lat = sharding.lateral_inflow(*(res[k] for k in sharding.LATERAL_TERMS), plan, p["tosegment"].shape[0])
+    np.testing.assert_array_equal(lat, res["seg_lateral_inflow"])
+
+
+def _worker_split(rank, world, port, nd, ret):
+    import sys
+    import pathlib as pl
+
+    root = pl.Path(__file__).resolve().parent.parent
+    for q in (root, root / "tests", root / "oracle"):
+        if str(q) not in sys.path:
+            sys.path.insert(0, str(q))
+    import torch
+    import torch.distributed as dist
+
+    import bench
+    import prms_oracle as po
+    import scenarios as sc
+    from pywatershed_b200 import sharding
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        p, f, start = sc.load_drb()
+        ntile = 3
+        pt, ft = sc.tile(p, {k: v[:nd] for k, v in f.items()}, ntile)
+        pt, _ = bench.chain_tiles(p, pt, ntile)           # ONE tree: basin sharding cannot split it
+        nhru, nseg = pt["hru_area"].shape[0], pt["tosegment"].shape[0]
+        hru_rank = sharding.partition_hrus(pt["hru_segment"], world)
+        q, hi = sharding.shard_hru_parameters(pt, hru_rank, rank)
+        o = po.Oracle(q, start=start)                      # the oracle stands in for the GPU
+        names_h = ["pkwater_equiv", "soil_moist"] + list(sharding.LATERAL_TERMS)
+        res, _ = o.run(ft["prcp"][:, hi], ft["tmax"][:, hi], ft["tmin"][:, hi], names_h, ())
+        o.close()
+        plan = sharding.lateral_plan(pt["hru_segment"], hi)
+        lat = sharding.lateral_inflow(*(res[k] for k in sharding.LATERAL_TERMS), plan, nseg)
+        lat_t = torch.from_numpy(lat)
+        sharding.exchange_lateral(lat_t, 0)               # the one exchange step
+        full = {k: sharding.gather_outputs(res[k], hi, nhru) for k in names_h}
+        if rank == 0:
+            routed = po.Oracle(pt, start=start).run_channel(lat_t.numpy())
+            ref_o = po.Oracle(pt, start=start)
+            ref, _ = ref_o.run(ft["prcp"], ft["tmax"], ft["tmin"], names_h, po.SEG_VARS)
+            ok = all(np.array_equal(full[k], ref[k]) for k in names_h)
+            ok = ok and all(np.array_equal(routed[k], ref[k]) for k in po.SEG_VARS)
+            ret["ok"] = bool(ok)
+            ret["nlocal"] = int(hi.size)
+            ret["flow"] = float(ref["seg_outflow"][-1].sum())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_gloo_split_columns_one_router_equals_unsharded():
+    """A network that is ONE tree (chained tiles): HRU columns split over two ranks,
+    lateral inflow reduced to rank 0 (gloo), which routes the whole network -- all
+    five segment variables equal the unsharded run bit for bit."""
+    import torch.multiprocessing as mp
+
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_split, args=(2, port, 25, ret), nprocs=2, join=True)
+    assert ret.get("ok") is True
+    assert 0 < ret["nlocal"] < 3 * 765 and ret["flow"] > 0.0
