@@ -713,6 +713,80 @@ def pcie_ceiling(D: Dist, nbytes=1 << 30, reps=3):
     return res
 
 
+def run_split_columns(args):
+    """--workload conus_split | conus_split_chained: BASELINE.json configs[2] with its
+    segment graph kept on ONE rank (as a real basin with one dominant outlet tree
+    would need; `_chained`: the 144 tiles really are one tree, outlet -> headwater):
+    HRU columns split over the ranks (sharding.partition_hrus), ONE exchange step per
+    block of days -- an NCCL reduce of seg_lateral_inflow [T, nsegment] to the router --
+    and PRMSChannel alone on the router (sharding.SplitColumnsOneRouter).  Strong
+    scaling; `value` = HRU-days of the whole domain / max-over-ranks time."""
+    import torch
+    import __graft_entry__ as g
+
+    D = Dist()
+    if D.rank == 0:
+        g.build()
+    D.barrier()
+    from pywatershed_b200 import sharding
+
+    spec = workload_spec("conus")
+    p0, f0, pt, start = build_domain(spec)
+    chained = args.workload.endswith("_chained")
+    if chained:
+        pt, _ = chain_tiles(p0, pt, spec["ntile"])
+    nhru, nseg, nd = pt["hru_area"].shape[0], pt["tosegment"].shape[0], spec["ndays"]
+    T = max(1, min(args.block_days, nd))
+    # the router also routes (about a fifth of the one-GPU step): its share of the HRUs
+    share = args.router_share if args.router_share is not None else max(0.0, 1.0 - 0.2 * D.world)
+    run = sharding.SplitColumnsOneRouter(pt, start, D.rank, D.world, D.local_rank, block_days=T,
+                                         router_share=share, lanes=args.lanes,
+                                         channel_chunk=args.channel_chunk)
+    forc = device_forcings(f0, spec, 0, D.dev, hru_idx=run.hru_idx)
+    seg = torch.zeros((nd, len(run.seg_vars), nseg), dtype=torch.float64, device=D.dev) \
+        if run.route is not None else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def one_pass():
+        run.reset()
+        D.barrier()
+        e0.record()
+        run.run_device(forc["prcp"], forc["tmax"], forc["tmin"], seg_out=seg)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    for _ in range(args.warmup):
+        one_pass()
+    sampler = ClockSampler(D.local_rank)
+    if D.rank == 0:
+        sampler.start()
+    ms = D.max(sum(one_pass() for _ in range(args.steps)))
+    clocks = sampler.stop() if D.rank == 0 else None
+    chk = float(seg[-1, run.seg_vars.index("seg_outflow")].sum()) if seg is not None else 0.0
+    launches = run.cols.launch_count() + (run.route.launch_count() if run.route is not None else 0)
+    nloc = run.cols.nhru
+    if D.rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": nhru * nd * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": D.world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": spec["label"] + (", tiles chained into ONE outlet tree" if chained else "")
+                       + "; segment graph on rank 0, HRU columns split over the ranks",
+                       "parallelism": f"hru-split x{D.world} + 1 router, one NCCL reduce of "
+                                      f"seg_lateral_inflow [{T}, {nseg}] f64 per block",
+                       "block_days": T, "router_share": share, "nhru_rank0": nloc, "job_hrus": nhru, "job_segments": nseg,
+                       "outputs": "5 segment variables every day on the router (HRU variables: the three "
+                                  "volume fluxes of the exchange, on each rank's device)",
+                       "l2": "forcings and results exceed L2"},
+            "exchange_bytes_per_block": T * nseg * 8,
+            "checksum_seg_outflow_last_day": chk, "gpu_launches": launches, "clocks": clocks}))
+    run.close()
+    D.close()
+
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -747,6 +821,9 @@ def main():
                     help="HRUs per column CTA (library option column_hrus; default: by domain size)")
     ap.add_argument("--lib-opt", action="append", default=[], metavar="NAME=VALUE",
                     help="pws_set_option(NAME, VALUE) on every engine (tuning aid), e.g. wide_column=0")
+    ap.add_argument("--router-share", type=float, default=None,
+                    help="--workload conus_split: the router rank's share of the HRUs relative to "
+                         "another rank's (default max(0, 1 - 0.2 N))")
     ap.add_argument("--shard-of", type=int, default=None,
                     help="tuning aid on ONE GPU: run rank 0's share of an N-way split; `value` is then "
                          "what N GPUs would give if every rank took as long as this one")
@@ -756,6 +833,8 @@ def main():
     args = ap.parse_args()
     if args.workload in ("channel", "channel_chained"):
         return run_channel_only(args)
+    if args.workload in ("conus_split", "conus_split_chained"):
+        return run_split_columns(args)
     spec = workload_spec(args.workload)
     if args.impl == "reference":
         return run_reference(args, spec)

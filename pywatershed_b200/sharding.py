@@ -154,19 +154,24 @@ _SEG_NAMES = ("mann_n", "seg_depth", "seg_length", "seg_slope", "x_coef", "segme
               "seg_cum_area", "seg_elev", "obsin_segment", "obsout_segment", "seg_humidity")
 
 
-def partition_hrus(hru_segment, nranks: int) -> np.ndarray:
+def partition_hrus(hru_segment, nranks: int, weights=None) -> np.ndarray:
     """hru_rank [nhru] for a domain whose segment graph stays on one rank: all HRUs
     of a segment go to the same rank (so each segment's lateral inflow is summed by
     ONE rank, in the reference's order: ascending HRU index, prms_channel.py:396-421),
-    segments are dealt in runs of consecutive numbers holding about nhru / nranks HRUs;
-    HRUs without a segment are dealt round-robin."""
+    segments are dealt in runs of consecutive numbers holding about nhru / nranks HRUs
+    (`weights` [nranks]: relative shares instead, e.g. a smaller one for the rank that
+    also routes); HRUs without a segment are dealt round-robin."""
     hs = np.asarray(hru_segment, dtype=np.int64)
     att = hs > 0
     nseg = int(hs.max(initial=0))
     cnt = np.bincount(hs[att] - 1, minlength=nseg)
     before = np.cumsum(cnt) - cnt
     total = max(int(cnt.sum()), 1)
-    seg_rank = np.minimum((before * nranks) // total, nranks - 1)
+    w = np.ones(nranks) if weights is None else np.asarray(weights, dtype=np.float64)
+    if w.shape != (nranks,) or (w < 0).any() or w.sum() <= 0:
+        raise ValueError("partition_hrus: weights must be [nranks], non-negative, not all zero")
+    edges = np.cumsum(w) / w.sum() * total            # rank r takes HRU counts [edges[r-1], edges[r])
+    seg_rank = np.minimum(np.searchsorted(edges, before, side="right"), nranks - 1)
     hru_rank = np.empty(hs.shape[0], dtype=np.int64)
     hru_rank[att] = seg_rank[hs[att] - 1]
     loose = np.where(~att)[0]
@@ -253,7 +258,10 @@ class SplitColumnsOneRouter:
     overlap on the device."""
 
     def __init__(self, params: dict, start, rank: int, world: int, device: int, router: int = 0,
-                 hru_vars=(), seg_vars=None, block_days: int = 256, group=None, **engine_kw):
+                 hru_vars=(), seg_vars=None, block_days: int = 256, group=None,
+                 router_share: float = 1.0, **engine_kw):
+        """`router_share`: the router's share of the HRUs relative to another rank's (it
+        also routes: a smaller share evens the ranks out; at least a few HRUs stay)."""
         import torch
 
         from .engine import Engine
@@ -262,7 +270,9 @@ class SplitColumnsOneRouter:
         self.dev = torch.device("cuda", device)
         self.T = int(block_days)
         self.nseg = int(np.asarray(params["tosegment"]).shape[0])
-        hru_rank = partition_hrus(params["hru_segment"], world)
+        w = np.ones(world)
+        w[router] = max(float(router_share), 0.02) if world > 1 else 1.0
+        hru_rank = partition_hrus(params["hru_segment"], world, w)
         q, self.hru_idx = shard_hru_parameters(params, hru_rank, rank)
         self.cols = Engine(q, start, device=device, channel=False, **engine_kw)
         self.hru_vars = list(hru_vars)

@@ -127,6 +127,12 @@ def test_partition_hrus_keeps_a_segments_hrus_together(drb):
                 assert np.unique(sg).size == sg.size          # a pass touches a segment once
             assert np.array_equal(np.unique(touched), np.unique(hs[hi][hs[hi] > 0] - 1))
         assert (seen == 1).all()
+    # a lighter share for the rank that also routes
+    hru_rank = sharding.partition_hrus(hs, 4, weights=[0.25, 1, 1, 1])
+    load = np.bincount(hru_rank, minlength=4)
+    assert load.sum() == hs.size and abs(load[0] - hs.size / 13) <= 8 and load[1:].min() > 3 * load[0]
+    for sgm in np.unique(hs[hs > 0]):
+        assert np.unique(hru_rank[hs == sgm]).size == 1
 
 
 def test_lateral_inflow_is_the_channels_hru_side(drb):
