@@ -291,7 +291,9 @@ class SplitColumnsOneRouter:
         nv = len(self.cols.sel_f64)
         self.out = [torch.empty((self.T, nv, self.cols.nhru), dtype=torch.float64, device=self.dev)
                     for _ in range(2)]
-        self.lat = [torch.empty((self.T, self.nseg), dtype=torch.float64, device=self.dev) for _ in range(2)]
+        self.lat = []    # ring of exchange buffers, grown by run_device (LAT_RING_MAX blocks deep)
+
+    LAT_RING_MAX = 16
 
     def reset(self):
         self.cols.reset()
@@ -312,6 +314,12 @@ class SplitColumnsOneRouter:
 
         nd, nloc = prcp.shape[0], self.cols.nhru
         blocks = [(d, min(self.T, nd - d)) for d in range(0, nd, self.T)]
+        # one exchange buffer per block in flight: the router's launches queue up on its
+        # routing stream while later blocks are reduced, and the host waits for the routing
+        # only when a buffer comes round again
+        R = min(len(blocks), self.LAT_RING_MAX)
+        while len(self.lat) < R:
+            self.lat.append(torch.empty((self.T, self.nseg), dtype=torch.float64, device=self.dev))
 
         def columns(b):
             d, n = blocks[b]
@@ -324,10 +332,10 @@ class SplitColumnsOneRouter:
             self.cols.sync()                          # block b's columns are in self.out[b % 2]
             if b + 1 < len(blocks):
                 columns(b + 1)                        # runs beside the exchange and the routing of b
-            if self.route is not None:
-                self.route.sync()                     # the routing that read self.lat[b % 2] is done
+            if self.route is not None and b >= R:
+                self.route.sync()                     # the routing that read self.lat[b % R] is done
             o = self.out[b % 2][:n]
-            lat = self.lat[b % 2][:n]
+            lat = self.lat[b % R][:n]
             lateral_inflow(o[:, self._term[0]], o[:, self._term[1]], o[:, self._term[2]], self.plan,
                            self.nseg, out=lat)
             if hru_out is not None and self.hru_vars:

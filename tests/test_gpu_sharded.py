@@ -116,13 +116,15 @@ def _split_case(nd, ntile=4):
     return pt, ft, start
 
 
-def _run_split(pt, ft, start, rank, world, device, block_days):
+def _run_split(pt, ft, start, rank, world, device, block_days, ring=None):
     import torch
 
     from pywatershed_b200 import sharding
 
     hv = ["pkwater_equiv", "soil_moist", "sroff_vol"]
     run = sharding.SplitColumnsOneRouter(pt, start, rank, world, device, hru_vars=hv, block_days=block_days)
+    if ring is not None:
+        run.LAT_RING_MAX = ring                           # exchange buffers come round again
     dev = torch.device("cuda", device)
     hi = run.hru_idx
     forc = [torch.from_numpy(np.ascontiguousarray(ft[k][:, hi])).to(dev) for k in ("prcp", "tmax", "tmin")]
@@ -150,13 +152,15 @@ def test_split_columns_one_router_on_one_gpu_equals_the_chain():
     torch (sharding.lateral_inflow), PRMSChannel alone on a second handle, blocks of 7
     days pipelined -- every segment variable equals the fused chain bit for bit."""
     pt, ft, start = _split_case(30)
-    hv, sv, hi, hru, seg = _run_split(pt, ft, start, 0, 1, 0, 7)
-    ref = _reference(pt, ft, start, hv, sv)
-    assert float(seg[-1, sv.index("seg_outflow")].sum()) > 0.0
-    for k, v in enumerate(hv):
-        np.testing.assert_array_equal(hru[:, k], np.asarray(ref[v]), err_msg=v)
-    for k, v in enumerate(sv):
-        np.testing.assert_array_equal(seg[:, k], np.asarray(ref[v]), err_msg=v)
+    ref = None
+    for ring in (None, 2):
+        hv, sv, hi, hru, seg = _run_split(pt, ft, start, 0, 1, 0, 7, ring)
+        ref = ref or _reference(pt, ft, start, hv, sv)
+        assert float(seg[-1, sv.index("seg_outflow")].sum()) > 0.0
+        for k, v in enumerate(hv):
+            np.testing.assert_array_equal(hru[:, k], np.asarray(ref[v]), err_msg=v)
+        for k, v in enumerate(sv):
+            np.testing.assert_array_equal(seg[:, k], np.asarray(ref[v]), err_msg=v)
 
 
 def _worker_split(rank, world, port, nd, ret):
