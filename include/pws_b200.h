@@ -78,7 +78,8 @@ int pws_set_param_i32(pws_handle *h, const char *name, const int32_t *h_v, int64
  * default and maximum 512; outlet trees larger than a chunk are cut and linked
  * through HBM),
  * "route_hours" (hours a segment advances per step of k_route_chunks: 0,
- * default = 12 for segment graphs of at most 160 levels, else 4),
+ * default = 12 for segment graphs of at most 160 levels, 2 for more than 2,000
+ * levels, else 4),
  * "route_overlap" (1: the routing launch of block b+1 may start while that of
  * block b still runs, on a second stream, each chunk of connected segments
  * continuing from the state the same chunk of the previous launch stored -- a deep

@@ -487,9 +487,10 @@ extern "C" int pws_set_option(pws_handle* h, const char* name, double value) {
   }
   else if (!strcmp(name, "route_overlap")) { h->route_overlap_opt = value < 0 ? -1 : (value != 0.0); return 0; }
   else if (!strcmp(name, "route_hours")) {
-    if (value != 0 && value != PWS_ROUTE_HOURS && value != PWS_ROUTE_HOURS_SHALLOW)
-      PWS_FAIL(h, "pws_set_option: route_hours must be 0 (automatic), %d or %d", PWS_ROUTE_HOURS,
-               PWS_ROUTE_HOURS_SHALLOW);
+    if (value != 0 && value != PWS_ROUTE_HOURS && value != PWS_ROUTE_HOURS_SHALLOW &&
+        value != PWS_ROUTE_HOURS_DEEP)
+      PWS_FAIL(h, "pws_set_option: route_hours must be 0 (automatic), %d, %d or %d", PWS_ROUTE_HOURS_DEEP,
+               PWS_ROUTE_HOURS, PWS_ROUTE_HOURS_SHALLOW);
     h->route_hours_opt = (int)value;
   }
   else if (!strcmp(name, "channel_chunk")) {
@@ -507,7 +508,8 @@ extern "C" int pws_set_option(pws_handle* h, const char* name, double value) {
 // step per level; see PWS_ROUTE_HOURS in pws_kernels.cuh).
 static int route_hours(const pws_handle* h) {
   if (h->route_hours_opt) return h->route_hours_opt;
-  return h->nlevels <= 160 ? PWS_ROUTE_HOURS_SHALLOW : PWS_ROUTE_HOURS;
+  if (h->nlevels <= 160) return PWS_ROUTE_HOURS_SHALLOW;
+  return h->nlevels > PWS_ROUTE_DEEP_LEVELS ? PWS_ROUTE_HOURS_DEEP : PWS_ROUTE_HOURS;
 }
 
 // May the routing launch of block b+1 start while that of block b still runs?
@@ -1183,6 +1185,24 @@ static void mark_base(pws_handle* h, cudaStream_t st) {
   if (h->ev_pairs_col.empty() && h->ev_pairs_ch.empty()) cudaEventRecord(h->ev_base, st);
 }
 
+// k_route_chunks<G> and its FlowGraph variant: shared-memory attribute, launch
+template <int G>
+static cudaError_t route_attrs() {
+  cudaError_t e = cudaFuncSetAttribute(k_route_chunks<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)route_smem_bytes(G));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_route_chunks<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)route_smem_bytes(G));
+  return e;
+}
+template <int G>
+static void route_launch(bool graph, int nchunks, cudaStream_t st, const ChannelArgs& a) {
+  if (graph)
+    k_route_chunks<G, true><<<(unsigned)nchunks, PWS_CHUNK_THREADS, route_smem_bytes(G), st>>>(a);
+  else
+    k_route_chunks<G><<<(unsigned)nchunks, PWS_CHUNK_THREADS, route_smem_bytes(G), st>>>(a);
+}
+
 // enqueue the channel kernels for one block on stream `st`; `viol` = the
 // block's verdict rows (or null: no channel budget)
 static int enqueue_channel(pws_handle* h, cudaStream_t st, int ndays, const double* d_hru_lat,
@@ -1236,35 +1256,19 @@ static int enqueue_channel(pws_handle* h, cudaStream_t st, int ndays, const doub
   // progress counters (cross-chunk edges) and the chunk ticket start at 0
   PWS_CUDA(h, cudaMemsetAsync(h->d_progress[q], 0, (size_t)(h->sstride + 32) * sizeof(int), st));
   if (!h->route_attr_set) {
-    PWS_CUDA(h, cudaFuncSetAttribute(k_route_chunks<PWS_ROUTE_HOURS>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)route_smem_bytes(PWS_ROUTE_HOURS)));
-    PWS_CUDA(h, cudaFuncSetAttribute(k_route_chunks<PWS_ROUTE_HOURS_SHALLOW>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)route_smem_bytes(PWS_ROUTE_HOURS_SHALLOW)));
-    PWS_CUDA(h, (cudaFuncSetAttribute(k_route_chunks<PWS_ROUTE_HOURS, true>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)route_smem_bytes(PWS_ROUTE_HOURS))));
-    PWS_CUDA(h, (cudaFuncSetAttribute(k_route_chunks<PWS_ROUTE_HOURS_SHALLOW, true>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)route_smem_bytes(PWS_ROUTE_HOURS_SHALLOW))));
+    if (route_attrs<PWS_ROUTE_HOURS>() != cudaSuccess || route_attrs<PWS_ROUTE_HOURS_SHALLOW>() != cudaSuccess ||
+        route_attrs<PWS_ROUTE_HOURS_DEEP>() != cudaSuccess)
+      PWS_CUDA(h, cudaGetLastError());
     h->route_attr_set = true;
   }
   cudaEvent_t e0 = new_event(h), e1 = new_event(h);
   mark_base(h, st);
   cudaEventRecord(e0, st);
-  if (graph && route_hours(h) == PWS_ROUTE_HOURS_SHALLOW)
-    k_route_chunks<PWS_ROUTE_HOURS_SHALLOW, true><<<(unsigned)h->nchunks, PWS_CHUNK_THREADS,
-                                                    route_smem_bytes(PWS_ROUTE_HOURS_SHALLOW), st>>>(a);
-  else if (graph)
-    k_route_chunks<PWS_ROUTE_HOURS, true><<<(unsigned)h->nchunks, PWS_CHUNK_THREADS,
-                                            route_smem_bytes(PWS_ROUTE_HOURS), st>>>(a);
-  else if (route_hours(h) == PWS_ROUTE_HOURS_SHALLOW)
-    k_route_chunks<PWS_ROUTE_HOURS_SHALLOW><<<(unsigned)h->nchunks, PWS_CHUNK_THREADS,
-                                              route_smem_bytes(PWS_ROUTE_HOURS_SHALLOW), st>>>(a);
-  else
-    k_route_chunks<PWS_ROUTE_HOURS><<<(unsigned)h->nchunks, PWS_CHUNK_THREADS,
-                                      route_smem_bytes(PWS_ROUTE_HOURS), st>>>(a);
+  switch (route_hours(h)) {
+    case PWS_ROUTE_HOURS_SHALLOW: route_launch<PWS_ROUTE_HOURS_SHALLOW>(graph, h->nchunks, st, a); break;
+    case PWS_ROUTE_HOURS_DEEP: route_launch<PWS_ROUTE_HOURS_DEEP>(graph, h->nchunks, st, a); break;
+    default: route_launch<PWS_ROUTE_HOURS>(graph, h->nchunks, st, a); break;
+  }
   h->launches++;
   h->last_channel_launches += 1;
   if (viol) {

@@ -990,13 +990,25 @@ enum {
 // but the pipeline fill is dmax steps of G hours each.  Per launch of T days a
 // chunk takes about (24 T / G + dmax) (0.39 + 0.2 G) us (fit to G = 4 .. 12 on the
 // CONUS domain, where G = 12 routes a 10-year pass in 24.2 ms against 28.4 for
-// G = 4), so shallow networks get G = 12 and deep ones G = 4 (pws_init picks by
-// the number of levels of the segment graph; option "route_hours").
+// G = 4), so shallow networks get G = 12, deep ones G = 4 and very deep ones G = 2 (pws_init
+// picks by the number of levels of the segment graph; option "route_hours").
 #ifndef PWS_ROUTE_HOURS
 #define PWS_ROUTE_HOURS 4    // deep networks
 #endif
 #ifndef PWS_ROUTE_HOURS_SHALLOW
 #define PWS_ROUTE_HOURS_SHALLOW 12
+#endif
+// Very deep graphs (thousands of levels) in launches of a few hundred days are all
+// fill: G = 2 routes the chained configs[4] network (8,856 levels) at 2.06e9
+// segment-days/s in 256-day launches against 1.55e9 for G = 4 and 1.80e9 for G = 3,
+// and at 3.78e9 against 4.06e9 when the ten years are one launch
+// (profiles/r02_route_hours_experiment.log); by the fit above G = 2 wins while
+// levels > ~6 x days per launch.
+#ifndef PWS_ROUTE_HOURS_DEEP
+#define PWS_ROUTE_HOURS_DEEP 2
+#endif
+#ifndef PWS_ROUTE_DEEP_LEVELS
+#define PWS_ROUTE_DEEP_LEVELS 2000
 #endif
 // lateral-inflow ring: kLatDepth days x 3 addends per segment, filled by cp.async
 constexpr int kLatDepth = 3;

@@ -712,11 +712,11 @@ def test_output_writes_stay_inside_their_buffers(drb, ntile, nhru_keep, nd, outp
     np.testing.assert_array_equal(viol, rviol)
 
 
-@pytest.mark.parametrize("hours", [4, 12])
+@pytest.mark.parametrize("hours", [2, 4, 12])
 def test_route_hours_are_equivalent(drb, hours):
     """k_route_chunks advances 12 hours per systolic step on shallow segment
-    graphs and 4 on deep ones (option route_hours); the schedule must not
-    change a bit of the routing."""
+    graphs, 4 on deep ones and 2 on very deep ones (option route_hours); the
+    schedule must not change a bit of the routing."""
     import torch
 
     p, f, start = drb
