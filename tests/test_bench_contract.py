@@ -70,3 +70,23 @@ def test_ensemble_parameters_follow_the_recipe(drb):
         np.testing.assert_array_equal(v[..., 765:], np.asarray(again[k]))  # a member does not depend on its rank
     np.testing.assert_array_equal(pt["hru_area"][:765], pt["hru_area"][765:])
     assert pt["tosegment"][456:].max() <= 2 * 456 and pt["hru_segment"][765:].max() > 456
+
+
+def test_every_bench_leg_selects_the_outputs_it_reports():
+    """A handle's default output selection is EMPTY (nothing is written): a bench leg
+    that builds an Engine must select outputs before it times anything, and its line
+    must carry a checksum of what was written.  (The channel-only workload once ran
+    without a selection; its figures were no-output figures.)"""
+    import inspect
+
+    import bench
+
+    for fn in (bench.run_channel_only, bench.run_split_columns):
+        src = inspect.getsource(fn)
+        assert "checksum_seg_outflow_last_day" in src, fn.__name__
+    src = inspect.getsource(bench.run_channel_only)
+    assert src.index("select_outputs") < src.index("def one_pass")
+    main = inspect.getsource(bench.main)
+    assert main.count("Engine(") == main.count("def engine_for")  # engines come from one factory ...
+    leg = main[main.index("def device_leg"):main.index("main_leg =")]
+    assert "eng.select_outputs(hru_vars, seg_vars)" in leg and "seg_last" in leg  # ... and select + checksum
