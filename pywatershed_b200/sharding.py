@@ -259,15 +259,20 @@ class SplitColumnsOneRouter:
 
     def __init__(self, params: dict, start, rank: int, world: int, device: int, router: int = 0,
                  hru_vars=(), seg_vars=None, block_days: int = 256, group=None,
-                 router_share: float = 1.0, **engine_kw):
+                 router_share: float = 1.0, engine_cls=None, **engine_kw):
         """`router_share`: the router's share of the HRUs relative to another rank's (it
-        also routes: a smaller share evens the ranks out; at least a few HRUs stay)."""
+        also routes: a smaller share evens the ranks out; at least a few HRUs stay).
+        `engine_cls` (tests only): a stand-in for Engine with `device=None`, buffers on
+        the CPU -- tests/test_sharding.py drives this class under gloo with the oracle."""
         import torch
 
-        from .engine import Engine
+        if engine_cls is None:
+            from .engine import Engine
+        else:
+            Engine = engine_cls
 
         self.rank, self.world, self.router, self.group = rank, world, router, group
-        self.dev = torch.device("cuda", device)
+        self.dev = torch.device("cuda", device) if device is not None else torch.device("cpu")
         self.T = int(block_days)
         self.nseg = int(np.asarray(params["tosegment"]).shape[0])
         w = np.ones(world)
@@ -342,7 +347,8 @@ class SplitColumnsOneRouter:
                 hru_out[d:d + n] = o[:, :len(self.hru_vars)]
             if self.world > 1:
                 exchange_lateral(lat, self.router, self.group)
-            torch.cuda.current_stream().synchronize()
+            if self.dev.type == "cuda":
+                torch.cuda.current_stream().synchronize()
             if self.route is not None:
                 self.route.run_channel_device(n, lat.data_ptr(),
                                               seg_out[d:d + n].data_ptr() if seg_out is not None else 0,

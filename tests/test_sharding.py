@@ -212,3 +212,127 @@ def test_two_rank_gloo_split_columns_one_router_equals_unsharded():
     mp.spawn(_worker_split, args=(2, port, 25, ret), nprocs=2, join=True)
     assert ret.get("ok") is True
     assert 0 < ret["nlocal"] < 3 * 765 and ret["flow"] > 0.0
+
+
+# ---------------------------------------------------------------- the driver class itself, under gloo
+class _OracleEngine:
+    """The slice of Engine that sharding.SplitColumnsOneRouter uses, on the CPU oracle and
+    CPU buffers (raw pointers, as the library takes them): a stand-in for tests only."""
+
+    def __init__(self, params, start, device=None, channel=True, **kw):
+        import types
+
+        import prms_oracle as po
+
+        self._po, self._params, self._start = po, params, start
+        self.o = po.Oracle(params, start=start)
+        self.nhru, self.nseg = self.o.nhru, (self.o.nseg if channel else 0)
+        self.reg = types.SimpleNamespace(seg_vars=list(po.SEG_VARS))
+        self.sel_f64, self.sel_i32, self.sel_seg = [], [], []
+        self.day, self._launches = 0, 0
+
+    @staticmethod
+    def _arr(ptr, shape):
+        import ctypes as C
+
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=shape)
+
+    def select_outputs(self, hru_vars=(), seg_vars=()):
+        self.sel_f64, self.sel_seg = list(hru_vars), list(seg_vars)
+
+    def run_device(self, n, d_prcp, d_tmax, d_tmin, d_out_f64=0, d_out_i32=0, d_seg_out=0, viol=None,
+                   sync=True):
+        f = [self._arr(q, (n, self.nhru)) for q in (d_prcp, d_tmax, d_tmin)]
+        res, _ = self.o.run(*f, self.sel_f64, (), budgets=False)
+        out = self._arr(d_out_f64, (n, len(self.sel_f64), self.nhru))
+        for k, v in enumerate(self.sel_f64):
+            out[:, k] = res[v]
+        self.day += n
+        self._launches += 1
+
+    def run_channel_device(self, n, d_lat, d_out, sync=True):
+        res = self.o.run_channel(self._arr(d_lat, (n, self.nseg)), self.sel_seg)
+        if d_out:
+            out = self._arr(d_out, (n, len(self.sel_seg), self.nseg))
+            for k, v in enumerate(self.sel_seg):
+                out[:, k] = res[v]
+        self._launches += 1
+
+    def sync(self):
+        pass
+
+    def reset(self):
+        self.o.close()
+        self.o = self._po.Oracle(self._params, start=self._start)
+        self.day = 0
+
+    def close(self):
+        self.o.close()
+
+    def launch_count(self):
+        return self._launches
+
+
+def _worker_driver(rank, world, port, nd, ret):
+    import sys
+    import pathlib as pl
+
+    root = pl.Path(__file__).resolve().parent.parent
+    for q in (root, root / "tests", root / "oracle"):
+        if str(q) not in sys.path:
+            sys.path.insert(0, str(q))
+    import torch
+    import torch.distributed as dist
+
+    import bench
+    import prms_oracle as po
+    import scenarios as sc
+    from pywatershed_b200 import sharding
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        p, f, start = sc.load_drb()
+        ntile = 3
+        pt, ft = sc.tile(p, {k: v[:nd] for k, v in f.items()}, ntile)
+        pt, _ = bench.chain_tiles(p, pt, ntile)
+        nhru, nseg = pt["hru_area"].shape[0], pt["tosegment"].shape[0]
+        hv = ["pkwater_equiv", "sroff_vol"]
+        run = sharding.SplitColumnsOneRouter(pt, start, rank, world, None, hru_vars=hv, block_days=4,
+                                             router_share=0.5, engine_cls=_OracleEngine)
+        run.LAT_RING_MAX = 3                               # 7 blocks: the exchange buffers come round twice
+        hi = run.hru_idx
+        forc = [torch.from_numpy(np.ascontiguousarray(ft[k][:, hi])) for k in ("prcp", "tmax", "tmin")]
+        seg = torch.zeros((nd, 5, nseg), dtype=torch.float64) if run.route is not None else None
+        hru = torch.zeros((nd, len(hv), hi.size), dtype=torch.float64)
+        for _ in range(2):                                 # a second pass after reset() gives the same
+            run.reset()
+            run.run_device(*forc, seg_out=seg, hru_out=hru)
+        full = {v: sharding.gather_outputs(hru[:, k].numpy(), hi, nhru) for k, v in enumerate(hv)}
+        sizes = sharding.gather_outputs(np.full((1, hi.size), float(rank)), hi, nhru)
+        if rank == 0:
+            ref, _ = po.Oracle(pt, start=start).run(ft["prcp"], ft["tmax"], ft["tmin"], hv, po.SEG_VARS)
+            ok = all(np.array_equal(full[v], ref[v]) for v in hv)
+            ok = ok and all(np.array_equal(seg[:, k].numpy(), ref[v]) for k, v in enumerate(run.seg_vars))
+            ret["ok"] = bool(ok)
+            ret["share0"] = float((sizes == 0).mean())
+            ret["flow"] = float(ref["seg_outflow"][-1].sum())
+        run.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_split_columns_one_router_driver_under_gloo():
+    """sharding.SplitColumnsOneRouter itself (blocks, double-buffered results, the ring of
+    exchange buffers, the router's lighter share) on two gloo ranks with the oracle standing
+    in for the Engine: HRU and segment results equal the unsharded oracle run bit for bit."""
+    import torch.multiprocessing as mp
+
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_driver, args=(2, port, 26, ret), nprocs=2, join=True)
+    assert ret.get("ok") is True and ret["flow"] > 0.0
+    assert 0.25 < ret["share0"] < 0.42                    # a third of the HRUs for the router
